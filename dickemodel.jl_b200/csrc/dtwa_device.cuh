@@ -1,0 +1,523 @@
+// dtwa_device.cuh -- device-side building blocks of libdicketwa (sm_100a, FP64, one trajectory per thread).
+//
+// Everything a trajectory needs lives in registers: state, RK stages, step controller, Philox
+// counters.  Floating-point sequences are written with explicit fma()/__dmul_rn()/__dadd_rn() so
+// that every kernel instantiating a stepper executes the same instruction sequence and therefore
+// produces bit-identical trajectories (dtwa_integrate vs dtwa_ensemble).
+//
+// Reference behaviour restated (paths relative to the reference checkout):
+//   equations of motion   src/ClassicalDicke.jl:11-17, src/ClassicalLMG.jl:8-11
+//   domain                src/ClassicalDicke.jl:18-20, src/ClassicalLMG.jl:12-14
+//   Hamiltonians          src/ClassicalDicke.jl:80-88, src/ClassicalLMG.jl:63-70
+//   samplers / pdfs       src/TWA.jl:689-764, src/PhaseSpaces.jl:16,34,49,63
+//   scale_to_index        src/TWA.jl:53-64
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/dicketwa.h"
+
+namespace dtwa {
+
+// ------------------------------------------------------------------------------------------------
+// parameters (sign of `integate_backwards` folded in: every term of both vector fields is linear in
+// exactly one parameter, so sigma*f(u; p) == f(u; sigma*p))
+struct SysPar {
+    double a, b, c, d;  // Dicke: w0, w, g, -      LMG: Omega, xi, xi/2, 2*xi+Omega
+};
+
+// 1/sqrt(x) for x > 0: MUFU.RSQ64H seed (rel. err ~2^-22) + one third-order polish.  No special
+// cases: x <= 0 or non-finite yields NaN/Inf, which the domain checks catch.
+__device__ __forceinline__ double rsqrt_fast(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    double t = __dmul_rn(x, y0);
+    double e = fma(-t, y0, 1.0);           // 1 - x*y0^2
+    double p = fma(0.375, e, 0.5);         // 1/2 + 3/8 e
+    double ye = __dmul_rn(y0, e);
+    return fma(ye, p, y0);                 // y0 (1 + e/2 + 3/8 e^2)
+}
+
+template <int SYS>
+struct Sys;
+
+template <>
+struct Sys<DTWA_SYS_DICKE> {
+    static constexpr int NV = 4;
+    static constexpr int QI = 0, PI = 2;
+    // 19 FP64-pipe instructions + 1 MUFU
+    __device__ __forceinline__ static void rhs(const SysPar &p, const double (&u)[4], double (&du)[4])
+    {
+        const double Q = u[0], q = u[1], P = u[2], pp = u[3];
+        double r2 = fma(-P, P, 4.0);
+        r2 = fma(-Q, Q, r2);               // 4 - P^2 - Q^2
+        const double is = rsqrt_fast(r2);  // 1/s
+        const double s = __dmul_rn(r2, is);
+        const double gq = __dmul_rn(p.c, q);
+        const double gqQ = __dmul_rn(gq, Q);
+        const double e = fma(gqQ, is, -p.a);      // g q Q / s - w0
+        du[0] = __dmul_rn(-P, e);                 // P w0 - g P q Q / s
+        du[1] = __dmul_rn(pp, p.b);               // p w
+        const double gqs = __dmul_rn(gq, s);
+        du[2] = fma(Q, e, -gqs);                  // g q Q^2/s - g q s - Q w0
+        const double Qs = __dmul_rn(Q, s);
+        const double qw = __dmul_rn(q, p.b);
+        du[3] = fma(-p.c, Qs, -qw);               // -g Q s - q w
+    }
+    __device__ __forceinline__ static double hamiltonian(const double *par, const double *u)
+    {
+        // reference operation order, no contraction
+        const double w0 = par[0], w = par[1], g = par[2];
+        const double Q = u[0], q = u[1], P = u[2], p = u[3];
+        const double QQ = __dmul_rn(Q, Q), PP = __dmul_rn(P, P);
+        const double R = __dadd_rn(QQ, PP);
+        const double r = __dsub_rn(1.0, __ddiv_rn(R, 4.0));
+        double h = __dmul_rn(__ddiv_rn(w0, 2.0), R);
+        h = __dadd_rn(h, __dmul_rn(__ddiv_rn(w, 2.0), __dadd_rn(__dmul_rn(q, q), __dmul_rn(p, p))));
+        h = __dadd_rn(h, __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, g), q), Q), __dsqrt_rn(r)));
+        return __dsub_rn(h, w0);
+    }
+};
+
+template <>
+struct Sys<DTWA_SYS_LMG> {
+    static constexpr int NV = 2;
+    static constexpr int QI = 0, PI = 1;
+    // 7 FP64-pipe instructions
+    __device__ __forceinline__ static void rhs(const SysPar &p, const double (&u)[2], double (&du)[2])
+    {
+        const double Q = u[0], P = u[1];
+        const double Q2 = __dmul_rn(Q, Q);
+        const double P2 = __dmul_rn(P, P);
+        du[0] = __dmul_rn(P, fma(-p.c, Q2, p.a));        // P (Om - xi Q^2/2)
+        const double in = fma(p.c, P2, -p.d);            // xi P^2/2 - (2 xi + Om)
+        du[1] = __dmul_rn(Q, fma(p.b, Q2, in));          // Q(...) + xi Q^3
+    }
+    __device__ __forceinline__ static double hamiltonian(const double *par, const double *u)
+    {
+        const double Om = par[0], xi = par[1];
+        const double Q = u[0], P = u[1];
+        const double QQ = __dmul_rn(Q, Q), PP = __dmul_rn(P, P);
+        double a = __ddiv_rn(__dmul_rn(Om, __dadd_rn(QQ, PP)), 2.0);
+        double b = __dsub_rn(QQ, __ddiv_rn(__dmul_rn(PP, QQ), 4.0));
+        b = __dsub_rn(b, __ddiv_rn(__dmul_rn(QQ, QQ), 4.0));   // Q^4 as (Q*Q)*(Q*Q)
+        return __dsub_rn(__dadd_rn(a, __dmul_rn(xi, b)), Om);
+    }
+};
+
+template <int SYS>
+__device__ __forceinline__ bool state_bad(const double (&u)[Sys<SYS>::NV])
+{
+    // non-finite anywhere, or outside the chart 4 - P^2 - Q^2 > 0
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < Sys<SYS>::NV; ++i) acc += __dmul_rn(u[i], 0.0);  // NaN/Inf -> NaN
+    const double Q = u[Sys<SYS>::QI], P = u[Sys<SYS>::PI];
+    const double r2 = __dsub_rn(__dsub_rn(4.0, __dmul_rn(P, P)), __dmul_rn(Q, Q));
+    return !(acc == 0.0) || !(r2 > 0.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fixed-step steppers
+struct StepTab {  // one row per output interval (built on the host, dtwa_api.cu build_step_table)
+    double h, hh, h3, h6;
+    int32_t n;
+    int32_t pad;
+};
+
+template <int SYS>
+__device__ __forceinline__ void rk4_step(const SysPar &p, double (&u)[Sys<SYS>::NV], double h, double hh, double h3,
+                                         double h6)
+{
+    constexpr int NV = Sys<SYS>::NV;
+    double k[NV], y[NV], acc[NV];
+    Sys<SYS>::rhs(p, u, k);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        y[i] = fma(hh, k[i], u[i]);
+        acc[i] = fma(h6, k[i], u[i]);
+    }
+    Sys<SYS>::rhs(p, y, k);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        y[i] = fma(hh, k[i], u[i]);
+        acc[i] = fma(h3, k[i], acc[i]);
+    }
+    Sys<SYS>::rhs(p, y, k);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        y[i] = fma(h, k[i], u[i]);
+        acc[i] = fma(h3, k[i], acc[i]);
+    }
+    Sys<SYS>::rhs(p, y, k);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) u[i] = fma(h6, k[i], acc[i]);
+}
+
+#define RHS(in, out) Sys<SYS>::rhs(p, in, out)
+
+// one DOP853 step with the 8th-order weights only (fixed step)
+template <int SYS>
+__device__ __forceinline__ void rk8_step(const SysPar &p, double (&y)[Sys<SYS>::NV], double h)
+{
+    constexpr int NV = Sys<SYS>::NV;
+    double k0[NV];
+    RHS(y, k0);
+    // stages 1..11 and the weighted sum, generated straight-line code; the FSAL evaluation and
+    // the error combinations it also emits are dead here and removed by the compiler
+#include "dop853_body.inc"
+    (void)e5;
+    (void)e3;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) y[i] = ynew[i];
+#undef DOP853_KNEW
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedded adaptive pairs.  Controller = SciPy's RungeKutta._step_impl (the oracle restates the same):
+// RMS error norm with scale = tol + max(|y|,|ynew|) tol, factor in [0.2, 10], safety 0.9, plus the
+// reference's solver contract (src/ClassicalSystems.jl:138): dtmin with force_dtmin, out-of-domain
+// trial steps rejected with a shrink of 0.2, maxiters.
+template <int NV>
+__device__ __forceinline__ double rms_norm(const double (&x)[NV])
+{
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s = fma(x[i], x[i], s);
+    return sqrt(s) / sqrt((double)NV);
+}
+
+template <int SYS, int ALG>
+struct Adaptive {
+    static constexpr int NV = Sys<SYS>::NV;
+    static constexpr int ERR_ORDER = (ALG == DTWA_ALG_DP5) ? 4 : 7;
+    double t, habs;
+    double k0[NV];
+    bool rejected;
+
+    __device__ __forceinline__ void init(const SysPar &p, const double (&y)[NV], double tend, double tol)
+    {
+        t = 0.0;
+        rejected = false;
+        RHS(y, k0);
+        // Hairer's starting step (scipy common.select_initial_step, direction +1, max_step inf)
+        double sc[NV], a[NV];
+        if (tend == 0.0) {
+            habs = 0.0;
+            return;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sc[i] = fma(fabs(y[i]), tol, tol);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) a[i] = y[i] / sc[i];
+        const double d0 = rms_norm<NV>(a);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) a[i] = k0[i] / sc[i];
+        const double d1 = rms_norm<NV>(a);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = fmin(h0, tend);
+        double y1[NV], f1[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) y1[i] = fma(h0, k0[i], y[i]);
+        RHS(y1, f1);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) a[i] = (f1[i] - k0[i]) / sc[i];
+        const double d2 = rms_norm<NV>(a) / h0;
+        double h1;
+        if (d1 <= 1e-15 && d2 <= 1e-15)
+            h1 = fmax(1e-6, h0 * 1e-3);
+        else
+            h1 = pow(0.01 / fmax(d1, d2), 1.0 / (ERR_ORDER + 1));
+        double h = fmin(100.0 * h0, h1);
+        if (!(h == h)) h = 1e-6;
+        habs = fmin(h, tend);
+    }
+
+    // one attempted step towards tstop.  Returns 0 = keep going, 1 = trajectory failed (DOMAIN).
+    // `accepted` reports whether y/t advanced.
+    __device__ __forceinline__ int attempt(const SysPar &p, double (&y)[NV], double tstop, double tol, double dtmin,
+                                           bool &accepted)
+    {
+        accepted = false;
+        bool forced = false;
+        if (habs < dtmin) {
+            habs = dtmin;
+            forced = true;
+        }
+        double h = habs;
+        bool clipped = false;
+        const bool last = (t + h >= tstop);
+        if (last) {
+            clipped = (tstop - t) < habs;
+            h = tstop - t;
+        }
+        double err;
+        double yn[NV], kn[NV];
+        if constexpr (ALG == DTWA_ALG_DP5) {
+#include "dp5_body.inc"
+            double en[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const double sc = fma(fmax(fabs(y[i]), fabs(ynew[i])), tol, tol);
+                en[i] = e5[i] * h / sc;
+                yn[i] = ynew[i];
+                kn[i] = DP5_KNEW[i];
+            }
+            err = rms_norm<NV>(en);
+#undef DP5_KNEW
+        } else {
+#include "dop853_body.inc"
+            double n5 = 0.0, n3 = 0.0;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const double sc = fma(fmax(fabs(y[i]), fabs(ynew[i])), tol, tol);
+                const double a5 = e5[i] / sc, a3 = e3[i] / sc;
+                n5 = fma(a5, a5, n5);
+                n3 = fma(a3, a3, n3);
+                yn[i] = ynew[i];
+                kn[i] = DOP853_KNEW[i];
+            }
+            if (n5 == 0.0 && n3 == 0.0)
+                err = 0.0;
+            else
+                err = fabs(h) * n5 / sqrt(fma(0.01, n3, n5) * (double)NV);
+#undef DOP853_KNEW
+        }
+        const bool bad = state_bad<SYS>(yn) || !(err == err) || isinf(err);
+        constexpr double EXPO = -1.0 / (ERR_ORDER + 1);
+        if (bad) {
+            if (forced) return 1;
+            habs = h * 0.2;
+            rejected = true;
+            return 0;
+        }
+        if (err < 1.0 || forced) {
+            double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err, EXPO));
+            if (rejected) factor = fmin(1.0, factor);
+            double hn = h * factor;
+            if (clipped && hn < habs) hn = habs;
+            habs = hn;
+            t = last ? tstop : t + h;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                y[i] = yn[i];
+                k0[i] = kn[i];
+            }
+            rejected = false;
+            accepted = true;
+        } else {
+            habs = h * fmax(0.2, 0.9 * pow(err, EXPO));
+            rejected = true;
+        }
+        return 0;
+    }
+};
+#undef RHS
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  key = seed, counter = (idx, attempt, block).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b)
+{
+    const uint64_t m = ((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6);
+    return __dmul_rn(__dadd_rn((double)m, 0.5), 1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ void uniforms4(uint64_t seed, uint64_t idx, uint32_t attempt, double (&U)[4])
+{
+    uint32_t r[4];
+    philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), attempt, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    U[0] = u53(r[0], r[1]);
+    U[1] = u53(r[2], r[3]);
+    philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), attempt, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    U[2] = u53(r[0], r[1]);
+    U[3] = u53(r[2], r[3]);
+}
+
+struct SamplerPar {
+    int32_t kind;
+    int32_t nv;
+    double center[4];
+    double hbar;
+    uint64_t seed;
+    uint64_t offset;
+    const double *u0;  // device pointer for array samplers
+};
+
+#define DTWA_TWO_PI 6.283185307179586476925286766559
+#define DTWA_PI 3.14159265358979323846
+
+__device__ __forceinline__ double mod2pi_pos(double x)
+{
+    double r = fmod(x, DTWA_TWO_PI);
+    if (r < 0.0) r += DTWA_TWO_PI;
+    return r;
+}
+__device__ __forceinline__ double theta_of_QP(double Q, double P) { return acos(1.0 - (Q * Q + P * P) / 2.0); }
+__device__ __forceinline__ double phi_of_QP(double Q, double P) { return mod2pi_pos(atan2(-P, Q)); }
+
+// src/TWA.jl:708-745 sample(): Theta ~ Rayleigh(sigma) by inversion of U1, azimuth 2 pi U2, rotation
+// R(theta,phi,theta0,phi0) of :712-714, then (Q,P) of src/PhaseSpaces.jl:16,34 -- formula for formula.
+__device__ __noinline__ void sample_su2(double Q0, double P0, double hbar, double U1, double U2, double &Q, double &P)
+{
+    const double sigma = sqrt(hbar / 2.0);
+    const double th0 = theta_of_QP(Q0, P0), ph0 = phi_of_QP(Q0, P0);
+    const double th = sigma * sqrt(-2.0 * log(U1));
+    const double ph = U2 * 2.0 * DTWA_PI;
+    const double sth = sin(th), cth = cos(th), sph = sin(ph), cph = cos(ph);
+    const double st0 = sin(th0), ct0 = cos(th0), sp0 = sin(ph0), cp0 = cos(ph0);
+    const double a = ct0 * cph * sth - cth * st0;
+    const double thr = atan2(sqrt(a * a + sth * sth * sph * sph), cth * ct0 + cph * sth * st0);
+    const double phr = mod2pi_pos(atan2(-cp0 * sth * sph - ct0 * cph * sth * sp0 + cth * st0 * sp0,
+                                        -ct0 * cph * cp0 * sth + cth * cp0 * st0 + sth * sph * sp0));
+    const double rad = sqrt(2.0 * (1.0 - cos(thr)));
+    Q = rad * cos(phr);
+    P = -rad * sin(phr);
+}
+
+// src/TWA.jl:689-700: two independent normals (Box-Muller on U3, U4)
+__device__ __noinline__ void sample_hw(double q0, double p0, double hbar, double U3, double U4, double &q, double &p)
+{
+    const double sigma = sqrt(hbar / 2.0);
+    const double r = sigma * sqrt(-2.0 * log(U3));
+    const double a = U4 * 2.0 * DTWA_PI;
+    q = q0 + r * cos(a);
+    p = p0 + r * sin(a);
+}
+
+template <int NV>
+__device__ __forceinline__ void draw_initial(const SamplerPar &sp, uint64_t local_idx, uint32_t attempt, double (&u)[NV])
+{
+    if (sp.kind == DTWA_SAMPLER_HOST_ARRAY || sp.kind == DTWA_SAMPLER_DEVICE_ARRAY) {
+        const double *src = sp.u0 + local_idx * NV;
+        if constexpr (NV == 4) {
+            const double2 a = __ldg(reinterpret_cast<const double2 *>(src));
+            const double2 b = __ldg(reinterpret_cast<const double2 *>(src) + 1);
+            u[0] = a.x; u[1] = a.y; u[2] = b.x; u[3] = b.y;
+        } else {
+            const double2 a = __ldg(reinterpret_cast<const double2 *>(src));
+            u[0] = a.x; u[1] = a.y;
+        }
+        return;
+    }
+    double U[4];
+    uniforms4(sp.seed, sp.offset + local_idx, attempt, U);
+    if constexpr (NV == 4) {
+        sample_su2(sp.center[0], sp.center[2], sp.hbar, U[0], U[1], u[0], u[2]);
+        sample_hw(sp.center[1], sp.center[3], sp.hbar, U[2], U[3], u[1], u[3]);
+    } else {
+        if (sp.kind == DTWA_SAMPLER_COHERENT_HW)
+            sample_hw(sp.center[0], sp.center[1], sp.hbar, U[2], U[3], u[0], u[1]);
+        else
+            sample_su2(sp.center[0], sp.center[1], sp.hbar, U[0], U[1], u[0], u[1]);
+    }
+}
+
+// probability densities: src/TWA.jl:692-694 (MvNormal pdf), :719-736 (W_theta; 0.0 where the
+// reference's try/catch swallows an acos DomainError), :757 (product)
+__device__ __noinline__ double pdf_hw(double q0, double p0, double hbar, double q, double p)
+{
+    const double s2 = hbar / 2.0;
+    return exp(-((q - q0) * (q - q0) + (p - p0) * (p - p0)) / (2.0 * s2)) / (2.0 * DTWA_PI * s2);
+}
+__device__ __noinline__ double pdf_su2(double Q0, double P0, double hbar, double Q, double P)
+{
+    const double sigma = sqrt(hbar / 2.0);
+    const double a = 1.0 - (Q * Q + P * P) / 2.0;
+    if (!(a >= -1.0 && a <= 1.0)) return 0.0;
+    const double th = acos(a), ph = phi_of_QP(Q, P);
+    const double th0 = theta_of_QP(Q0, P0), ph0 = phi_of_QP(Q0, P0);
+    const double c = cos(th) * cos(th0) + sin(th) * sin(th0) * cos(ph - ph0);
+    if (!(c >= -1.0 && c <= 1.0)) return 0.0;
+    const double T = acos(c);
+    const double g = exp(-(T * T) / (2.0 * sigma * sigma)) / (sqrt(2.0 * DTWA_PI) * sigma);
+    return g * sqrt(2.0 * DTWA_PI) * sigma * (1.0 / (2.0 * DTWA_PI * sigma * sigma));
+}
+template <int NV>
+__device__ __forceinline__ double pdf_eval(const SamplerPar &sp, const double (&u)[NV])
+{
+    if constexpr (NV == 4) {
+        return pdf_su2(sp.center[0], sp.center[2], sp.hbar, u[0], u[2]) *
+               pdf_hw(sp.center[1], sp.center[3], sp.hbar, u[1], u[3]);
+    } else {
+        if (sp.kind == DTWA_SAMPLER_COHERENT_HW) return pdf_hw(sp.center[0], sp.center[1], sp.hbar, u[0], u[1]);
+        return pdf_su2(sp.center[0], sp.center[1], sp.hbar, u[0], u[1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// src/TWA.jl:53-64 scale_to_index, un-fused, round-half-even; 1-based, 0 = dropped
+struct RangeD {
+    double start, stop, lenm1;
+    int64_t len;
+};
+__device__ __forceinline__ long long scale_to_index(double v, const RangeD &r)
+{
+    if (v < r.start || r.stop < v) return 0;
+    if (!(v == v)) return 0;
+    if (r.len == 1) return 1;
+    const double x = __ddiv_rn(__dsub_rn(v, r.start), __dsub_rn(r.stop, r.start));
+    return (long long)rint(__dadd_rn(__dmul_rn(x, r.lenm1), 1.0));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Observable VM: a postfix program shared by all threads of the launch (uniform control flow).
+// Every arithmetic op is a single correctly rounded IEEE operation (no contraction), so + - * /
+// sqrt and integer powers agree bit for bit with the CPU oracle's evaluator.
+enum VmOp : uint8_t {
+    OP_END = 0, OP_VAR, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_IPOW, OP_POW, OP_SQRT, OP_SIN, OP_COS,
+    OP_TAN, OP_EXP, OP_LOG, OP_ABS, OP_ACOS, OP_ASIN, OP_ATAN, OP_ATAN2, OP_MIN, OP_MAX, OP_PDF,
+    // sinks
+    OP_SUM,     // pop -> sums slot b
+    OP_BIN,     // pop -> index register a (0/1) through range b
+    OP_HIST,    // histogram b from the index register(s)
+    OP_STORE    // pop -> out[b] (dtwa_eval_expr)
+};
+struct VmIns {
+    uint8_t op;
+    uint8_t a;
+    uint16_t b;
+};
+constexpr int VM_STACK = 16;
+constexpr int VM_MAX_INS = 1024;
+constexpr int VM_MAX_CONST = 256;
+constexpr int VM_MAX_RANGE = 32;
+constexpr int VM_MAX_HIST = 16;
+constexpr int VM_MAX_SLOTS = 64;
+
+__device__ __forceinline__ double ipow_rn(double x, int n)
+{
+    // left-to-right binary powering: x^2 = x*x, x^3 = (x*x)*x, x^4 = (x*x)*(x*x) ...
+    if (n == 0) return 1.0;
+    const bool neg = n < 0;
+    unsigned m = neg ? (unsigned)(-n) : (unsigned)n;
+    int top = 31 - __clz(m);
+    double r = x;
+    for (int bit = top - 1; bit >= 0; --bit) {
+        r = __dmul_rn(r, r);
+        if ((m >> bit) & 1u) r = __dmul_rn(r, x);
+    }
+    return neg ? __ddiv_rn(1.0, r) : r;
+}
+
+}  // namespace dtwa

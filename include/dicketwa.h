@@ -1,0 +1,217 @@
+/*
+ * dicketwa.h -- C ABI of libdicketwa.so, the B200 (sm_100a) implementation of DickeModel.jl's
+ * Truncated-Wigner (TWA) ensemble hot path.
+ *
+ * The reference is pure Julia and has no FFI of its own; its extension points on this path are
+ * Julia dispatch and closures.  Each entry point below therefore names the
+ * reference *function* it replaces (paths relative to the reference checkout).  A Julia package
+ * that `ccall`s these functions keeps the reference's module/function names
+ * (dickemodel.jl_b200/julia/DickeModelB200.jl); the Python ctypes mirror in
+ * dickemodel.jl_b200/ is the executable harness because Julia is absent from the build image.
+ *
+ * Conventions
+ *  - plain pointers and sizes, POD structs, no C++/torch types;
+ *  - the caller owns every host buffer, the library owns all device memory inside dtwa_ctx;
+ *  - every function returns an int status (DTWA_OK = 0, negative = error) and never throws;
+ *    dtwa_last_error() returns a thread-local message for the last failure;
+ *  - calls are blocking unless stated; a context is not re-entrant, distinct contexts may be used
+ *    from distinct threads;
+ *  - there is NO CPU fallback: without a usable sm_100-class CUDA device dtwa_create fails.
+ *  - state ordering: Dicke u = [Q,q,P,p] (src/ClassicalDicke.jl:21), LMG u = [Q,P]
+ *    (src/ClassicalLMG.jl:15); all arrays row-major, trajectory index slowest.
+ */
+#ifndef DICKETWA_H
+#define DICKETWA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTWA_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes ---- */
+#define DTWA_OK 0
+#define DTWA_ERR_INVALID (-1)      /* bad argument (the reference's error(...) calls) */
+#define DTWA_ERR_CUDA (-2)         /* CUDA runtime failure */
+#define DTWA_ERR_NO_DEVICE (-3)    /* no CUDA device: this library has no CPU path */
+#define DTWA_ERR_EXPR (-4)         /* observable expression does not parse / unknown variable (src/TWA.jl:291-293) */
+#define DTWA_ERR_NCCL (-5)
+#define DTWA_ERR_TOO_MANY_FAILURES (-6) /* >100 consecutive resampling rounds (src/TWA.jl:202-206) */
+#define DTWA_ERR_BOUNDS (-7)       /* initial condition out of bounds (src/ClassicalSystems.jl:100-102) */
+#define DTWA_ERR_CAPACITY (-8)     /* caller buffer too small / internal limit exceeded */
+
+/* ---- per-trajectory status (dtwa_integrate) ---- */
+#define DTWA_TRAJ_OK 0
+#define DTWA_TRAJ_DOMAIN 1   /* left the chart 4-P^2-Q^2>0 or became non-finite: the reference throws */
+#define DTWA_TRAJ_MAXITERS 2 /* adaptive solver used up maxiters attempts */
+#define DTWA_TRAJ_BAD_IC 3   /* initial condition out of bounds */
+
+typedef struct dtwa_ctx dtwa_ctx;
+typedef struct dtwa_plan dtwa_plan;
+
+/* ---- system: replaces ClassicalDickeSystem (src/ClassicalDicke.jl:48-52) and
+ *      ClassicalLMGSystem (src/ClassicalLMG.jl:32-36); params in the reference's own order:
+ *      Dicke {w0, w, gamma}, LMG {Omega, xi}. ---- */
+#define DTWA_SYS_DICKE 0
+#define DTWA_SYS_LMG 1
+typedef struct {
+    int32_t kind;
+    int32_t reserved;
+    double params[4];
+} dtwa_system;
+
+/* ---- solver: the keyword arguments ClassicalSystems.integrate forwards to solve()
+ *      (src/ClassicalSystems.jl:78-88,138).  tol is abstol=reltol; dtmin<=0 means dtmin=tol with
+ *      force_dtmin (the reference default); maxiters<=0 means 100000 (OrdinaryDiffEq default).
+ *      Fixed-step algorithms take ceil(interval/dt) equal sub-steps per output interval so that
+ *      every ts[k] is hit exactly. ---- */
+#define DTWA_ALG_RK4 0     /* classical 4th order, fixed step dt */
+#define DTWA_ALG_RK8 1     /* DOP853 8th-order weights, fixed step dt */
+#define DTWA_ALG_DP5 2     /* Dormand-Prince 5(4), adaptive  (reference: integrator_alg=DP5()) */
+#define DTWA_ALG_DOP853 3  /* Hairer DOP853 8(5,3), adaptive (reference: integrator_alg=DP8()) */
+typedef struct {
+    int32_t alg;
+    int32_t backwards; /* the reference's `integate_backwards` [sic] */
+    double dt;
+    double tol;
+    double dtmin;
+    int64_t maxiters;
+} dtwa_solver;
+
+/* ---- sampler: replaces PhaseSpaceDistribution.sample of coherent_Wigner_HW / _SU2 / _HWxSU2
+ *      (src/TWA.jl:689-764).  center = {q0,p0} | {Q0,P0} | {Q0,q0,P0,p0}; hbar = 1/j.
+ *      Counter-based Philox4x32-10: key = seed, counter = (offset + i, attempt, block), so the
+ *      sample set does not depend on the launch shape or on how many GPUs share the ensemble.
+ *      HOST_ARRAY / DEVICE_ARRAY take caller-supplied initial conditions u0[N][nvar]. ---- */
+#define DTWA_SAMPLER_HOST_ARRAY 0
+#define DTWA_SAMPLER_COHERENT_HW 1
+#define DTWA_SAMPLER_COHERENT_SU2 2
+#define DTWA_SAMPLER_COHERENT_HWXSU2 3
+#define DTWA_SAMPLER_DEVICE_ARRAY 4
+typedef struct {
+    int32_t kind;
+    int32_t reserved;
+    double center[4];
+    double hbar;
+    uint64_t seed;
+    uint64_t offset;  /* global index of this call's first trajectory */
+    const double *u0; /* HOST_ARRAY: host pointer, DEVICE_ARRAY: device pointer; else NULL */
+} dtwa_sampler;
+
+/* ---- reducers: replace the MonteCarloSystem closures (src/TWA.jl:37-51) built by
+ *      mcs_for_averaging (:336-370), mcs_for_distributions (:413-543) and
+ *      mcs_for_survival_probability (:652-668).  Expressions are UTF-8 strings over the system's
+ *      varnames with + - * / ^ ( ) unary minus, numbers, pi, and
+ *      sqrt sin cos tan exp log abs acos asin atan min max pow atan2.  Several reducers in one
+ *      call share the same trajectories (mcs_chain, src/TWA.jl:235-274). ---- */
+#define DTWA_RED_AVERAGE 0
+#define DTWA_RED_HIST 1
+#define DTWA_RED_SURVIVAL 2
+#define DTWA_AXIS_EXPR 0
+#define DTWA_AXIS_TIME 1
+typedef struct {
+    double start, stop; /* LinRange(start, stop, len), both ends inclusive (src/TWA.jl:53-64) */
+    int64_t len;
+} dtwa_range;
+typedef struct {
+    int32_t kind;
+    int32_t nexpr;            /* AVERAGE: number of observables */
+    const char *const *exprs; /* AVERAGE: nexpr strings */
+    int32_t x_axis, y_axis;   /* HIST: DTWA_AXIS_* ; at most one may be TIME */
+    const char *x_expr;       /* HIST: used when x_axis == EXPR */
+    const char *y_expr;
+    dtwa_range xs, ys;        /* HIST: bins of the EXPR axes */
+    int32_t animate;          /* HIST with two EXPR axes: one matrix per time (src/TWA.jl:480-489) */
+    int32_t reserved;
+} dtwa_reducer;
+
+/* Result buffers, caller-allocated.  Raw (un-normalised) accumulators: the shim divides by N
+ * (src/TWA.jl:362,518,664).
+ *   AVERAGE : sums[nt][nexpr]
+ *   SURVIVAL: sums[nt]
+ *   HIST    : x TIME -> counts[nt][ys.len]; y TIME -> counts[nt][xs.len];
+ *             two EXPR axes -> counts[ys.len][xs.len] (all times) or counts[nt][ys.len][xs.len] (animate) */
+typedef struct {
+    double *sums;
+    int64_t sums_len; /* capacity in elements, checked */
+    uint64_t *counts;
+    int64_t counts_len;
+} dtwa_reducer_out;
+
+typedef struct {
+    dtwa_reducer_out *red;   /* [nred] */
+    uint64_t *n_valid;       /* [nt] trajectories that contributed at each time (may be NULL) */
+    uint64_t n_failed;       /* trajectories that hit DOMAIN (each resampling attempt counts) */
+    uint64_t n_unfinished;   /* trajectories that ended with MAXITERS or could not be resampled */
+    uint64_t steps_accepted; /* trajectory-steps taken */
+    uint64_t steps_rejected; /* adaptive only */
+    uint64_t lane_steps;     /* 32 x warp-level step iterations: steps/(lane_steps) = lane efficiency */
+    int32_t resample_rounds;
+    int32_t launches;        /* kernels launched by this call */
+    double kernel_ms;        /* CUDA-event time of the ensemble kernels on the context's stream */
+    double total_ms;         /* CUDA-event time incl. host<->device copies */
+} dtwa_result;
+
+/* ---- context ---- */
+const char *dtwa_last_error(void);
+int dtwa_version(void);
+/* device_ids[ndev]; ndev>1 shards [0,N) by contiguous index blocks over the devices of one
+ * process and merges the per-time arrays with one grouped ncclAllReduce (libnccl is dlopen'ed).
+ * stream: an existing cudaStream_t (as void*) to enqueue on when ndev==1, or NULL for a private one. */
+int dtwa_create(dtwa_ctx **out, const int *device_ids, int ndev, void *stream);
+int dtwa_destroy(dtwa_ctx *ctx);
+/* name[256]; sm_count, clock_khz, cc (major*10+minor) */
+int dtwa_device_info(dtwa_ctx *ctx, int which, char *name, int *sm_count, int *clock_khz, int *cc);
+/* tuning: threads per CTA (0 = default) and resident CTAs per SM (0 = occupancy query) */
+int dtwa_set_launch(dtwa_ctx *ctx, int block_threads, int ctas_per_sm);
+
+/* ---- a5: ClassicalDicke.hamiltonian / ClassicalLMG.hamiltonian (src/ClassicalDicke.jl:80-88,
+ *      src/ClassicalLMG.jl:63-70) on a batch u[n][nvar] -> h[n] ---- */
+int dtwa_hamiltonian(dtwa_ctx *ctx, const dtwa_system *sys, const double *u, int64_t n, double *h);
+
+/* ---- a7: ClassicalSystems.integrate (src/ClassicalSystems.jl:78-140) for n independent initial
+ *      conditions, states reported at ts[nt] (sorted, >= 0, t0 = 0):
+ *      out[n][nt][nvar] (NaN after a failure), status[n] (DTWA_TRAJ_*), nsteps[n] (accepted +
+ *      rejected attempts; may be NULL). ---- */
+int dtwa_integrate(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const double *u0, int64_t n,
+                   const double *ts, int32_t nt, double *out, int32_t *status, int64_t *nsteps);
+
+/* ---- a8-a10: distribution.sample() / distribution.probability_density (src/TWA.jl:692-698,
+ *      719-743,757-762) on the device: u[n][nvar] for trajectories offset..offset+n-1 ---- */
+int dtwa_sample(dtwa_ctx *ctx, const dtwa_sampler *smp, int64_t n, uint32_t attempt, double *u);
+int dtwa_pdf(dtwa_ctx *ctx, const dtwa_sampler *smp, const double *u, int64_t n, double *w);
+
+/* ---- a12/a17 test hooks: evaluate an observable expression and scale_to_index (src/TWA.jl:53-64,
+ *      277-299) on the device.  idx is 1-based, 0 = dropped. ---- */
+int dtwa_eval_expr(dtwa_ctx *ctx, const dtwa_system *sys, const char *expr, const double *u, int64_t n, double *v);
+int dtwa_scale_to_index(dtwa_ctx *ctx, const double *v, int64_t n, const dtwa_range *r, int64_t *idx);
+
+/* ---- a13-a20: TWA.monte_carlo_integrate (src/TWA.jl:100-224) with the reducers of average
+ *      (:565-568), variance (:630-633, composed by the shim), survival_probability (:677-680) and
+ *      calculate_distribution (:552-556); nred > 1 is mcs_chain.
+ *      tolerate_errors: failed trajectories are resampled (attempt+1) in follow-up rounds and the
+ *      replacement contributes from the failure index on (src/TWA.jl:186-209). ---- */
+int dtwa_ensemble(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const dtwa_sampler *smp, int64_t N,
+                  const double *ts, int32_t nt, const dtwa_reducer *red, int32_t nred, int32_t tolerate_errors,
+                  dtwa_result *res);
+
+/* Split form for one-process-per-GPU jobs: launch leaves the reduced accumulators of this rank in
+ * two device arenas (f64 sums, u64 counts+counters) that the host framework all-reduces (NCCL
+ * ncclSum) on the same stream before fetch unpacks them into the caller's buffers. */
+int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const dtwa_sampler *smp,
+                         int64_t N, const double *ts, int32_t nt, const dtwa_reducer *red, int32_t nred,
+                         int32_t tolerate_errors, dtwa_plan **plan);
+int dtwa_plan_arenas(dtwa_plan *plan, void **d_f64, int64_t *n_f64, void **d_u64, int64_t *n_u64);
+int dtwa_plan_fetch(dtwa_plan *plan, dtwa_result *res);
+int dtwa_plan_free(dtwa_plan *plan);
+
+/* ---- K0: FP64 roofline denominator: a DFMA-chain micro-benchmark on every SM; returns the
+ *      achieved TFLOP/s (FMA = 2 flops) and the kernel time ---- */
+int dtwa_fp64_peak(dtwa_ctx *ctx, double *tflops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DICKETWA_H */
