@@ -1,0 +1,191 @@
+"""ClassicalSystems -- the abstract system protocol and `integrate`.
+
+Mirrors src/ClassicalSystems.jl:19-45 (protocol) and :78-140 (integrate) of the reference.  The
+solve itself runs on the GPU through dtwa_integrate (include/dicketwa.h); nothing here integrates
+on the CPU.  Out of scope: get_fundamental_matrix, use_big_numbers,
+lyapunov_spectrum / lyapunov_exponent, DiffEq callbacks.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+class ClassicalSystem:
+    """src/ClassicalSystems.jl:19 -- subclasses provide parameters/varnames/out_of_bounds and a
+    dtwa_system kind."""
+    _kind = None
+
+    def parameters(self):
+        raise NotImplementedError("Please define parameters() for this system")
+
+    def varnames(self):
+        raise NotImplementedError("Please define varnames() for this system")
+
+    def out_of_bounds(self, u):
+        raise NotImplementedError("Please define out_of_bounds() for this system")
+
+    def _c_system(self):
+        s = _lib.System()
+        s.kind = self._kind
+        for i, v in enumerate(self.parameters()):
+            s.params[i] = float(v)
+        return s
+
+
+def parameters(system):
+    return system.parameters()
+
+
+def varnames(system):
+    return system.varnames()
+
+
+def out_of_bounds(system):
+    return lambda u, _=None, t=0: system.out_of_bounds(u)
+
+
+def nvars(system, *vars):
+    """src/ClassicalSystems.jl:37-45 (1-based like the reference)"""
+    d = {v: i + 1 for i, v in enumerate(system.varnames())}
+    return [d[v] for v in vars]
+
+
+# ---- integrator algorithms (markers standing for the OrdinaryDiffEq objects the reference passes) ----
+class _Alg:
+    def __init__(self, name, code, fixed, note=""):
+        self.name, self.code, self.fixed, self.note = name, code, fixed, note
+
+    def __call__(self):
+        return self
+
+    def __repr__(self):
+        return f"{self.name}()"
+
+
+DP8 = _Alg("DP8", _lib.ALG_DOP853, False)
+DOP853 = DP8
+DP5 = _Alg("DP5", _lib.ALG_DP5, False)
+RK4 = _Alg("RK4", _lib.ALG_RK4, True)
+RK8 = _Alg("RK8", _lib.ALG_RK8, True)
+# The reference default (src/ClassicalSystems.jl:84).  Its coefficients are not available offline
+# (hard part 8), so the same-order Hairer pair DOP853 (= DP8()) is run instead.
+TsitPap8 = _Alg("TsitPap8", _lib.ALG_DOP853, False, "runs as DOP853: the Tsitouras-Papakostas tableau is not available offline")
+Vern8 = _Alg("Vern8", _lib.ALG_DOP853, False, "runs as DOP853")
+Tsit5 = _Alg("Tsit5", _lib.ALG_DP5, False, "runs as DP5")
+_BY_NAME = {a.name.lower(): a for a in (DP8, DP5, RK4, RK8, TsitPap8, Vern8, Tsit5)}
+_BY_NAME["dop853"] = DP8
+
+
+def _resolve_alg(alg):
+    if alg is None:
+        return TsitPap8
+    if isinstance(alg, _Alg):
+        return alg
+    if isinstance(alg, str) and alg.lower().rstrip("()") in _BY_NAME:
+        return _BY_NAME[alg.lower().rstrip("()")]
+    raise ValueError(f"integrator_alg={alg!r} is not available; use one of {sorted(_BY_NAME)}")
+
+
+def solver_from_kargs(kargs: dict) -> _lib.Solver:
+    """Turn the keyword arguments the reference forwards integrate -> solve
+    (src/ClassicalSystems.jl:78-88,138; src/TWA.jl:190) into a dtwa_solver."""
+    k = dict(kargs)
+    alg = _resolve_alg(k.pop("integrator_alg", k.pop("alg", None)))
+    tol = float(k.pop("tol", 1e-12))
+    backwards = bool(k.pop("integate_backwards", k.pop("integrate_backwards", False)))
+    dt = k.pop("dt", None)
+    adaptive = k.pop("adaptive", None)
+    dtmin = k.pop("dtmin", None)
+    maxiters = k.pop("maxiters", None)
+    for ignored in ("save_everystep", "show_progress", "progress", "verbose", "dense"):
+        k.pop(ignored, None)
+    for unsupported in ("get_fundamental_matrix", "use_big_numbers", "callback", "fundamental_matrix_initial"):
+        if k.pop(unsupported, None):
+            raise NotImplementedError(f"{unsupported} is outside the GPU hot path (SURVEY.md section 8)")
+    if k:
+        raise TypeError(f"unsupported solver keyword(s): {sorted(k)}")
+    code = alg.code
+    if adaptive is False and not alg.fixed:
+        if code == _lib.ALG_DOP853:
+            code = _lib.ALG_RK8
+        else:
+            raise ValueError(f"adaptive=false is only available for RK4 and the 8th-order tableau, not {alg}")
+    fixed = code in (_lib.ALG_RK4, _lib.ALG_RK8)
+    if fixed and (dt is None or not dt > 0):
+        raise ValueError("fixed-step integration needs dt > 0")
+    s = _lib.Solver()
+    s.alg = code
+    s.backwards = int(backwards)
+    s.dt = float(dt) if dt else 0.0
+    s.tol = tol
+    s.dtmin = float(dtmin) if dtmin else 0.0
+    s.maxiters = int(maxiters) if maxiters else 0
+    return s
+
+
+class ODESolution:
+    """What `integrate` returns: times `.t`, states `.u` (len(t) x nvar), `.retcode`; calling it
+    with a time re-integrates to that time on the GPU (the reference interpolates)."""
+
+    def __init__(self, system, u0, t0, t, u, retcode, nsteps, kargs):
+        self._system, self._u0, self._t0, self._kargs = system, u0, t0, kargs
+        self.t, self.u, self.retcode, self.nsteps = t, u, retcode, nsteps
+
+    def __call__(self, tq):
+        tq = np.atleast_1d(np.asarray(tq, dtype=float))
+        order = np.argsort(tq)
+        s = integrate(self._system, self._u0, float(tq[order][-1]), t0=self._t0, saveat=tq[order], **self._kargs)
+        out = np.empty_like(s.u)
+        out[order] = s.u
+        return out[0] if out.shape[0] == 1 else out
+
+    def __getitem__(self, i):
+        return self.u[i]
+
+    def __len__(self):
+        return len(self.t)
+
+
+_RETCODES = {_lib.TRAJ_OK: "Success", _lib.TRAJ_DOMAIN: "DomainError", _lib.TRAJ_MAXITERS: "MaxIters",
+             _lib.TRAJ_BAD_IC: "OutOfBounds"}
+
+
+def integrate(system, u0, t, *, t0=0.0, tol=1e-12, get_fundamental_matrix=False, integrator_alg=None,
+              use_big_numbers=False, integate_backwards=False, fundamental_matrix_initial=None, saveat=None,
+              **kargs):
+    """src/ClassicalSystems.jl:78-140.  Integrates u0 from t0 to t; the states are reported at
+    `saveat` (array of times in [t0, t]; default [t0, t])."""
+    if t < t0:
+        raise ValueError("Use integate_backwards=true instead of negative time")  # :89-91
+    u0 = np.asarray(u0, dtype=np.float64).ravel()
+    names = system.varnames()
+    if len(u0) != len(names):
+        raise ValueError(f"u₀ should have length {len(names)}, which is the dimension of the phase space of system")  # :97-99
+    if system.out_of_bounds(u0):
+        raise ValueError(f"The initial condition u₀={u0.tolist()} is out of bounds")  # :100-102
+    if get_fundamental_matrix or use_big_numbers or fundamental_matrix_initial is not None:
+        raise NotImplementedError("fundamental matrix / BigFloat integration is outside the GPU hot path (SURVEY.md section 8)")
+    sol = solver_from_kargs(dict(kargs, tol=tol, integrator_alg=integrator_alg, integate_backwards=integate_backwards))
+    ts = np.array([t0, t], dtype=float) if saveat is None else np.atleast_1d(np.asarray(saveat, dtype=float))
+    if np.any(ts < t0) or np.any(ts > t) or np.any(np.diff(ts) < 0):
+        raise ValueError("saveat must be sorted and lie in [t₀, t]")
+    out, status, nsteps = _lib.default_context().integrate(system._c_system(), sol, u0[None, :], ts - t0)
+    return ODESolution(system, u0, t0, ts, out[0], _RETCODES[int(status[0])], int(nsteps[0]),
+                       dict(kargs, tol=tol, integrator_alg=integrator_alg, integate_backwards=integate_backwards))
+
+
+def integrate_batch(system, U0, ts, **kargs):
+    """Many initial conditions at once (the K3 kernel): returns (out[n][nt][nvar], status[n], nsteps[n]).
+    No counterpart in the reference, which loops over `integrate`."""
+    sol = solver_from_kargs(kargs)
+    return _lib.default_context().integrate(system._c_system(), sol, U0, ts)
+
+
+def lyapunov_spectrum(*a, **k):
+    raise NotImplementedError("lyapunov_spectrum needs the variational system: out of scope (SURVEY.md section 8f, rank 2)")
+
+
+def lyapunov_exponent(*a, **k):
+    raise NotImplementedError("lyapunov_exponent needs the variational system: out of scope (SURVEY.md section 8f, rank 2)")

@@ -1,0 +1,1041 @@
+// dtwa_api.cu -- the C ABI of libdicketwa.so (include/dicketwa.h) and its host-side logic:
+// argument validation (the reference's error(...) calls), the fixed-step table, the reducer
+// program, launch shapes, device arenas, the resampling rounds of tolerate_errors and the
+// multi-device merge.  No CPU compute path exists here: without a CUDA device dtwa_create fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "dtwa_kernels.cuh"
+#include "dtwa_expr.hpp"
+
+using namespace dtwa;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int set_err(int code, const std::string &m)
+{
+    g_err = m;
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return set_err(DTWA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define TRY(call)            \
+    do {                     \
+        int rc_ = (call);    \
+        if (rc_) return rc_; \
+    } while (0)
+
+extern "C" const char *dtwa_last_error(void) { return g_err.c_str(); }
+extern "C" int dtwa_version(void) { return DTWA_VERSION; }
+
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(DTWA_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+        }
+        cap = want;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct DevCtx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int sm_count = 0, clock_khz = 0, cc = 0;
+    char name[256] = {0};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    DevBuf partial, meta, u0, fail[2], scratch_a, scratch_b, scratch_c;
+};
+
+// NCCL, loaded lazily (only a multi-device context needs it)
+typedef struct ncclComm *ncclComm_t;
+struct NcclApi {
+    void *handle = nullptr;
+    int (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+
+struct dtwa_ctx {
+    std::vector<DevCtx> devs;
+    int block_threads = 0, ctas_per_sm = 0;
+    NcclApi nccl;
+    std::vector<ncclComm_t> comms;
+};
+
+static int load_nccl(dtwa_ctx *ctx)
+{
+    NcclApi &n = ctx->nccl;
+    if (n.handle) return 0;
+    const char *cands[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *c : cands) {
+        n.handle = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+        if (n.handle) break;
+    }
+    if (!n.handle) return set_err(DTWA_ERR_NCCL, std::string("cannot dlopen libnccl: ") + dlerror());
+#define SYM(field, name)                                                                       \
+    *(void **)(&n.field) = dlsym(n.handle, name);                                              \
+    if (!n.field) return set_err(DTWA_ERR_NCCL, std::string("libnccl lacks symbol ") + name);
+    SYM(CommInitAll, "ncclCommInitAll")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(AllReduce, "ncclAllReduce")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return 0;
+}
+
+extern "C" int dtwa_create(dtwa_ctx **out, const int *device_ids, int ndev, void *stream)
+{
+    if (!out) return set_err(DTWA_ERR_INVALID, "dtwa_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return set_err(DTWA_ERR_NO_DEVICE,
+                       std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count=0") +
+                           "); libdicketwa has no CPU path");
+    }
+    if (ndev <= 0) ndev = 1;
+    if (stream && ndev != 1) return set_err(DTWA_ERR_INVALID, "an external stream requires ndev == 1");
+    dtwa_ctx *ctx = new dtwa_ctx;
+    ctx->devs.resize(ndev);
+    for (int i = 0; i < ndev; ++i) {
+        DevCtx &d = ctx->devs[i];
+        d.device = device_ids ? device_ids[i] : i;
+        if (d.device < 0 || d.device >= count) {
+            delete ctx;
+            return set_err(DTWA_ERR_INVALID, "dtwa_create: device id out of range");
+        }
+        cudaDeviceProp prop;
+        if (cudaSetDevice(d.device) != cudaSuccess || cudaGetDeviceProperties(&prop, d.device) != cudaSuccess) {
+            delete ctx;
+            return set_err(DTWA_ERR_CUDA, "cannot select device");
+        }
+        if (prop.major < 10) {
+            delete ctx;
+            return set_err(DTWA_ERR_NO_DEVICE, std::string("device ") + prop.name + " is not sm_100-class; this library ships sm_100a code only");
+        }
+        d.sm_count = prop.multiProcessorCount;
+        d.cc = prop.major * 10 + prop.minor;
+        cudaDeviceGetAttribute(&d.clock_khz, cudaDevAttrClockRate, d.device);
+        std::snprintf(d.name, sizeof(d.name), "%s", prop.name);
+        if (stream) {
+            d.stream = (cudaStream_t)stream;
+            d.own_stream = false;
+        } else if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return set_err(DTWA_ERR_CUDA, "cudaStreamCreate failed");
+        }
+        for (auto &ev : d.ev) cudaEventCreate(&ev);
+    }
+    if (ndev > 1) {
+        int rc = load_nccl(ctx);
+        if (rc) {
+            delete ctx;
+            return rc;
+        }
+        std::vector<int> ids(ndev);
+        for (int i = 0; i < ndev; ++i) ids[i] = ctx->devs[i].device;
+        ctx->comms.resize(ndev);
+        int r = ctx->nccl.CommInitAll(ctx->comms.data(), ndev, ids.data());
+        if (r) {
+            std::string m = std::string("ncclCommInitAll: ") + ctx->nccl.GetErrorString(r);
+            delete ctx;
+            return set_err(DTWA_ERR_NCCL, m);
+        }
+    }
+    *out = ctx;
+    return DTWA_OK;
+}
+
+extern "C" int dtwa_destroy(dtwa_ctx *ctx)
+{
+    if (!ctx) return DTWA_OK;
+    for (auto &c : ctx->comms)
+        if (c) ctx->nccl.CommDestroy(c);
+    for (auto &d : ctx->devs) {
+        cudaSetDevice(d.device);
+        cudaStreamSynchronize(d.stream);
+        for (DevBuf *b : {&d.partial, &d.meta, &d.u0, &d.fail[0], &d.fail[1], &d.scratch_a, &d.scratch_b, &d.scratch_c}) b->release();
+        for (auto &ev : d.ev)
+            if (ev) cudaEventDestroy(ev);
+        if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+    return DTWA_OK;
+}
+
+extern "C" int dtwa_device_info(dtwa_ctx *ctx, int which, char *name, int *sm_count, int *clock_khz, int *cc)
+{
+    if (!ctx || which < 0 || which >= (int)ctx->devs.size()) return set_err(DTWA_ERR_INVALID, "bad context/device index");
+    const DevCtx &d = ctx->devs[which];
+    if (name) std::snprintf(name, 256, "%s", d.name);
+    if (sm_count) *sm_count = d.sm_count;
+    if (clock_khz) *clock_khz = d.clock_khz;
+    if (cc) *cc = d.cc;
+    return DTWA_OK;
+}
+
+extern "C" int dtwa_set_launch(dtwa_ctx *ctx, int block_threads, int ctas_per_sm)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    if (block_threads < 0 || (block_threads % 32) != 0 || block_threads > 512)
+        return set_err(DTWA_ERR_INVALID, "block_threads must be a multiple of 32 in [32, 512] (0 = default)");
+    ctx->block_threads = block_threads;
+    ctx->ctas_per_sm = ctas_per_sm < 0 ? 0 : ctas_per_sm;
+    return DTWA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// validation helpers
+static int nvar_of(int kind) { return kind == DTWA_SYS_DICKE ? 4 : 2; }
+
+static int check_system(const dtwa_system *sys)
+{
+    if (!sys) return set_err(DTWA_ERR_INVALID, "system is NULL");
+    if (sys->kind != DTWA_SYS_DICKE && sys->kind != DTWA_SYS_LMG) return set_err(DTWA_ERR_INVALID, "unknown system kind");
+    return 0;
+}
+
+static std::vector<std::string> varnames_of(int kind)
+{
+    if (kind == DTWA_SYS_DICKE) return {"Q", "q", "P", "p"};  // src/ClassicalDicke.jl:21
+    return {"Q", "P"};                                         // src/ClassicalLMG.jl:15
+}
+
+static SysPar make_par(const dtwa_system *sys, int backwards)
+{
+    const double sg = backwards ? -1.0 : 1.0;
+    SysPar p;
+    if (sys->kind == DTWA_SYS_DICKE) {
+        p.a = sg * sys->params[0];
+        p.b = sg * sys->params[1];
+        p.c = sg * sys->params[2];
+        p.d = 0.0;
+    } else {
+        const double Om = sg * sys->params[0], xi = sg * sys->params[1];
+        p.a = Om;
+        p.b = xi;
+        p.c = xi / 2.0;
+        p.d = 2.0 * xi + Om;
+    }
+    return p;
+}
+
+static int check_solver(const dtwa_solver *sol, bool fixed_needs_dt = true)
+{
+    if (!sol) return set_err(DTWA_ERR_INVALID, "solver is NULL");
+    if (sol->alg < DTWA_ALG_RK4 || sol->alg > DTWA_ALG_DOP853) return set_err(DTWA_ERR_INVALID, "unknown solver alg");
+    const bool fixed = sol->alg == DTWA_ALG_RK4 || sol->alg == DTWA_ALG_RK8;
+    if (fixed && fixed_needs_dt && !(sol->dt > 0)) return set_err(DTWA_ERR_INVALID, "fixed-step algorithms need dt > 0");
+    if (!fixed && !(sol->tol > 0)) return set_err(DTWA_ERR_INVALID, "adaptive algorithms need tol > 0");
+    return 0;
+}
+
+// Fixed-step table (same rule as oracle/oracle.c orc_step_table): interval k = (ts[k-1] or 0, ts[k]]
+// in n = ceil(d/dt - 1e-9) equal sub-steps.  Also validates ts (src/ClassicalSystems.jl:89-91:
+// "Use integate_backwards=true instead of negative time").
+static int build_step_table(const double *ts, int nt, double dt, std::vector<StepTab> &tab)
+{
+    if (!ts || nt < 1) return set_err(DTWA_ERR_INVALID, "ts must hold at least one time");
+    tab.resize(nt);
+    double tprev = 0.0;
+    for (int k = 0; k < nt; ++k) {
+        const double d = ts[k] - tprev;
+        if (!(d >= 0)) {
+            if (ts[k] < 0) return set_err(DTWA_ERR_INVALID, "Use integate_backwards=true instead of negative time");
+            return set_err(DTWA_ERR_INVALID, "ts should be a sorted array of times");
+        }
+        StepTab r;
+        std::memset(&r, 0, sizeof(r));
+        if (d > 0 && dt > 0) {
+            long long n = (long long)std::ceil(d / dt - 1e-9);
+            if (n < 1) n = 1;
+            if (n > 2000000000ll) return set_err(DTWA_ERR_INVALID, "dt too small for the requested ts spacing");
+            r.n = (int32_t)n;
+            r.h = d / (double)n;
+            r.hh = r.h / 2.0;
+            r.h3 = r.h / 3.0;
+            r.h6 = r.h / 6.0;
+        }
+        tab[k] = r;
+        tprev = ts[k];
+    }
+    return 0;
+}
+
+static SolverArgs make_solver_args(const dtwa_system *sys, const dtwa_solver *sol, const StepTab *d_tab, const double *d_ts,
+                                   const double *ts, int nt)
+{
+    SolverArgs S;
+    S.par = make_par(sys, sol->backwards);
+    S.tab = d_tab;
+    S.ts = d_ts;
+    S.tol = sol->tol;
+    S.dtmin = sol->dtmin > 0 ? sol->dtmin : sol->tol;  // src/ClassicalSystems.jl:138 dtmin=tol
+    S.tend = ts[nt - 1];
+    S.maxiters = sol->maxiters > 0 ? sol->maxiters : 100000;
+    S.nt = nt;
+    S.pad = 0;
+    return S;
+}
+
+static int make_sampler_par(const dtwa_system *sys, const dtwa_sampler *smp, SamplerPar &sp)
+{
+    if (!smp) return set_err(DTWA_ERR_INVALID, "sampler is NULL");
+    const int nv = nvar_of(sys->kind);
+    sp.kind = smp->kind;
+    sp.nv = nv;
+    for (int i = 0; i < 4; ++i) sp.center[i] = smp->center[i];
+    sp.hbar = smp->hbar;
+    sp.seed = smp->seed;
+    sp.offset = smp->offset;
+    sp.u0 = nullptr;
+    switch (smp->kind) {
+    case DTWA_SAMPLER_HOST_ARRAY:
+    case DTWA_SAMPLER_DEVICE_ARRAY:
+        if (!smp->u0) return set_err(DTWA_ERR_INVALID, "array sampler needs u0");
+        return 0;
+    case DTWA_SAMPLER_COHERENT_HWXSU2:
+        if (nv != 4) return set_err(DTWA_ERR_INVALID, "coherent_Wigner_HWxSU2 samples 4 variables; the system has 2");
+        break;
+    case DTWA_SAMPLER_COHERENT_HW:
+    case DTWA_SAMPLER_COHERENT_SU2:
+        if (nv != 2) return set_err(DTWA_ERR_INVALID, "coherent_Wigner_HW / _SU2 sample 2 variables; the system has 4");
+        break;
+    default: return set_err(DTWA_ERR_INVALID, "unknown sampler kind");
+    }
+    if (!(smp->hbar > 0)) return set_err(DTWA_ERR_INVALID, "sampler needs hbar > 0");
+    return 0;
+}
+
+template <typename F>
+static int by_system(int kind, F &&f)
+{
+    if (kind == DTWA_SYS_DICKE) return f(std::integral_constant<int, DTWA_SYS_DICKE>());
+    return f(std::integral_constant<int, DTWA_SYS_LMG>());
+}
+template <typename F>
+static int by_alg(int alg, F &&f)
+{
+    switch (alg) {
+    case DTWA_ALG_RK4: return f(std::integral_constant<int, DTWA_ALG_RK4>());
+    case DTWA_ALG_RK8: return f(std::integral_constant<int, DTWA_ALG_RK8>());
+    case DTWA_ALG_DP5: return f(std::integral_constant<int, DTWA_ALG_DP5>());
+    default: return f(std::integral_constant<int, DTWA_ALG_DOP853>());
+    }
+}
+
+static inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------------
+// simple batch entry points
+extern "C" int dtwa_hamiltonian(dtwa_ctx *ctx, const dtwa_system *sys, const double *u, int64_t n, double *h)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    TRY(check_system(sys));
+    if (n < 0 || (n > 0 && (!u || !h))) return set_err(DTWA_ERR_INVALID, "bad buffers");
+    if (n == 0) return DTWA_OK;
+    DevCtx &d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    const int nv = nvar_of(sys->kind);
+    TRY(d.scratch_a.ensure(sizeof(double) * n * nv));
+    TRY(d.scratch_b.ensure(sizeof(double) * n));
+    CK(cudaMemcpyAsync(d.scratch_a.p, u, sizeof(double) * n * nv, cudaMemcpyHostToDevice, d.stream));
+    if (sys->kind == DTWA_SYS_DICKE)
+        hamiltonian_kernel<DTWA_SYS_DICKE><<<blocks_for(n, 256), 256, 0, d.stream>>>(sys->params[0], sys->params[1], sys->params[2],
+                                                                                  (const double *)d.scratch_a.p, n, (double *)d.scratch_b.p);
+    else
+        hamiltonian_kernel<DTWA_SYS_LMG><<<blocks_for(n, 256), 256, 0, d.stream>>>(sys->params[0], sys->params[1], 0.0,
+                                                                                (const double *)d.scratch_a.p, n, (double *)d.scratch_b.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h, d.scratch_b.p, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    return DTWA_OK;
+}
+
+extern "C" int dtwa_sample(dtwa_ctx *ctx, const dtwa_sampler *smp, int64_t n, uint32_t attempt, double *u)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    if (!smp || n < 0 || (n > 0 && !u)) return set_err(DTWA_ERR_INVALID, "bad arguments");
+    if (smp->kind < DTWA_SAMPLER_COHERENT_HW || smp->kind > DTWA_SAMPLER_COHERENT_HWXSU2)
+        return set_err(DTWA_ERR_INVALID, "dtwa_sample needs a coherent_Wigner_* sampler");
+    if (!(smp->hbar > 0)) return set_err(DTWA_ERR_INVALID, "sampler needs hbar > 0");
+    if (n == 0) return DTWA_OK;
+    dtwa_system fake;
+    fake.kind = smp->kind == DTWA_SAMPLER_COHERENT_HWXSU2 ? DTWA_SYS_DICKE : DTWA_SYS_LMG;
+    SamplerPar sp;
+    TRY(make_sampler_par(&fake, smp, sp));
+    DevCtx &d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    TRY(d.scratch_a.ensure(sizeof(double) * n * sp.nv));
+    if (sp.nv == 4)
+        sample_kernel<4><<<blocks_for(n, 128), 128, 0, d.stream>>>(sp, n, attempt, (double *)d.scratch_a.p);
+    else
+        sample_kernel<2><<<blocks_for(n, 128), 128, 0, d.stream>>>(sp, n, attempt, (double *)d.scratch_a.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(u, d.scratch_a.p, sizeof(double) * n * sp.nv, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    return DTWA_OK;
+}
+
+extern "C" int dtwa_pdf(dtwa_ctx *ctx, const dtwa_sampler *smp, const double *u, int64_t n, double *w)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    if (!smp || n < 0 || (n > 0 && (!u || !w))) return set_err(DTWA_ERR_INVALID, "bad arguments");
+    if (smp->kind < DTWA_SAMPLER_COHERENT_HW || smp->kind > DTWA_SAMPLER_COHERENT_HWXSU2)
+        return set_err(DTWA_ERR_INVALID, "dtwa_pdf needs a coherent_Wigner_* sampler");
+    if (n == 0) return DTWA_OK;
+    dtwa_system fake;
+    fake.kind = smp->kind == DTWA_SAMPLER_COHERENT_HWXSU2 ? DTWA_SYS_DICKE : DTWA_SYS_LMG;
+    SamplerPar sp;
+    TRY(make_sampler_par(&fake, smp, sp));
+    DevCtx &d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    TRY(d.scratch_a.ensure(sizeof(double) * n * sp.nv));
+    TRY(d.scratch_b.ensure(sizeof(double) * n));
+    CK(cudaMemcpyAsync(d.scratch_a.p, u, sizeof(double) * n * sp.nv, cudaMemcpyHostToDevice, d.stream));
+    if (sp.nv == 4)
+        pdf_kernel<4><<<blocks_for(n, 128), 128, 0, d.stream>>>(sp, (const double *)d.scratch_a.p, n, (double *)d.scratch_b.p);
+    else
+        pdf_kernel<2><<<blocks_for(n, 128), 128, 0, d.stream>>>(sp, (const double *)d.scratch_a.p, n, (double *)d.scratch_b.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(w, d.scratch_b.p, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    return DTWA_OK;
+}
+
+extern "C" int dtwa_eval_expr(dtwa_ctx *ctx, const dtwa_system *sys, const char *expr, const double *u, int64_t n, double *v)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    TRY(check_system(sys));
+    if (!expr || n < 0 || (n > 0 && (!u || !v))) return set_err(DTWA_ERR_INVALID, "bad arguments");
+    Program prog;
+    try {
+        auto vars = varnames_of(sys->kind);
+        ExprCompiler c(vars);
+        c.compile(expr, prog);
+    } catch (const std::exception &e) {
+        return set_err(DTWA_ERR_EXPR, e.what());
+    }
+    if (prog.max_depth > VM_STACK) return set_err(DTWA_ERR_EXPR, "expression too deeply nested for the VM stack");
+    prog.emit(OP_STORE, 0, 0, -1);
+    prog.emit(OP_END);
+    if (n == 0) return DTWA_OK;
+    if (prog.consts.empty()) prog.consts.push_back(0.0);
+    DevCtx &d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    const int nv = nvar_of(sys->kind);
+    const size_t pb = sizeof(VmIns) * prog.ins.size(), cb = sizeof(double) * prog.consts.size();
+    TRY(d.scratch_a.ensure(sizeof(double) * n * nv));
+    TRY(d.scratch_b.ensure(sizeof(double) * n));
+    TRY(d.scratch_c.ensure(((cb + 15) & ~size_t(15)) + pb));
+    unsigned char *meta = (unsigned char *)d.scratch_c.p;
+    CK(cudaMemcpyAsync(meta, prog.consts.data(), cb, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(meta + ((cb + 15) & ~size_t(15)), prog.ins.data(), pb, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(d.scratch_a.p, u, sizeof(double) * n * nv, cudaMemcpyHostToDevice, d.stream));
+    const VmIns *dprog = (const VmIns *)(meta + ((cb + 15) & ~size_t(15)));
+    if (nv == 4)
+        eval_kernel<4><<<blocks_for(n, 128), 128, 0, d.stream>>>(dprog, (const double *)meta, (const double *)d.scratch_a.p, n, (double *)d.scratch_b.p);
+    else
+        eval_kernel<2><<<blocks_for(n, 128), 128, 0, d.stream>>>(dprog, (const double *)meta, (const double *)d.scratch_a.p, n, (double *)d.scratch_b.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(v, d.scratch_b.p, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    return DTWA_OK;
+}
+
+static int make_range(const dtwa_range &r, RangeD &out)
+{
+    if (r.len < 1) return set_err(DTWA_ERR_INVALID, "histogram range needs len >= 1");
+    if (!(r.stop >= r.start)) return set_err(DTWA_ERR_INVALID, "histogram range needs stop >= start");
+    out.start = r.start;
+    out.stop = r.stop;
+    out.len = r.len;
+    out.lenm1 = (double)(r.len - 1);
+    return 0;
+}
+
+extern "C" int dtwa_scale_to_index(dtwa_ctx *ctx, const double *v, int64_t n, const dtwa_range *r, int64_t *idx)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    if (!r || n < 0 || (n > 0 && (!v || !idx))) return set_err(DTWA_ERR_INVALID, "bad arguments");
+    RangeD rd;
+    TRY(make_range(*r, rd));
+    if (n == 0) return DTWA_OK;
+    DevCtx &d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    TRY(d.scratch_a.ensure(sizeof(double) * n));
+    TRY(d.scratch_b.ensure(sizeof(long long) * n));
+    CK(cudaMemcpyAsync(d.scratch_a.p, v, sizeof(double) * n, cudaMemcpyHostToDevice, d.stream));
+    bin_kernel<<<blocks_for(n, 256), 256, 0, d.stream>>>((const double *)d.scratch_a.p, n, rd, (long long *)d.scratch_b.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(idx, d.scratch_b.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    return DTWA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a7: batch integrate
+extern "C" int dtwa_integrate(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const double *u0, int64_t n,
+                              const double *ts, int32_t nt, double *out, int32_t *status, int64_t *nsteps)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    TRY(check_system(sys));
+    TRY(check_solver(sol));
+    if (n < 0 || (n > 0 && (!u0 || !out || !status))) return set_err(DTWA_ERR_INVALID, "bad buffers");
+    std::vector<StepTab> tab;
+    TRY(build_step_table(ts, nt, sol->dt, tab));
+    if (n == 0) return DTWA_OK;
+    DevCtx &d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    const int nv = nvar_of(sys->kind);
+    const size_t tab_b = sizeof(StepTab) * nt, ts_b = sizeof(double) * nt;
+    TRY(d.meta.ensure(tab_b + ts_b));
+    TRY(d.u0.ensure(sizeof(double) * n * nv));
+    TRY(d.scratch_a.ensure(sizeof(double) * (size_t)n * nt * nv));
+    TRY(d.scratch_b.ensure(sizeof(int32_t) * n));
+    TRY(d.scratch_c.ensure(sizeof(long long) * n));
+    unsigned char *meta = (unsigned char *)d.meta.p;
+    CK(cudaMemcpyAsync(meta, tab.data(), tab_b, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(meta + tab_b, ts, ts_b, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(d.u0.p, u0, sizeof(double) * n * nv, cudaMemcpyHostToDevice, d.stream));
+    const SolverArgs S = make_solver_args(sys, sol, (const StepTab *)meta, (const double *)(meta + tab_b), ts, nt);
+    const unsigned grid = blocks_for(n, 128);
+    by_system(sys->kind, [&](auto sk) {
+        return by_alg(sol->alg, [&](auto ak) {
+            integrate_kernel<decltype(sk)::value, decltype(ak)::value><<<grid, 128, 0, d.stream>>>(
+                S, (const double *)d.u0.p, n, (double *)d.scratch_a.p, (int32_t *)d.scratch_b.p, (long long *)d.scratch_c.p);
+            return 0;
+        });
+    });
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d.scratch_a.p, sizeof(double) * (size_t)n * nt * nv, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(status, d.scratch_b.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d.stream));
+    if (nsteps) CK(cudaMemcpyAsync(nsteps, d.scratch_c.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    return DTWA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a13-a20: the ensemble
+struct RedLayout {
+    int kind = 0;
+    int nexpr = 0;
+    int slot0 = 0;          // first sums slot (AVERAGE / SURVIVAL)
+    int64_t u64_off = 0;    // first counts element in the u64 arena (HIST)
+    int64_t counts_len = 0;
+};
+
+struct DevPlan {
+    DevCtx *dc = nullptr;
+    long long lo = 0, n = 0;  // this device's trajectory block
+    double *d_f64 = nullptr;
+    unsigned long long *d_u64 = nullptr;
+    int grid = 0, block = 0;
+};
+
+struct dtwa_plan {
+    dtwa_ctx *ctx = nullptr;
+    int nt = 0, nslots = 0;
+    int64_t n_f64 = 0, n_u64 = 0;
+    std::vector<RedLayout> reds;
+    std::vector<DevPlan> devs;
+    int launches = 0, rounds = 0;
+    bool fetched = false;
+};
+
+struct LaunchShape {
+    int block, grid;
+    size_t smem;
+};
+
+template <int SYS, int ALG>
+static int shape_for(dtwa_ctx *ctx, DevCtx &d, const EnsArgs &A, long long n, LaunchShape &ls)
+{
+    int block = ctx->block_threads ? ctx->block_threads : (is_fixed<ALG>::value ? 256 : 64);
+    if (block > max_block<ALG>::value) block = max_block<ALG>::value;
+    const size_t smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, block / 32);
+    auto kern = ensemble_kernel<SYS, ALG>;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
+    if (per_sm < 1) return set_err(DTWA_ERR_CAPACITY, "ensemble kernel does not fit on an SM with this reducer set");
+    if (ctx->ctas_per_sm > 0 && ctx->ctas_per_sm < per_sm) per_sm = ctx->ctas_per_sm;
+    long long want = (n + block - 1) / block;
+    long long cap = (long long)d.sm_count * per_sm;
+    ls.block = block;
+    ls.grid = (int)std::max(1ll, std::min(want, cap));
+    ls.smem = smem;
+    return 0;
+}
+
+template <int SYS, int ALG>
+static int launch_ens(DevCtx &d, const EnsArgs &A, const LaunchShape &ls)
+{
+    ensemble_kernel<SYS, ALG><<<ls.grid, ls.block, ls.smem, d.stream>>>(A);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int dispatch_shape(dtwa_ctx *ctx, DevCtx &d, int sys, int alg, const EnsArgs &A, long long n, LaunchShape &ls)
+{
+    return by_system(sys, [&](auto sk) {
+        return by_alg(alg, [&](auto ak) { return shape_for<decltype(sk)::value, decltype(ak)::value>(ctx, d, A, n, ls); });
+    });
+}
+static int dispatch_launch(DevCtx &d, int sys, int alg, const EnsArgs &A, const LaunchShape &ls)
+{
+    return by_system(sys, [&](auto sk) {
+        return by_alg(alg, [&](auto ak) { return launch_ens<decltype(sk)::value, decltype(ak)::value>(d, A, ls); });
+    });
+}
+
+extern "C" int dtwa_plan_free(dtwa_plan *plan)
+{
+    if (!plan) return DTWA_OK;
+    for (auto &dp : plan->devs) {
+        if (!dp.dc) continue;
+        cudaSetDevice(dp.dc->device);
+        cudaStreamSynchronize(dp.dc->stream);
+        if (dp.d_f64) cudaFree(dp.d_f64);
+        if (dp.d_u64) cudaFree(dp.d_u64);
+    }
+    delete plan;
+    return DTWA_OK;
+}
+
+extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const dtwa_sampler *smp,
+                                    int64_t N, const double *ts, int32_t nt, const dtwa_reducer *red, int32_t nred,
+                                    int32_t tolerate_errors, dtwa_plan **plan_out)
+{
+    if (!ctx || !plan_out) return set_err(DTWA_ERR_INVALID, "NULL context/plan");
+    *plan_out = nullptr;
+    TRY(check_system(sys));
+    TRY(check_solver(sol, /*fixed_needs_dt=*/false));
+    if (N < 1) return set_err(DTWA_ERR_INVALID, "N must be >= 1");
+    if (!red || nred < 1) return set_err(DTWA_ERR_INVALID, "at least one reducer is required");
+    SamplerPar sp0;
+    TRY(make_sampler_par(sys, smp, sp0));
+    std::vector<StepTab> tab;
+    TRY(build_step_table(ts, nt, sol->dt, tab));
+    const bool fixed = sol->alg == DTWA_ALG_RK4 || sol->alg == DTWA_ALG_RK8;
+    if (fixed && ts[nt - 1] > 0 && !(sol->dt > 0)) return set_err(DTWA_ERR_INVALID, "fixed-step algorithms need dt > 0");
+    const int ndev = (int)ctx->devs.size();
+    if (smp->kind == DTWA_SAMPLER_DEVICE_ARRAY && ndev != 1)
+        return set_err(DTWA_ERR_INVALID, "DEVICE_ARRAY sampler needs a single-device context");
+
+    // ---- reducer program + arena layout ----
+    Program prog;
+    std::vector<RangeD> ranges;
+    std::vector<HistDesc> hists;
+    std::vector<RedLayout> reds(nred);
+    int nslots = 0;
+    int64_t u64_len = CNT_N + nt;
+    int stage_bins = 0;
+    const int STAGE_BUDGET_BINS = 8192;  // x2 buffers x4 B = 64 KB of shared memory at most
+    auto vars = varnames_of(sys->kind);
+    try {
+        ExprCompiler comp(vars);
+        for (int r = 0; r < nred; ++r) {
+            const dtwa_reducer &R = red[r];
+            RedLayout &L = reds[r];
+            L.kind = R.kind;
+            if (R.kind == DTWA_RED_AVERAGE) {
+                if (R.nexpr < 1 || !R.exprs) return set_err(DTWA_ERR_INVALID, "AVERAGE reducer needs at least one expression");
+                L.nexpr = R.nexpr;
+                L.slot0 = nslots;
+                for (int i = 0; i < R.nexpr; ++i) {
+                    if (!R.exprs[i]) return set_err(DTWA_ERR_INVALID, "NULL expression");
+                    comp.compile(R.exprs[i], prog);
+                    prog.emit(OP_SUM, 0, (uint16_t)nslots++, -1);
+                }
+            } else if (R.kind == DTWA_RED_SURVIVAL) {
+                if (smp->kind < DTWA_SAMPLER_COHERENT_HW || smp->kind > DTWA_SAMPLER_COHERENT_HWXSU2)
+                    return set_err(DTWA_ERR_INVALID, "survival probability needs a coherent_Wigner_* distribution (its pdf is the observable)");
+                L.nexpr = 1;
+                L.slot0 = nslots;
+                prog.emit(OP_PDF, 0, 0, +1);
+                prog.emit(OP_SUM, 0, (uint16_t)nslots++, -1);
+            } else if (R.kind == DTWA_RED_HIST) {
+                const bool xt = R.x_axis == DTWA_AXIS_TIME, yt = R.y_axis == DTWA_AXIS_TIME;
+                if (xt && yt) return set_err(DTWA_ERR_INVALID, "at most one histogram axis may be :t");
+                HistDesc H;
+                std::memset(&H, 0, sizeof(H));
+                H.staged_off = -1;
+                H.base = u64_len;
+                if (xt || yt) {
+                    const char *e = xt ? R.y_expr : R.x_expr;
+                    if (!e) return set_err(DTWA_ERR_INVALID, "histogram needs an expression for its non-time axis");
+                    RangeD rd;
+                    TRY(make_range(xt ? R.ys : R.xs, rd));
+                    if (rd.len > 0x7fffffff) return set_err(DTWA_ERR_INVALID, "histogram axis too long");
+                    comp.compile(e, prog);
+                    prog.emit(OP_BIN, 0, (uint16_t)ranges.size(), -1);
+                    ranges.push_back(rd);
+                    H.two_d = 0;
+                    H.n0 = (int32_t)rd.len;
+                    H.n1 = 1;
+                    H.tstride = rd.len;
+                    L.counts_len = (int64_t)nt * rd.len;
+                    if (stage_bins + H.n0 <= STAGE_BUDGET_BINS) {
+                        H.staged_off = stage_bins;
+                        stage_bins += H.n0;
+                    }
+                } else {
+                    if (!R.x_expr || !R.y_expr) return set_err(DTWA_ERR_INVALID, "histogram needs x and y expressions");
+                    RangeD rx, ry;
+                    TRY(make_range(R.xs, rx));
+                    TRY(make_range(R.ys, ry));
+                    if (rx.len * ry.len > 0x7fffffffll) return set_err(DTWA_ERR_INVALID, "histogram matrix too large");
+                    comp.compile(R.x_expr, prog);
+                    prog.emit(OP_BIN, 0, (uint16_t)ranges.size(), -1);
+                    ranges.push_back(rx);
+                    comp.compile(R.y_expr, prog);
+                    prog.emit(OP_BIN, 1, (uint16_t)ranges.size(), -1);
+                    ranges.push_back(ry);
+                    H.two_d = 1;
+                    H.n0 = (int32_t)rx.len;
+                    H.n1 = (int32_t)ry.len;
+                    H.tstride = R.animate ? rx.len * ry.len : 0;
+                    L.counts_len = (R.animate ? (int64_t)nt : 1) * rx.len * ry.len;
+                }
+                L.u64_off = u64_len;
+                u64_len += L.counts_len;
+                prog.emit(OP_HIST, 0, (uint16_t)hists.size());
+                hists.push_back(H);
+            } else {
+                return set_err(DTWA_ERR_INVALID, "unknown reducer kind");
+            }
+        }
+    } catch (const std::exception &e) {
+        return set_err(DTWA_ERR_EXPR, e.what());
+    }
+    prog.emit(OP_END);
+    if (prog.max_depth > VM_STACK) return set_err(DTWA_ERR_EXPR, "expression too deeply nested for the VM stack");
+    if ((int)prog.ins.size() > VM_MAX_INS || (int)prog.consts.size() > VM_MAX_CONST || (int)ranges.size() > VM_MAX_RANGE ||
+        (int)hists.size() > VM_MAX_HIST || nslots > VM_MAX_SLOTS)
+        return set_err(DTWA_ERR_CAPACITY, "reducer set exceeds the VM limits (instructions/constants/ranges/histograms/slots)");
+    if (prog.consts.empty()) prog.consts.push_back(0.0);
+
+    dtwa_plan *plan = new dtwa_plan;
+    plan->ctx = ctx;
+    plan->nt = nt;
+    plan->nslots = nslots;
+    plan->n_f64 = (int64_t)nt * std::max(nslots, 1);
+    plan->n_u64 = u64_len;
+    plan->reds = reds;
+    plan->devs.resize(ndev);
+    const int nv = nvar_of(sys->kind);
+
+    // meta blob: [consts | ranges | hists | tab | ts | prog]
+    auto al = [](size_t x) { return (x + 31) & ~size_t(31); };
+    const size_t o_c = 0, o_r = al(o_c + sizeof(double) * prog.consts.size()), o_h = al(o_r + sizeof(RangeD) * ranges.size()),
+                 o_t = al(o_h + sizeof(HistDesc) * hists.size()), o_s = al(o_t + sizeof(StepTab) * nt),
+                 o_p = al(o_s + sizeof(double) * nt), meta_b = al(o_p + sizeof(VmIns) * prog.ins.size());
+    std::vector<unsigned char> blob(meta_b, 0);
+    std::memcpy(blob.data() + o_c, prog.consts.data(), sizeof(double) * prog.consts.size());
+    if (!ranges.empty()) std::memcpy(blob.data() + o_r, ranges.data(), sizeof(RangeD) * ranges.size());
+    if (!hists.empty()) std::memcpy(blob.data() + o_h, hists.data(), sizeof(HistDesc) * hists.size());
+    std::memcpy(blob.data() + o_t, tab.data(), sizeof(StepTab) * nt);
+    std::memcpy(blob.data() + o_s, ts, sizeof(double) * nt);
+    std::memcpy(blob.data() + o_p, prog.ins.data(), sizeof(VmIns) * prog.ins.size());
+
+    const long long per = (N + ndev - 1) / ndev;
+    int rc = 0;
+    std::vector<EnsArgs> args(ndev);
+    std::vector<LaunchShape> shapes(ndev);
+    std::vector<unsigned *> fail_counts(ndev, nullptr);
+    std::vector<unsigned> fail_caps(ndev, 0);
+
+    // ---- phase 1: main pass on every device (asynchronous) ----
+    for (int di = 0; di < ndev && !rc; ++di) {
+        DevCtx &d = ctx->devs[di];
+        DevPlan &dp = plan->devs[di];
+        dp.dc = &d;
+        dp.lo = std::min<long long>(N, per * di);
+        dp.n = std::min<long long>(N, per * (di + 1)) - dp.lo;
+        auto body = [&]() -> int {
+            CK(cudaSetDevice(d.device));
+            CK(cudaEventRecord(d.ev[0], d.stream));
+            CK(cudaMalloc(&dp.d_f64, sizeof(double) * plan->n_f64));
+            CK(cudaMalloc(&dp.d_u64, sizeof(unsigned long long) * plan->n_u64));
+            CK(cudaMemsetAsync(dp.d_f64, 0, sizeof(double) * plan->n_f64, d.stream));
+            CK(cudaMemsetAsync(dp.d_u64, 0, sizeof(unsigned long long) * plan->n_u64, d.stream));
+            if (dp.n == 0) {
+                CK(cudaEventRecord(d.ev[1], d.stream));
+                CK(cudaEventRecord(d.ev[2], d.stream));
+                return 0;
+            }
+            TRY(d.meta.ensure(meta_b));
+            CK(cudaMemcpyAsync(d.meta.p, blob.data(), meta_b, cudaMemcpyHostToDevice, d.stream));
+            unsigned char *m = (unsigned char *)d.meta.p;
+            EnsArgs &A = args[di];
+            std::memset(&A, 0, sizeof(A));
+            A.S = make_solver_args(sys, sol, (const StepTab *)(m + o_t), (const double *)(m + o_s), ts, nt);
+            A.smp = sp0;
+            A.smp.offset = smp->offset + (uint64_t)dp.lo;
+            if (smp->kind == DTWA_SAMPLER_HOST_ARRAY) {
+                TRY(d.u0.ensure(sizeof(double) * dp.n * nv));
+                CK(cudaMemcpyAsync(d.u0.p, smp->u0 + dp.lo * nv, sizeof(double) * dp.n * nv, cudaMemcpyHostToDevice, d.stream));
+                A.smp.u0 = (const double *)d.u0.p;
+            } else if (smp->kind == DTWA_SAMPLER_DEVICE_ARRAY) {
+                A.smp.u0 = smp->u0;
+            }
+            A.N = dp.n;
+            A.attempt = 0;
+            A.nslots = nslots;
+            A.nins = (int)prog.ins.size();
+            A.ncst = (int)prog.consts.size();
+            A.nrange = (int)ranges.size();
+            A.nhist = (int)hists.size();
+            A.stage_bins = stage_bins;
+            A.redo = nullptr;
+            const bool can_redo = tolerate_errors && smp->kind != DTWA_SAMPLER_HOST_ARRAY && smp->kind != DTWA_SAMPLER_DEVICE_ARRAY;
+            fail_caps[di] = (unsigned)std::min<long long>(dp.n, 1ll << 22);
+            TRY(d.fail[0].ensure(sizeof(FailRec) * fail_caps[di] + 16));
+            TRY(d.fail[1].ensure(sizeof(FailRec) * fail_caps[di] + 16));
+            // fail buffers: [count (16 B) | records]
+            CK(cudaMemsetAsync(d.fail[0].p, 0, 16, d.stream));
+            A.fail_count = (unsigned *)d.fail[0].p;
+            A.fail_out = can_redo ? (FailRec *)((unsigned char *)d.fail[0].p + 16) : nullptr;
+            A.fail_cap = fail_caps[di];
+            A.prog = (const VmIns *)(m + o_p);
+            A.consts = (const double *)(m + o_c);
+            A.ranges = (const RangeD *)(m + o_r);
+            A.hists = (const HistDesc *)(m + o_h);
+            A.u64 = dp.d_u64;
+            TRY(dispatch_shape(ctx, d, sys->kind, sol->alg, A, dp.n, shapes[di]));
+            dp.grid = shapes[di].grid;
+            dp.block = shapes[di].block;
+            const size_t pbytes = sizeof(double) * (size_t)dp.grid * nt * std::max(nslots, 1);
+            TRY(d.partial.ensure(pbytes));
+            CK(cudaMemsetAsync(d.partial.p, 0, pbytes, d.stream));
+            A.partial = (double *)d.partial.p;
+            CK(cudaEventRecord(d.ev[1], d.stream));
+            TRY(dispatch_launch(d, sys->kind, sol->alg, A, shapes[di]));
+            plan->launches++;
+            return 0;
+        };
+        rc = body();
+    }
+
+    // ---- phase 2: resampling rounds (src/TWA.jl:186-209) + fixed-order merge of the partial sums ----
+    for (int di = 0; di < ndev && !rc; ++di) {
+        DevCtx &d = ctx->devs[di];
+        DevPlan &dp = plan->devs[di];
+        if (dp.n == 0) continue;
+        auto body = [&]() -> int {
+            CK(cudaSetDevice(d.device));
+            EnsArgs A = args[di];
+            int cur = 0;
+            for (int round = 1;; ++round) {
+                unsigned cnt = 0;
+                CK(cudaMemcpyAsync(&cnt, d.fail[cur].p, sizeof(unsigned), cudaMemcpyDeviceToHost, d.stream));
+                CK(cudaStreamSynchronize(d.stream));
+                if (!A.fail_out) {
+                    if (cnt && !tolerate_errors)
+                        return set_err(DTWA_ERR_BOUNDS, "a trajectory left the domain (DomainError in the reference) and tolerate_errors=false");
+                    break;
+                }
+                if (cnt == 0) break;
+                if (cnt > fail_caps[di]) cnt = fail_caps[di];
+                if (round > 100) return set_err(DTWA_ERR_TOO_MANY_FAILURES, "Too many errors: a trajectory failed in more than 100 consecutive resampling rounds");
+                // sort the failure list by trajectory index so that the round is reproducible
+                std::vector<FailRec> recs(cnt);
+                CK(cudaMemcpyAsync(recs.data(), (unsigned char *)d.fail[cur].p + 16, sizeof(FailRec) * cnt, cudaMemcpyDeviceToHost, d.stream));
+                CK(cudaStreamSynchronize(d.stream));
+                std::sort(recs.begin(), recs.end(), [](const FailRec &a, const FailRec &b) { return a.idx < b.idx; });
+                CK(cudaMemcpyAsync((unsigned char *)d.fail[cur].p + 16, recs.data(), sizeof(FailRec) * cnt, cudaMemcpyHostToDevice, d.stream));
+                const int nxt = cur ^ 1;
+                CK(cudaMemsetAsync(d.fail[nxt].p, 0, 16, d.stream));
+                A.redo = (const FailRec *)((unsigned char *)d.fail[cur].p + 16);
+                A.fail_count = (unsigned *)d.fail[nxt].p;
+                A.fail_out = (FailRec *)((unsigned char *)d.fail[nxt].p + 16);
+                A.N = cnt;
+                A.attempt = (uint32_t)round;
+                LaunchShape ls = shapes[di];
+                ls.grid = (int)std::max(1ll, std::min<long long>((cnt + ls.block - 1) / ls.block, shapes[di].grid));
+                TRY(dispatch_launch(d, sys->kind, sol->alg, A, ls));
+                CK(cudaStreamSynchronize(d.stream));  // recs must outlive the H2D copy
+                plan->launches++;
+                plan->rounds = std::max(plan->rounds, round);
+                cur = nxt;
+            }
+            if (nslots > 0) {
+                const long long nsum = (long long)nt * nslots;
+                finalize_sums_kernel<<<blocks_for(nsum, 256), 256, 0, d.stream>>>((const double *)d.partial.p, dp.grid, nsum, dp.d_f64);
+                CK(cudaGetLastError());
+                plan->launches++;
+            }
+            CK(cudaEventRecord(d.ev[2], d.stream));
+            return 0;
+        };
+        rc = body();
+    }
+
+    // ---- phase 3: one grouped all-reduce over NVLink when the context spans several devices ----
+    if (!rc && ndev > 1) {
+        NcclApi &n = ctx->nccl;
+        int r = n.GroupStart();
+        for (int di = 0; di < ndev && !r; ++di) {
+            DevPlan &dp = plan->devs[di];
+            r = n.AllReduce(dp.d_f64, dp.d_f64, (size_t)plan->n_f64, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->comms[di], dp.dc->stream);
+            if (!r)
+                r = n.AllReduce(dp.d_u64, dp.d_u64, (size_t)plan->n_u64, /*ncclUint64*/ 5, /*ncclSum*/ 0, ctx->comms[di], dp.dc->stream);
+        }
+        int r2 = n.GroupEnd();
+        if (r || r2) rc = set_err(DTWA_ERR_NCCL, std::string("ncclAllReduce: ") + n.GetErrorString(r ? r : r2));
+    }
+    if (rc) {
+        dtwa_plan_free(plan);
+        return rc;
+    }
+    *plan_out = plan;
+    return DTWA_OK;
+}
+
+extern "C" int dtwa_plan_arenas(dtwa_plan *plan, void **d_f64, int64_t *n_f64, void **d_u64, int64_t *n_u64)
+{
+    if (!plan) return set_err(DTWA_ERR_INVALID, "NULL plan");
+    if (d_f64) *d_f64 = plan->devs[0].d_f64;
+    if (n_f64) *n_f64 = plan->n_f64;
+    if (d_u64) *d_u64 = plan->devs[0].d_u64;
+    if (n_u64) *n_u64 = plan->n_u64;
+    return DTWA_OK;
+}
+
+extern "C" int dtwa_plan_fetch(dtwa_plan *plan, dtwa_result *res)
+{
+    if (!plan || !res) return set_err(DTWA_ERR_INVALID, "NULL plan/result");
+    DevPlan &dp = plan->devs[0];
+    DevCtx &d = *dp.dc;
+    CK(cudaSetDevice(d.device));
+    // validate capacities before copying anything
+    for (size_t r = 0; r < plan->reds.size(); ++r) {
+        const RedLayout &L = plan->reds[r];
+        if (!res->red) return set_err(DTWA_ERR_INVALID, "result.red is NULL");
+        const dtwa_reducer_out &o = res->red[r];
+        if (L.kind == DTWA_RED_HIST) {
+            if (!o.counts || o.counts_len < L.counts_len) return set_err(DTWA_ERR_CAPACITY, "counts buffer too small");
+        } else {
+            if (!o.sums || o.sums_len < (int64_t)plan->nt * L.nexpr) return set_err(DTWA_ERR_CAPACITY, "sums buffer too small");
+        }
+    }
+    std::vector<double> f64(plan->n_f64);
+    std::vector<unsigned long long> head(CNT_N + plan->nt);
+    CK(cudaMemcpyAsync(f64.data(), dp.d_f64, sizeof(double) * plan->n_f64, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(head.data(), dp.d_u64, sizeof(unsigned long long) * head.size(), cudaMemcpyDeviceToHost, d.stream));
+    for (size_t r = 0; r < plan->reds.size(); ++r) {
+        const RedLayout &L = plan->reds[r];
+        if (L.kind == DTWA_RED_HIST)
+            CK(cudaMemcpyAsync(res->red[r].counts, dp.d_u64 + L.u64_off, sizeof(unsigned long long) * L.counts_len, cudaMemcpyDeviceToHost, d.stream));
+    }
+    CK(cudaEventRecord(d.ev[3], d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    for (size_t r = 0; r < plan->reds.size(); ++r) {
+        const RedLayout &L = plan->reds[r];
+        if (L.kind == DTWA_RED_HIST) continue;
+        double *o = res->red[r].sums;
+        for (int k = 0; k < plan->nt; ++k)
+            for (int i = 0; i < L.nexpr; ++i) o[(size_t)k * L.nexpr + i] = f64[(size_t)k * plan->nslots + L.slot0 + i];
+    }
+    if (res->n_valid)
+        for (int k = 0; k < plan->nt; ++k) res->n_valid[k] = head[CNT_N + k];
+    res->n_failed = head[CNT_FAILED];
+    res->n_unfinished = head[CNT_UNFINISHED];
+    res->steps_accepted = head[CNT_ACC];
+    res->steps_rejected = head[CNT_REJ];
+    res->lane_steps = head[CNT_LANE];
+    res->resample_rounds = plan->rounds;
+    res->launches = plan->launches;
+    float kms = 0.f, tms = 0.f;
+    double kmax = 0.0;
+    for (auto &p : plan->devs) {  // max over devices, each timed on its own stream
+        if (!p.dc) continue;
+        cudaSetDevice(p.dc->device);
+        cudaEventSynchronize(p.dc->ev[2]);
+        float m = 0.f;
+        if (cudaEventElapsedTime(&m, p.dc->ev[1], p.dc->ev[2]) == cudaSuccess) kmax = std::max(kmax, (double)m);
+    }
+    cudaSetDevice(d.device);
+    (void)kms;
+    cudaEventElapsedTime(&tms, d.ev[0], d.ev[3]);
+    cudaGetLastError();
+    res->kernel_ms = kmax;
+    res->total_ms = tms;
+    plan->fetched = true;
+    return DTWA_OK;
+}
+
+extern "C" int dtwa_ensemble(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const dtwa_sampler *smp, int64_t N,
+                             const double *ts, int32_t nt, const dtwa_reducer *red, int32_t nred, int32_t tolerate_errors,
+                             dtwa_result *res)
+{
+    if (!res) return set_err(DTWA_ERR_INVALID, "result is NULL");
+    dtwa_plan *plan = nullptr;
+    TRY(dtwa_ensemble_launch(ctx, sys, sol, smp, N, ts, nt, red, nred, tolerate_errors, &plan));
+    int rc = dtwa_plan_fetch(plan, res);
+    dtwa_plan_free(plan);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int dtwa_fp64_peak(dtwa_ctx *ctx, double *tflops, double *ms_out)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    DevCtx &d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    const int block = 256, grid = d.sm_count * 8, iters = 4096;
+    TRY(d.scratch_a.ensure(sizeof(double) * (size_t)grid * block));
+    double best = 1e30;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(d.ev[0], d.stream));
+        fp64_peak_kernel<<<grid, block, 0, d.stream>>>((double *)d.scratch_a.p, iters, 0.999999, 1e-7);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(d.ev[3], d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+        float m = 0.f;
+        CK(cudaEventElapsedTime(&m, d.ev[0], d.ev[3]));
+        if (rep > 0 && m < best) best = m;
+    }
+    const double flops = (double)grid * block * (double)iters * 64.0 * 2.0;
+    if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return DTWA_OK;
+}

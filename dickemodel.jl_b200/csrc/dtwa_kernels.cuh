@@ -1,0 +1,529 @@
+// dtwa_kernels.cuh -- the sm_100a kernels of libdicketwa.
+//
+//   K1/K2 ensemble_kernel<SYS,ALG>   sample -> integrate -> observables -> per-time reduction, fused
+//                                    (replaces src/TWA.jl:163-213 + src/ClassicalSystems.jl:135-138 +
+//                                    the reducers src/TWA.jl:336-370,413-491,652-668)
+//   K3    integrate_kernel<SYS,ALG>  many independent trajectories, dense [n][nt][nvar] output
+//                                    (src/ClassicalSystems.jl:78-140)
+//   K4    the ts == [0.0] path is the same ensemble kernel with an all-zero step table
+//                                    (src/TWA.jl:177,187-188)
+//   K0    fp64_peak_kernel           DFMA-chain micro-benchmark, the roofline denominator
+//   aux   finalize_sums_kernel (fixed-order merge of per-CTA partial sums), sample/pdf/eval/bin hooks
+#pragma once
+#include <type_traits>
+#include "dtwa_device.cuh"
+
+namespace dtwa {
+
+constexpr int ST_OK = DTWA_TRAJ_OK, ST_DOMAIN = DTWA_TRAJ_DOMAIN, ST_MAXITERS = DTWA_TRAJ_MAXITERS,
+              ST_BAD_IC = DTWA_TRAJ_BAD_IC, ST_INACTIVE = 4;
+
+struct SolverArgs {
+    SysPar par;
+    const StepTab *tab;  // [nt] fixed-step table
+    const double *ts;    // [nt]
+    double tol, dtmin, tend;
+    long long maxiters;
+    int32_t nt;
+    int32_t pad;
+};
+
+template <int ALG>
+struct is_fixed {
+    static constexpr bool value = (ALG == DTWA_ALG_RK4 || ALG == DTWA_ALG_RK8);
+};
+struct Empty {};
+
+// One trajectory in registers.
+template <int SYS, int ALG>
+struct Traj {
+    static constexpr int NV = Sys<SYS>::NV;
+    static constexpr bool FIXED = is_fixed<ALG>::value;
+    double u[NV];
+    int status;
+    uint32_t nacc, nrej;
+    typename std::conditional<FIXED, Empty, Adaptive<SYS, ALG>>::type ad;
+
+    __device__ __forceinline__ void begin(const SolverArgs &S)
+    {
+        nacc = 0;
+        nrej = 0;
+        if (status == ST_OK && state_bad<SYS>(u)) status = ST_BAD_IC;
+        if constexpr (!FIXED) {
+            if (status == ST_OK) ad.init(S.par, u, S.tend, S.tol);
+        }
+    }
+
+    // integrate from the previous output time to ts[k]; returns the number of step iterations
+    // this lane executed (for the lane-efficiency counter)
+    __device__ __forceinline__ uint32_t advance(const SolverArgs &S, int k)
+    {
+        if constexpr (FIXED) {
+            const StepTab r = S.tab[k];
+#pragma unroll 1
+            for (int s = 0; s < r.n; ++s) {
+                if constexpr (ALG == DTWA_ALG_RK4)
+                    rk4_step<SYS>(S.par, u, r.h, r.hh, r.h3, r.h6);
+                else
+                    rk8_step<SYS>(S.par, u, r.h);
+            }
+            if (status == ST_OK) nacc += (uint32_t)r.n;
+            return (uint32_t)r.n;
+        } else {
+            uint32_t iters = 0;
+            if (status == ST_OK) {
+                const double tstop = S.ts[k];
+#pragma unroll 1
+                while (ad.t < tstop) {
+                    if ((long long)(nacc + nrej) >= S.maxiters) {
+                        status = ST_MAXITERS;
+                        break;
+                    }
+                    bool accepted;
+                    const int f = ad.attempt(S.par, u, tstop, S.tol, S.dtmin, accepted);
+                    ++iters;
+                    if (f) {
+                        status = ST_DOMAIN;
+                        break;
+                    }
+                    if (accepted)
+                        ++nacc;
+                    else
+                        ++nrej;
+                }
+            }
+            return iters;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+struct FailRec {
+    uint64_t idx;  // trajectory index relative to the sampler offset
+    int32_t k;     // output index at which it failed
+    int32_t pad;
+};
+
+struct HistDesc {
+    int32_t two_d;       // 0: one expression axis (index register 0) against time; 1: two expression axes
+    int32_t staged_off;  // offset (u32 elements) of the per-CTA shared-memory staging bins, -1 = straight to global
+    int64_t base;        // element offset in the u64 arena
+    int64_t tstride;     // elements per output time (0: all times share one matrix)
+    int32_t n0, n1;      // bins along index register 0 (x) / 1 (y)
+};
+
+// counters at the head of the u64 arena
+enum { CNT_ACC = 0, CNT_REJ, CNT_LANE, CNT_FAILED, CNT_UNFINISHED, CNT_RESERVED5, CNT_RESERVED6, CNT_RESERVED7, CNT_N };
+
+struct EnsArgs {
+    SolverArgs S;
+    SamplerPar smp;
+    long long N;       // trajectories in this launch
+    uint32_t attempt;  // resampling round (0 = first draw)
+    int32_t nslots, nins, ncst, nrange, nhist, stage_bins;
+    const FailRec *redo;  // NULL in the main pass; else trajectory j re-draws redo[j].idx and contributes from redo[j].k
+    FailRec *fail_out;
+    unsigned *fail_count;
+    unsigned fail_cap;
+    const VmIns *prog;
+    const double *consts;
+    const RangeD *ranges;
+    const HistDesc *hists;
+    double *partial;          // [grid][nt][nslots]
+    unsigned long long *u64;  // [CNT_N | n_valid[nt] | histograms...]
+};
+
+struct VmShared {
+    const double *consts;
+    const RangeD *ranges;
+    const HistDesc *hists;
+    const VmIns *prog;
+    double *wsum;        // [2][nwarps][nslots]
+    unsigned *stage;     // [2][stage_bins]
+    unsigned *nvalid;    // [2]
+    int nslots, stage_bins, nwarps;
+};
+
+__host__ __device__ inline size_t ens_smem_bytes(int ncst, int nrange, int nhist, int nslots, int stage_bins, int nins,
+                                                 int nwarps)
+{
+    size_t b = 0;
+    b += sizeof(double) * (size_t)ncst;
+    b += sizeof(RangeD) * (size_t)nrange;
+    b += sizeof(HistDesc) * (size_t)nhist;
+    b += sizeof(double) * 2 * (size_t)nwarps * (size_t)(nslots > 0 ? nslots : 1);
+    b += sizeof(unsigned) * 2 * (size_t)stage_bins;
+    b += sizeof(unsigned) * 2;
+    b += sizeof(VmIns) * (size_t)nins;
+    return (b + 15) & ~size_t(15);
+}
+
+// Evaluate the reducer program for one thread at output index k.  Control flow is uniform across
+// the CTA (the program is shared); `valid` masks this thread's contributions.
+template <int NV>
+__device__ __noinline__ void vm_run(const VmShared V, const SamplerPar *smp, unsigned long long *u64, double x0,
+                                    double x1, double x2, double x3, bool valid, int k, int buf, double *store_out)
+{
+    double st[VM_STACK];
+    double acc = 0.0;
+    int sp = 0;  // number of values below acc
+    long long ireg0 = 0, ireg1 = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int pc = 0;; ++pc) {
+        const VmIns in = V.prog[pc];
+        if (in.op == OP_END) break;
+        switch (in.op) {
+        case OP_VAR:
+            st[sp++] = acc;
+            acc = (in.a == 0) ? x0 : (in.a == 1) ? x1 : (in.a == 2) ? x2 : x3;
+            break;
+        case OP_CONST:
+            st[sp++] = acc;
+            acc = V.consts[in.b];
+            break;
+        case OP_ADD: acc = __dadd_rn(st[--sp], acc); break;
+        case OP_SUB: acc = __dsub_rn(st[--sp], acc); break;
+        case OP_MUL: acc = __dmul_rn(st[--sp], acc); break;
+        case OP_DIV: acc = __ddiv_rn(st[--sp], acc); break;
+        case OP_NEG: acc = -acc; break;
+        case OP_IPOW: acc = ipow_rn(acc, (int)(int16_t)in.b); break;
+        case OP_POW: acc = pow(st[--sp], acc); break;
+        case OP_SQRT: acc = __dsqrt_rn(acc); break;
+        case OP_SIN: acc = sin(acc); break;
+        case OP_COS: acc = cos(acc); break;
+        case OP_TAN: acc = tan(acc); break;
+        case OP_EXP: acc = exp(acc); break;
+        case OP_LOG: acc = log(acc); break;
+        case OP_ABS: acc = fabs(acc); break;
+        case OP_ACOS: acc = acos(acc); break;
+        case OP_ASIN: acc = asin(acc); break;
+        case OP_ATAN: acc = atan(acc); break;
+        case OP_ATAN2: acc = atan2(st[--sp], acc); break;
+        case OP_MIN: acc = fmin(st[--sp], acc); break;
+        case OP_MAX: acc = fmax(st[--sp], acc); break;
+        case OP_PDF: {
+            st[sp++] = acc;
+            double uu[NV];
+            uu[0] = x0;
+            uu[1] = x1;
+            if constexpr (NV == 4) {
+                uu[2] = x2;
+                uu[3] = x3;
+            }
+            acc = pdf_eval<NV>(*smp, uu);
+            break;
+        }
+        case OP_SUM: {
+            double v = valid ? acc : 0.0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
+            if (lane == 0) V.wsum[((size_t)buf * V.nwarps + warp) * V.nslots + in.b] = v;
+            acc = st[--sp];
+            break;
+        }
+        case OP_BIN: {
+            const long long idx = scale_to_index(acc, V.ranges[in.b]);
+            if (in.a == 0)
+                ireg0 = idx;
+            else
+                ireg1 = idx;
+            acc = st[--sp];
+            break;
+        }
+        case OP_HIST: {
+            const HistDesc h = V.hists[in.b];
+            if (!h.two_d) {
+                if (valid && ireg0 > 0) {
+                    if (h.staged_off >= 0)
+                        atomicAdd(&V.stage[(size_t)buf * V.stage_bins + h.staged_off + (int)(ireg0 - 1)], 1u);
+                    else
+                        atomicAdd(&u64[h.base + (long long)k * h.tstride + (ireg0 - 1)], 1ull);
+                }
+            } else {
+                if (valid && ireg0 > 0 && ireg1 > 0)
+                    atomicAdd(&u64[h.base + (long long)k * h.tstride + (ireg1 - 1) * (long long)h.n0 + (ireg0 - 1)], 1ull);
+            }
+            break;
+        }
+        case OP_STORE:
+            if (store_out) store_out[in.b] = acc;
+            acc = st[--sp];
+            break;
+        default: break;
+        }
+    }
+}
+
+template <int ALG>
+struct max_block {  // register budget: RK4 fits 128 regs/thread, the embedded pairs want the full 255
+    static constexpr int value = (ALG == DTWA_ALG_RK4) ? 512 : 128;
+};
+
+template <int SYS, int ALG>
+__global__ void __launch_bounds__(max_block<ALG>::value) ensemble_kernel(const EnsArgs A)
+{
+    constexpr int NV = Sys<SYS>::NV;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- carve shared memory and stage the reducer program ----
+    VmShared V;
+    {
+        unsigned char *p = smem_raw;
+        double *consts = reinterpret_cast<double *>(p);
+        p += sizeof(double) * A.ncst;
+        RangeD *ranges = reinterpret_cast<RangeD *>(p);
+        p += sizeof(RangeD) * A.nrange;
+        HistDesc *hists = reinterpret_cast<HistDesc *>(p);
+        p += sizeof(HistDesc) * A.nhist;
+        V.wsum = reinterpret_cast<double *>(p);
+        p += sizeof(double) * 2 * nwarps * (A.nslots > 0 ? A.nslots : 1);
+        V.stage = reinterpret_cast<unsigned *>(p);
+        p += sizeof(unsigned) * 2 * A.stage_bins;
+        V.nvalid = reinterpret_cast<unsigned *>(p);
+        p += sizeof(unsigned) * 2;
+        VmIns *prog = reinterpret_cast<VmIns *>(p);
+        for (int i = threadIdx.x; i < A.ncst; i += blockDim.x) consts[i] = A.consts[i];
+        for (int i = threadIdx.x; i < A.nrange; i += blockDim.x) ranges[i] = A.ranges[i];
+        for (int i = threadIdx.x; i < A.nhist; i += blockDim.x) hists[i] = A.hists[i];
+        for (int i = threadIdx.x; i < A.nins; i += blockDim.x) prog[i] = A.prog[i];
+        for (int i = threadIdx.x; i < 2 * A.stage_bins; i += blockDim.x) V.stage[i] = 0u;
+        if (threadIdx.x < 2) V.nvalid[threadIdx.x] = 0u;
+        V.consts = consts;
+        V.ranges = ranges;
+        V.hists = hists;
+        V.prog = prog;
+        V.nslots = A.nslots;
+        V.stage_bins = A.stage_bins;
+        V.nwarps = nwarps;
+    }
+    __syncthreads();
+
+    const int nt = A.S.nt;
+    double *my_partial = A.partial + (size_t)blockIdx.x * nt * A.nslots;
+    unsigned long long *nvalid_g = A.u64 + CNT_N;
+
+    // ---- persistent loop over batches of blockDim.x trajectories ----
+    for (long long batch = blockIdx.x; batch * (long long)blockDim.x < A.N; batch += gridDim.x) {
+        const long long j = batch * (long long)blockDim.x + threadIdx.x;
+        const bool active = j < A.N;
+        Traj<SYS, ALG> T;
+        uint64_t idx = (uint64_t)j;
+        int start_k = 0;
+        T.status = active ? ST_OK : ST_INACTIVE;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) T.u[i] = 0.0;
+        if (active) {
+            if (A.redo) {
+                const FailRec r = A.redo[j];
+                idx = r.idx;
+                start_k = r.k;
+            }
+            draw_initial<NV>(A.smp, idx, A.attempt, T.u);
+        }
+        T.begin(A.S);
+        bool failed_reported = false;
+        uint32_t warp_iters = 0;  // max over lanes of step iterations, summed over intervals
+
+        for (int k = 0; k < nt; ++k) {
+            const uint32_t it = T.advance(A.S, k);
+            if constexpr (Traj<SYS, ALG>::FIXED)
+                warp_iters += it;
+            else
+                warp_iters += __reduce_max_sync(0xffffffffu, it);
+            if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
+            if ((T.status == ST_DOMAIN || T.status == ST_BAD_IC) && !failed_reported) {
+                failed_reported = true;
+                atomicAdd(&A.u64[CNT_FAILED], 1ull);
+                const bool can_redo = A.fail_out && A.smp.kind != DTWA_SAMPLER_HOST_ARRAY &&
+                                      A.smp.kind != DTWA_SAMPLER_DEVICE_ARRAY;
+                bool queued = false;
+                if (can_redo) {
+                    const unsigned pos = atomicAdd(A.fail_count, 1u);
+                    if (pos < A.fail_cap) {
+                        FailRec r;
+                        r.idx = idx;
+                        r.k = k;
+                        r.pad = 0;
+                        A.fail_out[pos] = r;
+                        queued = true;
+                    }
+                }
+                if (!queued) atomicAdd(&A.u64[CNT_UNFINISHED], 1ull);
+            }
+            if (T.status == ST_MAXITERS && !failed_reported) {
+                failed_reported = true;
+                atomicAdd(&A.u64[CNT_UNFINISHED], 1ull);
+            }
+            const bool valid = (T.status == ST_OK) && (k >= start_k);
+            const int buf = k & 1;
+            // observables + reducers
+            vm_run<NV>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0, valid, k,
+                       buf, nullptr);
+            const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
+            if (lane == 0 && nv) atomicAdd(&V.nvalid[buf], nv);
+            __syncthreads();
+            // flush this output's staging buffers (double-buffered by parity: no second barrier)
+            for (int sl = threadIdx.x; sl < A.nslots; sl += blockDim.x) {
+                double s = 0.0;
+                for (int w = 0; w < nwarps; ++w) s = __dadd_rn(s, V.wsum[((size_t)buf * nwarps + w) * A.nslots + sl]);
+                atomicAdd(&my_partial[(size_t)k * A.nslots + sl], s);  // only this thread ever adds here: ordered, deterministic
+            }
+            if (threadIdx.x == blockDim.x - 1) {
+                const unsigned c = V.nvalid[buf];
+                if (c) {
+                    atomicAdd(&nvalid_g[k], (unsigned long long)c);
+                    V.nvalid[buf] = 0u;
+                }
+            }
+            for (int hI = 0; hI < A.nhist; ++hI) {
+                const HistDesc h = V.hists[hI];
+                if (h.staged_off < 0) continue;
+                unsigned *sb = V.stage + (size_t)buf * A.stage_bins + h.staged_off;
+                for (int i = threadIdx.x; i < h.n0; i += blockDim.x) {
+                    const unsigned c = sb[i];
+                    if (c) {
+                        atomicAdd(&A.u64[h.base + (long long)k * h.tstride + i], (unsigned long long)c);
+                        sb[i] = 0u;
+                    }
+                }
+            }
+        }
+        // ---- step counters: one atomic per warp per batch ----
+        const unsigned long long a = __reduce_add_sync(0xffffffffu, T.nacc);
+        const unsigned long long r = __reduce_add_sync(0xffffffffu, T.nrej);
+        if (lane == 0) {
+            atomicAdd(&A.u64[CNT_ACC], a);
+            if (r) atomicAdd(&A.u64[CNT_REJ], r);
+            atomicAdd(&A.u64[CNT_LANE], 32ull * warp_iters);
+        }
+    }
+}
+
+// partial[grid][n] -> out[n], CTA order fixed => run-to-run reproducible sums
+__global__ void finalize_sums_kernel(const double *__restrict__ partial, int grid, long long n, double *__restrict__ out)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int c = 0; c < grid; ++c) s = __dadd_rn(s, partial[(size_t)c * n + i]);
+    out[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: dense trajectories
+template <int SYS, int ALG>
+__global__ void __launch_bounds__(128) integrate_kernel(const SolverArgs S, const double *__restrict__ u0, long long n,
+                                                        double *__restrict__ out, int32_t *__restrict__ status,
+                                                        long long *__restrict__ nsteps)
+{
+    constexpr int NV = Sys<SYS>::NV;
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    Traj<SYS, ALG> T;
+    T.status = ST_OK;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) T.u[i] = u0[j * NV + i];
+    T.begin(S);
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    for (int k = 0; k < S.nt; ++k) {
+        T.advance(S, k);
+        if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
+        double *o = out + ((size_t)j * S.nt + k) * NV;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) o[i] = (T.status == ST_OK) ? T.u[i] : qnan;
+    }
+    status[j] = T.status;
+    if (nsteps) nsteps[j] = (long long)T.nacc + (long long)T.nrej;
+}
+
+// ------------------------------------------------------------------------------------------------
+// hooks
+template <int NV>
+__global__ void sample_kernel(const SamplerPar sp, long long n, uint32_t attempt, double *__restrict__ u)
+{
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double x[NV];
+    draw_initial<NV>(sp, (uint64_t)j, attempt, x);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) u[j * NV + i] = x[i];
+}
+
+template <int NV>
+__global__ void pdf_kernel(const SamplerPar sp, const double *__restrict__ u, long long n, double *__restrict__ w)
+{
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double x[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) x[i] = u[j * NV + i];
+    w[j] = pdf_eval<NV>(sp, x);
+}
+
+template <int SYS>
+__global__ void hamiltonian_kernel(const double p0, const double p1, const double p2, const double *__restrict__ u,
+                                   long long n, double *__restrict__ h)
+{
+    constexpr int NV = Sys<SYS>::NV;
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double par[3] = {p0, p1, p2};
+    double x[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) x[i] = u[j * NV + i];
+    h[j] = Sys<SYS>::hamiltonian(par, x);
+}
+
+// expression evaluation through the same VM as the ensemble kernel (program: <expr> OP_STORE 0 OP_END)
+template <int NV>
+__global__ void eval_kernel(const VmIns *__restrict__ prog, const double *__restrict__ consts, const double *__restrict__ u,
+                            long long n, double *__restrict__ v)
+{
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    VmShared V = {};
+    V.consts = consts;
+    V.prog = prog;
+    double x[4] = {0, 0, 0, 0};
+    if (j < n) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) x[i] = u[j * NV + i];
+    }
+    double outv = 0.0;
+    vm_run<NV>(V, nullptr, nullptr, x[0], x[1], x[2], x[3], j < n, 0, 0, &outv);
+    if (j < n) v[j] = outv;
+}
+
+__global__ void bin_kernel(const double *__restrict__ v, long long n, const RangeD r, long long *__restrict__ idx)
+{
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    idx[j] = scale_to_index(v[j], r);
+}
+
+// K0: 8 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+           x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            x0 = fma(x0, a, b);
+            x1 = fma(x1, a, b);
+            x2 = fma(x2, a, b);
+            x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b);
+            x5 = fma(x5, a, b);
+            x6 = fma(x6, a, b);
+            x7 = fma(x7, a, b);
+        }
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace dtwa

@@ -92,7 +92,7 @@ double orc_hamiltonian(int kind, const double *par, const double *u)
     } else {
         double Om = par[0], xi = par[1];
         double Q = u[0], P = u[1];
-        return Om * (Q * Q + P * P) / 2 + xi * (Q * Q - P * P * Q * Q / 4 - Q * Q * Q * Q / 4) - Om;
+        return Om * (Q * Q + P * P) / 2 + xi * (Q * Q - (P * P) * (Q * Q) / 4 - (Q * Q) * (Q * Q) / 4) - Om; /* x^4 = (x*x)*(x*x), DESIGN.md */
     }
 }
 

@@ -1,0 +1,195 @@
+"""The fused ensemble kernel through the reference-shaped Python API, against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+DPAR = [1.0, 1.0, 1.0]
+DOCS_PT = [1.0, 0.31783724519578205, 1.0, 0.0]
+
+
+@pytest.fixture(scope="module")
+def mods(pkg):
+    from dickemodel_jl_b200 import TWA, ClassicalDicke, ClassicalLMG, ClassicalSystems
+    return TWA, ClassicalDicke, ClassicalLMG, ClassicalSystems
+
+
+def test_average_matches_oracle_on_host_supplied_ics(ctx, mods, O):
+    TWA, CD, _, _ = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    j, N = 100, 3000
+    u0 = O.sample(O.SAMPLER_HWXSU2, [0, 0, 0, 0], 1 / j, N, seed=21)
+    ts = TWA.jrange(0, 0.05, 10)
+    obs = [TWA.Weyl.Jz(j) / j, "q", "p^2"]
+    got = TWA.average(system, observable=obs, N=N, ts=ts, distribution=TWA.samples_from_array(u0, j=j), integrator_alg="RK4", dt=2.0 ** -7)
+    traj, st, acc, _ = O.integrate(O.SYS_DICKE, DPAR, u0, np.asarray(ts), alg=O.ALG_RK4, dt=2.0 ** -7)
+    assert (st == 0).all()
+    valid = np.isfinite(traj).all(axis=2)
+    for i, e in enumerate(obs):
+        want = O.average_sums(O.eval_expr(str(e), O.varnames(0), traj), valid) / N
+        assert np.abs(got[:, i] - want).max() < 1e-10, e
+    assert TWA.last_info["steps_accepted"] == int(acc.sum())
+    assert (TWA.last_info["n_valid"] == N).all() and TWA.last_info["n_failed"] == 0
+    # scalar observable -> vector of scalars (src/TWA.jl:363-365)
+    one = TWA.average(system, observable=obs[0], N=N, ts=ts, distribution=TWA.samples_from_array(u0, j=j), integrator_alg="RK4", dt=2.0 ** -7)
+    assert one.shape == (len(ts),) and np.array_equal(one, got[:, 0])
+
+
+def test_runs_are_bitwise_reproducible(ctx, mods):
+    TWA, CD, _, _ = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    a = TWA.average(system, observable=TWA.Weyl.Jz(50), N=20000, ts=TWA.jrange(0, 0.5, 5), distribution=TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=50, seed=5), integrator_alg="RK4", dt=0.01)
+    b = TWA.average(system, observable=TWA.Weyl.Jz(50), N=20000, ts=TWA.jrange(0, 0.5, 5), distribution=TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=50, seed=5), integrator_alg="RK4", dt=0.01)
+    assert np.array_equal(a, b)
+
+
+def test_histograms_bit_exact_given_identical_trajectories(ctx, mods, O, pkg):
+    """counts from the fused kernel == oracle binning of the states dtwa_integrate reports for the
+    same initial conditions (both kernels run the same stepper instruction sequence)"""
+    TWA, CD, _, CS = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    j, N = 100, 4000
+    u0 = O.sample(O.SAMPLER_HWXSU2, DOCS_PT, 1 / j, N, seed=33)
+    ts = TWA.jrange(0, 0.1, 8)
+    jz = TWA.Weyl.Jz(j) / j
+    ys, qs, ps = TWA.jrange(-1.1, 0.01, 1.1), TWA.jrange(-4.3, 0.02, 4.3), TWA.jrange(-2.4, 0.02, 2.4)
+    mk = lambda **kw: TWA.mcs_for_distributions(system, N=N, distribution=dist, ts=ts, **kw)
+    dist = TWA.samples_from_array(u0, j=j)
+    chain = TWA.mcs_chain(mk(x="t", y=jz, ys=ys), mk(y="t", x="q", xs=qs), mk(x="q", xs=qs, y="p", ys=ps),
+                          mk(x="q", xs=qs, y="p", ys=ps, animate=True))
+    m_jz, m_q, m_qp, m_anim = TWA.monte_carlo_integrate(system, chain, integrator_alg="RK4", dt=2.0 ** -7)
+    traj, st, _ = CS.integrate_batch(system, u0, np.asarray(ts), integrator_alg="RK4", dt=2.0 ** -7)
+    valid = (st == 0)[:, None] & np.isfinite(traj).all(axis=2)
+    vjz = O.eval_expr(str(jz), O.varnames(0), traj)
+    c_jz = O.hist_time(vjz, valid, *ys.linrange())
+    c_q = O.hist_time(traj[:, :, 1], valid, *qs.linrange())
+    c_qp = O.hist_2d(traj[:, :, 1], traj[:, :, 3], valid, qs.linrange(), ps.linrange(), animate=False)
+    c_an = O.hist_2d(traj[:, :, 1], traj[:, :, 3], valid, qs.linrange(), ps.linrange(), animate=True)
+    assert m_jz.shape == (len(ys), len(ts)) and np.array_equal(m_jz, c_jz.T / N)       # [iy, i_t]  (src/TWA.jl:459)
+    assert m_q.shape == (len(ts), len(qs)) and np.array_equal(m_q, c_q / N)            # [i_t, ix]  (:466)
+    assert m_qp.shape == (len(ps), len(qs)) and np.array_equal(m_qp, c_qp / N)         # [iy, ix]   (:474)
+    assert len(m_anim) == len(ts) and all(np.array_equal(m, c / N) for m, c in zip(m_anim, c_an))
+    assert c_jz.sum() == N * len(ts)   # jz in [-1,1] always lands in -1.1:0.01:1.1
+
+
+def test_no_time_evolution_path_bit_exact(ctx, mods, O):
+    """ts == [0.0]: sample -> observable -> bin, no integration (src/TWA.jl:177,187-188); the LDoS
+    example passes the Hamiltonian closure as observable (docs/src/TWAExamples.md:369-376)"""
+    TWA, CD, _, _ = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    j, N = 1000, 50000
+    x = CD.Point(system, Q=-1, P=0, p=0, ϵ=-0.5)
+    u0 = O.sample(O.SAMPLER_HWXSU2, x, 1 / j, N, seed=8)
+    es = TWA.jrange(-0.8, 0.02, 0)
+    rho = TWA.calculate_distribution(system, distribution=TWA.samples_from_array(u0, j=j), N=N, x=CD.hamiltonian(system), xs=es)
+    assert rho.shape == (1, len(es))
+    h = O.eval_expr(TWA._expr_of(system, CD.hamiltonian(system)), O.varnames(0), u0)
+    want = O.hist_time(h[:, None], np.ones((N, 1), bool), *es.linrange())
+    assert np.array_equal(rho, want / N)
+    assert abs((rho[0] * np.asarray(es)).sum() / rho.sum() + 0.5) < 0.01      # centred on the state's energy
+
+
+def test_variance_and_fotoc_initial_value(ctx, mods, O):
+    TWA, CD, _, _ = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    j, N = 1000, 40000
+    x = CD.Point(system, Q=1, P=0, p=0, ϵ=-0.6)
+    W = TWA.coherent_Wigner_HWxSU2(x, j=j, seed=77)
+    ts = TWA.jrange(0, 0.5, 3)
+    var, mean = TWA.variance(system, observable=["Q", "q", "P", "p"], distribution=W, N=N, ts=ts, tol=1e-8, return_average=True)
+    fotoc = var.sum(axis=1)
+    assert abs(fotoc[0] - 2 / j) < 0.05 * 2 / j          # docs/src/TWAExamples.md:334
+    assert np.abs(mean[0] - x).max() < 5 * np.sqrt(1 / (2 * j) / N) + 1e-3
+    # against the oracle on the same Philox samples (adaptive DOP853 at the docs' tol)
+    u0 = O.sample(O.SAMPLER_HWXSU2, x, 1 / j, N, seed=77)
+    traj, st, _, _ = O.integrate(O.SYS_DICKE, DPAR, u0, np.asarray(ts), alg=O.ALG_DOP853, tol=1e-8)
+    assert relerr(var, traj.var(axis=0), floor=1e-6).max() < 1e-5
+    one = TWA.variance(system, observable="Q", distribution=TWA.coherent_Wigner_HWxSU2(x, j=j, seed=77), N=N, ts=ts, tol=1e-8)
+    assert one.shape == (len(ts),) and np.allclose(one, var[:, 0], rtol=1e-12)
+
+
+def test_survival_probability(ctx, mods, O):
+    TWA, CD, _, _ = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    j, N = 30, 20000
+    x = CD.Point(system, Q=1.75, P=0, p=0, ϵ=-0.5)
+    ts = np.concatenate([[0.0], 10.0 ** np.arange(-2, 0.51, 0.25)])
+    sp = TWA.survival_probability(system, distribution=TWA.coherent_Wigner_HWxSU2(x, j=j, seed=3), N=N, ts=ts, tol=1e-9)
+    # t = 0: (2 pi hbar)^2 E_W[W] = (2 pi hbar)^2 int W^2 = 1 for Gaussians of variance hbar/2 per coordinate
+    assert abs(sp[0] - 1.0) < 0.03
+    u0 = O.sample(O.SAMPLER_HWXSU2, x, 1 / j, N, seed=3)
+    traj, st, _, _ = O.integrate(O.SYS_DICKE, DPAR, u0, ts, alg=O.ALG_DOP853, tol=1e-9, backwards=True)
+    w = O.pdf(O.SAMPLER_HWXSU2, x, 1 / j, traj.reshape(-1, 4)).reshape(N, len(ts))
+    want = w.sum(axis=0) * (2 * np.pi / j) ** 2 / N
+    assert relerr(sp, want, floor=1e-4).max() < 1e-6
+
+
+def test_philox_ensemble_matches_oracle_ensemble(ctx, mods, O):
+    """fused Philox sampling: same seed => same sample set as the oracle => same sums up to rounding"""
+    TWA, CD, _, _ = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    j, N = 100, 5000
+    ts = TWA.jrange(0, 0.25, 5)
+    W = TWA.coherent_Wigner_HWxSU2([0, 0, 0, 0], j=j, seed=424242)
+    got = TWA.average(system, observable=TWA.Weyl.Jz(j) / j, N=N, ts=ts, distribution=W, integrator_alg="RK4", dt=2.0 ** -7)
+    sp = O.make_sampler(O.SAMPLER_HWXSU2, [0, 0, 0, 0], 1 / j, seed=424242)
+    c = float(np.sqrt(j * (j + 1)))
+    ref = O.ensemble(O.SYS_DICKE, DPAR, sp, N, np.asarray(ts), values=[(2, 0, c)], alg=O.ALG_RK4, dt=2.0 ** -7, workers=4)
+    assert np.abs(got - ref["sums"][:, 0] / j / N).max() < 1e-9
+    assert W.offset == N      # the next ensemble draws fresh trajectories
+    again = TWA.average(system, observable=TWA.Weyl.Jz(j) / j, N=N, ts=ts, distribution=W, integrator_alg="RK4", dt=2.0 ** -7)
+    assert not np.array_equal(again, got) and np.abs(again - got).max() < 0.05
+
+
+def test_resampling_of_failed_trajectories(ctx, mods, O):
+    """tolerate_errors (src/TWA.jl:186-209): a broad (j=20) chaotic ensemble, ~5% of whose trajectories reach the chart
+    singularity; replacements contribute from the failure index on, so every time has >= N samples"""
+    TWA, CD, _, _ = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    N = 20000
+    W = TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=20, seed=2)
+    ts = TWA.jrange(0, 0.5, 20)
+    TWA.average(system, observable="Q", N=N, ts=ts, distribution=W, integrator_alg="RK4", dt=2.0 ** -5)
+    info = TWA.last_info
+    assert info["n_failed"] > 0 and info["resample_rounds"] >= 1 and info["n_unfinished"] == 0
+    assert info["n_valid"].min() >= N
+    sp = O.make_sampler(O.SAMPLER_HWXSU2, DOCS_PT, 1 / 20, seed=2)
+    ref = O.ensemble(O.SYS_DICKE, DPAR, sp, N, np.asarray(ts), values=[(0, 0, 0.0)], alg=O.ALG_RK4, dt=2.0 ** -5, workers=1)
+    # same trajectories, same replacement draws (attempt counter), same failure indices
+    # (trajectories that graze the singularity amplify last-bit differences, so allow a few to differ)
+    assert abs(info["n_failed"] - ref["n_failed"]) <= max(3, 0.03 * ref["n_failed"])
+    assert np.abs(info["n_valid"].astype(np.int64) - ref["n_valid"].astype(np.int64)).max() <= max(3, 0.03 * ref["n_failed"])
+
+
+def test_lmg_variance_example(ctx, mods, O):
+    """docs/src/ClassicalLMGExamples.md:22-38"""
+    TWA, _, CL, _ = mods
+    system = CL.ClassicalLMGSystem(Ω=1, ξ=-1)
+    j, N = 500, 5000
+    ts = TWA.jrange(0, 0.1, 50)
+    W = TWA.coherent_Wigner_SU2([0, 0], j=j, seed=12)
+    var = TWA.variance(system, observable=["Q", "P"], N=N, ts=ts, distribution=W, integrator_alg="RK4", dt=2.0 ** -7)
+    u0 = O.sample(O.SAMPLER_SU2, [0, 0], 1 / j, N, seed=12)
+    traj, st, _, _ = O.integrate(O.SYS_LMG, [1.0, -1.0], u0, np.asarray(ts), alg=O.ALG_RK4, dt=2.0 ** -7)
+    assert (st == 0).all()
+    assert relerr(var, traj.var(axis=0), floor=1e-9).max() < 1e-6
+    assert abs(var[0].sum() - 1 / j) < 0.1 / j
+
+
+def test_single_trajectory_integrate_api(ctx, mods, O):
+    """docs/src/ClassicalDickeExamples.md:43-51"""
+    _, CD, _, CS = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    u0 = CD.Point(system, Q=1, P=1, p=0, ϵ=0.5)
+    sol = CS.integrate(system, u0, 10.0)
+    ref, st, _, _ = O.integrate(O.SYS_DICKE, DPAR, [u0], [10.0], alg=O.ALG_DOP853, tol=1e-12)
+    assert sol.retcode == "Success" and relerr(sol.u[-1], ref[0, 0]).max() < 1e-9
+    assert relerr(sol(5.0), O.integrate(O.SYS_DICKE, DPAR, [u0], [5.0], alg=O.ALG_DOP853, tol=1e-12)[0][0, 0]).max() < 1e-9
+    with pytest.raises(ValueError, match="out of bounds"):
+        CS.integrate(system, [1.5, 0, 1.5, 0], 1.0)
+    with pytest.raises(ValueError, match="negative time"):
+        CS.integrate(system, u0, -1.0)
+    with pytest.raises(ValueError, match="should have length 4"):
+        CS.integrate(system, [0.0, 0.0], 1.0)

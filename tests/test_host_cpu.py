@@ -1,0 +1,215 @@
+"""Host-side logic and the C-ABI surface, on a box without a GPU (no compute calls here)."""
+import ctypes
+import math
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    L = pkg.load_library()
+    header = open(os.path.join(ROOT, "include", "dicketwa.h")).read()
+    declared = set(re.findall(r"\b(dtwa_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(pkg._lib.EXPORTS), declared ^ set(pkg._lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.dtwa_version() == 100
+
+
+def test_struct_layouts_match_the_header(pkg):
+    lib = pkg._lib
+    assert ctypes.sizeof(lib.System) == 40 and ctypes.sizeof(lib.Solver) == 40
+    assert ctypes.sizeof(lib.Sampler) == 72 and ctypes.sizeof(lib.Range) == 24
+    assert ctypes.sizeof(lib.Reducer) == 96 and ctypes.sizeof(lib.ReducerOut) == 32
+    assert ctypes.sizeof(lib.Result) == 80
+
+
+def test_no_cpu_fallback(pkg):
+    """without a CUDA device the product fails loudly instead of computing on the host"""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(pkg.DtwaError, match="no CUDA device"):
+        pkg.Context([0])
+    from dickemodel_jl_b200 import TWA, ClassicalDicke as CD
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    with pytest.raises(pkg.DtwaError):
+        TWA.average(system, observable="Q", N=10, ts=[0.0, 1.0], distribution=TWA.coherent_Wigner_HWxSU2([0, 0, 0, 0], j=10))
+
+
+def test_product_never_imports_the_oracle():
+    """the oracle is test infrastructure: nothing under the package may import, link or load it"""
+    pk = os.path.join(ROOT, "dickemodel.jl_b200")
+    bad = re.compile(r"^\s*(from|import)\s+oracle|liboracle|oracle/_build|oracle\.c\b|\borc_[a-z]", re.M)
+    for dirpath, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".inc", ".jl")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not bad.search(txt.replace("oracle/oracle.c orc_step_table", "")), f
+
+
+def test_weyl_symbols_equal_the_oracles_strings(pkg, O):
+    """two independent renderings of src/TWA.jl:798-883 evaluate to the same bits"""
+    from dickemodel_jl_b200 import TWA
+    rng = np.random.default_rng(0)
+    u = np.column_stack([rng.uniform(-1.3, 1.3, 500), rng.normal(0, 1, 500), rng.uniform(-1.3, 1.3, 500), rng.normal(0, 1, 500)])
+    names = O.varnames(O.SYS_DICKE)
+    for j in (30, 100, 300.5):
+        for ours, theirs in ((TWA.Weyl.Jz, O.Weyl.Jz), (TWA.Weyl.Jx, O.Weyl.Jx), (TWA.Weyl.Jy, O.Weyl.Jy), (TWA.Weyl.Jz2, O.Weyl.Jz2),
+                             (TWA.Weyl.Jx2, O.Weyl.Jx2), (TWA.Weyl.Jy2, O.Weyl.Jy2), (TWA.Weyl.n, O.Weyl.n), (TWA.Weyl.n2, O.Weyl.n2)):
+            assert np.array_equal(O.eval_expr(str(ours(j)), names, u), O.eval_expr(theirs(j), names, u))
+    assert getattr(TWA.Weyl, "Jz²") is TWA.Weyl.Jz2
+    # Jz^2 + Jx^2 + Jy^2 = j(j+1) (Casimir) holds for the Weyl symbols up to rounding
+    j = 100
+    tot = sum(O.eval_expr(str(f(j)), names, u) for f in (TWA.Weyl.Jx2, TWA.Weyl.Jy2, TWA.Weyl.Jz2))
+    assert np.allclose(tot, j * (j + 1), rtol=1e-12)
+
+
+def test_observable_forms(pkg, O):
+    """src/TWA.jl:277-299: n-argument function, vector function, symbol, expression"""
+    from dickemodel_jl_b200 import TWA, ClassicalDicke as CD, symbolic
+    system = CD.ClassicalDickeSystem(w0=1.0, w=0.8, g=0.3)
+    u = np.random.default_rng(1).uniform(-1, 1, (50, 4))
+    names = system.varnames()
+    forms = [":(q+p^2-Q)", lambda Q, q, P, p: q + p ** 2 - Q, lambda x: x[1] + x[3] ** 2 - x[0]]
+    vals = [O.eval_expr(TWA._expr_of(system, f).lstrip(":"), names, u) for f in forms]
+    assert np.array_equal(vals[0], vals[1]) and np.array_equal(vals[1], vals[2])
+    H = CD.hamiltonian(system)
+    assert np.allclose(O.eval_expr(TWA._expr_of(system, H), names, u), O.hamiltonian(O.SYS_DICKE, system.parameters(), u), rtol=1e-14)
+    assert math.isclose(H(u[0]), O.hamiltonian(O.SYS_DICKE, system.parameters(), u[0])[0], rel_tol=1e-14)
+    assert "sqrt" in TWA._expr_of(system, lambda Q, q, P, p: symbolic.sqrt(4 - Q ** 2 - P ** 2))
+    with pytest.raises(ValueError, match="n-vector or n arguments"):
+        TWA._expr_of(system, lambda a, b: a + b)
+
+
+def test_julia_range_semantics(pkg):
+    from dickemodel_jl_b200 import TWA
+    r = TWA.jrange(-1.1, 0.01, 1.1)
+    assert len(r) == 221 and r.linrange() == (-1.1, 1.1, 221)
+    ts = np.asarray(TWA.jrange(0, 0.05, 100))
+    assert len(ts) == 2001 and ts[-1] == 100.0 and ts[3] == 0.15 and ts[7] == 0.35   # correctly rounded k/20, not k*0.05
+    assert len(TWA.jrange(0, 0)) == 1 and len(TWA.jrange(0, 0.3, 1)) == 4 and TWA.jrange(0, 0.3, 1).stop == 0.9
+    assert TWA._as_linrange(np.linspace(-2.4, 2.4, 241), "ys") == (-2.4, 2.4, 241)
+    with pytest.raises(ValueError):
+        TWA._as_linrange([0.0, 0.1, 0.5], "xs")
+
+
+def test_dicke_points_and_energies(pkg, O):
+    from dickemodel_jl_b200 import ClassicalDicke as CD, ClassicalLMG as CL, PhaseSpaces as PS
+    system = CD.ClassicalDickeSystem(**{"ω₀": 1.0, "ω": 1.0, "γ": 1.0})
+    assert system.parameters() == [1.0, 1.0, 1.0] and system.varnames() == ["Q", "q", "P", "p"]
+    x = CD.Point(system, Q=1, P=1, p=0, ϵ=0.5)      # docs/src/TWAExamples.md:48
+    assert math.isclose(x[1], 0.31783724519578224, rel_tol=1e-13)
+    assert math.isclose(O.hamiltonian(O.SYS_DICKE, [1, 1, 1], x)[0], 0.5, abs_tol=1e-14)
+    xm = CD.Point(system, Q=1, P=1, p=0, ϵ=0.5, sgn="-")
+    assert math.isclose(O.hamiltonian(O.SYS_DICKE, [1, 1, 1], xm)[0], 0.5, abs_tol=1e-14) and xm[1] < x[1]
+    with pytest.raises(ValueError, match="There is no q"):
+        CD.Point(system, Q=1, P=1, p=0, ϵ=-5)
+    gs = CD.minimum_energy_point(system)
+    assert math.isclose(O.hamiltonian(O.SYS_DICKE, [1, 1, 1], gs)[0], CD.minimum_energy(system), rel_tol=1e-13)
+    assert CD.minimum_energy(CD.ClassicalDickeSystem(w0=1, w=1, g=0.3)) == -1.0
+    lmg = CL.ClassicalLMGSystem(Ω=1, ξ=-1)
+    y = CL.Point(lmg, Q=0.5, ϵ=-0.4)
+    assert math.isclose(O.hamiltonian(O.SYS_LMG, [1, -1], y)[0], -0.4, abs_tol=1e-14)
+    th, ph = PS.θ_of_QP(0.3, -0.4), PS.ϕ_of_QP(0.3, -0.4)
+    assert math.isclose(PS.Q_of_θϕ(th, ph), 0.3, rel_tol=1e-12) and math.isclose(PS.P_of_θϕ(th, ph), -0.4, rel_tol=1e-12)
+    assert system.out_of_bounds([1.5, 0, 1.5, 0]) and not system.out_of_bounds([1, 0, 1, 0])
+
+
+def test_solver_keyword_mapping(pkg):
+    from dickemodel_jl_b200 import ClassicalSystems as CS
+    lib = pkg._lib
+    s = CS.solver_from_kargs({})
+    assert s.alg == lib.ALG_DOP853 and s.tol == 1e-12 and s.backwards == 0     # reference defaults (src/ClassicalSystems.jl:82-86)
+    s = CS.solver_from_kargs({"integrator_alg": CS.DP5(), "tol": 1e-8, "integate_backwards": True, "maxiters": 500})
+    assert (s.alg, s.tol, s.backwards, s.maxiters) == (lib.ALG_DP5, 1e-8, 1, 500)
+    assert CS.solver_from_kargs({"integrator_alg": "RK4", "dt": 0.01}).alg == lib.ALG_RK4
+    assert CS.solver_from_kargs({"integrator_alg": CS.DP8(), "adaptive": False, "dt": 0.1}).alg == lib.ALG_RK8
+    with pytest.raises(ValueError, match="dt > 0"):
+        CS.solver_from_kargs({"integrator_alg": "RK4"})
+    with pytest.raises(TypeError, match="unsupported solver keyword"):
+        CS.solver_from_kargs({"abstol": 1e-3})
+    with pytest.raises(NotImplementedError):
+        CS.solver_from_kargs({"get_fundamental_matrix": True})
+
+
+def test_monte_carlo_system_protocol(pkg):
+    from dickemodel_jl_b200 import TWA, ClassicalDicke as CD
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    W = TWA.coherent_Wigner_HWxSU2([0, 0, 0, 0], j=10, seed=1)
+    W2 = TWA.coherent_Wigner_HWxSU2([0, 0, 0, 0], j=10, seed=2)
+    ts = TWA.jrange(0, 1, 3)
+    a = TWA.mcs_for_averaging(system, observable="Q", ts=ts, N=10, distribution=W)
+    b = TWA.mcs_for_distributions(system, x="t", y="q", ys=TWA.jrange(-1, 0.5, 1), ts=ts, N=10, distribution=W)
+    c = TWA.mcs_chain(a, b)
+    assert len(c.f_loop) == 2 and c.N == 10
+    with pytest.raises(ValueError, match="same N"):
+        TWA.mcs_chain(a, TWA.mcs_for_averaging(system, observable="Q", ts=ts, N=11, distribution=W))
+    with pytest.raises(ValueError, match="same ts"):
+        TWA.mcs_chain(a, TWA.mcs_for_averaging(system, observable="Q", ts=TWA.jrange(0, 1, 4), N=10, distribution=W))
+    with pytest.raises(ValueError, match="same phase space distribution"):
+        TWA.mcs_chain(a, TWA.mcs_for_averaging(system, observable="Q", ts=ts, N=10, distribution=W2))
+    with pytest.raises(ValueError, match="pass :ts"):
+        TWA.mcs_for_distributions(system, x="q", xs=TWA.jrange(0, 1), y="p", ys=TWA.jrange(0, 1), N=10, distribution=W)
+    d = TWA.mcs_for_distributions(system, x="q", xs=TWA.jrange(-1, 0.5, 1), N=10, distribution=W)   # y=:t, ts=0:0 default (:417-420)
+    assert d.f_loop[0]["y_axis"] == pkg._lib.AXIS_TIME and len(d.ts) == 1
+    # finalisers: /N, scalar unwrapping, orientation
+    assert np.array_equal(a.f_final(np.full((4, 1), 20.0)), np.full(4, 2.0))
+    assert b.f_final(np.ones((4, 5), dtype=np.uint64)).shape == (5, 4)
+    v = TWA.mcs_for_variance(system, observable=["Q", "q"], ts=ts, N=10, distribution=W, return_average=True)
+    assert v.f_loop[0]["exprs"] == ["Q", "q", "(Q)^2", "(q)^2"]
+    raw = np.array([[10.0, 20.0, 30.0, 80.0]])
+    var, mean = v.f_final(raw)
+    assert np.allclose(mean, [[1.0, 2.0]]) and np.allclose(var, [[3.0 - 1.0, 8.0 - 4.0]])
+    s = TWA.mcs_for_survival_probability(system, ts=ts, N=10, distribution=W)
+    assert np.allclose(s.f_final(np.ones((4, 1))), (2 * np.pi / 10) ** 2 / 10)
+
+
+GLOO_WORKER = r'''
+import os, sys, json
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["DTWA_ROOT"])
+import __graft_entry__ as graft
+pkg = graft.load_package()
+from oracle import oracle as O
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+N, j = 600, 50
+ts = np.arange(0, 9) * 0.25
+lo, hi = pkg.distributed.shard_bounds(N, rank, world)
+sp = O.make_sampler(O.SAMPLER_HWXSU2, [1.0, 0.31783724519578205, 1.0, 0.0], 1 / j, seed=99, offset=lo)
+r = O.ensemble(O.SYS_DICKE, [1, 1, 1], sp, hi - lo, ts, values=[(2, 0, 1.0)], hists=[(0, -1.1, 1.1, 221)], alg=O.ALG_RK4, dt=2.0 ** -6)
+arrays = [r["sums"], r["counts"][0], r["n_valid"]]
+pkg.distributed.reduce_host_arrays(arrays)
+if rank == 0:
+    full = O.ensemble(O.SYS_DICKE, [1, 1, 1], O.make_sampler(O.SAMPLER_HWXSU2, [1.0, 0.31783724519578205, 1.0, 0.0], 1 / j, seed=99), N, ts,
+                      values=[(2, 0, 1.0)], hists=[(0, -1.1, 1.1, 221)], alg=O.ALG_RK4, dt=2.0 ** -6)
+    ok = bool(np.array_equal(arrays[1], full["counts"][0]) and np.array_equal(arrays[2], full["n_valid"])
+              and np.allclose(arrays[0], full["sums"], rtol=1e-12, atol=1e-12))
+    print(json.dumps({"ok": ok, "total": int(arrays[2][0])}))
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_ensemble_world_size_2_gloo(tmp_path, pkg):
+    """N > 1 path: contiguous index blocks + one all-reduce (sum) reproduce the single-rank result;
+    integer counts bit for bit.  Runs the CPU oracle per rank over gloo."""
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, DTWA_ROOT=ROOT, OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29613", str(script)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    assert '"ok": true' in line and '"total": 600' in line
+    assert pkg.distributed.shard_bounds(10, 0, 4) == (0, 3) and pkg.distributed.shard_bounds(10, 3, 4) == (9, 10)

@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""A short, ncu-friendly run of the bench workload's kernel (same system, sampler, observable,
+step size; fewer trajectories and a shorter time axis so that ~40 replays stay cheap).
+
+usage: python tools/profile_case.py [--n 1048576] [--tend 5] [--alg RK4] [--reps 2]
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=1 << 20)
+ap.add_argument("--tend", type=float, default=5.0)
+ap.add_argument("--alg", default="RK4")
+ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--block", type=int, default=0)
+ap.add_argument("--ctas-per-sm", type=int, default=0)
+ap.add_argument("--hist", action="store_true", help="config-3 style chain: jz-vs-t and q-vs-t histograms")
+ap.add_argument("--state", default="A", choices=["A", "B"])
+ap.add_argument("--tol", type=float, default=1e-8)
+a = ap.parse_args()
+pkg = graft.load_package()
+TWA, CD = pkg.TWA, pkg.ClassicalDicke
+ctx = pkg.default_context()
+if a.block or a.ctas_per_sm:
+    ctx.set_launch(a.block, a.ctas_per_sm)
+system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+j = 100
+center = [0, 0, 0, 0] if a.state == "A" else [1.0, 0.31783724519578205, 1.0, 0.0]
+ts = TWA.jrange(0, 0.05, a.tend)
+jz = TWA.Weyl.Jz(j) / j
+kw = dict(integrator_alg="RK4", dt=2.0 ** -7) if a.alg == "RK4" else dict(integrator_alg=a.alg, tol=a.tol)
+for rep in range(a.reps):
+    W = TWA.coherent_Wigner_HWxSU2(center, j=j, seed=20261019)
+    if a.hist:
+        mk = lambda **k: TWA.mcs_for_distributions(system, N=a.n, distribution=W, ts=ts, **k)
+        out = TWA.monte_carlo_integrate(system, TWA.mcs_chain(mk(x="t", y=jz, ys=TWA.jrange(-1.1, 0.01, 1.1)), mk(y="t", x="q", xs=TWA.jrange(-4.3, 0.02, 4.3))), **kw)
+    else:
+        out = TWA.average(system, observable=jz, N=a.n, ts=ts, distribution=W, **kw)
+    i = TWA.last_info
+    steps = i["steps_accepted"] + i["steps_rejected"]
+    print(f"rep {rep}: {steps} steps in {i['kernel_ms']:.3f} ms kernel = {steps / i['kernel_ms'] / 1e6:.2f} Gsteps/s; "
+          f"lane efficiency {steps / max(1, i['lane_steps']):.3f}; failed {i['n_failed']}; launches {i['launches']}")
