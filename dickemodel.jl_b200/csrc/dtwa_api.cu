@@ -454,7 +454,7 @@ extern "C" int dtwa_eval_expr(dtwa_ctx *ctx, const dtwa_system *sys, const char 
         return set_err(DTWA_ERR_EXPR, e.what());
     }
     if (prog.max_depth > VM_STACK) return set_err(DTWA_ERR_EXPR, "expression too deeply nested for the VM stack");
-    prog.emit(OP_STORE, 0, 0, -1);
+    prog.emit(OP_STORE);
     prog.emit(OP_END);
     if (n == 0) return DTWA_OK;
     if (prog.consts.empty()) prog.consts.push_back(0.0);
@@ -581,7 +581,7 @@ struct dtwa_plan {
 };
 
 struct LaunchShape {
-    int block, grid;
+    int block, grid, window;
     size_t smem;
 };
 
@@ -589,8 +589,12 @@ template <int SYS, int ALG>
 static int shape_for(dtwa_ctx *ctx, DevCtx &d, const EnsArgs &A, long long n, LaunchShape &ls)
 {
     int block = ctx->block_threads ? ctx->block_threads : (is_fixed<ALG>::value ? 256 : 64);
-    if (block > max_block<ALG>::value) block = max_block<ALG>::value;
-    const size_t smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, block / 32);
+    if (block > ens_launch<ALG>::max_threads) block = ens_launch<ALG>::max_threads;
+    // window: output times staged in shared memory between two CTA-wide flushes (<= 24 KB of staging)
+    const size_t per_out = sizeof(double) * (block / 32) * (A.nslots > 0 ? A.nslots : 1) + sizeof(unsigned) * A.stage_bins + sizeof(unsigned);
+    int window = (int)std::max<size_t>(1, std::min<size_t>({(size_t)16, (size_t)A.S.nt, (size_t)(24 * 1024) / per_out}));
+    const size_t smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, block / 32, window);
+    ls.window = window;
     auto kern = ensemble_kernel<SYS, ALG>;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -606,8 +610,10 @@ static int shape_for(dtwa_ctx *ctx, DevCtx &d, const EnsArgs &A, long long n, La
 }
 
 template <int SYS, int ALG>
-static int launch_ens(DevCtx &d, const EnsArgs &A, const LaunchShape &ls)
+static int launch_ens(DevCtx &d, const EnsArgs &A0, const LaunchShape &ls)
 {
+    EnsArgs A = A0;
+    A.window = ls.window;
     ensemble_kernel<SYS, ALG><<<ls.grid, ls.block, ls.smem, d.stream>>>(A);
     CK(cudaGetLastError());
     return 0;
@@ -683,15 +689,15 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
                 for (int i = 0; i < R.nexpr; ++i) {
                     if (!R.exprs[i]) return set_err(DTWA_ERR_INVALID, "NULL expression");
                     comp.compile(R.exprs[i], prog);
-                    prog.emit(OP_SUM, 0, (uint16_t)nslots++, -1);
+                    prog.emit(OP_SUM, 0, (uint16_t)nslots++);
                 }
             } else if (R.kind == DTWA_RED_SURVIVAL) {
                 if (smp->kind < DTWA_SAMPLER_COHERENT_HW || smp->kind > DTWA_SAMPLER_COHERENT_HWXSU2)
                     return set_err(DTWA_ERR_INVALID, "survival probability needs a coherent_Wigner_* distribution (its pdf is the observable)");
                 L.nexpr = 1;
                 L.slot0 = nslots;
-                prog.emit(OP_PDF, 0, 0, +1);
-                prog.emit(OP_SUM, 0, (uint16_t)nslots++, -1);
+                prog.emit(OP_LDPDF);
+                prog.emit(OP_SUM, 0, (uint16_t)nslots++);
             } else if (R.kind == DTWA_RED_HIST) {
                 const bool xt = R.x_axis == DTWA_AXIS_TIME, yt = R.y_axis == DTWA_AXIS_TIME;
                 if (xt && yt) return set_err(DTWA_ERR_INVALID, "at most one histogram axis may be :t");
@@ -706,7 +712,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
                     TRY(make_range(xt ? R.ys : R.xs, rd));
                     if (rd.len > 0x7fffffff) return set_err(DTWA_ERR_INVALID, "histogram axis too long");
                     comp.compile(e, prog);
-                    prog.emit(OP_BIN, 0, (uint16_t)ranges.size(), -1);
+                    prog.emit(OP_BIN, 0, (uint16_t)ranges.size());
                     ranges.push_back(rd);
                     H.two_d = 0;
                     H.n0 = (int32_t)rd.len;
@@ -724,10 +730,10 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
                     TRY(make_range(R.ys, ry));
                     if (rx.len * ry.len > 0x7fffffffll) return set_err(DTWA_ERR_INVALID, "histogram matrix too large");
                     comp.compile(R.x_expr, prog);
-                    prog.emit(OP_BIN, 0, (uint16_t)ranges.size(), -1);
+                    prog.emit(OP_BIN, 0, (uint16_t)ranges.size());
                     ranges.push_back(rx);
                     comp.compile(R.y_expr, prog);
-                    prog.emit(OP_BIN, 1, (uint16_t)ranges.size(), -1);
+                    prog.emit(OP_BIN, 1, (uint16_t)ranges.size());
                     ranges.push_back(ry);
                     H.two_d = 1;
                     H.n0 = (int32_t)rx.len;

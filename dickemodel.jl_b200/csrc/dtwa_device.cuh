@@ -481,24 +481,31 @@ __device__ __forceinline__ long long scale_to_index(double v, const RangeD &r)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Observable VM: a postfix program shared by all threads of the launch (uniform control flow).
-// Every arithmetic op is a single correctly rounded IEEE operation (no contraction), so + - * /
-// sqrt and integer powers agree bit for bit with the CPU oracle's evaluator.
+// Observable VM: an accumulator machine with a small operand stack, one program shared by all threads
+// of the launch (uniform control flow).  Every arithmetic op is a single correctly rounded IEEE
+// operation (no contraction), so + - * / sqrt and integer powers agree bit for bit with the CPU
+// oracle's evaluator.  Operand forms: stack (pop), constant table entry b, state variable a.
 enum VmOp : uint8_t {
-    OP_END = 0, OP_VAR, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_IPOW, OP_POW, OP_SQRT, OP_SIN, OP_COS,
-    OP_TAN, OP_EXP, OP_LOG, OP_ABS, OP_ACOS, OP_ASIN, OP_ATAN, OP_ATAN2, OP_MIN, OP_MAX, OP_PDF,
-    // sinks
-    OP_SUM,     // pop -> sums slot b
-    OP_BIN,     // pop -> index register a (0/1) through range b
+    OP_END = 0,
+    OP_LDV, OP_LDC, OP_LDPDF,      // acc = var a | const b | pdf of the sampling distribution at the current state
+    OP_PLDV, OP_PLDC, OP_PLDPDF,   // push acc first
+    OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_ATAN2, OP_MIN, OP_MAX,   // acc = pop() (op) acc
+    OP_ADDC, OP_SUBC, OP_RSUBC, OP_MULC, OP_DIVC, OP_RDIVC,             // acc (op) const b ; R*: const (op) acc
+    OP_ADDV, OP_SUBV, OP_RSUBV, OP_MULV, OP_DIVV, OP_RDIVV,             // acc (op) var a
+    OP_NEG, OP_SQR, OP_CUBE, OP_IPOW, OP_SQRT, OP_SIN, OP_COS, OP_TAN, OP_EXP, OP_LOG, OP_ABS, OP_ACOS, OP_ASIN, OP_ATAN,
+    // sinks (consume acc)
+    OP_SUM,     // -> sums slot b
+    OP_BIN,     // -> index register a (0/1) through range b
     OP_HIST,    // histogram b from the index register(s)
-    OP_STORE    // pop -> out[b] (dtwa_eval_expr)
+    OP_STORE    // -> out (dtwa_eval_expr)
 };
 struct VmIns {
     uint8_t op;
     uint8_t a;
     uint16_t b;
 };
-constexpr int VM_STACK = 16;
+constexpr int VM_REG_STACK = 4;    // operand stack entries held in registers
+constexpr int VM_STACK = 16;       // total operand stack depth (the rest overflows to local memory)
 constexpr int VM_MAX_INS = 1024;
 constexpr int VM_MAX_CONST = 256;
 constexpr int VM_MAX_RANGE = 32;

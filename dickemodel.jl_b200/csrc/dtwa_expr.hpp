@@ -26,7 +26,7 @@ namespace dtwa {
 struct Program {
     std::vector<VmIns> ins;
     std::vector<double> consts;
-    int depth = 0, max_depth = 0;  // values on the VM stack incl. the accumulator
+    int depth = 0, max_depth = 0;  // entries on the VM operand stack
 
     int add_const(double v)
     {
@@ -306,25 +306,62 @@ class ExprCompiler {
         n->kind = 0;
         n->val = v;
     }
-    static void gen(Node *n, Program &p)
+    static bool is_pow2(double c)
+    {
+        if (!(c > 0) || !std::isfinite(c)) return false;
+        int e;
+        const double m = std::frexp(c, &e);
+        return m == 0.5 && e > -1000 && e < 1000;
+    }
+    // Emits code that leaves the value of n in the accumulator.  `push`: the accumulator holds a live
+    // value that must be saved on the operand stack before it is overwritten.
+    static void gen(Node *n, Program &p, bool push = false)
     {
         switch (n->kind) {
-        case 0: p.emit(OP_CONST, 0, (uint16_t)p.add_const(n->val), +1); break;
-        case 1: p.emit(OP_VAR, (uint8_t)n->ivar, 0, +1); break;
+        case 0: p.emit(push ? OP_PLDC : OP_LDC, 0, (uint16_t)p.add_const(n->val), push ? +1 : 0); break;
+        case 1: p.emit(push ? OP_PLDV : OP_LDV, (uint8_t)n->ivar, 0, push ? +1 : 0); break;
+        case 5: p.emit(push ? OP_PLDPDF : OP_LDPDF, 0, 0, push ? +1 : 0); break;
         case 2:
-            gen(n->l, p);
+            gen(n->l, p, push);
             p.emit(n->op);
             break;
-        case 3:
-            gen(n->l, p);
-            gen(n->r, p);
-            p.emit(n->op, 0, 0, -1);
-            break;
         case 4:
-            gen(n->l, p);
-            p.emit(OP_IPOW, 0, (uint16_t)(int16_t)n->n);
+            gen(n->l, p, push);
+            if (n->n == 2)
+                p.emit(OP_SQR);
+            else if (n->n == 3)
+                p.emit(OP_CUBE);
+            else
+                p.emit(OP_IPOW, 0, (uint16_t)(int16_t)n->n);
             break;
-        case 5: p.emit(OP_PDF, 0, 0, +1); break;
+        case 3: {
+            Node *L = n->l, *R = n->r;
+            const uint8_t op = n->op;
+            const bool arith = (op == OP_ADD || op == OP_SUB || op == OP_MUL || op == OP_DIV);
+            if (arith && R->kind == 0) {
+                gen(L, p, push);
+                if (op == OP_DIV && is_pow2(R->val))   // x / 2^k == x * 2^-k exactly
+                    p.emit(OP_MULC, 0, (uint16_t)p.add_const(1.0 / R->val));
+                else
+                    p.emit(op == OP_ADD ? OP_ADDC : op == OP_SUB ? OP_SUBC : op == OP_MUL ? OP_MULC : OP_DIVC, 0,
+                           (uint16_t)p.add_const(R->val));
+            } else if (arith && R->kind == 1) {
+                gen(L, p, push);
+                p.emit(op == OP_ADD ? OP_ADDV : op == OP_SUB ? OP_SUBV : op == OP_MUL ? OP_MULV : OP_DIVV, (uint8_t)R->ivar);
+            } else if (arith && L->kind == 0) {   // IEEE + and * commute bit for bit
+                gen(R, p, push);
+                p.emit(op == OP_ADD ? OP_ADDC : op == OP_SUB ? OP_RSUBC : op == OP_MUL ? OP_MULC : OP_RDIVC, 0,
+                       (uint16_t)p.add_const(L->val));
+            } else if (arith && L->kind == 1) {
+                gen(R, p, push);
+                p.emit(op == OP_ADD ? OP_ADDV : op == OP_SUB ? OP_RSUBV : op == OP_MUL ? OP_MULV : OP_RDIVV, (uint8_t)L->ivar);
+            } else {
+                gen(L, p, push);
+                gen(R, p, true);
+                p.emit(op, 0, 0, -1);
+            }
+            break;
+        }
         }
     }
 };

@@ -121,6 +121,7 @@ struct EnsArgs {
     long long N;       // trajectories in this launch
     uint32_t attempt;  // resampling round (0 = first draw)
     int32_t nslots, nins, ncst, nrange, nhist, stage_bins;
+    int32_t window;    // output times staged in shared memory between two CTA-wide flushes
     const FailRec *redo;  // NULL in the main pass; else trajectory j re-draws redo[j].idx and contributes from redo[j].k
     FailRec *fail_out;
     unsigned *fail_count;
@@ -133,77 +134,75 @@ struct EnsArgs {
     unsigned long long *u64;  // [CNT_N | n_valid[nt] | histograms...]
 };
 
+// Per-CTA shared-memory view used by the reducer VM.  Staging is per WINDOW of output times:
+//   wsum  [nwarps][window][nslots]  each warp's shuffle-reduced observable sums (plain stores)
+//   stage [window][stage_bins]      1-D histogram bins (shared-memory integer atomics)
+//   nvalid[window]                  contributing trajectories per time
+// A CTA-wide barrier + flush happens once per window, not once per output time, so the warps of a
+// CTA drift by up to `window` outputs and overlap each other's reduction latency.
 struct VmShared {
     const double *consts;
     const RangeD *ranges;
     const HistDesc *hists;
     const VmIns *prog;
-    double *wsum;        // [2][nwarps][nslots]
-    unsigned *stage;     // [2][stage_bins]
-    unsigned *nvalid;    // [2]
-    int nslots, stage_bins, nwarps;
+    double *wsum;
+    unsigned *stage;
+    unsigned *nvalid;
+    int nslots, stage_bins, nwarps, window;
 };
 
 __host__ __device__ inline size_t ens_smem_bytes(int ncst, int nrange, int nhist, int nslots, int stage_bins, int nins,
-                                                 int nwarps)
+                                                 int nwarps, int window)
 {
     size_t b = 0;
     b += sizeof(double) * (size_t)ncst;
     b += sizeof(RangeD) * (size_t)nrange;
     b += sizeof(HistDesc) * (size_t)nhist;
-    b += sizeof(double) * 2 * (size_t)nwarps * (size_t)(nslots > 0 ? nslots : 1);
-    b += sizeof(unsigned) * 2 * (size_t)stage_bins;
-    b += sizeof(unsigned) * 2;
+    b += sizeof(double) * (size_t)nwarps * (size_t)window * (size_t)(nslots > 0 ? nslots : 1);
+    b += sizeof(unsigned) * (size_t)window * (size_t)stage_bins;
+    b += sizeof(unsigned) * (size_t)window;
     b += sizeof(VmIns) * (size_t)nins;
     return (b + 15) & ~size_t(15);
 }
 
-// Evaluate the reducer program for one thread at output index k.  Control flow is uniform across
-// the CTA (the program is shared); `valid` masks this thread's contributions.
+// Evaluate the reducer program for one thread at output index k (slot w of the current window).
+// Control flow is uniform across the CTA (the program is shared); `valid` masks this thread's
+// contributions.  Accumulator + 4 stack entries live in registers.
 template <int NV>
-__device__ __noinline__ void vm_run(const VmShared V, const SamplerPar *smp, unsigned long long *u64, double x0,
-                                    double x1, double x2, double x3, bool valid, int k, int buf, double *store_out)
+__device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp, unsigned long long *u64, const double x0,
+                                       const double x1, const double x2, const double x3, const bool valid, const int k,
+                                       const int w, double *store_out)
 {
-    double st[VM_STACK];
-    double acc = 0.0;
-    int sp = 0;  // number of values below acc
+    double acc = 0.0, s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    double ov[VM_STACK - VM_REG_STACK];
+    int depth = 0;
     long long ireg0 = 0, ireg1 = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#define VM_PUSH()                               \
+    do {                                        \
+        if (depth >= VM_REG_STACK) ov[depth - VM_REG_STACK] = s3; \
+        s3 = s2; s2 = s1; s1 = s0; s0 = acc;    \
+        ++depth;                                \
+    } while (0)
+#define VM_POP(dst)                             \
+    do {                                        \
+        dst = s0; s0 = s1; s1 = s2; s2 = s3;    \
+        --depth;                                \
+        if (depth >= VM_REG_STACK) s3 = ov[depth - VM_REG_STACK]; \
+    } while (0)
+#define VM_VAR(a) (((a) == 0) ? x0 : ((a) == 1) ? x1 : ((a) == 2) ? x2 : x3)
+    VmIns in = V.prog[0];
 #pragma unroll 1
-    for (int pc = 0;; ++pc) {
-        const VmIns in = V.prog[pc];
-        if (in.op == OP_END) break;
+    for (int pc = 1; in.op != OP_END; ++pc) {
+        const VmIns nxt = V.prog[pc];  // prefetch: the program always ends with OP_END
+        double t;
         switch (in.op) {
-        case OP_VAR:
-            st[sp++] = acc;
-            acc = (in.a == 0) ? x0 : (in.a == 1) ? x1 : (in.a == 2) ? x2 : x3;
-            break;
-        case OP_CONST:
-            st[sp++] = acc;
-            acc = V.consts[in.b];
-            break;
-        case OP_ADD: acc = __dadd_rn(st[--sp], acc); break;
-        case OP_SUB: acc = __dsub_rn(st[--sp], acc); break;
-        case OP_MUL: acc = __dmul_rn(st[--sp], acc); break;
-        case OP_DIV: acc = __ddiv_rn(st[--sp], acc); break;
-        case OP_NEG: acc = -acc; break;
-        case OP_IPOW: acc = ipow_rn(acc, (int)(int16_t)in.b); break;
-        case OP_POW: acc = pow(st[--sp], acc); break;
-        case OP_SQRT: acc = __dsqrt_rn(acc); break;
-        case OP_SIN: acc = sin(acc); break;
-        case OP_COS: acc = cos(acc); break;
-        case OP_TAN: acc = tan(acc); break;
-        case OP_EXP: acc = exp(acc); break;
-        case OP_LOG: acc = log(acc); break;
-        case OP_ABS: acc = fabs(acc); break;
-        case OP_ACOS: acc = acos(acc); break;
-        case OP_ASIN: acc = asin(acc); break;
-        case OP_ATAN: acc = atan(acc); break;
-        case OP_ATAN2: acc = atan2(st[--sp], acc); break;
-        case OP_MIN: acc = fmin(st[--sp], acc); break;
-        case OP_MAX: acc = fmax(st[--sp], acc); break;
-        case OP_PDF: {
-            st[sp++] = acc;
+        case OP_PLDV: VM_PUSH();
+        case OP_LDV: acc = VM_VAR(in.a); break;
+        case OP_PLDC: VM_PUSH();
+        case OP_LDC: acc = V.consts[in.b]; break;
+        case OP_PLDPDF: VM_PUSH();
+        case OP_LDPDF: {
             double uu[NV];
             uu[0] = x0;
             uu[1] = x1;
@@ -214,12 +213,45 @@ __device__ __noinline__ void vm_run(const VmShared V, const SamplerPar *smp, uns
             acc = pdf_eval<NV>(*smp, uu);
             break;
         }
+        case OP_ADD: VM_POP(t); acc = __dadd_rn(t, acc); break;
+        case OP_SUB: VM_POP(t); acc = __dsub_rn(t, acc); break;
+        case OP_MUL: VM_POP(t); acc = __dmul_rn(t, acc); break;
+        case OP_DIV: VM_POP(t); acc = __ddiv_rn(t, acc); break;
+        case OP_POW: VM_POP(t); acc = pow(t, acc); break;
+        case OP_ATAN2: VM_POP(t); acc = atan2(t, acc); break;
+        case OP_MIN: VM_POP(t); acc = fmin(t, acc); break;
+        case OP_MAX: VM_POP(t); acc = fmax(t, acc); break;
+        case OP_ADDC: acc = __dadd_rn(acc, V.consts[in.b]); break;
+        case OP_SUBC: acc = __dsub_rn(acc, V.consts[in.b]); break;
+        case OP_RSUBC: acc = __dsub_rn(V.consts[in.b], acc); break;
+        case OP_MULC: acc = __dmul_rn(acc, V.consts[in.b]); break;
+        case OP_DIVC: acc = __ddiv_rn(acc, V.consts[in.b]); break;
+        case OP_RDIVC: acc = __ddiv_rn(V.consts[in.b], acc); break;
+        case OP_ADDV: acc = __dadd_rn(acc, VM_VAR(in.a)); break;
+        case OP_SUBV: acc = __dsub_rn(acc, VM_VAR(in.a)); break;
+        case OP_RSUBV: acc = __dsub_rn(VM_VAR(in.a), acc); break;
+        case OP_MULV: acc = __dmul_rn(acc, VM_VAR(in.a)); break;
+        case OP_DIVV: acc = __ddiv_rn(acc, VM_VAR(in.a)); break;
+        case OP_RDIVV: acc = __ddiv_rn(VM_VAR(in.a), acc); break;
+        case OP_NEG: acc = -acc; break;
+        case OP_SQR: acc = __dmul_rn(acc, acc); break;
+        case OP_CUBE: acc = __dmul_rn(__dmul_rn(acc, acc), acc); break;
+        case OP_IPOW: acc = ipow_rn(acc, (int)(int16_t)in.b); break;
+        case OP_SQRT: acc = __dsqrt_rn(acc); break;
+        case OP_SIN: acc = sin(acc); break;
+        case OP_COS: acc = cos(acc); break;
+        case OP_TAN: acc = tan(acc); break;
+        case OP_EXP: acc = exp(acc); break;
+        case OP_LOG: acc = log(acc); break;
+        case OP_ABS: acc = fabs(acc); break;
+        case OP_ACOS: acc = acos(acc); break;
+        case OP_ASIN: acc = asin(acc); break;
+        case OP_ATAN: acc = atan(acc); break;
         case OP_SUM: {
             double v = valid ? acc : 0.0;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
-            if (lane == 0) V.wsum[((size_t)buf * V.nwarps + warp) * V.nslots + in.b] = v;
-            acc = st[--sp];
+            if (lane == 0) V.wsum[((size_t)warp * V.window + w) * V.nslots + in.b] = v;
             break;
         }
         case OP_BIN: {
@@ -228,7 +260,6 @@ __device__ __noinline__ void vm_run(const VmShared V, const SamplerPar *smp, uns
                 ireg0 = idx;
             else
                 ireg1 = idx;
-            acc = st[--sp];
             break;
         }
         case OP_HIST: {
@@ -236,7 +267,7 @@ __device__ __noinline__ void vm_run(const VmShared V, const SamplerPar *smp, uns
             if (!h.two_d) {
                 if (valid && ireg0 > 0) {
                     if (h.staged_off >= 0)
-                        atomicAdd(&V.stage[(size_t)buf * V.stage_bins + h.staged_off + (int)(ireg0 - 1)], 1u);
+                        atomicAdd(&V.stage[(size_t)w * V.stage_bins + h.staged_off + (int)(ireg0 - 1)], 1u);
                     else
                         atomicAdd(&u64[h.base + (long long)k * h.tstride + (ireg0 - 1)], 1ull);
                 }
@@ -247,26 +278,31 @@ __device__ __noinline__ void vm_run(const VmShared V, const SamplerPar *smp, uns
             break;
         }
         case OP_STORE:
-            if (store_out) store_out[in.b] = acc;
-            acc = st[--sp];
+            if (store_out) *store_out = acc;
             break;
         default: break;
         }
+        in = nxt;
     }
+#undef VM_PUSH
+#undef VM_POP
+#undef VM_VAR
 }
 
 template <int ALG>
-struct max_block {  // register budget: RK4 fits 128 regs/thread, the embedded pairs want the full 255
-    static constexpr int value = (ALG == DTWA_ALG_RK4) ? 512 : 128;
+struct ens_launch {  // register budget: RK4 fits 64 regs/thread (4 CTAs of 256), the embedded pairs want the full 255
+    static constexpr int max_threads = (ALG == DTWA_ALG_RK4) ? 256 : 128;
+    static constexpr int min_blocks = (ALG == DTWA_ALG_RK4) ? 4 : 1;
 };
 
 template <int SYS, int ALG>
-__global__ void __launch_bounds__(max_block<ALG>::value) ensemble_kernel(const EnsArgs A)
+__global__ void __launch_bounds__(ens_launch<ALG>::max_threads, ens_launch<ALG>::min_blocks) ensemble_kernel(const EnsArgs A)
 {
     constexpr int NV = Sys<SYS>::NV;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nwarps = blockDim.x >> 5;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int W = A.window;
 
     // ---- carve shared memory and stage the reducer program ----
     VmShared V;
@@ -279,18 +315,18 @@ __global__ void __launch_bounds__(max_block<ALG>::value) ensemble_kernel(const E
         HistDesc *hists = reinterpret_cast<HistDesc *>(p);
         p += sizeof(HistDesc) * A.nhist;
         V.wsum = reinterpret_cast<double *>(p);
-        p += sizeof(double) * 2 * nwarps * (A.nslots > 0 ? A.nslots : 1);
+        p += sizeof(double) * (size_t)nwarps * W * (A.nslots > 0 ? A.nslots : 1);
         V.stage = reinterpret_cast<unsigned *>(p);
-        p += sizeof(unsigned) * 2 * A.stage_bins;
+        p += sizeof(unsigned) * (size_t)W * A.stage_bins;
         V.nvalid = reinterpret_cast<unsigned *>(p);
-        p += sizeof(unsigned) * 2;
+        p += sizeof(unsigned) * W;
         VmIns *prog = reinterpret_cast<VmIns *>(p);
         for (int i = threadIdx.x; i < A.ncst; i += blockDim.x) consts[i] = A.consts[i];
         for (int i = threadIdx.x; i < A.nrange; i += blockDim.x) ranges[i] = A.ranges[i];
         for (int i = threadIdx.x; i < A.nhist; i += blockDim.x) hists[i] = A.hists[i];
         for (int i = threadIdx.x; i < A.nins; i += blockDim.x) prog[i] = A.prog[i];
-        for (int i = threadIdx.x; i < 2 * A.stage_bins; i += blockDim.x) V.stage[i] = 0u;
-        if (threadIdx.x < 2) V.nvalid[threadIdx.x] = 0u;
+        for (int i = threadIdx.x; i < W * A.stage_bins; i += blockDim.x) V.stage[i] = 0u;
+        for (int i = threadIdx.x; i < W; i += blockDim.x) V.nvalid[i] = 0u;
         V.consts = consts;
         V.ranges = ranges;
         V.hists = hists;
@@ -298,6 +334,7 @@ __global__ void __launch_bounds__(max_block<ALG>::value) ensemble_kernel(const E
         V.nslots = A.nslots;
         V.stage_bins = A.stage_bins;
         V.nwarps = nwarps;
+        V.window = W;
     }
     __syncthreads();
 
@@ -327,69 +364,74 @@ __global__ void __launch_bounds__(max_block<ALG>::value) ensemble_kernel(const E
         bool failed_reported = false;
         uint32_t warp_iters = 0;  // max over lanes of step iterations, summed over intervals
 
-        for (int k = 0; k < nt; ++k) {
-            const uint32_t it = T.advance(A.S, k);
-            if constexpr (Traj<SYS, ALG>::FIXED)
-                warp_iters += it;
-            else
-                warp_iters += __reduce_max_sync(0xffffffffu, it);
-            if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
-            if ((T.status == ST_DOMAIN || T.status == ST_BAD_IC) && !failed_reported) {
-                failed_reported = true;
-                atomicAdd(&A.u64[CNT_FAILED], 1ull);
-                const bool can_redo = A.fail_out && A.smp.kind != DTWA_SAMPLER_HOST_ARRAY &&
-                                      A.smp.kind != DTWA_SAMPLER_DEVICE_ARRAY;
-                bool queued = false;
-                if (can_redo) {
-                    const unsigned pos = atomicAdd(A.fail_count, 1u);
-                    if (pos < A.fail_cap) {
-                        FailRec r;
-                        r.idx = idx;
-                        r.k = k;
-                        r.pad = 0;
-                        A.fail_out[pos] = r;
-                        queued = true;
+        for (int k0 = 0; k0 < nt; k0 += W) {
+            const int nw = min(W, nt - k0);
+            for (int w = 0; w < nw; ++w) {
+                const int k = k0 + w;
+                const uint32_t it = T.advance(A.S, k);
+                if constexpr (Traj<SYS, ALG>::FIXED)
+                    warp_iters += it;
+                else
+                    warp_iters += __reduce_max_sync(0xffffffffu, it);
+                if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
+                if (T.status != ST_OK && T.status != ST_INACTIVE && !failed_reported) {
+                    failed_reported = true;
+                    bool queued = false;
+                    if (T.status != ST_MAXITERS) {
+                        atomicAdd(&A.u64[CNT_FAILED], 1ull);
+                        const bool can_redo = A.fail_out && A.smp.kind != DTWA_SAMPLER_HOST_ARRAY &&
+                                              A.smp.kind != DTWA_SAMPLER_DEVICE_ARRAY;
+                        if (can_redo) {
+                            const unsigned pos = atomicAdd(A.fail_count, 1u);
+                            if (pos < A.fail_cap) {
+                                FailRec r;
+                                r.idx = idx;
+                                r.k = k;
+                                r.pad = 0;
+                                A.fail_out[pos] = r;
+                                queued = true;
+                            }
+                        }
                     }
+                    if (!queued) atomicAdd(&A.u64[CNT_UNFINISHED], 1ull);
                 }
-                if (!queued) atomicAdd(&A.u64[CNT_UNFINISHED], 1ull);
+                const bool valid = (T.status == ST_OK) && (k >= start_k);
+                // observables + reducers into this warp's / CTA's window staging
+                vm_run<NV>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0, valid,
+                           k, w, nullptr);
+                const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
+                if (lane == 0 && nv) atomicAdd(&V.nvalid[w], nv);
             }
-            if (T.status == ST_MAXITERS && !failed_reported) {
-                failed_reported = true;
-                atomicAdd(&A.u64[CNT_UNFINISHED], 1ull);
-            }
-            const bool valid = (T.status == ST_OK) && (k >= start_k);
-            const int buf = k & 1;
-            // observables + reducers
-            vm_run<NV>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0, valid, k,
-                       buf, nullptr);
-            const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
-            if (lane == 0 && nv) atomicAdd(&V.nvalid[buf], nv);
+            // ---- once per window: CTA-wide flush in a fixed order (deterministic sums) ----
             __syncthreads();
-            // flush this output's staging buffers (double-buffered by parity: no second barrier)
-            for (int sl = threadIdx.x; sl < A.nslots; sl += blockDim.x) {
+            for (int i = threadIdx.x; i < nw * A.nslots; i += blockDim.x) {
+                const int w = i / A.nslots, sl = i - w * A.nslots;
                 double s = 0.0;
-                for (int w = 0; w < nwarps; ++w) s = __dadd_rn(s, V.wsum[((size_t)buf * nwarps + w) * A.nslots + sl]);
-                atomicAdd(&my_partial[(size_t)k * A.nslots + sl], s);  // only this thread ever adds here: ordered, deterministic
+                for (int wp = 0; wp < nwarps; ++wp) s = __dadd_rn(s, V.wsum[((size_t)wp * W + w) * A.nslots + sl]);
+                // only this CTA ever adds to its partial row: RED in program order => reproducible
+                atomicAdd(&my_partial[(size_t)(k0 + w) * A.nslots + sl], s);
             }
-            if (threadIdx.x == blockDim.x - 1) {
-                const unsigned c = V.nvalid[buf];
+            for (int w = threadIdx.x; w < nw; w += blockDim.x) {
+                const unsigned c = V.nvalid[w];
                 if (c) {
-                    atomicAdd(&nvalid_g[k], (unsigned long long)c);
-                    V.nvalid[buf] = 0u;
+                    atomicAdd(&nvalid_g[k0 + w], (unsigned long long)c);
+                    V.nvalid[w] = 0u;
                 }
             }
             for (int hI = 0; hI < A.nhist; ++hI) {
                 const HistDesc h = V.hists[hI];
                 if (h.staged_off < 0) continue;
-                unsigned *sb = V.stage + (size_t)buf * A.stage_bins + h.staged_off;
-                for (int i = threadIdx.x; i < h.n0; i += blockDim.x) {
-                    const unsigned c = sb[i];
+                for (int i = threadIdx.x; i < nw * h.n0; i += blockDim.x) {
+                    const int w = i / h.n0, b = i - w * h.n0;
+                    unsigned *cell = V.stage + (size_t)w * A.stage_bins + h.staged_off + b;
+                    const unsigned c = *cell;
                     if (c) {
-                        atomicAdd(&A.u64[h.base + (long long)k * h.tstride + i], (unsigned long long)c);
-                        sb[i] = 0u;
+                        atomicAdd(&A.u64[h.base + (long long)(k0 + w) * h.tstride + b], (unsigned long long)c);
+                        *cell = 0u;
                     }
                 }
             }
+            __syncthreads();
         }
         // ---- step counters: one atomic per warp per batch ----
         const unsigned long long a = __reduce_add_sync(0xffffffffu, T.nacc);
@@ -477,7 +519,7 @@ __global__ void hamiltonian_kernel(const double p0, const double p1, const doubl
     h[j] = Sys<SYS>::hamiltonian(par, x);
 }
 
-// expression evaluation through the same VM as the ensemble kernel (program: <expr> OP_STORE 0 OP_END)
+// expression evaluation through the same VM as the ensemble kernel (program: <expr> OP_STORE OP_END)
 template <int NV>
 __global__ void eval_kernel(const VmIns *__restrict__ prog, const double *__restrict__ consts, const double *__restrict__ u,
                             long long n, double *__restrict__ v)
@@ -486,6 +528,7 @@ __global__ void eval_kernel(const VmIns *__restrict__ prog, const double *__rest
     VmShared V = {};
     V.consts = consts;
     V.prog = prog;
+    V.window = 1;
     double x[4] = {0, 0, 0, 0};
     if (j < n) {
 #pragma unroll
