@@ -393,7 +393,7 @@ def monte_carlo_integrate(system, mc_system, *, tolerate_errors=True, show_progr
             for a, b in zip(total, arrays):
                 a += b
             for k, v in info.items():
-                info_tot[k] = max(info_tot[k], v) if k == "resample_rounds" else info_tot[k] + v
+                info_tot[k] = max(info_tot[k], v) if k in ("resample_rounds", "jit") else info_tot[k] + v
         pos += n
     dist.offset = base + N
     last_info = info_tot

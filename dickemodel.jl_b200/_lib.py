@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libdicketwa.so")
 
 # ---- constants (include/dicketwa.h) ----
 OK = 0
-ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_EXPR, ERR_NCCL, ERR_TOO_MANY_FAILURES, ERR_BOUNDS, ERR_CAPACITY = range(-1, -9, -1)
+ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_EXPR, ERR_NCCL, ERR_TOO_MANY_FAILURES, ERR_BOUNDS, ERR_CAPACITY, ERR_JIT = range(-1, -10, -1)
 TRAJ_OK, TRAJ_DOMAIN, TRAJ_MAXITERS, TRAJ_BAD_IC = 0, 1, 2, 3
 SYS_DICKE, SYS_LMG = 0, 1
 ALG_RK4, ALG_RK8, ALG_DP5, ALG_DOP853 = 0, 1, 2, 3
@@ -27,7 +27,7 @@ AXIS_EXPR, AXIS_TIME = 0, 1
 EXPORTS = ["dtwa_last_error", "dtwa_version", "dtwa_create", "dtwa_destroy", "dtwa_device_info", "dtwa_set_launch",
            "dtwa_hamiltonian", "dtwa_integrate", "dtwa_sample", "dtwa_pdf", "dtwa_eval_expr", "dtwa_scale_to_index",
            "dtwa_ensemble", "dtwa_ensemble_launch", "dtwa_plan_arenas", "dtwa_plan_fetch", "dtwa_plan_free",
-           "dtwa_fp64_peak"]
+           "dtwa_fp64_peak", "dtwa_set_jit", "dtwa_jit_compile"]
 
 
 class DtwaError(RuntimeError):
@@ -71,7 +71,8 @@ class Result(C.Structure):
     _fields_ = [("red", C.POINTER(ReducerOut)), ("n_valid", C.POINTER(C.c_uint64)),
                 ("n_failed", C.c_uint64), ("n_unfinished", C.c_uint64), ("steps_accepted", C.c_uint64),
                 ("steps_rejected", C.c_uint64), ("lane_steps", C.c_uint64), ("resample_rounds", C.c_int32),
-                ("launches", C.c_int32), ("kernel_ms", C.c_double), ("total_ms", C.c_double)]
+                ("launches", C.c_int32), ("jit", C.c_int32), ("reserved", C.c_int32), ("kernel_ms", C.c_double),
+                ("total_ms", C.c_double)]
 
 
 _lib = None
@@ -111,6 +112,9 @@ def load():
         L.dtwa_plan_fetch.argtypes = [vp, C.POINTER(Result)]
         L.dtwa_plan_free.argtypes = [vp]
         L.dtwa_fp64_peak.argtypes = [vp, dp, dp]
+        L.dtwa_set_jit.argtypes = [vp, C.c_int]
+        L.dtwa_jit_compile.argtypes = [C.POINTER(System), C.POINTER(Solver), C.POINTER(C.c_char_p), C.c_int32, C.c_char_p,
+                                       C.c_int64, C.POINTER(C.c_int64)]
         for name in EXPORTS:
             getattr(L, name).restype = C.c_char_p if name == "dtwa_last_error" else C.c_int
         _lib = L
@@ -159,6 +163,10 @@ class Context:
 
     def set_launch(self, block_threads=0, ctas_per_sm=0):
         _check(load().dtwa_set_launch(self._h, block_threads, ctas_per_sm))
+
+    def set_jit(self, mode):
+        """0: interpret the reducer program, 1: always specialise with NVRTC, 2: auto (default)"""
+        _check(load().dtwa_set_jit(self._h, int(mode)))
 
     def fp64_peak(self):
         tf, ms = C.c_double(), C.c_double()
@@ -287,8 +295,18 @@ class Context:
         info = {"n_valid": n_valid, "n_failed": int(res.n_failed), "n_unfinished": int(res.n_unfinished),
                 "steps_accepted": int(res.steps_accepted), "steps_rejected": int(res.steps_rejected),
                 "lane_steps": int(res.lane_steps), "resample_rounds": int(res.resample_rounds),
-                "launches": int(res.launches), "kernel_ms": float(res.kernel_ms), "total_ms": float(res.total_ms)}
+                "launches": int(res.launches), "jit": int(res.jit), "kernel_ms": float(res.kernel_ms), "total_ms": float(res.total_ms)}
         return arrays, info
+
+
+def jit_compile(sys: System, sol: Solver, exprs):
+    """NVRTC compile check of the specialised ensemble kernel (no GPU needed): (source, cubin bytes)"""
+    ex = [e.encode("utf-8") for e in exprs]
+    arr = (C.c_char_p * len(ex))(*ex)
+    buf = C.create_string_buffer(1 << 16)
+    nb = C.c_int64()
+    _check(load().dtwa_jit_compile(C.byref(sys), C.byref(sol), arr, len(ex), buf, len(buf), C.byref(nb)))
+    return buf.value.decode(), nb.value
 
 
 _default_ctx = None
@@ -299,6 +317,8 @@ def default_context() -> Context:
     global _default_ctx
     if _default_ctx is None:
         _default_ctx = Context([int(os.environ.get("DTWA_DEVICE", "0"))])
+        if "DTWA_JIT" in os.environ:
+            _default_ctx.set_jit(int(os.environ["DTWA_JIT"]))
     return _default_ctx
 
 

@@ -15,6 +15,7 @@
 
 #include "dtwa_kernels.cuh"
 #include "dtwa_expr.hpp"
+#include "dtwa_jit.hpp"
 
 using namespace dtwa;
 
@@ -91,6 +92,7 @@ struct NcclApi {
 struct dtwa_ctx {
     std::vector<DevCtx> devs;
     int block_threads = 0, ctas_per_sm = 0;
+    int jit_mode = 2;  // 0: interpret the reducer program, 1: always specialise with NVRTC, 2: specialise large ensembles
     NcclApi nccl;
     std::vector<ncclComm_t> comms;
 };
@@ -208,6 +210,14 @@ extern "C" int dtwa_device_info(dtwa_ctx *ctx, int which, char *name, int *sm_co
     if (sm_count) *sm_count = d.sm_count;
     if (clock_khz) *clock_khz = d.clock_khz;
     if (cc) *cc = d.cc;
+    return DTWA_OK;
+}
+
+extern "C" int dtwa_set_jit(dtwa_ctx *ctx, int mode)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    if (mode < 0 || mode > 2) return set_err(DTWA_ERR_INVALID, "jit mode must be 0 (interpreter), 1 (always) or 2 (auto)");
+    ctx->jit_mode = mode;
     return DTWA_OK;
 }
 
@@ -577,7 +587,7 @@ struct dtwa_plan {
     std::vector<RedLayout> reds;
     std::vector<DevPlan> devs;
     int launches = 0, rounds = 0;
-    bool fetched = false;
+    bool fetched = false, jit = false;
 };
 
 struct LaunchShape {
@@ -585,17 +595,17 @@ struct LaunchShape {
     size_t smem;
 };
 
-template <int SYS, int ALG>
-static int shape_for(dtwa_ctx *ctx, DevCtx &d, const EnsArgs &A, long long n, LaunchShape &ls)
+static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const EnsArgs &A, long long n, LaunchShape &ls)
 {
-    int block = ctx->block_threads ? ctx->block_threads : (is_fixed<ALG>::value ? 256 : 64);
-    if (block > ens_launch<ALG>::max_threads) block = ens_launch<ALG>::max_threads;
+    const bool fixed = alg == DTWA_ALG_RK4 || alg == DTWA_ALG_RK8;
+    const int max_threads = alg == DTWA_ALG_RK4 ? ens_launch<DTWA_ALG_RK4>::max_threads : ens_launch<DTWA_ALG_DOP853>::max_threads;
+    int block = ctx->block_threads ? ctx->block_threads : (fixed ? 256 : 64);
+    if (block > max_threads) block = max_threads;
     // window: output times staged in shared memory between two CTA-wide flushes (<= 24 KB of staging)
     const size_t per_out = sizeof(double) * (block / 32) * (A.nslots > 0 ? A.nslots : 1) + sizeof(unsigned) * A.stage_bins + sizeof(unsigned);
     int window = (int)std::max<size_t>(1, std::min<size_t>({(size_t)16, (size_t)A.S.nt, (size_t)(24 * 1024) / per_out}));
     const size_t smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, block / 32, window);
     ls.window = window;
-    auto kern = ensemble_kernel<SYS, ALG>;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
@@ -609,27 +619,26 @@ static int shape_for(dtwa_ctx *ctx, DevCtx &d, const EnsArgs &A, long long n, La
     return 0;
 }
 
-template <int SYS, int ALG>
-static int launch_ens(DevCtx &d, const EnsArgs &A0, const LaunchShape &ls)
+static int launch_ens(DevCtx &d, const void *kern, const EnsArgs &A0, const LaunchShape &ls)
 {
     EnsArgs A = A0;
     A.window = ls.window;
-    ensemble_kernel<SYS, ALG><<<ls.grid, ls.block, ls.smem, d.stream>>>(A);
-    CK(cudaGetLastError());
+    void *args[] = {(void *)&A};
+    CK(cudaLaunchKernel(kern, dim3(ls.grid), dim3(ls.block), args, ls.smem, d.stream));
     return 0;
 }
 
-static int dispatch_shape(dtwa_ctx *ctx, DevCtx &d, int sys, int alg, const EnsArgs &A, long long n, LaunchShape &ls)
+// the ahead-of-time kernel that interprets the reducer program
+static const void *interpreter_kernel(int sys, int alg)
 {
-    return by_system(sys, [&](auto sk) {
-        return by_alg(alg, [&](auto ak) { return shape_for<decltype(sk)::value, decltype(ak)::value>(ctx, d, A, n, ls); });
+    const void *k = nullptr;
+    by_system(sys, [&](auto sk) {
+        return by_alg(alg, [&](auto ak) {
+            k = (const void *)ensemble_kernel<decltype(sk)::value, decltype(ak)::value>;
+            return 0;
+        });
     });
-}
-static int dispatch_launch(DevCtx &d, int sys, int alg, const EnsArgs &A, const LaunchShape &ls)
-{
-    return by_system(sys, [&](auto sk) {
-        return by_alg(alg, [&](auto ak) { return launch_ens<decltype(sk)::value, decltype(ak)::value>(d, A, ls); });
-    });
+    return k;
 }
 
 extern "C" int dtwa_plan_free(dtwa_plan *plan)
@@ -759,8 +768,20 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
         return set_err(DTWA_ERR_CAPACITY, "reducer set exceeds the VM limits (instructions/constants/ranges/histograms/slots)");
     if (prog.consts.empty()) prog.consts.push_back(0.0);
 
+    // ---- which kernel: the interpreter, or a run-time specialisation of it for this reducer set ----
+    const void *kern = interpreter_kernel(sys->kind, sol->alg);
+    const bool want_jit = ctx->jit_mode == 1 || (ctx->jit_mode == 2 && (double)N * (double)nt >= 2e9);
+    if (want_jit) {
+        cudaKernel_t jk;
+        std::string jerr;
+        CK(cudaSetDevice(ctx->devs[0].device));
+        if (jit_cache().get(sys->kind, sol->alg, prog, &jk, jerr)) return set_err(DTWA_ERR_JIT, jerr);
+        kern = (const void *)jk;
+    }
+
     dtwa_plan *plan = new dtwa_plan;
     plan->ctx = ctx;
+    plan->jit = want_jit;
     plan->nt = nt;
     plan->nslots = nslots;
     plan->n_f64 = (int64_t)nt * std::max(nslots, 1);
@@ -846,7 +867,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
             A.ranges = (const RangeD *)(m + o_r);
             A.hists = (const HistDesc *)(m + o_h);
             A.u64 = dp.d_u64;
-            TRY(dispatch_shape(ctx, d, sys->kind, sol->alg, A, dp.n, shapes[di]));
+            TRY(shape_for(ctx, d, kern, sol->alg, A, dp.n, shapes[di]));
             dp.grid = shapes[di].grid;
             dp.block = shapes[di].block;
             const size_t pbytes = sizeof(double) * (size_t)dp.grid * nt * std::max(nslots, 1);
@@ -854,7 +875,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
             CK(cudaMemsetAsync(d.partial.p, 0, pbytes, d.stream));
             A.partial = (double *)d.partial.p;
             CK(cudaEventRecord(d.ev[1], d.stream));
-            TRY(dispatch_launch(d, sys->kind, sol->alg, A, shapes[di]));
+            TRY(launch_ens(d, kern, A, shapes[di]));
             plan->launches++;
             return 0;
         };
@@ -897,7 +918,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
                 A.attempt = (uint32_t)round;
                 LaunchShape ls = shapes[di];
                 ls.grid = (int)std::max(1ll, std::min<long long>((cnt + ls.block - 1) / ls.block, shapes[di].grid));
-                TRY(dispatch_launch(d, sys->kind, sol->alg, A, ls));
+                TRY(launch_ens(d, kern, A, ls));
                 CK(cudaStreamSynchronize(d.stream));  // recs must outlive the H2D copy
                 plan->launches++;
                 plan->rounds = std::max(plan->rounds, round);
@@ -989,6 +1010,7 @@ extern "C" int dtwa_plan_fetch(dtwa_plan *plan, dtwa_result *res)
     res->steps_rejected = head[CNT_REJ];
     res->lane_steps = head[CNT_LANE];
     res->resample_rounds = plan->rounds;
+    res->jit = plan->jit ? 1 : 0;
     res->launches = plan->launches;
     float kms = 0.f, tms = 0.f;
     double kmax = 0.0;
@@ -1043,5 +1065,39 @@ extern "C" int dtwa_fp64_peak(dtwa_ctx *ctx, double *tflops, double *ms_out)
     const double flops = (double)grid * block * (double)iters * 64.0 * 2.0;
     if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
     if (ms_out) *ms_out = best;
+    return DTWA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Compile-only check of the run-time specialisation (needs libnvrtc but no GPU): generates the
+// specialised source for `nexpr` averaged observables, compiles it for sm_100a and reports the
+// cubin size; the generated source is copied to src_out (truncated to src_cap, always terminated).
+extern "C" int dtwa_jit_compile(const dtwa_system *sys, const dtwa_solver *sol, const char *const *exprs, int32_t nexpr,
+                                char *src_out, int64_t src_cap, int64_t *cubin_bytes)
+{
+    TRY(check_system(sys));
+    if (!sol || sol->alg < DTWA_ALG_RK4 || sol->alg > DTWA_ALG_DOP853) return set_err(DTWA_ERR_INVALID, "unknown solver alg");
+    if (!exprs || nexpr < 1) return set_err(DTWA_ERR_INVALID, "at least one expression is required");
+    Program prog;
+    try {
+        auto vars = varnames_of(sys->kind);
+        ExprCompiler comp(vars);
+        for (int i = 0; i < nexpr; ++i) {
+            comp.compile(exprs[i], prog);
+            prog.emit(OP_SUM, 0, (uint16_t)i);
+        }
+    } catch (const std::exception &e) {
+        return set_err(DTWA_ERR_EXPR, e.what());
+    }
+    prog.emit(OP_END);
+    const std::string src = jit_source(sys->kind, sol->alg, prog);
+    if (src_out && src_cap > 0) {
+        std::snprintf(src_out, (size_t)src_cap, "%s", src.c_str());
+    }
+    std::vector<char> cubin;
+    std::string log;
+    NvrtcApi api;
+    if (jit_compile(api, src, cubin, log)) return set_err(DTWA_ERR_JIT, log);
+    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
     return DTWA_OK;
 }

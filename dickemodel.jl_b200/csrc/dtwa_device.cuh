@@ -12,6 +12,8 @@
 //   samplers / pdfs       src/TWA.jl:689-764, src/PhaseSpaces.jl:16,34,49,63
 //   scale_to_index        src/TWA.jl:53-64
 #pragma once
+// (under NVRTC -- the run-time specialisation of the reducers, dtwa_jit.hpp -- these three names are
+//  served from in-memory headers: fixed-width typedefs, an empty cuda_runtime.h, the embedded C header)
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../include/dicketwa.h"

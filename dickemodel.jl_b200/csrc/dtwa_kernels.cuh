@@ -295,8 +295,15 @@ struct ens_launch {  // register budget: RK4 fits 64 regs/thread (4 CTAs of 256)
     static constexpr int min_blocks = (ALG == DTWA_ALG_RK4) ? 4 : 1;
 };
 
-template <int SYS, int ALG>
-__global__ void __launch_bounds__(ens_launch<ALG>::max_threads, ens_launch<ALG>::min_blocks) ensemble_kernel(const EnsArgs A)
+// Reducers compiled at run time for one reducer set (dtwa_jit.hpp generates the definition: the same
+// operation sequence as vm_run, as straight-line code).  Declared here, defined only in JIT units.
+template <int NV>
+__device__ __forceinline__ void jit_reduce(const VmShared &V, const SamplerPar *smp, unsigned long long *u64, const double x0,
+                                           const double x1, const double x2, const double x3, const bool valid, const int k,
+                                           const int w);
+
+template <int SYS, int ALG, bool JIT>
+__device__ __forceinline__ void ensemble_body(const EnsArgs &A)
 {
     constexpr int NV = Sys<SYS>::NV;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -397,8 +404,12 @@ __global__ void __launch_bounds__(ens_launch<ALG>::max_threads, ens_launch<ALG>:
                 }
                 const bool valid = (T.status == ST_OK) && (k >= start_k);
                 // observables + reducers into this warp's / CTA's window staging
-                vm_run<NV>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0, valid,
-                           k, w, nullptr);
+                if constexpr (JIT)
+                    jit_reduce<NV>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0,
+                                   valid, k, w);
+                else
+                    vm_run<NV>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0,
+                               valid, k, w, nullptr);
                 const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
                 if (lane == 0 && nv) atomicAdd(&V.nvalid[w], nv);
             }
@@ -444,6 +455,13 @@ __global__ void __launch_bounds__(ens_launch<ALG>::max_threads, ens_launch<ALG>:
     }
 }
 
+template <int SYS, int ALG>
+__global__ void __launch_bounds__(ens_launch<ALG>::max_threads, ens_launch<ALG>::min_blocks) ensemble_kernel(const EnsArgs A)
+{
+    ensemble_body<SYS, ALG, false>(A);
+}
+
+#ifndef DTWA_JIT_UNIT  // everything below is only needed in the ahead-of-time build
 // partial[grid][n] -> out[n], CTA order fixed => run-to-run reproducible sums
 __global__ void finalize_sums_kernel(const double *__restrict__ partial, int grid, long long n, double *__restrict__ out)
 {
@@ -568,5 +586,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
     const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
     if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+
+#endif  // DTWA_JIT_UNIT
 
 }  // namespace dtwa

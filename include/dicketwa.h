@@ -41,6 +41,7 @@ extern "C" {
 #define DTWA_ERR_TOO_MANY_FAILURES (-6) /* >100 consecutive resampling rounds (src/TWA.jl:202-206) */
 #define DTWA_ERR_BOUNDS (-7)       /* initial condition out of bounds (src/ClassicalSystems.jl:100-102) */
 #define DTWA_ERR_CAPACITY (-8)     /* caller buffer too small / internal limit exceeded */
+#define DTWA_ERR_JIT (-9)          /* run-time specialisation failed (libnvrtc missing or compile error) */
 
 /* ---- per-trajectory status (dtwa_integrate) ---- */
 #define DTWA_TRAJ_OK 0
@@ -150,6 +151,8 @@ typedef struct {
     uint64_t lane_steps;     /* 32 x warp-level step iterations: steps/(lane_steps) = lane efficiency */
     int32_t resample_rounds;
     int32_t launches;        /* kernels launched by this call */
+    int32_t jit;             /* 1 when the run-time specialised kernel ran, 0 for the interpreter */
+    int32_t reserved;
     double kernel_ms;        /* CUDA-event time of the ensemble kernels on the context's stream */
     double total_ms;         /* CUDA-event time incl. host<->device copies */
 } dtwa_result;
@@ -166,6 +169,16 @@ int dtwa_destroy(dtwa_ctx *ctx);
 int dtwa_device_info(dtwa_ctx *ctx, int which, char *name, int *sm_count, int *clock_khz, int *cc);
 /* tuning: threads per CTA (0 = default) and resident CTAs per SM (0 = occupancy query) */
 int dtwa_set_launch(dtwa_ctx *ctx, int block_threads, int ctas_per_sm);
+
+/* The observables are compiled the way the reference compiles them (it evals a Julia lambda per
+ * observable, src/TWA.jl:298): mode 1 specialises the ensemble kernel for the reducer set with NVRTC
+ * (libnvrtc is dlopen'ed; ~1 s per new reducer set, cached per process), mode 0 interprets the
+ * reducer program inside the ahead-of-time kernel, mode 2 (default) specialises when N*nt >= 2e9.
+ * Both paths execute the same correctly rounded operations in the same order: identical results. */
+int dtwa_set_jit(dtwa_ctx *ctx, int mode);
+/* compile-only check of the specialisation for `nexpr` averaged observables (no GPU needed) */
+int dtwa_jit_compile(const dtwa_system *sys, const dtwa_solver *sol, const char *const *exprs, int32_t nexpr, char *src_out,
+                     int64_t src_cap, int64_t *cubin_bytes);
 
 /* ---- a5: ClassicalDicke.hamiltonian / ClassicalLMG.hamiltonian (src/ClassicalDicke.jl:80-88,
  *      src/ClassicalLMG.jl:63-70) on a batch u[n][nvar] -> h[n] ---- */

@@ -193,3 +193,41 @@ def test_single_trajectory_integrate_api(ctx, mods, O):
         CS.integrate(system, u0, -1.0)
     with pytest.raises(ValueError, match="should have length 4"):
         CS.integrate(system, [0.0, 0.0], 1.0)
+
+
+def test_specialised_kernel_is_bit_identical_to_the_interpreter(ctx, mods, O):
+    """dtwa_set_jit: the NVRTC-specialised reducers execute the interpreter's operation sequence"""
+    TWA, CD, CL, _ = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    j, N = 100, 6000
+    ts = TWA.jrange(0, 0.1, 4)
+    jz = TWA.Weyl.Jz(j) / j
+
+    def run(mode, **solver):
+        ctx.set_jit(mode)
+        try:
+            W = TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=j, seed=31)
+            mk = lambda **kw: TWA.mcs_for_distributions(system, N=N, distribution=W, ts=ts, **kw)
+            chain = TWA.mcs_chain(TWA.mcs_for_averaging(system, observable=[jz, TWA.Weyl.Jx2(j), "sin(q)*exp(-p^2)", "Q^5/(1+P^4)"], N=N, ts=ts, distribution=W),
+                                  mk(x="t", y=jz, ys=TWA.jrange(-1.1, 0.01, 1.1)), mk(x="q", xs=TWA.jrange(-4.3, 0.1, 4.3), y="p", ys=TWA.jrange(-2.4, 0.1, 2.4)),
+                                  TWA.mcs_for_survival_probability(system, N=N, ts=ts, distribution=W))
+            out = TWA.monte_carlo_integrate(system, chain, **solver)
+            return out, TWA.last_info["jit"]
+        finally:
+            ctx.set_jit(2)
+
+    for solver in (dict(integrator_alg="RK4", dt=2.0 ** -6), dict(integrator_alg="DP8", tol=1e-9), dict(integrator_alg="DP5", tol=1e-7)):
+        a, ja = run(0, **solver)
+        b, jb = run(1, **solver)
+        assert (ja, jb) == (0, 1)
+        for x, y in zip(a, b):
+            assert np.array_equal(np.asarray(x), np.asarray(y))
+    # LMG through the same path
+    lmg = CL.ClassicalLMGSystem(Ω=1, ξ=-1)
+    res = []
+    for mode in (0, 1):
+        ctx.set_jit(mode)
+        W = TWA.coherent_Wigner_SU2([0.2, 0.1], j=50, seed=4)
+        res.append(TWA.variance(lmg, observable=["Q", "P", "Q*P"], N=3000, ts=TWA.jrange(0, 0.5, 5), distribution=W, integrator_alg="RK8", dt=0.05))
+    ctx.set_jit(2)
+    assert np.array_equal(res[0], res[1])

@@ -27,7 +27,7 @@ def test_struct_layouts_match_the_header(pkg):
     assert ctypes.sizeof(lib.System) == 40 and ctypes.sizeof(lib.Solver) == 40
     assert ctypes.sizeof(lib.Sampler) == 72 and ctypes.sizeof(lib.Range) == 24
     assert ctypes.sizeof(lib.Reducer) == 96 and ctypes.sizeof(lib.ReducerOut) == 32
-    assert ctypes.sizeof(lib.Result) == 80
+    assert ctypes.sizeof(lib.Result) == 88
 
 
 def test_no_cpu_fallback(pkg):
@@ -172,6 +172,26 @@ def test_monte_carlo_system_protocol(pkg):
     assert np.allclose(mean, [[1.0, 2.0]]) and np.allclose(var, [[3.0 - 1.0, 8.0 - 4.0]])
     s = TWA.mcs_for_survival_probability(system, ts=ts, N=10, distribution=W)
     assert np.allclose(s.f_final(np.ones((4, 1))), (2 * np.pi / 10) ** 2 / 10)
+
+
+def test_runtime_specialisation_compiles_without_a_gpu(pkg):
+    """NVRTC needs no device: the generated source for every system/algorithm compiles to an sm_100a cubin"""
+    from dickemodel_jl_b200 import TWA
+    lib = pkg._lib
+    for kind, exprs in ((lib.SYS_DICKE, [str(TWA.Weyl.Jz(100) / 100), "q", "sqrt(4-Q^2-P^2)*p"]), (lib.SYS_LMG, ["Q", "(Q)^2", "atan(P,Q)"])):
+        for alg in (lib.ALG_RK4, lib.ALG_DOP853):
+            s = lib.System()
+            s.kind = kind
+            s.params[0], s.params[1], s.params[2] = 1.0, 1.0, 1.0
+            sol = lib.Solver()
+            sol.alg, sol.dt, sol.tol = alg, 0.01, 1e-8
+            src, nbytes = lib.jit_compile(s, sol, exprs)
+            assert "dtwa_jit_ensemble" in src and "__dmul_rn" in src and nbytes > 10000
+    s = lib.System()
+    s.kind = lib.SYS_LMG
+    sol = lib.Solver()
+    with pytest.raises(pkg.DtwaError, match="unknown variable 'q'"):
+        lib.jit_compile(s, sol, ["q"])
 
 
 GLOO_WORKER = r'''

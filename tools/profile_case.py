@@ -22,10 +22,12 @@ ap.add_argument("--ctas-per-sm", type=int, default=0)
 ap.add_argument("--hist", action="store_true", help="config-3 style chain: jz-vs-t and q-vs-t histograms")
 ap.add_argument("--state", default="A", choices=["A", "B"])
 ap.add_argument("--tol", type=float, default=1e-8)
+ap.add_argument("--jit", type=int, default=2)
 a = ap.parse_args()
 pkg = graft.load_package()
 TWA, CD = pkg.TWA, pkg.ClassicalDicke
 ctx = pkg.default_context()
+ctx.set_jit(a.jit)
 if a.block or a.ctas_per_sm:
     ctx.set_launch(a.block, a.ctas_per_sm)
 system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
@@ -44,4 +46,4 @@ for rep in range(a.reps):
     i = TWA.last_info
     steps = i["steps_accepted"] + i["steps_rejected"]
     print(f"rep {rep}: {steps} steps in {i['kernel_ms']:.3f} ms kernel = {steps / i['kernel_ms'] / 1e6:.2f} Gsteps/s; "
-          f"lane efficiency {steps / max(1, i['lane_steps']):.3f}; failed {i['n_failed']}; launches {i['launches']}")
+          f"lane efficiency {steps / max(1, i['lane_steps']):.3f}; failed {i['n_failed']}; launches {i['launches']}; jit {i['jit']}")
