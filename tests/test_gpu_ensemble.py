@@ -231,3 +231,34 @@ def test_specialised_kernel_is_bit_identical_to_the_interpreter(ctx, mods, O):
         res.append(TWA.variance(lmg, observable=["Q", "P", "Q*P"], N=3000, ts=TWA.jrange(0, 0.5, 5), distribution=W, integrator_alg="RK8", dt=0.05))
     ctx.set_jit(2)
     assert np.array_equal(res[0], res[1])
+
+
+def test_multi_device_context_matches_single_device(pkg, mods, O):
+    """dtwa_create(ndev=2): contiguous index blocks + one grouped ncclAllReduce; integer counts are
+    bit-identical to the single-device run, sums agree to rounding"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    TWA, CD, _, _ = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    j, N = 100, 50001
+    ts = TWA.jrange(0, 0.1, 5)
+    jz = TWA.Weyl.Jz(j) / j
+
+    def run():
+        W = TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=j, seed=5)
+        chain = TWA.mcs_chain(TWA.mcs_for_averaging(system, observable=jz, N=N, ts=ts, distribution=W),
+                              TWA.mcs_for_distributions(system, x="t", y=jz, ys=TWA.jrange(-1.1, 0.01, 1.1), N=N, ts=ts, distribution=W))
+        out = TWA.monte_carlo_integrate(system, chain, integrator_alg="RK4", dt=2.0 ** -6)
+        return out, dict(TWA.last_info)
+
+    one, i1 = run()
+    old = pkg.default_context()
+    try:
+        pkg.set_default_context(pkg.Context([0, 1]))
+        two, i2 = run()
+    finally:
+        pkg.set_default_context(old)
+    assert np.array_equal(one[1], two[1])
+    assert np.abs(one[0] - two[0]).max() < 1e-12
+    assert i1["steps_accepted"] == i2["steps_accepted"] and np.array_equal(i1["n_valid"], i2["n_valid"])
