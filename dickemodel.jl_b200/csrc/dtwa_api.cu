@@ -280,7 +280,7 @@ static int check_solver(const dtwa_solver *sol, bool fixed_needs_dt = true)
 // Fixed-step table (same rule as oracle/oracle.c orc_step_table): interval k = (ts[k-1] or 0, ts[k]]
 // in n = ceil(d/dt - 1e-9) equal sub-steps.  Also validates ts (src/ClassicalSystems.jl:89-91:
 // "Use integate_backwards=true instead of negative time").
-static int build_step_table(const double *ts, int nt, double dt, std::vector<StepTab> &tab)
+static int build_step_table(const double *ts, int nt, double dt, double wfold, std::vector<StepTab> &tab)
 {
     if (!ts || nt < 1) return set_err(DTWA_ERR_INVALID, "ts must hold at least one time");
     tab.resize(nt);
@@ -302,6 +302,10 @@ static int build_step_table(const double *ts, int nt, double dt, std::vector<Ste
             r.hh = r.h / 2.0;
             r.h3 = r.h / 3.0;
             r.h6 = r.h / 6.0;
+            r.hw = r.h * wfold;
+            r.hhw = r.hh * wfold;
+            r.h3w = r.h3 * wfold;
+            r.h6w = r.h6 * wfold;
         }
         tab[k] = r;
         tprev = ts[k];
@@ -530,7 +534,7 @@ extern "C" int dtwa_integrate(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_
     TRY(check_solver(sol));
     if (n < 0 || (n > 0 && (!u0 || !out || !status))) return set_err(DTWA_ERR_INVALID, "bad buffers");
     std::vector<StepTab> tab;
-    TRY(build_step_table(ts, nt, sol->dt, tab));
+    TRY(build_step_table(ts, nt, sol->dt, make_par(sys, sol->backwards).b, tab));
     if (n == 0) return DTWA_OK;
     DevCtx &d = ctx->devs[0];
     CK(cudaSetDevice(d.device));
@@ -602,9 +606,12 @@ static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const 
     int block = ctx->block_threads ? ctx->block_threads : (fixed ? 256 : 64);
     if (block > max_threads) block = max_threads;
     // window: output times staged in shared memory between two CTA-wide flushes (<= 24 KB of staging)
-    const size_t per_out = sizeof(double) * (block / 32) * (A.nslots > 0 ? A.nslots : 1) + sizeof(unsigned) * A.stage_bins + sizeof(unsigned);
-    int window = (int)std::max<size_t>(1, std::min<size_t>({(size_t)16, (size_t)A.S.nt, (size_t)(24 * 1024) / per_out}));
-    const size_t smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, block / 32, window);
+    const int rows = fixed ? block / 32 : block;  // staging rows: one per warp (fixed step) or per thread (adaptive)
+    const size_t per_out = sizeof(double) * rows * (A.nslots > 0 ? A.nslots : 1) + sizeof(unsigned) * A.stage_bins + sizeof(unsigned);
+    // (adaptive kernels profit from long windows: the lanes' step counts average out before they wait for each other)
+    const size_t wcap = fixed ? 16 : 64, wbudget = fixed ? 24 * 1024 : 32 * 1024;
+    int window = (int)std::max<size_t>(1, std::min<size_t>({wcap, (size_t)A.S.nt, wbudget / per_out}));
+    const size_t smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, rows, window);
     ls.window = window;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -668,7 +675,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
     SamplerPar sp0;
     TRY(make_sampler_par(sys, smp, sp0));
     std::vector<StepTab> tab;
-    TRY(build_step_table(ts, nt, sol->dt, tab));
+    TRY(build_step_table(ts, nt, sol->dt, make_par(sys, sol->backwards).b, tab));
     const bool fixed = sol->alg == DTWA_ALG_RK4 || sol->alg == DTWA_ALG_RK8;
     if (fixed && ts[nt - 1] > 0 && !(sol->dt > 0)) return set_err(DTWA_ERR_INVALID, "fixed-step algorithms need dt > 0");
     const int ndev = (int)ctx->devs.size();
@@ -775,7 +782,9 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
         cudaKernel_t jk;
         std::string jerr;
         CK(cudaSetDevice(ctx->devs[0].device));
-        if (jit_cache().get(sys->kind, sol->alg, prog, &jk, jerr)) return set_err(DTWA_ERR_JIT, jerr);
+        const double wsigned = make_par(sys, sol->backwards).b;
+        const int wflag = (sys->kind == DTWA_SYS_DICKE && wsigned == 1.0) ? 1 : (sys->kind == DTWA_SYS_DICKE && wsigned == -1.0) ? -1 : 0;
+        if (jit_cache().get(sys->kind, sol->alg, wflag, prog, &jk, jerr)) return set_err(DTWA_ERR_JIT, jerr);
         kern = (const void *)jk;
     }
 
@@ -1090,7 +1099,7 @@ extern "C" int dtwa_jit_compile(const dtwa_system *sys, const dtwa_solver *sol, 
         return set_err(DTWA_ERR_EXPR, e.what());
     }
     prog.emit(OP_END);
-    const std::string src = jit_source(sys->kind, sol->alg, prog);
+    const std::string src = jit_source(sys->kind, sol->alg, (sys->kind == DTWA_SYS_DICKE && sys->params[1] == 1.0) ? 1 : 0, prog);
     if (src_out && src_cap > 0) {
         std::snprintf(src_out, (size_t)src_cap, "%s", src.c_str());
     }

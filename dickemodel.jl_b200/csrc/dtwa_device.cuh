@@ -47,7 +47,10 @@ template <>
 struct Sys<DTWA_SYS_DICKE> {
     static constexpr int NV = 4;
     static constexpr int QI = 0, PI = 2;
-    // 19 FP64-pipe instructions + 1 MUFU
+    // 18 FP64-pipe instructions + 1 MUFU.  FOLDQ: du[1] is returned as p (the factor w lives in the
+    // caller's step constants), 17 instructions.  DTWA_W_IS_ONE / DTWA_W_IS_MINUS_ONE (defined by the
+    // run-time specialisation when |w| == 1; x*1.0 == x exactly, so results do not change): 16.
+    template <bool FOLDQ = false>
     __device__ __forceinline__ static void rhs(const SysPar &p, const double (&u)[4], double (&du)[4])
     {
         const double Q = u[0], q = u[1], P = u[2], pp = u[3];
@@ -59,11 +62,20 @@ struct Sys<DTWA_SYS_DICKE> {
         const double gqQ = __dmul_rn(gq, Q);
         const double e = fma(gqQ, is, -p.a);      // g q Q / s - w0
         du[0] = __dmul_rn(-P, e);                 // P w0 - g P q Q / s
-        du[1] = __dmul_rn(pp, p.b);               // p w
+        if constexpr (FOLDQ)
+            du[1] = pp;
+        else
+            du[1] = __dmul_rn(pp, p.b);           // p w
         const double gqs = __dmul_rn(gq, s);
         du[2] = fma(Q, e, -gqs);                  // g q Q^2/s - g q s - Q w0
         const double Qs = __dmul_rn(Q, s);
+#if defined(DTWA_W_IS_ONE)
+        const double qw = q;
+#elif defined(DTWA_W_IS_MINUS_ONE)
+        const double qw = -q;
+#else
         const double qw = __dmul_rn(q, p.b);
+#endif
         du[3] = fma(-p.c, Qs, -qw);               // -g Q s - q w
     }
     __device__ __forceinline__ static double hamiltonian(const double *par, const double *u)
@@ -122,38 +134,63 @@ __device__ __forceinline__ bool state_bad(const double (&u)[Sys<SYS>::NV])
 // ------------------------------------------------------------------------------------------------
 // fixed-step steppers
 struct StepTab {  // one row per output interval (built on the host, dtwa_api.cu build_step_table)
-    double h, hh, h3, h6;
+    double h, hh, h3, h6;      // h, h/2, h/3, h/6
+    double hw, hhw, h3w, h6w;  // the same times the oscillator frequency (Dicke: dq/dt = w p is folded into the RK4 weights)
     int32_t n;
     int32_t pad;
 };
 
 template <int SYS>
-__device__ __forceinline__ void rk4_step(const SysPar &p, double (&u)[Sys<SYS>::NV], double h, double hh, double h3,
-                                         double h6)
+__device__ __forceinline__ void rk4_step(const SysPar &p, double (&u)[Sys<SYS>::NV], const StepTab &r)
 {
     constexpr int NV = Sys<SYS>::NV;
     double k[NV], y[NV], acc[NV];
-    Sys<SYS>::rhs(p, u, k);
+    if constexpr (SYS == DTWA_SYS_DICKE) {
+        // component 1 (q): k = w * p_stage is never formed; its weights carry the factor w
+        Sys<SYS>::template rhs<true>(p, u, k);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        y[i] = fma(hh, k[i], u[i]);
-        acc[i] = fma(h6, k[i], u[i]);
+        for (int i = 0; i < NV; ++i) {
+            y[i] = fma(i == 1 ? r.hhw : r.hh, k[i], u[i]);
+            acc[i] = fma(i == 1 ? r.h6w : r.h6, k[i], u[i]);
+        }
+        Sys<SYS>::template rhs<true>(p, y, k);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            y[i] = fma(i == 1 ? r.hhw : r.hh, k[i], u[i]);
+            acc[i] = fma(i == 1 ? r.h3w : r.h3, k[i], acc[i]);
+        }
+        Sys<SYS>::template rhs<true>(p, y, k);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            y[i] = fma(i == 1 ? r.hw : r.h, k[i], u[i]);
+            acc[i] = fma(i == 1 ? r.h3w : r.h3, k[i], acc[i]);
+        }
+        Sys<SYS>::template rhs<true>(p, y, k);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) u[i] = fma(i == 1 ? r.h6w : r.h6, k[i], acc[i]);
+    } else {
+        Sys<SYS>::rhs(p, u, k);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            y[i] = fma(r.hh, k[i], u[i]);
+            acc[i] = fma(r.h6, k[i], u[i]);
+        }
+        Sys<SYS>::rhs(p, y, k);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            y[i] = fma(r.hh, k[i], u[i]);
+            acc[i] = fma(r.h3, k[i], acc[i]);
+        }
+        Sys<SYS>::rhs(p, y, k);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            y[i] = fma(r.h, k[i], u[i]);
+            acc[i] = fma(r.h3, k[i], acc[i]);
+        }
+        Sys<SYS>::rhs(p, y, k);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) u[i] = fma(r.h6, k[i], acc[i]);
     }
-    Sys<SYS>::rhs(p, y, k);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        y[i] = fma(hh, k[i], u[i]);
-        acc[i] = fma(h3, k[i], acc[i]);
-    }
-    Sys<SYS>::rhs(p, y, k);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        y[i] = fma(h, k[i], u[i]);
-        acc[i] = fma(h3, k[i], acc[i]);
-    }
-    Sys<SYS>::rhs(p, y, k);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) u[i] = fma(h6, k[i], acc[i]);
 }
 
 #define RHS(in, out) Sys<SYS>::rhs(p, in, out)
@@ -187,6 +224,19 @@ __device__ __forceinline__ double rms_norm(const double (&x)[NV])
 #pragma unroll
     for (int i = 0; i < NV; ++i) s = fma(x[i], x[i], s);
     return sqrt(s) / sqrt((double)NV);
+}
+
+// err^(-1/(q+1)) for the step-size factor.  Only the *size* of the next step depends on it (never the
+// accept/reject decision, taken on err in full double precision), so single precision through the
+// MUFU units is ample; the result is clamped to [0.2, 10] by the caller.
+template <int ERR_ORDER>
+__device__ __forceinline__ double step_factor_pow(double err)
+{
+    const float e = fminf(fmaxf((float)err, 1e-30f), 1e30f);
+    if constexpr (ERR_ORDER == 7)
+        return (double)rsqrtf(sqrtf(sqrtf(e)));   // e^(-1/8)
+    else
+        return (double)exp2f((-1.0f / (ERR_ORDER + 1)) * __log2f(e));
 }
 
 template <int SYS, int ALG>
@@ -272,8 +322,8 @@ struct Adaptive {
             double n5 = 0.0, n3 = 0.0;
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
-                const double sc = fma(fmax(fabs(y[i]), fabs(ynew[i])), tol, tol);
-                const double a5 = e5[i] / sc, a3 = e3[i] / sc;
+                const double isc = 1.0 / fma(fmax(fabs(y[i]), fabs(ynew[i])), tol, tol);  // one division for both estimators
+                const double a5 = e5[i] * isc, a3 = e3[i] * isc;
                 n5 = fma(a5, a5, n5);
                 n3 = fma(a3, a3, n3);
                 yn[i] = ynew[i];
@@ -286,7 +336,6 @@ struct Adaptive {
 #undef DOP853_KNEW
         }
         const bool bad = state_bad<SYS>(yn) || !(err == err) || isinf(err);
-        constexpr double EXPO = -1.0 / (ERR_ORDER + 1);
         if (bad) {
             if (forced) return 1;
             habs = h * 0.2;
@@ -294,7 +343,7 @@ struct Adaptive {
             return 0;
         }
         if (err < 1.0 || forced) {
-            double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err, EXPO));
+            double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * step_factor_pow<ERR_ORDER>(err));
             if (rejected) factor = fmin(1.0, factor);
             double hn = h * factor;
             if (clipped && hn < habs) hn = habs;
@@ -308,7 +357,7 @@ struct Adaptive {
             rejected = false;
             accepted = true;
         } else {
-            habs = h * fmax(0.2, 0.9 * pow(err, EXPO));
+            habs = h * fmax(0.2, 0.9 * step_factor_pow<ERR_ORDER>(err));
             rejected = true;
         }
         return 0;

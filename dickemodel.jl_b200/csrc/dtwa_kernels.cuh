@@ -63,7 +63,7 @@ struct Traj {
 #pragma unroll 1
             for (int s = 0; s < r.n; ++s) {
                 if constexpr (ALG == DTWA_ALG_RK4)
-                    rk4_step<SYS>(S.par, u, r.h, r.hh, r.h3, r.h6);
+                    rk4_step<SYS>(S.par, u, r);
                 else
                     rk8_step<SYS>(S.par, u, r.h);
             }
@@ -135,7 +135,9 @@ struct EnsArgs {
 };
 
 // Per-CTA shared-memory view used by the reducer VM.  Staging is per WINDOW of output times:
-//   wsum  [nwarps][window][nslots]  each warp's shuffle-reduced observable sums (plain stores)
+//   wsum  [rows][window][nslots]    observable values: one row per warp (fixed step: shuffle-reduced
+//                                   first) or one row per thread (adaptive: lanes sit at different
+//                                   output times, see ensemble_body), plain stores
 //   stage [window][stage_bins]      1-D histogram bins (shared-memory integer atomics)
 //   nvalid[window]                  contributing trajectories per time
 // A CTA-wide barrier + flush happens once per window, not once per output time, so the warps of a
@@ -152,13 +154,13 @@ struct VmShared {
 };
 
 __host__ __device__ inline size_t ens_smem_bytes(int ncst, int nrange, int nhist, int nslots, int stage_bins, int nins,
-                                                 int nwarps, int window)
+                                                 int rows, int window)
 {
     size_t b = 0;
     b += sizeof(double) * (size_t)ncst;
     b += sizeof(RangeD) * (size_t)nrange;
     b += sizeof(HistDesc) * (size_t)nhist;
-    b += sizeof(double) * (size_t)nwarps * (size_t)window * (size_t)(nslots > 0 ? nslots : 1);
+    b += sizeof(double) * (size_t)rows * (size_t)window * (size_t)(nslots > 0 ? nslots : 1);
     b += sizeof(unsigned) * (size_t)window * (size_t)stage_bins;
     b += sizeof(unsigned) * (size_t)window;
     b += sizeof(VmIns) * (size_t)nins;
@@ -168,7 +170,7 @@ __host__ __device__ inline size_t ens_smem_bytes(int ncst, int nrange, int nhist
 // Evaluate the reducer program for one thread at output index k (slot w of the current window).
 // Control flow is uniform across the CTA (the program is shared); `valid` masks this thread's
 // contributions.  Accumulator + 4 stack entries live in registers.
-template <int NV>
+template <int NV, bool PERLANE>
 __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp, unsigned long long *u64, const double x0,
                                        const double x1, const double x2, const double x3, const bool valid, const int k,
                                        const int w, double *store_out)
@@ -249,9 +251,13 @@ __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp,
         case OP_ATAN: acc = atan(acc); break;
         case OP_SUM: {
             double v = valid ? acc : 0.0;
+            if constexpr (PERLANE) {
+                V.wsum[((size_t)threadIdx.x * V.window + w) * V.nslots + in.b] = v;
+            } else {
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
-            if (lane == 0) V.wsum[((size_t)warp * V.window + w) * V.nslots + in.b] = v;
+                for (int off = 16; off > 0; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
+                if (lane == 0) V.wsum[((size_t)warp * V.window + w) * V.nslots + in.b] = v;
+            }
             break;
         }
         case OP_BIN: {
@@ -289,15 +295,21 @@ __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp,
 #undef VM_VAR
 }
 
+#ifndef DTWA_ADAPT_MAX_THREADS
+#define DTWA_ADAPT_MAX_THREADS 128
+#endif
+#ifndef DTWA_ADAPT_MIN_BLOCKS
+#define DTWA_ADAPT_MIN_BLOCKS 1
+#endif
 template <int ALG>
-struct ens_launch {  // register budget: RK4 fits 64 regs/thread (4 CTAs of 256), the embedded pairs want the full 255
-    static constexpr int max_threads = (ALG == DTWA_ALG_RK4) ? 256 : 128;
-    static constexpr int min_blocks = (ALG == DTWA_ALG_RK4) ? 4 : 1;
+struct ens_launch {  // register budget: RK4 fits 64 regs/thread (4 CTAs of 256), the embedded pairs want more
+    static constexpr int max_threads = (ALG == DTWA_ALG_RK4) ? 256 : DTWA_ADAPT_MAX_THREADS;
+    static constexpr int min_blocks = (ALG == DTWA_ALG_RK4) ? 4 : DTWA_ADAPT_MIN_BLOCKS;
 };
 
 // Reducers compiled at run time for one reducer set (dtwa_jit.hpp generates the definition: the same
 // operation sequence as vm_run, as straight-line code).  Declared here, defined only in JIT units.
-template <int NV>
+template <int NV, bool PERLANE>
 __device__ __forceinline__ void jit_reduce(const VmShared &V, const SamplerPar *smp, unsigned long long *u64, const double x0,
                                            const double x1, const double x2, const double x3, const bool valid, const int k,
                                            const int w);
@@ -307,7 +319,10 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
 {
     constexpr int NV = Sys<SYS>::NV;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool FIXED = is_fixed<ALG>::value;
+    constexpr bool PERLANE = !FIXED;  // adaptive: one staging row per thread, no warp-level reduction
     const int nwarps = blockDim.x >> 5;
+    const int rows = PERLANE ? (int)blockDim.x : nwarps;
     const int lane = threadIdx.x & 31;
     const int W = A.window;
 
@@ -322,7 +337,7 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
         HistDesc *hists = reinterpret_cast<HistDesc *>(p);
         p += sizeof(HistDesc) * A.nhist;
         V.wsum = reinterpret_cast<double *>(p);
-        p += sizeof(double) * (size_t)nwarps * W * (A.nslots > 0 ? A.nslots : 1);
+        p += sizeof(double) * (size_t)rows * W * (A.nslots > 0 ? A.nslots : 1);
         V.stage = reinterpret_cast<unsigned *>(p);
         p += sizeof(unsigned) * (size_t)W * A.stage_bins;
         V.nvalid = reinterpret_cast<unsigned *>(p);
@@ -334,6 +349,8 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
         for (int i = threadIdx.x; i < A.nins; i += blockDim.x) prog[i] = A.prog[i];
         for (int i = threadIdx.x; i < W * A.stage_bins; i += blockDim.x) V.stage[i] = 0u;
         for (int i = threadIdx.x; i < W; i += blockDim.x) V.nvalid[i] = 0u;
+        if constexpr (PERLANE)
+            for (int i = threadIdx.x; i < rows * W * A.nslots; i += blockDim.x) V.wsum[i] = 0.0;
         V.consts = consts;
         V.ranges = ranges;
         V.hists = hists;
@@ -371,54 +388,98 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
         bool failed_reported = false;
         uint32_t warp_iters = 0;  // max over lanes of step iterations, summed over intervals
 
+        auto report_failure = [&](int k) {
+            failed_reported = true;
+            bool queued = false;
+            if (T.status != ST_MAXITERS) {
+                atomicAdd(&A.u64[CNT_FAILED], 1ull);
+                const bool can_redo = A.fail_out && A.smp.kind != DTWA_SAMPLER_HOST_ARRAY && A.smp.kind != DTWA_SAMPLER_DEVICE_ARRAY;
+                if (can_redo) {
+                    const unsigned pos = atomicAdd(A.fail_count, 1u);
+                    if (pos < A.fail_cap) {
+                        FailRec r;
+                        r.idx = idx;
+                        r.k = k;
+                        r.pad = 0;
+                        A.fail_out[pos] = r;
+                        queued = true;
+                    }
+                }
+            }
+            if (!queued) atomicAdd(&A.u64[CNT_UNFINISHED], 1ull);
+        };
+        auto reduce_at = [&](bool valid, int k, int w) {   // observables + reducers into the window staging
+            if constexpr (JIT)
+                jit_reduce<NV, PERLANE>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0,
+                                        valid, k, w);
+            else
+                vm_run<NV, PERLANE>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0,
+                                    valid, k, w, nullptr);
+        };
+
         for (int k0 = 0; k0 < nt; k0 += W) {
             const int nw = min(W, nt - k0);
-            for (int w = 0; w < nw; ++w) {
-                const int k = k0 + w;
-                const uint32_t it = T.advance(A.S, k);
-                if constexpr (Traj<SYS, ALG>::FIXED)
-                    warp_iters += it;
-                else
-                    warp_iters += __reduce_max_sync(0xffffffffu, it);
-                if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
-                if (T.status != ST_OK && T.status != ST_INACTIVE && !failed_reported) {
-                    failed_reported = true;
-                    bool queued = false;
-                    if (T.status != ST_MAXITERS) {
-                        atomicAdd(&A.u64[CNT_FAILED], 1ull);
-                        const bool can_redo = A.fail_out && A.smp.kind != DTWA_SAMPLER_HOST_ARRAY &&
-                                              A.smp.kind != DTWA_SAMPLER_DEVICE_ARRAY;
-                        if (can_redo) {
-                            const unsigned pos = atomicAdd(A.fail_count, 1u);
-                            if (pos < A.fail_cap) {
-                                FailRec r;
-                                r.idx = idx;
-                                r.k = k;
-                                r.pad = 0;
-                                A.fail_out[pos] = r;
-                                queued = true;
+            if constexpr (FIXED) {
+                // all lanes take the same steps: advance together, reduce with warp shuffles
+                for (int w = 0; w < nw; ++w) {
+                    const int k = k0 + w;
+                    warp_iters += T.advance(A.S, k);
+                    if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
+                    if (T.status != ST_OK && T.status != ST_INACTIVE && !failed_reported) report_failure(k);
+                    const bool valid = (T.status == ST_OK) && (k >= start_k);
+                    reduce_at(valid, k, w);
+                    const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
+                    if (lane == 0 && nv) atomicAdd(&V.nvalid[w], nv);
+                }
+            } else {
+                // Flat loop: in every iteration each lane that still owes a step attempts ONE step, and
+                // lanes that have reached their next output time emit it.  Lanes progress through the
+                // window's output times independently, so a lane that needs fewer steps in one interval
+                // is not idle while the others finish it; they only wait for each other at the window end.
+                int k = k0;
+                const int kend = k0 + nw;
+                double tstop = A.S.ts[k0];
+                uint32_t iters = 0;
+#pragma unroll 1
+                while (true) {
+                    const bool act = (T.status == ST_OK) && (k < kend);
+                    if (!__any_sync(0xffffffffu, act)) break;
+                    ++iters;
+                    if (act) {
+                        if (T.ad.t < tstop) {
+                            if ((long long)(T.nacc + T.nrej) >= A.S.maxiters) {
+                                T.status = ST_MAXITERS;
+                            } else {
+                                bool accepted;
+                                if (T.ad.attempt(A.S.par, T.u, tstop, A.S.tol, A.S.dtmin, accepted)) T.status = ST_DOMAIN;
+                                if (accepted)
+                                    ++T.nacc;
+                                else if (T.status == ST_OK)
+                                    ++T.nrej;
                             }
                         }
+                        if (T.status == ST_OK && !(T.ad.t < tstop)) {
+                            const bool valid = (k >= start_k);
+                            reduce_at(valid, k, k - k0);
+                            if (valid) atomicAdd(&V.nvalid[k - k0], 1u);
+                            ++k;
+                            if (k < kend) tstop = A.S.ts[k];
+                        }
                     }
-                    if (!queued) atomicAdd(&A.u64[CNT_UNFINISHED], 1ull);
                 }
-                const bool valid = (T.status == ST_OK) && (k >= start_k);
-                // observables + reducers into this warp's / CTA's window staging
-                if constexpr (JIT)
-                    jit_reduce<NV>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0,
-                                   valid, k, w);
-                else
-                    vm_run<NV>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0,
-                               valid, k, w, nullptr);
-                const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
-                if (lane == 0 && nv) atomicAdd(&V.nvalid[w], nv);
+                warp_iters += iters;
+                if (T.status != ST_OK && T.status != ST_INACTIVE && !failed_reported) report_failure(k);
             }
             // ---- once per window: CTA-wide flush in a fixed order (deterministic sums) ----
             __syncthreads();
             for (int i = threadIdx.x; i < nw * A.nslots; i += blockDim.x) {
                 const int w = i / A.nslots, sl = i - w * A.nslots;
                 double s = 0.0;
-                for (int wp = 0; wp < nwarps; ++wp) s = __dadd_rn(s, V.wsum[((size_t)wp * W + w) * A.nslots + sl]);
+                for (int rw = 0; rw < rows; ++rw) {
+                    double *cell = &V.wsum[((size_t)rw * W + w) * A.nslots + sl];
+                    s = __dadd_rn(s, *cell);
+                    if constexpr (PERLANE) *cell = 0.0;  // a lane that failed or finished early leaves zeros behind
+                }
                 // only this CTA ever adds to its partial row: RED in program order => reproducible
                 atomicAdd(&my_partial[(size_t)(k0 + w) * A.nslots + sl], s);
             }
@@ -553,7 +614,7 @@ __global__ void eval_kernel(const VmIns *__restrict__ prog, const double *__rest
         for (int i = 0; i < NV; ++i) x[i] = u[j * NV + i];
     }
     double outv = 0.0;
-    vm_run<NV>(V, nullptr, nullptr, x[0], x[1], x[2], x[3], j < n, 0, 0, &outv);
+    vm_run<NV, false>(V, nullptr, nullptr, x[0], x[1], x[2], x[3], j < n, 0, 0, &outv);
     if (j < n) v[j] = outv;
 }
 

@@ -76,9 +76,11 @@ mutable struct CResult
     lane_steps::UInt64
     resample_rounds::Int32
     launches::Int32
+    jit::Int32
+    reserved::Int32
     kernel_ms::Float64
     total_ms::Float64
-    CResult() = new(C_NULL, C_NULL, 0, 0, 0, 0, 0, 0, 0, 0.0, 0.0)
+    CResult() = new(C_NULL, C_NULL, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.0, 0.0)
 end
 
 const SYS_DICKE, SYS_LMG = Int32(0), Int32(1)
