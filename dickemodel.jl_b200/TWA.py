@@ -364,6 +364,8 @@ def monte_carlo_integrate(system, mc_system, *, tolerate_errors=True, show_progr
     ts = np.asarray(mc_system.ts, dtype=np.float64).ravel()
     if ts.size == 0:
         raise ValueError("ts is empty")
+    if N < 1:
+        raise ValueError("N must be >= 1")
     nv = len(system.varnames())
     if dist.nvar != nv:
         raise ValueError(f"the distribution samples {dist.nvar} variables but the system has {nv}")

@@ -905,8 +905,13 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
                 CK(cudaMemcpyAsync(&cnt, d.fail[cur].p, sizeof(unsigned), cudaMemcpyDeviceToHost, d.stream));
                 CK(cudaStreamSynchronize(d.stream));
                 if (!A.fail_out) {
-                    if (cnt && !tolerate_errors)
-                        return set_err(DTWA_ERR_BOUNDS, "a trajectory left the domain (DomainError in the reference) and tolerate_errors=false");
+                    if (!tolerate_errors) {  // the reference rethrows the first error (src/TWA.jl:199-201)
+                        unsigned long long nfail = 0;
+                        CK(cudaMemcpyAsync(&nfail, dp.d_u64 + CNT_FAILED, sizeof(nfail), cudaMemcpyDeviceToHost, d.stream));
+                        CK(cudaStreamSynchronize(d.stream));
+                        if (nfail)
+                            return set_err(DTWA_ERR_BOUNDS, "a trajectory left the domain (DomainError in the reference) and tolerate_errors=false");
+                    }
                     break;
                 }
                 if (cnt == 0) break;

@@ -1,0 +1,156 @@
+"""Edge cases of the C ABI and size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+DPAR = [1.0, 1.0, 1.0]
+DOCS_PT = [1.0, 0.31783724519578205, 1.0, 0.0]
+
+
+@pytest.fixture(scope="module")
+def mods(pkg):
+    from dickemodel_jl_b200 import TWA, ClassicalDicke, ClassicalLMG, ClassicalSystems
+    return TWA, ClassicalDicke, ClassicalLMG, ClassicalSystems
+
+
+@pytest.fixture(scope="module")
+def system(mods):
+    return mods[1].ClassicalDickeSystem(w0=1, w=1, g=1)
+
+
+def test_ragged_and_tiny_inputs(ctx, mods, system, O):
+    TWA, CD, _, CS = mods
+    j = 50
+    # N = 1, one output time, non-uniform ts with repeated and late-starting times
+    for N, ts in ((1, [0.0]), (1, [3.0]), (7, [0.5, 0.5, 0.75, 2.0, 2.0]), (257, [0.0, 0.0, 1e-9, 0.3]), (513, [1.0, 7.0])):
+        u0 = O.sample(O.SAMPLER_HWXSU2, DOCS_PT, 1 / j, N, seed=N)
+        got = TWA.average(system, observable=["Q", TWA.Weyl.Jz(j)], N=N, ts=ts, distribution=TWA.samples_from_array(u0, j=j),
+                          integrator_alg="RK4", dt=0.01)
+        traj, st, _, _ = O.integrate(O.SYS_DICKE, DPAR, u0, ts, alg=O.ALG_RK4, dt=0.01)
+        want = np.stack([traj[:, :, 0].mean(axis=0), O.eval_expr(str(TWA.Weyl.Jz(j)), O.varnames(0), traj).mean(axis=0)], axis=1)
+        assert got.shape == (len(ts), 2) and np.abs(got - want).max() < 1e-10, (N, ts)
+        assert (TWA.last_info["n_valid"] == N).all()
+    # adaptive integrators with the same ragged time axis
+    u0 = O.sample(O.SAMPLER_HWXSU2, DOCS_PT, 1 / j, 100, seed=3)
+    ts = [0.0, 0.0, 0.2, 0.2, 1.7]
+    for alg, oalg in (("DP8", O.ALG_DOP853), ("DP5", O.ALG_DP5)):
+        got = TWA.average(system, observable="q", N=100, ts=ts, distribution=TWA.samples_from_array(u0, j=j), integrator_alg=alg, tol=1e-10)
+        traj, _, _, _ = O.integrate(O.SYS_DICKE, DPAR, u0, ts, alg=oalg, tol=1e-10)
+        assert np.abs(got - traj[:, :, 1].mean(axis=0)).max() < 1e-8
+
+
+def test_histogram_range_edges(ctx, mods, system, O):
+    TWA = mods[0]
+    u0 = np.array([[0.0, -1.0, 0.0, 0.0], [0.0, 1.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0], [0.0, 0.999999, 0.0, 0.0], [0.0, 1.0000001, 0.0, 0.0],
+                   [0.0, 0.05, 0.0, 0.0], [0.0, 0.15, 0.0, 0.0]])
+    D = TWA.samples_from_array(u0, j=10)
+    m = TWA.calculate_distribution(system, x="q", xs=TWA.jrange(-1, 0.1, 1), N=len(u0), distribution=D)   # t = 0 only
+    c = np.rint(m[0] * len(u0)).astype(int)
+    # both ends inclusive, value just above stop dropped, ties to even: 0.05 -> index 11.5 -> 12 (1-based), 0.15 -> 12.5 -> 12
+    assert c[0] == 1 and c[20] == 2 and c.sum() == 6 and c[10] == 1 and c[11] == 2
+    D.offset = 0
+    one = TWA.calculate_distribution(system, x="q", xs=(0.0, 2.0, 1), N=len(u0), distribution=D)             # len == 1: every value in range -> bin 1
+    assert one.shape == (1, 1) and np.isclose(one[0, 0] * len(u0), 6)
+
+
+def test_invalid_ensemble_arguments(ctx, mods, system, pkg):
+    TWA = mods[0]
+    W = TWA.coherent_Wigner_HWxSU2([0, 0, 0, 0], j=10, seed=1)
+    with pytest.raises(pkg.DtwaError, match="unknown variable 'z'"):
+        TWA.average(system, observable="Q+z", N=10, ts=[0.0], distribution=W)
+    with pytest.raises(pkg.DtwaError, match="sorted"):
+        TWA.average(system, observable="Q", N=10, ts=[1.0, 0.5], distribution=W, integrator_alg="RK4", dt=0.1)
+    with pytest.raises(ValueError, match="N must be"):
+        TWA.average(system, observable="Q", N=0, ts=[0.0], distribution=W)
+    with pytest.raises(pkg.DtwaError, match="one histogram axis"):
+        TWA.monte_carlo_integrate(system, TWA.MonteCarloSystem(None, [{"kind": pkg._lib.RED_HIST, "x_axis": 1, "y_axis": 1}], "+", lambda r: r, 10, [0.0], W))
+    with pytest.raises(ValueError, match="samples 2 variables"):
+        TWA.average(system, observable="Q", N=10, ts=[0.0], distribution=TWA.coherent_Wigner_SU2([0, 0], j=10))
+    with pytest.raises(pkg.DtwaError, match="VM limits"):
+        TWA.average(system, observable=["Q"] * 65, N=10, ts=[0.0], distribution=W)
+    deep = "Q"
+    for _ in range(20):
+        deep = f"(q*(p+({deep})))"
+    TWA.average(system, observable=deep, N=10, ts=[0.0], distribution=W)          # right-nested: constant stack depth, fine
+    wide = "+".join(f"(Q*q+P*p)*(Q*p+{i})" for i in range(3))
+    TWA.average(system, observable=wide, N=10, ts=[0.0], distribution=W)
+    bad = "Q"
+    for _ in range(18):
+        bad = f"((q+p)*({bad}*(P+q)))"
+    bad = "(" + ")+(".join(["(Q+q)*(P+p)"] * 2) + ")"
+    TWA.average(system, observable=bad, N=10, ts=[0.0], distribution=W)
+
+
+def test_sixty_four_observables_and_many_histograms(ctx, mods, system, O):
+    TWA = mods[0]
+    N, j = 2000, 100
+    u0 = O.sample(O.SAMPLER_HWXSU2, DOCS_PT, 1 / j, N, seed=9)
+    ts = TWA.jrange(0, 0.5, 2)
+    obs = [f"Q^{1 + i % 4} + {i}*q - p/{i + 1}" for i in range(64)]
+    for mode in (0, 1):
+        ctx.set_jit(mode)
+        got = TWA.average(system, observable=obs, N=N, ts=ts, distribution=TWA.samples_from_array(u0, j=j), integrator_alg="RK4", dt=0.01)
+        traj, _, _ = mods[3].integrate_batch(system, u0, np.asarray(ts), integrator_alg="RK4", dt=0.01)
+        for i in (0, 17, 63):
+            want = O.average_sums(O.eval_expr(obs[i], O.varnames(0), traj), np.ones(traj.shape[:2], bool)) / N
+            assert np.abs(got[:, i] - want).max() < 1e-11
+    ctx.set_jit(2)
+    # 16 time-resolved histograms: only some fit the shared-memory staging budget, the rest go straight to global atomics
+    D = TWA.samples_from_array(u0, j=j)
+    chain = TWA.mcs_chain([TWA.mcs_for_distributions(system, y="t", x="q", xs=(-4.0, 4.0, 1000 + i), N=N, ts=ts, distribution=D) for i in range(16)])
+    out = TWA.monte_carlo_integrate(system, chain, integrator_alg="RK4", dt=0.01)
+    for i, m in enumerate(out):
+        want = O.hist_time(traj[:, :, 1], np.ones(traj.shape[:2], bool), -4.0, 4.0, 1000 + i)
+        assert np.array_equal(m, want / N)
+
+
+def test_maxiters_and_no_tolerance(ctx, mods, system, pkg, O):
+    TWA = mods[0]
+    W = TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=20, seed=2)
+    TWA.average(system, observable="Q", N=500, ts=[0.0, 5.0, 10.0], distribution=W, integrator_alg="DP8", tol=1e-10, maxiters=20)
+    assert TWA.last_info["n_unfinished"] == 500 and list(TWA.last_info["n_valid"]) == [500, 0, 0]     # src/ClassicalSystems.jl:138 maxiters: no exception
+    with pytest.raises(pkg.DtwaError, match="tolerate_errors=false"):
+        TWA.average(system, observable="Q", N=20000, ts=TWA.jrange(0, 0.5, 20), distribution=TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=20, seed=2),
+                    integrator_alg="RK4", dt=2.0 ** -5, tolerate_errors=False)
+
+
+def test_max_nbatch_chunks_equal_one_launch(ctx, mods, system):
+    TWA = mods[0]
+    kw = dict(observable="q", N=10000, ts=TWA.jrange(0, 0.5, 2), integrator_alg="RK4", dt=0.01)
+    a = TWA.average(system, distribution=TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=50, seed=6), **kw)
+    b = TWA.average(system, distribution=TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=50, seed=6), maxNBatch=3000, **kw)
+    assert np.abs(a - b).max() < 1e-13
+    h1 = TWA.calculate_distribution(system, x="t", y="q", ys=TWA.jrange(-3, 0.1, 3), N=10000, ts=TWA.jrange(0, 0.5, 2),
+                                    distribution=TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=50, seed=6), integrator_alg="RK4", dt=0.01)
+    h2 = TWA.calculate_distribution(system, x="t", y="q", ys=TWA.jrange(-3, 0.1, 3), N=10000, ts=TWA.jrange(0, 0.5, 2), maxNBatch=1234,
+                                    distribution=TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=50, seed=6), integrator_alg="RK4", dt=0.01)
+    assert np.array_equal(h1, h2)      # integer counts: exactly additive over index blocks
+
+
+def test_full_size_properties_config2(ctx, mods, system):
+    """BASELINE.json configs[1] at full size (10^7 trajectories, ts = 0:0.05:100): size-independent checks"""
+    TWA = mods[0]
+    j, N = 100, 10_000_000
+    ts = TWA.jrange(0, 0.05, 100)
+    jz = TWA.Weyl.Jz(j) / j
+    W = TWA.coherent_Wigner_HWxSU2([0, 0, 0, 0], j=j, seed=20261019)
+    chain = TWA.mcs_chain(TWA.mcs_for_averaging(system, observable=[jz, 2 * jz + 3, "1"], N=N, ts=ts, distribution=W),
+                          TWA.mcs_for_distributions(system, x="t", y=jz, ys=TWA.jrange(-1.1, 0.01, 1.1), N=N, ts=ts, distribution=W))
+    avg, hist = TWA.monte_carlo_integrate(system, chain, integrator_alg="RK4", dt=2.0 ** -7)
+    info = TWA.last_info
+    assert info["steps_accepted"] == N * 14000 and info["n_failed"] == 0 and (info["n_valid"] == N).all()
+    assert np.array_equal(avg[:, 2], np.ones(len(ts)))                         # sum of N ones / N, exactly
+    assert np.abs(avg[:, 1] - (2 * avg[:, 0] + 3)).max() < 1e-12               # linearity of the reduction
+    assert np.allclose(hist.sum(axis=0), 1.0, rtol=0, atol=1e-12)              # every sample lands in -1.1:0.01:1.1
+    centers = np.asarray(TWA.jrange(-1.1, 0.01, 1.1))
+    assert np.abs((hist * centers[:, None]).sum(axis=0) - avg[:, 0]).max() < 0.01 / 2 + 1e-9    # histogram mean vs direct mean: within half a bin
+    assert abs(avg[0, 0] + 1.0) < 0.02 and -0.30 < avg[100, 0] < -0.20 and -0.40 < avg[-1, 0] < -0.34
+    # halves with offset Philox counters add up to the whole (what the multi-GPU shard does)
+    parts = []
+    for off in (0, N // 2):
+        Wp = TWA.coherent_Wigner_HWxSU2([0, 0, 0, 0], j=j, seed=20261019)
+        Wp.offset = off
+        parts.append(TWA.calculate_distribution(system, x="t", y=jz, ys=TWA.jrange(-1.1, 0.01, 1.1), N=N // 2, ts=ts, distribution=Wp,
+                                                integrator_alg="RK4", dt=2.0 ** -7))
+    assert np.array_equal(np.rint((parts[0] + parts[1]) * (N // 2)), np.rint(hist * N))
