@@ -77,6 +77,14 @@ def clocks_summary(path, device_index):
     return {"sm_mhz": statistics.median(busy), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU arm)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference(N, threads, ts):
     """the restated reference CPU path on `N` trajectories of the bench workload"""
     from oracle import oracle as O
@@ -95,7 +103,7 @@ def run_reference(args):
     from oracle import oracle as O
     from dickemodel_jl_b200_loader import TWA  # noqa: F401  (only for jrange)
     ts = np.asarray(TWA.jrange(0, WORK["t_step"], WORK["t_end"]))
-    threads = O.max_threads()
+    threads = host_threads()
     pilot_n = 64 * threads
     cpu_reference(threads, threads, ts)   # load the library, spin up the OpenMP team
     r, dt = cpu_reference(pilot_n, threads, ts)
@@ -261,7 +269,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle as O
-        threads = O.max_threads()
+        threads = host_threads()
         tsn = np.asarray(ts)
         cpu_reference(threads, threads, tsn)
         r, dtp = cpu_reference(32 * threads, threads, tsn)
@@ -279,6 +287,9 @@ def main():
         cpu["mc_standard_error_bound"] = float(4.0 / np.sqrt(n_cpu))
 
     if rank == 0:
+        if not (abs(float(last[0]) + 1.0) < 0.02 and steps_done == args.steps * N_total * 14000):
+            raise SystemExit(f"bench self-check failed: <Jz>/j(t=0) = {float(last[0])}, steps counted {steps_done} "
+                             f"(expected {args.steps * N_total * 14000}): the per-rank arenas were not merged")
         line = {
             "metric": "FP64 trajectory-steps/s", "value": value, "unit": "trajectory-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,

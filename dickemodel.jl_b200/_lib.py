@@ -139,7 +139,11 @@ class Context:
         if devices is None:
             devices = [0]
         ids = (C.c_int * len(devices))(*devices)
-        _check(L.dtwa_create(C.byref(h), ids, len(devices), C.c_void_p(stream) if stream else None))
+        # stream: None -> the library creates a private non-blocking stream; an int is a cudaStream_t handle,
+        # where 0 (the legacy default stream, what torch.cuda.current_stream().cuda_stream returns by default)
+        # is passed as cudaStreamLegacy (0x1) because NULL means "private stream" in the C ABI
+        sp = None if stream is None else C.c_void_p(int(stream) if int(stream) != 0 else 1)
+        _check(L.dtwa_create(C.byref(h), ids, len(devices), sp))
         self._h = h
         self.devices = list(devices)
 

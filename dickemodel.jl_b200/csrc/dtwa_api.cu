@@ -963,6 +963,12 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
         int r2 = n.GroupEnd();
         if (r || r2) rc = set_err(DTWA_ERR_NCCL, std::string("ncclAllReduce: ") + n.GetErrorString(r ? r : r2));
     }
+    // every kernel (incl. the merge of the partial sums) has completed when launch returns, so a caller
+    // may all-reduce the arenas on any stream of its own before dtwa_plan_fetch
+    for (int di = 0; di < ndev && !rc; ++di) {
+        if (cudaSetDevice(ctx->devs[di].device) != cudaSuccess || cudaStreamSynchronize(ctx->devs[di].stream) != cudaSuccess)
+            rc = set_err(DTWA_ERR_CUDA, std::string("stream synchronize: ") + cudaGetErrorString(cudaGetLastError()));
+    }
     if (rc) {
         dtwa_plan_free(plan);
         return rc;

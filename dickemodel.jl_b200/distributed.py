@@ -33,6 +33,8 @@ def torch_allreduce(device_index: int, group=None):
         if n_u64:
             t = torch.as_tensor(_CudaArray(p_u64, n_u64, "<i8"), device=dev)   # two's complement: same bits as u64 sum
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        # dtwa_plan_fetch reads the arenas on the library's stream: make the collectives visible first
+        torch.cuda.current_stream(dev).synchronize()
     return allreduce
 
 

@@ -162,7 +162,8 @@ const char *dtwa_last_error(void);
 int dtwa_version(void);
 /* device_ids[ndev]; ndev>1 shards [0,N) by contiguous index blocks over the devices of one
  * process and merges the per-time arrays with one grouped ncclAllReduce (libnccl is dlopen'ed).
- * stream: an existing cudaStream_t (as void*) to enqueue on when ndev==1, or NULL for a private one. */
+ * stream: an existing cudaStream_t (as void*) to enqueue on when ndev==1, or NULL for a private
+ * non-blocking one (pass cudaStreamLegacy / cudaStreamPerThread to name the default streams). */
 int dtwa_create(dtwa_ctx **out, const int *device_ids, int ndev, void *stream);
 int dtwa_destroy(dtwa_ctx *ctx);
 /* name[256]; sm_count, clock_khz, cc (major*10+minor) */
@@ -211,8 +212,9 @@ int dtwa_ensemble(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol,
                   dtwa_result *res);
 
 /* Split form for one-process-per-GPU jobs: launch leaves the reduced accumulators of this rank in
- * two device arenas (f64 sums, u64 counts+counters) that the host framework all-reduces (NCCL
- * ncclSum) on the same stream before fetch unpacks them into the caller's buffers. */
+ * two device arenas (f64 sums, u64 counts+counters) and returns when they are complete; the host
+ * framework all-reduces them (NCCL ncclSum) and makes the result visible (stream/event sync) before
+ * fetch unpacks them into the caller's buffers. */
 int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const dtwa_sampler *smp,
                          int64_t N, const double *ts, int32_t nt, const dtwa_reducer *red, int32_t nred,
                          int32_t tolerate_errors, dtwa_plan **plan);

@@ -1,0 +1,62 @@
+"""One process per GPU over NCCL (the bench.py --gpus N path): needs >= 2 GPUs, skipped otherwise."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, json
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["DTWA_ROOT"])
+import __graft_entry__ as graft
+pkg = graft.load_package()
+from dickemodel_jl_b200 import TWA, ClassicalDicke as CD
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+pkg.set_default_context(pkg.Context([local], stream=torch.cuda.current_stream().cuda_stream))
+pkg.set_distributed(rank, world, pkg.distributed.torch_allreduce(local))
+system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+N, j = 200001, 100
+ts = TWA.jrange(0, 0.1, 5)
+jz = TWA.Weyl.Jz(j) / j
+W = TWA.coherent_Wigner_HWxSU2([1.0, 0.31783724519578205, 1.0, 0.0], j=j, seed=5)
+chain = TWA.mcs_chain(TWA.mcs_for_averaging(system, observable=jz, N=N, ts=ts, distribution=W),
+                      TWA.mcs_for_distributions(system, x="t", y=jz, ys=TWA.jrange(-1.1, 0.01, 1.1), N=N, ts=ts, distribution=W))
+avg, hist = TWA.monte_carlo_integrate(system, chain, integrator_alg="RK4", dt=2.0 ** -6)
+if rank == 0:
+    print(json.dumps({"avg": avg.tolist(), "hist": np.rint(hist * N).astype(int).tolist(), "steps": TWA.last_info["steps_accepted"],
+                      "n_valid": [int(x) for x in TWA.last_info["n_valid"]]}))
+dist.destroy_process_group()
+'''
+
+
+def test_two_ranks_reproduce_the_single_rank_result(tmp_path, pkg):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from dickemodel_jl_b200 import TWA, ClassicalDicke as CD
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, DTWA_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29617", str(script)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    two = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    N, j = 200001, 100
+    ts = TWA.jrange(0, 0.1, 5)
+    jz = TWA.Weyl.Jz(j) / j
+    W = TWA.coherent_Wigner_HWxSU2([1.0, 0.31783724519578205, 1.0, 0.0], j=j, seed=5)
+    chain = TWA.mcs_chain(TWA.mcs_for_averaging(system, observable=jz, N=N, ts=ts, distribution=W),
+                          TWA.mcs_for_distributions(system, x="t", y=jz, ys=TWA.jrange(-1.1, 0.01, 1.1), N=N, ts=ts, distribution=W))
+    avg, hist = TWA.monte_carlo_integrate(system, chain, integrator_alg="RK4", dt=2.0 ** -6)
+    assert np.array_equal(np.rint(hist * N).astype(int), np.array(two["hist"]))          # integer counts: bit-identical for any rank count
+    assert np.abs(avg - np.array(two["avg"])).max() < 1e-12
+    assert TWA.last_info["steps_accepted"] == two["steps"] and [int(x) for x in TWA.last_info["n_valid"]] == two["n_valid"]

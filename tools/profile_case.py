@@ -20,6 +20,7 @@ ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--block", type=int, default=0)
 ap.add_argument("--ctas-per-sm", type=int, default=0)
 ap.add_argument("--hist", action="store_true", help="config-3 style chain: jz-vs-t and q-vs-t histograms")
+ap.add_argument("--mode", default="", choices=["", "hist2d", "animate", "variance", "survival", "chain3"])
 ap.add_argument("--state", default="A", choices=["A", "B"])
 ap.add_argument("--tol", type=float, default=1e-8)
 ap.add_argument("--jit", type=int, default=2)
@@ -38,7 +39,19 @@ jz = TWA.Weyl.Jz(j) / j
 kw = dict(integrator_alg="RK4", dt=2.0 ** -7) if a.alg == "RK4" else dict(integrator_alg=a.alg, tol=a.tol)
 for rep in range(a.reps):
     W = TWA.coherent_Wigner_HWxSU2(center, j=j, seed=20261019)
-    if a.hist:
+    qs, ps = TWA.jrange(-4.3, 0.02, 4.3), TWA.jrange(-2.4, 0.02, 2.4)
+    if a.mode == "hist2d":
+        out = TWA.calculate_distribution(system, x="q", xs=qs, y="p", ys=ps, ts=ts, N=a.n, distribution=W, **kw)
+    elif a.mode == "animate":
+        out = TWA.calculate_distribution(system, x="q", xs=TWA.jrange(-4.3, 0.04, 4.3), y="p", ys=TWA.jrange(-2.4, 0.04, 2.4), ts=ts, N=a.n, distribution=W, animate=True, **kw)
+    elif a.mode == "variance":
+        out = TWA.variance(system, observable=["Q", "q", "P", "p"], ts=ts, N=a.n, distribution=W, **kw)
+    elif a.mode == "survival":
+        out = TWA.survival_probability(system, ts=ts, N=a.n, distribution=W, **kw)
+    elif a.mode == "chain3":   # docs/src/TWAExamples.md:101-131
+        mk = lambda **k: TWA.mcs_for_distributions(system, N=a.n, distribution=W, ts=ts, **k)
+        out = TWA.monte_carlo_integrate(system, TWA.mcs_chain(mk(y="t", x="q", xs=qs), mk(x="t", y="p", ys=ps), mk(x="q", xs=qs, y="p", ys=ps)), **kw)
+    elif a.hist:
         mk = lambda **k: TWA.mcs_for_distributions(system, N=a.n, distribution=W, ts=ts, **k)
         out = TWA.monte_carlo_integrate(system, TWA.mcs_chain(mk(x="t", y=jz, ys=TWA.jrange(-1.1, 0.01, 1.1)), mk(y="t", x="q", xs=TWA.jrange(-4.3, 0.02, 4.3))), **kw)
     else:
