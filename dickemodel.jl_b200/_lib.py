@@ -27,7 +27,7 @@ AXIS_EXPR, AXIS_TIME = 0, 1
 EXPORTS = ["dtwa_last_error", "dtwa_version", "dtwa_create", "dtwa_destroy", "dtwa_device_info", "dtwa_set_launch",
            "dtwa_hamiltonian", "dtwa_integrate", "dtwa_sample", "dtwa_pdf", "dtwa_eval_expr", "dtwa_scale_to_index",
            "dtwa_ensemble", "dtwa_ensemble_launch", "dtwa_plan_arenas", "dtwa_plan_fetch", "dtwa_plan_free",
-           "dtwa_fp64_peak", "dtwa_set_jit", "dtwa_jit_compile"]
+           "dtwa_fp64_peak", "dtwa_fp64_peak_regs", "dtwa_set_jit", "dtwa_jit_compile"]
 
 
 class DtwaError(RuntimeError):
@@ -112,6 +112,7 @@ def load():
         L.dtwa_plan_fetch.argtypes = [vp, C.POINTER(Result)]
         L.dtwa_plan_free.argtypes = [vp]
         L.dtwa_fp64_peak.argtypes = [vp, dp, dp]
+        L.dtwa_fp64_peak_regs.argtypes = [vp, dp, dp]
         L.dtwa_set_jit.argtypes = [vp, C.c_int]
         L.dtwa_jit_compile.argtypes = [C.POINTER(System), C.POINTER(Solver), C.POINTER(C.c_char_p), C.c_int32, C.c_char_p,
                                        C.c_int64, C.POINTER(C.c_int64)]
@@ -175,6 +176,11 @@ class Context:
     def fp64_peak(self):
         tf, ms = C.c_double(), C.c_double()
         _check(load().dtwa_fp64_peak(self._h, C.byref(tf), C.byref(ms)))
+        return tf.value, ms.value
+
+    def fp64_peak_regs(self):
+        tf, ms = C.c_double(), C.c_double()
+        _check(load().dtwa_fp64_peak_regs(self._h, C.byref(tf), C.byref(ms)))
         return tf.value, ms.value
 
     # ---- batch helpers ----

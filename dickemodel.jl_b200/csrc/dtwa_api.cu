@@ -313,11 +313,44 @@ static int build_step_table(const double *ts, int nt, double dt, double wfold, s
     return 0;
 }
 
+// Uniform grid detection (same rule as oracle/oracle.c orc_step_table): if every interval after the
+// first has the same number of sub-steps and its length differs from the mean by no more than the
+// rounding noise of the ts values themselves (8 ulp of the largest time), all those intervals use one
+// sub-step h = (ts[nt-1] - ts[0]) / (n (nt-1)); interval 0 must be empty (ts[0] == 0) or of the same kind.
+static void detect_uniform(const double *ts, int nt, const std::vector<StepTab> &tab, double wfold, SolverArgs &S)
+{
+    S.uniform = 0;
+    S.first_n = 0;
+    std::memset(&S.uni, 0, sizeof(S.uni));
+    if (nt < 2 || tab[1].n < 1) return;
+    const int n = tab[1].n;
+    const double span = ts[nt - 1] - ts[0], mean = span / (double)(nt - 1);
+    const double noise = 8.0 * 2.220446049250313e-16 * std::fabs(ts[nt - 1]);
+    for (int k = 1; k < nt; ++k)
+        if (tab[k].n != n || std::fabs((ts[k] - ts[k - 1]) - mean) > noise) return;
+    if (!(tab[0].n == 0 || (tab[0].n == n && std::fabs(ts[0] - mean) <= noise))) return;
+    StepTab r;
+    std::memset(&r, 0, sizeof(r));
+    r.n = n;
+    r.h = mean / (double)n;
+    r.hh = r.h / 2.0;
+    r.h3 = r.h / 3.0;
+    r.h6 = r.h / 6.0;
+    r.hw = r.h * wfold;
+    r.hhw = r.hh * wfold;
+    r.h3w = r.h3 * wfold;
+    r.h6w = r.h6 * wfold;
+    S.uni = r;
+    S.uniform = 1;
+    S.first_n = tab[0].n;
+}
+
 static SolverArgs make_solver_args(const dtwa_system *sys, const dtwa_solver *sol, const StepTab *d_tab, const double *d_ts,
-                                   const double *ts, int nt)
+                                   const double *ts, int nt, const std::vector<StepTab> &tab)
 {
     SolverArgs S;
     S.par = make_par(sys, sol->backwards);
+    detect_uniform(ts, nt, tab, S.par.b, S);
     S.tab = d_tab;
     S.ts = d_ts;
     S.tol = sol->tol;
@@ -549,7 +582,7 @@ extern "C" int dtwa_integrate(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_
     CK(cudaMemcpyAsync(meta, tab.data(), tab_b, cudaMemcpyHostToDevice, d.stream));
     CK(cudaMemcpyAsync(meta + tab_b, ts, ts_b, cudaMemcpyHostToDevice, d.stream));
     CK(cudaMemcpyAsync(d.u0.p, u0, sizeof(double) * n * nv, cudaMemcpyHostToDevice, d.stream));
-    const SolverArgs S = make_solver_args(sys, sol, (const StepTab *)meta, (const double *)(meta + tab_b), ts, nt);
+    const SolverArgs S = make_solver_args(sys, sol, (const StepTab *)meta, (const double *)(meta + tab_b), ts, nt, tab);
     const unsigned grid = blocks_for(n, 128);
     by_system(sys->kind, [&](auto sk) {
         return by_alg(sol->alg, [&](auto ak) {
@@ -843,7 +876,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
             unsigned char *m = (unsigned char *)d.meta.p;
             EnsArgs &A = args[di];
             std::memset(&A, 0, sizeof(A));
-            A.S = make_solver_args(sys, sol, (const StepTab *)(m + o_t), (const double *)(m + o_s), ts, nt);
+            A.S = make_solver_args(sys, sol, (const StepTab *)(m + o_t), (const double *)(m + o_s), ts, nt, tab);
             A.smp = sp0;
             A.smp.offset = smp->offset + (uint64_t)dp.lo;
             if (smp->kind == DTWA_SAMPLER_HOST_ARRAY) {
@@ -1075,6 +1108,35 @@ extern "C" int dtwa_fp64_peak(dtwa_ctx *ctx, double *tflops, double *ms_out)
     for (int rep = 0; rep < 5; ++rep) {
         CK(cudaEventRecord(d.ev[0], d.stream));
         fp64_peak_kernel<<<grid, block, 0, d.stream>>>((double *)d.scratch_a.p, iters, 0.999999, 1e-7);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(d.ev[3], d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+        float m = 0.f;
+        CK(cudaEventElapsedTime(&m, d.ev[0], d.ev[3]));
+        if (rep > 0 && m < best) best = m;
+    }
+    const double flops = (double)grid * block * (double)iters * 64.0 * 2.0;
+    if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return DTWA_OK;
+}
+
+// K0b: DFMA rate with three distinct register operands per instruction (see fp64_peak_regs_kernel)
+extern "C" int dtwa_fp64_peak_regs(dtwa_ctx *ctx, double *tflops, double *ms_out)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    DevCtx &d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    const int block = 256, grid = d.sm_count * 8, iters = 4096;
+    TRY(d.scratch_a.ensure(sizeof(double) * (size_t)grid * block));
+    TRY(d.scratch_b.ensure(sizeof(double) * 64));
+    double host[64];
+    for (int i = 0; i < 64; ++i) host[i] = 1.0 + 1e-3 * i;
+    CK(cudaMemcpyAsync(d.scratch_b.p, host, sizeof(host), cudaMemcpyHostToDevice, d.stream));
+    double best = 1e30;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(d.ev[0], d.stream));
+        fp64_peak_regs_kernel<<<grid, block, 0, d.stream>>>((double *)d.scratch_a.p, (const double *)d.scratch_b.p, iters);
         CK(cudaGetLastError());
         CK(cudaEventRecord(d.ev[3], d.stream));
         CK(cudaStreamSynchronize(d.stream));

@@ -20,7 +20,16 @@ constexpr int ST_OK = DTWA_TRAJ_OK, ST_DOMAIN = DTWA_TRAJ_DOMAIN, ST_MAXITERS = 
 
 struct SolverArgs {
     SysPar par;
-    const StepTab *tab;  // [nt] fixed-step table
+    // Uniform output grids (Julia ranges -- every docs example): all intervals share ONE row, which then
+    // lives in kernel-parameter (constant-bank) space.  That matters: a DFMA with three distinct
+    // vector-register operands issues every 3 cycles (register-bank reads), one with a constant-bank
+    // operand every 2 (dtwa_fp64_peak_regs 24.7 vs dtwa_fp64_peak 34.2 TFLOP/s), and 28 of the 60
+    // DFMAs of an RK4 step multiply by a step constant.  Per-interval rows loaded from `tab` end up in
+    // vector registers (ptxas does not keep loaded values in uniform registers).
+    StepTab uni;
+    int32_t uniform;     // 1: intervals k >= 1 all use `uni`
+    int32_t first_n;     // sub-steps of interval 0 in uniform mode (0 when ts[0] == 0)
+    const StepTab *tab;  // [nt] fixed-step table (general case)
     const double *ts;    // [nt]
     double tol, dtmin, tend;
     long long maxiters;
@@ -59,16 +68,29 @@ struct Traj {
     __device__ __forceinline__ uint32_t advance(const SolverArgs &S, int k)
     {
         if constexpr (FIXED) {
-            const StepTab r = S.tab[k];
+            int n;
+            if (S.uniform) {
+                n = (k == 0) ? S.first_n : S.uni.n;
 #pragma unroll 1
-            for (int s = 0; s < r.n; ++s) {
-                if constexpr (ALG == DTWA_ALG_RK4)
-                    rk4_step<SYS>(S.par, u, r);
-                else
-                    rk8_step<SYS>(S.par, u, r.h);
+                for (int s = 0; s < n; ++s) {
+                    if constexpr (ALG == DTWA_ALG_RK4)
+                        rk4_step<SYS>(S.par, u, S.uni);  // constants are constant-bank operands
+                    else
+                        rk8_step<SYS>(S.par, u, S.uni.h);
+                }
+            } else {
+                const StepTab r = S.tab[k];
+                n = r.n;
+#pragma unroll 1
+                for (int s = 0; s < n; ++s) {
+                    if constexpr (ALG == DTWA_ALG_RK4)
+                        rk4_step<SYS>(S.par, u, r);
+                    else
+                        rk8_step<SYS>(S.par, u, r.h);
+                }
             }
-            if (status == ST_OK) nacc += (uint32_t)r.n;
-            return (uint32_t)r.n;
+            if (status == ST_OK) nacc += (uint32_t)n;
+            return (uint32_t)n;
         } else {
             uint32_t iters = 0;
             if (status == ST_OK) {
@@ -541,8 +563,9 @@ __global__ void __launch_bounds__(128) integrate_kernel(const SolverArgs S, cons
                                                         long long *__restrict__ nsteps)
 {
     constexpr int NV = Sys<SYS>::NV;
-    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    const long long j0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool live = j0 < n;
+    const long long j = live ? j0 : n - 1;  // tail lanes shadow the last trajectory: warp-wide ops need every lane
     Traj<SYS, ALG> T;
     T.status = ST_OK;
 #pragma unroll
@@ -552,12 +575,16 @@ __global__ void __launch_bounds__(128) integrate_kernel(const SolverArgs S, cons
     for (int k = 0; k < S.nt; ++k) {
         T.advance(S, k);
         if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
-        double *o = out + ((size_t)j * S.nt + k) * NV;
+        if (live) {
+            double *o = out + ((size_t)j * S.nt + k) * NV;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) o[i] = (T.status == ST_OK) ? T.u[i] : qnan;
+            for (int i = 0; i < NV; ++i) o[i] = (T.status == ST_OK) ? T.u[i] : qnan;
+        }
     }
-    status[j] = T.status;
-    if (nsteps) nsteps[j] = (long long)T.nacc + (long long)T.nrej;
+    if (live) {
+        status[j] = T.status;
+        if (nsteps) nsteps[j] = (long long)T.nacc + (long long)T.nrej;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -645,6 +672,31 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
         }
     }
     const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// K0b: the same 8 chains with three distinct REGISTER operands per DFMA (what an ODE right-hand side
+// looks like; K0's multiplier/addend are warp-uniform).  Reported next to K0 as the practical ceiling.
+__global__ void __launch_bounds__(256) fp64_peak_regs_kernel(double *out, const double *in, int iters)
+{
+    double x[8], y[8], z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x[i] = in[(threadIdx.x + i) & 63] + threadIdx.x * 1e-3;
+        y[i] = in[(threadIdx.x + 8 + i) & 63] * 0.999;
+        z[i] = in[(threadIdx.x + 16 + i) & 63] * 1e-7;
+    }
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = fma(x[i], y[i], z[(i + r) & 7]);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
     if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 

@@ -225,6 +225,8 @@ int dtwa_plan_free(dtwa_plan *plan);
 /* ---- K0: FP64 roofline denominator: a DFMA-chain micro-benchmark on every SM; returns the
  *      achieved TFLOP/s (FMA = 2 flops) and the kernel time ---- */
 int dtwa_fp64_peak(dtwa_ctx *ctx, double *tflops, double *ms);
+/* K0b: the same with three distinct register operands per DFMA (the practical ceiling of an ODE kernel) */
+int dtwa_fp64_peak_regs(dtwa_ctx *ctx, double *tflops, double *ms);
 
 #ifdef __cplusplus
 }

@@ -131,6 +131,18 @@ int orc_step_table(const double *ts, int nt, double dt, int *nsub, double *hsub)
         }
         tprev = ts[k];
     }
+    /* uniform grids (Julia ranges): one common sub-step, the library's detect_uniform rule */
+    if (nt >= 2 && nsub[1] >= 1) {
+        int n = nsub[1], ok = 1;
+        double span = ts[nt - 1] - ts[0], mean = span / (double)(nt - 1);
+        double noise = 8.0 * 2.220446049250313e-16 * fabs(ts[nt - 1]);
+        for (int k = 1; k < nt && ok; ++k)
+            if (nsub[k] != n || fabs((ts[k] - ts[k - 1]) - mean) > noise) ok = 0;
+        if (ok && !(nsub[0] == 0 || (nsub[0] == n && fabs(ts[0] - mean) <= noise))) ok = 0;
+        if (ok)
+            for (int k = 0; k < nt; ++k)
+                if (nsub[k]) hsub[k] = mean / (double)n;
+    }
     return 0;
 }
 
