@@ -286,6 +286,16 @@ def main():
         cpu["max_abs_diff_mean_jz_vs_gpu"] = float(np.max(np.abs(r["sums"][:, 0] / j / n_cpu - last)))
         cpu["mc_standard_error_bound"] = float(4.0 / np.sqrt(n_cpu))
 
+    # DRAM bytes of one launch of the dominant kernel, from the committed `ncu --set full` capture of this
+    # same workload (profiles/traffic_rk4_bench.json, written by tools/ncu_summary.py --traffic-json)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic_rk4_bench.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if int(tj.get("n_traj", 0)) == args.n_traj:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_src = tj.get("source")
+
     if rank == 0:
         if not (abs(float(last[0]) + 1.0) < 0.02 and steps_done == args.steps * N_total * 14000):
             raise SystemExit(f"bench self-check failed: <Jz>/j(t=0) = {float(last[0])}, steps counted {steps_done} "
@@ -301,10 +311,10 @@ def main():
             "e2e": e2e,
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / peak_tflops, "traffic": None,
+                         "frac": achieved_tflops / peak_tflops, "traffic": traffic, "traffic_source": traffic_src,
                          "flops_per_step": FLOPS_PER_STEP["dicke_rk4"],
                          "peak_source": "K0 DFMA-chain micro-benchmark run in this process (dtwa_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; nominal 37.2 TFLOP/s at 1965 MHz",
-                         "kernel": "ensemble_kernel<DICKE,RK4>", "kernel_ms_per_step": kernel_ms / args.steps,
+                         "kernel": "dtwa_jit_ensemble (NVRTC specialisation of ensemble_kernel<DICKE,RK4> for this reducer set)", "kernel_ms_per_step": kernel_ms / args.steps,
                          "kernel_steps_per_s_per_gpu": kern_rate,
                          "fp64_pipe_frac_est": kern_rate * FP64_INSTR_PER_STEP["dicke_rk4"] / (peak_tflops * 1e12 / 2.0),
                          "note": "frac is ALGORITHMIC flops (136/step) over the measured DFMA peak; fp64_pipe_frac_est counts the 92 FP64-pipe instructions/step of the SASS hot loop (w = 1 specialisation), each of which occupies one DFMA issue slot"},

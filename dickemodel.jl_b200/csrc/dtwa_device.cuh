@@ -27,17 +27,21 @@ struct SysPar {
     double a, b, c, d;  // Dicke: w0, w, g, -      LMG: Omega, xi, xi/2, 2*xi+Omega
 };
 
-// 1/sqrt(x) for x > 0: MUFU.RSQ64H seed (rel. err ~2^-22) + one third-order polish.  No special
-// cases: x <= 0 or non-finite yields NaN/Inf, which the domain checks catch.
-__device__ __forceinline__ double rsqrt_fast(double x)
+// 1/sqrt(x) and sqrt(x) for x > 0 together: MUFU.RSQ64H seed (rel. err ~2^-22) + one third-order
+// polish, six FP64 instructions.  No special cases: x <= 0 or non-finite yields NaN/Inf, which the
+// domain checks catch.  No instruction reads three distinct registers (a DFMA with three distinct
+// register operands needs three register-file cycles against two issue cycles, see
+// fp64_peak_regs_kernel) and sqrt(x) does not wait for 1/sqrt(x).
+__device__ __forceinline__ void rsqrt_sqrt_pair(double x, double &is, double &s)
 {
     double y0;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
-    double t = __dmul_rn(x, y0);
-    double e = fma(-t, y0, 1.0);           // 1 - x*y0^2
-    double p = fma(0.375, e, 0.5);         // 1/2 + 3/8 e
-    double ye = __dmul_rn(y0, e);
-    return fma(ye, p, y0);                 // y0 (1 + e/2 + 3/8 e^2)
+    const double t = __dmul_rn(x, y0);           // ~ sqrt(x)
+    const double e = fma(-t, y0, 1.0);           // 1 - x*y0^2
+    const double p = fma(0.375, e, 0.5);
+    const double ep = __dmul_rn(e, p);           // e/2 + 3/8 e^2
+    is = fma(y0, ep, y0);
+    s = fma(t, ep, t);
 }
 
 template <int SYS>
@@ -56,8 +60,8 @@ struct Sys<DTWA_SYS_DICKE> {
         const double Q = u[0], q = u[1], P = u[2], pp = u[3];
         double r2 = fma(-P, P, 4.0);
         r2 = fma(-Q, Q, r2);               // 4 - P^2 - Q^2
-        const double is = rsqrt_fast(r2);  // 1/s
-        const double s = __dmul_rn(r2, is);
+        double is, s;
+        rsqrt_sqrt_pair(r2, is, s);        // 1/s and s
         const double gq = __dmul_rn(p.c, q);
         const double gqQ = __dmul_rn(gq, Q);
         const double e = fma(gqQ, is, -p.a);      // g q Q / s - w0
@@ -122,13 +126,16 @@ struct Sys<DTWA_SYS_LMG> {
 template <int SYS>
 __device__ __forceinline__ bool state_bad(const double (&u)[Sys<SYS>::NV])
 {
-    // non-finite anywhere, or outside the chart 4 - P^2 - Q^2 > 0
-    double acc = 0.0;
-#pragma unroll
-    for (int i = 0; i < Sys<SYS>::NV; ++i) acc += __dmul_rn(u[i], 0.0);  // NaN/Inf -> NaN
+    // non-finite anywhere, or outside the chart 4 - P^2 - Q^2 > 0 (un-fused, src/ClassicalDicke.jl:19).
+    // A non-finite Q or P makes r2 NaN or -Inf; the other components are tested on their exponent
+    // bits (integer pipe -- this runs at every output time, next to a saturated FP64 pipe).
     const double Q = u[Sys<SYS>::QI], P = u[Sys<SYS>::PI];
     const double r2 = __dsub_rn(__dsub_rn(4.0, __dmul_rn(P, P)), __dmul_rn(Q, Q));
-    return !(acc == 0.0) || !(r2 > 0.0);
+    bool nonfinite = false;
+#pragma unroll
+    for (int i = 0; i < Sys<SYS>::NV; ++i)
+        if (i != Sys<SYS>::QI && i != Sys<SYS>::PI) nonfinite |= ((__double2hiint(u[i]) & 0x7ff00000) == 0x7ff00000);
+    return nonfinite || !(r2 > 0.0);
 }
 
 // ------------------------------------------------------------------------------------------------

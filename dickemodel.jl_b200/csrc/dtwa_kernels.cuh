@@ -144,6 +144,7 @@ struct EnsArgs {
     uint32_t attempt;  // resampling round (0 = first draw)
     int32_t nslots, nins, ncst, nrange, nhist, stage_bins;
     int32_t window;    // output times staged in shared memory between two CTA-wide flushes
+    int32_t pad0;
     const FailRec *redo;  // NULL in the main pass; else trajectory j re-draws redo[j].idx and contributes from redo[j].k
     FailRec *fail_out;
     unsigned *fail_count;
@@ -450,8 +451,10 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
                     if (T.status != ST_OK && T.status != ST_INACTIVE && !failed_reported) report_failure(k);
                     const bool valid = (T.status == ST_OK) && (k >= start_k);
                     reduce_at(valid, k, w);
-                    const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
-                    if (lane == 0 && nv) atomicAdd(&V.nvalid[w], nv);
+                    // fixed step: V.nvalid counts the threads that do NOT contribute (failed, inactive tail,
+                    // before start_k), so the common all-valid case costs one vote and no shared-memory atomic
+                    const unsigned inv = __ballot_sync(0xffffffffu, !valid);
+                    if (inv && lane == 0) atomicAdd(&V.nvalid[w], (unsigned)__popc(inv));
                 }
             } else {
                 // Flat loop: in every iteration each lane that still owes a step attempts ONE step, and
@@ -506,11 +509,9 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
                 atomicAdd(&my_partial[(size_t)(k0 + w) * A.nslots + sl], s);
             }
             for (int w = threadIdx.x; w < nw; w += blockDim.x) {
-                const unsigned c = V.nvalid[w];
-                if (c) {
-                    atomicAdd(&nvalid_g[k0 + w], (unsigned long long)c);
-                    V.nvalid[w] = 0u;
-                }
+                const unsigned c = FIXED ? blockDim.x - V.nvalid[w] : V.nvalid[w];
+                if (c) atomicAdd(&nvalid_g[k0 + w], (unsigned long long)c);
+                V.nvalid[w] = 0u;
             }
             for (int hI = 0; hI < A.nhist; ++hI) {
                 const HistDesc h = V.hists[hI];

@@ -17,6 +17,7 @@ ap.add_argument("--n", type=int, default=1 << 20)
 ap.add_argument("--tend", type=float, default=5.0)
 ap.add_argument("--alg", default="RK4")
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--tstep", type=float, default=0.05, help="output-time spacing")
 ap.add_argument("--block", type=int, default=0)
 ap.add_argument("--ctas-per-sm", type=int, default=0)
 ap.add_argument("--hist", action="store_true", help="config-3 style chain: jz-vs-t and q-vs-t histograms")
@@ -34,7 +35,7 @@ if a.block or a.ctas_per_sm:
 system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
 j = 100
 center = [0, 0, 0, 0] if a.state == "A" else [1.0, 0.31783724519578205, 1.0, 0.0]
-ts = TWA.jrange(0, 0.05, a.tend)
+ts = TWA.jrange(0, a.tstep, a.tend)
 jz = TWA.Weyl.Jz(j) / j
 kw = dict(integrator_alg="RK4", dt=2.0 ** -7) if a.alg == "RK4" else dict(integrator_alg=a.alg, tol=a.tol)
 for rep in range(a.reps):
