@@ -109,6 +109,38 @@ def minimum_ϵ_for(system, *, Q=None, q=None, P=None, p=None):
     raise NotImplementedError("Sorry, that combinanation of variables is not implemented")
 
 
+def _clamp(x, lo, hi):
+    return min(max(x, lo), hi)
+
+
+def maximum_P_for_ϵ(system, ϵ):
+    """src/ClassicalDicke.jl:351-360"""
+    w0, w, g = system.parameters()
+    if ϵ >= w0:
+        return 2.0
+    if w * w0 > math.sqrt(2) * g * math.sqrt(w * (w0 - ϵ)):
+        return math.sqrt(2 * (w0 + ϵ) / w0)
+    return math.sqrt(_clamp((2 * math.sqrt(2 * g ** 6 * w * (w0 - ϵ))) / (-g ** 4) + w * w0 / (g ** 2) + 4, 0, 4))
+
+
+def maximum_Q_for_ϵ(system, ϵ):
+    """src/ClassicalDicke.jl:372-378"""
+    w0, w, g = system.parameters()
+    if ϵ >= w0:
+        return 2.0
+    return math.sqrt(_clamp((4 * g ** 2 - w * w0) / (2 * g ** 2)
+                            + (1 / 2) * math.sqrt(max(0, (16 * g ** 4 + 8 * g ** 2 * ϵ * w + w ** 2 * w0 ** 2) / g ** 4)), 0, 4))
+
+
+def minimum_nonnegative_Q_for_ϵ(system, ϵ):
+    """src/ClassicalDicke.jl:390-396"""
+    w0, w, g = system.parameters()
+    if ϵ >= -w0:
+        return 0.0
+    return math.sqrt(_clamp((4 * g ** 2 - w * w0) / (2 * g ** 2)
+                            - (1 / 2) * math.sqrt(max(0, (16 * g ** 4 + 8 * g ** 2 * ϵ * w + w ** 2 * w0 ** 2) / g ** 4)), 0, 4))
+
+
 def q_of_ϵ(system, *, Q, P, p, ϵ, sgn="+", returnNaNonError=True):
     """src/ClassicalDicke.jl:255-273"""
     Δ = discriminant_of_q_solution(system, Q=Q, P=P, p=p, ϵ=ϵ)

@@ -2,8 +2,9 @@
 
 Mirrors src/ClassicalSystems.jl:19-45 (protocol) and :78-140 (integrate) of the reference.  The
 solve itself runs on the GPU through dtwa_integrate (include/dicketwa.h); nothing here integrates
-on the CPU.  Out of scope: get_fundamental_matrix, use_big_numbers,
-lyapunov_spectrum / lyapunov_exponent, DiffEq callbacks.
+on the CPU.  The fundamental matrix (get_fundamental_matrix, :110-128) and lyapunov_spectrum /
+lyapunov_exponent (:157-224) run on the GPU too (dtwa_integrate_fm, dtwa_lyapunov).  Out of scope
+(SURVEY.md section 8): use_big_numbers, DiffEq callbacks.
 """
 from __future__ import annotations
 
@@ -101,9 +102,12 @@ def solver_from_kargs(kargs: dict) -> _lib.Solver:
     maxiters = k.pop("maxiters", None)
     for ignored in ("save_everystep", "show_progress", "progress", "verbose", "dense"):
         k.pop(ignored, None)
-    for unsupported in ("get_fundamental_matrix", "use_big_numbers", "callback", "fundamental_matrix_initial"):
+    for unsupported in ("use_big_numbers", "callback"):
         if k.pop(unsupported, None):
             raise NotImplementedError(f"{unsupported} is outside the GPU hot path (SURVEY.md section 8)")
+    for unsupported in ("get_fundamental_matrix", "fundamental_matrix_initial"):   # integrate() handles these itself
+        if k.pop(unsupported, None) is not None:
+            raise NotImplementedError(f"{unsupported} is only available through ClassicalSystems.integrate / lyapunov_spectrum")
     if k:
         raise TypeError(f"unsupported solver keyword(s): {sorted(k)}")
     code = alg.code
@@ -132,6 +136,13 @@ class ODESolution:
     def __init__(self, system, u0, t0, t, u, retcode, nsteps, kargs):
         self._system, self._u0, self._t0, self._kargs = system, u0, t0, kargs
         self.t, self.u, self.retcode, self.nsteps = t, u, retcode, nsteps
+        self.fundamental_matrix = None   # [len(t)][nvar][nvar] when get_fundamental_matrix=True
+
+    def x(self, i=-1):
+        """`(x, Φ)` at saved time i -- the reference's `s.u[i].x` of an ArrayPartition (src/ClassicalSystems.jl:118)"""
+        if self.fundamental_matrix is None:
+            raise ValueError("integrate was called without get_fundamental_matrix=True")
+        return self.u[i], self.fundamental_matrix[i]
 
     def __call__(self, tq):
         tq = np.atleast_1d(np.asarray(tq, dtype=float))
@@ -165,12 +176,25 @@ def integrate(system, u0, t, *, t0=0.0, tol=1e-12, get_fundamental_matrix=False,
         raise ValueError(f"u₀ should have length {len(names)}, which is the dimension of the phase space of system")  # :97-99
     if system.out_of_bounds(u0):
         raise ValueError(f"The initial condition u₀={u0.tolist()} is out of bounds")  # :100-102
-    if get_fundamental_matrix or use_big_numbers or fundamental_matrix_initial is not None:
-        raise NotImplementedError("fundamental matrix / BigFloat integration is outside the GPU hot path (SURVEY.md section 8)")
+    if use_big_numbers:
+        raise NotImplementedError("BigFloat integration is outside the GPU hot path (SURVEY.md section 8)")
     sol = solver_from_kargs(dict(kargs, tol=tol, integrator_alg=integrator_alg, integate_backwards=integate_backwards))
     ts = np.array([t0, t], dtype=float) if saveat is None else np.atleast_1d(np.asarray(saveat, dtype=float))
     if np.any(ts < t0) or np.any(ts > t) or np.any(np.diff(ts) < 0):
         raise ValueError("saveat must be sorted and lie in [t₀, t]")
+    full_kargs = dict(kargs, tol=tol, integrator_alg=integrator_alg, integate_backwards=integate_backwards)
+    if get_fundamental_matrix:   # src/ClassicalSystems.jl:110-128
+        n = len(u0)
+        fm0 = None
+        if fundamental_matrix_initial is not None:
+            fm0 = np.asarray(fundamental_matrix_initial, dtype=np.float64)
+            if fm0.shape != (n, n):
+                raise ValueError(f"fundamental_matrix_initial should be a {n}x{n} matrix")
+            fm0 = fm0[None]
+        xs, fm, status, nsteps = _lib.default_context().integrate_fm(system._c_system(), sol, u0[None, :], ts - t0, fm0)
+        s = ODESolution(system, u0, t0, ts, xs[0], _RETCODES[int(status[0])], int(nsteps[0]), full_kargs)
+        s.fundamental_matrix = fm[0]
+        return s
     out, status, nsteps = _lib.default_context().integrate(system._c_system(), sol, u0[None, :], ts - t0)
     return ODESolution(system, u0, t0, ts, out[0], _RETCODES[int(status[0])], int(nsteps[0]),
                        dict(kargs, tol=tol, integrator_alg=integrator_alg, integate_backwards=integate_backwards))
@@ -183,9 +207,47 @@ def integrate_batch(system, U0, ts, **kargs):
     return _lib.default_context().integrate(system._c_system(), sol, U0, ts)
 
 
-def lyapunov_spectrum(*a, **k):
-    raise NotImplementedError("lyapunov_spectrum needs the variational system: out of scope (SURVEY.md section 8f, rank 2)")
+def integrate_fm_batch(system, U0, ts, fundamental_matrix_initial=None, **kargs):
+    """Many (x, Φ) trajectories at once: (x[n][nt][nvar], Φ[n][nt][nvar][nvar], status[n], nsteps[n])."""
+    sol = solver_from_kargs(kargs)
+    return _lib.default_context().integrate_fm(system._c_system(), sol, U0, ts, fundamental_matrix_initial)
 
 
-def lyapunov_exponent(*a, **k):
-    raise NotImplementedError("lyapunov_exponent needs the variational system: out of scope (SURVEY.md section 8f, rank 2)")
+last_lyapunov_info = {}
+
+
+def lyapunov_spectrum_batch(system, X, t=100, *, λtol=1e-4, λreltol=1e-3, maxiters=100, verbose=True, **kargs):
+    """lyapunov_spectrum for many initial conditions in one kernel launch (a Lyapunov map,
+    docs/src/ClassicalDickeExamples.md:133-236).  Returns (λ[n][nvar], status[n]); status 0 = converged,
+    _lib.LYAP_MAXITERS = "Maximum iterations", 1..3 = the integration failed (DTWA_TRAJ_*).  Details of the
+    last call (final points, iterations, step counts, kernel time) are left in `last_lyapunov_info`."""
+    kargs.setdefault("maxiters_solver", None)
+    solver_maxiters = kargs.pop("maxiters_solver")
+    for k in ("fundamental_matrix_initial", "save_everystep", "get_fundamental_matrix"):
+        kargs.pop(k, None)
+    sol = solver_from_kargs(dict(kargs, maxiters=solver_maxiters))
+    X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, len(system.varnames()))
+    lam, xf, iters, status, nsteps, ms = _lib.default_context().lyapunov(system._c_system(), sol, X, t, λtol, λreltol, maxiters)
+    last_lyapunov_info.clear()
+    last_lyapunov_info.update(x_final=xf, iterations=iters, status=status, nsteps=nsteps, kernel_ms=ms)
+    return lam, status
+
+
+def lyapunov_spectrum(system, x, t=100, *, λtol=1e-4, λreltol=1e-3, maxiters=100, verbose=True, **kargs):
+    """src/ClassicalSystems.jl:183-224 (note: the signature's default λtol is 1e-4 there, :185)."""
+    x = np.asarray(x, dtype=np.float64).ravel()
+    if len(x) != len(system.varnames()):
+        raise ValueError(f"u₀ should have length {len(system.varnames())}, which is the dimension of the phase space of system")
+    if system.out_of_bounds(x):
+        raise ValueError(f"The initial condition u₀={x.tolist()} is out of bounds")
+    lam, status = lyapunov_spectrum_batch(system, x[None, :], t, λtol=λtol, λreltol=λreltol, maxiters=maxiters, **kargs)
+    if status[0] == _lib.LYAP_MAXITERS:
+        raise RuntimeError("Maximum iterations")   # :223
+    if status[0] != _lib.TRAJ_OK:
+        raise RuntimeError(f"integration failed: {_RETCODES[int(status[0])]}")
+    return lam[0]
+
+
+def lyapunov_exponent(system, x, t=100, **kargs):
+    """src/ClassicalSystems.jl:166-171"""
+    return float(np.max(lyapunov_spectrum(system, x, t, **kargs)))

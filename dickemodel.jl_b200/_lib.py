@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libdicketwa.so")
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_EXPR, ERR_NCCL, ERR_TOO_MANY_FAILURES, ERR_BOUNDS, ERR_CAPACITY, ERR_JIT = range(-1, -10, -1)
 TRAJ_OK, TRAJ_DOMAIN, TRAJ_MAXITERS, TRAJ_BAD_IC = 0, 1, 2, 3
+LYAP_MAXITERS = 5
 SYS_DICKE, SYS_LMG = 0, 1
 ALG_RK4, ALG_RK8, ALG_DP5, ALG_DOP853 = 0, 1, 2, 3
 SAMPLER_HOST_ARRAY, SAMPLER_COHERENT_HW, SAMPLER_COHERENT_SU2, SAMPLER_COHERENT_HWXSU2, SAMPLER_DEVICE_ARRAY = 0, 1, 2, 3, 4
@@ -27,7 +28,7 @@ AXIS_EXPR, AXIS_TIME = 0, 1
 EXPORTS = ["dtwa_last_error", "dtwa_version", "dtwa_create", "dtwa_destroy", "dtwa_device_info", "dtwa_set_launch",
            "dtwa_hamiltonian", "dtwa_integrate", "dtwa_sample", "dtwa_pdf", "dtwa_eval_expr", "dtwa_scale_to_index",
            "dtwa_ensemble", "dtwa_ensemble_launch", "dtwa_plan_arenas", "dtwa_plan_fetch", "dtwa_plan_free",
-           "dtwa_fp64_peak", "dtwa_fp64_peak_regs", "dtwa_set_jit", "dtwa_jit_compile"]
+           "dtwa_fp64_peak", "dtwa_fp64_peak_regs", "dtwa_set_jit", "dtwa_jit_compile", "dtwa_integrate_fm", "dtwa_lyapunov"]
 
 
 class DtwaError(RuntimeError):
@@ -113,6 +114,10 @@ def load():
         L.dtwa_plan_free.argtypes = [vp]
         L.dtwa_fp64_peak.argtypes = [vp, dp, dp]
         L.dtwa_fp64_peak_regs.argtypes = [vp, dp, dp]
+        i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+        L.dtwa_integrate_fm.argtypes = [vp, C.POINTER(System), C.POINTER(Solver), dp, dp, C.c_int64, dp, C.c_int32, dp, dp, i32p, i64p]
+        L.dtwa_lyapunov.argtypes = [vp, C.POINTER(System), C.POINTER(Solver), dp, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                    C.c_int32, dp, dp, i32p, i32p, i64p, dp]
         L.dtwa_set_jit.argtypes = [vp, C.c_int]
         L.dtwa_jit_compile.argtypes = [C.POINTER(System), C.POINTER(Solver), C.POINTER(C.c_char_p), C.c_int32, C.c_char_p,
                                        C.c_int64, C.POINTER(C.c_int64)]
@@ -203,6 +208,36 @@ class Context:
                                      status.ctypes.data_as(C.POINTER(C.c_int32)),
                                      nsteps.ctypes.data_as(C.POINTER(C.c_int64))))
         return out, status, nsteps
+
+    def integrate_fm(self, sys: System, sol: Solver, u0, ts, fm0=None):
+        """(x[n][nt][nv], Phi[n][nt][nv][nv] (Phi[..., r, c]), status, nsteps); fm0[n][nv][nv] or None = identity"""
+        nv = 4 if sys.kind == SYS_DICKE else 2
+        u0 = np.ascontiguousarray(u0, dtype=np.float64).reshape(-1, nv)
+        ts = np.ascontiguousarray(ts, dtype=np.float64)
+        n, nt = u0.shape[0], ts.shape[0]
+        f0 = None
+        if fm0 is not None:   # row/column indexed -> column-major flat (Julia's layout)
+            f0 = np.ascontiguousarray(np.swapaxes(np.asarray(fm0, dtype=np.float64).reshape(n, nv, nv), 1, 2))
+        out_u, out_fm = np.empty((n, nt, nv)), np.empty((n, nt, nv * nv))
+        status, nsteps = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int64)
+        _check(load().dtwa_integrate_fm(self._h, C.byref(sys), C.byref(sol), _dp(u0), _dp(f0) if f0 is not None else None, n,
+                                        _dp(ts), nt, _dp(out_u), _dp(out_fm), status.ctypes.data_as(C.POINTER(C.c_int32)),
+                                        nsteps.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out_u, np.swapaxes(out_fm.reshape(n, nt, nv, nv), 2, 3), status, nsteps
+
+    def lyapunov(self, sys: System, sol: Solver, u0, t, ltol, lreltol, maxiters):
+        """(lambda[n][nv], x_final[n][nv], iters[n], status[n], nsteps[n], kernel_ms)"""
+        nv = 4 if sys.kind == SYS_DICKE else 2
+        u0 = np.ascontiguousarray(u0, dtype=np.float64).reshape(-1, nv)
+        n = u0.shape[0]
+        lam, xf = np.empty((n, nv)), np.empty((n, nv))
+        iters, status, nsteps = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int64)
+        ms = C.c_double()
+        _check(load().dtwa_lyapunov(self._h, C.byref(sys), C.byref(sol), _dp(u0), n, float(t), float(ltol), float(lreltol),
+                                    int(maxiters), _dp(lam), _dp(xf), iters.ctypes.data_as(C.POINTER(C.c_int32)),
+                                    status.ctypes.data_as(C.POINTER(C.c_int32)), nsteps.ctypes.data_as(C.POINTER(C.c_int64)),
+                                    C.byref(ms)))
+        return lam, xf, iters, status, nsteps, ms.value
 
     def sample(self, smp: Sampler, n, attempt=0):
         nv = 4 if smp.kind == SAMPLER_COHERENT_HWXSU2 else 2

@@ -600,6 +600,124 @@ extern "C" int dtwa_integrate(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_
 }
 
 // ------------------------------------------------------------------------------------------------
+// fundamental matrix and Lyapunov spectra (src/ClassicalSystems.jl:110-128,183-224)
+template <typename F>
+static int by_var_system(int kind, F &&f)
+{
+    if (kind == DTWA_SYS_DICKE) return f(std::integral_constant<int, DTWA_SYS_DICKE_VAR>());
+    return f(std::integral_constant<int, DTWA_SYS_LMG_VAR>());
+}
+
+extern "C" int dtwa_integrate_fm(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const double *u0,
+                                 const double *fm0, int64_t n, const double *ts, int32_t nt, double *out_u, double *out_fm,
+                                 int32_t *status, int64_t *nsteps)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    TRY(check_system(sys));
+    TRY(check_solver(sol));
+    if (n < 0 || (n > 0 && (!u0 || !out_u || !out_fm || !status))) return set_err(DTWA_ERR_INVALID, "bad buffers");
+    std::vector<StepTab> tab;
+    TRY(build_step_table(ts, nt, sol->dt, make_par(sys, sol->backwards).b, tab));
+    if (n == 0) return DTWA_OK;
+    DevCtx &d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    const int nv = nvar_of(sys->kind), nn = nv * nv;
+    const size_t tab_b = sizeof(StepTab) * nt, ts_b = sizeof(double) * nt;
+    const size_t b_u0 = sizeof(double) * n * nv, b_fm0 = fm0 ? sizeof(double) * n * nn : 0;
+    const size_t b_ou = sizeof(double) * (size_t)n * nt * nv, b_of = sizeof(double) * (size_t)n * nt * nn;
+    TRY(d.meta.ensure(tab_b + ts_b));
+    TRY(d.u0.ensure(b_u0 + b_fm0));
+    TRY(d.scratch_a.ensure(b_ou + b_of));
+    TRY(d.scratch_b.ensure(sizeof(int32_t) * n));
+    TRY(d.scratch_c.ensure(sizeof(long long) * n));
+    unsigned char *meta = (unsigned char *)d.meta.p;
+    CK(cudaMemcpyAsync(meta, tab.data(), tab_b, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(meta + tab_b, ts, ts_b, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(d.u0.p, u0, b_u0, cudaMemcpyHostToDevice, d.stream));
+    if (fm0) CK(cudaMemcpyAsync((unsigned char *)d.u0.p + b_u0, fm0, b_fm0, cudaMemcpyHostToDevice, d.stream));
+    const SolverArgs S = make_solver_args(sys, sol, (const StepTab *)meta, (const double *)(meta + tab_b), ts, nt, tab);
+    const unsigned grid = blocks_for(n * nv, 128);
+    const double *d_fm0 = fm0 ? (const double *)((unsigned char *)d.u0.p + b_u0) : nullptr;
+    by_var_system(sys->kind, [&](auto sk) {
+        return by_alg(sol->alg, [&](auto ak) {
+            integrate_fm_kernel<decltype(sk)::value, decltype(ak)::value><<<grid, 128, 0, d.stream>>>(
+                S, (const double *)d.u0.p, d_fm0, n, (double *)d.scratch_a.p, (double *)((unsigned char *)d.scratch_a.p + b_ou),
+                (int32_t *)d.scratch_b.p, (long long *)d.scratch_c.p);
+            return 0;
+        });
+    });
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_u, d.scratch_a.p, b_ou, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(out_fm, (unsigned char *)d.scratch_a.p + b_ou, b_of, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(status, d.scratch_b.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d.stream));
+    if (nsteps) CK(cudaMemcpyAsync(nsteps, d.scratch_c.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    return DTWA_OK;
+}
+
+extern "C" int dtwa_lyapunov(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const double *u0, int64_t n,
+                             double t_interval, double lam_tol, double lam_reltol, int32_t maxiters, double *lambda,
+                             double *x_final, int32_t *iters, int32_t *status, int64_t *nsteps, double *kernel_ms)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    TRY(check_system(sys));
+    TRY(check_solver(sol));
+    if (n < 0 || (n > 0 && (!u0 || !lambda || !iters || !status))) return set_err(DTWA_ERR_INVALID, "bad buffers");
+    if (!(t_interval > 0)) return set_err(DTWA_ERR_INVALID, "the renormalisation interval t must be > 0");
+    if (maxiters < 1) return set_err(DTWA_ERR_INVALID, "maxiters must be >= 1");
+    std::vector<StepTab> tab;
+    const double ts1[1] = {t_interval};
+    TRY(build_step_table(ts1, 1, sol->dt, make_par(sys, sol->backwards).b, tab));
+    if (n == 0) return DTWA_OK;
+    DevCtx &d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    const int nv = nvar_of(sys->kind);
+    const size_t tab_b = sizeof(StepTab), ts_b = sizeof(double);
+    const size_t b_u0 = sizeof(double) * n * nv;
+    TRY(d.meta.ensure(tab_b + ts_b));
+    TRY(d.u0.ensure(b_u0));
+    TRY(d.scratch_a.ensure(2 * b_u0));
+    TRY(d.scratch_b.ensure(2 * sizeof(int32_t) * n));
+    TRY(d.scratch_c.ensure(sizeof(long long) * n));
+    unsigned char *meta = (unsigned char *)d.meta.p;
+    CK(cudaMemcpyAsync(meta, tab.data(), tab_b, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(meta + tab_b, ts1, ts_b, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(d.u0.p, u0, b_u0, cudaMemcpyHostToDevice, d.stream));
+    const SolverArgs S = make_solver_args(sys, sol, (const StepTab *)meta, (const double *)(meta + tab_b), ts1, 1, tab);
+    LyapArgs L;
+    L.t_interval = t_interval;
+    L.ltol = lam_tol;
+    L.lreltol = lam_reltol;
+    L.maxiters = maxiters;
+    L.pad = 0;
+    const unsigned grid = blocks_for(n * nv, 128);
+    double *d_lam = (double *)d.scratch_a.p, *d_x = (double *)((unsigned char *)d.scratch_a.p + b_u0);
+    int32_t *d_it = (int32_t *)d.scratch_b.p, *d_st = d_it + n;
+    CK(cudaEventRecord(d.ev[0], d.stream));
+    by_var_system(sys->kind, [&](auto sk) {
+        return by_alg(sol->alg, [&](auto ak) {
+            lyapunov_kernel<decltype(sk)::value, decltype(ak)::value><<<grid, 128, 0, d.stream>>>(
+                S, L, (const double *)d.u0.p, n, d_lam, d_x, d_it, d_st, (long long *)d.scratch_c.p);
+            return 0;
+        });
+    });
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(d.ev[3], d.stream));
+    CK(cudaMemcpyAsync(lambda, d_lam, b_u0, cudaMemcpyDeviceToHost, d.stream));
+    if (x_final) CK(cudaMemcpyAsync(x_final, d_x, b_u0, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(iters, d_it, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d.stream));
+    if (nsteps) CK(cudaMemcpyAsync(nsteps, d.scratch_c.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    if (kernel_ms) {
+        float m = 0.f;
+        CK(cudaEventElapsedTime(&m, d.ev[0], d.ev[3]));
+        *kernel_ms = m;
+    }
+    return DTWA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // a13-a20: the ensemble
 struct RedLayout {
     int kind = 0;

@@ -51,6 +51,7 @@ template <>
 struct Sys<DTWA_SYS_DICKE> {
     static constexpr int NV = 4;
     static constexpr int QI = 0, PI = 2;
+    static constexpr int NVB = 4, GROUP = 1, NORM_N = 4;  // see the variational systems below
     // 18 FP64-pipe instructions + 1 MUFU.  FOLDQ: du[1] is returned as p (the factor w lives in the
     // caller's step constants), 17 instructions.  DTWA_W_IS_ONE / DTWA_W_IS_MINUS_ONE (defined by the
     // run-time specialisation when |w| == 1; x*1.0 == x exactly, so results do not change): 16.
@@ -101,6 +102,7 @@ template <>
 struct Sys<DTWA_SYS_LMG> {
     static constexpr int NV = 2;
     static constexpr int QI = 0, PI = 1;
+    static constexpr int NVB = 2, GROUP = 1, NORM_N = 2;
     // 7 FP64-pipe instructions
     __device__ __forceinline__ static void rhs(const SysPar &p, const double (&u)[2], double (&du)[2])
     {
@@ -123,6 +125,104 @@ struct Sys<DTWA_SYS_LMG> {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Variational systems (src/ClassicalSystems.jl:110-128, `get_fundamental_matrix=true`):
+//   d/dt (x, Phi) = (f(x), J(x) Phi),  J = df/dx  (the reference takes `step(system).jac` from
+//   ParameterizedFunctions' symbolic differentiation; here it is written out).
+// The columns of Phi are independent given x(t), so a GROUP of NVB adjacent threads integrates one
+// initial condition: thread c carries x (redundantly, bit-identical in every thread of the group) and
+// column c of Phi -- 2*NVB doubles per thread instead of NVB + NVB^2, everything stays in registers.
+// Only the error norm of the adaptive pairs couples the columns: group-wide sums over NORM_N =
+// NVB + NVB^2 components (x counted once), combined with a butterfly of shuffles inside the group.
+constexpr int DTWA_SYS_DICKE_VAR = 2, DTWA_SYS_LMG_VAR = 3;
+
+template <>
+struct Sys<DTWA_SYS_DICKE_VAR> {
+    static constexpr int NV = 8;
+    static constexpr int QI = 0, PI = 2;
+    static constexpr int NVB = 4, GROUP = 4, NORM_N = 20;
+    __device__ __forceinline__ static void rhs(const SysPar &p, const double (&y)[8], double (&dy)[8])
+    {
+        const double Q = y[0], q = y[1], P = y[2], pp = y[3];
+        const double a = y[4], b = y[5], c = y[6], d = y[7];   // perturbation of (Q, q, P, p)
+        double r2 = fma(-P, P, 4.0);
+        r2 = fma(-Q, Q, r2);
+        double is, s;
+        rsqrt_sqrt_pair(r2, is, s);
+        const double gq = __dmul_rn(p.c, q);
+        const double f = __dmul_rn(__dmul_rn(gq, Q), is);       // g q Q / s
+        const double e = f - p.a;                               // f - w0
+        dy[0] = __dmul_rn(-P, e);
+        dy[1] = __dmul_rn(pp, p.b);
+        dy[2] = fma(Q, e, -__dmul_rn(gq, s));
+        dy[3] = fma(-p.c, __dmul_rn(Q, s), -__dmul_rn(q, p.b));
+        // df = f_Q a + f_q b + f_P c,  ds = -(Q a + P c)/s
+        const double is2 = __dmul_rn(is, is);
+        const double fQ = __dmul_rn(__dmul_rn(gq, is), fma(__dmul_rn(Q, Q), is2, 1.0));   // g q (1/s + Q^2/s^3)
+        const double fq = __dmul_rn(__dmul_rn(p.c, Q), is);                               // g Q / s
+        const double fP = __dmul_rn(__dmul_rn(f, P), is2);                                // g q Q P / s^3
+        const double df = fma(fQ, a, fma(fq, b, __dmul_rn(fP, c)));
+        const double ds = -__dmul_rn(fma(Q, a, __dmul_rn(P, c)), is);
+        dy[4] = fma(-P, df, -__dmul_rn(c, e));                                            // c (w0 - f) - P df
+        dy[5] = __dmul_rn(d, p.b);
+        dy[6] = fma(a, e, fma(Q, df, -__dmul_rn(p.c, fma(b, s, __dmul_rn(q, ds)))));      // a (f - w0) + Q df - g (b s + q ds)
+        dy[7] = fma(-p.c, fma(a, s, __dmul_rn(Q, ds)), -__dmul_rn(b, p.b));               // -g (a s + Q ds) - w b
+    }
+};
+
+template <>
+struct Sys<DTWA_SYS_LMG_VAR> {
+    static constexpr int NV = 4;
+    static constexpr int QI = 0, PI = 1;
+    static constexpr int NVB = 2, GROUP = 2, NORM_N = 6;
+    __device__ __forceinline__ static void rhs(const SysPar &p, const double (&y)[4], double (&dy)[4])
+    {
+        const double Q = y[0], P = y[1], a = y[2], c = y[3];
+        const double Q2 = __dmul_rn(Q, Q), P2 = __dmul_rn(P, P);
+        const double A = fma(-p.c, Q2, p.a);                  // Om - xi Q^2/2   = d(dQ)/dP
+        dy[0] = __dmul_rn(P, A);
+        const double in = fma(p.c, P2, -p.d);                 // xi P^2/2 - (2 xi + Om)
+        dy[1] = __dmul_rn(Q, fma(p.b, Q2, in));
+        const double xQP = __dmul_rn(p.b, __dmul_rn(Q, P));   // xi Q P
+        const double B = fma(__dmul_rn(3.0, p.b), Q2, in);    // d(dP)/dQ
+        dy[2] = fma(A, c, -__dmul_rn(xQP, a));
+        dy[3] = fma(B, a, __dmul_rn(xQP, c));
+    }
+};
+
+// does component i of this thread enter the group-wide norms?  (x is replicated: thread 0 of the group counts it)
+template <int SYS>
+__device__ __forceinline__ bool norm_counted(int i)
+{
+    if constexpr (Sys<SYS>::GROUP == 1)
+        return true;
+    else
+        return i >= Sys<SYS>::NVB || (threadIdx.x & (Sys<SYS>::GROUP - 1)) == 0;
+}
+// sum over the threads of a group; every thread of the group receives the same bits
+template <int SYS>
+__device__ __forceinline__ double group_sum(double s)
+{
+    if constexpr (Sys<SYS>::GROUP > 1) {
+        constexpr int G = Sys<SYS>::GROUP;
+        const unsigned base = (threadIdx.x & 31u) & ~(unsigned)(G - 1);
+        const unsigned mask = ((1u << G) - 1u) << base;
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_xor_sync(mask, s, off));
+    }
+    return s;
+}
+template <int SYS>
+__device__ __forceinline__ double group_rms(const double (&x)[Sys<SYS>::NV])
+{
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < Sys<SYS>::NV; ++i)
+        if (norm_counted<SYS>(i)) s = fma(x[i], x[i], s);
+    s = group_sum<SYS>(s);
+    return sqrt(s) / sqrt((double)Sys<SYS>::NORM_N);
+}
+
 template <int SYS>
 __device__ __forceinline__ bool state_bad(const double (&u)[Sys<SYS>::NV])
 {
@@ -135,7 +235,15 @@ __device__ __forceinline__ bool state_bad(const double (&u)[Sys<SYS>::NV])
 #pragma unroll
     for (int i = 0; i < Sys<SYS>::NV; ++i)
         if (i != Sys<SYS>::QI && i != Sys<SYS>::PI) nonfinite |= ((__double2hiint(u[i]) & 0x7ff00000) == 0x7ff00000);
-    return nonfinite || !(r2 > 0.0);
+    bool bad = nonfinite || !(r2 > 0.0);
+    if constexpr (Sys<SYS>::GROUP > 1) {
+        // one decision per group (a non-finite column must stop every thread of the group)
+        constexpr int G = Sys<SYS>::GROUP;
+        const unsigned base = (threadIdx.x & 31u) & ~(unsigned)(G - 1);
+        const unsigned mask = ((1u << G) - 1u) << base;
+        bad = (__ballot_sync(mask, bad) & mask) != 0u;
+    }
+    return bad;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -269,10 +377,10 @@ struct Adaptive {
         for (int i = 0; i < NV; ++i) sc[i] = fma(fabs(y[i]), tol, tol);
 #pragma unroll
         for (int i = 0; i < NV; ++i) a[i] = y[i] / sc[i];
-        const double d0 = rms_norm<NV>(a);
+        const double d0 = group_rms<SYS>(a);
 #pragma unroll
         for (int i = 0; i < NV; ++i) a[i] = k0[i] / sc[i];
-        const double d1 = rms_norm<NV>(a);
+        const double d1 = group_rms<SYS>(a);
         double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
         h0 = fmin(h0, tend);
         double y1[NV], f1[NV];
@@ -281,7 +389,7 @@ struct Adaptive {
         RHS(y1, f1);
 #pragma unroll
         for (int i = 0; i < NV; ++i) a[i] = (f1[i] - k0[i]) / sc[i];
-        const double d2 = rms_norm<NV>(a) / h0;
+        const double d2 = group_rms<SYS>(a) / h0;
         double h1;
         if (d1 <= 1e-15 && d2 <= 1e-15)
             h1 = fmax(1e-6, h0 * 1e-3);
@@ -322,7 +430,7 @@ struct Adaptive {
                 yn[i] = ynew[i];
                 kn[i] = DP5_KNEW[i];
             }
-            err = rms_norm<NV>(en);
+            err = group_rms<SYS>(en);
 #undef DP5_KNEW
         } else {
 #include "dop853_body.inc"
@@ -331,15 +439,19 @@ struct Adaptive {
             for (int i = 0; i < NV; ++i) {
                 const double isc = 1.0 / fma(fmax(fabs(y[i]), fabs(ynew[i])), tol, tol);  // one division for both estimators
                 const double a5 = e5[i] * isc, a3 = e3[i] * isc;
-                n5 = fma(a5, a5, n5);
-                n3 = fma(a3, a3, n3);
+                if (norm_counted<SYS>(i)) {
+                    n5 = fma(a5, a5, n5);
+                    n3 = fma(a3, a3, n3);
+                }
                 yn[i] = ynew[i];
                 kn[i] = DOP853_KNEW[i];
             }
+            n5 = group_sum<SYS>(n5);
+            n3 = group_sum<SYS>(n3);
             if (n5 == 0.0 && n3 == 0.0)
                 err = 0.0;
             else
-                err = fabs(h) * n5 / sqrt(fma(0.01, n3, n5) * (double)NV);
+                err = fabs(h) * n5 / sqrt(fma(0.01, n3, n5) * (double)Sys<SYS>::NORM_N);
 #undef DOP853_KNEW
         }
         const bool bad = state_bad<SYS>(yn) || !(err == err) || isinf(err);

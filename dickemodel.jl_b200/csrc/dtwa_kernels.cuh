@@ -589,6 +589,165 @@ __global__ void __launch_bounds__(128) integrate_kernel(const SolverArgs S, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5: trajectories with their fundamental matrix (src/ClassicalSystems.jl:110-128).  SYS is one of the
+// variational systems; GROUP adjacent threads share one initial condition (dtwa_device.cuh).
+//   out_u [n][nt][NVB], out_fm[n][nt][NVB*NVB] column-major (Julia's layout): thread c writes column c.
+template <int SYS, int ALG>
+__global__ void __launch_bounds__(128) integrate_fm_kernel(const SolverArgs S, const double *__restrict__ u0,
+                                                           const double *__restrict__ fm0, long long n,
+                                                           double *__restrict__ out_u, double *__restrict__ out_fm,
+                                                           int32_t *__restrict__ status, long long *__restrict__ nsteps)
+{
+    constexpr int NVB = Sys<SYS>::NVB, G = Sys<SYS>::GROUP;
+    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int c = (int)(gid % G);
+    const long long j0 = gid / G;
+    const bool live = j0 < n;
+    const long long j = live ? j0 : n - 1;  // tail groups shadow the last initial condition
+    Traj<SYS, ALG> T;
+    T.status = ST_OK;
+#pragma unroll
+    for (int i = 0; i < NVB; ++i) {
+        T.u[i] = u0[j * NVB + i];
+        T.u[NVB + i] = fm0 ? fm0[(j * NVB + c) * NVB + i] : (i == c ? 1.0 : 0.0);
+    }
+    T.begin(S);
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    for (int k = 0; k < S.nt; ++k) {
+        T.advance(S, k);
+        if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
+        if (live) {
+            const bool ok = T.status == ST_OK;
+            if (c == 0) {
+                double *o = out_u + ((size_t)j * S.nt + k) * NVB;
+#pragma unroll
+                for (int i = 0; i < NVB; ++i) o[i] = ok ? T.u[i] : qnan;
+            }
+            double *o = out_fm + (((size_t)j * S.nt + k) * NVB + c) * NVB;
+#pragma unroll
+            for (int i = 0; i < NVB; ++i) o[i] = ok ? T.u[NVB + i] : qnan;
+        }
+    }
+    if (live && c == 0) {
+        status[j] = T.status;
+        if (nsteps) nsteps[j] = (long long)T.nacc + (long long)T.nrej;
+    }
+}
+
+// K6: Lyapunov spectra, one group per initial condition -- src/ClassicalSystems.jl:183-224, the
+// algorithm of Fig. 3.7 of Parker & Chua as the reference codes it: integrate (x, Phi = U) over an
+// interval t, modified Gram-Schmidt of the columns against the NEW u_j (j < i), sums_i += log|v_i|,
+// lambda_i = sums_i / (k t), and -- inside the loop over i -- stop as soon as
+// |lambda_old - lambda| < lreltol |lambda| + ltol (so the returned vector may mix entries of
+// iteration k and k-1, exactly like the reference).  Each interval is a fresh `integrate` call
+// (new starting step).  status: 0 ok, DTWA_TRAJ_* if the integration failed, DTWA_LYAP_MAXITERS.
+struct LyapArgs {
+    double t_interval, ltol, lreltol;
+    int32_t maxiters, pad;
+};
+template <int SYS, int ALG>
+__global__ void __launch_bounds__(128) lyapunov_kernel(const SolverArgs S, const LyapArgs L, const double *__restrict__ u0,
+                                                       long long n, double *__restrict__ lambda_out,
+                                                       double *__restrict__ x_out, int32_t *__restrict__ iters_out,
+                                                       int32_t *__restrict__ status, long long *__restrict__ nsteps)
+{
+    constexpr int NVB = Sys<SYS>::NVB, G = Sys<SYS>::GROUP;
+    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int c = (int)(gid % G);
+    const long long j0 = gid / G;
+    const bool live = j0 < n;
+    const long long j = live ? j0 : n - 1;
+    const unsigned base = (threadIdx.x & 31u) & ~(unsigned)(G - 1);
+    const unsigned mask = ((1u << G) - 1u) << base;
+    double x[NVB], w[NVB], lam[NVB], lam_old[NVB];
+    double sums = 0.0;
+#pragma unroll
+    for (int i = 0; i < NVB; ++i) {
+        x[i] = u0[j * NVB + i];
+        w[i] = (i == c) ? 1.0 : 0.0;
+        lam[i] = 0.0;
+    }
+    int st = ST_OK, it = 0;
+    long long steps = 0;
+    bool done = false;
+#pragma unroll 1
+    for (int k = 1; k <= L.maxiters && !done && st == ST_OK; ++k) {
+        it = k;
+#pragma unroll
+        for (int i = 0; i < NVB; ++i) lam_old[i] = lam[i];
+        Traj<SYS, ALG> T;
+        T.status = ST_OK;
+#pragma unroll
+        for (int i = 0; i < NVB; ++i) {
+            T.u[i] = x[i];
+            T.u[NVB + i] = w[i];
+        }
+        T.begin(S);
+        T.advance(S, 0);
+        if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
+        steps += (long long)T.nacc + (long long)T.nrej;
+        if (T.status != ST_OK) {
+            st = T.status;
+            break;
+        }
+#pragma unroll
+        for (int i = 0; i < NVB; ++i) {
+            x[i] = T.u[i];
+            w[i] = T.u[NVB + i];
+        }
+        const double kt = __dmul_rn((double)k, L.t_interval);
+#pragma unroll
+        for (int i = 0; i < NVB; ++i) {
+            if (done) break;
+#pragma unroll
+            for (int jj = 0; jj < i; ++jj) {
+                double uj[NVB];
+#pragma unroll
+                for (int r = 0; r < NVB; ++r) uj[r] = __shfl_sync(mask, w[r], (int)base + jj);
+                if (c == i) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int r = 0; r < NVB; ++r) d = __dadd_rn(d, __dmul_rn(w[r], uj[r]));
+#pragma unroll
+                    for (int r = 0; r < NVB; ++r) w[r] = __dsub_rn(w[r], __dmul_rn(d, uj[r]));
+                }
+            }
+            double li = 0.0;
+            if (c == i) {
+                double n2 = 0.0;
+#pragma unroll
+                for (int r = 0; r < NVB; ++r) n2 = __dadd_rn(n2, __dmul_rn(w[r], w[r]));
+                const double nrm = __dsqrt_rn(n2);
+#pragma unroll
+                for (int r = 0; r < NVB; ++r) w[r] = __ddiv_rn(w[r], nrm);
+                sums = __dadd_rn(sums, log(nrm));
+                li = __ddiv_rn(sums, kt);
+            }
+            lam[i] = __shfl_sync(mask, li, (int)base + i);
+            double e2 = 0.0, l2 = 0.0;
+#pragma unroll
+            for (int r = 0; r < NVB; ++r) {
+                const double dl = __dsub_rn(lam_old[r], lam[r]);
+                e2 = __dadd_rn(e2, __dmul_rn(dl, dl));
+                l2 = __dadd_rn(l2, __dmul_rn(lam[r], lam[r]));
+            }
+            if (__dsqrt_rn(e2) < __dadd_rn(__dmul_rn(L.lreltol, __dsqrt_rn(l2)), L.ltol)) done = true;
+        }
+    }
+    if (st == ST_OK && !done) st = DTWA_LYAP_MAXITERS;
+    if (live && c == 0) {
+#pragma unroll
+        for (int i = 0; i < NVB; ++i) {
+            lambda_out[j * NVB + i] = lam[i];
+            if (x_out) x_out[j * NVB + i] = x[i];
+        }
+        iters_out[j] = it;
+        status[j] = st;
+        if (nsteps) nsteps[j] = steps;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // hooks
 template <int NV>
 __global__ void sample_kernel(const SamplerPar sp, long long n, uint32_t attempt, double *__restrict__ u)

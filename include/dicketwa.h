@@ -48,6 +48,7 @@ extern "C" {
 #define DTWA_TRAJ_DOMAIN 1   /* left the chart 4-P^2-Q^2>0 or became non-finite: the reference throws */
 #define DTWA_TRAJ_MAXITERS 2 /* adaptive solver used up maxiters attempts */
 #define DTWA_TRAJ_BAD_IC 3   /* initial condition out of bounds */
+#define DTWA_LYAP_MAXITERS 5 /* dtwa_lyapunov: no convergence within maxiters intervals (the reference: error("Maximum iterations")) */
 
 typedef struct dtwa_ctx dtwa_ctx;
 typedef struct dtwa_plan dtwa_plan;
@@ -191,6 +192,25 @@ int dtwa_hamiltonian(dtwa_ctx *ctx, const dtwa_system *sys, const double *u, int
  *      rejected attempts; may be NULL). ---- */
 int dtwa_integrate(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const double *u0, int64_t n,
                    const double *ts, int32_t nt, double *out, int32_t *status, int64_t *nsteps);
+
+/* ---- integrate(...; get_fundamental_matrix=true, fundamental_matrix_initial=fm0)
+ *      (src/ClassicalSystems.jl:110-128): the variational system d/dt (x, Phi) = (f(x), J(x) Phi) for n
+ *      independent initial conditions; abstol=reltol=tol act on all nvar + nvar^2 components, like the
+ *      reference's ArrayPartition.  fm0[n][nvar*nvar] column-major (Julia layout) or NULL = identity.
+ *      out_u[n][nt][nvar], out_fm[n][nt][nvar*nvar] column-major. ---- */
+int dtwa_integrate_fm(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const double *u0, const double *fm0,
+                      int64_t n, const double *ts, int32_t nt, double *out_u, double *out_fm, int32_t *status,
+                      int64_t *nsteps);
+
+/* ---- ClassicalSystems.lyapunov_spectrum (src/ClassicalSystems.jl:183-224) for n
+ *      initial conditions at once (a Lyapunov map, docs/src/ClassicalDickeExamples.md:133-236): integrate
+ *      (x, Phi = U) over intervals of length t_interval, modified Gram-Schmidt, lambda_i = sum log|v_i| / (k t),
+ *      stop when |lambda_old - lambda| < lam_reltol |lambda| + lam_tol (tested after every column, as the
+ *      reference does).  lambda[n][nvar]; x_final[n][nvar] (may be NULL); iters[n]; status[n] is
+ *      DTWA_TRAJ_* or DTWA_LYAP_MAXITERS; nsteps[n] (may be NULL); kernel_ms (may be NULL). ---- */
+int dtwa_lyapunov(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const double *u0, int64_t n,
+                  double t_interval, double lam_tol, double lam_reltol, int32_t maxiters, double *lambda, double *x_final,
+                  int32_t *iters, int32_t *status, int64_t *nsteps, double *kernel_ms);
 
 /* ---- a8-a10: distribution.sample() / distribution.probability_density (src/TWA.jl:692-698,
  *      719-743,757-762) on the device: u[n][nvar] for trajectories offset..offset+n-1 ---- */

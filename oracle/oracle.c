@@ -821,3 +821,353 @@ void orc_truth_ld(int kind, const double *par, int backwards, const double *u0, 
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* the variational system and Lyapunov spectra.
+ * src/ClassicalSystems.jl:110-128: with get_fundamental_matrix=true the reference integrates the
+ * ArrayPartition (x, Phi) with d Phi/dt = J(x) Phi, J = step(system).jac (ParameterizedFunctions'
+ * symbolic Jacobian of src/ClassicalDicke.jl:11-17 / src/ClassicalLMG.jl:8-11; written out here).
+ * Flat layout y = [x (nv) | Phi column-major (nv*nv)], N = nv + nv*nv <= 20. */
+#define VAR_MAXN 20
+
+static void orc_jacobian(int kind, const double *par, double sg, const double *u, double *J /* row-major [nv][nv] */)
+{
+    if (kind == SYS_DICKE) {
+        double w0 = par[0], w = par[1], g = par[2];
+        double Q = u[0], q = u[1], P = u[2];
+        double s = sqrt(4 - P * P - Q * Q), s3 = s * s * s;
+        /* f = g q Q / s */
+        double f = g * q * Q / s;
+        double fQ = g * q * (1 / s + Q * Q / s3), fq = g * Q / s, fP = g * q * Q * P / s3;
+        double sQ = -Q / s, sP = -P / s;
+        memset(J, 0, sizeof(double) * 16);
+        /* dQ = P w0 - P f */
+        J[0 * 4 + 0] = -P * fQ;
+        J[0 * 4 + 1] = -P * fq;
+        J[0 * 4 + 2] = w0 - f - P * fP;
+        /* dq = w p */
+        J[1 * 4 + 3] = w;
+        /* dP = Q f - g q s - Q w0 */
+        J[2 * 4 + 0] = f + Q * fQ - g * q * sQ - w0;
+        J[2 * 4 + 1] = Q * fq - g * s;
+        J[2 * 4 + 2] = Q * fP - g * q * sP;
+        /* dp = -g Q s - q w */
+        J[3 * 4 + 0] = -g * s - g * Q * sQ;
+        J[3 * 4 + 1] = -w;
+        J[3 * 4 + 2] = -g * Q * sP;
+        for (int i = 0; i < 16; ++i) J[i] *= sg;
+    } else {
+        double Om = par[0], xi = par[1];
+        double Q = u[0], P = u[1];
+        J[0] = -xi * Q * P;
+        J[1] = Om - xi * Q * Q / 2;
+        J[2] = xi * P * P / 2 - (2 * xi + Om) + 3 * xi * Q * Q;
+        J[3] = xi * Q * P;
+        for (int i = 0; i < 4; ++i) J[i] *= sg;
+    }
+}
+
+/* the reference's `sistemaconmatriz` (src/ClassicalSystems.jl:121-125) */
+static int orc_var_rhs(int kind, const double *par, double sg, const double *y, double *dy)
+{
+    int nv = orc_nvar(kind);
+    double J[16];
+    int bad = orc_rhs(kind, par, sg, y, dy);
+    orc_jacobian(kind, par, sg, y, J);
+    for (int c = 0; c < nv; ++c)
+        for (int r = 0; r < nv; ++r) {
+            double s = 0;
+            for (int m = 0; m < nv; ++m) s += J[r * nv + m] * y[nv + c * nv + m];
+            dy[nv + c * nv + r] = s;
+        }
+    return bad;
+}
+
+static int var_nonfinite(const double *y, int N)
+{
+    for (int i = 0; i < N; ++i)
+        if (!isfinite(y[i])) return 1;
+    return 0;
+}
+
+static int var_rk_trial(int kind, const double *par, double sg, int N, int S, const double *A, int lda, const double *B,
+                        double h, const double *y, double K[][VAR_MAXN], double *ynew)
+{
+    int bad = 0;
+    double yt[VAR_MAXN];
+    for (int s = 1; s < S; ++s) {
+        for (int i = 0; i < N; ++i) {
+            double dy = 0;
+            for (int j = 0; j < s; ++j) dy += A[s * lda + j] * K[j][i];
+            yt[i] = y[i] + dy * h;
+        }
+        bad |= orc_var_rhs(kind, par, sg, yt, K[s]);
+    }
+    for (int i = 0; i < N; ++i) {
+        double dy = 0;
+        for (int j = 0; j < S; ++j) dy += B[j] * K[j][i];
+        ynew[i] = y[i] + h * dy;
+    }
+    bad |= orc_var_rhs(kind, par, sg, ynew, K[S]);
+    return bad;
+}
+
+static double var_initial_step(int kind, const double *par, double sg, int N, const double *y0, const double *f0,
+                               double interval, int err_order, double tol)
+{
+    double sc[VAR_MAXN], a[VAR_MAXN], y1[VAR_MAXN], f1[VAR_MAXN];
+    if (interval == 0) return 0;
+    for (int i = 0; i < N; ++i) sc[i] = tol + fabs(y0[i]) * tol;
+    for (int i = 0; i < N; ++i) a[i] = y0[i] / sc[i];
+    double d0 = rms(a, N);
+    for (int i = 0; i < N; ++i) a[i] = f0[i] / sc[i];
+    double d1 = rms(a, N);
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    if (h0 > interval) h0 = interval;
+    for (int i = 0; i < N; ++i) y1[i] = y0[i] + h0 * f0[i];
+    orc_var_rhs(kind, par, sg, y1, f1);
+    for (int i = 0; i < N; ++i) a[i] = (f1[i] - f0[i]) / sc[i];
+    double d2 = rms(a, N) / h0;
+    double h1;
+    if (d1 <= 1e-15 && d2 <= 1e-15)
+        h1 = fmax(1e-6, h0 * 1e-3);
+    else
+        h1 = pow(0.01 / fmax(d1, d2), 1.0 / (err_order + 1));
+    double h = fmin(100 * h0, h1);
+    if (!(h == h)) h = 1e-6;
+    return fmin(h, interval);
+}
+
+/* One (x, Phi) trajectory, same solver contract and controller as orc_solve_one, stepping exactly onto
+ * every ts[k]; out[nt][N] (may be NULL: only the final state is kept in y). */
+static int var_solve_one(const orc_problem *pb, double *y, const double *ts, int nt, const int *nsub, const double *hsub,
+                         double *out, long *nsteps)
+{
+    int kind = pb->kind, nv = orc_nvar(kind), N = nv + nv * nv;
+    double sg = pb->backwards ? -1.0 : 1.0;
+    const double *par = pb->par;
+    long att = 0;
+    int status = ST_OK;
+    *nsteps = 0;
+    if (var_nonfinite(y, N) || orc_out_of_bounds(kind, y)) return ST_BAD_IC;
+    if (pb->alg == ALG_RK4 || pb->alg == ALG_RK8) {
+        double K[13][VAR_MAXN], yt[VAR_MAXN], yn[VAR_MAXN];
+        for (int k = 0; k < nt; ++k) {
+            int bad = 0;
+            for (int s = 0; s < nsub[k]; ++s) {
+                double h = hsub[k];
+                if (pb->alg == ALG_RK4) {
+                    bad |= orc_var_rhs(kind, par, sg, y, K[0]);
+                    for (int i = 0; i < N; ++i) yt[i] = y[i] + (h / 2) * K[0][i];
+                    bad |= orc_var_rhs(kind, par, sg, yt, K[1]);
+                    for (int i = 0; i < N; ++i) yt[i] = y[i] + (h / 2) * K[1][i];
+                    bad |= orc_var_rhs(kind, par, sg, yt, K[2]);
+                    for (int i = 0; i < N; ++i) yt[i] = y[i] + h * K[2][i];
+                    bad |= orc_var_rhs(kind, par, sg, yt, K[3]);
+                    for (int i = 0; i < N; ++i) y[i] = y[i] + (h / 6) * (K[0][i] + 2 * K[1][i] + 2 * K[2][i] + K[3][i]);
+                } else {
+                    bad |= orc_var_rhs(kind, par, sg, y, K[0]);
+                    bad |= var_rk_trial(kind, par, sg, N, 12, &DOP853_A[0][0], 12, DOP853_B, h, y, K, yn);
+                    memcpy(y, yn, sizeof(double) * N);
+                }
+                att++;
+            }
+            if (bad || var_nonfinite(y, N) || orc_out_of_bounds(kind, y)) {
+                status = ST_DOMAIN;
+                break;
+            }
+            if (out) memcpy(out + (size_t)k * N, y, sizeof(double) * N);
+        }
+    } else {
+        int S = (pb->alg == ALG_DP5) ? 6 : 12;
+        int err_order = (pb->alg == ALG_DP5) ? 4 : 7;
+        double expo = -1.0 / (err_order + 1);
+        double tol = pb->tol, dtmin = pb->dtmin;
+        double K[13][VAR_MAXN], yn[VAR_MAXN];
+        double t = 0, tend = ts[nt - 1], h_abs = 0;
+        int have_f = 0, rejected = 0;
+        for (int k = 0; k < nt && status == ST_OK; ++k) {
+            double tstop = ts[k];
+            while (t < tstop) {
+                if (!have_f) {
+                    if (orc_var_rhs(kind, par, sg, y, K[0])) {
+                        status = ST_DOMAIN;
+                        break;
+                    }
+                    h_abs = var_initial_step(kind, par, sg, N, y, K[0], tend - t, err_order, tol);
+                    have_f = 1;
+                }
+                if (att >= pb->maxiters) {
+                    status = ST_MAXITERS;
+                    break;
+                }
+                att++;
+                int forced = 0;
+                if (h_abs < dtmin) {
+                    h_abs = dtmin;
+                    forced = 1;
+                }
+                double h = h_abs;
+                int clipped = 0;
+                if (t + h >= tstop) {
+                    clipped = (tstop - t) < h_abs;
+                    h = tstop - t;
+                }
+                int bad;
+                if (pb->alg == ALG_DP5)
+                    bad = var_rk_trial(kind, par, sg, N, 6, &DP5_A[0][0], 6, DP5_B, h, y, K, yn);
+                else
+                    bad = var_rk_trial(kind, par, sg, N, 12, &DOP853_A[0][0], 12, DOP853_B, h, y, K, yn);
+                double err, sc[VAR_MAXN];
+                for (int i = 0; i < N; ++i) sc[i] = tol + fmax(fabs(y[i]), fabs(yn[i])) * tol;
+                if (pb->alg == ALG_DP5) {
+                    double e[VAR_MAXN];
+                    for (int i = 0; i < N; ++i) {
+                        double s = 0;
+                        for (int j = 0; j <= S; ++j) s += DP5_E[j] * K[j][i];
+                        e[i] = s * h / sc[i];
+                    }
+                    err = rms(e, N);
+                } else {
+                    double n5 = 0, n3 = 0;
+                    for (int i = 0; i < N; ++i) {
+                        double s5 = 0, s3 = 0;
+                        for (int j = 0; j <= S; ++j) {
+                            s5 += DOP853_E5[j] * K[j][i];
+                            s3 += DOP853_E3[j] * K[j][i];
+                        }
+                        s5 /= sc[i];
+                        s3 /= sc[i];
+                        n5 += s5 * s5;
+                        n3 += s3 * s3;
+                    }
+                    err = (n5 == 0 && n3 == 0) ? 0 : fabs(h) * n5 / sqrt((n5 + 0.01 * n3) * N);
+                }
+                bad = bad || var_nonfinite(yn, N) || !isfinite(err) || orc_out_of_bounds(kind, yn);
+                if (bad) {
+                    if (forced) {
+                        status = ST_DOMAIN;
+                        break;
+                    }
+                    h_abs = h * 0.2;
+                    rejected = 1;
+                    continue;
+                }
+                if (err < 1 || forced) {
+                    double factor = (err == 0) ? 10.0 : fmin(10.0, 0.9 * pow(err, expo));
+                    if (rejected) factor = fmin(1.0, factor);
+                    double hn = h * factor;
+                    if (clipped && hn < h_abs) hn = h_abs;
+                    h_abs = hn;
+                    t = (t + h >= tstop) ? tstop : t + h;
+                    memcpy(y, yn, sizeof(double) * N);
+                    memcpy(K[0], K[S], sizeof(double) * N);
+                    rejected = 0;
+                } else {
+                    h_abs = h * fmax(0.2, 0.9 * pow(err, expo));
+                    rejected = 1;
+                }
+            }
+            if (status != ST_OK) break;
+            if (out) memcpy(out + (size_t)k * N, y, sizeof(double) * N);
+        }
+    }
+    *nsteps = att;
+    return status;
+}
+
+/* integrate(...; get_fundamental_matrix=true): out_u[n][nt][nv], out_fm[n][nt][nv*nv] column-major */
+int orc_integrate_fm(const orc_problem *pb, const double *u0, const double *fm0, long n, const double *ts, int nt,
+                     double *out_u, double *out_fm, int *status, long *nsteps)
+{
+    int nv = orc_nvar(pb->kind), nn = nv * nv, N = nv + nn;
+    int *nsub = (int *)malloc(sizeof(int) * nt);
+    double *hsub = (double *)malloc(sizeof(double) * nt);
+    if (orc_step_table(ts, nt, pb->dt > 0 ? pb->dt : 1.0, nsub, hsub)) {
+        free(nsub);
+        free(hsub);
+        return -1;
+    }
+#pragma omp parallel for schedule(dynamic, 4)
+    for (long i = 0; i < n; ++i) {
+        double y[VAR_MAXN];
+        double *tmp = (double *)malloc(sizeof(double) * (size_t)nt * N);
+        for (long j = 0; j < (long)nt * N; ++j) tmp[j] = NAN;
+        memcpy(y, u0 + i * nv, sizeof(double) * nv);
+        for (int c = 0; c < nv; ++c)
+            for (int r = 0; r < nv; ++r) y[nv + c * nv + r] = fm0 ? fm0[i * nn + c * nv + r] : (r == c ? 1.0 : 0.0);
+        long ns;
+        int st = var_solve_one(pb, y, ts, nt, nsub, hsub, tmp, &ns);
+        for (int k = 0; k < nt; ++k) {
+            memcpy(out_u + ((size_t)i * nt + k) * nv, tmp + (size_t)k * N, sizeof(double) * nv);
+            memcpy(out_fm + ((size_t)i * nt + k) * nn, tmp + (size_t)k * N + nv, sizeof(double) * nn);
+        }
+        free(tmp);
+        if (status) status[i] = st;
+        if (nsteps) nsteps[i] = ns;
+    }
+    free(nsub);
+    free(hsub);
+    return 0;
+}
+
+/* lyapunov_spectrum, src/ClassicalSystems.jl:183-224, loop for loop (including the convergence test
+ * inside the loop over columns).  status: ST_* of the integration, or 5 = "Maximum iterations". */
+int orc_lyapunov(const orc_problem *pb, const double *u0, long n, double t_interval, double ltol, double lreltol,
+                 int maxiters, double *lambda, double *x_final, int *iters, int *status, long *nsteps)
+{
+    int nv = orc_nvar(pb->kind);
+    int nsub[1];
+    double hsub[1], ts1[1] = {t_interval};
+    if (orc_step_table(ts1, 1, pb->dt > 0 ? pb->dt : 1.0, nsub, hsub)) return -1;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long ic = 0; ic < n; ++ic) {
+        double x[4], u[16], v[16], lam[4] = {0, 0, 0, 0}, lam_old[4], sums[4] = {0, 0, 0, 0};
+        memcpy(x, u0 + ic * nv, sizeof(double) * nv);
+        for (int c = 0; c < nv; ++c)
+            for (int r = 0; r < nv; ++r) u[c * nv + r] = (r == c) ? 1.0 : 0.0;
+        int st = ST_OK, done = 0, it = 0;
+        long steps = 0;
+        for (int k = 1; k <= maxiters && !done && st == ST_OK; ++k) {
+            it = k;
+            memcpy(lam_old, lam, sizeof(lam));
+            double y[VAR_MAXN];
+            memcpy(y, x, sizeof(double) * nv);
+            memcpy(y + nv, u, sizeof(double) * nv * nv);
+            long ns;
+            st = var_solve_one(pb, y, ts1, 1, nsub, hsub, NULL, &ns);
+            steps += ns;
+            if (st != ST_OK) break;
+            memcpy(x, y, sizeof(double) * nv);
+            for (int i = 0; i < nv && !done; ++i) {
+                for (int r = 0; r < nv; ++r) v[i * nv + r] = y[nv + i * nv + r];
+                for (int j = 0; j < i; ++j) {
+                    double d = 0;
+                    for (int r = 0; r < nv; ++r) d += v[i * nv + r] * u[j * nv + r];
+                    for (int r = 0; r < nv; ++r) v[i * nv + r] -= d * u[j * nv + r];
+                }
+                double n2 = 0;
+                for (int r = 0; r < nv; ++r) n2 += v[i * nv + r] * v[i * nv + r];
+                double nrm = sqrt(n2);
+                for (int r = 0; r < nv; ++r) u[i * nv + r] = v[i * nv + r] / nrm;
+                sums[i] += log(nrm);
+                lam[i] = sums[i] / (k * t_interval);
+                double e2 = 0, l2 = 0;
+                for (int r = 0; r < nv; ++r) {
+                    e2 += (lam_old[r] - lam[r]) * (lam_old[r] - lam[r]);
+                    l2 += lam[r] * lam[r];
+                }
+                if (sqrt(e2) < lreltol * sqrt(l2) + ltol) done = 1;
+            }
+            /* columns not reached this round keep last round's orthonormal u (they are re-read from y next round only
+             * if the loop completed; when `done` the function returns, as in the reference) */
+        }
+        if (st == ST_OK && !done) st = 5;
+        memcpy(lambda + ic * nv, lam, sizeof(double) * nv);
+        if (x_final) memcpy(x_final + ic * nv, x, sizeof(double) * nv);
+        iters[ic] = it;
+        status[ic] = st;
+        if (nsteps) nsteps[ic] = steps;
+    }
+    return 0;
+}

@@ -85,6 +85,12 @@ def lib(fast: bool = False):
                                    C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long)]
         L.orc_ensemble.restype = C.c_int
         L.orc_max_threads.restype = C.c_int
+        ip, lp = C.POINTER(C.c_int), C.POINTER(C.c_long)
+        L.orc_integrate_fm.argtypes = [C.POINTER(Problem), dp, dp, C.c_long, dp, C.c_int, dp, dp, ip, lp]
+        L.orc_integrate_fm.restype = C.c_int
+        L.orc_lyapunov.argtypes = [C.POINTER(Problem), dp, C.c_long, C.c_double, C.c_double, C.c_double, C.c_int,
+                                   dp, dp, ip, ip, lp]
+        L.orc_lyapunov.restype = C.c_int
         _libs[key] = L
     return _libs[key]
 
@@ -173,6 +179,45 @@ def integrate(kind, par, u0, ts, alg=ALG_DOP853, dt=0.0, tol=1e-12, dtmin=None, 
     if rc:
         raise ValueError("ts must be sorted and non-negative")
     return out, status, nacc, nrej
+
+
+def integrate_fm(kind, par, u0, ts, fm0=None, alg=ALG_DOP853, dt=0.0, tol=1e-12, dtmin=None, maxiters=100000,
+                 backwards=False, fast=False):
+    """integrate(...; get_fundamental_matrix=true) (src/ClassicalSystems.jl:110-128): returns
+    (x[n][nt][nv], Phi[n][nt][nv][nv] with Phi[..., r, c] = d x_r(t) / d x_c(0), status[n], attempts[n])."""
+    nv = nvar(kind)
+    u0 = np.ascontiguousarray(u0, dtype=np.float64).reshape(-1, nv)
+    ts = np.ascontiguousarray(ts, dtype=np.float64)
+    n, nt = u0.shape[0], len(ts)
+    f0 = None
+    if fm0 is not None:   # [n][r][c] -> column-major flat
+        f0 = np.ascontiguousarray(np.swapaxes(np.asarray(fm0, dtype=np.float64).reshape(n, nv, nv), 1, 2))
+    out_u, out_fm = np.empty((n, nt, nv)), np.empty((n, nt, nv * nv))
+    status, nsteps = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int64)
+    pb = make_problem(kind, par, alg, dt, tol, dtmin, maxiters, backwards)
+    rc = lib(fast).orc_integrate_fm(C.byref(pb), _dp(u0), _dp(f0) if f0 is not None else None, n, _dp(ts), nt, _dp(out_u),
+                                    _dp(out_fm), status.ctypes.data_as(C.POINTER(C.c_int)),
+                                    nsteps.ctypes.data_as(C.POINTER(C.c_long)))
+    if rc:
+        raise ValueError("ts must be sorted and non-negative")
+    return out_u, np.swapaxes(out_fm.reshape(n, nt, nv, nv), 2, 3), status, nsteps
+
+
+def lyapunov(kind, par, u0, t=100.0, ltol=1e-4, lreltol=1e-3, maxiters=100, alg=ALG_DOP853, dt=0.0, tol=1e-12,
+             dtmin=None, solver_maxiters=10 ** 9, fast=False):
+    """lyapunov_spectrum (src/ClassicalSystems.jl:183-224) for a batch: (lambda[n][nv], x_final, iters, status, attempts)."""
+    nv = nvar(kind)
+    u0 = np.ascontiguousarray(u0, dtype=np.float64).reshape(-1, nv)
+    n = u0.shape[0]
+    lam, xf = np.empty((n, nv)), np.empty((n, nv))
+    iters, status, nsteps = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int64)
+    pb = make_problem(kind, par, alg, dt, tol, dtmin, solver_maxiters, False)
+    rc = lib(fast).orc_lyapunov(C.byref(pb), _dp(u0), n, float(t), float(ltol), float(lreltol), int(maxiters), _dp(lam), _dp(xf),
+                                iters.ctypes.data_as(C.POINTER(C.c_int)), status.ctypes.data_as(C.POINTER(C.c_int)),
+                                nsteps.ctypes.data_as(C.POINTER(C.c_long)))
+    if rc:
+        raise ValueError("bad interval")
+    return lam, xf, iters, status, nsteps
 
 
 def philox(ctr, key):

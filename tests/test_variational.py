@@ -1,0 +1,187 @@
+"""fundamental matrix (get_fundamental_matrix=true, src/ClassicalSystems.jl:110-128) and
+lyapunov_spectrum (:183-224).  CPU tests pin the oracle (mpmath/sympy truth, symplecticity, finite
+differences); `gpu` tests compare the CUDA kernels (through the C ABI) with the oracle and the truth."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, relerr
+
+DPAR = [1.0, 1.0, 1.0]
+LPAR = [1.0, -1.0]
+DOCS_PT = [1.0, 0.31783724519578205, 1.0, 0.0]
+OMEGA4 = np.array([[0, 0, 1, 0], [0, 0, 0, 1], [-1, 0, 0, 0], [0, -1, 0, 0]], float)   # order (Q, q, P, p)
+OMEGA2 = np.array([[0, 1], [-1, 0]], float)
+
+
+@pytest.fixture(scope="module")
+def vgold():
+    with open(os.path.join(GOLD, "variational.json")) as f:
+        return json.load(f)["cases"]
+
+
+def _truth(case):
+    n = len(case["u0"])
+    ts = [r["t"] for r in case["rows"]]
+    x = np.array([r["x"] for r in case["rows"]])
+    phi = np.array([np.array(r["phi_colmajor"]).reshape(n, n).T for r in case["rows"]])   # -> [r][c]
+    return ts, x, phi
+
+
+# ---------------------------------------------------------------- oracle (CPU)
+def test_oracle_fundamental_matrix_matches_mpmath_sympy_truth(O, vgold):
+    """hand-written Jacobian (oracle.c) == sympy Jacobian of the reference's equations, integrated to 30 digits"""
+    for c in vgold:
+        kind = O.SYS_DICKE if c["kind"] == "dicke" else O.SYS_LMG
+        ts, x, phi = _truth(c)
+        xo, fo, st, _ = O.integrate_fm(kind, c["par"], [c["u0"]], ts, alg=O.ALG_DOP853, tol=1e-13)
+        assert st[0] == 0
+        assert relerr(xo[0], x).max() < 1e-10
+        assert relerr(fo[0], phi).max() < 1e-9, (c["kind"], relerr(fo[0], phi).max())
+
+
+def test_oracle_fundamental_matrix_is_symplectic_and_matches_finite_differences(O):
+    x, F, st, _ = O.integrate_fm(O.SYS_DICKE, DPAR, [DOCS_PT], [0.0, 1.0, 5.0], tol=1e-12)
+    assert np.allclose(F[0, 0], np.eye(4))
+    for k in range(3):
+        M = F[0, k]
+        assert np.abs(M.T @ OMEGA4 @ M - OMEGA4).max() < 1e-10
+        assert abs(np.linalg.det(M) - 1) < 1e-10
+    eps, cols = 1e-6, []
+    for c in range(4):
+        up, um = np.array(DOCS_PT), np.array(DOCS_PT)
+        up[c] += eps
+        um[c] -= eps
+        a, _, _, _ = O.integrate(O.SYS_DICKE, DPAR, [up], [1.0], tol=1e-13)
+        b, _, _, _ = O.integrate(O.SYS_DICKE, DPAR, [um], [1.0], tol=1e-13)
+        cols.append((a[0, 0] - b[0, 0]) / (2 * eps))
+    assert np.abs(np.array(cols).T - F[0, 1]).max() < 1e-8
+    # initial matrix: Phi(t; U) = Phi(t; I) U   (src/ClassicalSystems.jl:113-115)
+    U = np.array([[1, 2, 0, 0], [0, 1, 0, 3], [0, 0, 1, 0], [1, 0, 0, 1]], float)
+    _, FU, _, _ = O.integrate_fm(O.SYS_DICKE, DPAR, [DOCS_PT], [1.0], fm0=[U], tol=1e-12)
+    assert np.abs(FU[0, 0] - F[0, 1] @ U).max() < 1e-8
+
+
+def test_oracle_lyapunov_spectrum(O):
+    """chaotic docs point: lambda_max > 0 and the Hamiltonian pairing (l, ~0, ~0, -l) with a short interval;
+    LMG (one degree of freedom, integrable): exponents -> 0 and sum = 0"""
+    lam, xf, it, st, ns = O.lyapunov(O.SYS_DICKE, DPAR, [DOCS_PT], t=5.0, tol=1e-10, ltol=1e-4, maxiters=2000)
+    assert st[0] == 0 and lam[0, 0] > 0.1
+    assert abs(lam[0].sum()) < 1e-3 and abs(lam[0, 0] + lam[0, 3]) < 0.02 and abs(lam[0, 1]) < 0.1   # (the early return mixes rounds k and k-1)
+    lam, xf, it, st, ns = O.lyapunov(O.SYS_LMG, LPAR, [[0.5, 0.3]], t=100.0, tol=1e-8)
+    assert st[0] == 0 and abs(lam[0]).max() < 0.02 and abs(lam[0].sum()) < 1e-3
+    # the reference's defaults (t = 100): only the largest exponent is meaningful in double precision
+    lam, xf, it, st, ns = O.lyapunov(O.SYS_DICKE, DPAR, [DOCS_PT], t=100.0, tol=1e-8, ltol=5e-5)
+    assert st[0] == 0 and 0.3 < lam[0].max() < 0.5
+    # no convergence within maxiters -> status 5 ("Maximum iterations", src/ClassicalSystems.jl:223)
+    lam, xf, it, st, ns = O.lyapunov(O.SYS_DICKE, DPAR, [DOCS_PT], t=1.0, tol=1e-8, ltol=1e-12, lreltol=0.0, maxiters=3)
+    assert st[0] == 5 and it[0] == 3
+
+
+# ---------------------------------------------------------------- GPU
+def csys(pkg, kind, par):
+    s = pkg._lib.System()
+    s.kind = kind
+    for i, v in enumerate(par):
+        s.params[i] = v
+    return s
+
+
+def csol(pkg, alg, dt=0.0, tol=1e-12, backwards=False):
+    s = pkg._lib.Solver()
+    s.alg, s.backwards, s.dt, s.tol = alg, int(backwards), dt, tol
+    return s
+
+
+@pytest.mark.gpu
+def test_gpu_fundamental_matrix_matches_truth_and_oracle(ctx, pkg, O, vgold):
+    for c in vgold:
+        kind = 0 if c["kind"] == "dicke" else 1
+        ts, x, phi = _truth(c)
+        for alg, kw, tol_x, tol_f in ((pkg._lib.ALG_DOP853, dict(tol=1e-13), 1e-10, 1e-9), (pkg._lib.ALG_DP5, dict(tol=1e-13), 1e-9, 1e-8),
+                                      (pkg._lib.ALG_RK8, dict(dt=2.0 ** -5), 1e-10, 1e-9), (pkg._lib.ALG_RK4, dict(dt=2.0 ** -9), 1e-9, 1e-8)):
+            xg, fg, st, ns = ctx.integrate_fm(csys(pkg, kind, c["par"]), csol(pkg, alg, **kw), [c["u0"]], ts)
+            assert st[0] == 0 and ns[0] > 0
+            assert relerr(xg[0], x).max() < tol_x, (c["kind"], alg, relerr(xg[0], x).max())
+            assert relerr(fg[0], phi).max() < tol_f, (c["kind"], alg, relerr(fg[0], phi).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,par,name", [(0, DPAR, "dicke"), (1, LPAR, "lmg")])
+def test_gpu_fundamental_matrix_batch_matches_oracle(ctx, pkg, O, gold, kind, par, name):
+    """matched step / tolerance against the oracle on the golden initial conditions, ragged batch size,
+    custom initial matrices, backwards integration; the x part must equal dtwa_integrate's trajectories"""
+    g = gold["truth_ld"][name]
+    u0 = np.array(g["u0"])[:37]
+    nv = u0.shape[1]
+    ts = np.array([0.0, 0.5, 1.0, 2.0])
+    rng = np.random.default_rng(5)
+    fm0 = np.eye(nv)[None] + 0.3 * rng.standard_normal((len(u0), nv, nv))
+    okind = O.SYS_DICKE if kind == 0 else O.SYS_LMG
+    for alg, oalg, kw in ((pkg._lib.ALG_RK4, O.ALG_RK4, dict(dt=2.0 ** -7)), (pkg._lib.ALG_DOP853, O.ALG_DOP853, dict(tol=1e-11))):
+        for backwards in (False, True):
+            xg, fg, st, ns = ctx.integrate_fm(csys(pkg, kind, par), csol(pkg, alg, backwards=backwards, **kw), u0, ts, fm0)
+            xo, fo, so, no = O.integrate_fm(okind, par, u0, ts, fm0=fm0, alg=oalg, backwards=backwards, **kw)
+            assert np.array_equal(st, so)
+            ok = st == 0
+            assert ok.sum() >= len(u0) - 2
+            assert relerr(xg[ok], xo[ok]).max() < 1e-10
+            assert relerr(fg[ok], fo[ok], floor=1e-2).max() < 2e-9
+            xs, st2, _ = ctx.integrate(csys(pkg, kind, par), csol(pkg, alg, backwards=backwards, **kw), u0, ts)
+            if alg == pkg._lib.ALG_RK4:
+                assert relerr(xg[ok], xs[ok]).max() < 1e-12     # same steps; the variational RHS is not w-folded
+    om = OMEGA4 if kind == 0 else OMEGA2
+    xg, fg, st, ns = ctx.integrate_fm(csys(pkg, kind, par), csol(pkg, pkg._lib.ALG_DOP853, tol=1e-12), u0, ts)
+    for i in np.flatnonzero(st == 0):
+        for k in range(len(ts)):
+            assert np.abs(fg[i, k].T @ om @ fg[i, k] - om).max() < 1e-8
+
+
+@pytest.mark.gpu
+def test_gpu_lyapunov_matches_oracle(ctx, pkg, O):
+    """a small Lyapunov map (docs/src/ClassicalDickeExamples.md:133-236 parameters): same exponents and the
+    same number of renormalisation rounds as the oracle's restatement of the reference loop"""
+    from dickemodel_jl_b200 import ClassicalDicke as CD, ClassicalSystems as CS
+    system = CD.ClassicalDickeSystem(w=0.8, g=0.8, w0=1)
+    eps = -1.35
+    pts = []
+    for Q in np.linspace(CD.minimum_nonnegative_Q_for_ϵ(system, eps), CD.maximum_Q_for_ϵ(system, eps), 9)[1:-1]:
+        for P in np.linspace(0, CD.maximum_P_for_ϵ(system, eps), 7)[:-1]:
+            if CD.minimum_ϵ_for(system, P=P, p=0, Q=Q) <= eps:
+                pts.append(CD.Point(system, Q=Q, P=P, p=0, ϵ=eps))
+    pts = np.array(pts)
+    assert len(pts) >= 15
+    lam, status = CS.lyapunov_spectrum_batch(system, pts, 100, tol=1e-8, λtol=5e-5, integrator_alg="DP8")
+    info = dict(CS.last_lyapunov_info)
+    lo, xo, ito, sto, nso = O.lyapunov(O.SYS_DICKE, [1.0, 0.8, 0.8], pts, t=100, ltol=5e-5, lreltol=1e-3, maxiters=100, tol=1e-8)
+    same = (info["iterations"] == ito) & (status == sto)
+    assert same.mean() > 0.8          # chaotic orbits: rounding-level differences can shift the stopping round
+    conv = same & (status == 0)
+    assert conv.sum() >= 10
+    assert np.abs(lam[conv].max(axis=1) - lo[conv].max(axis=1)).max() < 2e-3
+    regular = conv & (lo.max(axis=1) < 0.01)
+    if regular.any():
+        assert np.abs(lam[regular] - lo[regular]).max() < 1e-5
+    # drop-in single-point API (src/ClassicalSystems.jl:166-171)
+    i = int(np.flatnonzero(conv)[0])
+    le = CS.lyapunov_exponent(system, pts[i], tol=1e-8, λtol=5e-5, verbose=False)
+    assert abs(le - lam[i].max()) < 1e-12
+    with pytest.raises(RuntimeError, match="Maximum iterations"):
+        CS.lyapunov_spectrum(system, pts[i], 1.0, tol=1e-8, λtol=1e-13, λreltol=0.0, maxiters=2)
+
+
+@pytest.mark.gpu
+def test_integrate_api_with_fundamental_matrix(pkg, O):
+    from dickemodel_jl_b200 import ClassicalDicke as CD, ClassicalSystems as CS
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    s = CS.integrate(system, DOCS_PT, 2.0, get_fundamental_matrix=True, tol=1e-12)
+    x, Phi = s.x()
+    xo, fo, st, _ = O.integrate_fm(O.SYS_DICKE, DPAR, [DOCS_PT], [0.0, 2.0], tol=1e-12)
+    assert relerr(x, xo[0, 1]).max() < 1e-10 and relerr(Phi, fo[0, 1]).max() < 1e-9
+    U = np.diag([1.0, 2.0, 3.0, 4.0])
+    s2 = CS.integrate(system, DOCS_PT, 2.0, get_fundamental_matrix=True, fundamental_matrix_initial=U, tol=1e-12)
+    assert relerr(s2.fundamental_matrix[-1], Phi @ U, floor=1e-2).max() < 1e-8
+    with pytest.raises(ValueError):
+        CS.integrate(system, DOCS_PT, 2.0, get_fundamental_matrix=True, fundamental_matrix_initial=np.eye(3))
