@@ -3,8 +3,10 @@
 Mirrors src/ClassicalSystems.jl:19-45 (protocol) and :78-140 (integrate) of the reference.  The
 solve itself runs on the GPU through dtwa_integrate (include/dicketwa.h); nothing here integrates
 on the CPU.  The fundamental matrix (get_fundamental_matrix, :110-128) and lyapunov_spectrum /
-lyapunov_exponent (:157-224) run on the GPU too (dtwa_integrate_fm, dtwa_lyapunov).  Out of scope
-(SURVEY.md section 8): use_big_numbers, DiffEq callbacks.
+lyapunov_exponent (:157-224) run on the GPU too (dtwa_integrate_fm, dtwa_lyapunov), and so does the one
+DiffEq callback the docs use: ContinuousCallback with save_positions=(false,false) on a linear condition
+(surfaces of section, dtwa_integrate_events).  Out of scope: use_big_numbers,
+other DiffEq callbacks.
 """
 from __future__ import annotations
 
@@ -102,7 +104,7 @@ def solver_from_kargs(kargs: dict) -> _lib.Solver:
     maxiters = k.pop("maxiters", None)
     for ignored in ("save_everystep", "show_progress", "progress", "verbose", "dense"):
         k.pop(ignored, None)
-    for unsupported in ("use_big_numbers", "callback"):
+    for unsupported in ("use_big_numbers", "callback"):   # integrate() handles ContinuousCallback itself
         if k.pop(unsupported, None):
             raise NotImplementedError(f"{unsupported} is outside the GPU hot path (SURVEY.md section 8)")
     for unsupported in ("get_fundamental_matrix", "fundamental_matrix_initial"):   # integrate() handles these itself
@@ -159,13 +161,52 @@ class ODESolution:
         return len(self.t)
 
 
+class _IntegratorView:
+    """What `affect!(integrator)` sees in the reference: `.u` and `.t` at the event."""
+
+    def __init__(self, u, t, direction):
+        self.u, self.t, self.direction = u, t, direction
+
+
+class ContinuousCallback:
+    """DiffEqBase.ContinuousCallback as the docs use it (docs/src/ClassicalDickeExamples.md:82-109,180-184):
+    `condition(x, t, integrator)` must be an affine function of the state (e.g. `lambda x, t, _: x[3]` for p = 0);
+    `affect(integrator)` is called, in time order, for every zero crossing found on the GPU and must not modify
+    the integrator (save_positions=(false,false) semantics).  `affect_neg` defaults to `affect`; pass None to ignore
+    down-crossings.  `abstol`/`rootfind`/`interp_points` are accepted and ignored: crossings are located by a Henon
+    step to integrator accuracy, not by a tolerance-driven root search."""
+    _same = object()
+
+    def __init__(self, condition, affect, affect_neg=_same, *, save_positions=(False, False), abstol=None, reltol=None,
+                 rootfind=True, interp_points=10, max_events=65536):
+        if tuple(save_positions) != (False, False):
+            raise NotImplementedError("only save_positions=(false,false) is available on the GPU path")
+        self.condition, self.affect = condition, affect
+        self.affect_neg = affect if affect_neg is ContinuousCallback._same else affect_neg
+        self.max_events = int(max_events)
+
+    def linear_form(self, nvar):
+        """coef, offset with condition(x) == coef . x - offset (checked at random points)"""
+        g0 = float(self.condition(np.zeros(nvar), 0.0, None))
+        coef = np.array([float(self.condition(np.eye(nvar)[i], 0.0, None)) - g0 for i in range(nvar)])
+        rng = np.random.default_rng(1)
+        for _ in range(3):
+            x = rng.standard_normal(nvar)
+            if abs(float(self.condition(x, 0.0, None)) - (coef @ x + g0)) > 1e-12 * (1 + np.abs(x).max()):
+                raise NotImplementedError("ContinuousCallback condition must be an affine function of the state on the GPU path")
+        if self.affect is None and self.affect_neg is None:
+            raise ValueError("ContinuousCallback without affect")
+        direction = 0 if (self.affect is not None and self.affect_neg is not None) else (1 if self.affect is not None else -1)
+        return coef, -g0, direction
+
+
 _RETCODES = {_lib.TRAJ_OK: "Success", _lib.TRAJ_DOMAIN: "DomainError", _lib.TRAJ_MAXITERS: "MaxIters",
              _lib.TRAJ_BAD_IC: "OutOfBounds"}
 
 
 def integrate(system, u0, t, *, t0=0.0, tol=1e-12, get_fundamental_matrix=False, integrator_alg=None,
               use_big_numbers=False, integate_backwards=False, fundamental_matrix_initial=None, saveat=None,
-              **kargs):
+              callback=None, **kargs):
     """src/ClassicalSystems.jl:78-140.  Integrates u0 from t0 to t; the states are reported at
     `saveat` (array of times in [t0, t]; default [t0, t])."""
     if t < t0:
@@ -183,6 +224,20 @@ def integrate(system, u0, t, *, t0=0.0, tol=1e-12, get_fundamental_matrix=False,
     if np.any(ts < t0) or np.any(ts > t) or np.any(np.diff(ts) < 0):
         raise ValueError("saveat must be sorted and lie in [t₀, t]")
     full_kargs = dict(kargs, tol=tol, integrator_alg=integrator_alg, integate_backwards=integate_backwards)
+    if callback is not None:   # docs/src/ClassicalDickeExamples.md:82-109
+        if not isinstance(callback, ContinuousCallback):
+            raise NotImplementedError("only ClassicalSystems.ContinuousCallback is available on the GPU path")
+        if get_fundamental_matrix or saveat is not None:
+            raise NotImplementedError("callback cannot be combined with get_fundamental_matrix / saveat")
+        coef, offset, direction = callback.linear_form(len(u0))
+        ev_t, ev_u, ev_dir, cnt, u_end, status, nsteps, _ = _lib.default_context().integrate_events(
+            system._c_system(), sol, u0[None, :], t - t0, coef, offset, direction, callback.max_events)
+        if cnt[0] > callback.max_events:
+            raise RuntimeError(f"{int(cnt[0])} events exceed ContinuousCallback(max_events={callback.max_events})")
+        for k in range(int(cnt[0])):
+            fn = callback.affect if ev_dir[0, k] > 0 else callback.affect_neg
+            fn(_IntegratorView(ev_u[0, k].copy(), float(ev_t[0, k]) + t0, int(ev_dir[0, k])))
+        return ODESolution(system, u0, t0, ts, np.stack([u0, u_end[0]]), _RETCODES[int(status[0])], int(nsteps[0]), full_kargs)
     if get_fundamental_matrix:   # src/ClassicalSystems.jl:110-128
         n = len(u0)
         fm0 = None
@@ -211,6 +266,17 @@ def integrate_fm_batch(system, U0, ts, fundamental_matrix_initial=None, **kargs)
     """Many (x, Φ) trajectories at once: (x[n][nt][nvar], Φ[n][nt][nvar][nvar], status[n], nsteps[n])."""
     sol = solver_from_kargs(kargs)
     return _lib.default_context().integrate_fm(system._c_system(), sol, U0, ts, fundamental_matrix_initial)
+
+
+def poincare_section_batch(system, U0, t, *, coef, offset=0.0, direction=0, max_events=1024, **kargs):
+    """Crossings of the section coef . u = offset for many initial conditions in one launch (the docs' Poincare
+    surface, docs/src/ClassicalDickeExamples.md:82-109, draws one `integrate` per initial condition).
+    Returns a dict: t[n][cap], u[n][cap][nvar], direction[n][cap], count[n], u_end, status, nsteps, kernel_ms;
+    unused slots are NaN."""
+    sol = solver_from_kargs(kargs)
+    ev_t, ev_u, ev_dir, cnt, u_end, status, nsteps, ms = _lib.default_context().integrate_events(
+        system._c_system(), sol, U0, t, coef, offset, direction, max_events)
+    return dict(t=ev_t, u=ev_u, direction=ev_dir, count=cnt, u_end=u_end, status=status, nsteps=nsteps, kernel_ms=ms)
 
 
 last_lyapunov_info = {}

@@ -28,7 +28,12 @@ AXIS_EXPR, AXIS_TIME = 0, 1
 EXPORTS = ["dtwa_last_error", "dtwa_version", "dtwa_create", "dtwa_destroy", "dtwa_device_info", "dtwa_set_launch",
            "dtwa_hamiltonian", "dtwa_integrate", "dtwa_sample", "dtwa_pdf", "dtwa_eval_expr", "dtwa_scale_to_index",
            "dtwa_ensemble", "dtwa_ensemble_launch", "dtwa_plan_arenas", "dtwa_plan_fetch", "dtwa_plan_free",
-           "dtwa_fp64_peak", "dtwa_fp64_peak_regs", "dtwa_set_jit", "dtwa_jit_compile", "dtwa_integrate_fm", "dtwa_lyapunov"]
+           "dtwa_fp64_peak", "dtwa_fp64_peak_regs", "dtwa_set_jit", "dtwa_jit_compile", "dtwa_integrate_fm", "dtwa_lyapunov", "dtwa_integrate_events"]
+
+
+class Event(C.Structure):
+    """dtwa_event: the section coef . u - offset = 0"""
+    _fields_ = [("coef", C.c_double * 4), ("offset", C.c_double), ("direction", C.c_int32), ("pad", C.c_int32)]
 
 
 class DtwaError(RuntimeError):
@@ -116,6 +121,8 @@ def load():
         L.dtwa_fp64_peak_regs.argtypes = [vp, dp, dp]
         i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
         L.dtwa_integrate_fm.argtypes = [vp, C.POINTER(System), C.POINTER(Solver), dp, dp, C.c_int64, dp, C.c_int32, dp, dp, i32p, i64p]
+        L.dtwa_integrate_events.argtypes = [vp, C.POINTER(System), C.POINTER(Solver), dp, C.c_int64, C.c_double, C.POINTER(Event),
+                                            C.c_int32, dp, dp, i32p, i32p, dp, i32p, i64p, dp]
         L.dtwa_lyapunov.argtypes = [vp, C.POINTER(System), C.POINTER(Solver), dp, C.c_int64, C.c_double, C.c_double, C.c_double,
                                     C.c_int32, dp, dp, i32p, i32p, i64p, dp]
         L.dtwa_set_jit.argtypes = [vp, C.c_int]
@@ -224,6 +231,31 @@ class Context:
                                         _dp(ts), nt, _dp(out_u), _dp(out_fm), status.ctypes.data_as(C.POINTER(C.c_int32)),
                                         nsteps.ctypes.data_as(C.POINTER(C.c_int64))))
         return out_u, np.swapaxes(out_fm.reshape(n, nt, nv, nv), 2, 3), status, nsteps
+
+    def integrate_events(self, sys: System, sol: Solver, u0, t_end, coef, offset=0.0, direction=0, max_events=1024):
+        """(ev_t[n][cap], ev_u[n][cap][nv], ev_dir[n][cap], ev_count[n], u_end[n][nv], status[n], nsteps[n], kernel_ms)"""
+        nv = 4 if sys.kind == SYS_DICKE else 2
+        u0 = np.ascontiguousarray(u0, dtype=np.float64).reshape(-1, nv)
+        n, cap = u0.shape[0], int(max_events)
+        ev = Event()
+        for i, c in enumerate(np.asarray(coef, dtype=float).ravel()[:nv]):
+            ev.coef[i] = float(c)
+        ev.offset, ev.direction = float(offset), int(direction)
+        ev_t, ev_u = np.full((n, cap), np.nan), np.full((n, cap, nv), np.nan)
+        ev_dir, cnt = np.zeros((n, cap), dtype=np.int32), np.empty(n, dtype=np.int32)
+        u_end, status, nsteps = np.empty((n, nv)), np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int64)
+        ms = C.c_double()
+        i32p = C.POINTER(C.c_int32)
+        _check(load().dtwa_integrate_events(self._h, C.byref(sys), C.byref(sol), _dp(u0), n, float(t_end), C.byref(ev), cap, _dp(ev_t),
+                                            _dp(ev_u), ev_dir.ctypes.data_as(i32p), cnt.ctypes.data_as(i32p), _dp(u_end),
+                                            status.ctypes.data_as(i32p), nsteps.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(ms)))
+        for a in (ev_t, ev_u):   # slots beyond ev_count hold scratch
+            pass
+        valid = np.arange(cap)[None, :] < np.minimum(cnt, cap)[:, None]
+        ev_t[~valid] = np.nan
+        ev_u[~valid] = np.nan
+        ev_dir[~valid] = 0
+        return ev_t, ev_u, ev_dir, cnt, u_end, status, nsteps, ms.value
 
     def lyapunov(self, sys: System, sol: Solver, u0, t, ltol, lreltol, maxiters):
         """(lambda[n][nv], x_final[n][nv], iters[n], status[n], nsteps[n], kernel_ms)"""

@@ -718,6 +718,83 @@ extern "C" int dtwa_lyapunov(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_s
 }
 
 // ------------------------------------------------------------------------------------------------
+// surfaces of section (integrate + ContinuousCallback, docs/src/ClassicalDickeExamples.md:82-109)
+extern "C" int dtwa_integrate_events(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const double *u0, int64_t n,
+                                     double t_end, const dtwa_event *ev, int32_t max_events, double *ev_t, double *ev_u,
+                                     int32_t *ev_dir, int32_t *ev_count, double *u_end, int32_t *status, int64_t *nsteps,
+                                     double *kernel_ms)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    TRY(check_system(sys));
+    TRY(check_solver(sol));
+    if (!ev) return set_err(DTWA_ERR_INVALID, "NULL event");
+    if (n < 0 || max_events < 0 || (n > 0 && (!u0 || !ev_count || !status || !u_end)) || (n > 0 && max_events > 0 && (!ev_t || !ev_u || !ev_dir)))
+        return set_err(DTWA_ERR_INVALID, "bad buffers");
+    if (!(t_end >= 0)) return set_err(DTWA_ERR_INVALID, "Use integate_backwards=true instead of negative time");
+    if (ev->direction < -1 || ev->direction > 1) return set_err(DTWA_ERR_INVALID, "event direction must be -1, 0 or +1");
+    const int nv = nvar_of(sys->kind);
+    double cn = 0;
+    for (int i = 0; i < nv; ++i) cn += std::fabs(ev->coef[i]);
+    if (!(cn > 0) || !std::isfinite(cn) || !std::isfinite(ev->offset))
+        return set_err(DTWA_ERR_INVALID, "the event function coef . u - offset needs a non-zero, finite coefficient vector");
+    std::vector<StepTab> tab;
+    const double ts1[1] = {t_end};
+    TRY(build_step_table(ts1, 1, sol->dt, make_par(sys, sol->backwards).b, tab));
+    if (n == 0) return DTWA_OK;
+    DevCtx &d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    const size_t tab_b = sizeof(StepTab), ts_b = sizeof(double);
+    const size_t b_u0 = sizeof(double) * n * nv, cap = (size_t)max_events;
+    const size_t b_t = sizeof(double) * n * cap, b_u = b_t * nv, b_dir = sizeof(int32_t) * n * cap;
+    TRY(d.meta.ensure(tab_b + ts_b));
+    TRY(d.u0.ensure(2 * b_u0));
+    TRY(d.scratch_a.ensure(b_t + b_u + 16));
+    TRY(d.scratch_b.ensure(b_dir + 2 * sizeof(int32_t) * n + 16));
+    TRY(d.scratch_c.ensure(sizeof(long long) * n));
+    unsigned char *meta = (unsigned char *)d.meta.p;
+    CK(cudaMemcpyAsync(meta, tab.data(), tab_b, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(meta + tab_b, ts1, ts_b, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(d.u0.p, u0, b_u0, cudaMemcpyHostToDevice, d.stream));
+    const SolverArgs S = make_solver_args(sys, sol, (const StepTab *)meta, (const double *)(meta + tab_b), ts1, 1, tab);
+    EventArgs E;
+    std::memset(&E, 0, sizeof(E));
+    for (int i = 0; i < nv; ++i) E.coef[i] = ev->coef[i];
+    E.offset = ev->offset;
+    E.t_end = t_end;
+    E.direction = ev->direction;
+    E.cap = max_events;
+    double *d_t = (double *)d.scratch_a.p, *d_u = d_t + n * cap;
+    int32_t *d_dir = (int32_t *)d.scratch_b.p, *d_cnt = d_dir + n * cap, *d_st = d_cnt + n;
+    double *d_end = (double *)((unsigned char *)d.u0.p + b_u0);
+    CK(cudaEventRecord(d.ev[0], d.stream));
+    by_system(sys->kind, [&](auto sk) {
+        return by_alg(sol->alg, [&](auto ak) {
+            events_kernel<decltype(sk)::value, decltype(ak)::value><<<blocks_for(n, 128), 128, 0, d.stream>>>(
+                S, E, (const double *)d.u0.p, n, d_t, d_u, d_dir, d_cnt, d_end, d_st, (long long *)d.scratch_c.p);
+            return 0;
+        });
+    });
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(d.ev[3], d.stream));
+    if (cap) {
+        CK(cudaMemcpyAsync(ev_t, d_t, b_t, cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaMemcpyAsync(ev_u, d_u, b_u, cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaMemcpyAsync(ev_dir, d_dir, b_dir, cudaMemcpyDeviceToHost, d.stream));
+    }
+    CK(cudaMemcpyAsync(ev_count, d_cnt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(u_end, d_end, b_u0, cudaMemcpyDeviceToHost, d.stream));
+    if (nsteps) CK(cudaMemcpyAsync(nsteps, d.scratch_c.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    if (kernel_ms) {
+        float m = 0.f;
+        CK(cudaEventElapsedTime(&m, d.ev[0], d.ev[3]));
+        *kernel_ms = m;
+    }
+    return DTWA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // a13-a20: the ensemble
 struct RedLayout {
     int kind = 0;

@@ -190,6 +190,40 @@ struct Sys<DTWA_SYS_LMG_VAR> {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Henon's trick for surfaces of section (M. Henon, Physica D 5 (1982) 412): with the event function
+// g(u) = coef . u - offset as the independent variable, du/dg = f(u) / g', dt/dg = 1 / g',
+// g' = coef . f(u), ONE Runge-Kutta step of length -g(u1) from the end of the step that crossed the
+// section lands on it (g = 0 to rounding).  State: y = [u (NVB) | t].
+struct HenonPar : SysPar {
+    double coef[4];
+};
+template <int BASE>
+struct HenonSys {
+    static constexpr int NVB = Sys<BASE>::NV, NV = NVB + 1;
+    static constexpr int QI = Sys<BASE>::QI, PI = Sys<BASE>::PI, GROUP = 1, NORM_N = NV;
+    __device__ __forceinline__ static void rhs(const SysPar &p0, const double (&y)[NV], double (&dy)[NV])
+    {
+        const HenonPar &p = static_cast<const HenonPar &>(p0);
+        double u[NVB], f[NVB];
+#pragma unroll
+        for (int i = 0; i < NVB; ++i) u[i] = y[i];
+        Sys<BASE>::rhs(p, u, f);
+        double gd = 0.0;
+#pragma unroll
+        for (int i = 0; i < NVB; ++i) gd = fma(p.coef[i], f[i], gd);
+        const double inv = 1.0 / gd;
+#pragma unroll
+        for (int i = 0; i < NVB; ++i) dy[i] = f[i] * inv;
+        dy[NVB] = inv;
+    }
+};
+constexpr int DTWA_SYS_DICKE_HENON = 4, DTWA_SYS_LMG_HENON = 5;
+template <>
+struct Sys<DTWA_SYS_DICKE_HENON> : HenonSys<DTWA_SYS_DICKE> {};
+template <>
+struct Sys<DTWA_SYS_LMG_HENON> : HenonSys<DTWA_SYS_LMG> {};
+
 // does component i of this thread enter the group-wide norms?  (x is replicated: thread 0 of the group counts it)
 template <int SYS>
 __device__ __forceinline__ bool norm_counted(int i)

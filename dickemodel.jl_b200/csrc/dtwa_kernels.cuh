@@ -747,6 +747,174 @@ __global__ void __launch_bounds__(128) lyapunov_kernel(const SolverArgs S, const
     }
 }
 
+// K7: surfaces of section -- SURVEY 8f rank 3 (docs/src/ClassicalDickeExamples.md:82-109: integrate with a
+// DiffEq ContinuousCallback on p = 0, save_positions=(false,false)).  One thread per initial condition
+// integrates to t_end and records every crossing of g(u) = coef . u - offset = 0 (direction: 0 both,
+// +1 g increasing, -1 decreasing), located with Henon steps (dtwa_device.cuh) instead of the reference's
+// root search on the interpolant: predict the crossing time with a Henon step back from the end of the
+// crossing step; re-take the integrator's own step from the step start to that time (local error of an
+// accepted step) and polish the time with up to four Newton iterations on g (each one such step);
+// remove what is left of |g| (rounding level) with a last Henon step.
+//   ev_t[n][cap], ev_u[n][cap][NV], ev_dir[n][cap] (+1/-1), ev_count[n] (keeps counting beyond cap)
+struct EventArgs {
+    double coef[4];
+    double offset, t_end;
+    int32_t direction, cap;
+};
+template <int SYS, int ALG>
+__global__ void __launch_bounds__(128) events_kernel(const SolverArgs S, const EventArgs E, const double *__restrict__ u0,
+                                                     long long n, double *__restrict__ ev_t, double *__restrict__ ev_u,
+                                                     int32_t *__restrict__ ev_dir, int32_t *__restrict__ ev_count,
+                                                     double *__restrict__ u_end, int32_t *__restrict__ status,
+                                                     long long *__restrict__ nsteps)
+{
+    constexpr int NV = Sys<SYS>::NV;
+    constexpr int HSYS = (SYS == DTWA_SYS_DICKE) ? DTWA_SYS_DICKE_HENON : DTWA_SYS_LMG_HENON;
+    constexpr bool FIXED = is_fixed<ALG>::value;
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    HenonPar hp;
+    static_cast<SysPar &>(hp) = S.par;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hp.coef[i] = E.coef[i];
+    auto gfun = [&](const double (&u)[NV]) {
+        double g = -E.offset;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) g = fma(E.coef[i], u[i], g);
+        return g;
+    };
+    Traj<SYS, ALG> T;
+    T.status = ST_OK;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) T.u[i] = u0[j * NV + i];
+    T.begin(S);
+    int count = 0;
+    double t = 0.0, g0 = (T.status == ST_OK) ? gfun(T.u) : 0.0;
+    double us[NV], ts0 = 0.0;           // state and time at the start of the current step
+    auto henon = [&](double (&y)[NV + 1], double hg) {
+        if constexpr (ALG == DTWA_ALG_RK4) {
+            StepTab r;
+            r.h = hg; r.hh = hg / 2.0; r.h3 = hg / 3.0; r.h6 = hg / 6.0;
+            r.hw = r.hhw = r.h3w = r.h6w = 0.0;
+            r.n = 1; r.pad = 0;
+            rk4_step<HSYS>(hp, y, r);
+        } else {
+            rk8_step<HSYS>(hp, y, hg);
+        }
+    };
+    auto crossing = [&](double t1) {   // called with T.u = state at the end of an accepted step, time t1
+        const double g1 = gfun(T.u);
+        const bool up = g0 < 0.0 && g1 >= 0.0, down = g0 > 0.0 && g1 <= 0.0;
+        if ((up && E.direction >= 0) || (down && E.direction <= 0)) {
+            double y[NV + 1];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) y[i] = T.u[i];
+            y[NV] = t1;
+            if (g1 != 0.0) {
+                henon(y, -g1);                                   // predictor: crossing time from the step end
+                const double hs = t1 - ts0;
+                double th = y[NV] - ts0;
+                if (!(th > 0.0) || !(th <= hs)) th = hs * (g0 / (g0 - g1));   // grazing contact: fall back to the chord
+                double z[NV], g2 = 0.0;
+#pragma unroll 1
+                for (int it = 0; it < 5; ++it) {
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) z[i] = us[i];
+                    if constexpr (ALG == DTWA_ALG_RK4) {          // the integrator's own step, start -> predicted time
+                        StepTab r;
+                        const double wf = (SYS == DTWA_SYS_DICKE) ? S.par.b : 1.0;
+                        r.h = th; r.hh = th / 2.0; r.h3 = th / 3.0; r.h6 = th / 6.0;
+                        r.hw = r.h * wf; r.hhw = r.hh * wf; r.h3w = r.h3 * wf; r.h6w = r.h6 * wf;
+                        r.n = 1; r.pad = 0;
+                        rk4_step<SYS>(S.par, z, r);
+                    } else {
+                        rk8_step<SYS>(S.par, z, th);
+                    }
+                    g2 = gfun(z);
+                    if (it == 4 || fabs(g2) <= 1e-13) break;
+                    double f[NV], gd = 0.0;                       // Newton on the crossing time
+                    Sys<SYS>::rhs(S.par, z, f);
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) gd = fma(E.coef[i], f[i], gd);
+                    const double tn = th - g2 / gd;
+                    if (!(tn > 0.0) || !(tn <= hs)) break;
+                    th = tn;
+                }
+#pragma unroll
+                for (int i = 0; i < NV; ++i) y[i] = z[i];
+                y[NV] = ts0 + th;
+                if (g2 != 0.0) henon(y, -g2);                    // |g2| is at rounding level (unless Newton left the step)
+                bool fin = true;
+#pragma unroll
+                for (int i = 0; i <= NV; ++i) fin = fin && (y[i] == y[i]) && !isinf(y[i]);
+                if (!fin) {
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) y[i] = z[i];
+                    y[NV] = ts0 + th;
+                }
+            }
+            if (count < E.cap) {
+                const size_t e = (size_t)j * E.cap + count;
+                ev_t[e] = y[NV];
+#pragma unroll
+                for (int i = 0; i < NV; ++i) ev_u[e * NV + i] = y[i];
+                ev_dir[e] = up ? 1 : -1;
+            }
+            ++count;
+        }
+        g0 = g1;
+    };
+    if (T.status == ST_OK && E.t_end > 0.0) {
+        if constexpr (FIXED) {
+            const StepTab r = S.uniform ? S.uni : S.tab[0];
+            const int nst = S.uniform ? S.first_n : r.n;
+#pragma unroll 1
+            for (int s = 0; s < nst && T.status == ST_OK; ++s) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) us[i] = T.u[i];
+                ts0 = t;
+                if constexpr (ALG == DTWA_ALG_RK4)
+                    rk4_step<SYS>(S.par, T.u, r);
+                else
+                    rk8_step<SYS>(S.par, T.u, r.h);
+                ++T.nacc;
+                if (state_bad<SYS>(T.u)) {
+                    T.status = ST_DOMAIN;
+                    break;
+                }
+                t = (s + 1 == nst) ? E.t_end : r.h * (double)(s + 1);
+                crossing(t);
+            }
+        } else {
+#pragma unroll 1
+            while (T.ad.t < E.t_end) {
+                if ((long long)(T.nacc + T.nrej) >= S.maxiters) {
+                    T.status = ST_MAXITERS;
+                    break;
+                }
+                bool accepted;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) us[i] = T.u[i];
+                ts0 = T.ad.t;
+                if (T.ad.attempt(S.par, T.u, E.t_end, S.tol, S.dtmin, accepted)) {
+                    T.status = ST_DOMAIN;
+                    break;
+                }
+                if (accepted) {
+                    ++T.nacc;
+                    crossing(T.ad.t);
+                } else
+                    ++T.nrej;
+            }
+        }
+    }
+    ev_count[j] = count;
+    status[j] = T.status;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) u_end[j * NV + i] = T.u[i];
+    if (nsteps) nsteps[j] = (long long)T.nacc + (long long)T.nrej;
+}
+
 // ------------------------------------------------------------------------------------------------
 // hooks
 template <int NV>

@@ -212,6 +212,23 @@ int dtwa_lyapunov(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol,
                   double t_interval, double lam_tol, double lam_reltol, int32_t maxiters, double *lambda, double *x_final,
                   int32_t *iters, int32_t *status, int64_t *nsteps, double *kernel_ms);
 
+/* ---- integrate(...; callback=ContinuousCallback(condition, affect; save_positions=(false,false)))
+ *      as the docs use it for Poincare sections (docs/src/ClassicalDickeExamples.md:82-109,180-184): n initial
+ *      conditions are integrated from 0 to t_end and every crossing of coef . u - offset = 0 is recorded
+ *      (direction 0: both, +1: increasing, -1: decreasing).  The crossing is located with one Henon step
+ *      (the event function as independent variable) of the integrator's order; the reference searches a root
+ *      of its interpolant.  ev_t[n][max_events], ev_u[n][max_events][nvar], ev_dir[n][max_events] (+1/-1),
+ *      ev_count[n] (keeps counting past max_events), u_end[n][nvar], status[n], nsteps[n] (may be NULL). ---- */
+typedef struct dtwa_event {
+    double coef[4];
+    double offset;
+    int32_t direction;
+    int32_t pad;
+} dtwa_event;
+int dtwa_integrate_events(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const double *u0, int64_t n,
+                          double t_end, const dtwa_event *ev, int32_t max_events, double *ev_t, double *ev_u, int32_t *ev_dir,
+                          int32_t *ev_count, double *u_end, int32_t *status, int64_t *nsteps, double *kernel_ms);
+
 /* ---- a8-a10: distribution.sample() / distribution.probability_density (src/TWA.jl:692-698,
  *      719-743,757-762) on the device: u[n][nvar] for trajectories offset..offset+n-1 ---- */
 int dtwa_sample(dtwa_ctx *ctx, const dtwa_sampler *smp, int64_t n, uint32_t attempt, double *u);

@@ -1171,3 +1171,249 @@ int orc_lyapunov(const orc_problem *pb, const double *u0, long n, double t_inter
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* surfaces of section.  The docs (docs/src/ClassicalDickeExamples.md:82-109) integrate
+ * with ContinuousCallback((x,t,_) -> x[4], save; save_positions=(false,false)): every zero crossing of
+ * the condition during the solve calls `save`.  DiffEqCallbacks is not in the image; the crossing is
+ * located here with Henon's trick (the event function g = coef.u - offset as independent variable, one
+ * step of the integrator's tableau of length -g from the end of the crossing step), which the library
+ * does too.  ev_t[n][cap], ev_u[n][cap][nv], ev_dir[n][cap], ev_count[n] (counts beyond cap). */
+static double ev_g(const double *coef, double offset, const double *u, int nv)
+{
+    double g = -offset;
+    for (int i = 0; i < nv; ++i) g += coef[i] * u[i];
+    return g;
+}
+static void henon_rhs(int kind, const double *par, double sg, const double *coef, const double *y, double *dy)
+{
+    int nv = orc_nvar(kind);
+    double f[4], gd = 0;
+    orc_rhs(kind, par, sg, y, f);
+    for (int i = 0; i < nv; ++i) gd += coef[i] * f[i];
+    for (int i = 0; i < nv; ++i) dy[i] = f[i] / gd;
+    dy[nv] = 1.0 / gd;
+}
+static void henon_step(int kind, const double *par, double sg, const double *coef, int rk4, double hg, double *y)
+{
+    int N = orc_nvar(kind) + 1;
+    double K[13][5], yt[5], yn[5];
+    if (rk4) {
+        henon_rhs(kind, par, sg, coef, y, K[0]);
+        for (int i = 0; i < N; ++i) yt[i] = y[i] + (hg / 2) * K[0][i];
+        henon_rhs(kind, par, sg, coef, yt, K[1]);
+        for (int i = 0; i < N; ++i) yt[i] = y[i] + (hg / 2) * K[1][i];
+        henon_rhs(kind, par, sg, coef, yt, K[2]);
+        for (int i = 0; i < N; ++i) yt[i] = y[i] + hg * K[2][i];
+        henon_rhs(kind, par, sg, coef, yt, K[3]);
+        for (int i = 0; i < N; ++i) y[i] = y[i] + (hg / 6) * (K[0][i] + 2 * K[1][i] + 2 * K[2][i] + K[3][i]);
+    } else {
+        henon_rhs(kind, par, sg, coef, y, K[0]);
+        for (int s = 1; s < 12; ++s) {
+            for (int i = 0; i < N; ++i) {
+                double dy = 0;
+                for (int j = 0; j < s; ++j) dy += DOP853_A[s][j] * K[j][i];
+                yt[i] = y[i] + dy * hg;
+            }
+            henon_rhs(kind, par, sg, coef, yt, K[s]);
+        }
+        for (int i = 0; i < N; ++i) {
+            double dy = 0;
+            for (int j = 0; j < 12; ++j) dy += DOP853_B[j] * K[j][i];
+            yn[i] = y[i] + hg * dy;
+        }
+        memcpy(y, yn, sizeof(double) * N);
+    }
+}
+
+typedef struct {
+    const orc_problem *pb;
+    const double *coef;
+    double offset, g0;
+    int direction, cap, count;
+    double *ev_t, *ev_u;
+    int *ev_dir;
+    double us[4], ts0; /* state and time at the start of the current step */
+} ev_ctx;
+
+static void ev_check(ev_ctx *c, const double *u, double t1)
+{
+    int kind = c->pb->kind, nv = orc_nvar(kind);
+    double g1 = ev_g(c->coef, c->offset, u, nv);
+    int up = c->g0 < 0 && g1 >= 0, down = c->g0 > 0 && g1 <= 0;
+    if ((up && c->direction >= 0) || (down && c->direction <= 0)) {
+        double y[5];
+        memcpy(y, u, sizeof(double) * nv);
+        y[nv] = t1;
+        if (g1 != 0) {
+            /* predictor (Henon step back from the step end), the integrator's own step from the step start
+             * to the predicted time, corrector (Henon step over the remaining, tiny g) */
+            double sgn = c->pb->backwards ? -1.0 : 1.0;
+            int rk4 = c->pb->alg == ALG_RK4;
+            henon_step(kind, c->pb->par, sgn, c->coef, rk4, -g1, y);
+            double hs = t1 - c->ts0, th = y[nv] - c->ts0, z[4];
+            if (!(th > 0) || !(th <= hs)) th = hs * (c->g0 / (c->g0 - g1));
+            double g2 = 0;
+            for (int it = 0; it < 5; ++it) {
+                memcpy(z, c->us, sizeof(double) * nv);
+                if (rk4)
+                    rk4_step(kind, c->pb->par, sgn, th, z);
+                else
+                    rk8_fixed_step(kind, c->pb->par, sgn, th, z);
+                g2 = ev_g(c->coef, c->offset, z, nv);
+                if (it == 4 || fabs(g2) <= 1e-13) break;
+                double f[4], gd = 0; /* Newton on the crossing time */
+                orc_rhs(kind, c->pb->par, sgn, z, f);
+                for (int i = 0; i < nv; ++i) gd += c->coef[i] * f[i];
+                double tn = th - g2 / gd;
+                if (!(tn > 0) || !(tn <= hs)) break;
+                th = tn;
+            }
+            memcpy(y, z, sizeof(double) * nv);
+            y[nv] = c->ts0 + th;
+            if (g2 != 0) henon_step(kind, c->pb->par, sgn, c->coef, rk4, -g2, y);
+            int fin = 1;
+            for (int i = 0; i <= nv; ++i) fin = fin && isfinite(y[i]);
+            if (!fin) {
+                memcpy(y, z, sizeof(double) * nv);
+                y[nv] = c->ts0 + th;
+            }
+        }
+        if (c->count < c->cap) {
+            c->ev_t[c->count] = y[nv];
+            memcpy(c->ev_u + (size_t)c->count * nv, y, sizeof(double) * nv);
+            c->ev_dir[c->count] = up ? 1 : -1;
+        }
+        c->count++;
+    }
+    c->g0 = g1;
+}
+
+int orc_integrate_events(const orc_problem *pb, const double *u0, long n, double t_end, const double *coef, double offset,
+                         int direction, int cap, double *ev_t, double *ev_u, int *ev_dir, int *ev_count, double *u_end,
+                         int *status, long *nsteps)
+{
+    int kind = pb->kind, nv = orc_nvar(kind);
+    double sg = pb->backwards ? -1.0 : 1.0;
+    const double *par = pb->par;
+    int nsub[1];
+    double hsub[1], ts1[1] = {t_end};
+    if (orc_step_table(ts1, 1, pb->dt > 0 ? pb->dt : 1.0, nsub, hsub)) return -1;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long ic = 0; ic < n; ++ic) {
+        double u[4];
+        memcpy(u, u0 + ic * nv, sizeof(double) * nv);
+        ev_ctx c = {pb, coef, offset, 0.0, direction, cap, 0, ev_t + (size_t)ic * cap, ev_u + (size_t)ic * cap * nv,
+                    ev_dir + (size_t)ic * cap, {0, 0, 0, 0}, 0.0};
+        int st = ST_OK;
+        long att = 0;
+        if (nonfinite(u, nv) || orc_out_of_bounds(kind, u))
+            st = ST_BAD_IC;
+        else if (t_end > 0) {
+            c.g0 = ev_g(coef, offset, u, nv);
+            if (pb->alg == ALG_RK4 || pb->alg == ALG_RK8) {
+                for (int s = 0; s < nsub[0]; ++s) {
+                    memcpy(c.us, u, sizeof(double) * nv);
+                    c.ts0 = (s == 0) ? 0.0 : hsub[0] * (double)s;
+                    int bad = (pb->alg == ALG_RK4) ? rk4_step(kind, par, sg, hsub[0], u) : rk8_fixed_step(kind, par, sg, hsub[0], u);
+                    att++;
+                    if (bad || nonfinite(u, nv) || orc_out_of_bounds(kind, u)) {
+                        st = ST_DOMAIN;
+                        break;
+                    }
+                    ev_check(&c, u, (s + 1 == nsub[0]) ? t_end : hsub[0] * (double)(s + 1));
+                }
+            } else {
+                /* the adaptive loop of orc_solve_one with a per-accepted-step hook */
+                int S = (pb->alg == ALG_DP5) ? 6 : 12, err_order = (pb->alg == ALG_DP5) ? 4 : 7;
+                double expo = -1.0 / (err_order + 1), tol = pb->tol, dtmin = pb->dtmin;
+                double K[13][4], yn[4], t = 0, h_abs;
+                int rejected = 0;
+                if (orc_rhs(kind, par, sg, u, K[0]))
+                    st = ST_DOMAIN;
+                else {
+                    h_abs = initial_step(kind, par, sg, u, K[0], t_end, err_order, tol);
+                    while (t < t_end) {
+                        if (att >= pb->maxiters) {
+                            st = ST_MAXITERS;
+                            break;
+                        }
+                        att++;
+                        int forced = 0;
+                        if (h_abs < dtmin) {
+                            h_abs = dtmin;
+                            forced = 1;
+                        }
+                        double h = h_abs;
+                        int clipped = 0;
+                        if (t + h >= t_end) {
+                            clipped = (t_end - t) < h_abs;
+                            h = t_end - t;
+                        }
+                        int bad = (pb->alg == ALG_DP5) ? rk_trial(kind, par, sg, 6, &DP5_A[0][0], 6, DP5_B, h, u, K, yn)
+                                                       : rk_trial(kind, par, sg, 12, &DOP853_A[0][0], 12, DOP853_B, h, u, K, yn);
+                        double err, sc[4];
+                        for (int i = 0; i < nv; ++i) sc[i] = tol + fmax(fabs(u[i]), fabs(yn[i])) * tol;
+                        if (pb->alg == ALG_DP5) {
+                            double e[4];
+                            for (int i = 0; i < nv; ++i) {
+                                double s = 0;
+                                for (int j = 0; j <= S; ++j) s += DP5_E[j] * K[j][i];
+                                e[i] = s * h / sc[i];
+                            }
+                            err = rms(e, nv);
+                        } else {
+                            double n5 = 0, n3 = 0;
+                            for (int i = 0; i < nv; ++i) {
+                                double s5 = 0, s3 = 0;
+                                for (int j = 0; j <= S; ++j) {
+                                    s5 += DOP853_E5[j] * K[j][i];
+                                    s3 += DOP853_E3[j] * K[j][i];
+                                }
+                                s5 /= sc[i];
+                                s3 /= sc[i];
+                                n5 += s5 * s5;
+                                n3 += s3 * s3;
+                            }
+                            err = (n5 == 0 && n3 == 0) ? 0 : fabs(h) * n5 / sqrt((n5 + 0.01 * n3) * nv);
+                        }
+                        bad = bad || nonfinite(yn, nv) || !isfinite(err) || orc_out_of_bounds(kind, yn);
+                        if (bad) {
+                            if (forced) {
+                                st = ST_DOMAIN;
+                                break;
+                            }
+                            h_abs = h * 0.2;
+                            rejected = 1;
+                            continue;
+                        }
+                        if (err < 1 || forced) {
+                            double factor = (err == 0) ? 10.0 : fmin(10.0, 0.9 * pow(err, expo));
+                            if (rejected) factor = fmin(1.0, factor);
+                            double hn = h * factor;
+                            if (clipped && hn < h_abs) hn = h_abs;
+                            h_abs = hn;
+                            memcpy(c.us, u, sizeof(double) * nv);
+                            c.ts0 = t;
+                            t = (t + h >= t_end) ? t_end : t + h;
+                            for (int i = 0; i < nv; ++i) {
+                                u[i] = yn[i];
+                                K[0][i] = K[S][i];
+                            }
+                            rejected = 0;
+                            ev_check(&c, u, t);
+                        } else {
+                            h_abs = h * fmax(0.2, 0.9 * pow(err, expo));
+                            rejected = 1;
+                        }
+                    }
+                }
+            }
+        }
+        ev_count[ic] = c.count;
+        status[ic] = st;
+        memcpy(u_end + ic * nv, u, sizeof(double) * nv);
+        if (nsteps) nsteps[ic] = att;
+    }
+    return 0;
+}

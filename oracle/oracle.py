@@ -91,6 +91,9 @@ def lib(fast: bool = False):
         L.orc_lyapunov.argtypes = [C.POINTER(Problem), dp, C.c_long, C.c_double, C.c_double, C.c_double, C.c_int,
                                    dp, dp, ip, ip, lp]
         L.orc_lyapunov.restype = C.c_int
+        L.orc_integrate_events.argtypes = [C.POINTER(Problem), dp, C.c_long, C.c_double, dp, C.c_double, C.c_int, C.c_int,
+                                           dp, dp, ip, ip, dp, ip, lp]
+        L.orc_integrate_events.restype = C.c_int
         _libs[key] = L
     return _libs[key]
 
@@ -218,6 +221,28 @@ def lyapunov(kind, par, u0, t=100.0, ltol=1e-4, lreltol=1e-3, maxiters=100, alg=
     if rc:
         raise ValueError("bad interval")
     return lam, xf, iters, status, nsteps
+
+
+def integrate_events(kind, par, u0, t_end, coef, offset=0.0, direction=0, max_events=1024, alg=ALG_DOP853, dt=0.0, tol=1e-12,
+                     dtmin=None, maxiters=10 ** 9, backwards=False, fast=False):
+    """surface-of-section crossings of coef.u - offset = 0 on [0, t_end] (docs/src/ClassicalDickeExamples.md:82-109):
+    (ev_t[n][cap], ev_u[n][cap][nv], ev_dir[n][cap], ev_count[n], u_end[n][nv], status[n], attempts[n])"""
+    nv = nvar(kind)
+    u0 = np.ascontiguousarray(u0, dtype=np.float64).reshape(-1, nv)
+    n, cap = u0.shape[0], int(max_events)
+    cf = np.zeros(4)
+    cf[:nv] = coef
+    ev_t, ev_u = np.full((n, cap), np.nan), np.full((n, cap, nv), np.nan)
+    ev_dir, cnt = np.zeros((n, cap), dtype=np.int32), np.empty(n, dtype=np.int32)
+    u_end, status, nsteps = np.empty((n, nv)), np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int64)
+    pb = make_problem(kind, par, alg, dt, tol, dtmin, maxiters, backwards)
+    ip, lp = C.POINTER(C.c_int), C.POINTER(C.c_long)
+    rc = lib(fast).orc_integrate_events(C.byref(pb), _dp(u0), n, float(t_end), _dp(cf), float(offset), int(direction), cap, _dp(ev_t),
+                                        _dp(ev_u), ev_dir.ctypes.data_as(ip), cnt.ctypes.data_as(ip), _dp(u_end),
+                                        status.ctypes.data_as(ip), nsteps.ctypes.data_as(lp))
+    if rc:
+        raise ValueError("bad t_end")
+    return ev_t, ev_u, ev_dir, cnt, u_end, status, nsteps
 
 
 def philox(ctr, key):

@@ -185,3 +185,88 @@ def test_integrate_api_with_fundamental_matrix(pkg, O):
     assert relerr(s2.fundamental_matrix[-1], Phi @ U, floor=1e-2).max() < 1e-8
     with pytest.raises(ValueError):
         CS.integrate(system, DOCS_PT, 2.0, get_fundamental_matrix=True, fundamental_matrix_initial=np.eye(3))
+
+
+# ---------------------------------------------------------------- surfaces of section
+PPAR = [1.0, 0.8, 0.8]   # docs/src/ClassicalDickeExamples.md:86  (w0, w, g)
+
+
+def test_oracle_section_crossings_lie_on_the_section_and_on_the_energy_shell(O):
+    u0 = np.array([[1.0, 0.5, 0.2, 0.0], [0.7, -0.3, 0.1, 0.2]])
+    et, eu, ed, cnt, ue, st, ns = O.integrate_events(O.SYS_DICKE, PPAR, u0, 60.0, [0, 0, 0, 1], tol=1e-12, max_events=64)
+    assert (st == 0).all() and (cnt >= 8).all()
+    for i in range(2):
+        k = cnt[i]
+        assert np.abs(eu[i, :k, 3]).max() < 1e-13                       # Henon step: g = 0 to rounding
+        assert (np.diff(et[i, :k]) > 0).all() and (ed[i, :k][1:] * ed[i, :k][:-1] == -1).all()   # alternate up/down
+        h = O.hamiltonian(O.SYS_DICKE, PPAR, eu[i, :k])
+        assert np.abs(h - O.hamiltonian(O.SYS_DICKE, PPAR, u0[i:i + 1])[0]).max() < 1e-9
+        # the crossing states are states of the trajectory: integrate to the event times and compare
+        out, s2, _, _ = O.integrate(O.SYS_DICKE, PPAR, u0[i:i + 1], et[i, :k], tol=1e-12)
+        early = et[i, :k] < 15
+        assert np.abs(out[0] - eu[i, :k])[early].max() < 1e-9 and np.abs(out[0] - eu[i, :k]).max() < 1e-5   # (chaos amplifies late)
+    # direction filter and an offset section (q = 0.25, increasing only)
+    et2, eu2, ed2, cnt2, *_ = O.integrate_events(O.SYS_DICKE, PPAR, u0, 60.0, [0, 1, 0, 0], offset=0.25, direction=1, tol=1e-12, max_events=64)
+    assert cnt2.sum() >= 4
+    for i in range(2):
+        if cnt2[i]:
+            assert (ed2[i, :cnt2[i]] == 1).all() and np.abs(eu2[i, :cnt2[i], 1] - 0.25).max() < 1e-13
+    # capacity: counting continues, storage stops
+    et3, eu3, ed3, cnt3, *_ = O.integrate_events(O.SYS_DICKE, PPAR, u0, 60.0, [0, 0, 0, 1], tol=1e-12, max_events=3)
+    assert np.array_equal(cnt3, cnt) and np.allclose(et3, et[:, :3])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alg,kw", [("RK4", dict(dt=2.0 ** -7)), ("RK8", dict(dt=2.0 ** -4)), ("DOP853", dict(tol=1e-11)), ("DP5", dict(tol=1e-11))])
+def test_gpu_section_crossings_match_oracle(ctx, pkg, O, alg, kw):
+    rng = np.random.default_rng(3)
+    u0 = np.column_stack([rng.uniform(-1, 1, 33), rng.uniform(-1, 1, 33), rng.uniform(-0.8, 0.8, 33), rng.uniform(-1, 1, 33)])
+    code, ocode = getattr(pkg._lib, "ALG_" + alg), getattr(O, "ALG_" + alg)
+    for coef, offset, direction in (([0, 0, 0, 1], 0.0, 0), ([0, 1, 0, 0], 0.25, 1), ([1, 0, -0.5, 0], 0.1, -1)):
+        tg, ug, dg, cg, eg, sg, ng, ms = ctx.integrate_events(csys(pkg, 0, PPAR), csol(pkg, code, **kw), u0, 12.0, coef, offset, direction, 32)
+        to, uo, do, co, eo, so, no = O.integrate_events(O.SYS_DICKE, PPAR, u0, 12.0, coef, offset, direction, 32, alg=ocode, **kw)
+        assert np.array_equal(sg, so) and np.array_equal(cg, co) and np.array_equal(dg, do)
+        assert cg.max() <= 32 and cg.sum() > 15
+        m = ~np.isnan(to)
+        assert np.array_equal(m, ~np.isnan(tg))
+        tol_ev = 1e-9 if alg in ("RK4", "RK8") else 2e-8   # adaptive: the step sequences differ at rounding level (float step factor)
+        assert np.abs(tg[m] - to[m]).max() < tol_ev and np.abs(ug[m] - uo[m]).max() < tol_ev
+        assert relerr(eg, eo).max() < 1e-9
+        g = ug[m] @ np.array(coef, float) - offset
+        assert np.abs(g).max() < 1e-13
+    # LMG: P = 0 section of closed orbits -> crossings repeat with the orbit's period
+    v0 = np.array([[0.5, 0.3], [1.2, -0.6]])
+    tg, ug, dg, cg, *_ = ctx.integrate_events(csys(pkg, 1, LPAR), csol(pkg, code, **kw), v0, 40.0, [0, 1], 0.0, 1, 64)
+    to, uo, do, co, *_ = O.integrate_events(O.SYS_LMG, LPAR, v0, 40.0, [0, 1], 0.0, 1, 64, alg=ocode, **kw)
+    assert np.array_equal(cg, co) and (cg >= 3).all()
+    for i in range(2):
+        per = np.diff(tg[i, :cg[i]])
+        assert np.abs(per - per[0]).max() < 1e-5 and np.abs(ug[i, :cg[i], 0] - ug[i, 0, 0]).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_integrate_with_continuous_callback_like_the_docs(pkg, O):
+    """docs/src/ClassicalDickeExamples.md:82-109: save (Q, P) whenever p = 0 and q is the q+ root"""
+    from dickemodel_jl_b200 import ClassicalDicke as CD, ClassicalSystems as CS
+    system = CD.ClassicalDickeSystem(w=0.8, g=0.8, w0=1)
+    eps = -1.35
+    pts = []
+
+    def save(state):
+        if CD.q_sign(system, state.u, eps) == "+":
+            Q, q, P, p = state.u
+            pts.append((Q, P, state.t))
+    cb = CS.ContinuousCallback(lambda x, t, _: x[3], save, save_positions=(False, False), abstol=1e-3)
+    Q0 = 0.5 * (CD.minimum_nonnegative_Q_for_ϵ(system, eps) + CD.maximum_Q_for_ϵ(system, eps))
+    u0 = CD.Point(system, ϵ=eps, P=0, p=0, Q=Q0)
+    sol = CS.integrate(system, u0, 200.0, callback=cb, save_everystep=False, tol=1e-10)
+    assert sol.retcode == "Success" and len(pts) > 10
+    et, eu, ed, cnt, ue, st, ns = O.integrate_events(O.SYS_DICKE, [1.0, 0.8, 0.8], [u0], 200.0, [0, 0, 0, 1], tol=1e-10, max_events=4096)
+    want = [(eu[0, k, 0], eu[0, k, 2], et[0, k]) for k in range(cnt[0]) if CD.q_sign(system, eu[0, k], eps) == "+"]
+    assert len(want) == len(pts)
+    assert np.abs(np.array(want) - np.array(pts)).max() < 1e-6
+    assert relerr(sol.u[-1], ue[0]).max() < 1e-6
+    with pytest.raises(NotImplementedError, match="affine"):
+        CS.integrate(system, u0, 1.0, callback=CS.ContinuousCallback(lambda x, t, _: x[3] ** 2 - 1, save))
+    res = CS.poincare_section_batch(system, np.array([u0, u0]), 50.0, coef=[0, 0, 0, 1], tol=1e-10, max_events=8)
+    assert np.array_equal(res["count"], [res["count"][0]] * 2) and np.array_equal(res["t"][0], res["t"][1], equal_nan=True)
