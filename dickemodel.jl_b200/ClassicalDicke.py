@@ -64,6 +64,25 @@ def hamiltonian(system: DickeSystem):
     return H
 
 
+def energy_shell_volume(system, ϵ):
+    """src/ClassicalDicke.jl:110-124 (the reference integrates Pmax(Q) with QuadGK; here Gauss-Legendre on the
+    substitution Q = Qmin + (Qmax-Qmin) sin^2(t), which removes the square-root end-point singularities)"""
+    w0, w, g = system.parameters()
+    if ϵ <= minimum_energy(system):
+        return 0.0
+    if ϵ >= w0:
+        return 8 * math.pi ** 2 / w
+    a, b = minimum_nonnegative_Q_for_ϵ(system, ϵ), maximum_Q_for_ϵ(system, ϵ)
+    import numpy as np
+    x, wt = np.polynomial.legendre.leggauss(200)
+    t = (x + 1) * math.pi / 4
+    Q = a + (b - a) * np.sin(t) ** 2
+    arg = (w * (2 * ϵ + 2 * w0) - Q ** 2 * ((-4 + Q ** 2) * g ** 2 + w * w0)) / (Q ** 2 * g ** 2 + w * w0)
+    Pmax = np.sqrt(np.maximum(arg, 0.0))
+    integral = float(np.sum(wt * Pmax * (b - a) * np.sin(2 * t)) * math.pi / 4)
+    return integral * 2 * math.pi * 4 / w
+
+
 def normal_frequency(system, sgn="+"):
     w0, w, g = system.parameters()
     gc = math.sqrt(w0 * w) / 2

@@ -28,7 +28,8 @@ AXIS_EXPR, AXIS_TIME = 0, 1
 EXPORTS = ["dtwa_last_error", "dtwa_version", "dtwa_create", "dtwa_destroy", "dtwa_device_info", "dtwa_set_launch",
            "dtwa_hamiltonian", "dtwa_integrate", "dtwa_sample", "dtwa_pdf", "dtwa_eval_expr", "dtwa_scale_to_index",
            "dtwa_ensemble", "dtwa_ensemble_launch", "dtwa_plan_arenas", "dtwa_plan_fetch", "dtwa_plan_free",
-           "dtwa_fp64_peak", "dtwa_fp64_peak_regs", "dtwa_set_jit", "dtwa_jit_compile", "dtwa_integrate_fm", "dtwa_lyapunov", "dtwa_integrate_events"]
+           "dtwa_fp64_peak", "dtwa_fp64_peak_regs", "dtwa_set_jit", "dtwa_jit_compile", "dtwa_integrate_fm", "dtwa_lyapunov", "dtwa_integrate_events",
+           "dtwa_shell_quadrature"]
 
 
 class Event(C.Structure):
@@ -123,6 +124,8 @@ def load():
         L.dtwa_integrate_fm.argtypes = [vp, C.POINTER(System), C.POINTER(Solver), dp, dp, C.c_int64, dp, C.c_int32, dp, dp, i32p, i64p]
         L.dtwa_integrate_events.argtypes = [vp, C.POINTER(System), C.POINTER(Solver), dp, C.c_int64, C.c_double, C.POINTER(Event),
                                             C.c_int32, dp, dp, i32p, i32p, dp, i32p, i64p, dp]
+        L.dtwa_shell_quadrature.argtypes = [vp, C.POINTER(System), C.c_double, dp, C.c_int64, C.POINTER(C.c_char_p), C.c_int32, C.c_double,
+                                            C.c_int32, dp, i32p, i32p, dp]
         L.dtwa_lyapunov.argtypes = [vp, C.POINTER(System), C.POINTER(Solver), dp, C.c_int64, C.c_double, C.c_double, C.c_double,
                                     C.c_int32, dp, dp, i32p, i32p, i64p, dp]
         L.dtwa_set_jit.argtypes = [vp, C.c_int]
@@ -256,6 +259,20 @@ class Context:
         ev_u[~valid] = np.nan
         ev_dir[~valid] = 0
         return ev_t, ev_u, ev_dir, cnt, u_end, status, nsteps, ms.value
+
+    def shell_quadrature(self, sys: System, eps, QP, exprs, p_res=0.01, onlyqroot=0):
+        """(out[ncell][nexpr] (NaN = outside the shell), valid[ncell], nodes[ncell], kernel_ms)"""
+        QP = np.ascontiguousarray(QP, dtype=np.float64).reshape(-1, 2)
+        n = QP.shape[0]
+        ex = [e.encode("utf-8") for e in exprs]
+        arr = (C.c_char_p * len(ex))(*ex)
+        out = np.empty((n, len(ex)))
+        valid, nodes = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+        ms = C.c_double()
+        i32p = C.POINTER(C.c_int32)
+        _check(load().dtwa_shell_quadrature(self._h, C.byref(sys), float(eps), _dp(QP), n, arr, len(ex), float(p_res), int(onlyqroot),
+                                            _dp(out), valid.ctypes.data_as(i32p), nodes.ctypes.data_as(i32p), C.byref(ms)))
+        return out, valid, nodes, ms.value
 
     def lyapunov(self, sys: System, sol: Solver, u0, t, ltol, lreltol, maxiters):
         """(lambda[n][nv], x_final[n][nv], iters[n], status[n], nsteps[n], kernel_ms)"""

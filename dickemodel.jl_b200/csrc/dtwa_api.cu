@@ -795,6 +795,79 @@ extern "C" int dtwa_integrate_events(dtwa_ctx *ctx, const dtwa_system *sys, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// energy-shell quadrature (src/EnergyShellProjections.jl:49-96) for classical expressions
+extern "C" int dtwa_shell_quadrature(dtwa_ctx *ctx, const dtwa_system *sys, double eps, const double *QP, int64_t ncell,
+                                     const char *const *exprs, int32_t nexpr, double p_res, int32_t onlyqroot, double *out,
+                                     int32_t *valid, int32_t *nodes, double *kernel_ms)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    TRY(check_system(sys));
+    if (sys->kind != DTWA_SYS_DICKE) return set_err(DTWA_ERR_INVALID, "the energy-shell quadrature is defined for the Dicke model");
+    if (ncell < 0 || (ncell > 0 && (!QP || !out || !valid))) return set_err(DTWA_ERR_INVALID, "bad buffers");
+    if (!exprs || nexpr < 1 || nexpr > SHELL_MAX_EXPR) return set_err(DTWA_ERR_INVALID, "between 1 and 8 expressions are required");
+    if (!(p_res > 0)) return set_err(DTWA_ERR_INVALID, "p_res must be > 0");
+    if (onlyqroot < -1 || onlyqroot > 1) return set_err(DTWA_ERR_INVALID, "onlyqroot must be -1, 0 or +1");
+    Program prog;
+    std::vector<int32_t> offs;
+    try {
+        auto vars = varnames_of(sys->kind);
+        for (int e = 0; e < nexpr; ++e) {
+            if (!exprs[e]) return set_err(DTWA_ERR_INVALID, "NULL expression");
+            offs.push_back((int32_t)prog.ins.size());
+            ExprCompiler c(vars);
+            c.compile(exprs[e], prog);
+            prog.emit(OP_STORE);
+            prog.emit(OP_END);
+        }
+    } catch (const std::exception &e) {
+        return set_err(DTWA_ERR_EXPR, e.what());
+    }
+    if (prog.max_depth > VM_STACK) return set_err(DTWA_ERR_EXPR, "expression too deeply nested for the VM stack");
+    if (ncell == 0) return DTWA_OK;
+    if (prog.consts.empty()) prog.consts.push_back(0.0);
+    DevCtx &d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    const size_t cb = (sizeof(double) * prog.consts.size() + 15) & ~size_t(15), pb = (sizeof(VmIns) * prog.ins.size() + 15) & ~size_t(15);
+    const size_t ob = sizeof(int32_t) * offs.size();
+    TRY(d.meta.ensure(cb + pb + ob));
+    TRY(d.u0.ensure(sizeof(double) * 2 * ncell));
+    TRY(d.scratch_a.ensure(sizeof(double) * ncell * nexpr));
+    TRY(d.scratch_b.ensure(2 * sizeof(int32_t) * ncell));
+    unsigned char *meta = (unsigned char *)d.meta.p;
+    CK(cudaMemcpyAsync(meta, prog.consts.data(), sizeof(double) * prog.consts.size(), cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(meta + cb, prog.ins.data(), sizeof(VmIns) * prog.ins.size(), cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(meta + cb + pb, offs.data(), ob, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(d.u0.p, QP, sizeof(double) * 2 * ncell, cudaMemcpyHostToDevice, d.stream));
+    ShellArgs A;
+    A.w0 = sys->params[0];
+    A.w = sys->params[1];
+    A.g = sys->params[2];
+    A.eps = eps;
+    A.p_res = p_res;
+    A.onlyqroot = onlyqroot;
+    A.nexpr = nexpr;
+    A.consts = (const double *)meta;
+    A.prog = (const VmIns *)(meta + cb);
+    A.prog_off = (const int32_t *)(meta + cb + pb);
+    int32_t *d_valid = (int32_t *)d.scratch_b.p, *d_nodes = d_valid + ncell;
+    CK(cudaEventRecord(d.ev[0], d.stream));
+    shell_quadrature_kernel<<<blocks_for(ncell * 32, 128), 128, 0, d.stream>>>(A, (const double *)d.u0.p, ncell, (double *)d.scratch_a.p,
+                                                                              d_valid, d_nodes);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(d.ev[3], d.stream));
+    CK(cudaMemcpyAsync(out, d.scratch_a.p, sizeof(double) * ncell * nexpr, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(valid, d_valid, sizeof(int32_t) * ncell, cudaMemcpyDeviceToHost, d.stream));
+    if (nodes) CK(cudaMemcpyAsync(nodes, d_nodes, sizeof(int32_t) * ncell, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    if (kernel_ms) {
+        float m = 0.f;
+        CK(cudaEventElapsedTime(&m, d.ev[0], d.ev[3]));
+        *kernel_ms = m;
+    }
+    return DTWA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // a13-a20: the ensemble
 struct RedLayout {
     int kind = 0;
@@ -1008,7 +1081,12 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
 
     // ---- which kernel: the interpreter, or a run-time specialisation of it for this reducer set ----
     const void *kern = interpreter_kernel(sys->kind, sol->alg);
-    const bool want_jit = ctx->jit_mode == 1 || (ctx->jit_mode == 2 && (double)N * (double)nt >= 2e9);
+    // auto mode: specialise when the estimated work repays ~1 s of NVRTC.  Fixed step: the reducers run N * nt times.
+    // Adaptive: lanes reach their output times out of step, so the reducer code runs (partially masked) in most
+    // iterations of the step loop -- count attempted steps instead, ~8 per unit time as a floor.
+    double jit_work = (double)N * (double)nt;
+    if (!fixed) jit_work = std::max(jit_work, (double)N * 8.0 * ts[nt - 1]);
+    const bool want_jit = ctx->jit_mode == 1 || (ctx->jit_mode == 2 && jit_work >= 2e9);
     if (want_jit) {
         cudaKernel_t jk;
         std::string jerr;

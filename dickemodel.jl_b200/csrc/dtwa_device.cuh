@@ -44,6 +44,22 @@ __device__ __forceinline__ void rsqrt_sqrt_pair(double x, double &is, double &s)
     s = fma(t, ep, t);
 }
 
+// 1/x for the error norms of the step controllers: MUFU.RCP64H seed + one Newton step, relative error
+// ~1e-13 (the accept/reject threshold err < 1 does not need more), 2 FP64 instructions instead of ~9.
+__device__ __forceinline__ double rcp_fast(double x)
+{
+    double y0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    return fma(y0, fma(-x, y0, 1.0), y0);
+}
+// sqrt(x) for x >= 0 through the same polished rsqrt (0 stays 0)
+__device__ __forceinline__ double sqrt_fast(double x)
+{
+    double is, s;
+    rsqrt_sqrt_pair(x, is, s);
+    return x > 0.0 ? s : 0.0;
+}
+
 template <int SYS>
 struct Sys;
 
@@ -69,8 +85,15 @@ struct Sys<DTWA_SYS_DICKE> {
         du[0] = __dmul_rn(-P, e);                 // P w0 - g P q Q / s
         if constexpr (FOLDQ)
             du[1] = pp;
-        else
+        else {
+#if defined(DTWA_W_IS_ONE)
+            du[1] = pp;
+#elif defined(DTWA_W_IS_MINUS_ONE)
+            du[1] = -pp;
+#else
             du[1] = __dmul_rn(pp, p.b);           // p w
+#endif
+        }
         const double gqs = __dmul_rn(gq, s);
         du[2] = fma(Q, e, -gqs);                  // g q Q^2/s - g q s - Q w0
         const double Qs = __dmul_rn(Q, s);
@@ -254,7 +277,7 @@ __device__ __forceinline__ double group_rms(const double (&x)[Sys<SYS>::NV])
     for (int i = 0; i < Sys<SYS>::NV; ++i)
         if (norm_counted<SYS>(i)) s = fma(x[i], x[i], s);
     s = group_sum<SYS>(s);
-    return sqrt(s) / sqrt((double)Sys<SYS>::NORM_N);
+    return sqrt_fast(s * (1.0 / (double)Sys<SYS>::NORM_N));
 }
 
 template <int SYS>
@@ -460,7 +483,7 @@ struct Adaptive {
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const double sc = fma(fmax(fabs(y[i]), fabs(ynew[i])), tol, tol);
-                en[i] = e5[i] * h / sc;
+                en[i] = e5[i] * h * rcp_fast(sc);
                 yn[i] = ynew[i];
                 kn[i] = DP5_KNEW[i];
             }
@@ -471,7 +494,7 @@ struct Adaptive {
             double n5 = 0.0, n3 = 0.0;
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
-                const double isc = 1.0 / fma(fmax(fabs(y[i]), fabs(ynew[i])), tol, tol);  // one division for both estimators
+                const double isc = rcp_fast(fma(fmax(fabs(y[i]), fabs(ynew[i])), tol, tol));  // one reciprocal for both estimators
                 const double a5 = e5[i] * isc, a3 = e3[i] * isc;
                 if (norm_counted<SYS>(i)) {
                     n5 = fma(a5, a5, n5);
@@ -484,8 +507,11 @@ struct Adaptive {
             n3 = group_sum<SYS>(n3);
             if (n5 == 0.0 && n3 == 0.0)
                 err = 0.0;
-            else
-                err = fabs(h) * n5 / sqrt(fma(0.01, n3, n5) * (double)Sys<SYS>::NORM_N);
+            else {
+                double is, sq;
+                rsqrt_sqrt_pair(fma(0.01, n3, n5) * (double)Sys<SYS>::NORM_N, is, sq);
+                err = fabs(h) * n5 * is;
+            }
 #undef DOP853_KNEW
         }
         const bool bad = state_bad<SYS>(yn) || !(err == err) || isinf(err);

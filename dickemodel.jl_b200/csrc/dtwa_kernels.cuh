@@ -915,6 +915,82 @@ __global__ void __launch_bounds__(128) events_kernel(const SolverArgs S, const E
     if (nsteps) nsteps[j] = (long long)T.nacc + (long long)T.nrej;
 }
 
+// K8: energy-shell quadrature -- SURVEY 8f rank 4, src/EnergyShellProjections.jl:49-96 (the double integral of
+// f(x) delta(h_cl(x) - eps) over q and p by Chebyshev-Gauss quadrature in p, Eq. (8) of Pilatowsky-Cameo et al.,
+// Nat. Commun. 2021).  One warp per (Q, P) cell; the lanes stride over the 2 n (or n) nodes, evaluate the
+// nexpr classical expressions with the observable VM at [Q, q_+-(Q,P,p,eps), P, p] and the warp reduces.
+//   out[ncell][nexpr] (NaN where the reference returns `nonvalue`), valid[ncell], nodes[ncell]
+struct ShellArgs {
+    double w0, w, g, eps, p_res;
+    int32_t onlyqroot;   // 0: both roots of q, +1 / -1: only q_+ / q_-
+    int32_t nexpr;
+    const VmIns *prog;   // nexpr programs `<expr> STORE END`, back to back
+    const int32_t *prog_off;
+    const double *consts;
+};
+constexpr int SHELL_MAX_EXPR = 8;
+__global__ void __launch_bounds__(128) shell_quadrature_kernel(const ShellArgs A, const double *__restrict__ QP, long long ncell,
+                                                               double *__restrict__ out, int32_t *__restrict__ valid,
+                                                               int32_t *__restrict__ nodes)
+{
+    const long long cell = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (cell >= ncell) return;
+    const double Q = QP[2 * cell], P = QP[2 * cell + 1];
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    const double R = Q * Q + P * P, r = 1.0 - R / 4.0;
+    // src/EnergyShellProjections.jl:57-72
+    const double Aq = 4.0 * A.g * A.g * (Q * Q) * r - A.w * A.w0 * (P * P + Q * Q - 2.0) + 2.0 * A.w * A.eps;
+    const double pplus = sqrt(Aq) / A.w - 1e-10;
+    const bool ok = !(R > 4.0) && !(Aq < 0.0) && !(pplus < 0.0);
+    if (!ok) {
+        if (lane == 0) {
+            for (int e = 0; e < A.nexpr; ++e) out[cell * A.nexpr + e] = qnan;
+            valid[cell] = 0;
+            nodes[cell] = 0;
+        }
+        return;
+    }
+    const int n = (int)(2.0 * floor(pplus / A.p_res) + 1.0);
+    const int nroots = A.onlyqroot == 0 ? 2 : 1;
+    const double wgt = DTWA_PI / ((double)n * A.w);
+    const double sr = sqrt(r);
+    double acc[SHELL_MAX_EXPR];
+#pragma unroll
+    for (int e = 0; e < SHELL_MAX_EXPR; ++e) acc[e] = 0.0;
+    VmShared V = {};
+    V.consts = A.consts;
+    V.window = 1;
+    for (int idx = lane; idx < n * nroots; idx += 32) {
+        const int root = idx / n, k = idx - root * n + 1;
+        const double sgn = (A.onlyqroot != 0) ? (double)A.onlyqroot : (root == 0 ? 1.0 : -1.0);
+        const double p = pplus * cos(DTWA_PI * (double)(2 * k - 1) / (double)(2 * n));
+        // q_of_eps, src/ClassicalDicke.jl:224-228,255-273
+        const double disc = 4.0 * A.g * A.g * (Q * Q) * r - (p * p) * (A.w * A.w) - A.w * A.w0 * (P * P + Q * Q - 2.0) + 2.0 * A.w * A.eps;
+        const double q = (-2.0 * A.g * Q * sr + sgn * sqrt(disc)) / A.w;   // disc < 0 -> NaN (the reference raises)
+#pragma unroll 1
+        for (int e = 0; e < A.nexpr; ++e) {
+            V.prog = A.prog + A.prog_off[e];
+            double v = 0.0;
+            vm_run<4, false>(V, nullptr, nullptr, Q, q, P, p, true, 0, 0, &v);
+            acc[e] += wgt * v;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < SHELL_MAX_EXPR; ++e) {
+        if (e < A.nexpr) {
+            double sum = acc[e];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, off));
+            if (lane == 0) out[cell * A.nexpr + e] = sum;
+        }
+    }
+    if (lane == 0) {
+        valid[cell] = 1;
+        nodes[cell] = n * nroots;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // hooks
 template <int NV>

@@ -366,4 +366,78 @@ survival_probability(system; distribution, N::Integer, ts::AbstractArray{<:Real}
 calculate_distribution(system; x, N::Integer, animate::Bool=false, xs=nothing, y=nothing, ts=nothing, ys=nothing, distribution, kargs...) =
     monte_carlo_integrate(system, mcs_for_distributions(system; x=x, y=y, ts=ts, xs=xs, ys=ys, N=N, distribution=distribution, animate=animate); kargs...)
 
+# ---- SURVEY 8f ranks 2-4: fundamental matrix, Lyapunov spectra, surfaces of section, energy-shell quadrature ----
+# integrate(...; get_fundamental_matrix=true) (src/ClassicalSystems.jl:110-128): returns (x(t), Φ(t)) at saveat times
+function integrate_with_fundamental_matrix(system::ClassicalSystem, u₀::AbstractVector{<:Real}, t::Real; t₀::Real=0.0,
+                                           saveat=nothing, fundamental_matrix_initial=nothing, kargs...)
+    nv = length(varnames(system))
+    ts = saveat === nothing ? [Float64(t₀), Float64(t)] : collect(Float64, saveat)
+    rel = ts .- t₀
+    xs = Array{Float64}(undef, nv, length(ts)); Φs = Array{Float64}(undef, nv, nv, length(ts))   # column-major == the C layout
+    fm0 = fundamental_matrix_initial === nothing ? C_NULL : pointer(Matrix{Float64}(fundamental_matrix_initial))
+    status = Ref{Int32}(0); nsteps = Ref{Int64}(0); u0 = Float64.(u₀)
+    sys = Ref(csystem(system)); sol = Ref(csolver(; kargs...))
+    GC.@preserve u0 rel xs Φs fundamental_matrix_initial begin
+        check(ccall((:dtwa_integrate_fm, libdicketwa), Cint,
+                    (Ptr{Cvoid}, Ref{CSystem}, Ref{CSolver}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int32,
+                     Ptr{Float64}, Ptr{Float64}, Ref{Int32}, Ref{Int64}),
+                    context().handle, sys, sol, u0, fm0, 1, rel, length(ts), xs, Φs, status, nsteps))
+    end
+    return [(xs[:, k], Φs[:, :, k]) for k in 1:length(ts)]
+end
+
+# lyapunov_spectrum (src/ClassicalSystems.jl:183-224); `x` may be a matrix nvar × n: one launch for a whole map
+function lyapunov_spectrum(system::ClassicalSystem, x::AbstractVecOrMat{<:Real}, t::Real=100; λtol::Real=1e-4, λreltol::Real=1e-3,
+                           maxiters::Integer=100, verbose::Bool=true, kargs...)
+    nv = length(varnames(system)); X = Matrix{Float64}(reshape(x, nv, :)); n = size(X, 2)
+    λ = Array{Float64}(undef, nv, n); iters = Vector{Int32}(undef, n); status = Vector{Int32}(undef, n)
+    sys = Ref(csystem(system)); sol = Ref(csolver(; kargs...))
+    GC.@preserve X λ iters status begin
+        check(ccall((:dtwa_lyapunov, libdicketwa), Cint,
+                    (Ptr{Cvoid}, Ref{CSystem}, Ref{CSolver}, Ptr{Float64}, Int64, Float64, Float64, Float64, Int32,
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Ptr{Float64}),
+                    context().handle, sys, sol, X, n, t, λtol, λreltol, maxiters, λ, C_NULL, iters, status, C_NULL, C_NULL))
+    end
+    any(status .== 5) && x isa AbstractVector && error("Maximum iterations")
+    return x isa AbstractVector ? λ[:, 1] : λ
+end
+lyapunov_exponent(system::ClassicalSystem, x::AbstractVector{<:Real}, t::Real=100; kargs...) = maximum(lyapunov_spectrum(system, x, t; kargs...))
+
+# integrate(...; callback=ContinuousCallback((x,t,_)->coef⋅x-offset, affect!; save_positions=(false,false)))
+# (docs/src/ClassicalDickeExamples.md:82-109): all crossings found on the GPU, `affect!` called afterwards in time order
+struct CEvent; coef::NTuple{4,Float64}; offset::Float64; direction::Int32; pad::Int32; end
+function section_crossings(system::ClassicalSystem, u₀::AbstractVector{<:Real}, t::Real; coef::AbstractVector{<:Real}, offset::Real=0.0,
+                           direction::Integer=0, max_events::Integer=65536, kargs...)
+    nv = length(varnames(system)); cf = zeros(4); cf[1:nv] .= coef
+    ev = Ref(CEvent(Tuple(cf), offset, direction, 0))
+    et = Vector{Float64}(undef, max_events); eu = Array{Float64}(undef, nv, max_events); ed = Vector{Int32}(undef, max_events)
+    cnt = Ref{Int32}(0); uend = Vector{Float64}(undef, nv); status = Ref{Int32}(0); u0 = Float64.(u₀)
+    sys = Ref(csystem(system)); sol = Ref(csolver(; kargs...))
+    GC.@preserve u0 et eu ed uend begin
+        check(ccall((:dtwa_integrate_events, libdicketwa), Cint,
+                    (Ptr{Cvoid}, Ref{CSystem}, Ref{CSolver}, Ptr{Float64}, Int64, Float64, Ref{CEvent}, Int32, Ptr{Float64}, Ptr{Float64},
+                     Ptr{Int32}, Ref{Int32}, Ptr{Float64}, Ref{Int32}, Ptr{Int64}, Ptr{Float64}),
+                    context().handle, sys, sol, u0, 1, t, ev, max_events, et, eu, ed, cnt, uend, status, C_NULL, C_NULL))
+    end
+    k = min(cnt[], max_events)
+    return et[1:k], [eu[:, i] for i in 1:k], ed[1:k], uend
+end
+
+# EnergyShellProjections.∫∫dqdpδϵ / matrix_QP∫∫dqdpδϵ (src/EnergyShellProjections.jl:49-96,159-199) for classical f
+function ∫∫dqdpδϵ(system::ClassicalDickeSystem; ϵ::Real, Q, P, f, p_res::Real=0.01, nonvalue=NaN, onlyqroot=nothing)
+    QP = Matrix{Float64}(vcat(reshape(collect(Float64, Q), 1, :), reshape(collect(Float64, P), 1, :))); n = size(QP, 2)
+    exprs = f isa AbstractVector ? [expression_string(system, g) for g in f] : [expression_string(system, f)]
+    out = Array{Float64}(undef, length(exprs), n); valid = Vector{Int32}(undef, n)
+    root = onlyqroot === nothing ? 0 : (onlyqroot === (+) ? 1 : -1)
+    sys = Ref(csystem(system))
+    GC.@preserve QP exprs out valid begin
+        check(ccall((:dtwa_shell_quadrature, libdicketwa), Cint,
+                    (Ptr{Cvoid}, Ref{CSystem}, Float64, Ptr{Float64}, Int64, Ptr{Cstring}, Int32, Float64, Int32, Ptr{Float64},
+                     Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
+                    context().handle, sys, ϵ, QP, n, pointer.(exprs), length(exprs), p_res, root, out, valid, C_NULL, C_NULL))
+    end
+    res = [valid[i] == 1 ? (f isa AbstractVector ? out[:, i] : out[1, i]) : nonvalue for i in 1:n]
+    return Q isa Real ? res[1] : res
+end
+
 end # module

@@ -229,6 +229,15 @@ int dtwa_integrate_events(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solv
                           double t_end, const dtwa_event *ev, int32_t max_events, double *ev_t, double *ev_u, int32_t *ev_dir,
                           int32_t *ev_count, double *u_end, int32_t *status, int64_t *nsteps, double *kernel_ms);
 
+/* ---- EnergyShellProjections.∫∫dqdpδϵ (src/EnergyShellProjections.jl:49-96) for ncell cells
+ *      (Q, P) at once (matrix_QP∫∫dqdpδϵ :159-199, energy_shell_average :476-508) and classical functions f
+ *      given as 1..8 expressions over Q,q,P,p: out[ncell][nexpr] = sum over the roots q_+- and the n =
+ *      2 floor(p_+/p_res) + 1 Chebyshev-Gauss nodes of (pi/(n w)) f([Q, q, P, p]); NaN and valid = 0 where the
+ *      reference returns `nonvalue`.  onlyqroot: 0 both, +1, -1.  nodes[ncell] (may be NULL). ---- */
+int dtwa_shell_quadrature(dtwa_ctx *ctx, const dtwa_system *sys, double eps, const double *QP, int64_t ncell,
+                          const char *const *exprs, int32_t nexpr, double p_res, int32_t onlyqroot, double *out,
+                          int32_t *valid, int32_t *nodes, double *kernel_ms);
+
 /* ---- a8-a10: distribution.sample() / distribution.probability_density (src/TWA.jl:692-698,
  *      719-743,757-762) on the device: u[n][nvar] for trajectories offset..offset+n-1 ---- */
 int dtwa_sample(dtwa_ctx *ctx, const dtwa_sampler *smp, int64_t n, uint32_t attempt, double *u);

@@ -245,6 +245,35 @@ def integrate_events(kind, par, u0, t_end, coef, offset=0.0, direction=0, max_ev
     return ev_t, ev_u, ev_dir, cnt, u_end, status, nsteps
 
 
+def shell_quadrature(par, eps, Q, P, exprs, p_res=0.01, onlyqroot=0):
+    """∫∫dqdpδϵ, src/EnergyShellProjections.jl:49-96, statement for statement (sequential sums): returns the list of
+    values for `exprs` (expression strings over Q,q,P,p) or None where the reference returns `nonvalue`."""
+    w0, w, g = par
+    if Q ** 2 + P ** 2 > 4:
+        return None
+    A = (4 * g ** 2 * Q ** 2 * (1 - (Q ** 2 + P ** 2) / 4) - w * w0 * (P ** 2 + Q ** 2 - 2) + 2 * w * eps)
+    if A < 0:
+        return None
+    pp = math.sqrt(A) / w - 1e-10
+    if pp < 0:
+        return None
+    n = int(2 * math.floor(pp / p_res) + 1)
+    val = None
+    for sgn in (+1, -1):
+        if onlyqroot not in (0, None) and onlyqroot != sgn:
+            continue
+        k = np.arange(1, n + 1)
+        p = pp * np.cos(math.pi * (2 * k - 1) / (2 * n))
+        r = 1 - (Q ** 2 + P ** 2) / 4
+        disc = 4 * g ** 2 * Q ** 2 * r - p ** 2 * w ** 2 - w * w0 * (P ** 2 + Q ** 2 - 2) + 2 * w * eps   # src/ClassicalDicke.jl:224-228
+        q = (-2 * g * Q * math.sqrt(r) + sgn * np.sqrt(disc)) / w                                        # :271-272
+        X = np.column_stack([np.full(n, Q), q, np.full(n, P), p])
+        for kk in range(n):
+            mv = [(math.pi / (n * w)) * float(eval_expr(e, ["Q", "q", "P", "p"], X[kk])) for e in exprs]
+            val = mv if val is None else [a + b for a, b in zip(val, mv)]
+    return val
+
+
 def philox(ctr, key):
     c = (C.c_uint32 * 4)(*ctr)
     k = (C.c_uint32 * 2)(*key)
