@@ -268,8 +268,9 @@ def shell_quadrature(par, eps, Q, P, exprs, p_res=0.01, onlyqroot=0):
         disc = 4 * g ** 2 * Q ** 2 * r - p ** 2 * w ** 2 - w * w0 * (P ** 2 + Q ** 2 - 2) + 2 * w * eps   # src/ClassicalDicke.jl:224-228
         q = (-2 * g * Q * math.sqrt(r) + sgn * np.sqrt(disc)) / w                                        # :271-272
         X = np.column_stack([np.full(n, Q), q, np.full(n, P), p])
-        for kk in range(n):
-            mv = [(math.pi / (n * w)) * float(eval_expr(e, ["Q", "q", "P", "p"], X[kk])) for e in exprs]
+        F = [np.broadcast_to(eval_expr(e, ["Q", "q", "P", "p"], X), (n,)) for e in exprs]   # f at every node
+        for kk in range(n):                                                                  # the reference's sequential sum
+            mv = [(math.pi / (n * w)) * float(Fe[kk]) for Fe in F]
             val = mv if val is None else [a + b for a, b in zip(val, mv)]
     return val
 
