@@ -36,7 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOPS_PER_STEP = {"dicke_rk4": 136.0}      # SURVEY.md section 8d / BASELINE.md section 4
-FP64_INSTR_PER_STEP = {"dicke_rk4": 92.0}  # SASS of the run-time specialised hot loop for w = 1: 60 DFMA + 32 DMUL (96 for general w)
+FP64_INSTR_PER_STEP = {"dicke_rk4": 92.0}  # SASS of the run-time specialised hot loop for w = 1: 64 DFMA + 28 DMUL (96 for general w); tools/jit_sass.py dumps it
 
 WORK = {"system": "dicke", "par": [1.0, 1.0, 1.0], "j": 100, "center": [0.0, 0.0, 0.0, 0.0], "t_end": 100, "t_step": 0.05,
         "dt": 2.0 ** -7, "seed": 20261019}
