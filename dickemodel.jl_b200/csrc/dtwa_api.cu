@@ -678,7 +678,7 @@ extern "C" int dtwa_lyapunov(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_s
     TRY(d.u0.ensure(b_u0));
     TRY(d.scratch_a.ensure(2 * b_u0));
     TRY(d.scratch_b.ensure(2 * sizeof(int32_t) * n));
-    TRY(d.scratch_c.ensure(sizeof(long long) * n));
+    TRY(d.scratch_c.ensure(sizeof(long long) * (n + 1)));
     unsigned char *meta = (unsigned char *)d.meta.p;
     CK(cudaMemcpyAsync(meta, tab.data(), tab_b, cudaMemcpyHostToDevice, d.stream));
     CK(cudaMemcpyAsync(meta + tab_b, ts1, ts_b, cudaMemcpyHostToDevice, d.stream));
@@ -690,14 +690,20 @@ extern "C" int dtwa_lyapunov(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_s
     L.lreltol = lam_reltol;
     L.maxiters = maxiters;
     L.pad = 0;
-    const unsigned grid = blocks_for(n * nv, 128);
     double *d_lam = (double *)d.scratch_a.p, *d_x = (double *)((unsigned char *)d.scratch_a.p + b_u0);
     int32_t *d_it = (int32_t *)d.scratch_b.p, *d_st = d_it + n;
+    // persistent grid: groups draw initial conditions from a counter (kept behind the nsteps array)
+    unsigned long long *d_next = (unsigned long long *)d.scratch_c.p + n;
+    CK(cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), d.stream));
     CK(cudaEventRecord(d.ev[0], d.stream));
     by_var_system(sys->kind, [&](auto sk) {
         return by_alg(sol->alg, [&](auto ak) {
-            lyapunov_kernel<decltype(sk)::value, decltype(ak)::value><<<grid, 128, 0, d.stream>>>(
-                S, L, (const double *)d.u0.p, n, d_lam, d_x, d_it, d_st, (long long *)d.scratch_c.p);
+            auto kern = lyapunov_kernel<decltype(sk)::value, decltype(ak)::value>;
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+            const long long want = (n * nv + 127) / 128, cap = (long long)d.sm_count * per_sm;
+            const unsigned grid = (unsigned)std::max(1ll, std::min(want, cap));
+            kern<<<grid, 128, 0, d.stream>>>(S, L, (const double *)d.u0.p, n, d_lam, d_x, d_it, d_st, (long long *)d.scratch_c.p, d_next);
             return 0;
         });
     });

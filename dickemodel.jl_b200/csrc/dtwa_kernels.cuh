@@ -645,20 +645,27 @@ struct LyapArgs {
     double t_interval, ltol, lreltol;
     int32_t maxiters, pad;
 };
+// Orbits need very different numbers of rounds (4 .. maxiters), so the groups of a persistent grid draw their
+// next initial condition from a global counter (`next`, zeroed by the host) instead of owning a fixed one.
 template <int SYS, int ALG>
 __global__ void __launch_bounds__(128) lyapunov_kernel(const SolverArgs S, const LyapArgs L, const double *__restrict__ u0,
                                                        long long n, double *__restrict__ lambda_out,
                                                        double *__restrict__ x_out, int32_t *__restrict__ iters_out,
-                                                       int32_t *__restrict__ status, long long *__restrict__ nsteps)
+                                                       int32_t *__restrict__ status, long long *__restrict__ nsteps,
+                                                       unsigned long long *__restrict__ next)
 {
     constexpr int NVB = Sys<SYS>::NVB, G = Sys<SYS>::GROUP;
-    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const int c = (int)(gid % G);
-    const long long j0 = gid / G;
-    const bool live = j0 < n;
-    const long long j = live ? j0 : n - 1;
+    const int c = (int)(threadIdx.x % G);
     const unsigned base = (threadIdx.x & 31u) & ~(unsigned)(G - 1);
     const unsigned mask = ((1u << G) - 1u) << base;
+#pragma unroll 1
+    for (;;) {
+    unsigned long long jn = 0;
+    if (c == 0) jn = atomicAdd(next, 1ull);
+    jn = __shfl_sync(mask, jn, (int)base);
+    if (jn >= (unsigned long long)n) break;
+    const long long j = (long long)jn;
+    const bool live = true;
     double x[NVB], w[NVB], lam[NVB], lam_old[NVB];
     double sums = 0.0;
 #pragma unroll
@@ -745,6 +752,7 @@ __global__ void __launch_bounds__(128) lyapunov_kernel(const SolverArgs S, const
         status[j] = st;
         if (nsteps) nsteps[j] = steps;
     }
+    }  // work loop
 }
 
 // K7: surfaces of section -- SURVEY 8f rank 3 (docs/src/ClassicalDickeExamples.md:82-109: integrate with a
