@@ -758,11 +758,15 @@ __global__ void __launch_bounds__(128) lyapunov_kernel(const SolverArgs S, const
 // K7: surfaces of section -- SURVEY 8f rank 3 (docs/src/ClassicalDickeExamples.md:82-109: integrate with a
 // DiffEq ContinuousCallback on p = 0, save_positions=(false,false)).  One thread per initial condition
 // integrates to t_end and records every crossing of g(u) = coef . u - offset = 0 (direction: 0 both,
-// +1 g increasing, -1 decreasing), located with Henon steps (dtwa_device.cuh) instead of the reference's
-// root search on the interpolant: predict the crossing time with a Henon step back from the end of the
-// crossing step; re-take the integrator's own step from the step start to that time (local error of an
-// accepted step) and polish the time with up to four Newton iterations on g (each one such step);
-// remove what is left of |g| (rounding level) with a last Henon step.
+// +1 g increasing, -1 decreasing).  Where the reference searches a root of its interpolant, the crossing is
+// located to integrator accuracy: starting from the chord estimate, Newton on the crossing time, each
+// iteration re-taking the integrator's own step from the start of the crossing step (local error of an
+// accepted step); what is left of |g| (rounding level) is removed by one Henon step (dtwa_device.cuh), so
+// recorded states satisfy g = 0 to rounding.
+// Divergence: a crossing costs ~5 extra steps and happens in ~3 % of the steps of a lane.  A lane therefore
+// only NOTES a crossing (step start, times, g values) and keeps stepping; the warp refines all noted
+// crossings together when some lane meets its next one (or at the end), so the refinement runs with most
+// lanes active instead of one.
 //   ev_t[n][cap], ev_u[n][cap][NV], ev_dir[n][cap] (+1/-1), ev_count[n] (keeps counting beyond cap)
 struct EventArgs {
     double coef[4];
@@ -779,8 +783,9 @@ __global__ void __launch_bounds__(128) events_kernel(const SolverArgs S, const E
     constexpr int NV = Sys<SYS>::NV;
     constexpr int HSYS = (SYS == DTWA_SYS_DICKE) ? DTWA_SYS_DICKE_HENON : DTWA_SYS_LMG_HENON;
     constexpr bool FIXED = is_fixed<ALG>::value;
-    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    const long long j0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool live = j0 < n;
+    const long long j = live ? j0 : n - 1;
     HenonPar hp;
     static_cast<SysPar &>(hp) = S.par;
 #pragma unroll
@@ -791,14 +796,18 @@ __global__ void __launch_bounds__(128) events_kernel(const SolverArgs S, const E
         for (int i = 0; i < NV; ++i) g = fma(E.coef[i], u[i], g);
         return g;
     };
-    Traj<SYS, ALG> T;
-    T.status = ST_OK;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) T.u[i] = u0[j * NV + i];
-    T.begin(S);
-    int count = 0;
-    double t = 0.0, g0 = (T.status == ST_OK) ? gfun(T.u) : 0.0;
-    double us[NV], ts0 = 0.0;           // state and time at the start of the current step
+    auto own_step = [&](double (&z)[NV], double th) {   // the integrator's own one-step map
+        if constexpr (ALG == DTWA_ALG_RK4) {
+            StepTab r;
+            const double wf = (SYS == DTWA_SYS_DICKE) ? S.par.b : 1.0;
+            r.h = th; r.hh = th / 2.0; r.h3 = th / 3.0; r.h6 = th / 6.0;
+            r.hw = r.h * wf; r.hhw = r.hh * wf; r.h3w = r.h3 * wf; r.h6w = r.h6 * wf;
+            r.n = 1; r.pad = 0;
+            rk4_step<SYS>(S.par, z, r);
+        } else {
+            rk8_step<SYS>(S.par, z, th);
+        }
+    };
     auto henon = [&](double (&y)[NV + 1], double hg) {
         if constexpr (ALG == DTWA_ALG_RK4) {
             StepTab r;
@@ -810,117 +819,136 @@ __global__ void __launch_bounds__(128) events_kernel(const SolverArgs S, const E
             rk8_step<HSYS>(hp, y, hg);
         }
     };
-    auto crossing = [&](double t1) {   // called with T.u = state at the end of an accepted step, time t1
-        const double g1 = gfun(T.u);
-        const bool up = g0 < 0.0 && g1 >= 0.0, down = g0 > 0.0 && g1 <= 0.0;
-        if ((up && E.direction >= 0) || (down && E.direction <= 0)) {
-            double y[NV + 1];
+    Traj<SYS, ALG> T;
+    T.status = ST_OK;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) y[i] = T.u[i];
-            y[NV] = t1;
-            if (g1 != 0.0) {
-                henon(y, -g1);                                   // predictor: crossing time from the step end
-                const double hs = t1 - ts0;
-                double th = y[NV] - ts0;
-                if (!(th > 0.0) || !(th <= hs)) th = hs * (g0 / (g0 - g1));   // grazing contact: fall back to the chord
-                double z[NV], g2 = 0.0;
+    for (int i = 0; i < NV; ++i) T.u[i] = u0[j * NV + i];
+    T.begin(S);
+    int count = 0;
+    double t = 0.0, g0 = (T.status == ST_OK) ? gfun(T.u) : 0.0;
+    // the noted crossing of this lane
+    bool pending = false;
+    double ps[NV], pts0 = 0.0, phs = 0.0, pg0 = 0.0, pg1 = 0.0;
+    auto refine = [&]() {   // executed by all lanes with a noted crossing at once
+        double th = phs * (pg0 / (pg0 - pg1));           // chord
+        double z[NV], g2 = pg1;
+        if (pg1 == 0.0) th = phs;
 #pragma unroll 1
-                for (int it = 0; it < 5; ++it) {
+        for (int it = 0; it < 6; ++it) {
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) z[i] = us[i];
-                    if constexpr (ALG == DTWA_ALG_RK4) {          // the integrator's own step, start -> predicted time
-                        StepTab r;
-                        const double wf = (SYS == DTWA_SYS_DICKE) ? S.par.b : 1.0;
-                        r.h = th; r.hh = th / 2.0; r.h3 = th / 3.0; r.h6 = th / 6.0;
-                        r.hw = r.h * wf; r.hhw = r.hh * wf; r.h3w = r.h3 * wf; r.h6w = r.h6 * wf;
-                        r.n = 1; r.pad = 0;
-                        rk4_step<SYS>(S.par, z, r);
-                    } else {
-                        rk8_step<SYS>(S.par, z, th);
-                    }
-                    g2 = gfun(z);
-                    if (it == 4 || fabs(g2) <= 1e-13) break;
-                    double f[NV], gd = 0.0;                       // Newton on the crossing time
-                    Sys<SYS>::rhs(S.par, z, f);
+            for (int i = 0; i < NV; ++i) z[i] = ps[i];
+            own_step(z, th);
+            g2 = gfun(z);
+            if (it == 5 || fabs(g2) <= 1e-13) break;
+            double f[NV], gd = 0.0;                       // Newton on the crossing time
+            Sys<SYS>::rhs(S.par, z, f);
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) gd = fma(E.coef[i], f[i], gd);
-                    const double tn = th - g2 / gd;
-                    if (!(tn > 0.0) || !(tn <= hs)) break;
-                    th = tn;
-                }
+            for (int i = 0; i < NV; ++i) gd = fma(E.coef[i], f[i], gd);
+            const double tn = th - g2 / gd;
+            if (!(tn > 0.0) || !(tn <= phs)) break;
+            th = tn;
+        }
+        double y[NV + 1];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) y[i] = z[i];
+        y[NV] = pts0 + th;
+        if (g2 != 0.0) {
+            henon(y, -g2);                                // |g2| is at rounding level unless Newton left the step
+            bool fin = true;
+#pragma unroll
+            for (int i = 0; i <= NV; ++i) fin = fin && (y[i] == y[i]) && !isinf(y[i]);
+            if (!fin) {
 #pragma unroll
                 for (int i = 0; i < NV; ++i) y[i] = z[i];
-                y[NV] = ts0 + th;
-                if (g2 != 0.0) henon(y, -g2);                    // |g2| is at rounding level (unless Newton left the step)
-                bool fin = true;
-#pragma unroll
-                for (int i = 0; i <= NV; ++i) fin = fin && (y[i] == y[i]) && !isinf(y[i]);
-                if (!fin) {
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) y[i] = z[i];
-                    y[NV] = ts0 + th;
-                }
+                y[NV] = pts0 + th;
             }
-            if (count < E.cap) {
-                const size_t e = (size_t)j * E.cap + count;
-                ev_t[e] = y[NV];
-#pragma unroll
-                for (int i = 0; i < NV; ++i) ev_u[e * NV + i] = y[i];
-                ev_dir[e] = up ? 1 : -1;
-            }
-            ++count;
         }
-        g0 = g1;
-    };
-    if (T.status == ST_OK && E.t_end > 0.0) {
-        if constexpr (FIXED) {
-            const StepTab r = S.uniform ? S.uni : S.tab[0];
-            const int nst = S.uniform ? S.first_n : r.n;
-#pragma unroll 1
-            for (int s = 0; s < nst && T.status == ST_OK; ++s) {
+        if (count < E.cap && live) {
+            const size_t e = (size_t)j * E.cap + count;
+            ev_t[e] = y[NV];
 #pragma unroll
-                for (int i = 0; i < NV; ++i) us[i] = T.u[i];
-                ts0 = t;
+            for (int i = 0; i < NV; ++i) ev_u[e * NV + i] = y[i];
+            ev_dir[e] = (pg0 < 0.0) ? 1 : -1;
+        }
+        ++count;
+        pending = false;
+    };
+    const StepTab r = FIXED ? S.tab[0] : StepTab();
+    int sidx = 0;
+    bool done = !(T.status == ST_OK && E.t_end > 0.0);
+#pragma unroll 1
+    while (__any_sync(0xffffffffu, !done)) {
+        bool cross = false, accepted = false;
+        double cs[NV], cts0 = 0.0, chs = 0.0, cg1 = 0.0;
+        if (!done) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) cs[i] = T.u[i];
+            double t1 = t;
+            if constexpr (FIXED) {
                 if constexpr (ALG == DTWA_ALG_RK4)
                     rk4_step<SYS>(S.par, T.u, r);
                 else
                     rk8_step<SYS>(S.par, T.u, r.h);
                 ++T.nacc;
+                ++sidx;
                 if (state_bad<SYS>(T.u)) {
                     T.status = ST_DOMAIN;
-                    break;
+                    done = true;
+                } else {
+                    accepted = true;
+                    t1 = (sidx == r.n) ? E.t_end : r.h * (double)sidx;
+                    if (sidx == r.n) done = true;
                 }
-                t = (s + 1 == nst) ? E.t_end : r.h * (double)(s + 1);
-                crossing(t);
-            }
-        } else {
-#pragma unroll 1
-            while (T.ad.t < E.t_end) {
+            } else {
                 if ((long long)(T.nacc + T.nrej) >= S.maxiters) {
                     T.status = ST_MAXITERS;
-                    break;
-                }
-                bool accepted;
-#pragma unroll
-                for (int i = 0; i < NV; ++i) us[i] = T.u[i];
-                ts0 = T.ad.t;
-                if (T.ad.attempt(S.par, T.u, E.t_end, S.tol, S.dtmin, accepted)) {
+                    done = true;
+                } else if (T.ad.attempt(S.par, T.u, E.t_end, S.tol, S.dtmin, accepted)) {
                     T.status = ST_DOMAIN;
-                    break;
-                }
-                if (accepted) {
+                    done = true;
+                    accepted = false;
+                } else if (accepted) {
                     ++T.nacc;
-                    crossing(T.ad.t);
+                    t1 = T.ad.t;
+                    if (!(T.ad.t < E.t_end)) done = true;
                 } else
                     ++T.nrej;
             }
+            if (accepted) {
+                cg1 = gfun(T.u);
+                const bool up = g0 < 0.0 && cg1 >= 0.0, down = g0 > 0.0 && cg1 <= 0.0;
+                cross = (up && E.direction >= 0) || (down && E.direction <= 0);
+                cts0 = t;
+                chs = t1 - t;
+                t = t1;
+            }
+        }
+        // refine the noted crossings together when a lane needs its slot again ...
+        if (__any_sync(0xffffffffu, cross && pending)) {
+            if (pending) refine();
+        }
+        if (cross) {
+            pending = true;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) ps[i] = cs[i];
+            pts0 = cts0;
+            phs = chs;
+            pg0 = g0;
+            pg1 = cg1;
+        }
+        if (accepted) g0 = cg1;
+        // ... or when every lane of the warp has finished
+        if (!__any_sync(0xffffffffu, !done) && __any_sync(0xffffffffu, pending)) {
+            if (pending) refine();
         }
     }
-    ev_count[j] = count;
-    status[j] = T.status;
+    if (live) {
+        ev_count[j] = count;
+        status[j] = T.status;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) u_end[j * NV + i] = T.u[i];
-    if (nsteps) nsteps[j] = (long long)T.nacc + (long long)T.nrej;
+        for (int i = 0; i < NV; ++i) u_end[j * NV + i] = T.u[i];
+        if (nsteps) nsteps[j] = (long long)T.nacc + (long long)T.nrej;
+    }
 }
 
 // K8: energy-shell quadrature -- SURVEY 8f rank 4, src/EnergyShellProjections.jl:49-96 (the double integral of

@@ -1246,22 +1246,20 @@ static void ev_check(ev_ctx *c, const double *u, double t1)
         memcpy(y, u, sizeof(double) * nv);
         y[nv] = t1;
         if (g1 != 0) {
-            /* predictor (Henon step back from the step end), the integrator's own step from the step start
-             * to the predicted time, corrector (Henon step over the remaining, tiny g) */
+            /* chord estimate of the crossing time, then Newton on it: each iteration re-takes the integrator's own
+             * step from the step start; a last Henon step removes what is left of g (rounding level) */
             double sgn = c->pb->backwards ? -1.0 : 1.0;
             int rk4 = c->pb->alg == ALG_RK4;
-            henon_step(kind, c->pb->par, sgn, c->coef, rk4, -g1, y);
-            double hs = t1 - c->ts0, th = y[nv] - c->ts0, z[4];
-            if (!(th > 0) || !(th <= hs)) th = hs * (c->g0 / (c->g0 - g1));
+            double hs = t1 - c->ts0, th = hs * (c->g0 / (c->g0 - g1)), z[4];
             double g2 = 0;
-            for (int it = 0; it < 5; ++it) {
+            for (int it = 0; it < 6; ++it) {
                 memcpy(z, c->us, sizeof(double) * nv);
                 if (rk4)
                     rk4_step(kind, c->pb->par, sgn, th, z);
                 else
                     rk8_fixed_step(kind, c->pb->par, sgn, th, z);
                 g2 = ev_g(c->coef, c->offset, z, nv);
-                if (it == 4 || fabs(g2) <= 1e-13) break;
+                if (it == 5 || fabs(g2) <= 1e-13) break;
                 double f[4], gd = 0; /* Newton on the crossing time */
                 orc_rhs(kind, c->pb->par, sgn, z, f);
                 for (int i = 0; i < nv; ++i) gd += c->coef[i] * f[i];
