@@ -782,12 +782,20 @@ extern "C" int dtwa_integrate_events(dtwa_ctx *ctx, const dtwa_system *sys, cons
     });
     CK(cudaGetLastError());
     CK(cudaEventRecord(d.ev[3], d.stream));
-    if (cap) {
-        CK(cudaMemcpyAsync(ev_t, d_t, b_t, cudaMemcpyDeviceToHost, d.stream));
-        CK(cudaMemcpyAsync(ev_u, d_u, b_u, cudaMemcpyDeviceToHost, d.stream));
-        CK(cudaMemcpyAsync(ev_dir, d_dir, b_dir, cudaMemcpyDeviceToHost, d.stream));
-    }
     CK(cudaMemcpyAsync(ev_count, d_cnt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d.stream));
+    if (cap) {
+        // only the columns some trajectory used travel back (the arrays are [n][max_events] padded)
+        CK(cudaStreamSynchronize(d.stream));
+        size_t used = 0;
+        for (int64_t i = 0; i < n; ++i) used = std::max(used, (size_t)std::min<int64_t>(ev_count[i], (int64_t)cap));
+        if (used) {
+            CK(cudaMemcpy2DAsync(ev_t, cap * sizeof(double), d_t, cap * sizeof(double), used * sizeof(double), n, cudaMemcpyDeviceToHost, d.stream));
+            CK(cudaMemcpy2DAsync(ev_u, cap * nv * sizeof(double), d_u, cap * nv * sizeof(double), used * nv * sizeof(double), n,
+                                 cudaMemcpyDeviceToHost, d.stream));
+            CK(cudaMemcpy2DAsync(ev_dir, cap * sizeof(int32_t), d_dir, cap * sizeof(int32_t), used * sizeof(int32_t), n,
+                                 cudaMemcpyDeviceToHost, d.stream));
+        }
+    }
     CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaMemcpyAsync(u_end, d_end, b_u0, cudaMemcpyDeviceToHost, d.stream));
     if (nsteps) CK(cudaMemcpyAsync(nsteps, d.scratch_c.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, d.stream));

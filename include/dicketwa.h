@@ -219,7 +219,8 @@ int dtwa_lyapunov(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol,
  *      (Newton on the crossing time with the integrator's own step from the start of the crossing step, then
  *      one Henon step -- the event function as independent variable -- so that g = 0 to rounding); the
  *      reference searches a root of its interpolant.  ev_t[n][max_events], ev_u[n][max_events][nvar], ev_dir[n][max_events] (+1/-1),
- *      ev_count[n] (keeps counting past max_events), u_end[n][nvar], status[n], nsteps[n] (may be NULL). ---- */
+ *      ev_count[n] (keeps counting past max_events; entries of row i at or beyond min(ev_count[i], max_events)
+ *      are unspecified), u_end[n][nvar], status[n], nsteps[n] (may be NULL). ---- */
 typedef struct dtwa_event {
     double coef[4];
     double offset;

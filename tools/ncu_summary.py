@@ -2,6 +2,7 @@
 """Summarise an .ncu-rep (read here, no GPU needed) into the handful of numbers DESIGN.md / profiles/ quote.
 
 usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--md profiles/name.md] [--title "..."]
+                                   [--traffic-json profiles/traffic_rk4_bench.json --n-traj 10000000]
 """
 import csv
 import io
@@ -56,6 +57,19 @@ def main():
         out.append("warp stall reasons (warps stalled per issued instruction): " +
                    ", ".join(f"{n} {v:.2f}" for v, n in stalls[:9]))
         out.append("")
+    if "--traffic-json" in sys.argv:   # what bench.py reports as roofline.traffic (DRAM bytes of one launch)
+        import json
+        d, u = dict(zip(hdr, rows[2])), dict(zip(hdr, units))
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd = float(d["dram__bytes_read.sum"]) * scale[u["dram__bytes_read.sum"]]
+        wr = float(d["dram__bytes_write.sum"]) * scale[u["dram__bytes_write.sum"]]
+        n_traj = int(float(sys.argv[sys.argv.index("--n-traj") + 1])) if "--n-traj" in sys.argv else 0
+        json.dump({"kernel": d.get("Kernel Name"), "n_traj": n_traj, "dram_bytes_read": rd, "dram_bytes_write": wr, "unit": "bytes per launch",
+                   "kernel_ms_under_ncu": float(d["gpu__time_duration.sum"]) * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}.get(u["gpu__time_duration.sum"], 1.0),
+                   "source": f"ncu --set full --clock-control none, {rep} (one launch): dram__bytes_read.sum + dram__bytes_write.sum; "
+                             "reads are the per-CTA partial-sum rows (zero-filled, then RED-updated) and the meta blob; the kernel is "
+                             "FP64-pipe bound (1.9e13 flop against 1e7 B)"},
+                  open(sys.argv[sys.argv.index("--traffic-json") + 1], "w"), indent=1)
     text = "\n".join(out)
     print(text)
     if md:
