@@ -37,7 +37,8 @@ j = 100
 center = [0, 0, 0, 0] if a.state == "A" else [1.0, 0.31783724519578205, 1.0, 0.0]
 ts = TWA.jrange(0, a.tstep, a.tend)
 jz = TWA.Weyl.Jz(j) / j
-kw = dict(integrator_alg="RK4", dt=2.0 ** -7) if a.alg == "RK4" else dict(integrator_alg=a.alg, tol=a.tol)
+ap_dt = {"RK4": 2.0 ** -7, "RK8": 0.05}
+kw = dict(integrator_alg=a.alg, dt=ap_dt[a.alg]) if a.alg in ap_dt else dict(integrator_alg=a.alg, tol=a.tol)
 for rep in range(a.reps):
     W = TWA.coherent_Wigner_HWxSU2(center, j=j, seed=20261019)
     qs, ps = TWA.jrange(-4.3, 0.02, 4.3), TWA.jrange(-2.4, 0.02, 2.4)
