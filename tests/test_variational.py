@@ -270,3 +270,48 @@ def test_integrate_with_continuous_callback_like_the_docs(pkg, O):
         CS.integrate(system, u0, 1.0, callback=CS.ContinuousCallback(lambda x, t, _: x[3] ** 2 - 1, save))
     res = CS.poincare_section_batch(system, np.array([u0, u0]), 50.0, coef=[0, 0, 0, 1], tol=1e-10, max_events=8)
     assert np.array_equal(res["count"], [res["count"][0]] * 2) and np.array_equal(res["t"][0], res["t"][1], equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_edge_cases_of_the_widened_entry_points(ctx, pkg):
+    """empty batches, bad arguments (the reference's error messages where it has them), failing trajectories"""
+    lib = pkg._lib
+    sd, sl = csys(pkg, 0, DPAR), csys(pkg, 1, LPAR)
+    sol = csol(pkg, lib.ALG_DOP853, tol=1e-9)
+    e4, e2 = np.empty((0, 4)), np.empty((0, 2))
+    x, F, st, ns = ctx.integrate_fm(sd, sol, e4, [0.0, 1.0])
+    assert x.shape == (0, 2, 4) and F.shape == (0, 2, 4, 4)
+    lam, xf, it, st, ns, ms = ctx.lyapunov(sl, sol, e2, 10.0, 1e-4, 1e-3, 10)
+    assert lam.shape == (0, 2)
+    r = ctx.integrate_events(sd, sol, e4, 5.0, [0, 0, 0, 1])
+    assert r[0].shape == (0, 1024) and r[3].shape == (0,)
+    out, valid, nodes, ms = ctx.shell_quadrature(sd, 0.5, np.empty((0, 2)), ["1"])
+    assert out.shape == (0, 1)
+    with pytest.raises(pkg.DtwaError, match="interval t must be > 0"):
+        ctx.lyapunov(sd, sol, [DOCS_PT], 0.0, 1e-4, 1e-3, 10)
+    with pytest.raises(pkg.DtwaError, match="maxiters"):
+        ctx.lyapunov(sd, sol, [DOCS_PT], 1.0, 1e-4, 1e-3, 0)
+    with pytest.raises(pkg.DtwaError, match="negative time"):
+        ctx.integrate_events(sd, sol, [DOCS_PT], -1.0, [0, 0, 0, 1])
+    with pytest.raises(pkg.DtwaError, match="non-zero"):
+        ctx.integrate_events(sd, sol, [DOCS_PT], 1.0, [0, 0, 0, 0])
+    with pytest.raises(pkg.DtwaError, match="direction"):
+        ctx.integrate_events(sd, sol, [DOCS_PT], 1.0, [0, 0, 0, 1], direction=2)
+    with pytest.raises(pkg.DtwaError, match="Dicke"):
+        ctx.shell_quadrature(sl, 0.5, [[0.1, 0.1]], ["1"])
+    with pytest.raises(pkg.DtwaError, match="between 1 and 8"):
+        ctx.shell_quadrature(sd, 0.5, [[0.1, 0.1]], ["1"] * 9)
+    # out-of-bounds initial conditions are reported per trajectory, the rest of the batch is unaffected
+    u0 = np.array([DOCS_PT, [1.9, 0.0, 1.9, 0.0], [0.4, -0.7, 0.3, 0.5]])
+    x, F, st, ns = ctx.integrate_fm(sd, sol, u0, [0.0, 1.0])
+    assert list(st) == [0, lib.TRAJ_BAD_IC, 0] and np.isnan(x[1]).all() and np.isnan(F[1]).all() and np.isfinite(F[[0, 2]]).all()
+    lam, xf, it, st, ns, ms = ctx.lyapunov(sd, sol, u0, 5.0, 1e-3, 1e-2, 200)
+    assert st[1] == lib.TRAJ_BAD_IC and st[0] == 0 and st[2] == 0
+    et, eu, ed, cnt, ue, st, ns, ms = ctx.integrate_events(sd, sol, u0, 10.0, [0, 0, 0, 1], max_events=4)
+    assert st[1] == lib.TRAJ_BAD_IC and cnt[1] == 0 and cnt[0] > 0 and cnt[2] > 0
+    # t_end = 0: nothing happens
+    et, eu, ed, cnt, ue, st, ns, ms = ctx.integrate_events(sd, sol, u0[[0, 2]], 0.0, [0, 0, 0, 1], max_events=4)
+    assert (cnt == 0).all() and np.array_equal(ue, u0[[0, 2]]) and (st == 0).all()
+    # a section that is never reached
+    et, eu, ed, cnt, ue, st, ns, ms = ctx.integrate_events(sd, sol, u0[[0, 2]], 5.0, [0, 1, 0, 0], offset=50.0, max_events=4)
+    assert (cnt == 0).all() and np.isnan(et).all()
