@@ -205,3 +205,30 @@ def phase_space_dist_squared(x, y):
 
 
 q_of_eps, minimum_eps_for = q_of_ϵ, minimum_ϵ_for
+
+
+def classical_path_random_sampler(system, *, ϵ, dt=3, seed=None):
+    """src/ClassicalDicke.jl:502-531: sample() walks along one chaotic trajectory (integrated on the GPU) in
+    steps of dt, flipping (Q, q) -> (-Q, -q) at random.  `seed` makes the host-side coin flips reproducible."""
+    import random
+    from . import ClassicalSystems
+    rng = random.Random(seed)
+    w0, w, g = system.parameters()
+    s = math.sqrt(16 * g ** 4 + 8 * g ** 2 * ϵ * w + w ** 2 * w0 ** 2) / (2 * g ** 2)
+    a = 2 - w * w0 / (2 * g ** 2)
+    mx = math.sqrt(a + s)
+    mn = 0.0 if a < s else math.sqrt(a - s)
+    Q = mn if mn == mx else rng.uniform(mn, mx)
+    Q = Q * rng.choice((-1, 1))
+    state = {"u": Point(system, Q=Q, P=0, p=0, ϵ=ϵ)}
+
+    def sample():
+        u = ClassicalSystems.integrate(system, state["u"], dt, save_everystep=False, show_progress=False).u[-1].copy()
+        if rng.choice((True, False)):
+            u[0], u[1] = -u[0], -u[1]
+        state["u"] = u
+        return u.copy()
+    for _ in range(10):
+        sample()
+    return sample
+

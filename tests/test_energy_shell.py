@@ -87,3 +87,14 @@ def test_energy_shell_projections_api(pkg, O):
     b = ESP.energy_shell_average(system, ϵ=eps, f=lambda x: [x[1] ** 2 + x[3] ** 2, x[0] ** 2], res=0.05, symmetricQP=True)
     assert np.allclose(a, b, rtol=1e-9)
     assert abs(CD.energy_shell_volume(system, 1.5) - 8 * math.pi ** 2) < 1e-12 and CD.energy_shell_volume(system, -5.0) == 0.0
+
+
+@pytest.mark.gpu
+def test_classical_path_random_sampler_stays_on_the_shell(pkg, O):
+    """src/ClassicalDicke.jl:502-531: points along one chaotic trajectory, all at energy ϵ"""
+    from dickemodel_jl_b200 import ClassicalDicke as CD
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    sample = CD.classical_path_random_sampler(system, ϵ=-0.5, dt=3, seed=4)
+    pts = np.array([sample() for _ in range(6)])
+    assert np.abs(O.hamiltonian(O.SYS_DICKE, PAR, pts) + 0.5).max() < 1e-9
+    assert len({tuple(np.round(p, 6)) for p in pts}) == 6
