@@ -1101,19 +1101,26 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
     double jit_work = (double)N * (double)nt;
     if (!fixed) jit_work = std::max(jit_work, (double)N * 8.0 * ts[nt - 1]);
     const bool want_jit = ctx->jit_mode == 1 || (ctx->jit_mode == 2 && jit_work >= 2e9);
+    bool used_jit = want_jit;
     if (want_jit) {
         cudaKernel_t jk;
         std::string jerr;
         CK(cudaSetDevice(ctx->devs[0].device));
         const double wsigned = make_par(sys, sol->backwards).b;
         const int wflag = (sys->kind == DTWA_SYS_DICKE && wsigned == 1.0) ? 1 : (sys->kind == DTWA_SYS_DICKE && wsigned == -1.0) ? -1 : 0;
-        if (jit_cache().get(sys->kind, sol->alg, wflag, prog, &jk, jerr)) return set_err(DTWA_ERR_JIT, jerr);
-        kern = (const void *)jk;
+        if (jit_cache().get(sys->kind, sol->alg, wflag, prog, &jk, jerr)) {
+            // forced specialisation fails loudly; in auto mode the (slower) interpreter kernel runs instead -- still on
+            // the GPU -- and the result reports jit = 0 (e.g. libnvrtc is not installed next to the driver)
+            if (ctx->jit_mode == 1) return set_err(DTWA_ERR_JIT, jerr);
+            set_err(DTWA_ERR_JIT, jerr);
+            used_jit = false;
+        } else
+            kern = (const void *)jk;
     }
 
     dtwa_plan *plan = new dtwa_plan;
     plan->ctx = ctx;
-    plan->jit = want_jit;
+    plan->jit = used_jit;
     plan->nt = nt;
     plan->nslots = nslots;
     plan->n_f64 = (int64_t)nt * std::max(nslots, 1);

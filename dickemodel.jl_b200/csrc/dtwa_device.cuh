@@ -379,6 +379,7 @@ __device__ __forceinline__ void rk8_step(const SysPar &p, double (&y)[Sys<SYS>::
 #include "dop853_body.inc"
     (void)e5;
     (void)e3;
+    (void)dy;
 #pragma unroll
     for (int i = 0; i < NV; ++i) y[i] = ynew[i];
 #undef DOP853_KNEW
@@ -479,6 +480,7 @@ struct Adaptive {
         double yn[NV], kn[NV];
         if constexpr (ALG == DTWA_ALG_DP5) {
 #include "dp5_body.inc"
+            (void)dy;
             double en[NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
