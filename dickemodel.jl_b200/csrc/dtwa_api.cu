@@ -918,17 +918,19 @@ static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const 
 {
     const bool fixed = alg == DTWA_ALG_RK4 || alg == DTWA_ALG_RK8;
     const int max_threads = alg == DTWA_ALG_RK4 ? ens_launch<DTWA_ALG_RK4>::max_threads : ens_launch<DTWA_ALG_DOP853>::max_threads;
-    int block = ctx->block_threads ? ctx->block_threads : (fixed ? 256 : 64);
+    int block = ctx->block_threads ? ctx->block_threads : 256;
     if (block > max_threads) block = max_threads;
+    if (!fixed) block = 32;   // adaptive kernels: one warp per CTA (warp-level sliding flush, see ensemble_body)
     // window: output times staged in shared memory between two CTA-wide flushes (<= 24 KB of staging)
     // window: output times staged in shared memory between two CTA-wide flushes (<= 24 KB of staging)
     const int rows = fixed ? block / 32 : block;  // staging rows: one per warp (fixed step) or per thread (adaptive)
     const size_t per_out = sizeof(double) * rows * (A.nslots > 0 ? A.nslots : 1) + sizeof(unsigned) * A.stage_bins + sizeof(unsigned);
     // (adaptive kernels profit from long windows: the lanes' step counts average out before they wait for each
     //  other; fixed step: 16 -> 32 outputs per barrier is worth 0.6 %, measured)
-    size_t wcap = fixed ? 32 : 64, wbudget = fixed ? 24 * 1024 : 32 * 1024;
+    size_t wcap = fixed ? 32 : 64, wbudget = fixed ? 24 * 1024 : 16 * 1024;
     if (const char *e = std::getenv("DTWA_WINDOW")) wcap = (size_t)std::max(1, std::atoi(e));  // tuning experiments
     int window = (int)std::max<size_t>(1, std::min<size_t>({wcap, (size_t)A.S.nt, wbudget / per_out}));
+    if (!fixed && window > 1) window &= ~1;   // the adaptive ring is flushed in two halves
     const size_t smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, rows, window);
     ls.window = window;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

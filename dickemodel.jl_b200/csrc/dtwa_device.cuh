@@ -390,15 +390,6 @@ __device__ __forceinline__ void rk8_step(const SysPar &p, double (&y)[Sys<SYS>::
 // RMS error norm with scale = tol + max(|y|,|ynew|) tol, factor in [0.2, 10], safety 0.9, plus the
 // reference's solver contract (src/ClassicalSystems.jl:138): dtmin with force_dtmin, out-of-domain
 // trial steps rejected with a shrink of 0.2, maxiters.
-template <int NV>
-__device__ __forceinline__ double rms_norm(const double (&x)[NV])
-{
-    double s = 0.0;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) s = fma(x[i], x[i], s);
-    return sqrt(s) / sqrt((double)NV);
-}
-
 // err^(-1/(q+1)) for the step-size factor.  Only the *size* of the next step depends on it (never the
 // accept/reject decision, taken on err in full double precision), so single precision through the
 // MUFU units is ample; the result is clamped to [0.2, 10] by the caller.

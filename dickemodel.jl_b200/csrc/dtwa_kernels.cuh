@@ -440,76 +440,33 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
                                     valid, k, w, nullptr);
         };
 
+        if constexpr (FIXED) {
         for (int k0 = 0; k0 < nt; k0 += W) {
             const int nw = min(W, nt - k0);
-            if constexpr (FIXED) {
-                // all lanes take the same steps: advance together, reduce with warp shuffles
-                for (int w = 0; w < nw; ++w) {
-                    const int k = k0 + w;
-                    warp_iters += T.advance(A.S, k);
-                    if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
-                    if (T.status != ST_OK && T.status != ST_INACTIVE && !failed_reported) report_failure(k);
-                    const bool valid = (T.status == ST_OK) && (k >= start_k);
-                    reduce_at(valid, k, w);
-                    // fixed step: V.nvalid counts the threads that do NOT contribute (failed, inactive tail,
-                    // before start_k), so the common all-valid case costs one vote and no shared-memory atomic
-                    const unsigned inv = __ballot_sync(0xffffffffu, !valid);
-                    if (inv && lane == 0) atomicAdd(&V.nvalid[w], (unsigned)__popc(inv));
-                }
-            } else {
-                // Flat loop: in every iteration each lane that still owes a step attempts ONE step, and
-                // lanes that have reached their next output time emit it.  Lanes progress through the
-                // window's output times independently, so a lane that needs fewer steps in one interval
-                // is not idle while the others finish it; they only wait for each other at the window end.
-                int k = k0;
-                const int kend = k0 + nw;
-                double tstop = A.S.ts[k0];
-                uint32_t iters = 0;
-#pragma unroll 1
-                while (true) {
-                    const bool act = (T.status == ST_OK) && (k < kend);
-                    if (!__any_sync(0xffffffffu, act)) break;
-                    ++iters;
-                    if (act) {
-                        if (T.ad.t < tstop) {
-                            if ((long long)(T.nacc + T.nrej) >= A.S.maxiters) {
-                                T.status = ST_MAXITERS;
-                            } else {
-                                bool accepted;
-                                if (T.ad.attempt(A.S.par, T.u, tstop, A.S.tol, A.S.dtmin, accepted)) T.status = ST_DOMAIN;
-                                if (accepted)
-                                    ++T.nacc;
-                                else if (T.status == ST_OK)
-                                    ++T.nrej;
-                            }
-                        }
-                        if (T.status == ST_OK && !(T.ad.t < tstop)) {
-                            const bool valid = (k >= start_k);
-                            reduce_at(valid, k, k - k0);
-                            if (valid) atomicAdd(&V.nvalid[k - k0], 1u);
-                            ++k;
-                            if (k < kend) tstop = A.S.ts[k];
-                        }
-                    }
-                }
-                warp_iters += iters;
+            // all lanes take the same steps: advance together, reduce with warp shuffles
+            for (int w = 0; w < nw; ++w) {
+                const int k = k0 + w;
+                warp_iters += T.advance(A.S, k);
+                if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
                 if (T.status != ST_OK && T.status != ST_INACTIVE && !failed_reported) report_failure(k);
+                const bool valid = (T.status == ST_OK) && (k >= start_k);
+                reduce_at(valid, k, w);
+                // fixed step: V.nvalid counts the threads that do NOT contribute (failed, inactive tail,
+                // before start_k), so the common all-valid case costs one vote and no shared-memory atomic
+                const unsigned inv = __ballot_sync(0xffffffffu, !valid);
+                if (inv && lane == 0) atomicAdd(&V.nvalid[w], (unsigned)__popc(inv));
             }
             // ---- once per window: CTA-wide flush in a fixed order (deterministic sums) ----
             __syncthreads();
             for (int i = threadIdx.x; i < nw * A.nslots; i += blockDim.x) {
                 const int w = i / A.nslots, sl = i - w * A.nslots;
                 double s = 0.0;
-                for (int rw = 0; rw < rows; ++rw) {
-                    double *cell = &V.wsum[((size_t)rw * W + w) * A.nslots + sl];
-                    s = __dadd_rn(s, *cell);
-                    if constexpr (PERLANE) *cell = 0.0;  // a lane that failed or finished early leaves zeros behind
-                }
+                for (int rw = 0; rw < rows; ++rw) s = __dadd_rn(s, V.wsum[((size_t)rw * W + w) * A.nslots + sl]);
                 // only this CTA ever adds to its partial row: RED in program order => reproducible
                 atomicAdd(&my_partial[(size_t)(k0 + w) * A.nslots + sl], s);
             }
             for (int w = threadIdx.x; w < nw; w += blockDim.x) {
-                const unsigned c = FIXED ? blockDim.x - V.nvalid[w] : V.nvalid[w];
+                const unsigned c = blockDim.x - V.nvalid[w];
                 if (c) atomicAdd(&nvalid_g[k0 + w], (unsigned long long)c);
                 V.nvalid[w] = 0u;
             }
@@ -527,6 +484,91 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
                 }
             }
             __syncthreads();
+        }
+        } else {
+            // Adaptive pairs: ONE warp per CTA (the host launches 32 threads).  Flat loop: in every iteration each
+            // lane that still owes a step attempts ONE step, and lanes that have reached their next output time
+            // emit it into their own staging row, a ring of W output times.  The ring is flushed in halves: the
+            // older half as soon as every lane has passed it.  A lane therefore only waits when it is more than
+            // W/2 .. W outputs ahead of the slowest lane -- the spread of a random walk, which stays below that for
+            // hundreds of outputs -- instead of at every window boundary.
+            const int H = (W >= 2) ? W / 2 : 1, R = (W >= 2) ? 2 * H : 1;   // half and ring size
+            int k = 0, flushed = 0;
+            double tstop = A.S.ts[0];
+            uint32_t iters = 0;
+            int fail_k = (T.status != ST_OK && T.status != ST_INACTIVE) ? 0 : -1;   // 0: bad initial condition
+            auto flush_half = [&](int f0, int f1) {   // outputs [f0, f1), executed by the whole warp, fixed order
+                __syncwarp();
+                for (int i = lane; i < (f1 - f0) * A.nslots; i += 32) {
+                    const int kq = f0 + i / A.nslots, sl = i % A.nslots, w = kq % R;
+                    double s = 0.0;
+                    for (int rw = 0; rw < 32; ++rw) {
+                        double *cell = &V.wsum[((size_t)rw * W + w) * A.nslots + sl];
+                        s = __dadd_rn(s, *cell);
+                        *cell = 0.0;  // a lane that failed or finished early leaves zeros behind
+                    }
+                    atomicAdd(&my_partial[(size_t)kq * A.nslots + sl], s);
+                }
+                for (int kq = f0 + lane; kq < f1; kq += 32) {
+                    const unsigned c = V.nvalid[kq % R];
+                    if (c) atomicAdd(&nvalid_g[kq], (unsigned long long)c);
+                    V.nvalid[kq % R] = 0u;
+                }
+                for (int hI = 0; hI < A.nhist; ++hI) {
+                    const HistDesc h = V.hists[hI];
+                    if (h.staged_off < 0) continue;
+                    for (int i = lane; i < (f1 - f0) * h.n0; i += 32) {
+                        const int kq = f0 + i / h.n0, b = i % h.n0;
+                        unsigned *cell = V.stage + (size_t)(kq % R) * A.stage_bins + h.staged_off + b;
+                        const unsigned c = *cell;
+                        if (c) {
+                            atomicAdd(&A.u64[h.base + (long long)kq * h.tstride + b], (unsigned long long)c);
+                            *cell = 0u;
+                        }
+                    }
+                }
+                __syncwarp();
+            };
+#pragma unroll 1
+            while (flushed < nt) {
+                const int fend = min(flushed + H, nt);   // the older half of the ring ends here
+#pragma unroll 1
+                while (true) {
+                    // the slowest lane decides when it can be flushed (finished and failed lanes hold nothing back)
+                    const int kmine = (T.status == ST_OK && k < nt) ? k : nt;
+                    if (__reduce_min_sync(0xffffffffu, kmine) >= fend) break;
+                    ++iters;
+                    const bool act = (T.status == ST_OK) && (k < nt) && (k < flushed + R);
+                    if (act) {
+                        if (T.ad.t < tstop) {
+                            if ((long long)(T.nacc + T.nrej) >= A.S.maxiters) {
+                                T.status = ST_MAXITERS;
+                            } else {
+                                bool accepted;
+                                if (T.ad.attempt(A.S.par, T.u, tstop, A.S.tol, A.S.dtmin, accepted)) T.status = ST_DOMAIN;
+                                if (accepted)
+                                    ++T.nacc;
+                                else if (T.status == ST_OK)
+                                    ++T.nrej;
+                            }
+                        }
+                        if (T.status == ST_OK && !(T.ad.t < tstop)) {
+                            const bool valid = (k >= start_k);
+                            reduce_at(valid, k, k % R);
+                            if (valid) atomicAdd(&V.nvalid[k % R], 1u);
+                            ++k;
+                            if (k < nt) tstop = A.S.ts[k];
+                        }
+                        if (T.status != ST_OK && fail_k < 0) fail_k = k;
+                    }
+                }
+                flush_half(flushed, fend);
+                flushed += H;
+            }
+            warp_iters += iters;
+            // (reported after the loop: the lambda captures the trajectory by reference, and calling it inside the
+            //  loop makes the compiler keep the whole state in local memory)
+            if (fail_k >= 0 && !failed_reported) report_failure(fail_k);
         }
         // ---- step counters: one atomic per warp per batch ----
         const unsigned long long a = __reduce_add_sync(0xffffffffu, T.nacc);
