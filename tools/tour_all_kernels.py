@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""A small tour of every kernel for compute-sanitizer (memcheck / racecheck / synccheck), sizes chosen so that
-the instrumented run takes about a minute:  compute-sanitizer --tool racecheck python tools/sanitize_case.py"""
+"""A small tour of every kernel of libdicketwa (ensemble chains with all reducer kinds under the interpreter and the
+NVRTC specialisation, integrate, fundamental matrix, Lyapunov, sections, shell quadrature, sample/pdf) at sizes that
+finish in seconds -- a smoke run for a new box or a new build (compute-sanitizer is closed on this pool)."""
 import os
 import sys
 
