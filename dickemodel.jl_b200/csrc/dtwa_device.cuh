@@ -665,12 +665,17 @@ __device__ __noinline__ double pdf_hw(double q0, double p0, double hbar, double 
 }
 __device__ __noinline__ double pdf_su2(double Q0, double P0, double hbar, double Q, double P)
 {
+    // src/TWA.jl:719-736: W = N(Theta; 0, sigma) sqrt(2 pi) sigma / (2 pi sigma^2) with Theta the angle between the
+    // Bloch vectors of (Q,P) and of the centre, cos(Theta) = cos(th) cos(th0) + sin(th) sin(th0) cos(ph - ph0).
+    // With cos(th) = 1 - R/2, sin(th) (cos ph, sin ph) = sqrt(1 - R/4) (Q, -P), R = Q^2 + P^2 (src/PhaseSpaces.jl:49,63)
+    // that is  a a0 + (Q Q0 + P P0) sqrt((1 - R/4)(1 - R0/4)) : one sqrt instead of two acos, two atan2 and six
+    // sin/cos -- this runs for every trajectory at every output time of survival_probability.  0.0 where the
+    // reference's try/catch swallows an acos DomainError.
     const double sigma = sqrt(hbar / 2.0);
-    const double a = 1.0 - (Q * Q + P * P) / 2.0;
-    if (!(a >= -1.0 && a <= 1.0)) return 0.0;
-    const double th = acos(a), ph = phi_of_QP(Q, P);
-    const double th0 = theta_of_QP(Q0, P0), ph0 = phi_of_QP(Q0, P0);
-    const double c = cos(th) * cos(th0) + sin(th) * sin(th0) * cos(ph - ph0);
+    const double R = Q * Q + P * P, R0 = Q0 * Q0 + P0 * P0;
+    const double a = 1.0 - R / 2.0, a0 = 1.0 - R0 / 2.0;
+    if (!(a >= -1.0 && a <= 1.0) || !(a0 >= -1.0 && a0 <= 1.0)) return 0.0;
+    const double c = a * a0 + (Q * Q0 + P * P0) * sqrt((1.0 - R / 4.0) * (1.0 - R0 / 4.0));
     if (!(c >= -1.0 && c <= 1.0)) return 0.0;
     const double T = acos(c);
     const double g = exp(-(T * T) / (2.0 * sigma * sigma)) / (sqrt(2.0 * DTWA_PI) * sigma);
