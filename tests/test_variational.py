@@ -315,3 +315,22 @@ def test_edge_cases_of_the_widened_entry_points(ctx, pkg):
     # a section that is never reached
     et, eu, ed, cnt, ue, st, ns, ms = ctx.integrate_events(sd, sol, u0[[0, 2]], 5.0, [0, 1, 0, 0], offset=50.0, max_events=4)
     assert (cnt == 0).all() and np.isnan(et).all()
+
+
+@pytest.mark.gpu
+def test_docs_fotoc_example_grows_at_twice_the_lyapunov_exponent(pkg):
+    """docs/src/TWAExamples.md:300-335 end to end: FOTOC = sum of the variances of Q,q,P,p (adaptive, tol=1e-8) starts at
+    2ħ and grows like exp(2λt) with λ = lyapunov_exponent(system, x)"""
+    from dickemodel_jl_b200 import ClassicalDicke as CD, ClassicalSystems as CS, TWA
+    system = CD.ClassicalDickeSystem(w=1.0, g=1.0, w0=1.0)
+    ts = TWA.jrange(0, 0.1, 20)
+    j = 1000
+    x = CD.Point(system, Q=1, P=0, p=0, ϵ=-0.6)
+    W = TWA.coherent_Wigner_HWxSU2(x, j=j, seed=5)
+    fotoc = np.array([np.sum(v) for v in TWA.variance(system, observable=["Q", "q", "P", "p"], distribution=W, N=10000, ts=ts, tol=1e-8)])
+    lam = CS.lyapunov_exponent(system, x, verbose=False)
+    assert abs(fotoc[0] / (2 / j) - 1) < 0.1            # docs/src/TWAExamples.md:334: 2ħ at t = 0
+    assert 0.2 < lam < 0.45
+    tt = np.asarray(ts)
+    slope = np.log(fotoc[60] / fotoc[20]) / (tt[60] - tt[20])
+    assert abs(slope / (2 * lam) - 1) < 0.25, (slope, lam)
