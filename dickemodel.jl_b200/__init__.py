@@ -11,8 +11,8 @@ fallback: importing works anywhere, computing needs the built library and a B200
 """
 from . import _lib  # noqa: F401
 from . import symbolic, PhaseSpaces, ClassicalSystems, ClassicalDicke, ClassicalLMG, TWA, distributed  # noqa: F401
-from . import EnergyShellProjections  # noqa: F401
+from . import EnergyShellProjections, DickeBCE  # noqa: F401
 from ._lib import Context, DtwaError, default_context, set_default_context, set_distributed, load as load_library  # noqa: F401
 
-__all__ = ["ClassicalSystems", "ClassicalDicke", "ClassicalLMG", "PhaseSpaces", "TWA", "EnergyShellProjections", "symbolic", "Context",
+__all__ = ["ClassicalSystems", "ClassicalDicke", "ClassicalLMG", "PhaseSpaces", "TWA", "EnergyShellProjections", "DickeBCE", "symbolic", "Context",
            "DtwaError", "default_context", "set_default_context", "set_distributed", "load_library"]

@@ -233,3 +233,19 @@ def test_sharded_ensemble_world_size_2_gloo(tmp_path, pkg):
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
     assert '"ok": true' in line and '"total": 600' in line
     assert pkg.distributed.shard_bounds(10, 0, 4) == (0, 3) and pkg.distributed.shard_bounds(10, 3, 4) == (9, 10)
+
+
+def test_quantum_dicke_system_delegates_to_the_classical_one(pkg):
+    """src/DickeBCE.jl:51-72: the carrier every classical function accepts"""
+    from dickemodel_jl_b200 import ClassicalDicke as CD, DickeBCE
+    cs = CD.ClassicalDickeSystem(w0=1, w=0.8, g=0.9)
+    qs = DickeBCE.QuantumDickeSystem(cs, j=30, Nmax=120)
+    assert qs.parameters() == cs.parameters() and qs.varnames() == cs.varnames() and qs.j == 30
+    assert qs._c_system().kind == cs._c_system().kind and list(qs._c_system().params)[:3] == [1.0, 0.8, 0.9]
+    assert CD.minimum_energy(qs) == CD.minimum_energy(cs)
+    q2 = DickeBCE.QuantumDickeSystem(j=2.5, w0=1, w=1, g=1)
+    assert q2.j == 2.5 and q2.parameters() == [1.0, 1.0, 1.0]
+    with pytest.raises(ValueError, match="half-integer"):
+        DickeBCE.QuantumDickeSystem(cs, j=0.3)
+    with pytest.raises(ValueError, match="Nmax"):
+        DickeBCE.QuantumDickeSystem(cs, j=3, Nmax=0)
