@@ -306,11 +306,21 @@ def lyapunov_spectrum(system, x, t=100, *, λtol=1e-4, λreltol=1e-3, maxiters=1
         raise ValueError(f"u₀ should have length {len(system.varnames())}, which is the dimension of the phase space of system")
     if system.out_of_bounds(x):
         raise ValueError(f"The initial condition u₀={x.tolist()} is out of bounds")
+    callback = kargs.pop("callback", None)
     lam, status = lyapunov_spectrum_batch(system, x[None, :], t, λtol=λtol, λreltol=λreltol, maxiters=maxiters, **kargs)
     if status[0] == _lib.LYAP_MAXITERS:
         raise RuntimeError("Maximum iterations")   # :223
     if status[0] != _lib.TRAJ_OK:
         raise RuntimeError(f"integration failed: {_RETCODES[int(status[0])]}")
+    if callback is not None:
+        # docs/src/ClassicalDickeExamples.md:196-202 pass the section callback through lyapunov_exponent to collect the
+        # orbit's Poincare points.  Here the orbit is integrated once more, without its fundamental matrix, over the
+        # same total time (rounds x t) with the event kernel: the same orbit, up to the divergence of a chaotic
+        # trajectory under a different step sequence.
+        rounds = int(last_lyapunov_info["iterations"][0])
+        saved = dict(last_lyapunov_info)
+        integrate(system, x, rounds * float(t), callback=callback, **kargs)
+        last_lyapunov_info.update(saved)
     return lam[0]
 
 

@@ -334,3 +334,29 @@ def test_docs_fotoc_example_grows_at_twice_the_lyapunov_exponent(pkg):
     tt = np.asarray(ts)
     slope = np.log(fotoc[60] / fotoc[20]) / (tt[60] - tt[20])
     assert abs(slope / (2 * lam) - 1) < 0.25, (slope, lam)
+
+
+@pytest.mark.gpu
+def test_docs_lyapunov_map_step_with_section_callback(pkg):
+    """docs/src/ClassicalDickeExamples.md:180-202: lyapunov_exponent(..., callback=ContinuousCallback(p = 0, save)) returns the
+    exponent and fills `pts` with the orbit's Poincare points on the q+ sheet"""
+    from dickemodel_jl_b200 import ClassicalDicke as CD, ClassicalSystems as CS
+    system = CD.ClassicalDickeSystem(w=0.8, g=0.8, w0=1)
+    eps = -1.35
+    pts = []
+
+    def save(state):
+        if CD.q_sign(system, state.u, eps) == "+":
+            Q, q, P, p = state.u
+            pts.append((Q, P))
+    callback = CS.ContinuousCallback(lambda x, t, _: x[3], save, save_positions=(False, False), abstol=1e-3)
+    Q0 = 0.5 * (CD.minimum_nonnegative_Q_for_ϵ(system, eps) + CD.maximum_Q_for_ϵ(system, eps))
+    point = CD.Point(system, Q=Q0, P=0.1, p=0, ϵ=eps)
+    lam = CS.lyapunov_exponent(system, point, verbose=False, tol=1e-8, λtol=0.00005, callback=callback)
+    assert 0.0 <= lam < 0.2 and len(pts) > 20
+    rounds = int(CS.last_lyapunov_info["iterations"][0])
+    assert rounds >= 2
+    Qlo, Qhi, Pm = CD.minimum_nonnegative_Q_for_ϵ(system, eps), CD.maximum_Q_for_ϵ(system, eps), CD.maximum_P_for_ϵ(system, eps)
+    arr = np.array(pts)
+    assert (np.abs(arr[:, 0]) <= Qhi + 1e-9).all() and (np.abs(arr[:, 1]) <= Pm + 1e-9).all()
+    assert lam == CS.lyapunov_exponent(system, point, verbose=False, tol=1e-8, λtol=0.00005)
