@@ -74,7 +74,7 @@ struct DevCtx {
     int sm_count = 0, clock_khz = 0, cc = 0;
     char name[256] = {0};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    DevBuf partial, meta, u0, fail[2], scratch_a, scratch_b, scratch_c;
+    DevBuf partial, meta, u0, fail[2], scratch_a, scratch_b, scratch_c, ring;
 };
 
 // NCCL, loaded lazily (only a multi-device context needs it)
@@ -912,6 +912,7 @@ struct dtwa_plan {
 struct LaunchShape {
     int block, grid, window;
     size_t smem;
+    double *ring;   // adaptive kernels: per-lane ring of observable values in global memory (L2-resident)
 };
 
 static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const EnsArgs &A, long long n, LaunchShape &ls)
@@ -921,18 +922,17 @@ static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const 
     int block = ctx->block_threads ? ctx->block_threads : 256;
     if (block > max_threads) block = max_threads;
     if (!fixed) block = 32;   // adaptive kernels: one warp per CTA (warp-level sliding flush, see ensemble_body)
-    // window: output times staged in shared memory between two CTA-wide flushes (<= 24 KB of staging)
-    // window: output times staged in shared memory between two CTA-wide flushes (<= 24 KB of staging)
-    const int rows = fixed ? block / 32 : block;  // staging rows: one per warp (fixed step) or per thread (adaptive)
-    const size_t per_out = sizeof(double) * rows * (A.nslots > 0 ? A.nslots : 1) + sizeof(unsigned) * A.stage_bins + sizeof(unsigned);
-    // (adaptive kernels profit from long windows: the lanes' step counts average out before they wait for each
-    //  other; fixed step: 16 -> 32 outputs per barrier is worth 0.6 %, measured)
-    size_t wcap = fixed ? 32 : 64, wbudget = fixed ? 24 * 1024 : 16 * 1024;
+    // window: output times staged between two flushes.  Fixed step: one row per warp in shared memory (<= 24 KB),
+    // one CTA-wide flush per window (16 -> 32 outputs per barrier is worth 0.6 %, measured).  Adaptive: one row per
+    // lane; the ring lives in global memory (it stays in L2: a lane writes 8 B per observable and output time) so
+    // that it can be long -- lanes only wait for each other when they drift more than half a ring apart.
+    const size_t slots = A.nslots > 0 ? A.nslots : 1;
+    const int rows = fixed ? block / 32 : 0;   // rows of the shared-memory staging
+    const size_t per_out = sizeof(double) * rows * slots + sizeof(unsigned) * A.stage_bins + sizeof(unsigned);
+    size_t wcap = fixed ? 32 : 256, wbudget = 24 * 1024;
     if (const char *e = std::getenv("DTWA_WINDOW")) wcap = (size_t)std::max(1, std::atoi(e));  // tuning experiments
     int window = (int)std::max<size_t>(1, std::min<size_t>({wcap, (size_t)A.S.nt, wbudget / per_out}));
-    if (!fixed && window > 1) window &= ~1;   // the adaptive ring is flushed in two halves
-    const size_t smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, rows, window);
-    ls.window = window;
+    size_t smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, rows, window);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
@@ -940,8 +940,22 @@ static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const 
     if (ctx->ctas_per_sm > 0 && ctx->ctas_per_sm < per_sm) per_sm = ctx->ctas_per_sm;
     long long want = (n + block - 1) / block;
     long long cap = (long long)d.sm_count * per_sm;
+    const int grid = (int)std::max(1ll, std::min(want, cap));
+    ls.ring = nullptr;
+    if (!fixed) {
+        // ring length: even, <= wcap, and the whole ring buffer <= 1 GiB
+        const size_t per_ring_out = sizeof(double) * 32 * slots * (size_t)grid;
+        window = (int)std::max<size_t>(1, std::min<size_t>((size_t)window, ((size_t)1 << 30) / per_ring_out));
+        if (window > 1) window &= ~1;
+        if (A.nslots > 0) {
+            TRY(d.ring.ensure(per_ring_out * (size_t)window));
+            ls.ring = (double *)d.ring.p;
+        }
+        smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, rows, window);
+    }
+    ls.window = window;
     ls.block = block;
-    ls.grid = (int)std::max(1ll, std::min(want, cap));
+    ls.grid = grid;
     ls.smem = smem;
     return 0;
 }
@@ -950,6 +964,7 @@ static int launch_ens(DevCtx &d, const void *kern, const EnsArgs &A0, const Laun
 {
     EnsArgs A = A0;
     A.window = ls.window;
+    A.ring = ls.ring;
     void *args[] = {(void *)&A};
     CK(cudaLaunchKernel(kern, dim3(ls.grid), dim3(ls.block), args, ls.smem, d.stream));
     return 0;
@@ -1055,7 +1070,8 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
                     H.n1 = 1;
                     H.tstride = rd.len;
                     L.counts_len = (int64_t)nt * rd.len;
-                    if (stage_bins + H.n0 <= STAGE_BUDGET_BINS) {
+                    // (adaptive kernels keep a long ring of output times per lane and bin straight into the arena)
+                    if (fixed && stage_bins + H.n0 <= STAGE_BUDGET_BINS) {
                         H.staged_off = stage_bins;
                         stage_bins += H.n0;
                     }

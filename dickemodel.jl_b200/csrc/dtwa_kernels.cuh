@@ -153,6 +153,7 @@ struct EnsArgs {
     const double *consts;
     const RangeD *ranges;
     const HistDesc *hists;
+    double *ring;             // adaptive kernels: [grid][32 lanes][window][nslots] staging ring (global memory), or NULL
     double *partial;          // [grid][nt][nslots]
     unsigned long long *u64;  // [CNT_N | n_valid[nt] | histograms...]
 };
@@ -345,7 +346,7 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
     constexpr bool FIXED = is_fixed<ALG>::value;
     constexpr bool PERLANE = !FIXED;  // adaptive: one staging row per thread, no warp-level reduction
     const int nwarps = blockDim.x >> 5;
-    const int rows = PERLANE ? (int)blockDim.x : nwarps;
+    const int rows = PERLANE ? 0 : nwarps;   // rows of the shared-memory staging (adaptive kernels stage in A.ring)
     const int lane = threadIdx.x & 31;
     const int W = A.window;
 
@@ -372,8 +373,11 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
         for (int i = threadIdx.x; i < A.nins; i += blockDim.x) prog[i] = A.prog[i];
         for (int i = threadIdx.x; i < W * A.stage_bins; i += blockDim.x) V.stage[i] = 0u;
         for (int i = threadIdx.x; i < W; i += blockDim.x) V.nvalid[i] = 0u;
-        if constexpr (PERLANE)
-            for (int i = threadIdx.x; i < rows * W * A.nslots; i += blockDim.x) V.wsum[i] = 0.0;
+        if constexpr (PERLANE) {   // one row per lane, in global memory (stays in L2)
+            V.wsum = A.ring + (size_t)blockIdx.x * 32 * W * A.nslots;
+            if (A.nslots > 0)
+                for (int i = threadIdx.x; i < 32 * W * A.nslots; i += blockDim.x) V.wsum[i] = 0.0;
+        }
         V.consts = consts;
         V.ranges = ranges;
         V.hists = hists;
@@ -488,10 +492,10 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
         } else {
             // Adaptive pairs: ONE warp per CTA (the host launches 32 threads).  Flat loop: in every iteration each
             // lane that still owes a step attempts ONE step, and lanes that have reached their next output time
-            // emit it into their own staging row, a ring of W output times.  The ring is flushed in halves: the
-            // older half as soon as every lane has passed it.  A lane therefore only waits when it is more than
-            // W/2 .. W outputs ahead of the slowest lane -- the spread of a random walk, which stays below that for
-            // hundreds of outputs -- instead of at every window boundary.
+            // emit it into their own staging row, a ring of W <= 256 output times in global memory (A.ring; 8 B per
+            // observable and output, it stays in L2).  The ring is flushed in halves: the older half as soon as
+            // every lane has passed it.  A lane therefore only waits when it is more than W/2 .. W outputs ahead of
+            // the slowest lane -- the spread of a random walk -- instead of at every window boundary.
             const int H = (W >= 2) ? W / 2 : 1, R = (W >= 2) ? 2 * H : 1;   // half and ring size
             int k = 0, flushed = 0;
             double tstop = A.S.ts[0];
