@@ -191,6 +191,26 @@ __host__ __device__ inline size_t ens_smem_bytes(int ncst, int nrange, int nhist
     return (b + 15) & ~size_t(15);
 }
 
+// The transcendental operations of the VM, behind a call: inlined into the interpreter's switch they spread its
+// cases over tens of KB of code, and a small latency-bound ensemble then waits for the instruction cache at
+// almost every VM instruction.  (Same libdevice routines as the inlined / specialised forms: same bits.)
+__device__ __noinline__ double vm_slow_math(int op, double t, double acc)
+{
+    switch (op) {
+    case OP_POW: return pow(t, acc);
+    case OP_ATAN2: return atan2(t, acc);
+    case OP_SIN: return sin(acc);
+    case OP_COS: return cos(acc);
+    case OP_TAN: return tan(acc);
+    case OP_EXP: return exp(acc);
+    case OP_LOG: return log(acc);
+    case OP_ACOS: return acos(acc);
+    case OP_ASIN: return asin(acc);
+    case OP_ATAN: return atan(acc);
+    default: return acc;
+    }
+}
+
 // Evaluate the reducer program for one thread at output index k (slot w of the current window).
 // Control flow is uniform across the CTA (the program is shared); `valid` masks this thread's
 // contributions.  Accumulator + 4 stack entries live in registers.
@@ -243,8 +263,8 @@ __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp,
         case OP_SUB: VM_POP(t); acc = __dsub_rn(t, acc); break;
         case OP_MUL: VM_POP(t); acc = __dmul_rn(t, acc); break;
         case OP_DIV: VM_POP(t); acc = __ddiv_rn(t, acc); break;
-        case OP_POW: VM_POP(t); acc = pow(t, acc); break;
-        case OP_ATAN2: VM_POP(t); acc = atan2(t, acc); break;
+        case OP_POW:
+        case OP_ATAN2: VM_POP(t); acc = vm_slow_math(in.op, t, acc); break;
         case OP_MIN: VM_POP(t); acc = fmin(t, acc); break;
         case OP_MAX: VM_POP(t); acc = fmax(t, acc); break;
         case OP_ADDC: acc = __dadd_rn(acc, V.consts[in.b]); break;
@@ -264,15 +284,15 @@ __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp,
         case OP_CUBE: acc = __dmul_rn(__dmul_rn(acc, acc), acc); break;
         case OP_IPOW: acc = ipow_rn(acc, (int)(int16_t)in.b); break;
         case OP_SQRT: acc = __dsqrt_rn(acc); break;
-        case OP_SIN: acc = sin(acc); break;
-        case OP_COS: acc = cos(acc); break;
-        case OP_TAN: acc = tan(acc); break;
-        case OP_EXP: acc = exp(acc); break;
-        case OP_LOG: acc = log(acc); break;
+        case OP_SIN:
+        case OP_COS:
+        case OP_TAN:
+        case OP_EXP:
+        case OP_LOG:
+        case OP_ACOS:
+        case OP_ASIN:
+        case OP_ATAN: acc = vm_slow_math(in.op, 0.0, acc); break;
         case OP_ABS: acc = fabs(acc); break;
-        case OP_ACOS: acc = acos(acc); break;
-        case OP_ASIN: acc = asin(acc); break;
-        case OP_ATAN: acc = atan(acc); break;
         case OP_SUM: {
             double v = valid ? acc : 0.0;
             if constexpr (PERLANE) {
@@ -338,6 +358,185 @@ __device__ __forceinline__ void jit_reduce(const VmShared &V, const SamplerPar *
                                            const double x1, const double x2, const double x3, const bool valid, const int k,
                                            const int w);
 
+// Adaptive pairs: ONE warp per CTA (the host launches 32 threads).  Each lane integrates its own STREAM of
+// trajectories -- lane l of CTA c takes trajectories (c*32 + l) + m*gridDim*32, m = 0, 1, ... -- and numbers the output
+// times of the stream g = m*nt + k.  In every iteration of the flat loop each lane that owes a step attempts ONE
+// step; a lane that has reached its next output time emits it into its own row of a ring of R <= 256 outputs in
+// global memory (A.ring; 8 B per observable and output, it stays in L2) and, at the end of a trajectory, draws the
+// next one without waiting for the other lanes.  The ring is flushed in halves, in the order of g, as soon as the
+// slowest lane has passed a half: sums over the lanes in lane order, then one RED per (time, slot) into the CTA's
+// partial row -- the same values in the same order in every run.  A lane only waits when it is more than R/2 .. R
+// outputs ahead of the slowest lane of its warp.
+template <int SYS, int ALG, bool JIT>
+__device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared &V, double *my_partial,
+                                                unsigned long long *nvalid_g)
+{
+    constexpr int NV = Sys<SYS>::NV;
+    const int lane = threadIdx.x & 31;
+    const int nt = A.S.nt, W = A.window;
+    const int H = (W >= 2) ? W / 2 : 1, R = (W >= 2) ? 2 * H : 1;   // half and ring size
+    const long long stride = (long long)gridDim.x * 32;
+    long long j = (long long)blockIdx.x * 32 + lane;                  // current trajectory of this lane
+    long long g = 0, flushed = 0;                                     // stream positions: next output of this lane / flushed
+    int k = nt;                                                       // next output index of the current trajectory (nt: none)
+    int wslot = 0;                                                    // g % R, kept incrementally (no 64-bit division in the loop)
+    int start_k = 0;
+    uint64_t idx = 0;
+    bool have = false;                                                // a trajectory is in flight
+    double tstop = 0.0;
+    uint32_t iters = 0;
+    unsigned long long acc_steps = 0, rej_steps = 0;
+    Traj<SYS, ALG> T;
+    T.status = ST_INACTIVE;
+    T.nacc = T.nrej = 0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) T.u[i] = 0.0;
+
+    auto flush_half = [&](long long f0, long long f1) {   // stream outputs [f0, f1), executed by the whole warp, fixed order
+        __syncwarp();
+        const int cnt = (int)(f1 - f0), w0 = (int)(f0 % R), k0 = (int)(f0 % nt);
+        for (int i = lane; i < cnt * A.nslots; i += 32) {
+            const int o = i / A.nslots, sl = i % A.nslots, w = (w0 + o) % R, kq = (k0 + o) % nt;
+            double s = 0.0;
+            for (int rw = 0; rw < 32; ++rw) {
+                double *cell = &V.wsum[((size_t)rw * W + w) * A.nslots + sl];
+                s = __dadd_rn(s, *cell);
+                *cell = 0.0;  // lanes that failed, skipped or ran out of trajectories leave zeros behind
+            }
+            atomicAdd(&my_partial[(size_t)kq * A.nslots + sl], s);
+        }
+        for (int i = lane; i < cnt; i += 32) {
+            const int w = (w0 + i) % R;
+            const unsigned c = V.nvalid[w];
+            if (c) atomicAdd(&nvalid_g[(k0 + i) % nt], (unsigned long long)c);
+            V.nvalid[w] = 0u;
+        }
+        __syncwarp();
+    };
+
+#pragma unroll 1
+    while (true) {
+        // ================= service part (cold): new trajectories, failures, flushes =================
+        // a lane without a trajectory draws its next one (or retires)
+        if (!have && j < A.N) {
+            idx = (uint64_t)j;
+            start_k = 0;
+            if (A.redo) {
+                const FailRec r = A.redo[j];
+                idx = r.idx;
+                start_k = r.k;
+            }
+            acc_steps += T.nacc;
+            rej_steps += T.nrej;
+            T.status = ST_OK;
+            draw_initial<NV>(A.smp, idx, A.attempt, T.u);
+            T.begin(A.S);
+            have = true;
+            k = 0;
+            tstop = A.S.ts[0];
+        }
+        // failures end a trajectory: report, skip the rest of its outputs
+        if (have && T.status != ST_OK) {
+            bool queued = false;
+            if (T.status != ST_MAXITERS) {
+                atomicAdd(&A.u64[CNT_FAILED], 1ull);
+                if (A.fail_out && A.smp.kind != DTWA_SAMPLER_HOST_ARRAY && A.smp.kind != DTWA_SAMPLER_DEVICE_ARRAY) {
+                    const unsigned pos = atomicAdd(A.fail_count, 1u);
+                    if (pos < A.fail_cap) {
+                        FailRec r;
+                        r.idx = idx;
+                        r.k = k;
+                        r.pad = 0;
+                        A.fail_out[pos] = r;
+                        queued = true;
+                    }
+                }
+            }
+            if (!queued) atomicAdd(&A.u64[CNT_UNFINISHED], 1ull);
+            g += (long long)(nt - k);
+            wslot = (int)(((long long)wslot + (nt - k)) % R);
+            k = nt;
+        }
+        if (have && k >= nt) {   // trajectory finished (or abandoned): the next one is drawn in the following round
+            have = false;
+            j += stride;
+        }
+        // flush what every lane has passed; stop when nothing is left
+        {
+            const bool retired = !have && j >= A.N;
+            const long long ahead = retired ? (long long)0x7fffffff : g - flushed;
+            const int amin = __reduce_min_sync(0xffffffffu, (int)(ahead > 0x7fffffff ? 0x7fffffff : ahead));
+            if (amin == 0x7fffffff) {   // every lane has retired: flush the tail of the stream
+                const long long gend = __reduce_max_sync(0xffffffffu, (int)(g - flushed)) + flushed;
+                while (flushed < gend) {
+                    const long long f1 = (flushed + H < gend) ? flushed + H : gend;
+                    flush_half(flushed, f1);
+                    flushed = f1;
+                }
+                break;
+            }
+            if (amin >= H) {
+                flush_half(flushed, flushed + H);
+                flushed += H;
+            }
+        }
+        if (__any_sync(0xffffffffu, !have && j < A.N)) continue;   // somebody still has to draw
+        // ================= hot loop: one attempted step per lane and iteration =================
+        const long long glimit = flushed + R;
+#pragma unroll 1
+        while (true) {
+            // leave when a lane needs service or a half of the ring can be flushed
+            const bool service = have && (T.status != ST_OK || k >= nt);
+            const int ahead = (!have) ? 0x7fffffff : (int)(g - flushed);
+            if (__any_sync(0xffffffffu, service) || __reduce_min_sync(0xffffffffu, ahead) >= H) break;
+            ++iters;
+            if (have && g < glimit) {
+                if (T.ad.t < tstop) {
+                    if ((long long)(T.nacc + T.nrej) >= A.S.maxiters) {
+                        T.status = ST_MAXITERS;
+                    } else {
+                        bool accepted;
+                        if (T.ad.attempt(A.S.par, T.u, tstop, A.S.tol, A.S.dtmin, accepted)) T.status = ST_DOMAIN;
+                        if (accepted)
+                            ++T.nacc;
+                        else if (T.status == ST_OK)
+                            ++T.nrej;
+                    }
+                }
+                if (T.status == ST_OK && !(T.ad.t < tstop)) {
+                    const bool valid = (k >= start_k);
+                    const int w = wslot;
+                    if constexpr (JIT)
+                        jit_reduce<NV, true>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0, valid, k,
+                                             w);
+                    else
+                        vm_run<NV, true>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0, valid, k, w,
+                                         nullptr);
+                    if (valid) atomicAdd(&V.nvalid[w], 1u);
+                    ++k;
+                    ++g;
+                    wslot = (wslot + 1 == R) ? 0 : wslot + 1;
+                    if (k < nt) tstop = A.S.ts[k];
+                }
+            }
+        }
+    }
+    // ---- step counters: one atomic per warp ----
+    acc_steps += T.nacc;
+    rej_steps += T.nrej;
+    unsigned long long a = acc_steps, r = rej_steps;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        r += __shfl_xor_sync(0xffffffffu, r, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&A.u64[CNT_ACC], a);
+        if (r) atomicAdd(&A.u64[CNT_REJ], r);
+        atomicAdd(&A.u64[CNT_LANE], 32ull * iters);
+    }
+}
+
 template <int SYS, int ALG, bool JIT>
 __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
 {
@@ -393,7 +592,11 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
     double *my_partial = A.partial + (size_t)blockIdx.x * nt * A.nslots;
     unsigned long long *nvalid_g = A.u64 + CNT_N;
 
-    // ---- persistent loop over batches of blockDim.x trajectories ----
+    if constexpr (!FIXED) {
+        adaptive_stream<SYS, ALG, JIT>(A, V, my_partial, nvalid_g);
+        return;
+    }
+    // ---- fixed step: persistent loop over batches of blockDim.x trajectories ----
     for (long long batch = blockIdx.x; batch * (long long)blockDim.x < A.N; batch += gridDim.x) {
         const long long j = batch * (long long)blockDim.x + threadIdx.x;
         const bool active = j < A.N;
@@ -489,90 +692,6 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
             }
             __syncthreads();
         }
-        } else {
-            // Adaptive pairs: ONE warp per CTA (the host launches 32 threads).  Flat loop: in every iteration each
-            // lane that still owes a step attempts ONE step, and lanes that have reached their next output time
-            // emit it into their own staging row, a ring of W <= 256 output times in global memory (A.ring; 8 B per
-            // observable and output, it stays in L2).  The ring is flushed in halves: the older half as soon as
-            // every lane has passed it.  A lane therefore only waits when it is more than W/2 .. W outputs ahead of
-            // the slowest lane -- the spread of a random walk -- instead of at every window boundary.
-            const int H = (W >= 2) ? W / 2 : 1, R = (W >= 2) ? 2 * H : 1;   // half and ring size
-            int k = 0, flushed = 0;
-            double tstop = A.S.ts[0];
-            uint32_t iters = 0;
-            int fail_k = (T.status != ST_OK && T.status != ST_INACTIVE) ? 0 : -1;   // 0: bad initial condition
-            auto flush_half = [&](int f0, int f1) {   // outputs [f0, f1), executed by the whole warp, fixed order
-                __syncwarp();
-                for (int i = lane; i < (f1 - f0) * A.nslots; i += 32) {
-                    const int kq = f0 + i / A.nslots, sl = i % A.nslots, w = kq % R;
-                    double s = 0.0;
-                    for (int rw = 0; rw < 32; ++rw) {
-                        double *cell = &V.wsum[((size_t)rw * W + w) * A.nslots + sl];
-                        s = __dadd_rn(s, *cell);
-                        *cell = 0.0;  // a lane that failed or finished early leaves zeros behind
-                    }
-                    atomicAdd(&my_partial[(size_t)kq * A.nslots + sl], s);
-                }
-                for (int kq = f0 + lane; kq < f1; kq += 32) {
-                    const unsigned c = V.nvalid[kq % R];
-                    if (c) atomicAdd(&nvalid_g[kq], (unsigned long long)c);
-                    V.nvalid[kq % R] = 0u;
-                }
-                for (int hI = 0; hI < A.nhist; ++hI) {
-                    const HistDesc h = V.hists[hI];
-                    if (h.staged_off < 0) continue;
-                    for (int i = lane; i < (f1 - f0) * h.n0; i += 32) {
-                        const int kq = f0 + i / h.n0, b = i % h.n0;
-                        unsigned *cell = V.stage + (size_t)(kq % R) * A.stage_bins + h.staged_off + b;
-                        const unsigned c = *cell;
-                        if (c) {
-                            atomicAdd(&A.u64[h.base + (long long)kq * h.tstride + b], (unsigned long long)c);
-                            *cell = 0u;
-                        }
-                    }
-                }
-                __syncwarp();
-            };
-#pragma unroll 1
-            while (flushed < nt) {
-                const int fend = min(flushed + H, nt);   // the older half of the ring ends here
-#pragma unroll 1
-                while (true) {
-                    // the slowest lane decides when it can be flushed (finished and failed lanes hold nothing back)
-                    const int kmine = (T.status == ST_OK && k < nt) ? k : nt;
-                    if (__reduce_min_sync(0xffffffffu, kmine) >= fend) break;
-                    ++iters;
-                    const bool act = (T.status == ST_OK) && (k < nt) && (k < flushed + R);
-                    if (act) {
-                        if (T.ad.t < tstop) {
-                            if ((long long)(T.nacc + T.nrej) >= A.S.maxiters) {
-                                T.status = ST_MAXITERS;
-                            } else {
-                                bool accepted;
-                                if (T.ad.attempt(A.S.par, T.u, tstop, A.S.tol, A.S.dtmin, accepted)) T.status = ST_DOMAIN;
-                                if (accepted)
-                                    ++T.nacc;
-                                else if (T.status == ST_OK)
-                                    ++T.nrej;
-                            }
-                        }
-                        if (T.status == ST_OK && !(T.ad.t < tstop)) {
-                            const bool valid = (k >= start_k);
-                            reduce_at(valid, k, k % R);
-                            if (valid) atomicAdd(&V.nvalid[k % R], 1u);
-                            ++k;
-                            if (k < nt) tstop = A.S.ts[k];
-                        }
-                        if (T.status != ST_OK && fail_k < 0) fail_k = k;
-                    }
-                }
-                flush_half(flushed, fend);
-                flushed += H;
-            }
-            warp_iters += iters;
-            // (reported after the loop: the lambda captures the trajectory by reference, and calling it inside the
-            //  loop makes the compiler keep the whole state in local memory)
-            if (fail_k >= 0 && !failed_reported) report_failure(fail_k);
         }
         // ---- step counters: one atomic per warp per batch ----
         const unsigned long long a = __reduce_add_sync(0xffffffffu, T.nacc);
