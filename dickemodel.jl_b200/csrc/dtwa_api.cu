@@ -1120,6 +1120,18 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
     if (!fixed) jit_work = std::max(jit_work, (double)N * 8.0 * ts[nt - 1]);
     const bool want_jit = ctx->jit_mode == 1 || (ctx->jit_mode == 2 && jit_work >= 2e9);
     bool used_jit = want_jit;
+    if (!want_jit && ctx->jit_mode == 2 && std::getenv("DTWA_NO_BACKGROUND_JIT") == nullptr) {
+        // small call: never wait for NVRTC, but let a background thread specialise this reducer set; repeated calls
+        // (parameter scans) pick the specialised kernel up once it is ready -- same bits as the interpreter
+        cudaKernel_t jk;
+        CK(cudaSetDevice(ctx->devs[0].device));
+        const double wsigned = make_par(sys, sol->backwards).b;
+        const int wflag = (sys->kind == DTWA_SYS_DICKE && wsigned == 1.0) ? 1 : (sys->kind == DTWA_SYS_DICKE && wsigned == -1.0) ? -1 : 0;
+        if (jit_cache().get_async(sys->kind, sol->alg, wflag, prog, &jk) == 0) {
+            kern = (const void *)jk;
+            used_jit = true;
+        }
+    }
     if (want_jit) {
         cudaKernel_t jk;
         std::string jerr;

@@ -154,3 +154,25 @@ def test_full_size_properties_config2(ctx, mods, system):
         parts.append(TWA.calculate_distribution(system, x="t", y=jz, ys=TWA.jrange(-1.1, 0.01, 1.1), N=N // 2, ts=ts, distribution=Wp,
                                                 integrator_alg="RK4", dt=2.0 ** -7))
     assert np.array_equal(np.rint((parts[0] + parts[1]) * (N // 2)), np.rint(hist * N))
+
+
+def test_background_specialisation_takes_over_without_changing_a_bit(pkg, ctx):
+    """small calls never wait for NVRTC: the first one runs the interpreter kernel and starts a background compilation,
+    a later one picks the specialised kernel up; both produce the same bits"""
+    import time
+    from dickemodel_jl_b200 import TWA, ClassicalDicke as CD
+    ctx.set_jit(2)
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    ts = TWA.jrange(0, 0.5, 4)
+    obs = "Q*p - 0.37*q^2 + P"          # a reducer set no other test uses
+    runs = []
+    for attempt in range(40):
+        W = TWA.coherent_Wigner_HWxSU2([0.3, 0.1, -0.2, 0.4], j=50, seed=77)
+        out = TWA.average(system, observable=obs, N=3000, ts=ts, distribution=W, tol=1e-9)
+        runs.append((TWA.last_info["jit"], out.copy()))
+        if runs[-1][0] == 1:
+            break
+        time.sleep(0.25)
+    assert runs[0][0] == 0, "the first call must not wait for the compiler"
+    assert runs[-1][0] == 1, "the specialised kernel never became available"
+    assert all(np.array_equal(r[1], runs[0][1]) for r in runs)
