@@ -29,7 +29,7 @@ EXPORTS = ["dtwa_last_error", "dtwa_version", "dtwa_create", "dtwa_destroy", "dt
            "dtwa_hamiltonian", "dtwa_integrate", "dtwa_sample", "dtwa_pdf", "dtwa_eval_expr", "dtwa_scale_to_index",
            "dtwa_ensemble", "dtwa_ensemble_launch", "dtwa_plan_arenas", "dtwa_plan_fetch", "dtwa_plan_free",
            "dtwa_fp64_peak", "dtwa_fp64_peak_regs", "dtwa_set_jit", "dtwa_jit_compile", "dtwa_integrate_fm", "dtwa_lyapunov", "dtwa_integrate_events",
-           "dtwa_shell_quadrature"]
+           "dtwa_shell_quadrature", "dtwa_jit_quiesce"]
 
 
 class Event(C.Structure):
@@ -120,6 +120,9 @@ def load():
         L.dtwa_plan_free.argtypes = [vp]
         L.dtwa_fp64_peak.argtypes = [vp, dp, dp]
         L.dtwa_fp64_peak_regs.argtypes = [vp, dp, dp]
+        L.dtwa_jit_quiesce.argtypes = []
+        import atexit
+        atexit.register(L.dtwa_jit_quiesce)   # no thread may be inside libnvrtc when the process tears it down
         i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
         L.dtwa_integrate_fm.argtypes = [vp, C.POINTER(System), C.POINTER(Solver), dp, dp, C.c_int64, dp, C.c_int32, dp, dp, i32p, i64p]
         L.dtwa_integrate_events.argtypes = [vp, C.POINTER(System), C.POINTER(Solver), dp, C.c_int64, C.c_double, C.POINTER(Event),

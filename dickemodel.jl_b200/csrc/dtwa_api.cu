@@ -221,6 +221,12 @@ extern "C" int dtwa_set_jit(dtwa_ctx *ctx, int mode)
     return DTWA_OK;
 }
 
+extern "C" int dtwa_jit_quiesce(void)
+{
+    jit_cache().quiesce();
+    return DTWA_OK;
+}
+
 extern "C" int dtwa_set_launch(dtwa_ctx *ctx, int block_threads, int ctas_per_sm)
 {
     if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");

@@ -105,6 +105,9 @@ mutable struct Context
     end
 end
 const default_context = Ref{Union{Nothing,Context}}(nothing)
+# background specialisation threads must be idle before the process unloads libnvrtc
+atexit(() -> ccall((:dtwa_jit_quiesce, libdicketwa), Cint, ()))
+
 function context()
     # all visible GPUs of the box by default: the ensemble is sharded over them inside the library
     if default_context[] === nothing

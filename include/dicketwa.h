@@ -178,6 +178,11 @@ int dtwa_set_launch(dtwa_ctx *ctx, int block_threads, int ctas_per_sm);
  * reducer program inside the ahead-of-time kernel, mode 2 (default) specialises when N*nt >= 2e9.
  * Both paths execute the same correctly rounded operations in the same order: identical results. */
 int dtwa_set_jit(dtwa_ctx *ctx, int mode);
+/* Small calls are specialised by a background host thread (see dtwa_set_jit).  Call this before the process exits
+ * (atexit): it waits for compilations in flight and starts no new ones, so that no thread is inside libnvrtc while the
+ * process tears it down. */
+int dtwa_jit_quiesce(void);
+
 /* compile-only check of the specialisation for `nexpr` averaged observables (no GPU needed) */
 int dtwa_jit_compile(const dtwa_system *sys, const dtwa_solver *sol, const char *const *exprs, int32_t nexpr, char *src_out,
                      int64_t src_cap, int64_t *cubin_bytes);
