@@ -360,3 +360,39 @@ def test_docs_lyapunov_map_step_with_section_callback(pkg):
     arr = np.array(pts)
     assert (np.abs(arr[:, 0]) <= Qhi + 1e-9).all() and (np.abs(arr[:, 1]) <= Pm + 1e-9).all()
     assert lam == CS.lyapunov_exponent(system, point, verbose=False, tol=1e-8, λtol=0.00005)
+
+
+# ---------------------------------------------------------------- a pin from the reference's own closed forms
+def _normal_frequencies_from_phi(Phi, t):
+    ang = np.abs(np.angle(np.linalg.eigvals(Phi)))
+    return np.sort(ang)[[0, 2]] / t          # the spectrum is {exp(+-i Omega_A t), exp(+-i Omega_B t)}
+
+
+def test_oracle_linearisation_at_the_ground_state_has_the_references_normal_frequencies(O, pkg):
+    """src/ClassicalDicke.jl:139-147 (normal_frequency) and :164-177 (minimum_energy_point) are closed forms of the
+    reference; the fundamental matrix at that fixed point is exp(J t), so its eigenvalues are exp(+-i Omega t)"""
+    from dickemodel_jl_b200 import ClassicalDicke as CD
+    for par in ([1.0, 1.0, 1.0], [1.0, 0.8, 0.8], [2.0, 0.7, 1.3]):
+        system = CD.ClassicalDickeSystem(w0=par[0], w=par[1], g=par[2])
+        x0 = CD.minimum_energy_point(system)
+        want = sorted([CD.normal_frequency(system, "-"), CD.normal_frequency(system, "+")])
+        t = 0.5 * np.pi / want[1]
+        x, F, st, _ = O.integrate_fm(O.SYS_DICKE, par, [x0], [t], tol=1e-13)
+        assert st[0] == 0 and np.abs(x[0, 0] - x0).max() < 1e-12          # a fixed point stays put
+        got = _normal_frequencies_from_phi(F[0, 0], t)
+        assert np.abs(got - want).max() < 1e-9, (par, got, want)
+
+
+@pytest.mark.gpu
+def test_gpu_linearisation_at_the_ground_state_has_the_references_normal_frequencies(ctx, pkg):
+    from dickemodel_jl_b200 import ClassicalDicke as CD
+    for par in ([1.0, 1.0, 1.0], [1.0, 0.8, 0.8], [2.0, 0.7, 1.3]):
+        system = CD.ClassicalDickeSystem(w0=par[0], w=par[1], g=par[2])
+        x0 = CD.minimum_energy_point(system)
+        want = sorted([CD.normal_frequency(system, "-"), CD.normal_frequency(system, "+")])
+        t = 0.5 * np.pi / want[1]
+        for alg, kw in ((pkg._lib.ALG_DOP853, dict(tol=1e-13)), (pkg._lib.ALG_RK4, dict(dt=2.0 ** -9))):
+            x, F, st, _ = ctx.integrate_fm(csys(pkg, 0, par), csol(pkg, alg, **kw), [x0], [t])
+            assert st[0] == 0 and np.abs(x[0, 0] - x0).max() < 1e-11
+            got = _normal_frequencies_from_phi(F[0, 0], t)
+            assert np.abs(got - want).max() < 1e-8, (par, alg, got, want)
