@@ -10,7 +10,9 @@
  * arithmetic lives in un-vendored packages (OrdinaryDiffEq "5", DiffEqCallbacks "2",
  * Distributions "0.23, 0.25"; Project.toml:29-46).  What pins this oracle instead (see
  * oracle/make_golden.py, tests/golden/): 40-digit mpmath Taylor truth trajectories, SciPy
- * DOP853/RK45 runs of the same tableaux, energy conservation, time reversal and sampler moments.
+ * DOP853/RK45 runs of the same tableaux, energy conservation, time reversal and sampler moments; and,
+ * from the reference's own closed forms, the normal frequencies of src/ClassicalDicke.jl:139-147 (eigenvalues of
+ * the fundamental matrix at minimum_energy_point) and the shell volume of :110-124 (sum of the quadrature).
  *
  * Every function cites the reference file:line it restates (paths relative to /root/reference).
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off so that no FMA contraction happens and the
