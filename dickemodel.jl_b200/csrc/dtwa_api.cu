@@ -193,7 +193,7 @@ extern "C" int dtwa_destroy(dtwa_ctx *ctx)
     for (auto &d : ctx->devs) {
         cudaSetDevice(d.device);
         cudaStreamSynchronize(d.stream);
-        for (DevBuf *b : {&d.partial, &d.meta, &d.u0, &d.fail[0], &d.fail[1], &d.scratch_a, &d.scratch_b, &d.scratch_c}) b->release();
+        for (DevBuf *b : {&d.partial, &d.meta, &d.u0, &d.fail[0], &d.fail[1], &d.scratch_a, &d.scratch_b, &d.scratch_c, &d.ring}) b->release();
         for (auto &ev : d.ev)
             if (ev) cudaEventDestroy(ev);
         if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
