@@ -993,24 +993,32 @@ __global__ void __launch_bounds__(128) events_kernel(const SolverArgs S, const E
     double t = 0.0, g0 = (T.status == ST_OK) ? gfun(T.u) : 0.0;
     // the noted crossing of this lane
     bool pending = false;
-    double ps[NV], pts0 = 0.0, phs = 0.0, pg0 = 0.0, pg1 = 0.0;
+    // (step-start state, its time; the bracket [plo, phi] of step fractions -- in time units -- that holds the
+    //  crossing, and g at its ends: the whole step for an ordinary crossing, one side of the extremum for a tangency)
+    double ps[NV], pts0 = 0.0, plo = 0.0, phi = 0.0, pg0 = 0.0, pg1 = 0.0;
     auto refine = [&]() {   // executed by all lanes with a noted crossing at once
-        double th = phs * (pg0 / (pg0 - pg1));           // chord
+        double lo = plo, hi = phi, glo = pg0;
+        double th = lo + (hi - lo) * (pg0 / (pg0 - pg1));   // chord
         double z[NV], g2 = pg1;
-        if (pg1 == 0.0) th = phs;
+        if (pg1 == 0.0) th = hi;
 #pragma unroll 1
-        for (int it = 0; it < 6; ++it) {
+        for (int it = 0; it < 8; ++it) {
 #pragma unroll
             for (int i = 0; i < NV; ++i) z[i] = ps[i];
             own_step(z, th);
             g2 = gfun(z);
-            if (it == 5 || fabs(g2) <= 1e-13) break;
-            double f[NV], gd = 0.0;                       // Newton on the crossing time
+            if (it == 7 || fabs(g2) <= 1e-13) break;
+            if ((g2 < 0.0) == (glo < 0.0)) {              // keep the bracket
+                lo = th;
+                glo = g2;
+            } else
+                hi = th;
+            double f[NV], gd = 0.0;                       // Newton on the crossing time, bisection when it leaves the bracket
             Sys<SYS>::rhs(S.par, z, f);
 #pragma unroll
             for (int i = 0; i < NV; ++i) gd = fma(E.coef[i], f[i], gd);
-            const double tn = th - g2 / gd;
-            if (!(tn > 0.0) || !(tn <= phs)) break;
+            double tn = th - g2 / gd;
+            if (!(tn > lo) || !(tn < hi)) tn = 0.5 * (lo + hi);
             th = tn;
         }
         double y[NV + 1];
@@ -1043,11 +1051,15 @@ __global__ void __launch_bounds__(128) events_kernel(const SolverArgs S, const E
     bool done = !(T.status == ST_OK && E.t_end > 0.0);
 #pragma unroll 1
     while (__any_sync(0xffffffffu, !done)) {
-        bool cross = false, accepted = false;
-        double cs[NV], cts0 = 0.0, chs = 0.0, cg1 = 0.0;
+        bool cross = false, accepted = false, tang = false;
+        double cs[NV], cts0 = 0.0, chs = 0.0, cg1 = 0.0, gd0 = 0.0, thx = 0.0;
         if (!done) {
 #pragma unroll
             for (int i = 0; i < NV; ++i) cs[i] = T.u[i];
+            if constexpr (!FIXED) {   // dg/dt at the step start, from the FSAL derivative
+#pragma unroll
+                for (int i = 0; i < NV; ++i) gd0 = fma(E.coef[i], T.ad.k0[i], gd0);
+            }
             double t1 = t;
             if constexpr (FIXED) {
                 if constexpr (ALG == DTWA_ALG_RK4)
@@ -1086,6 +1098,33 @@ __global__ void __launch_bounds__(128) events_kernel(const SolverArgs S, const E
                 cts0 = t;
                 chs = t1 - t;
                 t = t1;
+                if constexpr (!FIXED) {
+                    // Tangency: no sign change over the step, but g turns round inside it (dg/dt changes sign) and the
+                    // cubic Hermite interpolant of g dips through zero at its extremum -> two crossings in this step.
+                    // (DiffEq samples `interp_points` inside every step for the same purpose.)
+                    double gd1 = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) gd1 = fma(E.coef[i], T.ad.k0[i], gd1);
+                    if (!up && !down && g0 * cg1 > 0.0 && gd0 * gd1 < 0.0) {
+                        const double d0 = chs * gd0, d1 = chs * gd1, dl = cg1 - g0;
+                        const double c2 = 3.0 * dl - 2.0 * d0 - d1, c3 = d0 + d1 - 2.0 * dl;   // g = g0 + d0 x + c2 x^2 + c3 x^3
+                        // g'(x) = d0 + 2 c2 x + 3 c3 x^2 = 0: the root in (0, 1)
+                        const double qa = 3.0 * c3, qb = 2.0 * c2, disc = qb * qb - 4.0 * qa * d0;
+                        double x = -1.0;
+                        if (disc >= 0.0) {
+                            const double sq = sqrt(disc), q = -0.5 * (qb + (qb >= 0.0 ? sq : -sq));
+                            const double x1 = (qa != 0.0) ? q / qa : -1.0, x2 = (q != 0.0) ? d0 / q : -1.0;
+                            x = (x1 > 0.0 && x1 < 1.0) ? x1 : x2;
+                        }
+                        if (x > 0.0 && x < 1.0) {
+                            const double gx = g0 + x * (d0 + x * (c2 + x * c3));
+                            if (gx * g0 < 0.0) {
+                                tang = true;
+                                thx = x * chs;
+                            }
+                        }
+                    }
+                }
             }
         }
         // refine the noted crossings together when a lane needs its slot again ...
@@ -1097,9 +1136,32 @@ __global__ void __launch_bounds__(128) events_kernel(const SolverArgs S, const E
 #pragma unroll
             for (int i = 0; i < NV; ++i) ps[i] = cs[i];
             pts0 = cts0;
-            phs = chs;
+            plo = 0.0;
+            phi = chs;
             pg0 = g0;
             pg1 = cg1;
+        }
+        if (tang) {   // rare: handled by the lane on its own, in time order
+            if (pending) refine();
+            double z[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) z[i] = cs[i];
+            own_step(z, thx);
+            const double gx = gfun(z);                    // the integrator's own value at the interpolant's extremum
+            if (gx * g0 < 0.0) {
+                const bool first_up = g0 < 0.0;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) ps[i] = cs[i];
+                pts0 = cts0;
+                if ((first_up && E.direction >= 0) || (!first_up && E.direction <= 0)) {
+                    plo = 0.0; phi = thx; pg0 = g0; pg1 = gx;
+                    refine();
+                }
+                if ((!first_up && E.direction >= 0) || (first_up && E.direction <= 0)) {
+                    plo = thx; phi = chs; pg0 = gx; pg1 = cg1;
+                    refine();
+                }
+            }
         }
         if (accepted) g0 = cg1;
         // ... or when every lane of the warp has finished

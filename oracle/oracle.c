@@ -1238,53 +1238,92 @@ typedef struct {
     double us[4], ts0; /* state and time at the start of the current step */
 } ev_ctx;
 
-static void ev_check(ev_ctx *c, const double *u, double t1)
+/* locate one crossing inside the bracket [lo, hi] (times measured from the step start c->ts0; g = glo, ghi at its
+ * ends): chord estimate, then Newton on the crossing time -- every iteration re-takes the integrator's own step from
+ * the step start -- with bisection whenever Newton leaves the bracket; a last Henon step removes what is left of g */
+static void ev_refine(ev_ctx *c, double lo, double hi, double glo, double ghi)
 {
     int kind = c->pb->kind, nv = orc_nvar(kind);
-    double g1 = ev_g(c->coef, c->offset, u, nv);
-    int up = c->g0 < 0 && g1 >= 0, down = c->g0 > 0 && g1 <= 0;
-    if ((up && c->direction >= 0) || (down && c->direction <= 0)) {
-        double y[5];
-        memcpy(y, u, sizeof(double) * nv);
-        y[nv] = t1;
-        if (g1 != 0) {
-            /* chord estimate of the crossing time, then Newton on it: each iteration re-takes the integrator's own
-             * step from the step start; a last Henon step removes what is left of g (rounding level) */
-            double sgn = c->pb->backwards ? -1.0 : 1.0;
-            int rk4 = c->pb->alg == ALG_RK4;
-            double hs = t1 - c->ts0, th = hs * (c->g0 / (c->g0 - g1)), z[4];
-            double g2 = 0;
-            for (int it = 0; it < 6; ++it) {
-                memcpy(z, c->us, sizeof(double) * nv);
-                if (rk4)
-                    rk4_step(kind, c->pb->par, sgn, th, z);
-                else
-                    rk8_fixed_step(kind, c->pb->par, sgn, th, z);
-                g2 = ev_g(c->coef, c->offset, z, nv);
-                if (it == 5 || fabs(g2) <= 1e-13) break;
-                double f[4], gd = 0; /* Newton on the crossing time */
-                orc_rhs(kind, c->pb->par, sgn, z, f);
-                for (int i = 0; i < nv; ++i) gd += c->coef[i] * f[i];
-                double tn = th - g2 / gd;
-                if (!(tn > 0) || !(tn <= hs)) break;
-                th = tn;
-            }
+    double sgn = c->pb->backwards ? -1.0 : 1.0;
+    int rk4 = c->pb->alg == ALG_RK4, up = glo < 0;
+    double th = lo + (hi - lo) * (glo / (glo - ghi)), z[4], y[5], g2 = ghi;
+    if (ghi == 0) th = hi;
+    for (int it = 0; it < 8; ++it) {
+        memcpy(z, c->us, sizeof(double) * nv);
+        if (rk4)
+            rk4_step(kind, c->pb->par, sgn, th, z);
+        else
+            rk8_fixed_step(kind, c->pb->par, sgn, th, z);
+        g2 = ev_g(c->coef, c->offset, z, nv);
+        if (it == 7 || fabs(g2) <= 1e-13) break;
+        if ((g2 < 0) == (glo < 0)) {
+            lo = th;
+            glo = g2;
+        } else
+            hi = th;
+        double f[4], gd = 0;
+        orc_rhs(kind, c->pb->par, sgn, z, f);
+        for (int i = 0; i < nv; ++i) gd += c->coef[i] * f[i];
+        double tn = th - g2 / gd;
+        if (!(tn > lo) || !(tn < hi)) tn = 0.5 * (lo + hi);
+        th = tn;
+    }
+    memcpy(y, z, sizeof(double) * nv);
+    y[nv] = c->ts0 + th;
+    if (g2 != 0) {
+        henon_step(kind, c->pb->par, sgn, c->coef, rk4, -g2, y);
+        int fin = 1;
+        for (int i = 0; i <= nv; ++i) fin = fin && isfinite(y[i]);
+        if (!fin) {
             memcpy(y, z, sizeof(double) * nv);
             y[nv] = c->ts0 + th;
-            if (g2 != 0) henon_step(kind, c->pb->par, sgn, c->coef, rk4, -g2, y);
-            int fin = 1;
-            for (int i = 0; i <= nv; ++i) fin = fin && isfinite(y[i]);
-            if (!fin) {
-                memcpy(y, z, sizeof(double) * nv);
-                y[nv] = c->ts0 + th;
+        }
+    }
+    if (c->count < c->cap) {
+        c->ev_t[c->count] = y[nv];
+        memcpy(c->ev_u + (size_t)c->count * nv, y, sizeof(double) * nv);
+        c->ev_dir[c->count] = up ? 1 : -1;
+    }
+    c->count++;
+}
+
+/* after an accepted step from (c->ts0, c->us) to (t1, u).  gd0, gd1: dg/dt at the two ends (adaptive pairs, from
+ * the FSAL derivatives; have_gd = 0 for fixed steps, which are short enough not to hide a pair of crossings) */
+static void ev_check(ev_ctx *c, const double *u, double t1, int have_gd, double gd0, double gd1)
+{
+    int kind = c->pb->kind, nv = orc_nvar(kind);
+    double g0 = c->g0, g1 = ev_g(c->coef, c->offset, u, nv), hs = t1 - c->ts0;
+    int up = g0 < 0 && g1 >= 0, down = g0 > 0 && g1 <= 0;
+    if ((up && c->direction >= 0) || (down && c->direction <= 0)) {
+        ev_refine(c, 0.0, hs, g0, g1);
+    } else if (have_gd && !up && !down && g0 * g1 > 0 && gd0 * gd1 < 0) {
+        /* tangency: the cubic Hermite interpolant of g has its extremum inside the step, on the other side of zero */
+        double d0 = hs * gd0, d1 = hs * gd1, dl = g1 - g0;
+        double c2 = 3 * dl - 2 * d0 - d1, c3 = d0 + d1 - 2 * dl;
+        double qa = 3 * c3, qb = 2 * c2, disc = qb * qb - 4 * qa * d0, x = -1;
+        if (disc >= 0) {
+            double sq = sqrt(disc), q = -0.5 * (qb + (qb >= 0 ? sq : -sq));
+            double x1 = (qa != 0) ? q / qa : -1, x2 = (q != 0) ? d0 / q : -1;
+            x = (x1 > 0 && x1 < 1) ? x1 : x2;
+        }
+        if (x > 0 && x < 1) {
+            double gx = g0 + x * (d0 + x * (c2 + x * c3));
+            if (gx * g0 < 0) {
+                double thx = x * hs, z[4];
+                double sgn = c->pb->backwards ? -1.0 : 1.0;
+                memcpy(z, c->us, sizeof(double) * nv);
+                if (c->pb->alg == ALG_RK4)
+                    rk4_step(kind, c->pb->par, sgn, thx, z);
+                else
+                    rk8_fixed_step(kind, c->pb->par, sgn, thx, z);
+                double gm = ev_g(c->coef, c->offset, z, nv); /* the integrator's own value at the extremum */
+                if (gm * g0 < 0) {
+                    int first_up = g0 < 0;
+                    if ((first_up && c->direction >= 0) || (!first_up && c->direction <= 0)) ev_refine(c, 0.0, thx, g0, gm);
+                    if ((!first_up && c->direction >= 0) || (first_up && c->direction <= 0)) ev_refine(c, thx, hs, gm, g1);
+                }
             }
         }
-        if (c->count < c->cap) {
-            c->ev_t[c->count] = y[nv];
-            memcpy(c->ev_u + (size_t)c->count * nv, y, sizeof(double) * nv);
-            c->ev_dir[c->count] = up ? 1 : -1;
-        }
-        c->count++;
     }
     c->g0 = g1;
 }
@@ -1321,7 +1360,7 @@ int orc_integrate_events(const orc_problem *pb, const double *u0, long n, double
                         st = ST_DOMAIN;
                         break;
                     }
-                    ev_check(&c, u, (s + 1 == nsub[0]) ? t_end : hsub[0] * (double)(s + 1));
+                    ev_check(&c, u, (s + 1 == nsub[0]) ? t_end : hsub[0] * (double)(s + 1), 0, 0.0, 0.0);
                 }
             } else {
                 /* the adaptive loop of orc_solve_one with a per-accepted-step hook */
@@ -1396,12 +1435,17 @@ int orc_integrate_events(const orc_problem *pb, const double *u0, long n, double
                             memcpy(c.us, u, sizeof(double) * nv);
                             c.ts0 = t;
                             t = (t + h >= t_end) ? t_end : t + h;
+                            double gd0 = 0, gd1 = 0; /* dg/dt at both ends, from the FSAL derivatives */
+                            for (int i = 0; i < nv; ++i) {
+                                gd0 += coef[i] * K[0][i];
+                                gd1 += coef[i] * K[S][i];
+                            }
                             for (int i = 0; i < nv; ++i) {
                                 u[i] = yn[i];
                                 K[0][i] = K[S][i];
                             }
                             rejected = 0;
-                            ev_check(&c, u, t);
+                            ev_check(&c, u, t, 1, gd0, gd1);
                         } else {
                             h_abs = h * fmax(0.2, 0.9 * pow(err, expo));
                             rejected = 1;

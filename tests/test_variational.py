@@ -396,3 +396,47 @@ def test_gpu_linearisation_at_the_ground_state_has_the_references_normal_frequen
             assert st[0] == 0 and np.abs(x[0, 0] - x0).max() < 1e-11
             got = _normal_frequencies_from_phi(F[0, 0], t)
             assert np.abs(got - want).max() < 1e-8, (par, alg, got, want)
+
+
+def _near_tangent_section(O):
+    """a section q = q_max - eps just below a local maximum of q(t): two crossings 0.08 apart, inside one DOP853 step"""
+    u0 = np.array([[1.0, 0.5, 0.2, 0.0]])
+    ts = np.linspace(18.0, 19.6, 1601)
+    out, st, _, _ = O.integrate(O.SYS_DICKE, PPAR, u0, ts, tol=1e-13)
+    q = out[0, :, 1]
+    i = int(np.argmax(q))
+    assert 0 < i < len(q) - 1
+    return u0, float(ts[i]), float(q[i])
+
+
+def test_oracle_finds_both_crossings_of_a_near_tangency(O):
+    u0, tmax, qmax = _near_tangent_section(O)
+    off = qmax - 1e-3
+    truth = O.integrate_events(O.SYS_DICKE, PPAR, u0, 30.0, [0, 1, 0, 0], offset=off, tol=1e-13, max_events=64)
+    tt = truth[0][0, :truth[3][0]]
+    pair = tt[np.abs(tt - tmax) < 0.3]
+    assert len(pair) == 2 and 0.05 < pair[1] - pair[0] < 0.12
+    for tol in (1e-8, 1e-10):      # steps of 0.1 - 0.25: the pair sits inside one step, no sign change at its ends
+        ev = O.integrate_events(O.SYS_DICKE, PPAR, u0, 30.0, [0, 1, 0, 0], offset=off, tol=tol, max_events=64)
+        te, de = ev[0][0, :ev[3][0]], ev[2][0, :ev[3][0]]
+        got = te[np.abs(te - tmax) < 0.3]
+        assert len(got) == 2 and np.abs(got - pair).max() < 0.01, (tol, got, pair)
+        assert list(de[np.abs(te - tmax) < 0.3]) == [1, -1]
+        assert np.abs(ev[1][0, :ev[3][0], 1] - off).max() < 1e-13
+    # direction filters keep one of the two
+    up = O.integrate_events(O.SYS_DICKE, PPAR, u0, 30.0, [0, 1, 0, 0], offset=off, direction=1, tol=1e-10, max_events=64)
+    tu = up[0][0, :up[3][0]]
+    assert len(tu[np.abs(tu - tmax) < 0.3]) == 1 and abs(tu[np.abs(tu - tmax) < 0.3][0] - pair[0]) < 0.01
+
+
+@pytest.mark.gpu
+def test_gpu_finds_both_crossings_of_a_near_tangency(ctx, pkg, O):
+    u0, tmax, qmax = _near_tangent_section(O)
+    off = qmax - 1e-3
+    for alg, ocode, tol in ((pkg._lib.ALG_DOP853, O.ALG_DOP853, 1e-10), (pkg._lib.ALG_DP5, O.ALG_DP5, 1e-10)):
+        tg, ug, dg, cg, eg, sg, ng, ms = ctx.integrate_events(csys(pkg, 0, PPAR), csol(pkg, alg, tol=tol), u0, 30.0, [0, 1, 0, 0], off, 0, 64)
+        to, uo, do, co, eo, so, no = O.integrate_events(O.SYS_DICKE, PPAR, u0, 30.0, [0, 1, 0, 0], offset=off, tol=tol, max_events=64, alg=ocode)
+        assert cg[0] == co[0] and np.array_equal(dg[0, :cg[0]], do[0, :co[0]])
+        got = tg[0, :cg[0]]
+        assert (np.abs(got - tmax) < 0.3).sum() == 2
+        assert np.abs(got - to[0, :co[0]]).max() < 1e-6        # (crossing times near a tangency amplify the rounding-level step differences)
