@@ -233,7 +233,8 @@ def test_specialised_kernel_is_bit_identical_to_the_interpreter(ctx, mods, O):
     assert np.array_equal(res[0], res[1])
 
 
-def test_multi_device_context_matches_single_device(pkg, mods, O):
+@pytest.mark.parametrize("solver", [dict(integrator_alg="RK4", dt=2.0 ** -6), dict(integrator_alg="DP8", tol=1e-9)])
+def test_multi_device_context_matches_single_device(pkg, mods, O, solver):
     """dtwa_create(ndev=2): contiguous index blocks + one grouped ncclAllReduce; integer counts are
     bit-identical to the single-device run, sums agree to rounding"""
     import torch
@@ -249,7 +250,7 @@ def test_multi_device_context_matches_single_device(pkg, mods, O):
         W = TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=j, seed=5)
         chain = TWA.mcs_chain(TWA.mcs_for_averaging(system, observable=jz, N=N, ts=ts, distribution=W),
                               TWA.mcs_for_distributions(system, x="t", y=jz, ys=TWA.jrange(-1.1, 0.01, 1.1), N=N, ts=ts, distribution=W))
-        out = TWA.monte_carlo_integrate(system, chain, integrator_alg="RK4", dt=2.0 ** -6)
+        out = TWA.monte_carlo_integrate(system, chain, **solver)
         return out, dict(TWA.last_info)
 
     one, i1 = run()
