@@ -1398,7 +1398,7 @@ extern "C" int dtwa_plan_fetch(dtwa_plan *plan, dtwa_result *res)
     res->resample_rounds = plan->rounds;
     res->jit = plan->jit ? 1 : 0;
     res->launches = plan->launches;
-    float kms = 0.f, tms = 0.f;
+    float tms = 0.f;
     double kmax = 0.0;
     for (auto &p : plan->devs) {  // max over devices, each timed on its own stream
         if (!p.dc) continue;
@@ -1408,7 +1408,6 @@ extern "C" int dtwa_plan_fetch(dtwa_plan *plan, dtwa_result *res)
         if (cudaEventElapsedTime(&m, p.dc->ev[1], p.dc->ev[2]) == cudaSuccess) kmax = std::max(kmax, (double)m);
     }
     cudaSetDevice(d.device);
-    (void)kms;
     cudaEventElapsedTime(&tms, d.ev[0], d.ev[3]);
     cudaGetLastError();
     res->kernel_ms = kmax;

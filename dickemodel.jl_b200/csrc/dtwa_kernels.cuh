@@ -594,8 +594,7 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
 
     if constexpr (!FIXED) {
         adaptive_stream<SYS, ALG, JIT>(A, V, my_partial, nvalid_g);
-        return;
-    }
+    } else {
     // ---- fixed step: persistent loop over batches of blockDim.x trajectories ----
     for (long long batch = blockIdx.x; batch * (long long)blockDim.x < A.N; batch += gridDim.x) {
         const long long j = batch * (long long)blockDim.x + threadIdx.x;
@@ -702,6 +701,7 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
             atomicAdd(&A.u64[CNT_LANE], 32ull * warp_iters);
         }
     }
+    }  // fixed step
 }
 
 template <int SYS, int ALG>
