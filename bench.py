@@ -296,6 +296,27 @@ def main():
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
             traffic_src = tj.get("source")
 
+    # ---- not the headline: the adaptive path (BASELINE.json configs[3]) on one GPU, for the record ----
+    extras = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            Bpt = CD.Point(system, Q=1, P=1, p=0, ϵ=0.5)
+            tsa = TWA.jrange(0, 1, 1000)
+            extras = {}
+            for alg in ("DP8", "DP5"):
+                for n_ad in (20000, 1000000):   # (the small call warms the specialisation up)
+                    Wa = TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=1)
+                    TWA.average(system, observable=jz, N=n_ad, ts=tsa, distribution=Wa, integrator_alg=alg, tol=1e-8)
+                ia = TWA.last_info
+                st_ad = ia["steps_accepted"] + ia["steps_rejected"]
+                extras["adaptive_" + alg.lower()] = {
+                    "workload": "configs[3]: chaotic state, tol=1e-8, ts=0:1:1000, 1e6 trajectories (one GPU's share of 8e6)",
+                    "attempted_steps_per_s": st_ad / (ia["kernel_ms"] * 1e-3), "kernel_ms": ia["kernel_ms"],
+                    "lane_efficiency": st_ad / max(1, ia["lane_steps"]), "rejected_fraction": ia["steps_rejected"] / max(1, st_ad),
+                    "specialised": ia["jit"]}
+        except Exception as e:   # never lose the headline line over the extras
+            extras = {"error": repr(e)}
+
     if rank == 0:
         if not (abs(float(last[0]) + 1.0) < 0.02 and steps_done == args.steps * N_total * 14000):
             raise SystemExit(f"bench self-check failed: <Jz>/j(t=0) = {float(last[0])}, steps counted {steps_done} "
@@ -319,6 +340,7 @@ def main():
                          "fp64_pipe_frac_est": kern_rate * FP64_INSTR_PER_STEP["dicke_rk4"] / (peak_tflops * 1e12 / 2.0),
                          "note": "frac is ALGORITHMIC flops (136/step) over the measured DFMA peak; fp64_pipe_frac_est counts the 92 FP64-pipe instructions/step of the SASS hot loop (w = 1 specialisation), each of which occupies one DFMA issue slot"},
             "cpu_baseline": cpu,
+            "extras": extras,
             "result_check": {"mean_jz_t0": float(last[0]), "mean_jz_t5": float(last[100]), "mean_jz_t100": float(last[-1])},
         }
         print(json.dumps(line))
