@@ -653,8 +653,12 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
             for (int w = 0; w < nw; ++w) {
                 const int k = k0 + w;
                 warp_iters += T.advance(A.S, k);
-                if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
-                if (T.status != ST_OK && T.status != ST_INACTIVE && !failed_reported) report_failure(k);
+                // one rarely taken branch per output time: the chart test runs unconditionally (cheap), everything else
+                // only for lanes that are not (or no longer) healthy
+                if (state_bad<SYS>(T.u) || T.status != ST_OK) {
+                    if (T.status == ST_OK) T.status = ST_DOMAIN;
+                    if (T.status != ST_INACTIVE && !failed_reported) report_failure(k);
+                }
                 const bool valid = (T.status == ST_OK) && (k >= start_k);
                 reduce_at(valid, k, w);
                 // fixed step: V.nvalid counts the threads that do NOT contribute (failed, inactive tail,
