@@ -365,6 +365,12 @@ __device__ __forceinline__ void rk4_step(const SysPar &p, double (&u)[Sys<SYS>::
     }
 }
 
+// coefficient tables of the embedded pairs, in constant memory (see tools/gen_tableaux.py)
+#define DTWA_TABLEAU_CONSTANTS
+#include "dp5_body.inc"
+#include "dop853_body.inc"
+#undef DTWA_TABLEAU_CONSTANTS
+
 #define RHS(in, out) Sys<SYS>::rhs(p, in, out)
 
 // one DOP853 step with the 8th-order weights only (fixed step)
