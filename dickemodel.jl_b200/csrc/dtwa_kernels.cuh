@@ -588,6 +588,15 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
     }
     __syncthreads();
 
+#if defined(DTWA_DIAG_SMID)
+    if (threadIdx.x == 0) {   // diagnostic: which SM hosts this CTA, and when
+        unsigned smid;
+        unsigned long long t0;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        printf("CTA %d sm %u t %llu\n", (int)blockIdx.x, smid, t0);
+    }
+#endif
     const int nt = A.S.nt;
     double *my_partial = A.partial + (size_t)blockIdx.x * nt * A.nslots;
     unsigned long long *nvalid_g = A.u64 + CNT_N;
