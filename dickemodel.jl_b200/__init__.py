@@ -16,3 +16,21 @@ from ._lib import Context, DtwaError, default_context, set_default_context, set_
 
 __all__ = ["ClassicalSystems", "ClassicalDicke", "ClassicalLMG", "PhaseSpaces", "TWA", "EnergyShellProjections", "DickeBCE", "symbolic", "Context",
            "DtwaError", "default_context", "set_default_context", "set_distributed", "load_library"]
+
+
+def _add_unnormalised_aliases():
+    """Python NFKC-normalises identifiers in source code (ϵ U+03F5 -> ε U+03B5, ϕ U+03D5 -> φ U+03C6), so
+    `ClassicalDicke.q_of_ϵ` written in a script finds `q_of_ε`.  getattr() with the reference's raw spelling does not
+    normalise: register those spellings too."""
+    import types
+    for mod in (ClassicalDicke, ClassicalLMG, ClassicalSystems, PhaseSpaces, TWA, EnergyShellProjections):
+        for name, obj in list(vars(mod).items()):
+            if name.startswith("_") or isinstance(obj, types.ModuleType):
+                continue
+            raw = name.replace("\u03b5", "\u03f5").replace("\u03c6", "\u03d5")
+            if raw != name and not hasattr(mod, raw):
+                setattr(mod, raw, obj)
+
+
+_add_unnormalised_aliases()
+

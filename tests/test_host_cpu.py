@@ -249,3 +249,14 @@ def test_quantum_dicke_system_delegates_to_the_classical_one(pkg):
         DickeBCE.QuantumDickeSystem(cs, j=0.3)
     with pytest.raises(ValueError, match="Nmax"):
         DickeBCE.QuantumDickeSystem(cs, j=3, Nmax=0)
+
+
+def test_reference_spellings_resolve(pkg):
+    """the reference's names use ϵ (U+03F5) and ϕ (U+03D5); Python source normalises them, getattr does not"""
+    from dickemodel_jl_b200 import ClassicalDicke as CD, ClassicalLMG as CL, PhaseSpaces as PS
+    for mod, names in ((CD, ["q_of_ϵ", "minimum_ϵ_for", "maximum_P_for_ϵ", "maximum_Q_for_ϵ", "minimum_nonnegative_Q_for_ϵ",
+                              "Pointθϕ", "discriminant_of_q_solution", "energy_shell_volume", "classical_path_random_sampler"]),
+                       (CL, ["P_of_ϵ"]), (PS, ["Q_of_θϕ", "P_of_θϕ", "ϕ_of_QP", "arc_between_θϕ"])):
+        for n in names:
+            assert callable(getattr(mod, n)), n
+    assert CD.q_of_ϵ is getattr(CD, "q_of_ϵ")
