@@ -246,6 +246,39 @@ def _expr_of(system, observable) -> str:
     raise TypeError(f"cannot interpret {observable!r} as an observable")
 
 
+def function_from_expression(system, expression):
+    """src/TWA.jl:277-299: observable -> callable of n arguments (or of one n-vector).  The callable evaluates on the
+    GPU (dtwa_eval_expr: the observable VM, one IEEE operation per arithmetic node); it also accepts an array
+    [m][nvar] and then returns m values."""
+    expr = _expr_of(system, expression).lstrip(":")
+    csys = system._c_system()
+    nv = len(system.varnames())
+
+    def f(*x):
+        u = np.asarray(x[0] if len(x) == 1 else x, dtype=np.float64)
+        if u.ndim == 1:
+            if u.shape[0] != nv:
+                raise ValueError("You should pass a n-vector or n arguments, where n is the dimension of the phase space.")
+            return float(_lib.default_context().eval_expr(csys, expr, u[None, :])[0])
+        return _lib.default_context().eval_expr(csys, expr, u)
+    f.expression = expr
+    return f
+
+
+def functions_from_expressions(system, expressions):
+    """src/TWA.jl:300-303"""
+    return [function_from_expression(system, s) for s in expressions]
+
+
+def scale_to_index(v, r):
+    """src/TWA.jl:53-64 for a LinRange-like r = (start, stop, len) / JRange / array: the 1-based index of the grid point
+    nearest to v (ties to even), NaN outside [start, stop].  Evaluated on the GPU with the kernels' own routine."""
+    start, stop, length = _as_linrange(r, "r")
+    idx = _lib.default_context().scale_to_index(np.atleast_1d(np.asarray(v, dtype=np.float64)), start, stop, length)
+    out = np.where(idx > 0, idx.astype(np.float64), np.nan)
+    return out if np.ndim(v) else (float("nan") if idx[0] == 0 else int(idx[0]))
+
+
 def mcs_for_averaging(system, *, observable, ts=(0.0,), N, distribution):
     """src/TWA.jl:336-370"""
     onevar = not isinstance(observable, (list, tuple, np.ndarray))

@@ -176,3 +176,21 @@ def test_background_specialisation_takes_over_without_changing_a_bit(pkg, ctx):
     assert runs[0][0] == 0, "the first call must not wait for the compiler"
     assert runs[-1][0] == 1, "the specialised kernel never became available"
     assert all(np.array_equal(r[1], runs[0][1]) for r in runs)
+
+
+def test_function_from_expression_and_scale_to_index_helpers(pkg, O):
+    """src/TWA.jl:277-303 and :53-64 as callable helpers (evaluated on the GPU)"""
+    from dickemodel_jl_b200 import TWA, ClassicalDicke as CD
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    f = TWA.function_from_expression(system, ":(q+p^2-Q)")
+    assert f(0.5, 1.0, 0.25, 2.0) == 1.0 + 4.0 - 0.5 and f([0.5, 1.0, 0.25, 2.0]) == 4.5
+    g1, g2 = TWA.functions_from_expressions(system, [lambda Q, q, P, p: Q * P, TWA.Weyl.Jz(10)])
+    u = np.random.default_rng(2).uniform(-1, 1, (7, 4))
+    assert np.array_equal(g1(u), u[:, 0] * u[:, 2])
+    assert np.array_equal(g2(u), O.eval_expr(str(TWA.Weyl.Jz(10)), O.varnames(O.SYS_DICKE), u))
+    r = TWA.jrange(-1.1, 0.01, 1.1)
+    assert TWA.scale_to_index(-1.1, r) == 1 and TWA.scale_to_index(1.1, r) == 221 and np.isnan(TWA.scale_to_index(1.2, r))
+    v = np.linspace(-1.2, 1.2, 97)
+    want = O.scale_to_index(v, -1.1, 1.1, 221).astype(float)
+    want[want == 0] = np.nan
+    assert np.array_equal(TWA.scale_to_index(v, r), want, equal_nan=True)
