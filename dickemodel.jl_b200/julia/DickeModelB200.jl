@@ -433,11 +433,12 @@ function ∫∫dqdpδϵ(system::ClassicalDickeSystem; ϵ::Real, Q, P, f, p_res::
     out = Array{Float64}(undef, length(exprs), n); valid = Vector{Int32}(undef, n)
     root = onlyqroot === nothing ? 0 : (onlyqroot === (+) ? 1 : -1)
     sys = Ref(csystem(system))
-    GC.@preserve QP exprs out valid begin
+    cptrs = [pointer(e) for e in exprs]        # NUL-terminated UTF-8 (Julia Strings are), kept alive by GC.@preserve exprs
+    GC.@preserve QP exprs cptrs out valid begin
         check(ccall((:dtwa_shell_quadrature, libdicketwa), Cint,
-                    (Ptr{Cvoid}, Ref{CSystem}, Float64, Ptr{Float64}, Int64, Ptr{Cstring}, Int32, Float64, Int32, Ptr{Float64},
+                    (Ptr{Cvoid}, Ref{CSystem}, Float64, Ptr{Float64}, Int64, Ptr{Ptr{UInt8}}, Int32, Float64, Int32, Ptr{Float64},
                      Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
-                    context().handle, sys, ϵ, QP, n, pointer.(exprs), length(exprs), p_res, root, out, valid, C_NULL, C_NULL))
+                    context().handle, sys, ϵ, QP, n, cptrs, length(exprs), p_res, root, out, valid, C_NULL, C_NULL))
     end
     res = [valid[i] == 1 ? (f isa AbstractVector ? out[:, i] : out[1, i]) : nonvalue for i in 1:n]
     return Q isa Real ? res[1] : res
