@@ -169,3 +169,55 @@ def test_scale_to_index_bit_exact(ctx, O):
                         [np.nan, np.inf, -np.inf, -1.1, 1.1]])
     for (a, b, n) in ((-1.1, 1.1, 221), (-4.3, 4.3, 431), (0.0, 1.0, 1), (-0.8, 0.0, 41)):
         assert np.array_equal(ctx.scale_to_index(v, a, b, n), O.scale_to_index(v, a, b, n))
+
+
+def _random_expression(rng, depth):
+    """a random arithmetic expression over Q,q,P,p with + - * / integer powers and sqrt(abs-free positive arguments)"""
+    if depth == 0 or rng.random() < 0.2:
+        r = rng.random()
+        if r < 0.6:
+            return str(rng.choice(["Q", "q", "P", "p"]))
+        if r < 0.8:
+            return repr(float(np.round(rng.uniform(0.1, 3.0), 3)))
+        return str(int(rng.integers(1, 6)))
+    op = rng.choice(["+", "-", "*", "/", "^", "sqrt", "neg"], p=[0.25, 0.2, 0.25, 0.1, 0.1, 0.05, 0.05])
+    a = _random_expression(rng, depth - 1)
+    if op == "sqrt":
+        return f"sqrt(({a})^2 + 1.5)"
+    if op == "neg":
+        return f"(-({a}))"
+    if op == "^":
+        return f"({a})^{int(rng.integers(2, 6))}"
+    b = _random_expression(rng, depth - 1)
+    if op == "/":
+        return f"({a})/(({b})^2 + 0.5)"
+    return f"({a}) {op} ({b})"
+
+
+def test_random_expressions_bit_exact_in_the_vm_and_when_specialised(ctx, pkg, O):
+    """200 random expression trees: the interpreter (dtwa_eval_expr), the NVRTC-specialised reducer and the oracle's
+    evaluator execute the same single-rounding operations -> identical bits"""
+    from dickemodel_jl_b200 import TWA, ClassicalDicke as CD
+    rng = np.random.default_rng(2026)
+    u = np.column_stack([rng.uniform(-1.3, 1.3, 64), rng.normal(0, 1, 64), rng.uniform(-1.3, 1.3, 64), rng.normal(0, 1, 64)])
+    sysd = csys(pkg, 0, DPAR)
+    names = O.varnames(O.SYS_DICKE)
+    exprs = [_random_expression(rng, 4) for _ in range(200)]
+    for e in exprs:
+        got = ctx.eval_expr(sysd, e, u)
+        want = O.eval_expr(e, names, u)
+        assert np.array_equal(got, want, equal_nan=True), e
+    # through the ensemble: one trajectory per call would be slow -- average 8 observables at a time over the 64 states
+    # at ts = [0] (sums of identical terms in a fixed order: interpreter == specialised kernel bit for bit)
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    try:
+        for i in range(0, 24, 8):
+            outs = []
+            for jit in (0, 1):
+                ctx.set_jit(jit)
+                outs.append(TWA.average(system, observable=exprs[i:i + 8], N=64, ts=[0.0], distribution=TWA.samples_from_array(u, j=10)))
+            assert np.array_equal(np.asarray(outs[0]), np.asarray(outs[1]), equal_nan=True), exprs[i:i + 8]
+            ref = np.array([O.eval_expr(e, names, u) for e in exprs[i:i + 8]]).mean(axis=1)
+            assert np.allclose(np.asarray(outs[0]).ravel(), ref, rtol=1e-12, atol=1e-12, equal_nan=True)
+    finally:
+        ctx.set_jit(2)
