@@ -260,3 +260,40 @@ def test_reference_spellings_resolve(pkg):
         for n in names:
             assert callable(getattr(mod, n)), n
     assert CD.q_of_ϵ is getattr(CD, "q_of_ϵ")
+
+
+def test_host_logic_of_the_widened_modules(pkg):
+    """grids of matrix_QP∫∫dqdpδϵ (src/EnergyShellProjections.jl:100-118), the affine form of a ContinuousCallback
+    condition, argument errors -- all decided on the host, before any kernel is launched"""
+    from dickemodel_jl_b200 import ClassicalDicke as CD, ClassicalSystems as CS, EnergyShellProjections as ESP
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    Qs, Ps = ESP._generate_QPs(False, False, 0.1, system, -0.5)
+    assert np.isclose(Qs[0], -Qs[-1]) and np.isclose(Ps[0], -Ps[-1]) and np.allclose(np.diff(Qs), 0.1)
+    assert abs(Qs[-1]) >= CD.maximum_Q_for_ϵ(system, -0.5) and abs(Qs[-1]) < CD.maximum_Q_for_ϵ(system, -0.5) + 0.1
+    Qh, Ph = ESP._generate_QPs(True, True, 0.1, system, -0.5)
+    assert np.isclose(Qh[-1], 0) and np.isclose(Ph[-1], 0) and len(Qh) == (len(Qs) + 1) // 2
+    Qp, Pp = ESP._generate_QPs(False, True, 0.1, system, -0.5)
+    assert len(Qp) == len(Qs) and np.isclose(Pp[-1], 0)
+    with pytest.raises(ValueError, match="integer fraction of 2"):
+        ESP._generate_QPs(False, False, 0.3, system, -0.5)
+    assert ESP._exprs(system, lambda x: [1, x[1] ** 2])[1] is False and ESP._exprs(system, lambda x: x[0])[1] is True
+    assert ESP._root(None) == 0 and ESP._root("+") == 1 and ESP._root("-") == -1
+
+    hits = []
+    cb = CS.ContinuousCallback(lambda x, t, _: 2 * x[3] - 0.5 * x[0] + 0.25, hits.append)
+    coef, offset, direction = cb.linear_form(4)
+    assert np.allclose(coef, [-0.5, 0, 0, 2]) and offset == -0.25 and direction == 0
+    assert CS.ContinuousCallback(lambda x, t, _: x[1], hits.append, None).linear_form(4)[2] == 1
+    assert CS.ContinuousCallback(lambda x, t, _: x[1], None, hits.append).linear_form(4)[2] == -1
+    with pytest.raises(NotImplementedError, match="affine"):
+        CS.ContinuousCallback(lambda x, t, _: x[1] * x[2], hits.append).linear_form(4)
+    with pytest.raises(NotImplementedError, match="save_positions"):
+        CS.ContinuousCallback(lambda x, t, _: x[1], hits.append, save_positions=(True, False))
+    with pytest.raises(NotImplementedError, match="ContinuousCallback"):
+        CS.integrate(system, [1.0, 0.3, 1.0, 0.0], 1.0, callback=object())
+    with pytest.raises(ValueError, match="out of bounds"):
+        CS.lyapunov_spectrum(system, [1.9, 0.0, 1.9, 0.0])
+    with pytest.raises(ValueError, match="should have length 4"):
+        CS.lyapunov_spectrum(system, [1.0, 0.0])
+    with pytest.raises(ValueError, match="3x3|4x4"):
+        CS.integrate(system, [1.0, 0.3, 1.0, 0.0], 1.0, get_fundamental_matrix=True, fundamental_matrix_initial=np.eye(3))
