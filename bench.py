@@ -314,6 +314,28 @@ def main():
                     "attempted_steps_per_s": st_ad / (ia["kernel_ms"] * 1e-3), "kernel_ms": ia["kernel_ms"],
                     "lane_efficiency": st_ad / max(1, ia["lane_steps"]), "rejected_fraction": ia["steps_rejected"] / max(1, st_ad),
                     "specialised": ia["jit"]}
+            # BASELINE.json configs[0] (the CPU-runnable case): N = 1e4, adaptive 8th order at the reference's default
+            # tol = 1e-12, GPU next to the oracle port on all host cores, same Philox samples
+            from oracle import oracle as O
+            ts0 = TWA.jrange(0, WORK["t_step"], WORK["t_end"])
+            for _ in range(2):
+                W0 = TWA.coherent_Wigner_HWxSU2(WORK["center"], j=j, seed=WORK["seed"])
+                t0 = time.perf_counter()
+                g0 = TWA.average(system, observable=jz, N=10000, ts=ts0, distribution=W0)
+                wall0 = time.perf_counter() - t0
+            i0 = dict(TWA.last_info)
+            sp0 = O.make_sampler(O.SAMPLER_HWXSU2, WORK["center"], 1.0 / j, seed=WORK["seed"])
+            cj = float(np.sqrt(j * (j + 1)))
+            thr = host_threads()
+            t0 = time.perf_counter()
+            r0 = O.ensemble(O.SYS_DICKE, WORK["par"], sp0, 10000, np.asarray(ts0), values=[(2, 0, cj)], alg=O.ALG_DOP853, tol=1e-12,
+                            workers=thr, fast=True)
+            cpu0 = time.perf_counter() - t0
+            extras["config0_default_adaptive"] = {
+                "workload": "configs[0]: N=1e4, ts=0:0.05:100, DOP853 tol=1e-12 (TsitPap8 is not available offline)",
+                "gpu_wall_s": wall0, "gpu_kernel_ms": i0["kernel_ms"], "gpu_attempted_steps": i0["steps_accepted"] + i0["steps_rejected"],
+                "cpu_port_s": cpu0, "cpu_cores": thr, "cpu_attempted_steps": r0["steps_accepted"] + r0["steps_rejected"],
+                "max_abs_diff_mean_jz": float(np.max(np.abs(r0["sums"][:, 0] / j / 10000 - g0)))}
         except Exception as e:   # never lose the headline line over the extras
             extras = {"error": repr(e)}
 
