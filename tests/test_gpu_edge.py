@@ -194,3 +194,54 @@ def test_function_from_expression_and_scale_to_index_helpers(pkg, O):
     want = O.scale_to_index(v, -1.1, 1.1, 221).astype(float)
     want[want == 0] = np.nan
     assert np.array_equal(TWA.scale_to_index(v, r), want, equal_nan=True)
+
+
+def test_full_size_properties_config3_share(ctx, mods, system):
+    """BASELINE.json configs[2]: the jz-vs-t and q-vs-t histograms, one GPU's share (1.25e8) of 10^9 trajectories"""
+    TWA, CD = mods[0], mods[1]
+    j, N = 100, 125_000_000
+    ts = TWA.jrange(0, 0.05, 40)
+    jz = TWA.Weyl.Jz(j) / j
+    B = CD.Point(system, Q=1, P=1, p=0, ϵ=0.5)
+    W = TWA.coherent_Wigner_HWxSU2(B, j=j, seed=1)
+    mk = lambda **k: TWA.mcs_for_distributions(system, N=N, distribution=W, ts=ts, **k)
+    hj, hq = TWA.monte_carlo_integrate(system, TWA.mcs_chain(mk(x="t", y=jz, ys=TWA.jrange(-1.1, 0.01, 1.1)),
+                                                             mk(y="t", x="q", xs=TWA.jrange(-4.3, 0.02, 4.3))),
+                                       integrator_alg="RK4", dt=2.0 ** -7)
+    info = TWA.last_info
+    assert hj.shape == (221, 801) and hq.shape == (801, 431)
+    nv = info["n_valid"].astype(np.float64)
+    cj, cq = np.rint(hj * N), np.rint(hq * N)
+    assert np.abs(hj * N - cj).max() < 1e-6 and np.abs(hq * N - cq).max() < 1e-6        # integer counts
+    assert np.array_equal(cj.sum(axis=0), nv)                                           # Jz/j always lies in -1.1:0.01:1.1
+    assert (cq.sum(axis=1) <= nv).all() and cq.sum(axis=1).min() > 0.99 * N             # a few q fall outside +-4.3
+    # failed trajectories were resampled (src/TWA.jl:186-209): every time has N contributions or a few more
+    assert info["n_unfinished"] == 0 and (nv >= N).all() and (nv <= N + 2 * info["n_failed"]).all()
+
+
+def test_full_size_properties_config4_share_and_config5(ctx, mods, system):
+    """configs[3] (adaptive, chaotic, t <= 1000; one GPU's share 10^6) and configs[4] (LMG, 10^8): the ensemble mean of the
+    Hamiltonian is a constant of motion; sums are linear"""
+    TWA, CD, CL = mods[0], mods[1], mods[2]
+    j = 100
+    B = CD.Point(system, Q=1, P=1, p=0, ϵ=0.5)
+    h = TWA._expr_of(system, CD.hamiltonian(system))
+    out = TWA.average(system, observable=[h, "1", "2*(" + h + ") - 1"], N=1_000_000, ts=TWA.jrange(0, 1, 1000),
+                      distribution=TWA.coherent_Wigner_HWxSU2(B, j=j, seed=1), integrator_alg="DP8", tol=1e-8)
+    info = TWA.last_info
+    out = np.asarray(out)
+    assert info["n_unfinished"] == 0 and np.array_equal(out[:, 1], info["n_valid"] / 1_000_000)
+    assert np.abs(out[:, 2] - (2 * out[:, 0] - out[:, 1])).max() < 1e-12
+    mean_h = out[:, 0] / out[:, 1]
+    assert np.abs(mean_h - mean_h[0]).max() < 2e-5          # tol = 1e-8 over t = 1000; resampled replacements shift it at 1e-6
+    lmg = CL.ClassicalLMGSystem(Ω=1, ξ=-1)
+    hl = TWA._expr_of(lmg, CL.hamiltonian(lmg))
+    N5 = 100_000_000
+    v = TWA.average(lmg, observable=[hl, "Q", "Q^2", "1"], N=N5, ts=TWA.jrange(0, 0.1, 50),
+                    distribution=TWA.coherent_Wigner_SU2([0, 0], j=500, seed=1), integrator_alg="RK4", dt=2.0 ** -7)
+    v = np.asarray(v)
+    i5 = TWA.last_info
+    assert i5["n_failed"] == 0 and (i5["n_valid"] == N5).all() and i5["steps_accepted"] == N5 * 13 * 500
+    assert np.array_equal(v[:, 3], np.ones(v.shape[0]))
+    assert np.abs(v[:, 0] - v[0, 0]).max() < 1e-9           # <h> conserved (RK4 at dt = 2^-7 drifts by 1.5e-10 over t = 50)
+    assert np.abs(v[:, 1]).max() < 5e-4 and (v[:, 2] > 0).all()          # the cloud stays centred; variance of Q positive
