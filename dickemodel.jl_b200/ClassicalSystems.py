@@ -257,14 +257,25 @@ def integrate(system, u0, t, *, t0=0.0, tol=1e-12, get_fundamental_matrix=False,
 
 def integrate_batch(system, U0, ts, **kargs):
     """Many initial conditions at once (the K3 kernel): returns (out[n][nt][nvar], status[n], nsteps[n]).
-    No counterpart in the reference, which loops over `integrate`."""
+    No counterpart in the reference, which loops over `integrate`.  devices=[...] splits the batch over several GPUs."""
+    devices = kargs.pop("devices", None)
     sol = solver_from_kargs(kargs)
+    if devices:
+        U0 = np.ascontiguousarray(U0, dtype=np.float64).reshape(-1, len(system.varnames()))
+        return _lib.split_over_devices(devices, len(U0), lambda c, it: c.integrate(system._c_system(), sol, U0[it], ts))
     return _lib.default_context().integrate(system._c_system(), sol, U0, ts)
 
 
 def integrate_fm_batch(system, U0, ts, fundamental_matrix_initial=None, **kargs):
     """Many (x, Φ) trajectories at once: (x[n][nt][nvar], Φ[n][nt][nvar][nvar], status[n], nsteps[n])."""
+    devices = kargs.pop("devices", None)
     sol = solver_from_kargs(kargs)
+    if devices:
+        U0 = np.ascontiguousarray(U0, dtype=np.float64).reshape(-1, len(system.varnames()))
+        nv = U0.shape[1]
+        F0 = None if fundamental_matrix_initial is None else np.asarray(fundamental_matrix_initial, dtype=np.float64).reshape(len(U0), nv, nv)
+        return _lib.split_over_devices(devices, len(U0), lambda c, it: c.integrate_fm(system._c_system(), sol, U0[it], ts,
+                                                                                      None if F0 is None else F0[it]))
     return _lib.default_context().integrate_fm(system._c_system(), sol, U0, ts, fundamental_matrix_initial)
 
 
@@ -273,9 +284,15 @@ def poincare_section_batch(system, U0, t, *, coef, offset=0.0, direction=0, max_
     surface, docs/src/ClassicalDickeExamples.md:82-109, draws one `integrate` per initial condition).
     Returns a dict: t[n][cap], u[n][cap][nvar], direction[n][cap], count[n], u_end, status, nsteps, kernel_ms;
     unused slots are NaN."""
+    devices = kargs.pop("devices", None)
     sol = solver_from_kargs(kargs)
-    ev_t, ev_u, ev_dir, cnt, u_end, status, nsteps, ms = _lib.default_context().integrate_events(
-        system._c_system(), sol, U0, t, coef, offset, direction, max_events)
+    if devices:
+        U0 = np.ascontiguousarray(U0, dtype=np.float64).reshape(-1, len(system.varnames()))
+        ev_t, ev_u, ev_dir, cnt, u_end, status, nsteps, ms = _lib.split_over_devices(
+            devices, len(U0), lambda c, it: c.integrate_events(system._c_system(), sol, U0[it], t, coef, offset, direction, max_events))
+    else:
+        ev_t, ev_u, ev_dir, cnt, u_end, status, nsteps, ms = _lib.default_context().integrate_events(
+            system._c_system(), sol, U0, t, coef, offset, direction, max_events)
     return dict(t=ev_t, u=ev_u, direction=ev_dir, count=cnt, u_end=u_end, status=status, nsteps=nsteps, kernel_ms=ms)
 
 
@@ -291,9 +308,14 @@ def lyapunov_spectrum_batch(system, X, t=100, *, λtol=1e-4, λreltol=1e-3, maxi
     solver_maxiters = kargs.pop("maxiters_solver")
     for k in ("fundamental_matrix_initial", "save_everystep", "get_fundamental_matrix"):
         kargs.pop(k, None)
+    devices = kargs.pop("devices", None)
     sol = solver_from_kargs(dict(kargs, maxiters=solver_maxiters))
     X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, len(system.varnames()))
-    lam, xf, iters, status, nsteps, ms = _lib.default_context().lyapunov(system._c_system(), sol, X, t, λtol, λreltol, maxiters)
+    if devices:   # independent orbits: contiguous blocks on several GPUs at once, no exchange step
+        lam, xf, iters, status, nsteps, ms = _lib.split_over_devices(
+            devices, len(X), lambda c, it: c.lyapunov(system._c_system(), sol, X[it], t, λtol, λreltol, maxiters))
+    else:
+        lam, xf, iters, status, nsteps, ms = _lib.default_context().lyapunov(system._c_system(), sol, X, t, λtol, λreltol, maxiters)
     last_lyapunov_info.clear()
     last_lyapunov_info.update(x_final=xf, iterations=iters, status=status, nsteps=nsteps, kernel_ms=ms)
     return lam, status

@@ -38,9 +38,14 @@ def _root(onlyqroot):
     return 1 if onlyqroot in ("+", 1, +1) else -1
 
 
-def _run(system, ϵ, QP, f, p_res, onlyqroot):
+def _run(system, ϵ, QP, f, p_res, onlyqroot, devices=None):
     exprs, scalar = _exprs(system, f)
-    out, valid, nodes, ms = _lib.default_context().shell_quadrature(system._c_system(), ϵ, QP, exprs, p_res, _root(onlyqroot))
+    if devices:   # (Q,P) cells are independent: contiguous blocks of cells on several GPUs at once
+        QP = np.ascontiguousarray(QP, dtype=np.float64).reshape(-1, 2)
+        out, valid, nodes, ms = _lib.split_over_devices(
+            devices, len(QP), lambda c, it: c.shell_quadrature(system._c_system(), ϵ, QP[it], exprs, p_res, _root(onlyqroot)))
+    else:
+        out, valid, nodes, ms = _lib.default_context().shell_quadrature(system._c_system(), ϵ, QP, exprs, p_res, _root(onlyqroot))
     last_info.clear()
     last_info.update(kernel_ms=ms, nodes=int(nodes.sum()), cells=int(len(valid)), cells_in_shell=int(valid.sum()))
     return out, valid.astype(bool), scalar
@@ -77,7 +82,7 @@ def matrix_QP_iint_dqdp_delta(system, *, f, ϵ, res=0.1, symmetricQP=False, symm
     symmetricP = symmetricQP if symmetricP is None else symmetricP
     Qs, Ps = _generate_QPs(symmetricQP, symmetricP, res, system, ϵ)
     QP = np.array([(Q, P) for P in Ps for Q in Qs])
-    out, valid, scalar = _run(system, ϵ, QP, f, res, kargs.pop("onlyqroot", None))
+    out, valid, scalar = _run(system, ϵ, QP, f, res, kargs.pop("onlyqroot", None), kargs.pop("devices", None))
     nonvalue = kargs.pop("nonvalue", float("nan"))
     if kargs:
         raise TypeError(f"unsupported keyword(s): {sorted(kargs)}")
@@ -92,12 +97,12 @@ def matrix_QP_iint_dqdp_delta(system, *, f, ϵ, res=0.1, symmetricQP=False, symm
     return Qs, Ps, (mat[..., 0] if scalar else mat)
 
 
-def energy_shell_average(system, *, ϵ, f, res=0.01, symmetricQP=False, symmetricP=None):
+def energy_shell_average(system, *, ϵ, f, res=0.01, symmetricQP=False, symmetricP=None, devices=None):
     """src/EnergyShellProjections.jl:476-508"""
     symmetricP = symmetricQP if symmetricP is None else symmetricP
     Qs, Ps = _generate_QPs(symmetricQP, symmetricP, res, system, ϵ)
     QP = np.array([(Q, P) for Q in Qs for P in Ps])     # the reference's loop order `for Q in Qs, P in Ps`
-    out, valid, scalar = _run(system, ϵ, QP, f, res, None)
+    out, valid, scalar = _run(system, ϵ, QP, f, res, None, devices)
     wq = np.where((QP[:, 0] != 0) & symmetricQP, 2.0, 1.0)
     wp = np.where((QP[:, 1] != 0) & (symmetricP or symmetricQP), 2.0, 1.0)
     wgt = (wq * wp)[valid]

@@ -419,6 +419,40 @@ def default_context() -> Context:
     return _default_ctx
 
 
+_device_ctxs = {}
+
+
+def device_context(dev: int) -> Context:
+    """one cached single-device context per GPU (for batches split over several GPUs, see split_over_devices)"""
+    dev = int(dev)
+    if dev not in _device_ctxs:
+        _device_ctxs[dev] = Context([dev])
+    return _device_ctxs[dev]
+
+
+def split_over_devices(devices, n, call):
+    """Independent batch items (initial conditions, (Q,P) cells) have no exchange step: GPU k of `devices` takes the items
+    k, k+ndev, k+2 ndev, ... (interleaved, so that regions of expensive items spread evenly) and `call(ctx, items)` runs for
+    all GPUs at once (ctypes releases the GIL while the C library runs).  `call` returns a tuple of per-item arrays
+    (first axis = items) and scalars; arrays are scattered back into item order, scalars (times) reduced with max."""
+    import concurrent.futures as cf
+    devices = list(devices)[:max(1, n)]
+    items = [slice(k, n, len(devices)) for k in range(len(devices))]
+    ctxs = [device_context(d) for d in devices]      # (created serially: context creation is not re-entrant)
+    with cf.ThreadPoolExecutor(max_workers=len(devices)) as ex:
+        parts = [f.result() for f in [ex.submit(call, c, it) for c, it in zip(ctxs, items)]]
+    merged = []
+    for j, first in enumerate(parts[0]):
+        if isinstance(first, np.ndarray):
+            full = np.empty((n,) + first.shape[1:], dtype=first.dtype)
+            for it, p in zip(items, parts):
+                full[it] = p[j]
+            merged.append(full)
+        else:
+            merged.append(max(p[j] for p in parts))
+    return tuple(merged)
+
+
 def set_default_context(ctx):
     global _default_ctx
     _default_ctx = ctx

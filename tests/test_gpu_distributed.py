@@ -60,3 +60,32 @@ def test_two_ranks_reproduce_the_single_rank_result(tmp_path, pkg):
     assert np.array_equal(np.rint(hist * N).astype(int), np.array(two["hist"]))          # integer counts: bit-identical for any rank count
     assert np.abs(avg - np.array(two["avg"])).max() < 1e-12
     assert TWA.last_info["steps_accepted"] == two["steps"] and [int(x) for x in TWA.last_info["n_valid"]] == two["n_valid"]
+
+
+def test_independent_batches_split_over_two_gpus(pkg):
+    """Lyapunov maps, sections and dense integration have no exchange step: devices=[0, 1] gives each GPU a contiguous
+    block of initial conditions, and the results equal the single-GPU ones bit for bit"""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from dickemodel_jl_b200 import ClassicalDicke as CD, ClassicalSystems as CS
+    system = CD.ClassicalDickeSystem(w=0.8, g=0.8, w0=1)
+    rng = np.random.default_rng(9)
+    X = np.column_stack([rng.uniform(0.7, 1.4, 301), rng.uniform(-0.5, 0.5, 301), rng.uniform(-0.4, 0.4, 301), rng.uniform(-0.5, 0.5, 301)])
+    l1, s1 = CS.lyapunov_spectrum_batch(system, X, 20, tol=1e-8, maxiters=30)
+    l2, s2 = CS.lyapunov_spectrum_batch(system, X, 20, tol=1e-8, maxiters=30, devices=[0, 1])
+    assert np.array_equal(l1, l2) and np.array_equal(s1, s2)
+    e1 = CS.poincare_section_batch(system, X, 30.0, coef=[0, 0, 0, 1], tol=1e-9, max_events=32)
+    e2 = CS.poincare_section_batch(system, X, 30.0, coef=[0, 0, 0, 1], tol=1e-9, max_events=32, devices=[0, 1])
+    assert np.array_equal(e1["count"], e2["count"]) and np.array_equal(e1["t"], e2["t"], equal_nan=True)
+    o1 = CS.integrate_batch(system, X, [0.0, 1.0, 2.0], tol=1e-9)
+    o2 = CS.integrate_batch(system, X, [0.0, 1.0, 2.0], tol=1e-9, devices=[0, 1])
+    assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(o1, o2))
+    f1 = CS.integrate_fm_batch(system, X[:65], [0.0, 1.5], tol=1e-9)
+    f2 = CS.integrate_fm_batch(system, X[:65], [0.0, 1.5], tol=1e-9, devices=[0, 1])
+    assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(f1, f2))
+    from dickemodel_jl_b200 import EnergyShellProjections as ESP
+    m1 = ESP.matrix_QP_iint_dqdp_delta(system, f=lambda x: [1, x[1] ** 2], ϵ=-0.5, res=0.05)
+    m2 = ESP.matrix_QP_iint_dqdp_delta(system, f=lambda x: [1, x[1] ** 2], ϵ=-0.5, res=0.05, devices=[0, 1])
+    assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(m1, m2))

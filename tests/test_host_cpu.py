@@ -297,3 +297,22 @@ def test_host_logic_of_the_widened_modules(pkg):
         CS.lyapunov_spectrum(system, [1.0, 0.0])
     with pytest.raises(ValueError, match="3x3|4x4"):
         CS.integrate(system, [1.0, 0.3, 1.0, 0.0], 1.0, get_fundamental_matrix=True, fundamental_matrix_initial=np.eye(3))
+
+
+def test_split_over_devices_interleaves_and_restores_item_order(pkg, monkeypatch):
+    """the multi-GPU split of independent batch items (Lyapunov maps, sections, ...) is host logic: item k goes to GPU
+    k mod ndev, per-item arrays come back in item order, times are reduced with max; more GPUs than items is fine"""
+    L = pkg._lib
+    monkeypatch.setattr(L, "device_context", lambda d: d)
+    x = np.arange(11.0)
+    seen = {}
+
+    def call(ctx, items):
+        seen[ctx] = x[items].copy()
+        return x[items] * 2, np.stack([x[items], -x[items]], 1), float(ctx)
+
+    a, b, ms = L.split_over_devices([0, 1, 2], 11, call)
+    assert np.array_equal(a, 2 * x) and np.array_equal(b[:, 1], -x) and ms == 2.0
+    assert np.array_equal(seen[1], [1.0, 4.0, 7.0, 10.0])
+    a, ms = L.split_over_devices([0, 1, 2, 3], 2, lambda c, it: (x[:2][it] + 1, 0.5))
+    assert np.array_equal(a, [1.0, 2.0])

@@ -23,6 +23,7 @@ ap.add_argument("--tol", type=float, default=1e-8)
 ap.add_argument("--alg", default="DP8")
 ap.add_argument("--dt", type=float, default=2.0 ** -6)
 ap.add_argument("--cpu-points", type=int, default=256)
+ap.add_argument("--devices", default="", help="comma-separated GPU ids: split the map over several GPUs (default: one)")
 a = ap.parse_args()
 pkg = graft.load_package()
 CD, CS = pkg.ClassicalDicke, pkg.ClassicalSystems
@@ -32,13 +33,15 @@ Qs = np.linspace(CD.minimum_nonnegative_Q_for_ϵ(system, eps), CD.maximum_Q_for_
 Ps = np.linspace(0, CD.maximum_P_for_ϵ(system, eps), a.n)
 pts = np.array([CD.Point(system, Q=Q, P=P, p=0, ϵ=eps) for Q in Qs for P in Ps if CD.minimum_ϵ_for(system, P=P, p=0, Q=Q) <= eps])
 kw = dict(integrator_alg=a.alg, tol=a.tol, λtol=5e-5) if a.alg not in ("RK4", "RK8") else dict(integrator_alg=a.alg, dt=a.dt, λtol=5e-5)
-CS.lyapunov_spectrum_batch(system, pts[:1024], 100, **kw)   # warm-up
+if a.devices:
+    kw["devices"] = [int(d) for d in a.devices.split(",")]
+CS.lyapunov_spectrum_batch(system, pts[:1024 * max(1, len(kw.get("devices", [0])))], 100, **kw)   # warm-up
 t0 = time.perf_counter()
 lam, status = CS.lyapunov_spectrum_batch(system, pts, 100, **kw)
 wall = time.perf_counter() - t0
 info = CS.last_lyapunov_info
 steps = int(info["nsteps"].sum())
-out = {"what": "Lyapunov map, variational system (4 + 16 variables), one launch", "grid": a.n, "points": int(len(pts)), "alg": a.alg,
+out = {"what": "Lyapunov map, variational system (4 + 16 variables), one launch", "grid": a.n, "devices": kw.get("devices", [0]), "points": int(len(pts)), "alg": a.alg,
        "tol": a.tol, "variational_steps": steps, "kernel_ms": info["kernel_ms"], "wall_s": wall,
        "steps_per_s_kernel": steps / (info["kernel_ms"] * 1e-3), "points_per_s": len(pts) / wall,
        "converged": int((status == 0).sum()), "max_iterations_reached": int((status == 5).sum()),
