@@ -12,7 +12,7 @@ import threading
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libdicketwa.so")
+LIB_PATH = os.environ.get("LIBDICKETWA") or os.path.join(HERE, "csrc", "libdicketwa.so")   # (the override is for A/B builds)
 
 # ---- constants (include/dicketwa.h) ----
 OK = 0

@@ -781,7 +781,7 @@ extern "C" int dtwa_integrate_events(dtwa_ctx *ctx, const dtwa_system *sys, cons
     CK(cudaEventRecord(d.ev[0], d.stream));
     by_system(sys->kind, [&](auto sk) {
         return by_alg(sol->alg, [&](auto ak) {
-            events_kernel<decltype(sk)::value, decltype(ak)::value><<<blocks_for(n, 128), 128, 0, d.stream>>>(
+            events_kernel<decltype(sk)::value, decltype(ak)::value><<<blocks_for(n, EVENTS_BLOCK), EVENTS_BLOCK, 0, d.stream>>>(
                 S, E, (const double *)d.u0.p, n, d_t, d_u, d_dir, d_cnt, d_end, d_st, (long long *)d.scratch_c.p);
             return 0;
         });

@@ -951,8 +951,12 @@ struct EventArgs {
     double offset, t_end;
     int32_t direction, cap;
 };
+#ifndef DTWA_EVENTS_MIN_BLOCKS
+#define DTWA_EVENTS_MIN_BLOCKS 12   // 168 registers (a few spilled doubles), 12 warps per SM: 10 % faster than the 212 registers ptxas takes unasked
+#endif
+constexpr int EVENTS_BLOCK = 32;   // one warp per CTA: lanes of a warp share the refinement service, warps share nothing
 template <int SYS, int ALG>
-__global__ void __launch_bounds__(128) events_kernel(const SolverArgs S, const EventArgs E, const double *__restrict__ u0,
+__global__ void __launch_bounds__(EVENTS_BLOCK, DTWA_EVENTS_MIN_BLOCKS) events_kernel(const SolverArgs S, const EventArgs E, const double *__restrict__ u0,
                                                      long long n, double *__restrict__ ev_t, double *__restrict__ ev_u,
                                                      int32_t *__restrict__ ev_dir, int32_t *__restrict__ ev_count,
                                                      double *__restrict__ u_end, int32_t *__restrict__ status,
@@ -1009,66 +1013,37 @@ __global__ void __launch_bounds__(128) events_kernel(const SolverArgs S, const E
     // (step-start state, its time; the bracket [plo, phi] of step fractions -- in time units -- that holds the
     //  crossing, and g at its ends: the whole step for an ordinary crossing, one side of the extremum for a tangency)
     double ps[NV], pts0 = 0.0, plo = 0.0, phi = 0.0, pg0 = 0.0, pg1 = 0.0;
-    auto refine = [&]() {   // executed by all lanes with a noted crossing at once
-        double lo = plo, hi = phi, glo = pg0;
-        double th = lo + (hi - lo) * (pg0 / (pg0 - pg1));   // chord
-        double z[NV], g2 = pg1;
+    // The refinement service.  Every integrator body is inlined exactly ONCE in this kernel (the adaptive attempt, the
+    // own-step map, the Henon step): a lane's refinement jobs -- its noted crossing, the probe of a tangency at the
+    // interpolant's extremum, the one or two crossings of a tangency -- all go through one loop as a small per-lane
+    // state machine.  (Five inlined copies of the refinement, as in the first version, made 255 registers with spills
+    // and an instruction-cache-bound kernel.)
+    enum { SV_IDLE = 0, SV_NEWTON = 1, SV_PROBE = 2, SV_FIN = 3 };
+    int mode = SV_IDLE, nit = 0;
+    double lo = 0.0, hi = 0.0, glo = 0.0, th = 0.0, g2 = 0.0, gx = 0.0, z[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) z[i] = ps[i] = 0.0;
+    auto start_newton = [&]() {   // chord estimate inside the bracket of the noted crossing
+        lo = plo;
+        hi = phi;
+        glo = pg0;
+        th = lo + (hi - lo) * (pg0 / (pg0 - pg1));
         if (pg1 == 0.0) th = hi;
-#pragma unroll 1
-        for (int it = 0; it < 8; ++it) {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) z[i] = ps[i];
-            own_step(z, th);
-            g2 = gfun(z);
-            if (it == 7 || fabs(g2) <= 1e-13) break;
-            if ((g2 < 0.0) == (glo < 0.0)) {              // keep the bracket
-                lo = th;
-                glo = g2;
-            } else
-                hi = th;
-            double f[NV], gd = 0.0;                       // Newton on the crossing time, bisection when it leaves the bracket
-            Sys<SYS>::rhs(S.par, z, f);
-#pragma unroll
-            for (int i = 0; i < NV; ++i) gd = fma(E.coef[i], f[i], gd);
-            double tn = th - g2 / gd;
-            if (!(tn > lo) || !(tn < hi)) tn = 0.5 * (lo + hi);
-            th = tn;
-        }
-        double y[NV + 1];
-#pragma unroll
-        for (int i = 0; i < NV; ++i) y[i] = z[i];
-        y[NV] = pts0 + th;
-        if (g2 != 0.0) {
-            henon(y, -g2);                                // |g2| is at rounding level unless Newton left the step
-            bool fin = true;
-#pragma unroll
-            for (int i = 0; i <= NV; ++i) fin = fin && (y[i] == y[i]) && !isinf(y[i]);
-            if (!fin) {
-#pragma unroll
-                for (int i = 0; i < NV; ++i) y[i] = z[i];
-                y[NV] = pts0 + th;
-            }
-        }
-        if (count < E.cap && live) {
-            const size_t e = (size_t)j * E.cap + count;
-            ev_t[e] = y[NV];
-#pragma unroll
-            for (int i = 0; i < NV; ++i) ev_u[e * NV + i] = y[i];
-            ev_dir[e] = (pg0 < 0.0) ? 1 : -1;
-        }
-        ++count;
-        pending = false;
+        nit = 0;
+        mode = SV_NEWTON;
     };
     const StepTab r = FIXED ? S.tab[0] : StepTab();
     int sidx = 0;
     bool done = !(T.status == ST_OK && E.t_end > 0.0);
 #pragma unroll 1
-    while (__any_sync(0xffffffffu, !done)) {
+    while (true) {
+        const bool all_done = !__any_sync(0xffffffffu, !done);
+        if (all_done && !__any_sync(0xffffffffu, pending)) break;
         bool cross = false, accepted = false, tang = false;
         double cs[NV], cts0 = 0.0, chs = 0.0, cg1 = 0.0, gd0 = 0.0, thx = 0.0;
-        if (!done) {
 #pragma unroll
-            for (int i = 0; i < NV; ++i) cs[i] = T.u[i];
+        for (int i = 0; i < NV; ++i) cs[i] = T.u[i];
+        if (!done) {
             if constexpr (!FIXED) {   // dg/dt at the step start, from the FSAL derivative
 #pragma unroll
                 for (int i = 0; i < NV; ++i) gd0 = fma(E.coef[i], T.ad.k0[i], gd0);
@@ -1130,8 +1105,8 @@ __global__ void __launch_bounds__(128) events_kernel(const SolverArgs S, const E
                             x = (x1 > 0.0 && x1 < 1.0) ? x1 : x2;
                         }
                         if (x > 0.0 && x < 1.0) {
-                            const double gx = g0 + x * (d0 + x * (c2 + x * c3));
-                            if (gx * g0 < 0.0) {
+                            const double gxi = g0 + x * (d0 + x * (c2 + x * c3));
+                            if (gxi * g0 < 0.0) {
                                 tang = true;
                                 thx = x * chs;
                             }
@@ -1140,9 +1115,104 @@ __global__ void __launch_bounds__(128) events_kernel(const SolverArgs S, const E
                 }
             }
         }
-        // refine the noted crossings together when a lane needs its slot again ...
-        if (__any_sync(0xffffffffu, cross && pending)) {
-            if (pending) refine();
+        // Noted crossings are refined together when some lane needs its slot again (it crossed again, or it met a
+        // tangency, which it handles in time order: noted crossing first), or when every lane has finished.
+        if (all_done || __any_sync(0xffffffffu, (cross && pending) || tang)) {
+            bool probe_left = tang, second = false;
+            if (pending)
+                start_newton();
+            else if (probe_left) {
+                probe_left = false;
+                mode = SV_PROBE;
+                th = thx;
+            }
+#pragma unroll 1
+            while (true) {
+                const bool stepping = mode == SV_NEWTON || mode == SV_PROBE;
+                if (__any_sync(0xffffffffu, stepping)) {
+                    if (stepping) {   // the integrator's own step from the start of the crossing step
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) z[i] = (mode == SV_PROBE) ? cs[i] : ps[i];
+                        own_step(z, th);
+                        g2 = gfun(z);
+                        if (mode == SV_PROBE) {   // the integrator's own value at the interpolant's extremum
+                            mode = SV_IDLE;
+                            if (g2 * g0 < 0.0) {
+                                const bool first_up = g0 < 0.0;
+                                const bool want1 = (first_up && E.direction >= 0) || (!first_up && E.direction <= 0);
+                                const bool want2 = (!first_up && E.direction >= 0) || (first_up && E.direction <= 0);
+                                gx = g2;
+#pragma unroll
+                                for (int i = 0; i < NV; ++i) ps[i] = cs[i];
+                                pts0 = cts0;
+                                if (want1) {
+                                    plo = 0.0; phi = thx; pg0 = g0; pg1 = gx;
+                                    second = want2;
+                                    start_newton();
+                                } else if (want2) {
+                                    plo = thx; phi = chs; pg0 = gx; pg1 = cg1;
+                                    start_newton();
+                                }
+                            }
+                        } else if (nit == 7 || fabs(g2) <= 1e-13) {
+                            mode = SV_FIN;
+                        } else {
+                            if ((g2 < 0.0) == (glo < 0.0)) {              // keep the bracket
+                                lo = th;
+                                glo = g2;
+                            } else
+                                hi = th;
+                            double f[NV], gd = 0.0;                       // Newton on the crossing time, bisection when it leaves the bracket
+                            Sys<SYS>::rhs(S.par, z, f);
+#pragma unroll
+                            for (int i = 0; i < NV; ++i) gd = fma(E.coef[i], f[i], gd);
+                            double tn = th - g2 / gd;
+                            if (!(tn > lo) || !(tn < hi)) tn = 0.5 * (lo + hi);
+                            th = tn;
+                            ++nit;
+                        }
+                    }
+                    continue;
+                }
+                // no lane is stepping: the located crossings take their Henon step together
+                if (!__any_sync(0xffffffffu, mode == SV_FIN)) break;
+                if (mode == SV_FIN) {
+                    double y[NV + 1];
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) y[i] = z[i];
+                    y[NV] = pts0 + th;
+                    if (g2 != 0.0) {
+                        henon(y, -g2);                            // |g2| is at rounding level unless Newton left the step
+                        bool fin = true;
+#pragma unroll
+                        for (int i = 0; i <= NV; ++i) fin = fin && (y[i] == y[i]) && !isinf(y[i]);
+                        if (!fin) {
+#pragma unroll
+                            for (int i = 0; i < NV; ++i) y[i] = z[i];
+                            y[NV] = pts0 + th;
+                        }
+                    }
+                    if (count < E.cap && live) {
+                        const size_t e = (size_t)j * E.cap + count;
+                        ev_t[e] = y[NV];
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) ev_u[e * NV + i] = y[i];
+                        ev_dir[e] = (pg0 < 0.0) ? 1 : -1;
+                    }
+                    ++count;
+                    pending = false;
+                    mode = SV_IDLE;
+                    if (second) {            // the way back through the section of a tangency
+                        second = false;
+                        plo = thx; phi = chs; pg0 = gx; pg1 = cg1;
+                        start_newton();
+                    } else if (probe_left) {
+                        probe_left = false;
+                        mode = SV_PROBE;
+                        th = thx;
+                    }
+                }
+            }
         }
         if (cross) {
             pending = true;
@@ -1154,33 +1224,7 @@ __global__ void __launch_bounds__(128) events_kernel(const SolverArgs S, const E
             pg0 = g0;
             pg1 = cg1;
         }
-        if (tang) {   // rare: handled by the lane on its own, in time order
-            if (pending) refine();
-            double z[NV];
-#pragma unroll
-            for (int i = 0; i < NV; ++i) z[i] = cs[i];
-            own_step(z, thx);
-            const double gx = gfun(z);                    // the integrator's own value at the interpolant's extremum
-            if (gx * g0 < 0.0) {
-                const bool first_up = g0 < 0.0;
-#pragma unroll
-                for (int i = 0; i < NV; ++i) ps[i] = cs[i];
-                pts0 = cts0;
-                if ((first_up && E.direction >= 0) || (!first_up && E.direction <= 0)) {
-                    plo = 0.0; phi = thx; pg0 = g0; pg1 = gx;
-                    refine();
-                }
-                if ((!first_up && E.direction >= 0) || (first_up && E.direction <= 0)) {
-                    plo = thx; phi = chs; pg0 = gx; pg1 = cg1;
-                    refine();
-                }
-            }
-        }
         if (accepted) g0 = cg1;
-        // ... or when every lane of the warp has finished
-        if (!__any_sync(0xffffffffu, !done) && __any_sync(0xffffffffu, pending)) {
-            if (pending) refine();
-        }
     }
     if (live) {
         ev_count[j] = count;
