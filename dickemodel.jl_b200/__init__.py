@@ -11,10 +11,10 @@ fallback: importing works anywhere, computing needs the built library and a B200
 """
 from . import _lib  # noqa: F401
 from . import symbolic, PhaseSpaces, ClassicalSystems, ClassicalDicke, ClassicalLMG, TWA, distributed  # noqa: F401
-from . import EnergyShellProjections, DickeBCE  # noqa: F401
+from . import EnergyShellProjections, DickeBCE, UPOs  # noqa: F401
 from ._lib import Context, DtwaError, default_context, set_default_context, set_distributed, load as load_library  # noqa: F401
 
-__all__ = ["ClassicalSystems", "ClassicalDicke", "ClassicalLMG", "PhaseSpaces", "TWA", "EnergyShellProjections", "DickeBCE", "symbolic", "Context",
+__all__ = ["ClassicalSystems", "ClassicalDicke", "ClassicalLMG", "PhaseSpaces", "TWA", "EnergyShellProjections", "DickeBCE", "UPOs", "symbolic", "Context",
            "DtwaError", "default_context", "set_default_context", "set_distributed", "load_library"]
 
 
@@ -23,7 +23,7 @@ def _add_unnormalised_aliases():
     `ClassicalDicke.q_of_ϵ` written in a script finds `q_of_ε`.  getattr() with the reference's raw spelling does not
     normalise: register those spellings too."""
     import types
-    for mod in (ClassicalDicke, ClassicalLMG, ClassicalSystems, PhaseSpaces, TWA, EnergyShellProjections):
+    for mod in (ClassicalDicke, ClassicalLMG, ClassicalSystems, PhaseSpaces, TWA, EnergyShellProjections, UPOs):
         for name, obj in list(vars(mod).items()):
             if name.startswith("_") or isinstance(obj, types.ModuleType):
                 continue
