@@ -153,21 +153,37 @@ struct Sys<DTWA_SYS_LMG> {
 //   d/dt (x, Phi) = (f(x), J(x) Phi),  J = df/dx  (the reference takes `step(system).jac` from
 //   ParameterizedFunctions' symbolic differentiation; here it is written out).
 // The columns of Phi are independent given x(t), so a GROUP of NVB adjacent threads integrates one
-// initial condition: thread c carries x (redundantly, bit-identical in every thread of the group) and
-// column c of Phi -- 2*NVB doubles per thread instead of NVB + NVB^2, everything stays in registers.
-// Only the error norm of the adaptive pairs couples the columns: group-wide sums over NORM_N =
-// NVB + NVB^2 components (x counted once), combined with a butterfly of shuffles inside the group.
+// initial condition: thread c carries COMPONENT c of x and column c of Phi -- state y = [x_c | Phi_{.,c}],
+// 1 + NVB doubles per thread instead of NVB + NVB^2, everything stays in registers.  Every right-hand side
+// gathers x from the group (NVB shuffles) and evaluates f and J once per thread; the stage sums -- most of
+// the work of the 12-stage pair -- are not replicated.  (The first version carried all of x in every thread:
+// 8 instead of 5 components per thread in every stage sum, 234 registers instead of 170.)
+// The error norm of the adaptive pairs is a group-wide sum over the NORM_N = NVB + NVB^2 components,
+// combined with a butterfly of shuffles inside the group, so all threads of a group take the same steps.
 constexpr int DTWA_SYS_DICKE_VAR = 2, DTWA_SYS_LMG_VAR = 3;
+template <int G>
+__device__ __forceinline__ unsigned group_base()
+{
+    return (threadIdx.x & 31u) & ~(unsigned)(G - 1);
+}
+template <int G>
+__device__ __forceinline__ unsigned group_mask()
+{
+    return ((1u << G) - 1u) << group_base<G>();
+}
 
 template <>
 struct Sys<DTWA_SYS_DICKE_VAR> {
-    static constexpr int NV = 8;
-    static constexpr int QI = 0, PI = 2;
+    static constexpr int NV = 5;
+    static constexpr int QI = 0, PI = 2;   // group lanes that hold Q and P
     static constexpr int NVB = 4, GROUP = 4, NORM_N = 20;
-    __device__ __forceinline__ static void rhs(const SysPar &p, const double (&y)[8], double (&dy)[8])
+    __device__ __forceinline__ static void rhs(const SysPar &p, const double (&y)[5], double (&dy)[5])
     {
-        const double Q = y[0], q = y[1], P = y[2], pp = y[3];
-        const double a = y[4], b = y[5], c = y[6], d = y[7];   // perturbation of (Q, q, P, p)
+        const unsigned gb = group_base<4>(), gm = group_mask<4>();
+        const int lane_c = (int)(threadIdx.x & 3u);
+        const double Q = __shfl_sync(gm, y[0], (int)gb + 0), q = __shfl_sync(gm, y[0], (int)gb + 1);
+        const double P = __shfl_sync(gm, y[0], (int)gb + 2), pp = __shfl_sync(gm, y[0], (int)gb + 3);
+        const double a = y[1], b = y[2], c = y[3], d = y[4];   // perturbation of (Q, q, P, p)
         double r2 = fma(-P, P, 4.0);
         r2 = fma(-Q, Q, r2);
         double is, s;
@@ -175,10 +191,11 @@ struct Sys<DTWA_SYS_DICKE_VAR> {
         const double gq = __dmul_rn(p.c, q);
         const double f = __dmul_rn(__dmul_rn(gq, Q), is);       // g q Q / s
         const double e = f - p.a;                               // f - w0
-        dy[0] = __dmul_rn(-P, e);
-        dy[1] = __dmul_rn(pp, p.b);
-        dy[2] = fma(Q, e, -__dmul_rn(gq, s));
-        dy[3] = fma(-p.c, __dmul_rn(Q, s), -__dmul_rn(q, p.b));
+        const double f0 = __dmul_rn(-P, e);
+        const double f1 = __dmul_rn(pp, p.b);
+        const double f2 = fma(Q, e, -__dmul_rn(gq, s));
+        const double f3 = fma(-p.c, __dmul_rn(Q, s), -__dmul_rn(q, p.b));
+        dy[0] = (lane_c & 2) ? ((lane_c & 1) ? f3 : f2) : ((lane_c & 1) ? f1 : f0);   // this thread's component of f(x)
         // df = f_Q a + f_q b + f_P c,  ds = -(Q a + P c)/s
         const double is2 = __dmul_rn(is, is);
         const double fQ = __dmul_rn(__dmul_rn(gq, is), fma(__dmul_rn(Q, Q), is2, 1.0));   // g q (1/s + Q^2/s^3)
@@ -186,30 +203,31 @@ struct Sys<DTWA_SYS_DICKE_VAR> {
         const double fP = __dmul_rn(__dmul_rn(f, P), is2);                                // g q Q P / s^3
         const double df = fma(fQ, a, fma(fq, b, __dmul_rn(fP, c)));
         const double ds = -__dmul_rn(fma(Q, a, __dmul_rn(P, c)), is);
-        dy[4] = fma(-P, df, -__dmul_rn(c, e));                                            // c (w0 - f) - P df
-        dy[5] = __dmul_rn(d, p.b);
-        dy[6] = fma(a, e, fma(Q, df, -__dmul_rn(p.c, fma(b, s, __dmul_rn(q, ds)))));      // a (f - w0) + Q df - g (b s + q ds)
-        dy[7] = fma(-p.c, fma(a, s, __dmul_rn(Q, ds)), -__dmul_rn(b, p.b));               // -g (a s + Q ds) - w b
+        dy[1] = fma(-P, df, -__dmul_rn(c, e));                                            // c (w0 - f) - P df
+        dy[2] = __dmul_rn(d, p.b);
+        dy[3] = fma(a, e, fma(Q, df, -__dmul_rn(p.c, fma(b, s, __dmul_rn(q, ds)))));      // a (f - w0) + Q df - g (b s + q ds)
+        dy[4] = fma(-p.c, fma(a, s, __dmul_rn(Q, ds)), -__dmul_rn(b, p.b));               // -g (a s + Q ds) - w b
     }
 };
 
 template <>
 struct Sys<DTWA_SYS_LMG_VAR> {
-    static constexpr int NV = 4;
-    static constexpr int QI = 0, PI = 1;
+    static constexpr int NV = 3;
+    static constexpr int QI = 0, PI = 1;   // group lanes that hold Q and P
     static constexpr int NVB = 2, GROUP = 2, NORM_N = 6;
-    __device__ __forceinline__ static void rhs(const SysPar &p, const double (&y)[4], double (&dy)[4])
+    __device__ __forceinline__ static void rhs(const SysPar &p, const double (&y)[3], double (&dy)[3])
     {
-        const double Q = y[0], P = y[1], a = y[2], c = y[3];
+        const unsigned gb = group_base<2>(), gm = group_mask<2>();
+        const double Q = __shfl_sync(gm, y[0], (int)gb + 0), P = __shfl_sync(gm, y[0], (int)gb + 1);
+        const double a = y[1], c = y[2];
         const double Q2 = __dmul_rn(Q, Q), P2 = __dmul_rn(P, P);
         const double A = fma(-p.c, Q2, p.a);                  // Om - xi Q^2/2   = d(dQ)/dP
-        dy[0] = __dmul_rn(P, A);
         const double in = fma(p.c, P2, -p.d);                 // xi P^2/2 - (2 xi + Om)
-        dy[1] = __dmul_rn(Q, fma(p.b, Q2, in));
+        dy[0] = (threadIdx.x & 1u) ? __dmul_rn(Q, fma(p.b, Q2, in)) : __dmul_rn(P, A);   // this thread's component of f(x)
         const double xQP = __dmul_rn(p.b, __dmul_rn(Q, P));   // xi Q P
         const double B = fma(__dmul_rn(3.0, p.b), Q2, in);    // d(dP)/dQ
-        dy[2] = fma(A, c, -__dmul_rn(xQP, a));
-        dy[3] = fma(B, a, __dmul_rn(xQP, c));
+        dy[1] = fma(A, c, -__dmul_rn(xQP, a));
+        dy[2] = fma(B, a, __dmul_rn(xQP, c));
     }
 };
 
@@ -247,14 +265,11 @@ struct Sys<DTWA_SYS_DICKE_HENON> : HenonSys<DTWA_SYS_DICKE> {};
 template <>
 struct Sys<DTWA_SYS_LMG_HENON> : HenonSys<DTWA_SYS_LMG> {};
 
-// does component i of this thread enter the group-wide norms?  (x is replicated: thread 0 of the group counts it)
+// does component i of this thread enter the group-wide norms?  (always: no component is replicated in a group)
 template <int SYS>
-__device__ __forceinline__ bool norm_counted(int i)
+__device__ __forceinline__ bool norm_counted(int)
 {
-    if constexpr (Sys<SYS>::GROUP == 1)
-        return true;
-    else
-        return i >= Sys<SYS>::NVB || (threadIdx.x & (Sys<SYS>::GROUP - 1)) == 0;
+    return true;
 }
 // sum over the threads of a group; every thread of the group receives the same bits
 template <int SYS>
@@ -262,8 +277,7 @@ __device__ __forceinline__ double group_sum(double s)
 {
     if constexpr (Sys<SYS>::GROUP > 1) {
         constexpr int G = Sys<SYS>::GROUP;
-        const unsigned base = (threadIdx.x & 31u) & ~(unsigned)(G - 1);
-        const unsigned mask = ((1u << G) - 1u) << base;
+        const unsigned mask = group_mask<G>();
 #pragma unroll
         for (int off = G / 2; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_xor_sync(mask, s, off));
     }
@@ -286,21 +300,27 @@ __device__ __forceinline__ bool state_bad(const double (&u)[Sys<SYS>::NV])
     // non-finite anywhere, or outside the chart 4 - P^2 - Q^2 > 0 (un-fused, src/ClassicalDicke.jl:19).
     // A non-finite Q or P makes r2 NaN or -Inf; the other components are tested on their exponent
     // bits (integer pipe -- this runs at every output time, next to a saturated FP64 pipe).
-    const double Q = u[Sys<SYS>::QI], P = u[Sys<SYS>::PI];
-    const double r2 = __dsub_rn(__dsub_rn(4.0, __dmul_rn(P, P)), __dmul_rn(Q, Q));
-    bool nonfinite = false;
-#pragma unroll
-    for (int i = 0; i < Sys<SYS>::NV; ++i)
-        if (i != Sys<SYS>::QI && i != Sys<SYS>::PI) nonfinite |= ((__double2hiint(u[i]) & 0x7ff00000) == 0x7ff00000);
-    bool bad = nonfinite || !(r2 > 0.0);
     if constexpr (Sys<SYS>::GROUP > 1) {
-        // one decision per group (a non-finite column must stop every thread of the group)
+        // variational systems: Q and P live in two lanes of the group; one decision per group (a non-finite
+        // column must stop every thread of the group)
         constexpr int G = Sys<SYS>::GROUP;
-        const unsigned base = (threadIdx.x & 31u) & ~(unsigned)(G - 1);
-        const unsigned mask = ((1u << G) - 1u) << base;
-        bad = (__ballot_sync(mask, bad) & mask) != 0u;
+        const unsigned base = group_base<G>(), mask = group_mask<G>();
+        const double Q = __shfl_sync(mask, u[0], (int)base + Sys<SYS>::QI), P = __shfl_sync(mask, u[0], (int)base + Sys<SYS>::PI);
+        const double r2 = __dsub_rn(__dsub_rn(4.0, __dmul_rn(P, P)), __dmul_rn(Q, Q));
+        bool nonfinite = false;
+#pragma unroll
+        for (int i = 0; i < Sys<SYS>::NV; ++i) nonfinite |= ((__double2hiint(u[i]) & 0x7ff00000) == 0x7ff00000);
+        const bool bad = nonfinite || !(r2 > 0.0);
+        return (__ballot_sync(mask, bad) & mask) != 0u;
+    } else {
+        const double Q = u[Sys<SYS>::QI], P = u[Sys<SYS>::PI];
+        const double r2 = __dsub_rn(__dsub_rn(4.0, __dmul_rn(P, P)), __dmul_rn(Q, Q));
+        bool nonfinite = false;
+#pragma unroll
+        for (int i = 0; i < Sys<SYS>::NV; ++i)
+            if (i != Sys<SYS>::QI && i != Sys<SYS>::PI) nonfinite |= ((__double2hiint(u[i]) & 0x7ff00000) == 0x7ff00000);
+        return nonfinite || !(r2 > 0.0);
     }
-    return bad;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(128) integrate_kernel(const SolverArgs S, cons
 // ------------------------------------------------------------------------------------------------
 // K5: trajectories with their fundamental matrix (src/ClassicalSystems.jl:110-128).  SYS is one of the
 // variational systems; GROUP adjacent threads share one initial condition (dtwa_device.cuh).
-//   out_u [n][nt][NVB], out_fm[n][nt][NVB*NVB] column-major (Julia's layout): thread c writes column c.
+//   out_u [n][nt][NVB], out_fm[n][nt][NVB*NVB] column-major (Julia's layout): thread c writes x_c and column c.
 template <int SYS, int ALG>
 __global__ void __launch_bounds__(128) integrate_fm_kernel(const SolverArgs S, const double *__restrict__ u0,
                                                            const double *__restrict__ fm0, long long n,
@@ -785,10 +785,9 @@ __global__ void __launch_bounds__(128) integrate_fm_kernel(const SolverArgs S, c
     Traj<SYS, ALG> T;
     T.status = ST_OK;
 #pragma unroll
-    for (int i = 0; i < NVB; ++i) {
-        T.u[i] = u0[j * NVB + i];
-        T.u[NVB + i] = fm0 ? fm0[(j * NVB + c) * NVB + i] : (i == c ? 1.0 : 0.0);
-    }
+    T.u[0] = u0[j * NVB + c];
+#pragma unroll
+    for (int i = 0; i < NVB; ++i) T.u[1 + i] = fm0 ? fm0[(j * NVB + c) * NVB + i] : (i == c ? 1.0 : 0.0);
     T.begin(S);
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
     for (int k = 0; k < S.nt; ++k) {
@@ -796,14 +795,10 @@ __global__ void __launch_bounds__(128) integrate_fm_kernel(const SolverArgs S, c
         if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
         if (live) {
             const bool ok = T.status == ST_OK;
-            if (c == 0) {
-                double *o = out_u + ((size_t)j * S.nt + k) * NVB;
-#pragma unroll
-                for (int i = 0; i < NVB; ++i) o[i] = ok ? T.u[i] : qnan;
-            }
+            out_u[((size_t)j * S.nt + k) * NVB + c] = ok ? T.u[0] : qnan;
             double *o = out_fm + (((size_t)j * S.nt + k) * NVB + c) * NVB;
 #pragma unroll
-            for (int i = 0; i < NVB; ++i) o[i] = ok ? T.u[NVB + i] : qnan;
+            for (int i = 0; i < NVB; ++i) o[i] = ok ? T.u[1 + i] : qnan;
         }
     }
     if (live && c == 0) {
@@ -825,8 +820,11 @@ struct LyapArgs {
 };
 // Orbits need very different numbers of rounds (4 .. maxiters), so the groups of a persistent grid draw their
 // next initial condition from a global counter (`next`, zeroed by the host) instead of owning a fixed one.
+#ifndef DTWA_LYAP_MIN_BLOCKS
+#define DTWA_LYAP_MIN_BLOCKS 3   // 168 registers, 12 warps per SM (3 % faster than 210 registers at 8 warps: the kernel is latency-bound)
+#endif
 template <int SYS, int ALG>
-__global__ void __launch_bounds__(128) lyapunov_kernel(const SolverArgs S, const LyapArgs L, const double *__restrict__ u0,
+__global__ void __launch_bounds__(128, DTWA_LYAP_MIN_BLOCKS) lyapunov_kernel(const SolverArgs S, const LyapArgs L, const double *__restrict__ u0,
                                                        long long n, double *__restrict__ lambda_out,
                                                        double *__restrict__ x_out, int32_t *__restrict__ iters_out,
                                                        int32_t *__restrict__ status, long long *__restrict__ nsteps,
@@ -844,11 +842,10 @@ __global__ void __launch_bounds__(128) lyapunov_kernel(const SolverArgs S, const
     if (jn >= (unsigned long long)n) break;
     const long long j = (long long)jn;
     const bool live = true;
-    double x[NVB], w[NVB], lam[NVB], lam_old[NVB];
+    double xc = u0[j * NVB + c], w[NVB], lam[NVB], lam_old[NVB];   // this thread's component of x, its column of Phi
     double sums = 0.0;
 #pragma unroll
     for (int i = 0; i < NVB; ++i) {
-        x[i] = u0[j * NVB + i];
         w[i] = (i == c) ? 1.0 : 0.0;
         lam[i] = 0.0;
     }
@@ -862,11 +859,9 @@ __global__ void __launch_bounds__(128) lyapunov_kernel(const SolverArgs S, const
         for (int i = 0; i < NVB; ++i) lam_old[i] = lam[i];
         Traj<SYS, ALG> T;
         T.status = ST_OK;
+        T.u[0] = xc;
 #pragma unroll
-        for (int i = 0; i < NVB; ++i) {
-            T.u[i] = x[i];
-            T.u[NVB + i] = w[i];
-        }
+        for (int i = 0; i < NVB; ++i) T.u[1 + i] = w[i];
         T.begin(S);
         T.advance(S, 0);
         if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
@@ -875,11 +870,9 @@ __global__ void __launch_bounds__(128) lyapunov_kernel(const SolverArgs S, const
             st = T.status;
             break;
         }
+        xc = T.u[0];
 #pragma unroll
-        for (int i = 0; i < NVB; ++i) {
-            x[i] = T.u[i];
-            w[i] = T.u[NVB + i];
-        }
+        for (int i = 0; i < NVB; ++i) w[i] = T.u[1 + i];
         const double kt = __dmul_rn((double)k, L.t_interval);
 #pragma unroll
         for (int i = 0; i < NVB; ++i) {
@@ -920,12 +913,10 @@ __global__ void __launch_bounds__(128) lyapunov_kernel(const SolverArgs S, const
         }
     }
     if (st == ST_OK && !done) st = DTWA_LYAP_MAXITERS;
+    if (live && x_out) x_out[j * NVB + c] = xc;
     if (live && c == 0) {
 #pragma unroll
-        for (int i = 0; i < NVB; ++i) {
-            lambda_out[j * NVB + i] = lam[i];
-            if (x_out) x_out[j * NVB + i] = x[i];
-        }
+        for (int i = 0; i < NVB; ++i) lambda_out[j * NVB + i] = lam[i];
         iters_out[j] = it;
         status[j] = st;
         if (nsteps) nsteps[j] = steps;
