@@ -279,20 +279,48 @@ def integrate_fm_batch(system, U0, ts, fundamental_matrix_initial=None, **kargs)
     return _lib.default_context().integrate_fm(system._c_system(), sol, U0, ts, fundamental_matrix_initial)
 
 
-def poincare_section_batch(system, U0, t, *, coef, offset=0.0, direction=0, max_events=1024, **kargs):
+def poincare_section_batch(system, U0, t, *, coef, offset=0.0, direction=0, max_events=1024, packed=False, **kargs):
     """Crossings of the section coef . u = offset for many initial conditions in one launch (the docs' Poincare
     surface, docs/src/ClassicalDickeExamples.md:82-109, draws one `integrate` per initial condition).
     Returns a dict: t[n][cap], u[n][cap][nvar], direction[n][cap], count[n], u_end, status, nsteps, kernel_ms;
-    unused slots are NaN."""
+    unused slots are NaN.  packed=True (large batches): t[total], u[total][nvar], direction[total] and offsets[n+1]
+    instead -- initial condition i owns the entries offsets[i]:offsets[i+1] -- compacted on the GPU, so that neither the
+    transfer nor the host arrays carry the [n][max_events] padding."""
     devices = kargs.pop("devices", None)
     sol = solver_from_kargs(kargs)
+    csys = system._c_system()
+    if packed:
+        if devices:
+            U0 = np.ascontiguousarray(U0, dtype=np.float64).reshape(-1, len(system.varnames()))
+            n, devices = len(U0), list(devices)[:max(1, len(U0))]
+            items = [slice(k, n, len(devices)) for k in range(len(devices))]
+            parts = _lib.run_on_devices(devices, [lambda c, it=it: c.integrate_events_packed(csys, sol, U0[it], t, coef, offset, direction, max_events)
+                                                   for it in items])
+            cnt, status, nsteps = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int64)
+            u_end = np.empty_like(U0)
+            for it, p in zip(items, parts):
+                cnt[it], u_end[it], status[it], nsteps[it] = p[4], p[5], p[6], p[7]
+            offsets = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(np.minimum(cnt, max_events), out=offsets[1:])
+            total = int(offsets[-1])
+            ev_t, ev_u, ev_dir = np.empty(total), np.empty((total, U0.shape[1])), np.empty(total, dtype=np.int32)
+            for it, p in zip(items, parts):      # every GPU's rows go to their places in item order
+                loc = p[0]
+                rows = np.repeat(np.arange(len(loc) - 1), np.diff(loc))
+                dest = offsets[:-1][it][rows] + (np.arange(int(loc[-1])) - loc[:-1][rows])
+                ev_t[dest], ev_u[dest], ev_dir[dest] = p[1], p[2], p[3]
+            ms = max(p[8] for p in parts)
+        else:
+            offsets, ev_t, ev_u, ev_dir, cnt, u_end, status, nsteps, ms = _lib.default_context().integrate_events_packed(
+                csys, sol, U0, t, coef, offset, direction, max_events)
+        return dict(t=ev_t, u=ev_u, direction=ev_dir, offsets=offsets, count=cnt, u_end=u_end, status=status, nsteps=nsteps, kernel_ms=ms)
     if devices:
         U0 = np.ascontiguousarray(U0, dtype=np.float64).reshape(-1, len(system.varnames()))
         ev_t, ev_u, ev_dir, cnt, u_end, status, nsteps, ms = _lib.split_over_devices(
-            devices, len(U0), lambda c, it: c.integrate_events(system._c_system(), sol, U0[it], t, coef, offset, direction, max_events))
+            devices, len(U0), lambda c, it: c.integrate_events(csys, sol, U0[it], t, coef, offset, direction, max_events))
     else:
         ev_t, ev_u, ev_dir, cnt, u_end, status, nsteps, ms = _lib.default_context().integrate_events(
-            system._c_system(), sol, U0, t, coef, offset, direction, max_events)
+            csys, sol, U0, t, coef, offset, direction, max_events)
     return dict(t=ev_t, u=ev_u, direction=ev_dir, count=cnt, u_end=u_end, status=status, nsteps=nsteps, kernel_ms=ms)
 
 

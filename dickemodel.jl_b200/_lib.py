@@ -29,7 +29,7 @@ EXPORTS = ["dtwa_last_error", "dtwa_version", "dtwa_create", "dtwa_destroy", "dt
            "dtwa_hamiltonian", "dtwa_integrate", "dtwa_sample", "dtwa_pdf", "dtwa_eval_expr", "dtwa_scale_to_index",
            "dtwa_ensemble", "dtwa_ensemble_launch", "dtwa_plan_arenas", "dtwa_plan_fetch", "dtwa_plan_free",
            "dtwa_fp64_peak", "dtwa_fp64_peak_regs", "dtwa_set_jit", "dtwa_jit_compile", "dtwa_integrate_fm", "dtwa_lyapunov", "dtwa_integrate_events",
-           "dtwa_shell_quadrature", "dtwa_jit_quiesce"]
+           "dtwa_integrate_events_packed", "dtwa_integrate_events_packed_fetch", "dtwa_shell_quadrature", "dtwa_jit_quiesce"]
 
 
 class Event(C.Structure):
@@ -127,6 +127,9 @@ def load():
         L.dtwa_integrate_fm.argtypes = [vp, C.POINTER(System), C.POINTER(Solver), dp, dp, C.c_int64, dp, C.c_int32, dp, dp, i32p, i64p]
         L.dtwa_integrate_events.argtypes = [vp, C.POINTER(System), C.POINTER(Solver), dp, C.c_int64, C.c_double, C.POINTER(Event),
                                             C.c_int32, dp, dp, i32p, i32p, dp, i32p, i64p, dp]
+        L.dtwa_integrate_events_packed.argtypes = [vp, C.POINTER(System), C.POINTER(Solver), dp, C.c_int64, C.c_double, C.POINTER(Event),
+                                                   C.c_int32, i64p, i32p, dp, i32p, i64p, dp]
+        L.dtwa_integrate_events_packed_fetch.argtypes = [vp, C.c_int64, dp, dp, i32p]
         L.dtwa_shell_quadrature.argtypes = [vp, C.POINTER(System), C.c_double, dp, C.c_int64, C.POINTER(C.c_char_p), C.c_int32, C.c_double,
                                             C.c_int32, dp, i32p, i32p, dp]
         L.dtwa_lyapunov.argtypes = [vp, C.POINTER(System), C.POINTER(Solver), dp, C.c_int64, C.c_double, C.c_double, C.c_double,
@@ -165,6 +168,7 @@ class Context:
         _check(L.dtwa_create(C.byref(h), ids, len(devices), sp))
         self._h = h
         self.devices = list(devices)
+        self._packed_lock = threading.Lock()
 
     def close(self):
         if getattr(self, "_h", None):
@@ -262,6 +266,29 @@ class Context:
         ev_u[~valid] = np.nan
         ev_dir[~valid] = 0
         return ev_t, ev_u, ev_dir, cnt, u_end, status, nsteps, ms.value
+
+    def integrate_events_packed(self, sys: System, sol: Solver, u0, t_end, coef, offset=0.0, direction=0, max_events=1024):
+        """CSR output: (offsets[n+1], ev_t[total], ev_u[total][nv], ev_dir[total], ev_count[n], u_end[n][nv], status[n],
+        nsteps[n], kernel_ms); row i owns [offsets[i], offsets[i+1])"""
+        nv = 4 if sys.kind == SYS_DICKE else 2
+        u0 = np.ascontiguousarray(u0, dtype=np.float64).reshape(-1, nv)
+        n, cap = u0.shape[0], int(max_events)
+        ev = Event()
+        for i, c in enumerate(np.asarray(coef, dtype=float).ravel()[:nv]):
+            ev.coef[i] = float(c)
+        ev.offset, ev.direction = float(offset), int(direction)
+        offsets, cnt = np.zeros(n + 1, dtype=np.int64), np.empty(n, dtype=np.int32)
+        u_end, status, nsteps = np.empty((n, nv)), np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int64)
+        ms = C.c_double()
+        i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+        with self._packed_lock:      # the packed arrays wait on the device between the two calls
+            _check(load().dtwa_integrate_events_packed(self._h, C.byref(sys), C.byref(sol), _dp(u0), n, float(t_end), C.byref(ev), cap,
+                                                       offsets.ctypes.data_as(i64p), cnt.ctypes.data_as(i32p), _dp(u_end),
+                                                       status.ctypes.data_as(i32p), nsteps.ctypes.data_as(i64p), C.byref(ms)))
+            total = int(offsets[n])
+            ev_t, ev_u, ev_dir = np.empty(total), np.empty((total, nv)), np.empty(total, dtype=np.int32)
+            _check(load().dtwa_integrate_events_packed_fetch(self._h, total, _dp(ev_t), _dp(ev_u), ev_dir.ctypes.data_as(i32p)))
+        return offsets, ev_t, ev_u, ev_dir, cnt, u_end, status, nsteps, ms.value
 
     def shell_quadrature(self, sys: System, eps, QP, exprs, p_res=0.01, onlyqroot=0):
         """(out[ncell][nexpr] (NaN = outside the shell), valid[ncell], nodes[ncell], kernel_ms)"""
@@ -430,17 +457,22 @@ def device_context(dev: int) -> Context:
     return _device_ctxs[dev]
 
 
+def run_on_devices(devices, calls):
+    """calls[k](context of devices[k]) for all k at once (host threads; ctypes releases the GIL inside the C library)"""
+    import concurrent.futures as cf
+    ctxs = [device_context(d) for d in devices]      # (created serially: context creation is not re-entrant)
+    with cf.ThreadPoolExecutor(max_workers=len(calls)) as ex:
+        return [f.result() for f in [ex.submit(call, c) for call, c in zip(calls, ctxs)]]
+
+
 def split_over_devices(devices, n, call):
     """Independent batch items (initial conditions, (Q,P) cells) have no exchange step: GPU k of `devices` takes the items
     k, k+ndev, k+2 ndev, ... (interleaved, so that regions of expensive items spread evenly) and `call(ctx, items)` runs for
     all GPUs at once (ctypes releases the GIL while the C library runs).  `call` returns a tuple of per-item arrays
     (first axis = items) and scalars; arrays are scattered back into item order, scalars (times) reduced with max."""
-    import concurrent.futures as cf
     devices = list(devices)[:max(1, n)]
     items = [slice(k, n, len(devices)) for k in range(len(devices))]
-    ctxs = [device_context(d) for d in devices]      # (created serially: context creation is not re-entrant)
-    with cf.ThreadPoolExecutor(max_workers=len(devices)) as ex:
-        parts = [f.result() for f in [ex.submit(call, c, it) for c, it in zip(ctxs, items)]]
+    parts = run_on_devices(devices, [lambda c, it=it: call(c, it) for it in items])
     merged = []
     for j, first in enumerate(parts[0]):
         if isinstance(first, np.ndarray):

@@ -75,6 +75,11 @@ struct DevCtx {
     char name[256] = {0};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf partial, meta, u0, fail[2], scratch_a, scratch_b, scratch_c, ring;
+    // packed events left on the device by dtwa_integrate_events_packed (inside `ring`)
+    int64_t packed_total = 0;
+    int packed_nv = 0;
+    double *packed_t = nullptr, *packed_u = nullptr;
+    int32_t *packed_dir = nullptr;
 };
 
 // NCCL, loaded lazily (only a multi-device context needs it)
@@ -731,17 +736,23 @@ extern "C" int dtwa_lyapunov(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_s
 
 // ------------------------------------------------------------------------------------------------
 // surfaces of section (integrate + ContinuousCallback, docs/src/ClassicalDickeExamples.md:82-109)
-extern "C" int dtwa_integrate_events(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const double *u0, int64_t n,
-                                     double t_end, const dtwa_event *ev, int32_t max_events, double *ev_t, double *ev_u,
-                                     int32_t *ev_dir, int32_t *ev_count, double *u_end, int32_t *status, int64_t *nsteps,
-                                     double *kernel_ms)
+// Runs the section kernel and leaves the padded event arrays on the device (scratch_a: t | u, scratch_b: dir | count |
+// status); counts, end states, status and step counts are copied to the host.  The stream is synchronised on return.
+struct EventsOnDevice {
+    double *d_t = nullptr, *d_u = nullptr;
+    int32_t *d_dir = nullptr, *d_cnt = nullptr;
+    int nv = 0;
+    size_t cap = 0;
+};
+static int events_solve(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const double *u0, int64_t n, double t_end,
+                        const dtwa_event *ev, int32_t max_events, int32_t *ev_count, double *u_end, int32_t *status, int64_t *nsteps,
+                        double *kernel_ms, EventsOnDevice &out)
 {
     if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
     TRY(check_system(sys));
     TRY(check_solver(sol));
     if (!ev) return set_err(DTWA_ERR_INVALID, "NULL event");
-    if (n < 0 || max_events < 0 || (n > 0 && (!u0 || !ev_count || !status || !u_end)) || (n > 0 && max_events > 0 && (!ev_t || !ev_u || !ev_dir)))
-        return set_err(DTWA_ERR_INVALID, "bad buffers");
+    if (n < 0 || max_events < 0 || (n > 0 && (!u0 || !ev_count || !status || !u_end))) return set_err(DTWA_ERR_INVALID, "bad buffers");
     if (!(t_end >= 0)) return set_err(DTWA_ERR_INVALID, "Use integate_backwards=true instead of negative time");
     if (ev->direction < -1 || ev->direction > 1) return set_err(DTWA_ERR_INVALID, "event direction must be -1, 0 or +1");
     const int nv = nvar_of(sys->kind);
@@ -752,6 +763,8 @@ extern "C" int dtwa_integrate_events(dtwa_ctx *ctx, const dtwa_system *sys, cons
     std::vector<StepTab> tab;
     const double ts1[1] = {t_end};
     TRY(build_step_table(ts1, 1, sol->dt, make_par(sys, sol->backwards).b, tab));
+    out.nv = nv;
+    out.cap = (size_t)max_events;
     if (n == 0) return DTWA_OK;
     DevCtx &d = ctx->devs[0];
     CK(cudaSetDevice(d.device));
@@ -789,19 +802,6 @@ extern "C" int dtwa_integrate_events(dtwa_ctx *ctx, const dtwa_system *sys, cons
     CK(cudaGetLastError());
     CK(cudaEventRecord(d.ev[3], d.stream));
     CK(cudaMemcpyAsync(ev_count, d_cnt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d.stream));
-    if (cap) {
-        // only the columns some trajectory used travel back (the arrays are [n][max_events] padded)
-        CK(cudaStreamSynchronize(d.stream));
-        size_t used = 0;
-        for (int64_t i = 0; i < n; ++i) used = std::max(used, (size_t)std::min<int64_t>(ev_count[i], (int64_t)cap));
-        if (used) {
-            CK(cudaMemcpy2DAsync(ev_t, cap * sizeof(double), d_t, cap * sizeof(double), used * sizeof(double), n, cudaMemcpyDeviceToHost, d.stream));
-            CK(cudaMemcpy2DAsync(ev_u, cap * nv * sizeof(double), d_u, cap * nv * sizeof(double), used * nv * sizeof(double), n,
-                                 cudaMemcpyDeviceToHost, d.stream));
-            CK(cudaMemcpy2DAsync(ev_dir, cap * sizeof(int32_t), d_dir, cap * sizeof(int32_t), used * sizeof(int32_t), n,
-                                 cudaMemcpyDeviceToHost, d.stream));
-        }
-    }
     CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaMemcpyAsync(u_end, d_end, b_u0, cudaMemcpyDeviceToHost, d.stream));
     if (nsteps) CK(cudaMemcpyAsync(nsteps, d.scratch_c.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, d.stream));
@@ -811,6 +811,87 @@ extern "C" int dtwa_integrate_events(dtwa_ctx *ctx, const dtwa_system *sys, cons
         CK(cudaEventElapsedTime(&m, d.ev[0], d.ev[3]));
         *kernel_ms = m;
     }
+    out.d_t = d_t;
+    out.d_u = d_u;
+    out.d_dir = d_dir;
+    out.d_cnt = d_cnt;
+    return DTWA_OK;
+}
+
+extern "C" int dtwa_integrate_events(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const double *u0, int64_t n,
+                                     double t_end, const dtwa_event *ev, int32_t max_events, double *ev_t, double *ev_u,
+                                     int32_t *ev_dir, int32_t *ev_count, double *u_end, int32_t *status, int64_t *nsteps,
+                                     double *kernel_ms)
+{
+    if (n > 0 && max_events > 0 && (!ev_t || !ev_u || !ev_dir)) return set_err(DTWA_ERR_INVALID, "bad buffers");
+    EventsOnDevice E;
+    TRY(events_solve(ctx, sys, sol, u0, n, t_end, ev, max_events, ev_count, u_end, status, nsteps, kernel_ms, E));
+    if (n == 0 || E.cap == 0) return DTWA_OK;
+    DevCtx &d = ctx->devs[0];
+    const size_t cap = E.cap, nv = (size_t)E.nv;
+    // only the columns some trajectory used travel back (the arrays are [n][max_events] padded)
+    size_t used = 0;
+    for (int64_t i = 0; i < n; ++i) used = std::max(used, (size_t)std::min<int64_t>(ev_count[i], (int64_t)cap));
+    if (used) {
+        CK(cudaMemcpy2DAsync(ev_t, cap * sizeof(double), E.d_t, cap * sizeof(double), used * sizeof(double), n, cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaMemcpy2DAsync(ev_u, cap * nv * sizeof(double), E.d_u, cap * nv * sizeof(double), used * nv * sizeof(double), n,
+                             cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaMemcpy2DAsync(ev_dir, cap * sizeof(int32_t), E.d_dir, cap * sizeof(int32_t), used * sizeof(int32_t), n,
+                             cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+    }
+    return DTWA_OK;
+}
+
+// Packed (CSR) event output: row i owns the entries [offsets[i], offsets[i+1]) of ev_t / ev_u / ev_dir, offsets[i+1] -
+// offsets[i] = min(ev_count[i], max_events).  Two calls, because the caller can only size its buffers once the total
+// is known: _packed solves, compacts on the device and returns the total; _packed_fetch copies the compacted arrays.
+extern "C" int dtwa_integrate_events_packed(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const double *u0,
+                                            int64_t n, double t_end, const dtwa_event *ev, int32_t max_events, int64_t *offsets,
+                                            int32_t *ev_count, double *u_end, int32_t *status, int64_t *nsteps, double *kernel_ms)
+{
+    if (!offsets) return set_err(DTWA_ERR_INVALID, "bad buffers");
+    EventsOnDevice E;
+    offsets[0] = 0;
+    if (ctx) ctx->devs[0].packed_total = 0;
+    TRY(events_solve(ctx, sys, sol, u0, n, t_end, ev, max_events, ev_count, u_end, status, nsteps, kernel_ms, E));
+    if (n == 0) return DTWA_OK;
+    for (int64_t i = 0; i < n; ++i) offsets[i + 1] = offsets[i] + std::min<int64_t>(ev_count[i], (int64_t)E.cap);
+    const int64_t total = offsets[n];
+    DevCtx &d = ctx->devs[0];
+    d.packed_nv = E.nv;
+    if (total == 0) return DTWA_OK;
+    const size_t nv = (size_t)E.nv;
+    const size_t b_off = sizeof(int64_t) * (size_t)(n + 1), b_t = sizeof(double) * (size_t)total;
+    TRY(d.ring.ensure(b_off + b_t * (1 + nv) + sizeof(int32_t) * (size_t)total + 64));
+    int64_t *d_off = (int64_t *)d.ring.p;
+    double *p_t = (double *)((unsigned char *)d.ring.p + ((b_off + 15) & ~(size_t)15)), *p_u = p_t + total;
+    int32_t *p_dir = (int32_t *)(p_u + (size_t)total * nv);
+    CK(cudaMemcpyAsync(d_off, offsets, b_off, cudaMemcpyHostToDevice, d.stream));
+    const long long warps_per_block = 8;
+    pack_events_kernel<<<(unsigned)((n + warps_per_block - 1) / warps_per_block), 32 * warps_per_block, 0, d.stream>>>(
+        E.d_t, E.d_u, E.d_dir, d_off, n, (long long)E.cap, E.nv, p_t, p_u, p_dir);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(d.stream));
+    d.packed_total = total;
+    d.packed_t = p_t;
+    d.packed_u = p_u;
+    d.packed_dir = p_dir;
+    return DTWA_OK;
+}
+
+extern "C" int dtwa_integrate_events_packed_fetch(dtwa_ctx *ctx, int64_t total, double *ev_t, double *ev_u, int32_t *ev_dir)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    DevCtx &d = ctx->devs[0];
+    if (total != d.packed_total) return set_err(DTWA_ERR_INVALID, "no packed events of this size are pending (call dtwa_integrate_events_packed first)");
+    if (total == 0) return DTWA_OK;
+    if (!ev_t || !ev_u || !ev_dir) return set_err(DTWA_ERR_INVALID, "bad buffers");
+    CK(cudaSetDevice(d.device));
+    CK(cudaMemcpyAsync(ev_t, d.packed_t, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(ev_u, d.packed_u, sizeof(double) * (size_t)total * d.packed_nv, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(ev_dir, d.packed_dir, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
     return DTWA_OK;
 }
 
@@ -955,6 +1036,7 @@ static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const 
         if (window > 1) window &= ~1;
         if (A.nslots > 0) {
             TRY(d.ring.ensure(per_ring_out * (size_t)window));
+            d.packed_total = 0;   // (packed events of an earlier dtwa_integrate_events_packed lived here)
             ls.ring = (double *)d.ring.p;
         }
         smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, rows, window);

@@ -1226,6 +1226,24 @@ __global__ void __launch_bounds__(EVENTS_BLOCK, DTWA_EVENTS_MIN_BLOCKS) events_k
     }
 }
 
+// Compaction of the padded event arrays: one warp per initial condition copies its min(count, cap) events to
+// [off[i], off[i+1]) (contiguous, coalesced).
+__global__ void __launch_bounds__(256) pack_events_kernel(const double *__restrict__ ev_t, const double *__restrict__ ev_u,
+                                                          const int32_t *__restrict__ ev_dir, const int64_t *__restrict__ off,
+                                                          long long n, long long cap, int nv, double *__restrict__ out_t,
+                                                          double *__restrict__ out_u, int32_t *__restrict__ out_dir)
+{
+    const long long i = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    const long long o = off[i], m = off[i + 1] - o;
+    for (long long k = lane; k < m; k += 32) {
+        out_t[o + k] = ev_t[i * cap + k];
+        out_dir[o + k] = ev_dir[i * cap + k];
+    }
+    for (long long k = lane; k < m * nv; k += 32) out_u[o * nv + k] = ev_u[i * cap * nv + k];
+}
+
 // K8: energy-shell quadrature -- SURVEY 8f rank 4, src/EnergyShellProjections.jl:49-96 (the double integral of
 // f(x) delta(h_cl(x) - eps) over q and p by Chebyshev-Gauss quadrature in p, Eq. (8) of Pilatowsky-Cameo et al.,
 // Nat. Commun. 2021).  One warp per (Q, P) cell; the lanes stride over the 2 n (or n) nodes, evaluate the

@@ -426,6 +426,31 @@ function section_crossings(system::ClassicalSystem, u₀::AbstractVector{<:Real}
     return et[1:k], [eu[:, i] for i in 1:k], ed[1:k], uend
 end
 
+# Sections of many initial conditions (columns of U₀) in one launch, packed output: (offsets, t, u, direction, count) where
+# initial condition i owns the entries offsets[i]+1 : offsets[i+1] (1-based) of t / u[:, k] / direction
+function section_crossings_batch(system::ClassicalSystem, U₀::AbstractMatrix{<:Real}, t::Real; coef::AbstractVector{<:Real},
+                                 offset::Real=0.0, direction::Integer=0, max_events::Integer=1024, kargs...)
+    nv = length(varnames(system)); cf = zeros(4); cf[1:nv] .= coef
+    ev = Ref(CEvent(Tuple(cf), offset, direction, 0))
+    U = Matrix{Float64}(U₀); n = size(U, 2)
+    offsets = Vector{Int64}(undef, n + 1); cnt = Vector{Int32}(undef, n); status = Vector{Int32}(undef, n)
+    uend = Matrix{Float64}(undef, nv, n)
+    sys = Ref(csystem(system)); sol = Ref(csolver(; kargs...))
+    GC.@preserve U offsets cnt status uend begin
+        check(ccall((:dtwa_integrate_events_packed, libdicketwa), Cint,
+                    (Ptr{Cvoid}, Ref{CSystem}, Ref{CSolver}, Ptr{Float64}, Int64, Float64, Ref{CEvent}, Int32, Ptr{Int64}, Ptr{Int32},
+                     Ptr{Float64}, Ptr{Int32}, Ptr{Int64}, Ptr{Float64}),
+                    context().handle, sys, sol, U, n, t, ev, max_events, offsets, cnt, uend, status, C_NULL, C_NULL))
+    end
+    total = offsets[end]
+    et = Vector{Float64}(undef, total); eu = Matrix{Float64}(undef, nv, total); ed = Vector{Int32}(undef, total)
+    GC.@preserve et eu ed begin
+        check(ccall((:dtwa_integrate_events_packed_fetch, libdicketwa), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+                    context().handle, total, et, eu, ed))
+    end
+    return offsets, et, eu, ed, cnt
+end
+
 # EnergyShellProjections.∫∫dqdpδϵ / matrix_QP∫∫dqdpδϵ (src/EnergyShellProjections.jl:49-96,159-199) for classical f
 function ∫∫dqdpδϵ(system::ClassicalDickeSystem; ϵ::Real, Q, P, f, p_res::Real=0.01, nonvalue=NaN, onlyqroot=nothing)
     QP = Matrix{Float64}(vcat(reshape(collect(Float64, Q), 1, :), reshape(collect(Float64, P), 1, :))); n = size(QP, 2)

@@ -236,6 +236,18 @@ int dtwa_integrate_events(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solv
                           double t_end, const dtwa_event *ev, int32_t max_events, double *ev_t, double *ev_u, int32_t *ev_dir,
                           int32_t *ev_count, double *u_end, int32_t *status, int64_t *nsteps, double *kernel_ms);
 
+/* ---- the same with packed (CSR) output, for large batches: row i owns the entries [offsets[i], offsets[i+1]) of the
+ *      event arrays, offsets[i+1] - offsets[i] = min(ev_count[i], max_events); offsets[n+1].  Two calls, because the
+ *      caller can size its buffers only when the total offsets[n] is known: dtwa_integrate_events_packed solves and
+ *      compacts on the device, dtwa_integrate_events_packed_fetch(total = offsets[n]) copies ev_t[total],
+ *      ev_u[total][nvar], ev_dir[total].  The packed arrays stay valid until the next call on this context that
+ *      integrates adaptive ensembles or events.  (No counterpart in the reference, which collects events in Julia
+ *      arrays inside `affect!`.) ---- */
+int dtwa_integrate_events_packed(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol, const double *u0, int64_t n,
+                                 double t_end, const dtwa_event *ev, int32_t max_events, int64_t *offsets, int32_t *ev_count,
+                                 double *u_end, int32_t *status, int64_t *nsteps, double *kernel_ms);
+int dtwa_integrate_events_packed_fetch(dtwa_ctx *ctx, int64_t total, double *ev_t, double *ev_u, int32_t *ev_dir);
+
 /* ---- EnergyShellProjections.∫∫dqdpδϵ (src/EnergyShellProjections.jl:49-96) for ncell cells
  *      (Q, P) at once (matrix_QP∫∫dqdpδϵ :159-199, energy_shell_average :476-508) and classical functions f
  *      given as 1..8 expressions over Q,q,P,p: out[ncell][nexpr] = sum over the roots q_+- and the n =

@@ -79,6 +79,9 @@ def test_independent_batches_split_over_two_gpus(pkg):
     e1 = CS.poincare_section_batch(system, X, 30.0, coef=[0, 0, 0, 1], tol=1e-9, max_events=32)
     e2 = CS.poincare_section_batch(system, X, 30.0, coef=[0, 0, 0, 1], tol=1e-9, max_events=32, devices=[0, 1])
     assert np.array_equal(e1["count"], e2["count"]) and np.array_equal(e1["t"], e2["t"], equal_nan=True)
+    p1 = CS.poincare_section_batch(system, X, 30.0, coef=[0, 0, 0, 1], tol=1e-9, max_events=32, packed=True)
+    p2 = CS.poincare_section_batch(system, X, 30.0, coef=[0, 0, 0, 1], tol=1e-9, max_events=32, packed=True, devices=[0, 1])
+    assert all(np.array_equal(p1[k], p2[k]) for k in ("offsets", "t", "u", "direction", "count", "u_end"))
     o1 = CS.integrate_batch(system, X, [0.0, 1.0, 2.0], tol=1e-9)
     o2 = CS.integrate_batch(system, X, [0.0, 1.0, 2.0], tol=1e-9, devices=[0, 1])
     assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(o1, o2))

@@ -440,3 +440,30 @@ def test_gpu_finds_both_crossings_of_a_near_tangency(ctx, pkg, O):
         got = tg[0, :cg[0]]
         assert (np.abs(got - tmax) < 0.3).sum() == 2
         assert np.abs(got - to[0, :co[0]]).max() < 1e-6        # (crossing times near a tangency amplify the rounding-level step differences)
+
+
+@pytest.mark.gpu
+def test_packed_section_output_equals_the_padded_one(ctx, pkg):
+    """dtwa_integrate_events_packed: the same events, compacted on the GPU into CSR form (rows of very different
+    lengths, a row with no crossing, rows cut at max_events)"""
+    CD, CS = pkg.ClassicalDicke, pkg.ClassicalSystems
+    system = CD.ClassicalDickeSystem(w=0.8, g=0.8, w0=1)
+    rng = np.random.default_rng(11)
+    X = np.column_stack([rng.uniform(0.7, 1.4, 203), rng.uniform(-0.5, 0.5, 203), rng.uniform(-0.4, 0.4, 203), rng.uniform(-0.5, 0.5, 203)])
+    X[7] = CD.minimum_energy_point(system, "+")      # the fixed point never crosses p = 0.3
+    for kw in (dict(coef=[0, 0, 0, 1], offset=0.3, max_events=15), dict(coef=[0, 1, 0, 0.5], direction=1, max_events=7)):
+        a = CS.poincare_section_batch(system, X, 60.0, tol=1e-9, **kw)
+        b = CS.poincare_section_batch(system, X, 60.0, tol=1e-9, packed=True, **kw)
+        assert np.array_equal(a["count"], b["count"]) and np.array_equal(a["u_end"], b["u_end"]) and np.array_equal(a["nsteps"], b["nsteps"])
+        m = np.minimum(a["count"], kw["max_events"])
+        assert np.array_equal(np.diff(b["offsets"]), m) and b["offsets"][0] == 0 and len(b["t"]) == m.sum()
+        assert m.min() == 0 and m.max() == kw["max_events"] and (a["count"] > kw["max_events"]).any()
+        assert kw["max_events"] != 15 or len(set(m.tolist())) > 3
+        for i in (0, 7, 50, 202):
+            lo, hi = b["offsets"][i], b["offsets"][i + 1]
+            assert np.array_equal(b["t"][lo:hi], a["t"][i, :m[i]]) and np.array_equal(b["u"][lo:hi], a["u"][i, :m[i]])
+            assert np.array_equal(b["direction"][lo:hi], a["direction"][i, :m[i]])
+        mask = np.arange(kw["max_events"])[None, :] < m[:, None]
+        assert np.array_equal(a["t"][mask], b["t"]) and np.array_equal(a["u"][mask], b["u"])
+    e = CS.poincare_section_batch(system, X[:0], 60.0, coef=[0, 0, 0, 1], packed=True)
+    assert len(e["t"]) == 0 and e["offsets"].tolist() == [0]

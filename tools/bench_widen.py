@@ -43,12 +43,17 @@ t0 = time.perf_counter()
 r = CS.poincare_section_batch(system, pts, 1000.0, **kw)
 wall = time.perf_counter() - t0
 steps, ev = int(r["nsteps"].sum()), int(np.minimum(r["count"], 512).sum())
+t0 = time.perf_counter()
+rp = CS.poincare_section_batch(system, pts, 1000.0, packed=True, **kw)      # CSR output: no [n][max_events] padding
+wall_packed = time.perf_counter() - t0
+assert len(rp["t"]) == ev
 m = min(256, a.n)
 t0 = time.perf_counter()
 et, eu, ed, cnt, ue, st, ns = O.integrate_events(O.SYS_DICKE, [1.0, 0.8, 0.8], pts[:m], 1000.0, [0, 0, 0, 1], tol=1e-10, max_events=512, fast=True)
 cw = time.perf_counter() - t0
 print(json.dumps({"what": "Poincare sections p=0, DOP853 tol=1e-10, t=1000, one launch", "initial_conditions": a.n, "steps": steps, "crossings": ev,
-                  "kernel_ms": r["kernel_ms"], "wall_s": wall, "steps_per_s_kernel": steps / (r["kernel_ms"] * 1e-3), "crossings_per_s": ev / wall,
+                  "kernel_ms": r["kernel_ms"], "wall_s": wall, "wall_packed_s": wall_packed, "steps_per_s_kernel": steps / (r["kernel_ms"] * 1e-3),
+                  "crossings_per_s": ev / wall, "crossings_per_s_packed": ev / wall_packed,
                   "failed": int((r["status"] != 0).sum()),
                   "cpu_baseline": {"kind": "port", "cores": O.lib(True).orc_max_threads(), "initial_conditions": m, "seconds": cw,
                                    "steps_per_s": float(ns.sum() / cw), "same_counts_fraction": float((cnt == r["count"][:m]).mean())}}))
