@@ -467,3 +467,17 @@ def test_packed_section_output_equals_the_padded_one(ctx, pkg):
         assert np.array_equal(a["t"][mask], b["t"]) and np.array_equal(a["u"][mask], b["u"])
     e = CS.poincare_section_batch(system, X[:0], 60.0, coef=[0, 0, 0, 1], packed=True)
     assert len(e["t"]) == 0 and e["offsets"].tolist() == [0]
+
+
+@pytest.mark.gpu
+def test_packed_fetch_rejects_a_stale_or_wrong_total(ctx, pkg):
+    import ctypes as C
+    L = pkg._lib.load()
+    buf = np.empty(64)
+    idir = np.empty(64, dtype=np.int32)
+    rc = L.dtwa_integrate_events_packed_fetch(ctx._h, 12345, buf.ctypes.data_as(C.POINTER(C.c_double)), buf.ctypes.data_as(C.POINTER(C.c_double)),
+                                              idir.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc != 0 and b"packed" in L.dtwa_last_error()
+    system = pkg.ClassicalDicke.ClassicalDickeSystem(w=0.8, g=0.8, w0=1)
+    r = pkg.ClassicalSystems.poincare_section_batch(system, [[1.0, 0.2, 0.1, 0.0]], 20.0, coef=[0, 0, 0, 1], packed=True, max_events=0)
+    assert len(r["t"]) == 0 and r["count"][0] > 0 and r["offsets"].tolist() == [0, 0]
