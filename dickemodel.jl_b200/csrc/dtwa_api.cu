@@ -11,6 +11,7 @@
 #include <cstring>
 #include <string>
 #include <type_traits>
+#include <thread>
 #include <vector>
 
 #include "dtwa_kernels.cuh"
@@ -100,7 +101,52 @@ struct dtwa_ctx {
     int jit_mode = 2;  // 0: interpret the reducer program, 1: always specialise with NVRTC, 2: specialise large ensembles
     NcclApi nccl;
     std::vector<ncclComm_t> comms;
+    // packed events of a split dtwa_integrate_events_packed: (device, first event, events) per block
+    struct PackedBlock {
+        int dev;
+        int64_t first, count;
+    };
+    std::vector<PackedBlock> packed_blocks;
 };
+
+// ---- batch entry points on a multi-device context -------------------------------------------------------------------
+// dtwa_integrate / _fm / _lyapunov / _integrate_events(_packed) / _shell_quadrature work on independent items with no
+// exchange step.  On a context with several devices they give every device one contiguous block of the items (host
+// arrays are addressed by block, nothing is copied or permuted) and run the single-device implementation for all
+// blocks at once, one host thread per device.  g_dev selects the device of the calling thread; g_no_split marks the
+// worker threads (and contexts with one device never split).
+static thread_local int g_dev = 0;
+static thread_local bool g_no_split = false;
+static DevCtx &cur_dev(dtwa_ctx *ctx) { return ctx->devs[(size_t)g_dev < ctx->devs.size() ? g_dev : 0]; }
+static bool should_split(const dtwa_ctx *ctx, int64_t n) { return ctx && !g_no_split && ctx->devs.size() > 1 && n >= 2 * (int64_t)ctx->devs.size(); }
+static void store_max_ms(double *kernel_ms, const std::vector<double> &ms)
+{
+    if (kernel_ms) *kernel_ms = *std::max_element(ms.begin(), ms.end());
+}
+// call(k, lo, hi) -> DTWA_* for block k = items [lo, hi)
+template <typename F>
+static int split_over_devices(dtwa_ctx *ctx, int64_t n, F &&call)
+{
+    const int nd = (int)ctx->devs.size();
+    const int64_t per = (n + nd - 1) / nd;
+    std::vector<int> rc(nd, DTWA_OK);
+    std::vector<std::string> msg(nd);
+    std::vector<std::thread> th;
+    for (int k = 0; k < nd; ++k) {
+        const int64_t lo = std::min<int64_t>(n, k * per), hi = std::min<int64_t>(n, lo + per);
+        if (hi <= lo) continue;
+        th.emplace_back([&, k, lo, hi] {
+            g_dev = k;
+            g_no_split = true;
+            rc[k] = call(k, lo, hi);
+            if (rc[k] != DTWA_OK) msg[k] = g_err;
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int k = 0; k < nd; ++k)
+        if (rc[k] != DTWA_OK) return set_err(rc[k], msg[k]);
+    return DTWA_OK;
+}
 
 static int load_nccl(dtwa_ctx *ctx)
 {
@@ -580,9 +626,13 @@ extern "C" int dtwa_integrate(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_
     std::vector<StepTab> tab;
     TRY(build_step_table(ts, nt, sol->dt, make_par(sys, sol->backwards).b, tab));
     if (n == 0) return DTWA_OK;
-    DevCtx &d = ctx->devs[0];
-    CK(cudaSetDevice(d.device));
     const int nv = nvar_of(sys->kind);
+    if (should_split(ctx, n))
+        return split_over_devices(ctx, n, [&](int, int64_t lo, int64_t hi) {
+            return dtwa_integrate(ctx, sys, sol, u0 + lo * nv, hi - lo, ts, nt, out + (size_t)lo * nt * nv, status + lo, nsteps ? nsteps + lo : nullptr);
+        });
+    DevCtx &d = cur_dev(ctx);
+    CK(cudaSetDevice(d.device));
     const size_t tab_b = sizeof(StepTab) * nt, ts_b = sizeof(double) * nt;
     TRY(d.meta.ensure(tab_b + ts_b));
     TRY(d.u0.ensure(sizeof(double) * n * nv));
@@ -630,9 +680,14 @@ extern "C" int dtwa_integrate_fm(dtwa_ctx *ctx, const dtwa_system *sys, const dt
     std::vector<StepTab> tab;
     TRY(build_step_table(ts, nt, sol->dt, make_par(sys, sol->backwards).b, tab));
     if (n == 0) return DTWA_OK;
-    DevCtx &d = ctx->devs[0];
-    CK(cudaSetDevice(d.device));
     const int nv = nvar_of(sys->kind), nn = nv * nv;
+    if (should_split(ctx, n))
+        return split_over_devices(ctx, n, [&](int, int64_t lo, int64_t hi) {
+            return dtwa_integrate_fm(ctx, sys, sol, u0 + lo * nv, fm0 ? fm0 + lo * nn : nullptr, hi - lo, ts, nt, out_u + (size_t)lo * nt * nv,
+                                     out_fm + (size_t)lo * nt * nn, status + lo, nsteps ? nsteps + lo : nullptr);
+        });
+    DevCtx &d = cur_dev(ctx);
+    CK(cudaSetDevice(d.device));
     const size_t tab_b = sizeof(StepTab) * nt, ts_b = sizeof(double) * nt;
     const size_t b_u0 = sizeof(double) * n * nv, b_fm0 = fm0 ? sizeof(double) * n * nn : 0;
     const size_t b_ou = sizeof(double) * (size_t)n * nt * nv, b_of = sizeof(double) * (size_t)n * nt * nn;
@@ -680,9 +735,18 @@ extern "C" int dtwa_lyapunov(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_s
     const double ts1[1] = {t_interval};
     TRY(build_step_table(ts1, 1, sol->dt, make_par(sys, sol->backwards).b, tab));
     if (n == 0) return DTWA_OK;
-    DevCtx &d = ctx->devs[0];
-    CK(cudaSetDevice(d.device));
     const int nv = nvar_of(sys->kind);
+    if (should_split(ctx, n)) {
+        std::vector<double> ms(ctx->devs.size(), 0.0);
+        TRY(split_over_devices(ctx, n, [&](int k, int64_t lo, int64_t hi) {
+            return dtwa_lyapunov(ctx, sys, sol, u0 + lo * nv, hi - lo, t_interval, lam_tol, lam_reltol, maxiters, lambda + lo * nv,
+                                 x_final ? x_final + lo * nv : nullptr, iters + lo, status + lo, nsteps ? nsteps + lo : nullptr, &ms[k]);
+        }));
+        store_max_ms(kernel_ms, ms);
+        return DTWA_OK;
+    }
+    DevCtx &d = cur_dev(ctx);
+    CK(cudaSetDevice(d.device));
     const size_t tab_b = sizeof(StepTab), ts_b = sizeof(double);
     const size_t b_u0 = sizeof(double) * n * nv;
     TRY(d.meta.ensure(tab_b + ts_b));
@@ -766,7 +830,7 @@ static int events_solve(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver
     out.nv = nv;
     out.cap = (size_t)max_events;
     if (n == 0) return DTWA_OK;
-    DevCtx &d = ctx->devs[0];
+    DevCtx &d = cur_dev(ctx);
     CK(cudaSetDevice(d.device));
     const size_t tab_b = sizeof(StepTab), ts_b = sizeof(double);
     const size_t b_u0 = sizeof(double) * n * nv, cap = (size_t)max_events;
@@ -824,10 +888,21 @@ extern "C" int dtwa_integrate_events(dtwa_ctx *ctx, const dtwa_system *sys, cons
                                      double *kernel_ms)
 {
     if (n > 0 && max_events > 0 && (!ev_t || !ev_u || !ev_dir)) return set_err(DTWA_ERR_INVALID, "bad buffers");
+    if (should_split(ctx, n) && sys && max_events >= 0 && u0 && ev_count && status && u_end) {
+        const size_t nv = (size_t)nvar_of(sys->kind), cap = (size_t)max_events;
+        std::vector<double> ms(ctx->devs.size(), 0.0);
+        TRY(split_over_devices(ctx, n, [&](int k, int64_t lo, int64_t hi) {
+            return dtwa_integrate_events(ctx, sys, sol, u0 + lo * nv, hi - lo, t_end, ev, max_events, ev_t ? ev_t + lo * cap : nullptr,
+                                         ev_u ? ev_u + lo * cap * nv : nullptr, ev_dir ? ev_dir + lo * cap : nullptr, ev_count + lo,
+                                         u_end + lo * nv, status + lo, nsteps ? nsteps + lo : nullptr, &ms[k]);
+        }));
+        store_max_ms(kernel_ms, ms);
+        return DTWA_OK;
+    }
     EventsOnDevice E;
     TRY(events_solve(ctx, sys, sol, u0, n, t_end, ev, max_events, ev_count, u_end, status, nsteps, kernel_ms, E));
     if (n == 0 || E.cap == 0) return DTWA_OK;
-    DevCtx &d = ctx->devs[0];
+    DevCtx &d = cur_dev(ctx);
     const size_t cap = E.cap, nv = (size_t)E.nv;
     // only the columns some trajectory used travel back (the arrays are [n][max_events] padded)
     size_t used = 0;
@@ -851,14 +926,44 @@ extern "C" int dtwa_integrate_events_packed(dtwa_ctx *ctx, const dtwa_system *sy
                                             int32_t *ev_count, double *u_end, int32_t *status, int64_t *nsteps, double *kernel_ms)
 {
     if (!offsets) return set_err(DTWA_ERR_INVALID, "bad buffers");
+    if (should_split(ctx, n) && sys && max_events >= 0 && u0 && ev_count && status && u_end) {
+        // every device packs its block (offsets local to the block), then the offsets are made global
+        const size_t nv = (size_t)nvar_of(sys->kind);
+        const int nd = (int)ctx->devs.size();
+        std::vector<double> ms(nd, 0.0);
+        std::vector<int64_t> lo_of(nd, -1), hi_of(nd, -1);
+        std::vector<std::vector<int64_t>> loc(nd);
+        ctx->packed_blocks.clear();
+        TRY(split_over_devices(ctx, n, [&](int k, int64_t lo, int64_t hi) {
+            lo_of[k] = lo;
+            hi_of[k] = hi;
+            loc[k].assign((size_t)(hi - lo) + 1, 0);
+            return dtwa_integrate_events_packed(ctx, sys, sol, u0 + lo * nv, hi - lo, t_end, ev, max_events, loc[k].data(), ev_count + lo,
+                                                u_end + lo * nv, status + lo, nsteps ? nsteps + lo : nullptr, &ms[k]);
+        }));
+        int64_t first = 0;
+        offsets[0] = 0;
+        for (int k = 0; k < nd; ++k) {
+            if (lo_of[k] < 0) continue;
+            for (int64_t i = lo_of[k]; i < hi_of[k]; ++i) offsets[i + 1] = first + loc[k][(size_t)(i - lo_of[k]) + 1];
+            const int64_t cnt = loc[k].back();
+            ctx->packed_blocks.push_back({k, first, cnt});
+            first += cnt;
+        }
+        store_max_ms(kernel_ms, ms);
+        return DTWA_OK;
+    }
     EventsOnDevice E;
     offsets[0] = 0;
-    if (ctx) ctx->devs[0].packed_total = 0;
+    if (ctx) {
+        cur_dev(ctx).packed_total = 0;
+        if (!g_no_split) ctx->packed_blocks.clear();
+    }
     TRY(events_solve(ctx, sys, sol, u0, n, t_end, ev, max_events, ev_count, u_end, status, nsteps, kernel_ms, E));
     if (n == 0) return DTWA_OK;
     for (int64_t i = 0; i < n; ++i) offsets[i + 1] = offsets[i] + std::min<int64_t>(ev_count[i], (int64_t)E.cap);
     const int64_t total = offsets[n];
-    DevCtx &d = ctx->devs[0];
+    DevCtx &d = cur_dev(ctx);
     d.packed_nv = E.nv;
     if (total == 0) return DTWA_OK;
     const size_t nv = (size_t)E.nv;
@@ -883,7 +988,31 @@ extern "C" int dtwa_integrate_events_packed(dtwa_ctx *ctx, const dtwa_system *sy
 extern "C" int dtwa_integrate_events_packed_fetch(dtwa_ctx *ctx, int64_t total, double *ev_t, double *ev_u, int32_t *ev_dir)
 {
     if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
-    DevCtx &d = ctx->devs[0];
+    if (!g_no_split && !ctx->packed_blocks.empty()) {   // the result of a split solve: one segment per device
+        int64_t sum = 0;
+        for (const auto &b : ctx->packed_blocks) sum += b.count;
+        if (total != sum) return set_err(DTWA_ERR_INVALID, "no packed events of this size are pending (call dtwa_integrate_events_packed first)");
+        if (total == 0) return DTWA_OK;
+        if (!ev_t || !ev_u || !ev_dir) return set_err(DTWA_ERR_INVALID, "bad buffers");
+        const auto blocks = ctx->packed_blocks;
+        std::vector<int> rc(blocks.size(), DTWA_OK);
+        std::vector<std::string> msg(blocks.size());
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < blocks.size(); ++i)
+            th.emplace_back([&, i] {
+                const auto &b = blocks[i];
+                g_dev = b.dev;
+                g_no_split = true;
+                const size_t nv = (size_t)ctx->devs[b.dev].packed_nv;
+                rc[i] = dtwa_integrate_events_packed_fetch(ctx, b.count, ev_t + b.first, ev_u + (size_t)b.first * nv, ev_dir + b.first);
+                if (rc[i] != DTWA_OK) msg[i] = g_err;
+            });
+        for (auto &t : th) t.join();
+        for (size_t i = 0; i < blocks.size(); ++i)
+            if (rc[i] != DTWA_OK) return set_err(rc[i], msg[i]);
+        return DTWA_OK;
+    }
+    DevCtx &d = cur_dev(ctx);
     if (total != d.packed_total) return set_err(DTWA_ERR_INVALID, "no packed events of this size are pending (call dtwa_integrate_events_packed first)");
     if (total == 0) return DTWA_OK;
     if (!ev_t || !ev_u || !ev_dir) return set_err(DTWA_ERR_INVALID, "bad buffers");
@@ -925,8 +1054,17 @@ extern "C" int dtwa_shell_quadrature(dtwa_ctx *ctx, const dtwa_system *sys, doub
     }
     if (prog.max_depth > VM_STACK) return set_err(DTWA_ERR_EXPR, "expression too deeply nested for the VM stack");
     if (ncell == 0) return DTWA_OK;
+    if (should_split(ctx, ncell)) {
+        std::vector<double> ms(ctx->devs.size(), 0.0);
+        TRY(split_over_devices(ctx, ncell, [&](int k, int64_t lo, int64_t hi) {
+            return dtwa_shell_quadrature(ctx, sys, eps, QP + 2 * lo, hi - lo, exprs, nexpr, p_res, onlyqroot, out + lo * nexpr, valid + lo,
+                                         nodes ? nodes + lo : nullptr, &ms[k]);
+        }));
+        store_max_ms(kernel_ms, ms);
+        return DTWA_OK;
+    }
     if (prog.consts.empty()) prog.consts.push_back(0.0);
-    DevCtx &d = ctx->devs[0];
+    DevCtx &d = cur_dev(ctx);
     CK(cudaSetDevice(d.device));
     const size_t cb = (sizeof(double) * prog.consts.size() + 15) & ~size_t(15), pb = (sizeof(VmIns) * prog.ins.size() + 15) & ~size_t(15);
     const size_t ob = sizeof(int32_t) * offs.size();

@@ -784,7 +784,6 @@ __global__ void __launch_bounds__(128) integrate_fm_kernel(const SolverArgs S, c
     const long long j = live ? j0 : n - 1;  // tail groups shadow the last initial condition
     Traj<SYS, ALG> T;
     T.status = ST_OK;
-#pragma unroll
     T.u[0] = u0[j * NVB + c];
 #pragma unroll
     for (int i = 0; i < NVB; ++i) T.u[1 + i] = fm0 ? fm0[(j * NVB + c) * NVB + i] : (i == c ? 1.0 : 0.0);

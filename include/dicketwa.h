@@ -164,7 +164,11 @@ int dtwa_version(void);
 /* device_ids[ndev]; ndev>1 shards [0,N) by contiguous index blocks over the devices of one
  * process and merges the per-time arrays with one grouped ncclAllReduce (libnccl is dlopen'ed).
  * stream: an existing cudaStream_t (as void*) to enqueue on when ndev==1, or NULL for a private
- * non-blocking one (pass cudaStreamLegacy / cudaStreamPerThread to name the default streams). */
+ * non-blocking one (pass cudaStreamLegacy / cudaStreamPerThread to name the default streams).
+ * The batch entry points on independent items (dtwa_integrate, _integrate_fm, _lyapunov, _integrate_events(_packed),
+ * _shell_quadrature) need no exchange at all: with ndev>1 every device takes one contiguous block of the items, the
+ * blocks run concurrently (one host thread per device) and the caller's arrays are filled block by block -- the same
+ * bits as on one device.  The remaining single-item helpers (dtwa_sample, _pdf, _hamiltonian, ...) use device_ids[0]. */
 int dtwa_create(dtwa_ctx **out, const int *device_ids, int ndev, void *stream);
 int dtwa_destroy(dtwa_ctx *ctx);
 /* name[256]; sm_count, clock_khz, cc (major*10+minor) */

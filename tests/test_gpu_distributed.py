@@ -92,3 +92,37 @@ def test_independent_batches_split_over_two_gpus(pkg):
     m1 = ESP.matrix_QP_iint_dqdp_delta(system, f=lambda x: [1, x[1] ** 2], ϵ=-0.5, res=0.05)
     m2 = ESP.matrix_QP_iint_dqdp_delta(system, f=lambda x: [1, x[1] ** 2], ϵ=-0.5, res=0.05, devices=[0, 1])
     assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(m1, m2))
+
+
+def test_batch_entry_points_split_inside_a_multi_device_context(pkg):
+    """a context created on two devices (what the Julia shim holds) gives each device one contiguous block of the
+    items of dtwa_integrate / _fm / _lyapunov / _integrate_events(_packed) / _shell_quadrature: same bits as one GPU"""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    L = pkg._lib
+    from dickemodel_jl_b200 import ClassicalDicke as CD, ClassicalSystems as CS, EnergyShellProjections as ESP
+    system = CD.ClassicalDickeSystem(w=0.8, g=0.8, w0=1)
+    rng = np.random.default_rng(5)
+    X = np.column_stack([rng.uniform(0.7, 1.4, 257), rng.uniform(-0.5, 0.5, 257), rng.uniform(-0.4, 0.4, 257), rng.uniform(-0.5, 0.5, 257)])
+    one, two = L.device_context(0), L.Context([0, 1])
+    sys_c = system._c_system()
+    sol = CS.solver_from_kargs(dict(tol=1e-9))
+    try:
+        for name, args in (("integrate", (sys_c, sol, X, [0.0, 1.0, 2.5])), ("integrate_fm", (sys_c, sol, X[:101], [0.0, 1.5])),
+                           ("lyapunov", (sys_c, sol, X, 20.0, 1e-4, 1e-3, 30)),
+                           ("integrate_events", (sys_c, sol, X, 30.0, [0, 0, 0, 1], 0.1, 0, 16)),
+                           ("integrate_events_packed", (sys_c, sol, X, 30.0, [0, 0, 0, 1], 0.1, 0, 16)),
+                           ("shell_quadrature", (sys_c, -0.5, np.column_stack([rng.uniform(-1, 1, 333), rng.uniform(-1, 1, 333)]), ["1", "q^2"], 0.02, 0))):
+            a, b = getattr(one, name)(*args), getattr(two, name)(*args)
+            for x, y in zip(a, b):
+                if isinstance(x, np.ndarray):
+                    assert np.array_equal(x, y, equal_nan=True), name
+        # a batch smaller than 2 x devices stays on the first device; errors of a worker thread reach the caller
+        a, b = one.integrate(sys_c, sol, X[:3], [0.0, 1.0]), two.integrate(sys_c, sol, X[:3], [0.0, 1.0])
+        assert np.array_equal(a[0], b[0])
+        with pytest.raises(L.DtwaError):
+            two.shell_quadrature(sys_c, -0.5, np.zeros((64, 2)), ["1 +"], 0.02, 0)
+    finally:
+        two.close()
