@@ -737,11 +737,35 @@ extern "C" int dtwa_lyapunov(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_s
     if (n == 0) return DTWA_OK;
     const int nv = nvar_of(sys->kind);
     if (should_split(ctx, n)) {
-        std::vector<double> ms(ctx->devs.size(), 0.0);
+        // The cost of an orbit (rounds until convergence) varies smoothly over a Lyapunov map, so contiguous blocks of a
+        // map are unbalanced.  Inputs and outputs are a few numbers per orbit: deal the orbits round-robin (orbit i to
+        // device i mod ndev) through permuted host copies and scatter the results back.
+        const int64_t nd = (int64_t)ctx->devs.size();
+        std::vector<int64_t> src;   // permuted position -> original index: residue classes mod ndev, one after the other
+        src.reserve((size_t)n);     // (the blocks of split_over_devices cut this list within a few items of the class ends)
+        for (int64_t k = 0; k < nd; ++k)
+            for (int64_t i = k; i < n; i += nd) src.push_back(i);
+        std::vector<double> pu0((size_t)n * nv), plam((size_t)n * nv), px(x_final ? (size_t)n * nv : 0);
+        std::vector<int32_t> pit((size_t)n), pst((size_t)n);
+        std::vector<int64_t> pns(nsteps ? (size_t)n : 0);
+        for (int64_t p = 0; p < n; ++p)
+            for (int c = 0; c < nv; ++c) pu0[(size_t)p * nv + c] = u0[src[(size_t)p] * nv + c];
+        std::vector<double> ms((size_t)nd, 0.0);
         TRY(split_over_devices(ctx, n, [&](int k, int64_t lo, int64_t hi) {
-            return dtwa_lyapunov(ctx, sys, sol, u0 + lo * nv, hi - lo, t_interval, lam_tol, lam_reltol, maxiters, lambda + lo * nv,
-                                 x_final ? x_final + lo * nv : nullptr, iters + lo, status + lo, nsteps ? nsteps + lo : nullptr, &ms[k]);
+            return dtwa_lyapunov(ctx, sys, sol, pu0.data() + lo * nv, hi - lo, t_interval, lam_tol, lam_reltol, maxiters, plam.data() + lo * nv,
+                                 x_final ? px.data() + lo * nv : nullptr, pit.data() + lo, pst.data() + lo, nsteps ? pns.data() + lo : nullptr,
+                                 &ms[k]);
         }));
+        for (int64_t p = 0; p < n; ++p) {
+            const int64_t i = src[(size_t)p];
+            for (int c = 0; c < nv; ++c) {
+                lambda[i * nv + c] = plam[(size_t)p * nv + c];
+                if (x_final) x_final[i * nv + c] = px[(size_t)p * nv + c];
+            }
+            iters[i] = pit[(size_t)p];
+            status[i] = pst[(size_t)p];
+            if (nsteps) nsteps[i] = pns[(size_t)p];
+        }
         store_max_ms(kernel_ms, ms);
         return DTWA_OK;
     }
