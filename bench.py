@@ -336,8 +336,36 @@ def main():
                 "gpu_wall_s": wall0, "gpu_kernel_ms": i0["kernel_ms"], "gpu_attempted_steps": i0["steps_accepted"] + i0["steps_rejected"],
                 "cpu_port_s": cpu0, "cpu_cores": thr, "cpu_attempted_steps": r0["steps_accepted"] + r0["steps_rejected"],
                 "max_abs_diff_mean_jz": float(np.max(np.abs(r0["sums"][:, 0] / j / 10000 - g0)))}
+            # SURVEY 8f ranks 2-4 (the callers on the other side of `integrate`), small instances, for the record
+            CSm, ESP = pkg.ClassicalSystems, pkg.EnergyShellProjections
+            sysw = CD.ClassicalDickeSystem(w=0.8, g=0.8, w0=1)
+            ew = -1.35
+            Qs = np.linspace(CD.minimum_nonnegative_Q_for_ϵ(sysw, ew), CD.maximum_Q_for_ϵ(sysw, ew), 128)
+            Ps = np.linspace(0, CD.maximum_P_for_ϵ(sysw, ew), 128)
+            pts = np.array([CD.Point(sysw, Q=Q, P=P, p=0, ϵ=ew) for Q in Qs for P in Ps if CD.minimum_ϵ_for(sysw, P=P, p=0, Q=Q) <= ew])
+            for _ in range(2):
+                lam, stl = CSm.lyapunov_spectrum_batch(sysw, pts, 100, tol=1e-8, λtol=5e-5, verbose=False)
+            il = CSm.last_lyapunov_info
+            extras["note_8f"] = ("lyapunov_map_128 / sections_p0_t1000 / shell_quadrature are small instances (12.6e3 orbits leave most of a "
+                                 "B200 idle in the tail); full-size numbers: profiles/r1_lyapunov_map_256.json, r1_sections_and_shell_quadrature.jsonl")
+            extras["lyapunov_map_128"] = {"orbits": int(len(pts)), "variational_steps": int(il["nsteps"].sum()), "kernel_ms": il["kernel_ms"],
+                                          "steps_per_s": float(il["nsteps"].sum() / (il["kernel_ms"] * 1e-3)), "converged": int((stl == 0).sum())}
+            for _ in range(2):
+                t0 = time.perf_counter()
+                sec = CSm.poincare_section_batch(sysw, pts, 1000.0, coef=[0, 0, 0, 1], tol=1e-10, max_events=512, packed=True)
+                wall_s = time.perf_counter() - t0
+            extras["sections_p0_t1000"] = {"orbits": int(len(pts)), "steps": int(sec["nsteps"].sum()), "crossings": int(len(sec["t"])),
+                                           "kernel_ms": sec["kernel_ms"], "wall_s": wall_s,
+                                           "steps_per_s": float(sec["nsteps"].sum() / (sec["kernel_ms"] * 1e-3)),
+                                           "max_abs_p_on_section": float(np.abs(sec["u"][:, 3]).max())}
+            for _ in range(2):
+                Qm, Pm, mat = ESP.matrix_QP_iint_dqdp_delta(system, f=lambda x: [1, x[1] ** 2 + x[3] ** 2], ϵ=-0.5, res=0.01)
+            ish = dict(ESP.last_info)
+            extras["shell_quadrature_res0.01"] = {"cells": ish["cells"], "nodes": ish["nodes"], "kernel_ms": ish["kernel_ms"],
+                                                  "nodes_per_s": ish["nodes"] / (ish["kernel_ms"] * 1e-3),
+                                                  "volume_over_closed_form": float(np.nansum(mat[..., 0]) * 1e-4 / CD.energy_shell_volume(system, -0.5))}
         except Exception as e:   # never lose the headline line over the extras
-            extras = {"error": repr(e)}
+            extras = dict(extras or {}, error=repr(e))
 
     if rank == 0:
         if not (abs(float(last[0]) + 1.0) < 0.02 and steps_done == args.steps * N_total * 14000):
