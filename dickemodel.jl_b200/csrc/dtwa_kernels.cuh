@@ -929,7 +929,7 @@ __global__ void __launch_bounds__(128, DTWA_LYAP_MIN_BLOCKS) lyapunov_kernel(con
 // +1 g increasing, -1 decreasing).  Where the reference searches a root of its interpolant, the crossing is
 // located to integrator accuracy: starting from the chord estimate, Newton on the crossing time, each
 // iteration re-taking the integrator's own step from the start of the crossing step (local error of an
-// accepted step); what is left of |g| (rounding level) is removed by one Henon step (dtwa_device.cuh), so
+// accepted step); what is left of |g| (rounding level) is removed by one Henon step (classical RK4 in the event variable, dtwa_device.cuh), so
 // recorded states satisfy g = 0 to rounding.
 // Divergence: a crossing costs ~5 extra steps and happens in ~3 % of the steps of a lane.  A lane therefore
 // only NOTES a crossing (step start, times, g values) and keeps stepping; the warp refines all noted
@@ -980,16 +980,14 @@ __global__ void __launch_bounds__(EVENTS_BLOCK, DTWA_EVENTS_MIN_BLOCKS) events_k
             rk8_step<SYS>(S.par, z, th);
         }
     };
+    // The Henon step has length |g| <= 1e-13 (what Newton left), so a classical RK4 step in the event variable is exact
+    // to rounding whatever the integrator; a 12-stage step here would only be one more large body in the instruction cache.
     auto henon = [&](double (&y)[NV + 1], double hg) {
-        if constexpr (ALG == DTWA_ALG_RK4) {
-            StepTab r;
-            r.h = hg; r.hh = hg / 2.0; r.h3 = hg / 3.0; r.h6 = hg / 6.0;
-            r.hw = r.hhw = r.h3w = r.h6w = 0.0;
-            r.n = 1; r.pad = 0;
-            rk4_step<HSYS>(hp, y, r);
-        } else {
-            rk8_step<HSYS>(hp, y, hg);
-        }
+        StepTab r;
+        r.h = hg; r.hh = hg / 2.0; r.h3 = hg / 3.0; r.h6 = hg / 6.0;
+        r.hw = r.hhw = r.h3w = r.h6w = 0.0;
+        r.n = 1; r.pad = 0;
+        rk4_step<HSYS>(hp, y, r);
     };
     Traj<SYS, ALG> T;
     T.status = ST_OK;

@@ -226,7 +226,7 @@ int dtwa_lyapunov(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver *sol,
  *      conditions are integrated from 0 to t_end and every crossing of coef . u - offset = 0 is recorded
  *      (direction 0: both, +1: increasing, -1: decreasing).  The crossing is located to integrator accuracy
  *      (Newton on the crossing time with the integrator's own step from the start of the crossing step, then
- *      one Henon step -- the event function as independent variable -- so that g = 0 to rounding); the
+ *      one classical RK4 Henon step -- the event function as independent variable -- so that g = 0 to rounding); the
  *      reference searches a root of its interpolant.  ev_t[n][max_events], ev_u[n][max_events][nvar], ev_dir[n][max_events] (+1/-1),
  *      ev_count[n] (keeps counting past max_events; entries of row i at or beyond min(ev_count[i], max_events)
  *      are unspecified), u_end[n][nvar], status[n], nsteps[n] (may be NULL). ---- */

@@ -1271,7 +1271,7 @@ static void ev_refine(ev_ctx *c, double lo, double hi, double glo, double ghi)
     memcpy(y, z, sizeof(double) * nv);
     y[nv] = c->ts0 + th;
     if (g2 != 0) {
-        henon_step(kind, c->pb->par, sgn, c->coef, rk4, -g2, y);
+        henon_step(kind, c->pb->par, sgn, c->coef, 1, -g2, y);   /* |g2| <= 1e-13 in all but degenerate cases: a classical RK4 step is exact to rounding */
         int fin = 1;
         for (int i = 0; i <= nv; ++i) fin = fin && isfinite(y[i]);
         if (!fin) {
