@@ -81,7 +81,7 @@ def matrix_QP_iint_dqdp_delta(system, *, f, ϵ, res=0.1, symmetricQP=False, symm
     reference's orientation (`QPs=[(Q,P) for P in Ps, Q in Qs]`).  All cells in one launch."""
     symmetricP = symmetricQP if symmetricP is None else symmetricP
     Qs, Ps = _generate_QPs(symmetricQP, symmetricP, res, system, ϵ)
-    QP = np.array([(Q, P) for P in Ps for Q in Qs])
+    QP = np.column_stack([np.tile(Qs, len(Ps)), np.repeat(Ps, len(Qs))])      # (Q, P) for P in Ps for Q in Qs
     out, valid, scalar = _run(system, ϵ, QP, f, res, kargs.pop("onlyqroot", None), kargs.pop("devices", None))
     nonvalue = kargs.pop("nonvalue", float("nan"))
     if kargs:
@@ -101,7 +101,7 @@ def energy_shell_average(system, *, ϵ, f, res=0.01, symmetricQP=False, symmetri
     """src/EnergyShellProjections.jl:476-508"""
     symmetricP = symmetricQP if symmetricP is None else symmetricP
     Qs, Ps = _generate_QPs(symmetricQP, symmetricP, res, system, ϵ)
-    QP = np.array([(Q, P) for Q in Qs for P in Ps])     # the reference's loop order `for Q in Qs, P in Ps`
+    QP = np.column_stack([np.repeat(Qs, len(Ps)), np.tile(Ps, len(Qs))])     # the reference's loop order `for Q in Qs, P in Ps`
     out, valid, scalar = _run(system, ϵ, QP, f, res, None, devices)
     wq = np.where((QP[:, 0] != 0) & symmetricQP, 2.0, 1.0)
     wp = np.where((QP[:, 1] != 0) & (symmetricP or symmetricQP), 2.0, 1.0)

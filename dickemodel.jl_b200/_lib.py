@@ -251,17 +251,15 @@ class Context:
         for i, c in enumerate(np.asarray(coef, dtype=float).ravel()[:nv]):
             ev.coef[i] = float(c)
         ev.offset, ev.direction = float(offset), int(direction)
-        ev_t, ev_u = np.full((n, cap), np.nan), np.full((n, cap, nv), np.nan)
-        ev_dir, cnt = np.zeros((n, cap), dtype=np.int32), np.empty(n, dtype=np.int32)
+        ev_t, ev_u = np.empty((n, cap)), np.empty((n, cap, nv))      # (slots beyond ev_count are set to NaN / 0 below)
+        ev_dir, cnt = np.empty((n, cap), dtype=np.int32), np.empty(n, dtype=np.int32)
         u_end, status, nsteps = np.empty((n, nv)), np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int64)
         ms = C.c_double()
         i32p = C.POINTER(C.c_int32)
         _check(load().dtwa_integrate_events(self._h, C.byref(sys), C.byref(sol), _dp(u0), n, float(t_end), C.byref(ev), cap, _dp(ev_t),
                                             _dp(ev_u), ev_dir.ctypes.data_as(i32p), cnt.ctypes.data_as(i32p), _dp(u_end),
                                             status.ctypes.data_as(i32p), nsteps.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(ms)))
-        for a in (ev_t, ev_u):   # slots beyond ev_count hold scratch
-            pass
-        valid = np.arange(cap)[None, :] < np.minimum(cnt, cap)[:, None]
+        valid = np.arange(cap)[None, :] < np.minimum(cnt, cap)[:, None]   # slots beyond ev_count hold scratch
         ev_t[~valid] = np.nan
         ev_u[~valid] = np.nan
         ev_dir[~valid] = 0
