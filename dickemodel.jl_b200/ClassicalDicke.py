@@ -26,6 +26,13 @@ class DickeSystem(ClassicalSystems.ClassicalSystem):
     def varnames(self):
         return ["Q", "q", "P", "p"]  # :21
 
+    def vector_field(self, u, pars=None):
+        """src/ClassicalDicke.jl:11-16: (dQ, dq, dP, dp)/dt at u = [Q, q, P, p] (host formula, see ClassicalSystems.step)"""
+        w0, w, g = self.parameters() if pars is None else pars
+        Q, q, P, p = u
+        s = math.sqrt(4.0 - Q * Q - P * P)
+        return [w0 * P - g * q * Q * P / s, w * p, -w0 * Q - g * q * (s - Q * Q / s), -w * q - g * Q * s]
+
     def out_of_bounds(self, u):
         return 4 - u[2] ** 2 - u[0] ** 2 <= 0  # :18-20
 

@@ -33,6 +33,12 @@ class ClassicalLMGSystem(ClassicalSystems.ClassicalSystem):
     def varnames(self):
         return ["Q", "P"]  # :15
 
+    def vector_field(self, u, pars=None):
+        """src/ClassicalLMG.jl:8-11: (dQ, dP)/dt (host formula, see ClassicalSystems.step)"""
+        Om, xi = self.parameters() if pars is None else pars
+        Q, P = u
+        return [P * (Om - xi * Q ** 2 / 2), Q * (xi * P ** 2 / 2 - (2 * xi + Om)) + xi * Q ** 3]
+
     def out_of_bounds(self, u):
         return 4 - u[1] ** 2 - u[0] ** 2 <= 0  # :12-14
 

@@ -49,6 +49,25 @@ def out_of_bounds(system):
     return lambda u, _=None, t=0: system.out_of_bounds(u)
 
 
+def eye(n):
+    """src/ClassicalSystems.jl: the n x n identity (the reference's default `fundamental_matrix_initial`)"""
+    return np.eye(int(n))
+
+
+def step(system):
+    """src/ClassicalSystems.jl:30 -- the equations of motion as `f(du, u, p, t)`, filling du in place like the reference's
+    ParameterizedFunction (host formula for inspection and for the Newton algebra of UPOs; trajectories are integrated on
+    the GPU, never with this).  `p = [parameters..., σ]` with σ = -1 for backward time (:133-134); p=None uses the system's."""
+    vf = system.vector_field
+
+    def f(du, u, p=None, t=0.0):
+        pars = system.parameters() if p is None else list(p)[:len(system.parameters())]
+        sgn = 1.0 if p is None or len(p) <= len(system.parameters()) else float(list(p)[len(system.parameters())])
+        du[:] = sgn * np.asarray(vf(u, pars))
+        return du
+    return f
+
+
 def nvars(system, *vars):
     """src/ClassicalSystems.jl:37-45 (1-based like the reference)"""
     d = {v: i + 1 for i, v in enumerate(system.varnames())}

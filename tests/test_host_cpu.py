@@ -316,3 +316,24 @@ def test_split_over_devices_interleaves_and_restores_item_order(pkg, monkeypatch
     assert np.array_equal(seen[1], [1.0, 4.0, 7.0, 10.0])
     a, ms = L.split_over_devices([0, 1, 2, 3], 2, lambda c, it: (x[:2][it] + 1, 0.5))
     assert np.array_equal(a, [1.0, 2.0])
+
+
+def test_step_and_eye_protocol_functions(pkg, O):
+    """ClassicalSystems.step(system)(du, u, p, t) and eye(n) (src/ClassicalSystems.jl:30): the host formula of the
+    equations of motion equals the oracle's right-hand side, and Hamilton's equations of `hamiltonian`"""
+    CS, CD, CL = pkg.ClassicalSystems, pkg.ClassicalDicke, pkg.ClassicalLMG
+    assert np.array_equal(CS.eye(3), np.eye(3))
+    for system, kind, u in ((CD.ClassicalDickeSystem(w0=1.1, w=0.9, g=0.7), O.SYS_DICKE, [0.4, -0.3, 0.8, 0.2]),
+                            (CL.ClassicalLMGSystem(Ω=1.0, ξ=-1.0), O.SYS_LMG, [0.5, 0.3])):
+        du = np.zeros(len(u))
+        CS.step(system)(du, u, list(system.parameters()) + [1.0], 0.0)
+        ref, bad = O.rhs(kind, list(system.parameters()), np.array(u))
+        assert not bad and np.allclose(du, ref, rtol=1e-14, atol=1e-15)
+        back = np.zeros(len(u))
+        CS.step(system)(back, u, list(system.parameters()) + [-1.0], 0.0)
+        assert np.allclose(back, -du)
+        H = (CD if kind == O.SYS_DICKE else CL).hamiltonian(system)
+        e, n = 1e-6, len(u) // 2
+        g = np.array([(H(np.array(u) + e * d) - H(np.array(u) - e * d)) / (2 * e) for d in np.eye(len(u))])
+        ham = np.concatenate([g[n:], -g[:n]]) if kind == O.SYS_DICKE else np.array([g[1], -g[0]])
+        assert np.allclose(du, ham, atol=1e-8)
