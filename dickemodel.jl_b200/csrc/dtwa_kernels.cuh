@@ -217,8 +217,10 @@ __device__ __noinline__ double vm_slow_math(int op, double t, double acc)
 template <int NV, bool PERLANE>
 __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp, unsigned long long *u64, const double x0,
                                        const double x1, const double x2, const double x3, const bool valid, const int k,
-                                       const int w, double *store_out)
+                                       const int w, double *store_out, const bool emit = true)
 {
+    // emit = false: this lane only keeps the warp company (the program is run by the whole warp so that its per-instruction
+    // loop never splits the warp); it stores and counts nothing.  valid implies emit.
     double acc = 0.0, s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     double ov[VM_STACK - VM_REG_STACK];
     int depth = 0;
@@ -296,7 +298,7 @@ __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp,
         case OP_SUM: {
             double v = valid ? acc : 0.0;
             if constexpr (PERLANE) {
-                V.wsum[((size_t)threadIdx.x * V.window + w) * V.nslots + in.b] = v;
+                if (emit) V.wsum[((size_t)threadIdx.x * V.window + w) * V.nslots + in.b] = v;
             } else {
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
@@ -490,34 +492,39 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
             const int ahead = (!have) ? 0x7fffffff : (int)(g - flushed);
             if (__any_sync(0xffffffffu, service) || __reduce_min_sync(0xffffffffu, ahead) >= H) break;
             ++iters;
-            if (have && g < glimit) {
-                if (T.ad.t < tstop) {
-                    if ((long long)(T.nacc + T.nrej) >= A.S.maxiters) {
-                        T.status = ST_MAXITERS;
-                    } else {
-                        bool accepted;
-                        if (T.ad.attempt(A.S.par, T.u, tstop, A.S.tol, A.S.dtmin, accepted)) T.status = ST_DOMAIN;
-                        if (accepted)
-                            ++T.nacc;
-                        else if (T.status == ST_OK)
-                            ++T.nrej;
-                    }
+            const bool stepping = have && g < glimit;
+            if (stepping && T.ad.t < tstop) {
+                if ((long long)(T.nacc + T.nrej) >= A.S.maxiters) {
+                    T.status = ST_MAXITERS;
+                } else {
+                    bool accepted;
+                    if (T.ad.attempt(A.S.par, T.u, tstop, A.S.tol, A.S.dtmin, accepted)) T.status = ST_DOMAIN;
+                    if (accepted)
+                        ++T.nacc;
+                    else if (T.status == ST_OK)
+                        ++T.nrej;
                 }
-                if (T.status == ST_OK && !(T.ad.t < tstop)) {
-                    const bool valid = (k >= start_k);
-                    const int w = wslot;
-                    if constexpr (JIT)
-                        jit_reduce<NV, true>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0, valid, k,
-                                             w);
-                    else
-                        vm_run<NV, true>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0, valid, k, w,
-                                         nullptr);
-                    if (valid) atomicAdd(&V.nvalid[w], 1u);
-                    ++k;
-                    ++g;
-                    wslot = (wslot + 1 == R) ? 0 : wslot + 1;
-                    if (k < nt) tstop = A.S.ts[k];
-                }
+            }
+            const bool reached = stepping && T.status == ST_OK && !(T.ad.t < tstop);   // this lane emits output k now
+            const bool valid = reached && (k >= start_k);
+            if constexpr (JIT) {
+                if (reached)
+                    jit_reduce<NV, true>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0, valid, k,
+                                         wslot);
+            } else {
+                // the interpreter's per-instruction loop is run by the WHOLE warp whenever some lane emits (lanes that do
+                // not emit are masked): run by the emitting lanes alone it left the warp split in two groups that then
+                // executed the step body one after the other (1.66 body executions per iteration at 18 active lanes)
+                if (__any_sync(0xffffffffu, reached))
+                    vm_run<NV, true>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0, valid, k, wslot,
+                                     nullptr, reached);
+            }
+            if (reached) {
+                if (valid) atomicAdd(&V.nvalid[wslot], 1u);
+                ++k;
+                ++g;
+                wslot = (wslot + 1 == R) ? 0 : wslot + 1;
+                if (k < nt) tstop = A.S.ts[k];
             }
         }
     }
