@@ -827,7 +827,7 @@ struct LyapArgs {
 // Orbits need very different numbers of rounds (4 .. maxiters), so the groups of a persistent grid draw their
 // next initial condition from a global counter (`next`, zeroed by the host) instead of owning a fixed one.
 #ifndef DTWA_LYAP_MIN_BLOCKS
-#define DTWA_LYAP_MIN_BLOCKS 3   // 168 registers, 12 warps per SM (3 % faster than 210 registers at 8 warps: the kernel is latency-bound)
+#define DTWA_LYAP_MIN_BLOCKS 2   // flat loop: 255 registers without spills at 8 warps/SM beat 168 registers with 350 B of spills at 12 (382 vs 402 ms, 256^2 map)
 #endif
 template <int SYS, int ALG>
 __global__ void __launch_bounds__(128, DTWA_LYAP_MIN_BLOCKS) lyapunov_kernel(const SolverArgs S, const LyapArgs L, const double *__restrict__ u0,
@@ -840,6 +840,146 @@ __global__ void __launch_bounds__(128, DTWA_LYAP_MIN_BLOCKS) lyapunov_kernel(con
     const int c = (int)(threadIdx.x % G);
     const unsigned base = (threadIdx.x & 31u) & ~(unsigned)(G - 1);
     const unsigned mask = ((1u << G) - 1u) << base;
+    // Gram-Schmidt of the columns, lambda_i and the convergence test of round k (src/ClassicalSystems.jl:199-218), group-wide
+    auto renormalise = [&](double (&w)[NVB], double &sums, double (&lam)[NVB], const double (&lam_old)[NVB], int k) -> bool {
+        bool done = false;
+        const double kt = __dmul_rn((double)k, L.t_interval);
+#pragma unroll
+        for (int i = 0; i < NVB; ++i) {
+            if (done) break;
+#pragma unroll
+            for (int jj = 0; jj < i; ++jj) {
+                double uj[NVB];
+#pragma unroll
+                for (int r = 0; r < NVB; ++r) uj[r] = __shfl_sync(mask, w[r], (int)base + jj);
+                if (c == i) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int r = 0; r < NVB; ++r) d = __dadd_rn(d, __dmul_rn(w[r], uj[r]));
+#pragma unroll
+                    for (int r = 0; r < NVB; ++r) w[r] = __dsub_rn(w[r], __dmul_rn(d, uj[r]));
+                }
+            }
+            double li = 0.0;
+            if (c == i) {
+                double n2 = 0.0;
+#pragma unroll
+                for (int r = 0; r < NVB; ++r) n2 = __dadd_rn(n2, __dmul_rn(w[r], w[r]));
+                const double nrm = __dsqrt_rn(n2);
+#pragma unroll
+                for (int r = 0; r < NVB; ++r) w[r] = __ddiv_rn(w[r], nrm);
+                sums = __dadd_rn(sums, log(nrm));
+                li = __ddiv_rn(sums, kt);
+            }
+            lam[i] = __shfl_sync(mask, li, (int)base + i);
+            double e2 = 0.0, l2 = 0.0;
+#pragma unroll
+            for (int r = 0; r < NVB; ++r) {
+                const double dl = __dsub_rn(lam_old[r], lam[r]);
+                e2 = __dadd_rn(e2, __dmul_rn(dl, dl));
+                l2 = __dadd_rn(l2, __dmul_rn(lam[r], lam[r]));
+            }
+            if (__dsqrt_rn(e2) < __dadd_rn(__dmul_rn(L.lreltol, __dsqrt_rn(l2)), L.ltol)) done = true;
+        }
+        return done;
+    };
+    if constexpr (!is_fixed<ALG>::value) {
+        // Adaptive pairs: FLAT loop.  Every iteration each group that is inside an interval attempts ONE step; starting a
+        // round (initial step size), ending it (renormalisation, convergence test) and drawing the next orbit are short
+        // group-local episodes.  With the loops nested (orbits > rounds > steps) the eight groups of a warp, which need
+        // different numbers of steps per interval and of rounds per orbit, executed the step body one after the other:
+        // 17.5 active lanes per executed instruction (ncu) instead of ~31.
+        bool have = false, exhausted = false, fresh = false;
+        long long j = 0, steps = 0;
+        double xc = 0.0, w[NVB], lam[NVB], lam_old[NVB], sums = 0.0;
+        int k = 0;
+        Traj<SYS, ALG> T;
+        T.status = ST_OK;
+        T.nacc = T.nrej = 0;
+#pragma unroll
+        for (int i = 0; i < NVB; ++i) w[i] = lam[i] = lam_old[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < Sys<SYS>::NV; ++i) T.u[i] = 0.0;
+        const double tstop = S.ts[0];
+        auto finish = [&](int st, int it) {
+            if (x_out) x_out[j * NVB + c] = xc;
+            if (c == 0) {
+#pragma unroll
+                for (int i = 0; i < NVB; ++i) lambda_out[j * NVB + i] = lam[i];
+                iters_out[j] = it;
+                status[j] = st;
+                if (nsteps) nsteps[j] = steps;
+            }
+            have = false;
+        };
+#pragma unroll 1
+        while (true) {
+            if (!have && !exhausted) {   // draw the next orbit (group-uniform)
+                unsigned long long jn = 0;
+                if (c == 0) jn = atomicAdd(next, 1ull);
+                jn = __shfl_sync(mask, jn, (int)base);
+                if (jn >= (unsigned long long)n)
+                    exhausted = true;
+                else {
+                    j = (long long)jn;
+                    xc = u0[j * NVB + c];
+#pragma unroll
+                    for (int i = 0; i < NVB; ++i) {
+                        w[i] = (i == c) ? 1.0 : 0.0;
+                        lam[i] = 0.0;
+                    }
+                    sums = 0.0;
+                    steps = 0;
+                    k = 0;
+                    have = true;
+                    fresh = true;
+                }
+            }
+            if (!__any_sync(0xffffffffu, have)) break;
+            if (have && fresh) {   // a round is a fresh `integrate` call: new starting step
+                ++k;
+#pragma unroll
+                for (int i = 0; i < NVB; ++i) lam_old[i] = lam[i];
+                T.status = ST_OK;
+                T.u[0] = xc;
+#pragma unroll
+                for (int i = 0; i < NVB; ++i) T.u[1 + i] = w[i];
+                T.begin(S);
+                fresh = false;
+            }
+            if (have && T.status == ST_OK && T.ad.t < tstop) {   // one attempted step
+                if ((long long)(T.nacc + T.nrej) >= S.maxiters) {
+                    T.status = ST_MAXITERS;
+                } else {
+                    bool accepted;
+                    if (T.ad.attempt(S.par, T.u, tstop, S.tol, S.dtmin, accepted))
+                        T.status = ST_DOMAIN;
+                    else if (accepted)
+                        ++T.nacc;
+                    else
+                        ++T.nrej;
+                }
+            }
+            if (have && (T.status != ST_OK || !(T.ad.t < tstop))) {   // the interval has ended
+                if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
+                steps += (long long)T.nacc + (long long)T.nrej;
+                if (T.status != ST_OK) {
+                    finish(T.status, k);
+                } else {
+                    xc = T.u[0];
+#pragma unroll
+                    for (int i = 0; i < NVB; ++i) w[i] = T.u[1 + i];
+                    const bool done = renormalise(w, sums, lam, lam_old, k);
+                    if (done)
+                        finish(ST_OK, k);
+                    else if (k >= L.maxiters)
+                        finish(DTWA_LYAP_MAXITERS, k);
+                    else
+                        fresh = true;
+                }
+            }
+        }
+    } else {
 #pragma unroll 1
     for (;;) {
     unsigned long long jn = 0;
@@ -879,44 +1019,7 @@ __global__ void __launch_bounds__(128, DTWA_LYAP_MIN_BLOCKS) lyapunov_kernel(con
         xc = T.u[0];
 #pragma unroll
         for (int i = 0; i < NVB; ++i) w[i] = T.u[1 + i];
-        const double kt = __dmul_rn((double)k, L.t_interval);
-#pragma unroll
-        for (int i = 0; i < NVB; ++i) {
-            if (done) break;
-#pragma unroll
-            for (int jj = 0; jj < i; ++jj) {
-                double uj[NVB];
-#pragma unroll
-                for (int r = 0; r < NVB; ++r) uj[r] = __shfl_sync(mask, w[r], (int)base + jj);
-                if (c == i) {
-                    double d = 0.0;
-#pragma unroll
-                    for (int r = 0; r < NVB; ++r) d = __dadd_rn(d, __dmul_rn(w[r], uj[r]));
-#pragma unroll
-                    for (int r = 0; r < NVB; ++r) w[r] = __dsub_rn(w[r], __dmul_rn(d, uj[r]));
-                }
-            }
-            double li = 0.0;
-            if (c == i) {
-                double n2 = 0.0;
-#pragma unroll
-                for (int r = 0; r < NVB; ++r) n2 = __dadd_rn(n2, __dmul_rn(w[r], w[r]));
-                const double nrm = __dsqrt_rn(n2);
-#pragma unroll
-                for (int r = 0; r < NVB; ++r) w[r] = __ddiv_rn(w[r], nrm);
-                sums = __dadd_rn(sums, log(nrm));
-                li = __ddiv_rn(sums, kt);
-            }
-            lam[i] = __shfl_sync(mask, li, (int)base + i);
-            double e2 = 0.0, l2 = 0.0;
-#pragma unroll
-            for (int r = 0; r < NVB; ++r) {
-                const double dl = __dsub_rn(lam_old[r], lam[r]);
-                e2 = __dadd_rn(e2, __dmul_rn(dl, dl));
-                l2 = __dadd_rn(l2, __dmul_rn(lam[r], lam[r]));
-            }
-            if (__dsqrt_rn(e2) < __dadd_rn(__dmul_rn(L.lreltol, __dsqrt_rn(l2)), L.ltol)) done = true;
-        }
+        done = renormalise(w, sums, lam, lam_old, k);
     }
     if (st == ST_OK && !done) st = DTWA_LYAP_MAXITERS;
     if (live && x_out) x_out[j * NVB + c] = xc;
@@ -928,6 +1031,7 @@ __global__ void __launch_bounds__(128, DTWA_LYAP_MIN_BLOCKS) lyapunov_kernel(con
         if (nsteps) nsteps[j] = steps;
     }
     }  // work loop
+    }  // fixed step
 }
 
 // K7: surfaces of section -- SURVEY 8f rank 3 (docs/src/ClassicalDickeExamples.md:82-109: integrate with a
