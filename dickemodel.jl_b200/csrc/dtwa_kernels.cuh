@@ -758,13 +758,46 @@ __global__ void __launch_bounds__(128) integrate_kernel(const SolverArgs S, cons
     for (int i = 0; i < NV; ++i) T.u[i] = u0[j * NV + i];
     T.begin(S);
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-    for (int k = 0; k < S.nt; ++k) {
-        T.advance(S, k);
+    auto emit = [&](int k) {
         if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
         if (live) {
             double *o = out + ((size_t)j * S.nt + k) * NV;
 #pragma unroll
             for (int i = 0; i < NV; ++i) o[i] = (T.status == ST_OK) ? T.u[i] : qnan;
+        }
+    };
+    if constexpr (is_fixed<ALG>::value) {
+        for (int k = 0; k < S.nt; ++k) {
+            T.advance(S, k);
+            emit(k);
+        }
+    } else {
+        // flat loop: one attempted step per lane and iteration; a lane that has reached its output time stores the state and
+        // moves on to the next one without waiting for the others (nested "for each output time: while (t < t_k) step"
+        // loops make every lane wait for the slowest one at every output time)
+        int k = 0;
+#pragma unroll 1
+        while (__any_sync(0xffffffffu, k < S.nt)) {
+            if (k < S.nt) {
+                const double tstop = S.ts[k];
+                if (T.status == ST_OK && T.ad.t < tstop) {
+                    if ((long long)(T.nacc + T.nrej) >= S.maxiters) {
+                        T.status = ST_MAXITERS;
+                    } else {
+                        bool accepted;
+                        if (T.ad.attempt(S.par, T.u, tstop, S.tol, S.dtmin, accepted))
+                            T.status = ST_DOMAIN;
+                        else if (accepted)
+                            ++T.nacc;
+                        else
+                            ++T.nrej;
+                    }
+                }
+                if (T.status != ST_OK || !(T.ad.t < tstop)) {
+                    emit(k);
+                    ++k;
+                }
+            }
         }
     }
     if (live) {
@@ -796,8 +829,7 @@ __global__ void __launch_bounds__(128) integrate_fm_kernel(const SolverArgs S, c
     for (int i = 0; i < NVB; ++i) T.u[1 + i] = fm0 ? fm0[(j * NVB + c) * NVB + i] : (i == c ? 1.0 : 0.0);
     T.begin(S);
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-    for (int k = 0; k < S.nt; ++k) {
-        T.advance(S, k);
+    auto emit = [&](int k) {
         if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
         if (live) {
             const bool ok = T.status == ST_OK;
@@ -805,6 +837,37 @@ __global__ void __launch_bounds__(128) integrate_fm_kernel(const SolverArgs S, c
             double *o = out_fm + (((size_t)j * S.nt + k) * NVB + c) * NVB;
 #pragma unroll
             for (int i = 0; i < NVB; ++i) o[i] = ok ? T.u[1 + i] : qnan;
+        }
+    };
+    if constexpr (is_fixed<ALG>::value) {
+        for (int k = 0; k < S.nt; ++k) {
+            T.advance(S, k);
+            emit(k);
+        }
+    } else {   // flat loop, as in integrate_kernel; every decision is uniform inside a group
+        int k = 0;
+#pragma unroll 1
+        while (__any_sync(0xffffffffu, k < S.nt)) {
+            if (k < S.nt) {
+                const double tstop = S.ts[k];
+                if (T.status == ST_OK && T.ad.t < tstop) {
+                    if ((long long)(T.nacc + T.nrej) >= S.maxiters) {
+                        T.status = ST_MAXITERS;
+                    } else {
+                        bool accepted;
+                        if (T.ad.attempt(S.par, T.u, tstop, S.tol, S.dtmin, accepted))
+                            T.status = ST_DOMAIN;
+                        else if (accepted)
+                            ++T.nacc;
+                        else
+                            ++T.nrej;
+                    }
+                }
+                if (T.status != ST_OK || !(T.ad.t < tstop)) {
+                    emit(k);
+                    ++k;
+                }
+            }
         }
     }
     if (live && c == 0) {
