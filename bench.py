@@ -36,7 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOPS_PER_STEP = {"dicke_rk4": 136.0}      # SURVEY.md section 8d / BASELINE.md section 4
-FP64_INSTR_PER_STEP = {"dicke_rk4": 92.0}  # SASS of the run-time specialised hot loop for w = 1: 64 DFMA + 28 DMUL (96 for general w); tools/jit_sass.py dumps it
+FP64_INSTR_PER_STEP = {"dicke_rk4": 88.0}  # SASS of the run-time specialised hot loop for w = g = 1: 64 DFMA + 24 DMUL (96 for general w and g); tools/jit_sass.py dumps it
 
 WORK = {"system": "dicke", "par": [1.0, 1.0, 1.0], "j": 100, "center": [0.0, 0.0, 0.0, 0.0], "t_end": 100, "t_step": 0.05,
         "dt": 2.0 ** -7, "seed": 20261019}
@@ -388,7 +388,7 @@ def main():
                          "kernel": "dtwa_jit_ensemble (NVRTC specialisation of ensemble_kernel<DICKE,RK4> for this reducer set)", "kernel_ms_per_step": kernel_ms / args.steps,
                          "kernel_steps_per_s_per_gpu": kern_rate,
                          "fp64_pipe_frac_est": kern_rate * FP64_INSTR_PER_STEP["dicke_rk4"] / (peak_tflops * 1e12 / 2.0),
-                         "note": "frac is ALGORITHMIC flops (136/step) over the measured DFMA peak; fp64_pipe_frac_est counts the 92 FP64-pipe instructions/step of the SASS hot loop (w = 1 specialisation), each of which occupies one DFMA issue slot"},
+                         "note": "frac is ALGORITHMIC flops (136/step) over the measured DFMA peak; fp64_pipe_frac_est counts the 88 FP64-pipe instructions/step of the SASS hot loop (w = g = 1 specialisation), each of which occupies one DFMA issue slot"},
             "cpu_baseline": cpu,
             "extras": extras,
             "result_check": {"mean_jz_t0": float(last[0]), "mean_jz_t5": float(last[100]), "mean_jz_t100": float(last[-1])},

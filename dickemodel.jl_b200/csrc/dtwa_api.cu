@@ -324,6 +324,17 @@ static SysPar make_par(const dtwa_system *sys, int backwards)
     return p;
 }
 
+// which of the (sign-folded) Dicke parameters are exactly +-1, for the run-time specialisation (x * 1.0 == x exactly, so the
+// specialised kernel keeps the bits of the generic one): (w == +-1 ? +-1 : 0) + 3 * (g == +-1 ? +-1 : 0), see jit_source
+static int unit_flags(const dtwa_system *sys, int backwards)
+{
+    if (sys->kind != DTWA_SYS_DICKE) return 0;
+    const SysPar p = make_par(sys, backwards);
+    const int wf = p.b == 1.0 ? 1 : p.b == -1.0 ? -1 : 0;
+    const int gf = p.c == 1.0 ? 1 : p.c == -1.0 ? -1 : 0;
+    return wf + 3 * gf;
+}
+
 static int check_solver(const dtwa_solver *sol, bool fixed_needs_dt = true)
 {
     if (!sol) return set_err(DTWA_ERR_INVALID, "solver is NULL");
@@ -1375,8 +1386,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
         // (parameter scans) pick the specialised kernel up once it is ready -- same bits as the interpreter
         cudaKernel_t jk;
         CK(cudaSetDevice(ctx->devs[0].device));
-        const double wsigned = make_par(sys, sol->backwards).b;
-        const int wflag = (sys->kind == DTWA_SYS_DICKE && wsigned == 1.0) ? 1 : (sys->kind == DTWA_SYS_DICKE && wsigned == -1.0) ? -1 : 0;
+        const int wflag = unit_flags(sys, sol->backwards);
         if (jit_cache().get_async(sys->kind, sol->alg, wflag, prog, &jk) == 0) {
             kern = (const void *)jk;
             used_jit = true;
@@ -1386,8 +1396,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
         cudaKernel_t jk;
         std::string jerr;
         CK(cudaSetDevice(ctx->devs[0].device));
-        const double wsigned = make_par(sys, sol->backwards).b;
-        const int wflag = (sys->kind == DTWA_SYS_DICKE && wsigned == 1.0) ? 1 : (sys->kind == DTWA_SYS_DICKE && wsigned == -1.0) ? -1 : 0;
+        const int wflag = unit_flags(sys, sol->backwards);
         if (jit_cache().get(sys->kind, sol->alg, wflag, prog, &jk, jerr)) {
             // forced specialisation fails loudly; in auto mode the (slower) interpreter kernel runs instead -- still on
             // the GPU -- and the result reports jit = 0 (e.g. libnvrtc is not installed next to the driver)
@@ -1748,7 +1757,7 @@ extern "C" int dtwa_jit_compile(const dtwa_system *sys, const dtwa_solver *sol, 
         return set_err(DTWA_ERR_EXPR, e.what());
     }
     prog.emit(OP_END);
-    const std::string src = jit_source(sys->kind, sol->alg, (sys->kind == DTWA_SYS_DICKE && sys->params[1] == 1.0) ? 1 : 0, prog);
+    const std::string src = jit_source(sys->kind, sol->alg, unit_flags(sys, sol->backwards), prog);
     if (src_out && src_cap > 0) {
         std::snprintf(src_out, (size_t)src_cap, "%s", src.c_str());
     }

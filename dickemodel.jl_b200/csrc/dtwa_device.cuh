@@ -70,7 +70,8 @@ struct Sys<DTWA_SYS_DICKE> {
     static constexpr int NVB = 4, GROUP = 1, NORM_N = 4;  // see the variational systems below
     // 18 FP64-pipe instructions + 1 MUFU.  FOLDQ: du[1] is returned as p (the factor w lives in the
     // caller's step constants), 17 instructions.  DTWA_W_IS_ONE / DTWA_W_IS_MINUS_ONE (defined by the
-    // run-time specialisation when |w| == 1; x*1.0 == x exactly, so results do not change): 16.
+    // run-time specialisation when |w| == 1; x*1.0 == x exactly, so results do not change): 16.  DTWA_G_IS_ONE /
+    // DTWA_G_IS_MINUS_ONE (|g| == 1, the same argument for g*q): 15.
     template <bool FOLDQ = false>
     __device__ __forceinline__ static void rhs(const SysPar &p, const double (&u)[4], double (&du)[4])
     {
@@ -79,7 +80,13 @@ struct Sys<DTWA_SYS_DICKE> {
         r2 = fma(-Q, Q, r2);               // 4 - P^2 - Q^2
         double is, s;
         rsqrt_sqrt_pair(r2, is, s);        // 1/s and s
+#if defined(DTWA_G_IS_ONE)
+        const double gq = q;
+#elif defined(DTWA_G_IS_MINUS_ONE)
+        const double gq = -q;
+#else
         const double gq = __dmul_rn(p.c, q);
+#endif
         const double gqQ = __dmul_rn(gq, Q);
         const double e = fma(gqQ, is, -p.a);      // g q Q / s - w0
         du[0] = __dmul_rn(-P, e);                 // P w0 - g P q Q / s
