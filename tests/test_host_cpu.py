@@ -194,6 +194,28 @@ def test_runtime_specialisation_compiles_without_a_gpu(pkg):
         lib.jit_compile(s, sol, ["q"])
 
 
+def test_runtime_specialisation_marks_unit_parameters(pkg):
+    """the generated source drops the multiplications by w and g only when the (sign-folded) parameter is exactly +-1
+    (x * 1.0 == x, so the specialised kernel keeps the bits of the generic one)"""
+    lib = pkg._lib
+
+    def defines(w, g, backwards=0):
+        s = lib.System()
+        s.kind = lib.SYS_DICKE
+        s.params[0], s.params[1], s.params[2] = 1.0, w, g
+        sol = lib.Solver()
+        sol.alg, sol.dt, sol.tol, sol.backwards = lib.ALG_RK4, 0.01, 1e-8, backwards
+        src, _ = lib.jit_compile(s, sol, ["Q"])
+        return {d for d in ("DTWA_W_IS_ONE", "DTWA_W_IS_MINUS_ONE", "DTWA_G_IS_ONE", "DTWA_G_IS_MINUS_ONE") if f"#define {d} 1" in src}
+
+    assert defines(1.0, 1.0) == {"DTWA_W_IS_ONE", "DTWA_G_IS_ONE"}
+    assert defines(1.0, 1.0, backwards=1) == {"DTWA_W_IS_MINUS_ONE", "DTWA_G_IS_MINUS_ONE"}
+    assert defines(0.8, 1.0) == {"DTWA_G_IS_ONE"}
+    assert defines(1.0, 0.66) == {"DTWA_W_IS_ONE"}
+    assert defines(0.8, -1.0) == {"DTWA_G_IS_MINUS_ONE"}
+    assert defines(2.0, 0.5) == set()
+
+
 GLOO_WORKER = r'''
 import os, sys, json
 import numpy as np
