@@ -126,7 +126,26 @@ def run_reference(args):
                                        "(restated reference CPU path; Julia unavailable)"},
             "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there at the C level (NCCL prints its version line on the first
+    communicator), so fd 1 is pointed at stderr for the whole run and the result line goes to the saved descriptor."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    text = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, text)
 
 
 def main():
@@ -144,6 +163,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.n_traj = int(args.n_traj)
+    claim_stdout()
 
     import __graft_entry__ as graft
     pkg = graft.load_package()
@@ -393,7 +413,7 @@ def main():
             "extras": extras,
             "result_check": {"mean_jz_t0": float(last[0]), "mean_jz_t5": float(last[100]), "mean_jz_t100": float(last[-1])},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
