@@ -76,14 +76,21 @@ def nvars(system, *vars):
 
 # ---- integrator algorithms (markers standing for the OrdinaryDiffEq objects the reference passes) ----
 class _Alg:
-    def __init__(self, name, code, fixed, note=""):
-        self.name, self.code, self.fixed, self.note = name, code, fixed, note
+    """name: the reference's spelling; code: the tableau that runs (DTWA_ALG_*); gains: OrdinaryDiffEq's default
+    (beta1, beta2, qmin, qmax) of the NAMED algorithm (alg_utils.jl), None = the library's defaults for `code`."""
+
+    def __init__(self, name, code, fixed, note="", gains=None):
+        self.name, self.code, self.fixed, self.note, self.gains = name, code, fixed, note, gains
 
     def __call__(self):
         return self
 
     def __repr__(self):
         return f"{self.name}()"
+
+    @property
+    def runs_as(self):
+        return {_lib.ALG_RK4: "RK4", _lib.ALG_RK8: "RK8 (DOP853 weights, fixed step)", _lib.ALG_DP5: "DP5", _lib.ALG_DOP853: "DOP853"}[self.code]
 
 
 DP8 = _Alg("DP8", _lib.ALG_DOP853, False)
@@ -92,12 +99,17 @@ DP5 = _Alg("DP5", _lib.ALG_DP5, False)
 RK4 = _Alg("RK4", _lib.ALG_RK4, True)
 RK8 = _Alg("RK8", _lib.ALG_RK8, True)
 # The reference default (src/ClassicalSystems.jl:84).  Its coefficients are not available offline
-# (hard part 8), so the same-order Hairer pair DOP853 (= DP8()) is run instead.
-TsitPap8 = _Alg("TsitPap8", _lib.ALG_DOP853, False, "runs as DOP853: the Tsitouras-Papakostas tableau is not available offline")
-Vern8 = _Alg("Vern8", _lib.ALG_DOP853, False, "runs as DOP853")
-Tsit5 = _Alg("Tsit5", _lib.ALG_DP5, False, "runs as DP5")
+# (hard part 8), so the same-order Hairer pair DOP853 (= DP8()) is run instead -- under the step
+# controller OrdinaryDiffEq gives the NAMED algorithm (generic order-p gains beta1 = 7/(10p), beta2 = 2/(5p), qmin 1/5, qmax 10).
+_GENERIC8 = (7.0 / 80.0, 2.0 / 40.0, 0.2, 10.0)
+_GENERIC5 = (7.0 / 50.0, 2.0 / 25.0, 0.2, 10.0)
+TsitPap8 = _Alg("TsitPap8", _lib.ALG_DOP853, False, "the Tsitouras-Papakostas tableau is not available offline", _GENERIC8)
+Vern8 = _Alg("Vern8", _lib.ALG_DOP853, False, "Verner's tableau is not available offline", _GENERIC8)
+Tsit5 = _Alg("Tsit5", _lib.ALG_DP5, False, "Tsitouras' tableau is not available offline", _GENERIC5)
 _BY_NAME = {a.name.lower(): a for a in (DP8, DP5, RK4, RK8, TsitPap8, Vern8, Tsit5)}
 _BY_NAME["dop853"] = DP8
+_warned_substitution = set()
+last_solver = {}   # what the most recent solver_from_kargs resolved to: requested/actual algorithm, controller, gains
 
 
 def _resolve_alg(alg):
@@ -121,6 +133,8 @@ def solver_from_kargs(kargs: dict) -> _lib.Solver:
     adaptive = k.pop("adaptive", None)
     dtmin = k.pop("dtmin", None)
     maxiters = k.pop("maxiters", None)
+    controller = k.pop("controller", None)
+    gains = {g: k.pop(g, None) for g in ("beta1", "beta2", "qmin", "qmax", "gamma", "qoldinit")}   # solve()'s own keywords
     for ignored in ("save_everystep", "show_progress", "progress", "verbose", "dense"):
         k.pop(ignored, None)
     for unsupported in ("use_big_numbers", "callback"):   # integrate() handles ContinuousCallback itself
@@ -140,6 +154,12 @@ def solver_from_kargs(kargs: dict) -> _lib.Solver:
     fixed = code in (_lib.ALG_RK4, _lib.ALG_RK8)
     if fixed and (dt is None or not dt > 0):
         raise ValueError("fixed-step integration needs dt > 0")
+    if alg.note and alg.name not in _warned_substitution:   # once per process and algorithm
+        _warned_substitution.add(alg.name)
+        import warnings
+        warnings.warn(f"integrator_alg={alg.name}(): {alg.note}; the same-order pair {alg.runs_as} runs instead, under "
+                      f"OrdinaryDiffEq's step controller for {alg.name} (the algorithm actually run is recorded in "
+                      "ClassicalSystems.last_solver / TWA.last_info['algorithm'])", RuntimeWarning, stacklevel=3)
     s = _lib.Solver()
     s.alg = code
     s.backwards = int(backwards)
@@ -147,7 +167,55 @@ def solver_from_kargs(kargs: dict) -> _lib.Solver:
     s.tol = tol
     s.dtmin = float(dtmin) if dtmin else 0.0
     s.maxiters = int(maxiters) if maxiters else 0
+    if controller in (None, "ode", "OrdinaryDiffEq", "pi", "PI"):
+        s.controller = _lib.CTRL_ODE
+        b1, b2, qmin, qmax = alg.gains if alg.gains is not None else (0.0, 0.0, 0.0, 0.0)
+        if gains["beta1"] is not None or gains["beta2"] is not None:
+            # OrdinaryDiffEq: beta2 given -> beta1 default follows from it; beta1 alone keeps the default beta2
+            d1, d2 = _default_betas(alg, code)
+            b2 = float(gains["beta2"]) if gains["beta2"] is not None else d2
+            b1 = float(gains["beta1"]) if gains["beta1"] is not None else _beta1_from_beta2(alg, code, b2)
+        s.beta1, s.beta2 = b1, b2
+        s.qmin = float(gains["qmin"]) if gains["qmin"] is not None else qmin
+        s.qmax = float(gains["qmax"]) if gains["qmax"] is not None else qmax
+        s.gamma = float(gains["gamma"]) if gains["gamma"] is not None else 0.0
+        s.qoldinit = float(gains["qoldinit"]) if gains["qoldinit"] is not None else 0.0
+        ctrl_name = "OrdinaryDiffEq PI"
+    elif controller in ("scipy", "SciPy"):
+        if any(v is not None for v in gains.values()):
+            raise ValueError("beta1/beta2/qmin/qmax/gamma/qoldinit belong to the OrdinaryDiffEq controller, not to controller='scipy'")
+        s.controller = _lib.CTRL_SCIPY
+        ctrl_name = "SciPy"
+    else:
+        raise ValueError(f"controller={controller!r}: use 'ode' (OrdinaryDiffEq's, the default) or 'scipy'")
+    last_solver.clear()
+    last_solver.update(requested=alg.name, algorithm={_lib.ALG_RK4: "RK4", _lib.ALG_RK8: "RK8", _lib.ALG_DP5: "DP5", _lib.ALG_DOP853: "DOP853"}[code],
+                       substituted=bool(alg.note), controller=None if fixed else ctrl_name,
+                       gains=None if (fixed or s.controller != _lib.CTRL_ODE) else effective_gains(s))
     return s
+
+
+def _default_betas(alg, code):
+    """OrdinaryDiffEq alg_utils.jl beta1_default / beta2_default of the algorithm the caller NAMED"""
+    if alg.gains is not None:
+        return alg.gains[0], alg.gains[1]
+    return (0.2 - 0.03, 0.04) if code == _lib.ALG_DP5 else (0.125, 0.0)
+
+
+def _beta1_from_beta2(alg, code, beta2):
+    if alg.gains is not None:     # generic: beta1_default does not depend on beta2
+        return alg.gains[0]
+    return 0.2 - 3.0 * beta2 / 4.0 if code == _lib.ALG_DP5 else 0.125 - beta2 / 5.0
+
+
+def effective_gains(s: _lib.Solver):
+    """the gains the library will use for this solver (mirror of make_ctrl in csrc/dtwa_api.cu)"""
+    dp5 = s.alg == _lib.ALG_DP5
+    beta2 = max(0.0, s.beta2) if s.beta1 > 0 else (0.04 if dp5 else 0.0)
+    beta1 = s.beta1 if s.beta1 > 0 else (0.2 - 3.0 * beta2 / 4.0 if dp5 else 0.125 - beta2 / 5.0)
+    return {"beta1": beta1, "beta2": beta2, "qmin": s.qmin if s.qmin > 0 else (0.2 if dp5 else 1.0 / 3.0),
+            "qmax": s.qmax if s.qmax > 0 else (10.0 if dp5 else 6.0), "gamma": s.gamma if s.gamma > 0 else 0.9,
+            "qoldinit": s.qoldinit if s.qoldinit > 0 else 1e-4}
 
 
 class ODESolution:
@@ -158,6 +226,7 @@ class ODESolution:
         self._system, self._u0, self._t0, self._kargs = system, u0, t0, kargs
         self.t, self.u, self.retcode, self.nsteps = t, u, retcode, nsteps
         self.fundamental_matrix = None   # [len(t)][nvar][nvar] when get_fundamental_matrix=True
+        self.solver = dict(last_solver)  # requested / actual algorithm, controller and gains of this solve
 
     def x(self, i=-1):
         """`(x, Φ)` at saved time i -- the reference's `s.u[i].x` of an ArrayPartition (src/ClassicalSystems.jl:118)"""

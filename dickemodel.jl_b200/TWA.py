@@ -22,7 +22,7 @@ from fractions import Fraction
 
 import numpy as np
 
-from . import ClassicalSystems, PhaseSpaces, symbolic
+from . import ClassicalSystems, PhaseSpaces, distributed, symbolic
 from . import _lib
 from .symbolic import Expr
 
@@ -406,19 +406,18 @@ def monte_carlo_integrate(system, mc_system, *, tolerate_errors=True, show_progr
     csys = system._c_system()
     dcfg = _lib.distributed()
     rank, world = dcfg["rank"], dcfg["world"]
-    per = -(-N // world)
-    lo, hi = min(N, rank * per), min(N, (rank + 1) * per)
-    if hi - lo < 1:
-        raise ValueError("N is smaller than the number of ranks")
-    chunk = hi - lo if maxNBatch == math.inf else int(max(1, min(hi - lo, maxNBatch)))
+    lo, hi = distributed.shard_bounds(N, rank, world)
+    # the launch count must not depend on the rank (every launch ends in a collective when world > 1): a rank whose
+    # block is shorter, or empty, runs empty chunks
+    chunk, nchunks = distributed.chunk_plan(N, world, maxNBatch)
     base = dist.offset
     if dist.u0 is not None and base + N > len(dist.u0):
         raise ValueError("not enough host-supplied initial conditions for N")
     total, info_tot = None, {}
-    pos = lo
-    while pos < hi:
-        n = min(chunk, hi - pos)
-        u0 = dist.u0[base + pos: base + pos + n] if dist.u0 is not None else None
+    for c in range(nchunks):
+        pos = min(hi, lo + c * chunk)
+        n = max(0, min(chunk, hi - pos))
+        u0 = dist.u0[base + pos: base + pos + n] if (dist.u0 is not None and n > 0) else None
         smp = dist._c_sampler(offset=base + pos, u0=u0)
         arrays, info = ctx.ensemble(csys, sol, smp, n, ts, mc_system.f_loop, tolerate_errors=tolerate_errors,
                                     allreduce=dcfg["allreduce"] if world > 1 else None)
@@ -429,8 +428,14 @@ def monte_carlo_integrate(system, mc_system, *, tolerate_errors=True, show_progr
                 a += b
             for k, v in info.items():
                 info_tot[k] = max(info_tot[k], v) if k in ("resample_rounds", "jit") else info_tot[k] + v
-        pos += n
     dist.offset = base + N
+    info_tot.update(algorithm=ClassicalSystems.last_solver.get("algorithm"), requested_algorithm=ClassicalSystems.last_solver.get("requested"),
+                    controller=ClassicalSystems.last_solver.get("controller"), controller_gains=ClassicalSystems.last_solver.get("gains"))
+    if tolerate_errors and info_tot.get("n_unfinished", 0) > 0:
+        import warnings
+        warnings.warn(f"{info_tot['n_unfinished']} of {N} trajectories did not finish (maxiters reached, or more failures than "
+                      "the resampling list holds) and contribute nothing after they stopped; results are still divided by N "
+                      "(TWA.last_info['n_valid'] has the per-time counts)", RuntimeWarning, stacklevel=2)
     last_info = info_tot
     res = total if (len(total) > 1 or getattr(mc_system, "_chained", False)) else total[0]
     return mc_system.f_final(res)

@@ -76,6 +76,7 @@ struct DevCtx {
     char name[256] = {0};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf partial, meta, u0, fail[2], scratch_a, scratch_b, scratch_c, ring;
+    DevBuf arena_f64, arena_u64;   // result arenas of the ensemble in flight (grow-only: no cudaMalloc/cudaFree per call)
     // packed events left on the device by dtwa_integrate_events_packed (inside `ring`)
     int64_t packed_total = 0;
     int packed_nv = 0;
@@ -101,6 +102,7 @@ struct dtwa_ctx {
     int jit_mode = 2;  // 0: interpret the reducer program, 1: always specialise with NVRTC, 2: specialise large ensembles
     NcclApi nccl;
     std::vector<ncclComm_t> comms;
+    bool plan_live = false;   // a dtwa_plan of this context has not been freed yet: its arenas live in the DevCtx buffers
     // packed events of a split dtwa_integrate_events_packed: (device, first event, events) per block
     struct PackedBlock {
         int dev;
@@ -244,7 +246,8 @@ extern "C" int dtwa_destroy(dtwa_ctx *ctx)
     for (auto &d : ctx->devs) {
         cudaSetDevice(d.device);
         cudaStreamSynchronize(d.stream);
-        for (DevBuf *b : {&d.partial, &d.meta, &d.u0, &d.fail[0], &d.fail[1], &d.scratch_a, &d.scratch_b, &d.scratch_c, &d.ring}) b->release();
+        for (DevBuf *b : {&d.partial, &d.meta, &d.u0, &d.fail[0], &d.fail[1], &d.scratch_a, &d.scratch_b, &d.scratch_c, &d.ring, &d.arena_f64, &d.arena_u64})
+            b->release();
         for (auto &ev : d.ev)
             if (ev) cudaEventDestroy(ev);
         if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
@@ -413,10 +416,41 @@ static void detect_uniform(const double *ts, int nt, const std::vector<StepTab> 
     S.first_n = tab[0].n;
 }
 
+// step-size controller of the adaptive pairs: OrdinaryDiffEq's defaults per algorithm (alg_utils.jl: beta2_default,
+// beta1_default, qmin_default, qmax_default, gamma_default; qoldinit = 1e-4) unless the caller gives gains
+static CtrlPar make_ctrl(const dtwa_solver *sol, bool force_scipy)
+{
+    CtrlPar c;
+    std::memset(&c, 0, sizeof(c));
+    if (force_scipy || sol->controller == DTWA_CTRL_SCIPY) {
+        c.kind = DTWA_CTRL_SCIPY;
+        c.dom_shrink = 0.2;
+        c.qoldinit = 1e-4f;
+        return c;
+    }
+    const bool dp5 = sol->alg == DTWA_ALG_DP5;
+    // gains: beta1 > 0 means the caller sets beta1 AND beta2 (beta2 = 0 is a legitimate choice); otherwise the defaults
+    const double beta2 = sol->beta1 > 0 ? std::max(0.0, sol->beta2) : (dp5 ? 0.04 : 0.0);
+    const double beta1 = sol->beta1 > 0 ? sol->beta1 : (dp5 ? 0.2 - 3.0 * beta2 / 4.0 : 0.125 - beta2 / 5.0);
+    const double qmin = sol->qmin > 0 ? sol->qmin : (dp5 ? 0.2 : 1.0 / 3.0);
+    const double qmax = sol->qmax > 0 ? sol->qmax : (dp5 ? 10.0 : 6.0);
+    const double gamma = sol->gamma > 0 ? sol->gamma : 0.9;
+    c.kind = DTWA_CTRL_ODE;
+    c.beta1 = (float)beta1;
+    c.nbeta2 = (float)(-beta2);
+    c.inv_gamma = (float)(1.0 / gamma);
+    c.q_lo = (float)(1.0 / qmax);
+    c.q_hi = (float)(1.0 / qmin);
+    c.qoldinit = (float)(sol->qoldinit > 0 ? sol->qoldinit : 1e-4);
+    c.dom_shrink = qmin;
+    return c;
+}
+
 static SolverArgs make_solver_args(const dtwa_system *sys, const dtwa_solver *sol, const StepTab *d_tab, const double *d_ts,
-                                   const double *ts, int nt, const std::vector<StepTab> &tab)
+                                   const double *ts, int nt, const std::vector<StepTab> &tab, bool force_scipy = false)
 {
     SolverArgs S;
+    S.ctrl = make_ctrl(sol, force_scipy);
     S.par = make_par(sys, sol->backwards);
     detect_uniform(ts, nt, tab, S.par.b, S);
     S.tab = d_tab;
@@ -712,7 +746,7 @@ extern "C" int dtwa_integrate_fm(dtwa_ctx *ctx, const dtwa_system *sys, const dt
     CK(cudaMemcpyAsync(meta + tab_b, ts, ts_b, cudaMemcpyHostToDevice, d.stream));
     CK(cudaMemcpyAsync(d.u0.p, u0, b_u0, cudaMemcpyHostToDevice, d.stream));
     if (fm0) CK(cudaMemcpyAsync((unsigned char *)d.u0.p + b_u0, fm0, b_fm0, cudaMemcpyHostToDevice, d.stream));
-    const SolverArgs S = make_solver_args(sys, sol, (const StepTab *)meta, (const double *)(meta + tab_b), ts, nt, tab);
+    const SolverArgs S = make_solver_args(sys, sol, (const StepTab *)meta, (const double *)(meta + tab_b), ts, nt, tab, /*force_scipy=*/true);
     const unsigned grid = blocks_for(n * nv, 128);
     const double *d_fm0 = fm0 ? (const double *)((unsigned char *)d.u0.p + b_u0) : nullptr;
     by_var_system(sys->kind, [&](auto sk) {
@@ -793,7 +827,7 @@ extern "C" int dtwa_lyapunov(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_s
     CK(cudaMemcpyAsync(meta, tab.data(), tab_b, cudaMemcpyHostToDevice, d.stream));
     CK(cudaMemcpyAsync(meta + tab_b, ts1, ts_b, cudaMemcpyHostToDevice, d.stream));
     CK(cudaMemcpyAsync(d.u0.p, u0, b_u0, cudaMemcpyHostToDevice, d.stream));
-    const SolverArgs S = make_solver_args(sys, sol, (const StepTab *)meta, (const double *)(meta + tab_b), ts1, 1, tab);
+    const SolverArgs S = make_solver_args(sys, sol, (const StepTab *)meta, (const double *)(meta + tab_b), ts1, 1, tab, /*force_scipy=*/true);
     LyapArgs L;
     L.t_interval = t_interval;
     L.ltol = lam_tol;
@@ -879,7 +913,7 @@ static int events_solve(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver
     CK(cudaMemcpyAsync(meta, tab.data(), tab_b, cudaMemcpyHostToDevice, d.stream));
     CK(cudaMemcpyAsync(meta + tab_b, ts1, ts_b, cudaMemcpyHostToDevice, d.stream));
     CK(cudaMemcpyAsync(d.u0.p, u0, b_u0, cudaMemcpyHostToDevice, d.stream));
-    const SolverArgs S = make_solver_args(sys, sol, (const StepTab *)meta, (const double *)(meta + tab_b), ts1, 1, tab);
+    const SolverArgs S = make_solver_args(sys, sol, (const StepTab *)meta, (const double *)(meta + tab_b), ts1, 1, tab, /*force_scipy=*/true);
     EventArgs E;
     std::memset(&E, 0, sizeof(E));
     for (int i = 0; i < nv; ++i) E.coef[i] = ev->coef[i];
@@ -1251,9 +1285,8 @@ extern "C" int dtwa_plan_free(dtwa_plan *plan)
         if (!dp.dc) continue;
         cudaSetDevice(dp.dc->device);
         cudaStreamSynchronize(dp.dc->stream);
-        if (dp.d_f64) cudaFree(dp.d_f64);
-        if (dp.d_u64) cudaFree(dp.d_u64);
     }
+    if (plan->ctx) plan->ctx->plan_live = false;   // (the arenas stay in the context's grow-only buffers)
     delete plan;
     return DTWA_OK;
 }
@@ -1266,10 +1299,19 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
     *plan_out = nullptr;
     TRY(check_system(sys));
     TRY(check_solver(sol, /*fixed_needs_dt=*/false));
-    if (N < 1) return set_err(DTWA_ERR_INVALID, "N must be >= 1");
+    // N == 0 is the empty block of a rank in a one-process-per-GPU job (more ranks than trajectories, or a short last
+    // chunk): zeroed arenas, no kernel -- so that every rank issues the same collectives (the shim rejects a total N < 1)
+    if (N < 0) return set_err(DTWA_ERR_INVALID, "N must be >= 0");
     if (!red || nred < 1) return set_err(DTWA_ERR_INVALID, "at least one reducer is required");
+    if (ctx->plan_live) return set_err(DTWA_ERR_INVALID, "the previous dtwa_plan of this context has not been freed (one ensemble in flight per context)");
     SamplerPar sp0;
-    TRY(make_sampler_par(sys, smp, sp0));
+    if (N == 0 && smp && (smp->kind == DTWA_SAMPLER_HOST_ARRAY || smp->kind == DTWA_SAMPLER_DEVICE_ARRAY) && !smp->u0) {
+        dtwa_sampler tmp = *smp;
+        static const double dummy[4] = {0, 0, 0, 0};
+        tmp.u0 = dummy;
+        TRY(make_sampler_par(sys, &tmp, sp0));
+    } else
+        TRY(make_sampler_par(sys, smp, sp0));
     std::vector<StepTab> tab;
     TRY(build_step_table(ts, nt, sol->dt, make_par(sys, sol->backwards).b, tab));
     const bool fixed = sol->alg == DTWA_ALG_RK4 || sol->alg == DTWA_ALG_RK8;
@@ -1431,8 +1473,10 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
     std::memcpy(blob.data() + o_s, ts, sizeof(double) * nt);
     std::memcpy(blob.data() + o_p, prog.ins.data(), sizeof(VmIns) * prog.ins.size());
 
-    const long long per = (N + ndev - 1) / ndev;
+    // balanced contiguous blocks: N / ndev trajectories each, the first N % ndev devices one more
+    const long long blk = N / ndev, extra = N % ndev;
     int rc = 0;
+    ctx->plan_live = true;
     std::vector<EnsArgs> args(ndev);
     std::vector<LaunchShape> shapes(ndev);
     std::vector<unsigned *> fail_counts(ndev, nullptr);
@@ -1443,13 +1487,15 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
         DevCtx &d = ctx->devs[di];
         DevPlan &dp = plan->devs[di];
         dp.dc = &d;
-        dp.lo = std::min<long long>(N, per * di);
-        dp.n = std::min<long long>(N, per * (di + 1)) - dp.lo;
+        dp.lo = blk * di + std::min<long long>(di, extra);
+        dp.n = blk + (di < extra ? 1 : 0);
         auto body = [&]() -> int {
             CK(cudaSetDevice(d.device));
             CK(cudaEventRecord(d.ev[0], d.stream));
-            CK(cudaMalloc(&dp.d_f64, sizeof(double) * plan->n_f64));
-            CK(cudaMalloc(&dp.d_u64, sizeof(unsigned long long) * plan->n_u64));
+            TRY(d.arena_f64.ensure(sizeof(double) * plan->n_f64));
+            TRY(d.arena_u64.ensure(sizeof(unsigned long long) * plan->n_u64));
+            dp.d_f64 = (double *)d.arena_f64.p;
+            dp.d_u64 = (unsigned long long *)d.arena_u64.p;
             CK(cudaMemsetAsync(dp.d_f64, 0, sizeof(double) * plan->n_f64, d.stream));
             CK(cudaMemsetAsync(dp.d_u64, 0, sizeof(unsigned long long) * plan->n_u64, d.stream));
             if (dp.n == 0) {
@@ -1510,63 +1556,93 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
         rc = body();
     }
 
-    // ---- phase 2: resampling rounds (src/TWA.jl:186-209) + fixed-order merge of the partial sums ----
-    for (int di = 0; di < ndev && !rc; ++di) {
-        DevCtx &d = ctx->devs[di];
-        DevPlan &dp = plan->devs[di];
-        if (dp.n == 0) continue;
-        auto body = [&]() -> int {
-            CK(cudaSetDevice(d.device));
-            EnsArgs A = args[di];
-            int cur = 0;
-            for (int round = 1;; ++round) {
-                unsigned cnt = 0;
-                CK(cudaMemcpyAsync(&cnt, d.fail[cur].p, sizeof(unsigned), cudaMemcpyDeviceToHost, d.stream));
-                CK(cudaStreamSynchronize(d.stream));
-                if (!A.fail_out) {
-                    if (!tolerate_errors) {  // the reference rethrows the first error (src/TWA.jl:199-201)
-                        unsigned long long nfail = 0;
-                        CK(cudaMemcpyAsync(&nfail, dp.d_u64 + CNT_FAILED, sizeof(nfail), cudaMemcpyDeviceToHost, d.stream));
-                        CK(cudaStreamSynchronize(d.stream));
-                        if (nfail)
-                            return set_err(DTWA_ERR_BOUNDS, "a trajectory left the domain (DomainError in the reference) and tolerate_errors=false");
-                    }
-                    break;
-                }
-                if (cnt == 0) break;
-                if (cnt > fail_caps[di]) cnt = fail_caps[di];
-                if (round > 100) return set_err(DTWA_ERR_TOO_MANY_FAILURES, "Too many errors: a trajectory failed in more than 100 consecutive resampling rounds");
-                // sort the failure list by trajectory index so that the round is reproducible
-                std::vector<FailRec> recs(cnt);
-                CK(cudaMemcpyAsync(recs.data(), (unsigned char *)d.fail[cur].p + 16, sizeof(FailRec) * cnt, cudaMemcpyDeviceToHost, d.stream));
-                CK(cudaStreamSynchronize(d.stream));
-                std::sort(recs.begin(), recs.end(), [](const FailRec &a, const FailRec &b) { return a.idx < b.idx; });
-                CK(cudaMemcpyAsync((unsigned char *)d.fail[cur].p + 16, recs.data(), sizeof(FailRec) * cnt, cudaMemcpyHostToDevice, d.stream));
-                const int nxt = cur ^ 1;
-                CK(cudaMemsetAsync(d.fail[nxt].p, 0, 16, d.stream));
-                A.redo = (const FailRec *)((unsigned char *)d.fail[cur].p + 16);
-                A.fail_count = (unsigned *)d.fail[nxt].p;
-                A.fail_out = (FailRec *)((unsigned char *)d.fail[nxt].p + 16);
-                A.N = cnt;
-                A.attempt = (uint32_t)round;
-                LaunchShape ls = shapes[di];
-                ls.grid = (int)std::max(1ll, std::min<long long>((cnt + ls.block - 1) / ls.block, shapes[di].grid));
-                TRY(launch_ens(d, kern, A, ls));
-                CK(cudaStreamSynchronize(d.stream));  // recs must outlive the H2D copy
-                plan->launches++;
-                plan->rounds = std::max(plan->rounds, round);
-                cur = nxt;
-            }
-            if (nslots > 0) {
-                const long long nsum = (long long)nt * nslots;
-                finalize_sums_kernel<<<blocks_for(nsum, 256), 256, 0, d.stream>>>((const double *)d.partial.p, dp.grid, nsum, dp.d_f64);
-                CK(cudaGetLastError());
-                plan->launches++;
-            }
-            CK(cudaEventRecord(d.ev[2], d.stream));
-            return 0;
+    // ---- phase 2: resampling rounds (src/TWA.jl:186-209), interleaved over the devices: every device's failure count
+    //      is requested before any stream is waited for, so device i+1 is not idle while device i resamples ----
+    {
+        std::vector<int> cur(ndev, 0);
+        std::vector<char> active(ndev, 0);
+        std::vector<unsigned> cnt(ndev, 0);
+        std::vector<std::vector<FailRec>> recs(ndev);
+        bool any_active = false;
+        for (int di = 0; di < ndev; ++di) active[di] = plan->devs[di].n > 0, any_active |= (bool)active[di];
+        auto on = [&](int di, auto &&f) -> int {   // run f on device di, folding its status into rc
+            if (rc || !active[di]) return 0;
+            if (cudaSetDevice(ctx->devs[di].device) != cudaSuccess) return rc = set_err(DTWA_ERR_CUDA, "cudaSetDevice failed");
+            return rc = f(ctx->devs[di], plan->devs[di], args[di]);
         };
-        rc = body();
+        for (int round = 1; !rc && any_active; ++round) {
+            for (int di = 0; di < ndev; ++di)
+                on(di, [&](DevCtx &d, DevPlan &, EnsArgs &) -> int {
+                    CK(cudaMemcpyAsync(&cnt[di], d.fail[cur[di]].p, sizeof(unsigned), cudaMemcpyDeviceToHost, d.stream));
+                    return 0;
+                });
+            for (int di = 0; di < ndev; ++di)
+                on(di, [&](DevCtx &d, DevPlan &dp, EnsArgs &A) -> int {
+                    CK(cudaStreamSynchronize(d.stream));
+                    if (!A.fail_out) {
+                        active[di] = 0;
+                        if (!tolerate_errors) {  // the reference rethrows the first error (src/TWA.jl:199-201)
+                            unsigned long long nfail = 0;
+                            CK(cudaMemcpyAsync(&nfail, dp.d_u64 + CNT_FAILED, sizeof(nfail), cudaMemcpyDeviceToHost, d.stream));
+                            CK(cudaStreamSynchronize(d.stream));
+                            if (nfail)
+                                return set_err(DTWA_ERR_BOUNDS, "a trajectory left the domain (DomainError in the reference) and tolerate_errors=false");
+                        }
+                        return 0;
+                    }
+                    if (cnt[di] == 0) {
+                        active[di] = 0;
+                        return 0;
+                    }
+                    if (cnt[di] > fail_caps[di]) cnt[di] = fail_caps[di];
+                    if (round > 100)
+                        return set_err(DTWA_ERR_TOO_MANY_FAILURES, "Too many errors: a trajectory failed in more than 100 consecutive resampling rounds");
+                    recs[di].resize(cnt[di]);
+                    CK(cudaMemcpyAsync(recs[di].data(), (unsigned char *)d.fail[cur[di]].p + 16, sizeof(FailRec) * cnt[di], cudaMemcpyDeviceToHost, d.stream));
+                    return 0;
+                });
+            any_active = false;
+            for (int di = 0; di < ndev; ++di)
+                on(di, [&](DevCtx &d, DevPlan &, EnsArgs &A) -> int {
+                    CK(cudaStreamSynchronize(d.stream));   // (also: the previous round's upload from recs[di] has completed)
+                    // sort the failure list by trajectory index so that the round is reproducible
+                    std::sort(recs[di].begin(), recs[di].end(), [](const FailRec &x, const FailRec &y) { return x.idx < y.idx; });
+                    const int c = cur[di], nxt = c ^ 1;
+                    CK(cudaMemcpyAsync((unsigned char *)d.fail[c].p + 16, recs[di].data(), sizeof(FailRec) * cnt[di], cudaMemcpyHostToDevice, d.stream));
+                    CK(cudaMemsetAsync(d.fail[nxt].p, 0, 16, d.stream));
+                    A.redo = (const FailRec *)((unsigned char *)d.fail[c].p + 16);
+                    A.fail_count = (unsigned *)d.fail[nxt].p;
+                    A.fail_out = (FailRec *)((unsigned char *)d.fail[nxt].p + 16);
+                    A.N = cnt[di];
+                    A.attempt = (uint32_t)round;
+                    LaunchShape ls = shapes[di];
+                    ls.grid = (int)std::max(1ll, std::min<long long>((cnt[di] + ls.block - 1) / ls.block, shapes[di].grid));
+                    TRY(launch_ens(d, kern, A, ls));
+                    plan->launches++;
+                    plan->rounds = std::max(plan->rounds, round);
+                    cur[di] = nxt;
+                    any_active = true;
+                    return 0;
+                });
+        }
+        // fixed-order merge of the per-CTA partial sums
+        for (int di = 0; di < ndev && !rc; ++di) {
+            DevCtx &d = ctx->devs[di];
+            DevPlan &dp = plan->devs[di];
+            if (dp.n == 0) continue;
+            auto body = [&]() -> int {
+                CK(cudaSetDevice(d.device));
+                if (nslots > 0) {
+                    const long long nsum = (long long)nt * nslots;
+                    finalize_sums_kernel<<<blocks_for(nsum, 256), 256, 0, d.stream>>>((const double *)d.partial.p, dp.grid, nsum, dp.d_f64);
+                    CK(cudaGetLastError());
+                    plan->launches++;
+                }
+                CK(cudaEventRecord(d.ev[2], d.stream));
+                return 0;
+            };
+            rc = body();
+        }
     }
 
     // ---- phase 3: one grouped all-reduce over NVLink when the context spans several devices ----

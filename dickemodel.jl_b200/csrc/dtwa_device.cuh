@@ -419,13 +419,29 @@ __device__ __forceinline__ void rk8_step(const SysPar &p, double (&y)[Sys<SYS>::
 }
 
 // ------------------------------------------------------------------------------------------------
-// embedded adaptive pairs.  Controller = SciPy's RungeKutta._step_impl (the oracle restates the same):
-// RMS error norm with scale = tol + max(|y|,|ynew|) tol, factor in [0.2, 10], safety 0.9, plus the
-// reference's solver contract (src/ClassicalSystems.jl:138): dtmin with force_dtmin, out-of-domain
-// trial steps rejected with a shrink of 0.2, maxiters.
-// err^(-1/(q+1)) for the step-size factor.  Only the *size* of the next step depends on it (never the
-// accept/reject decision, taken on err in full double precision), so single precision through the
-// MUFU units is ample; the result is clamped to [0.2, 10] by the caller.
+// embedded adaptive pairs.  Error norm: RMS of err_i / (tol + max(|y_i|,|ynew_i|) tol) (OrdinaryDiffEq's
+// calculate_residuals + ODE_DEFAULT_NORM and SciPy's rk.py agree on it), DOP853 with Hairer's 5/3 combination.
+// Two step-size controllers (CtrlPar::kind):
+//   DTWA_CTRL_ODE   the reference's: OrdinaryDiffEq v5 (solve() in src/ClassicalSystems.jl:138).  PI controller
+//                   q = EEst^beta1 / qold^beta2 / gamma clamped to [1/qmax, 1/qmin]; accept when EEst <= 1, then
+//                   dt <- dt/q and qold <- max(EEst, qoldinit); after a rejection dt <- dt / min(1/qmin, EEst^beta1/gamma);
+//                   after an isoutofdomain rejection dt <- dt qmin.  Gains: the algorithm's defaults in alg_utils.jl
+//                   (DP5 0.17/0.04, DP8 1/8 / 0 with qmin 1/3 qmax 6, order-8 generic = TsitPap8/Vern8 7/80 / 1/20) or the
+//                   caller's (solve's beta1/beta2/qmin/qmax/gamma/qoldinit keywords).
+//   DTWA_CTRL_SCIPY SciPy's RungeKutta._step_impl: factor = 0.9 err^(-1/(q+1)) in [0.2, 10], no growth right after a
+//                   rejection, accept when err < 1 -- what tests/golden/scipy_pairs.json pins the tableaux with.
+// Both under the reference's solver contract: dtmin with force_dtmin, isoutofdomain, maxiters.
+// The powers only size the next step (never the accept/reject decision, taken on err in full double precision), so
+// single precision through the MUFU units is ample.
+struct CtrlPar {
+    int32_t kind;
+    float beta1, nbeta2;           // q = EEst^beta1 * qold^nbeta2   (nbeta2 = -beta2)
+    float inv_gamma, q_lo, q_hi;   // q / gamma clamped to [q_lo, q_hi] = [1/qmax, 1/qmin]
+    float qoldinit;
+    float pad;
+    double dom_shrink;             // step factor after an isoutofdomain rejection: qmin (SciPy mode: 0.2)
+};
+
 template <int ERR_ORDER>
 __device__ __forceinline__ double step_factor_pow(double err)
 {
@@ -442,12 +458,15 @@ struct Adaptive {
     static constexpr int ERR_ORDER = (ALG == DTWA_ALG_DP5) ? 4 : 7;
     double t, habs;
     double k0[NV];
+    float qold, q11;   // PI controller memory
     bool rejected;
 
-    __device__ __forceinline__ void init(const SysPar &p, const double (&y)[NV], double tend, double tol)
+    __device__ __forceinline__ void init(const SysPar &p, const double (&y)[NV], double tend, double tol, const CtrlPar &c)
     {
         t = 0.0;
         rejected = false;
+        qold = c.qoldinit;
+        q11 = 1.0f;
         RHS(y, k0);
         // Hairer's starting step (scipy common.select_initial_step, direction +1, max_step inf)
         double sc[NV], a[NV];
@@ -485,7 +504,7 @@ struct Adaptive {
     // one attempted step towards tstop.  Returns 0 = keep going, 1 = trajectory failed (DOMAIN).
     // `accepted` reports whether y/t advanced.
     __device__ __forceinline__ int attempt(const SysPar &p, double (&y)[NV], double tstop, double tol, double dtmin,
-                                           bool &accepted)
+                                           bool &accepted, const CtrlPar &c)
     {
         accepted = false;
         bool forced = false;
@@ -543,27 +562,58 @@ struct Adaptive {
         const bool bad = state_bad<SYS>(yn) || !(err == err) || isinf(err);
         if (bad) {
             if (forced) return 1;
-            habs = h * 0.2;
+            habs = h * c.dom_shrink;
             rejected = true;
             return 0;
         }
-        if (err < 1.0 || forced) {
-            double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * step_factor_pow<ERR_ORDER>(err));
-            if (rejected) factor = fmin(1.0, factor);
-            double hn = h * factor;
-            if (clipped && hn < habs) hn = habs;
-            habs = hn;
-            t = last ? tstop : t + h;
+        if (c.kind == DTWA_CTRL_SCIPY) {
+            if (err < 1.0 || forced) {
+                double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * step_factor_pow<ERR_ORDER>(err));
+                if (rejected) factor = fmin(1.0, factor);
+                double hn = h * factor;
+                if (clipped && hn < habs) hn = habs;
+                habs = hn;
+                t = last ? tstop : t + h;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                y[i] = yn[i];
-                k0[i] = kn[i];
+                for (int i = 0; i < NV; ++i) {
+                    y[i] = yn[i];
+                    k0[i] = kn[i];
+                }
+                rejected = false;
+                accepted = true;
+            } else {
+                habs = h * fmax(0.2, 0.9 * step_factor_pow<ERR_ORDER>(err));
+                rejected = true;
             }
-            rejected = false;
-            accepted = true;
         } else {
-            habs = h * fmax(0.2, 0.9 * step_factor_pow<ERR_ORDER>(err));
-            rejected = true;
+            float q = c.q_lo;
+            if (err != 0.0) {
+                const float le = __log2f(fminf(fmaxf((float)err, 1e-30f), 1e30f));
+                q11 = exp2f(c.beta1 * le);
+                q = q11 * exp2f(c.nbeta2 * __log2f(qold));
+                q = fmaxf(c.q_lo, fminf(c.q_hi, q * c.inv_gamma));
+            }
+            if (err <= 1.0 || forced) {
+                double hn = h * (double)__frcp_rn(q);
+                if (clipped) {
+                    // a step cut short to land on ts[k] (the reference interpolates there, src/TWA.jl:180) does not feed the
+                    // controller: the un-clipped proposal stands unless the new one is larger
+                    if (hn < habs) hn = habs;
+                } else
+                    qold = fmaxf((float)err, c.qoldinit);
+                habs = hn;
+                t = last ? tstop : t + h;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    y[i] = yn[i];
+                    k0[i] = kn[i];
+                }
+                rejected = false;
+                accepted = true;
+            } else {
+                habs = h * (double)__frcp_rn(fminf(c.q_hi, q11 * c.inv_gamma));
+                rejected = true;
+            }
         }
         return 0;
     }

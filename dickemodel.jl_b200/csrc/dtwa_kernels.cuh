@@ -35,6 +35,7 @@ struct SolverArgs {
     long long maxiters;
     int32_t nt;
     int32_t pad;
+    CtrlPar ctrl;        // step-size controller of the adaptive pairs
 };
 
 template <int ALG>
@@ -59,7 +60,7 @@ struct Traj {
         nrej = 0;
         if (status == ST_OK && state_bad<SYS>(u)) status = ST_BAD_IC;
         if constexpr (!FIXED) {
-            if (status == ST_OK) ad.init(S.par, u, S.tend, S.tol);
+            if (status == ST_OK) ad.init(S.par, u, S.tend, S.tol, S.ctrl);
         }
     }
 
@@ -102,7 +103,7 @@ struct Traj {
                         break;
                     }
                     bool accepted;
-                    const int f = ad.attempt(S.par, u, tstop, S.tol, S.dtmin, accepted);
+                    const int f = ad.attempt(S.par, u, tstop, S.tol, S.dtmin, accepted, S.ctrl);
                     ++iters;
                     if (f) {
                         status = ST_DOMAIN;
@@ -498,7 +499,7 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
                     T.status = ST_MAXITERS;
                 } else {
                     bool accepted;
-                    if (T.ad.attempt(A.S.par, T.u, tstop, A.S.tol, A.S.dtmin, accepted)) T.status = ST_DOMAIN;
+                    if (T.ad.attempt(A.S.par, T.u, tstop, A.S.tol, A.S.dtmin, accepted, A.S.ctrl)) T.status = ST_DOMAIN;
                     if (accepted)
                         ++T.nacc;
                     else if (T.status == ST_OK)
@@ -785,7 +786,7 @@ __global__ void __launch_bounds__(128) integrate_kernel(const SolverArgs S, cons
                         T.status = ST_MAXITERS;
                     } else {
                         bool accepted;
-                        if (T.ad.attempt(S.par, T.u, tstop, S.tol, S.dtmin, accepted))
+                        if (T.ad.attempt(S.par, T.u, tstop, S.tol, S.dtmin, accepted, S.ctrl))
                             T.status = ST_DOMAIN;
                         else if (accepted)
                             ++T.nacc;
@@ -855,7 +856,7 @@ __global__ void __launch_bounds__(128) integrate_fm_kernel(const SolverArgs S, c
                         T.status = ST_MAXITERS;
                     } else {
                         bool accepted;
-                        if (T.ad.attempt(S.par, T.u, tstop, S.tol, S.dtmin, accepted))
+                        if (T.ad.attempt(S.par, T.u, tstop, S.tol, S.dtmin, accepted, S.ctrl))
                             T.status = ST_DOMAIN;
                         else if (accepted)
                             ++T.nacc;
@@ -1015,7 +1016,7 @@ __global__ void __launch_bounds__(128, DTWA_LYAP_MIN_BLOCKS) lyapunov_kernel(con
                     T.status = ST_MAXITERS;
                 } else {
                     bool accepted;
-                    if (T.ad.attempt(S.par, T.u, tstop, S.tol, S.dtmin, accepted))
+                    if (T.ad.attempt(S.par, T.u, tstop, S.tol, S.dtmin, accepted, S.ctrl))
                         T.status = ST_DOMAIN;
                     else if (accepted)
                         ++T.nacc;
@@ -1230,7 +1231,7 @@ __global__ void __launch_bounds__(EVENTS_BLOCK, DTWA_EVENTS_MIN_BLOCKS) events_k
                 if ((long long)(T.nacc + T.nrej) >= S.maxiters) {
                     T.status = ST_MAXITERS;
                     done = true;
-                } else if (T.ad.attempt(S.par, T.u, E.t_end, S.tol, S.dtmin, accepted)) {
+                } else if (T.ad.attempt(S.par, T.u, E.t_end, S.tol, S.dtmin, accepted, S.ctrl)) {
                     T.status = ST_DOMAIN;
                     done = true;
                     accepted = false;

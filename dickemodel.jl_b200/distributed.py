@@ -9,9 +9,22 @@ from __future__ import annotations
 
 
 def shard_bounds(N: int, rank: int, world: int):
-    """contiguous block of rank `rank`: the split of src/TWA.jl:119 (Neff = ceil(N/workers))"""
-    per = -(-int(N) // int(world))
-    return min(N, rank * per), min(N, (rank + 1) * per)
+    """contiguous block [lo, hi) of rank `rank`, balanced: N // world trajectories each, the first N % world ranks
+    one more.  (src/TWA.jl:119-128 hands out ceil(N/workers) per work item and leaves the last ones short or empty;
+    the balanced split covers the same index range with the same samples and never leaves a GPU idle.)"""
+    N, rank, world = int(N), int(rank), int(world)
+    base, extra = divmod(N, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def chunk_plan(N: int, world: int, maxNBatch=None):
+    """(chunk, nchunks) for maxNBatch-bounded launches (src/TWA.jl:119).  Both depend on N and world only, never on the
+    rank: every rank runs the same number of launches -- and therefore the same number of collectives -- even when its own
+    block is shorter or empty (it then launches an empty chunk)."""
+    per_max = -(-int(N) // int(world))
+    chunk = per_max if (maxNBatch is None or maxNBatch == float("inf")) else int(max(1, min(per_max, maxNBatch)))
+    return chunk, -(-per_max // chunk)
 
 
 class _CudaArray:

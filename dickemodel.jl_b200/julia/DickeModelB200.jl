@@ -32,6 +32,14 @@ struct CSolver
     tol::Float64
     dtmin::Float64
     maxiters::Int64
+    controller::Int32
+    reserved::Int32
+    beta1::Float64
+    beta2::Float64
+    qmin::Float64
+    qmax::Float64
+    gamma::Float64
+    qoldinit::Float64
 end
 struct CSampler
     kind::Int32
@@ -85,6 +93,7 @@ end
 
 const SYS_DICKE, SYS_LMG = Int32(0), Int32(1)
 const ALG_RK4, ALG_RK8, ALG_DP5, ALG_DOP853 = Int32(0), Int32(1), Int32(2), Int32(3)
+const CTRL_ODE, CTRL_SCIPY = Int32(0), Int32(1)
 const SAMPLER_HOST_ARRAY, SAMPLER_HW, SAMPLER_SU2, SAMPLER_HWXSU2 = Int32(0), Int32(1), Int32(2), Int32(3)
 const RED_AVERAGE, RED_HIST, RED_SURVIVAL = Int32(0), Int32(1), Int32(2)
 const AXIS_EXPR, AXIS_TIME = Int32(0), Int32(1)
@@ -141,18 +150,39 @@ end
 
 # ---- solver keyword arguments (src/ClassicalSystems.jl:78-88,138) ------------------------------
 # integrator_alg may be an OrdinaryDiffEq algorithm object or a Symbol; only the name is used.
+# The step controller is OrdinaryDiffEq's (DTWA_CTRL_ODE) with the gains of the NAMED algorithm (alg_utils.jl): TsitPap8 /
+# Vern8 (generic order 8: beta1 = 7/80, beta2 = 1/20, qmin 1/5, qmax 10), Tsit5 (7/50, 2/25); DP5 / DP8 use the
+# library's built-in defaults (zeros here).  solve()'s own keywords beta1/beta2/qmin/qmax/gamma/qoldinit are honoured;
+# controller=:scipy selects SciPy's controller (the one the golden step counts pin).
+const warned_substitution = Set{Symbol}()
 function csolver(; tol::Real=1e-12, integrator_alg=:TsitPap8, integate_backwards::Bool=false, dt=nothing,
-                 adaptive=nothing, dtmin=nothing, maxiters=nothing, ignored...)
+                 adaptive=nothing, dtmin=nothing, maxiters=nothing, controller=:ode, beta1=nothing, beta2=nothing,
+                 qmin=nothing, qmax=nothing, gamma=nothing, qoldinit=nothing, ignored...)
     name = Symbol(replace(string(integrator_alg isa Symbol ? integrator_alg : nameof(typeof(integrator_alg))), "()" => ""))
     alg = name in (:DP8, :TsitPap8, :Vern8, :DOP853) ? ALG_DOP853 :
           name in (:DP5, :Tsit5) ? ALG_DP5 :
           name == :RK4 ? ALG_RK4 : name == :RK8 ? ALG_RK8 :
           error("integrator_alg=$name is not available in libdicketwa")
+    if name in (:TsitPap8, :Vern8, :Tsit5) && !(name in warned_substitution)
+        push!(warned_substitution, name)
+        @warn "integrator_alg=$name(): its tableau is not part of libdicketwa; the same-order pair $(alg == ALG_DOP853 ? "DOP853" : "DP5") runs instead, under OrdinaryDiffEq's step controller for $name"
+    end
     if adaptive === false && alg == ALG_DOP853
         alg = ALG_RK8
     end
+    generic = name in (:TsitPap8, :Vern8) ? (7 / 80, 1 / 20, 0.2, 10.0) : name == :Tsit5 ? (7 / 50, 2 / 25, 0.2, 10.0) : (0.0, 0.0, 0.0, 0.0)
+    b1, b2 = generic[1], generic[2]
+    if beta1 !== nothing || beta2 !== nothing
+        d2 = name in (:TsitPap8, :Vern8, :Tsit5) ? generic[2] : alg == ALG_DP5 ? 0.04 : 0.0
+        b2 = beta2 === nothing ? d2 : Float64(beta2)
+        b1 = beta1 !== nothing ? Float64(beta1) : name in (:TsitPap8, :Vern8, :Tsit5) ? generic[1] : alg == ALG_DP5 ? 0.2 - 3b2 / 4 : 0.125 - b2 / 5
+    end
+    scipy = controller in (:scipy, :SciPy, "scipy")
     CSolver(alg, integate_backwards ? 1 : 0, dt === nothing ? 0.0 : Float64(dt), Float64(tol),
-            dtmin === nothing ? 0.0 : Float64(dtmin), maxiters === nothing ? 0 : Int64(maxiters))
+            dtmin === nothing ? 0.0 : Float64(dtmin), maxiters === nothing ? 0 : Int64(maxiters),
+            scipy ? CTRL_SCIPY : CTRL_ODE, 0, scipy ? 0.0 : b1, scipy ? 0.0 : b2,
+            qmin === nothing ? generic[3] : Float64(qmin), qmax === nothing ? generic[4] : Float64(qmax),
+            gamma === nothing ? 0.0 : Float64(gamma), qoldinit === nothing ? 0.0 : Float64(qoldinit))
 end
 
 # ---- integrate (src/ClassicalSystems.jl:78-140) -------------------------------------------------

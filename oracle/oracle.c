@@ -248,7 +248,17 @@ typedef struct {
     int alg;
     double dt, tol, dtmin;
     long maxiters;
+    /* step-size controller of the adaptive pairs.  0 = OrdinaryDiffEq's (the reference's solve(), src/ClassicalSystems.jl:138):
+     * PI controller q = EEst^beta1 / qold^beta2 / gamma clamped to [1/qmax, 1/qmin], accept when EEst <= 1, qold = max(EEst,
+     * qoldinit) after an accepted step, dt/min(1/qmin, EEst^beta1/gamma) after a rejected one, dt*qmin after an
+     * isoutofdomain rejection (OrdinaryDiffEq v5 integrators/controllers + integrator_utils loopheader!/loopfooter!).
+     * 1 = SciPy's (rk.py _step_impl): what tests/golden/scipy_pairs.json pins. */
+    int controller;
+    double beta1, beta2, qmin, qmax, gamma, qoldinit;
 } orc_problem;
+
+#define CTRL_ODE 0
+#define CTRL_SCIPY 1
 
 int orc_solve_one(const orc_problem *pb, const double *u0, const double *ts, int nt, const int *nsub,
                   const double *hsub, orc_out_cb cb, void *user, int *fail_index, long *nacc,
@@ -292,6 +302,7 @@ int orc_solve_one(const orc_problem *pb, const double *u0, const double *ts, int
         int have_f = 0;
         double h_abs = 0;
         int rejected = 0;
+        double qold = pb->qoldinit, q11 = 1.0;
         for (k = 0; k < nt && status == ST_OK; ++k) {
             double tstop = ts[k];
             while (t < tstop) {
@@ -361,28 +372,59 @@ int orc_solve_one(const orc_problem *pb, const double *u0, const double *ts, int
                         status = ST_DOMAIN;
                         break;
                     }
-                    h_abs = h * 0.2; /* isoutofdomain rejection: shrink by qmin */
+                    h_abs = h * (pb->controller == CTRL_SCIPY ? 0.2 : pb->qmin); /* isoutofdomain rejection: shrink by qmin */
                     rejected = 1;
                     rej++;
                     continue;
                 }
-                if (err < 1 || forced) {
-                    double factor = (err == 0) ? 10.0 : fmin(10.0, 0.9 * pow(err, expo));
-                    if (rejected) factor = fmin(1.0, factor);
-                    double hn = h * factor;
-                    if (clipped && hn < h_abs) hn = h_abs;
-                    h_abs = hn;
-                    t = (t + h >= tstop) ? tstop : t + h;
-                    for (int i = 0; i < nv; ++i) {
-                        u[i] = yn[i];
-                        K[0][i] = K[S][i];
+                if (pb->controller == CTRL_SCIPY) {
+                    if (err < 1 || forced) {
+                        double factor = (err == 0) ? 10.0 : fmin(10.0, 0.9 * pow(err, expo));
+                        if (rejected) factor = fmin(1.0, factor);
+                        double hn = h * factor;
+                        if (clipped && hn < h_abs) hn = h_abs;
+                        h_abs = hn;
+                        t = (t + h >= tstop) ? tstop : t + h;
+                        for (int i = 0; i < nv; ++i) {
+                            u[i] = yn[i];
+                            K[0][i] = K[S][i];
+                        }
+                        rejected = 0;
+                        acc++;
+                    } else {
+                        h_abs = h * fmax(0.2, 0.9 * pow(err, expo));
+                        rejected = 1;
+                        rej++;
                     }
-                    rejected = 0;
-                    acc++;
                 } else {
-                    h_abs = h * fmax(0.2, 0.9 * pow(err, expo));
-                    rejected = 1;
-                    rej++;
+                    /* OrdinaryDiffEq: stepsize_controller! / step_accept_controller! / step_reject_controller! */
+                    double q;
+                    if (err == 0)
+                        q = 1.0 / pb->qmax;
+                    else {
+                        q11 = pow(err, pb->beta1);
+                        q = q11 / pow(qold, pb->beta2);
+                        q = fmax(1.0 / pb->qmax, fmin(1.0 / pb->qmin, q / pb->gamma));
+                    }
+                    if (err <= 1 || forced) {
+                        double hn = h / q;
+                        if (clipped) {
+                            /* a step cut short to land on ts[k] (the reference interpolates there instead, src/TWA.jl:180)
+                             * does not feed the controller: the un-clipped proposal stands unless the new one is larger */
+                            if (hn < h_abs) hn = h_abs;
+                        } else
+                            qold = fmax(err, pb->qoldinit);
+                        h_abs = hn;
+                        t = (t + h >= tstop) ? tstop : t + h;
+                        for (int i = 0; i < nv; ++i) {
+                            u[i] = yn[i];
+                            K[0][i] = K[S][i];
+                        }
+                        acc++;
+                    } else {
+                        h_abs = h / fmin(1.0 / pb->qmin, q11 / pb->gamma);
+                        rej++;
+                    }
                 }
             }
             if (status != ST_OK) break;

@@ -40,7 +40,9 @@ def build(force: bool = False) -> None:
 
 class Problem(C.Structure):
     _fields_ = [("kind", C.c_int), ("par", C.c_double * 4), ("backwards", C.c_int), ("alg", C.c_int),
-                ("dt", C.c_double), ("tol", C.c_double), ("dtmin", C.c_double), ("maxiters", C.c_long)]
+                ("dt", C.c_double), ("tol", C.c_double), ("dtmin", C.c_double), ("maxiters", C.c_long),
+                ("controller", C.c_int), ("beta1", C.c_double), ("beta2", C.c_double), ("qmin", C.c_double),
+                ("qmax", C.c_double), ("gamma", C.c_double), ("qoldinit", C.c_double)]
 
 
 class Sampler(C.Structure):
@@ -111,8 +113,41 @@ def varnames(kind):
     return ["Q", "q", "P", "p"] if kind == SYS_DICKE else ["Q", "P"]
 
 
-def make_problem(kind, par, alg=ALG_DOP853, dt=0.0, tol=1e-12, dtmin=None, maxiters=100000, backwards=False):
+CTRL_ODE, CTRL_SCIPY = 0, 1
+# OrdinaryDiffEq v5 alg_utils.jl defaults (beta1, beta2, qmin, qmax); gamma = 9/10, qoldinit = 1e-4 for every explicit pair:
+#   DP5:  beta2 = 4/100, beta1 = 1/5 - 3 beta2/4;  DP8: beta2 = 0, beta1 = 1/8, qmin = 1/3, qmax = 6;
+#   anything else of order p (the reference's default TsitPap8, p = 8): beta2 = 2/(5p), beta1 = 7/(10p), qmin = 1/5, qmax = 10
+ODE_GAINS = {"dp5": (0.2 - 0.03, 0.04, 0.2, 10.0), "dp8": (0.125, 0.0, 1.0 / 3.0, 6.0), "tsitpap8": (7.0 / 80.0, 2.0 / 40.0, 0.2, 10.0),
+             "tsit5": (7.0 / 50.0, 2.0 / 25.0, 0.2, 10.0)}
+_controller_default = [None]   # tests may pin a module-wide default with set_default_controller
+
+
+def set_default_controller(c):
+    _controller_default[0] = c
+
+
+def _controller_fields(p, alg, controller):
+    """controller: None/"ode" (OrdinaryDiffEq gains of the algorithm), "scipy", a key of ODE_GAINS, or (beta1, beta2, qmin, qmax)"""
+    if controller is None:
+        controller = _controller_default[0]
+    p.gamma, p.qoldinit = 0.9, 1e-4
+    if controller == "scipy":
+        p.controller = CTRL_SCIPY
+        p.beta1, p.beta2, p.qmin, p.qmax = 0.0, 0.0, 0.2, 10.0
+        return
+    p.controller = CTRL_ODE
+    if controller is None or controller == "ode":
+        controller = "dp5" if alg == ALG_DP5 else "dp8"
+    if isinstance(controller, str):
+        controller = ODE_GAINS[controller.lower()]
+    p.beta1, p.beta2, p.qmin, p.qmax = (float(x) for x in controller[:4])
+    if len(controller) > 4:
+        p.gamma = float(controller[4])
+
+
+def make_problem(kind, par, alg=ALG_DOP853, dt=0.0, tol=1e-12, dtmin=None, maxiters=100000, backwards=False, controller=None):
     p = Problem()
+    _controller_fields(p, alg, controller)
     p.kind = kind
     for i, v in enumerate(par):
         p.par[i] = float(v)
@@ -163,7 +198,7 @@ def step_table(ts, dt):
 
 
 def integrate(kind, par, u0, ts, alg=ALG_DOP853, dt=0.0, tol=1e-12, dtmin=None, maxiters=100000,
-              backwards=False, fast=False):
+              backwards=False, fast=False, controller=None):
     """Dense restatement of ClassicalSystems.integrate + the per-time callback: returns
     (out[n][nt][nvar], status[n], accepted[n], rejected[n])."""
     nv = nvar(kind)
@@ -174,7 +209,7 @@ def integrate(kind, par, u0, ts, alg=ALG_DOP853, dt=0.0, tol=1e-12, dtmin=None, 
     status = np.empty(n, dtype=np.int32)
     nacc = np.empty(n, dtype=np.int64)
     nrej = np.empty(n, dtype=np.int64)
-    pb = make_problem(kind, par, alg, dt, tol, dtmin, maxiters, backwards)
+    pb = make_problem(kind, par, alg, dt, tol, dtmin, maxiters, backwards, controller)
     rc = lib(fast).orc_integrate(C.byref(pb), _dp(u0), n, _dp(ts), nt, _dp(out),
                                  status.ctypes.data_as(C.POINTER(C.c_int)),
                                  nacc.ctypes.data_as(C.POINTER(C.c_long)),
@@ -477,12 +512,12 @@ def hist_2d(xv, yv, valid, xr, yr, animate):
 
 
 def ensemble(kind, par, sampler, N, ts, values, hists=(), alg=ALG_RK4, dt=2.0 ** -7, tol=1e-12, dtmin=None,
-             maxiters=100000, backwards=False, host_u0=None, workers=1, tolerate_errors=True, fast=False):
+             maxiters=100000, backwards=False, host_u0=None, workers=1, tolerate_errors=True, fast=False, controller=None):
     """The C driver (src/TWA.jl:100-224 restated).  values: list of (kind, a, c); hists: list of
     (value_index, start, stop, len).  Returns a dict of raw sums / counts / counters."""
     ts = np.ascontiguousarray(ts, dtype=np.float64)
     nt = len(ts)
-    pb = make_problem(kind, par, alg, dt, tol, dtmin, maxiters, backwards)
+    pb = make_problem(kind, par, alg, dt, tol, dtmin, maxiters, backwards, controller)
     vals = (Value * len(values))(*[Value(k, a, c) for (k, a, c) in values])
     hs = (Hist * max(1, len(hists)))(*[Hist(v, a, b, n) for (v, a, b, n) in hists])
     sums = np.zeros((nt, len(values)))

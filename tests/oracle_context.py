@@ -12,9 +12,15 @@ class OracleContext:
         return dict(alg=int(sol.alg), dt=float(sol.dt), tol=float(sol.tol), dtmin=float(sol.dtmin) or None,
                     maxiters=int(sol.maxiters) or 10 ** 7, backwards=bool(sol.backwards), fast=True), int(sys.kind), par
 
+    @staticmethod
+    def _ctrl(sol):
+        if int(sol.controller) == 1:
+            return "scipy"
+        return (sol.beta1, sol.beta2, sol.qmin or (0.2 if int(sol.alg) == O.ALG_DP5 else 1 / 3), sol.qmax or (10.0 if int(sol.alg) == O.ALG_DP5 else 6.0)) if sol.beta1 > 0 else "ode"
+
     def integrate(self, sys, sol, u0, ts):
         kw, kind, par = self._pb(sys, sol)
-        out, status, nacc, nrej = O.integrate(kind, par, u0, ts, **kw)
+        out, status, nacc, nrej = O.integrate(kind, par, u0, ts, controller=self._ctrl(sol), **kw)
         return out, status, nacc + nrej
 
     def integrate_fm(self, sys, sol, u0, ts, fm0=None):

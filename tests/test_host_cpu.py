@@ -19,15 +19,111 @@ def test_library_exports_every_declared_symbol(pkg):
     assert declared == set(pkg._lib.EXPORTS), declared ^ set(pkg._lib.EXPORTS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.dtwa_version() == 100
+    assert L.dtwa_version() == 200
+
+
+# ---- struct layouts: include/dicketwa.h is the contract; the ctypes mirror and the Julia shim must both agree with it ----
+_C_TYPES = {"int32_t": (4, 4), "uint32_t": (4, 4), "int64_t": (8, 8), "uint64_t": (8, 8), "double": (8, 8), "int": (4, 4)}
+
+
+def _parse_header_structs():
+    """{name: [(field, offset, size)], sizeof} for every `typedef struct {...} name;` of the header, natural alignment"""
+    header = open(os.path.join(ROOT, "include", "dicketwa.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    structs = {}
+    for body, name in re.findall(r"typedef\s+struct\s*\w*\s*\{(.*?)\}\s*(\w+)\s*;", header, flags=re.S):
+        off, fields, maxal = 0, [], 1
+        for decl in [d.strip() for d in body.split(";") if d.strip()]:
+            m = re.match(r"^(?:const\s+)?(\w+)\s*((?:\*\s*(?:const\s*)?)*)\s*([\w, \[\]]+)$", decl)
+            assert m, decl
+            base, ptr, names = m.group(1), m.group(2), m.group(3)
+            for nm in [x.strip() for x in names.split(",")]:
+                arr = re.match(r"(\w+)\[(\d+)\]", nm)
+                cnt = int(arr.group(2)) if arr else 1
+                nm = arr.group(1) if arr else nm
+                if "*" in ptr:
+                    sz, al = 8, 8
+                elif base in _C_TYPES:
+                    sz, al = _C_TYPES[base]
+                else:
+                    sz, al = structs[base]["size"], structs[base]["align"]
+                off = (off + al - 1) // al * al
+                fields.append((nm, off, sz * cnt))
+                off += sz * cnt
+                maxal = max(maxal, al)
+        structs[name] = {"fields": fields, "size": (off + maxal - 1) // maxal * maxal, "align": maxal}
+    return structs
+
+
+_JL_TYPES = {"Int32": (4, 4), "UInt32": (4, 4), "Cint": (4, 4), "Int64": (8, 8), "UInt64": (8, 8), "Float64": (8, 8), "Cdouble": (8, 8),
+             "Cstring": (8, 8)}
+
+
+def _parse_julia_structs():
+    src = open(os.path.join(ROOT, "dickemodel.jl_b200", "julia", "DickeModelB200.jl")).read()
+    structs = {}
+    for name, body in re.findall(r"^(?:mutable )?struct (C\w+)\s*;?(.*?)\bend$", src, flags=re.S | re.M):
+        if name not in {j for _, _, j in _PAIRS}:
+            continue
+        off, fields, maxal = 0, [], 1
+        for nm, ty in re.findall(r"(\w+)::([\w{},]+)", body):
+            t = re.match(r"NTuple\{(\d+),(\w+)\}", ty)
+            if t:
+                sz, al = _JL_TYPES[t.group(2)]
+                sz *= int(t.group(1))
+            elif ty.startswith("Ptr{"):
+                sz, al = 8, 8
+            elif ty in _JL_TYPES:
+                sz, al = _JL_TYPES[ty]
+            else:
+                sz, al = structs[ty]["size"], structs[ty]["align"]
+            off = (off + al - 1) // al * al
+            fields.append((nm, off, sz))
+            off += sz
+            maxal = max(maxal, al)
+        structs[name] = {"fields": fields, "size": (off + maxal - 1) // maxal * maxal, "align": maxal}
+    return structs
+
+
+_PAIRS = [("dtwa_system", "System", "CSystem"), ("dtwa_solver", "Solver", "CSolver"), ("dtwa_sampler", "Sampler", "CSampler"),
+          ("dtwa_range", "Range", "CRange"), ("dtwa_reducer", "Reducer", "CReducer"), ("dtwa_reducer_out", "ReducerOut", "CReducerOut"),
+          ("dtwa_result", "Result", "CResult"), ("dtwa_event", "Event", "CEvent")]
 
 
 def test_struct_layouts_match_the_header(pkg):
+    """field names, offsets and sizes of the ctypes mirror, parsed against include/dicketwa.h"""
     lib = pkg._lib
-    assert ctypes.sizeof(lib.System) == 40 and ctypes.sizeof(lib.Solver) == 40
-    assert ctypes.sizeof(lib.Sampler) == 72 and ctypes.sizeof(lib.Range) == 24
-    assert ctypes.sizeof(lib.Reducer) == 96 and ctypes.sizeof(lib.ReducerOut) == 32
-    assert ctypes.sizeof(lib.Result) == 88
+    H = _parse_header_structs()
+    assert H["dtwa_solver"]["size"] == 96 and H["dtwa_system"]["size"] == 40 and H["dtwa_result"]["size"] == 88
+    for cname, pyname, _ in _PAIRS:
+        S = getattr(lib, pyname)
+        got = [(n, getattr(S, n).offset, getattr(S, n).size) for n, _ in S._fields_]
+        assert got == H[cname]["fields"], (cname, got, H[cname]["fields"])
+        assert ctypes.sizeof(S) == H[cname]["size"], cname
+
+
+def test_julia_shim_struct_layouts_match_the_header():
+    """Julia cannot run here: at least keep the `struct` blocks of julia/DickeModelB200.jl in step with the header
+    (same field names, offsets, sizes), and the positional constructor calls with the field counts"""
+    H, J = _parse_header_structs(), _parse_julia_structs()
+    for cname, _, jname in _PAIRS:
+        assert jname in J, jname
+        assert J[jname]["fields"] == H[cname]["fields"], (cname, J[jname]["fields"], H[cname]["fields"])
+        assert J[jname]["size"] == H[cname]["size"], cname
+    src = open(os.path.join(ROOT, "dickemodel.jl_b200", "julia", "DickeModelB200.jl")).read()
+    call = src[src.index("    CSolver(alg,"):]
+    call = call[:call.index("\nend")]
+    depth, nargs = 0, 1
+    for ch in call[call.index("(") + 1:]:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            if depth == 0:
+                break
+            depth -= 1
+        elif ch == "," and depth == 0:
+            nargs += 1
+    assert nargs == len(J["CSolver"]["fields"]), nargs
 
 
 def test_no_cpu_fallback(pkg):
@@ -254,7 +350,18 @@ def test_sharded_ensemble_world_size_2_gloo(tmp_path, pkg):
     assert r.returncode == 0, r.stderr[-2000:]
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
     assert '"ok": true' in line and '"total": 600' in line
-    assert pkg.distributed.shard_bounds(10, 0, 4) == (0, 3) and pkg.distributed.shard_bounds(10, 3, 4) == (9, 10)
+    sb, cp = pkg.distributed.shard_bounds, pkg.distributed.chunk_plan
+    assert [sb(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]        # balanced, contiguous, complete
+    assert [sb(3, r, 8) for r in range(8)] == [(0, 1), (1, 2), (2, 3)] + [(3, 3)] * 5   # more ranks than trajectories: empty blocks
+    for N, world, mb in ((100, 8, 5), (9, 4, math.inf), (25, 8, 2), (1, 8, math.inf), (10 ** 7, 3, 10 ** 6)):
+        chunk, nchunks = cp(N, world, mb)
+        per_rank = []
+        for r in range(world):       # what monte_carlo_integrate launches on rank r
+            lo, hi = sb(N, r, world)
+            ns = [max(0, min(chunk, hi - min(hi, lo + c * chunk))) for c in range(nchunks)]
+            assert sum(ns) == hi - lo and len(ns) == nchunks      # same number of launches (= collectives) on every rank
+            per_rank.append(ns)
+        assert sum(map(sum, per_rank)) == N and chunk <= (mb if mb != math.inf else N)
 
 
 def test_quantum_dicke_system_delegates_to_the_classical_one(pkg):
