@@ -6,9 +6,10 @@
 
 Workload (BASELINE.json configs[1]): Dicke w = w0 = 1, gamma = 2 gamma_c = 1,
 j = 100, coherent state of the normal-phase ground state x0 = [0,0,0,0] (the quench), 10^7
-trajectories PER GPU, ts = 0:0.05:100 (2001 output times), fixed-step RK4 with dt = 2^-7 (7 equal
-sub-steps per output interval => 14000 steps per trajectory), observable Weyl.Jz(j)/j averaged at
-every output time.  One bench "step" = one whole ensemble.
+trajectories PER GPU, ts = 0:0.05:100 (2001 output times), fixed-step RK4 with dt <= 2^-7: the library
+steps exactly onto every output time, so an output interval of 0.05 takes 7 equal sub-steps of 0.05/7
+(14000 RK4 steps per trajectory; SURVEY 8d-2 counts 12800 for a step of exactly 2^-7), observable
+Weyl.Jz(j)/j averaged at every output time.  One bench "step" = one whole ensemble.
 
   value     device-resident leg: initial conditions are drawn inside the kernel (Philox), timed with
             CUDA events on the stream the kernels run on, all K steps in one bracket.
@@ -44,7 +45,7 @@ WORK = {"system": "dicke", "par": [1.0, 1.0, 1.0], "j": 100, "center": [0.0, 0.0
 
 def workload_name(n_per_gpu):
     return (f"configs[1]: Dicke TWA quench w=w0=1 g=2gc j=100, coherent state x0=0, {n_per_gpu:.0e} trajectories/GPU, "
-            f"ts=0:0.05:100 (nt=2001), RK4 dt=2^-7, <Jz>/j")
+            f"ts=0:0.05:100 (nt=2001), RK4 with 7 sub-steps of 0.05/7 per output interval (dt <= 2^-7; 14000 steps/trajectory), <Jz>/j")
 
 
 def clocks_sampler_start(path):
@@ -161,6 +162,8 @@ def main():
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--extras-scale", type=float, default=1.0, help="scale the ensemble sizes of the extras (quick checks)")
     args = ap.parse_args()
     args.n_traj = int(args.n_traj)
     claim_stdout()
@@ -177,16 +180,21 @@ def main():
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")   # host-side waits (a rank parked in an NCCL barrier keeps its GPU spinning)
     TWA, CD = pkg.TWA, pkg.ClassicalDicke
     stream = torch.cuda.current_stream()
     ctx = pkg.Context([local], stream=stream.cuda_stream)
     pkg.set_default_context(ctx)
     if args.block or args.ctas_per_sm:
         ctx.set_launch(args.block, args.ctas_per_sm)
-    if world > 1:
-        pkg.set_distributed(rank, world, pkg.distributed.torch_allreduce(local))
+    allreduce = pkg.distributed.torch_allreduce(local) if world > 1 else None
+
+    def distributed_mode(on=True):
+        pkg.set_distributed(rank if on else 0, world if on else 1, allreduce if on else None)
+    distributed_mode(True)
 
     system = CD.ClassicalDickeSystem(w0=WORK["par"][0], w=WORK["par"][1], g=WORK["par"][2])
     j = WORK["j"]
@@ -201,8 +209,38 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
+    def allmax(vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def gather(val):
+        t = torch.tensor([float(val)], dtype=torch.float64, device="cuda")
+        if world == 1:
+            return [float(val)]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(x[0]) for x in out]
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        """fn() bracketed by barrier + synchronize on both sides, CUDA events on the library's stream; max over ranks (ms)"""
+        barrier()
+        e0.record(stream)
+        out = fn()
+        e1.record(stream)
+        barrier()
+        return out, allmax([e0.elapsed_time(e1)])[0]
+
     # ---- roofline denominator: K0 DFMA chains ----
-    peak_tflops, _ = ctx.fp64_peak()
+    peak_tflops, k0_ms = ctx.fp64_peak()
 
     # ---- device-resident leg ----
     W = TWA.coherent_Wigner_HWxSU2(WORK["center"], j=j, seed=WORK["seed"])
@@ -219,7 +257,6 @@ def main():
     clk_path = os.path.join(ROOT, "gpurun_out", f"clocks_rank{rank}.csv")
     os.makedirs(os.path.dirname(clk_path), exist_ok=True)
     sampler = clocks_sampler_start(clk_path) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     steps_done, kernel_ms, launches, last = 0, 0.0, 0, None
     for _ in range(args.steps):
@@ -233,10 +270,7 @@ def main():
     if sampler:
         sampler.terminate()
         sampler.wait()
-    t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, kernel_ms = float(t[0]), float(t[1])
+    elapsed_ms, kernel_ms = allmax([elapsed_ms, kernel_ms])
     value = steps_done / (elapsed_ms * 1e-3)
     per_gpu_kernel_steps = steps_done / world                       # steps one GPU's kernels processed
     kern_rate = per_gpu_kernel_steps / (kernel_ms * 1e-3)           # per-GPU steps/s inside the ensemble kernel
@@ -264,31 +298,29 @@ def main():
             out = TWA.average(system, observable=jz, N=N_total, ts=ts, distribution=D, **solver)
             return out, dict(TWA.last_info)
 
-        for _ in range(max(1, args.warmup - 2)):
+        for _ in range(max(1, min(args.warmup, 3))):
             step_e2e()
         barrier()
         e0.record(stream)
         st, e2e_out = 0, None
-        n_e2e = max(1, min(args.steps, 3))
+        n_e2e = max(1, args.steps)
         for _ in range(n_e2e):
             e2e_out, info = step_e2e()
             st += info["steps_accepted"]
         e1.record(stream)
         barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": st / (float(t[0]) * 1e-3), "unit": "trajectory-steps/s",
+        e2e_ms = allmax([e0.elapsed_time(e1)])[0]
+        e2e = {"value": st / (e2e_ms * 1e-3), "unit": "trajectory-steps/s",
                "h2d_bytes_per_step": int(n_loc * 4 * 8 * world + len(ts) * 8 * world), "d2h_bytes_per_step": int(len(ts) * 8 * world + len(ts) * 8 * world),
-               "steps": n_e2e, "note": "TWA.average with distribution=samples_from_array(pinned host u0[N][4]); H2D of the initial conditions and D2H of the per-time sums inside the timed region"}
+               "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e,
+               "note": "TWA.average with distribution=samples_from_array(pinned host u0[N][4]); H2D of the initial conditions and D2H of the per-time sums inside the timed region"}
         # same samples, same kernel: the two legs must agree to rounding
         e2e["max_abs_diff_vs_device_leg"] = float(np.max(np.abs(e2e_out - last))) if world == 1 else None
-        del host
+        del host, D, host_np
 
     # ---- CPU baseline (rank 0, N = 1 only): the restated reference CPU path on a bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import oracle as O
         threads = host_threads()
         tsn = np.asarray(ts)
         cpu_reference(threads, threads, tsn)
@@ -316,43 +348,168 @@ def main():
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
             traffic_src = tj.get("source")
 
-    # ---- not the headline: the adaptive path (BASELINE.json configs[3]) on one GPU, for the record ----
-    extras = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    # ==== extras: the other BASELINE.json configs, at EVERY world size (every rank takes part) ====
+    extras = {}
+    scale = args.extras_scale
+    Bpt = CD.Point(system, Q=1, P=1, p=0, ϵ=0.5)      # the docs' chaotic point (state B of SURVEY 8d)
+    hist_check = {}
+
+    def hist_chain(N, W_):
+        """SURVEY 8d-3 / docs/src/TWAExamples.md:75-83,101-117: Jz/j-vs-t and q-vs-t histograms over the same trajectories"""
+        tsh = TWA.jrange(0, 0.05, 40)
+        mk = lambda **k: TWA.mcs_for_distributions(system, N=N, distribution=W_, ts=tsh, **k)   # noqa: E731
+        m = TWA.monte_carlo_integrate(system, TWA.mcs_chain(mk(x="t", y=jz, ys=TWA.jrange(-1.1, 0.01, 1.1)), mk(y="t", x="q", xs=TWA.jrange(-4.3, 0.02, 4.3))),
+                                      integrator_alg="RK4", dt=WORK["dt"])
+        return [np.rint(np.asarray(x) * N).astype(np.uint64) for x in m], dict(TWA.last_info)   # back to the integer counts
+
+    def leg(name, fn):
+        """never lose the headline over an extra; an exception is recorded (it would be raised on every rank alike)"""
         try:
-            Bpt = CD.Point(system, Q=1, P=1, p=0, ϵ=0.5)
-            tsa = TWA.jrange(0, 1, 1000)
-            extras = {}
-            for alg in ("DP8", "DP5"):
-                for n_ad in (20000, 1000000):   # (the small call warms the specialisation up)
-                    Wa = TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=1)
-                    TWA.average(system, observable=jz, N=n_ad, ts=tsa, distribution=Wa, integrator_alg=alg, tol=1e-8)
-                ia = TWA.last_info
-                st_ad = ia["steps_accepted"] + ia["steps_rejected"]
-                extras["adaptive_" + alg.lower()] = {
-                    "workload": "configs[3]: chaotic state, tol=1e-8, ts=0:1:1000, 1e6 trajectories (one GPU's share of 8e6)",
-                    "attempted_steps_per_s": st_ad / (ia["kernel_ms"] * 1e-3), "kernel_ms": ia["kernel_ms"],
-                    "lane_efficiency": st_ad / max(1, ia["lane_steps"]), "rejected_fraction": ia["steps_rejected"] / max(1, st_ad),
-                    "specialised": ia["jit"]}
+            fn()
+        except Exception as e:   # noqa: BLE001
+            extras[name] = {"error": repr(e)}
+
+    def leg_hist():
+        n_per = max(1024, int(1.25e8 * scale))
+        Nh = n_per * world
+        hist_chain(max(1024, Nh // 64), TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=WORK["seed"]))   # warm-up (and run-time specialisation)
+        (counts, ih), wall_ms = timed(lambda: hist_chain(Nh, TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=WORK["seed"])))
+        kms = gather(ih["kernel_ms"])
+        # integer bit-exactness across the GPU count: the same index range [0, Nc), sharded over all ranks + all-reduce,
+        # against ONE rank integrating all of it (world = 1: against two half-ranges run one after the other and added)
+        Nc = max(2048, int((1 << 22) * min(1.0, scale)))
+        dist_counts, _ = hist_chain(Nc, TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=WORK["seed"]))
+        hist_check["Nc"], hist_check["counts"] = Nc, dist_counts
+        equal = None
+        if rank == 0:
+            distributed_mode(False)
+            try:
+                if world > 1:
+                    one, _ = hist_chain(Nc, TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=WORK["seed"]))
+                else:
+                    Wa = TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=WORK["seed"])
+                    h1, _ = hist_chain(Nc // 2, Wa)                    # indices [0, Nc/2)
+                    h2, _ = hist_chain(Nc - Nc // 2, Wa)               # indices [Nc/2, Nc): the distribution's offset advanced
+                    one = [x + y for x, y in zip(h1, h2)]
+                equal = bool(all(np.array_equal(x, y) for x, y in zip(one, dist_counts)))
+            finally:
+                distributed_mode(True)
+        host_barrier()
+        att = ih["steps_accepted"] + ih["steps_rejected"]
+        extras["config2_histograms"] = {
+            "workload": f"configs[2]: mcs_chain of Jz/j-vs-t (221 bins) and q-vs-t (431 bins) histograms, state B, ts=0:0.05:40 (nt=801), RK4 dt<=2^-7, "
+                        f"{n_per:.3g} trajectories/GPU (weak scaling; 1e9 at 8 GPUs)",
+            "trajectories_total": Nh, "steps_per_s": att / (max(kms) * 1e-3), "steps_per_s_wall": att / (wall_ms * 1e-3),
+            "kernel_ms_max": max(kms), "kernel_ms_min": min(kms), "wall_ms": wall_ms, "n_failed": ih["n_failed"], "resample_rounds": ih["resample_rounds"],
+            "histogram_mass": [float(c.sum()) / (Nh * 801) for c in counts],
+            "allreduce_bytes": int(8 * (801 * 221 + 801 * 431 + 801 + 8)),
+            "counts_check": {"trajectories": Nc, "bit_equal": equal,
+                             "against": "one rank integrating the whole index range" if world > 1 else "two half index ranges run one after the other and added"}}
+
+    def leg_adaptive():
+        tsa = TWA.jrange(0, 1, 1000)
+        Na = max(world * 32, int(8e6 * scale))      # FIXED total: strong scaling
+        for alg, label in (("TsitPap8", "adaptive_default_pi"), ("DP8", "adaptive_dp8"), ("DP5", "adaptive_dp5")):
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                TWA.average(system, observable=jz, N=max(world * 32, Na // 64), ts=tsa, distribution=TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=1),
+                            integrator_alg=alg, tol=1e-8)     # warm-up (and run-time specialisation)
+                _, wall_ms = timed(lambda: TWA.average(system, observable=jz, N=Na, ts=tsa, distribution=TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=1),
+                                                       integrator_alg=alg, tol=1e-8))
+            ia = dict(TWA.last_info)
+            kms = gather(ia["kernel_ms"])
+            att = ia["steps_accepted"] + ia["steps_rejected"]
+            one_gpu_rate = None
+            extras[label] = {
+                "workload": f"configs[3]: chaotic state B, tol=1e-8, ts=0:1:1000, N={Na:.3g} trajectories in total (strong scaling), integrator_alg={alg}",
+                "algorithm_run": ia.get("algorithm"), "controller": ia.get("controller"), "controller_gains": ia.get("controller_gains"),
+                "attempted_steps": att, "attempted_steps_per_s": att / (max(kms) * 1e-3), "attempted_steps_per_s_wall": att / (wall_ms * 1e-3),
+                "accepted_steps_per_s": ia["steps_accepted"] / (max(kms) * 1e-3),
+                "lane_efficiency": att / max(1, ia["lane_steps"]), "rejected_fraction": ia["steps_rejected"] / max(1, att),
+                "kernel_ms_per_rank": kms, "kernel_ms_max": max(kms), "kernel_ms_min": min(kms), "limiting_rank": int(np.argmax(kms)),
+                "imbalance_max_over_mean": max(kms) / (sum(kms) / len(kms)), "wall_ms": wall_ms,
+                "flops_per_attempt": {"DOP853": 876, "DP5": 366}.get(ia.get("algorithm")), "specialised": ia["jit"],
+                "roofline_frac_of_k0": (att / world / (max(kms) * 1e-3)) * {"DOP853": 876, "DP5": 366}.get(ia.get("algorithm"), 0) / (peak_tflops * 1e12),
+                "n_failed": ia["n_failed"], "n_unfinished": ia["n_unfinished"]}
+            del one_gpu_rate
+
+    def leg_general():
+        """the headline workload away from the unit-parameter specialisation (w = g = 1 saves 8 of 96 FP64 instructions/step)"""
+        sysg = CD.ClassicalDickeSystem(w0=1.0, w=0.8, g=0.66)
+        Wg = TWA.coherent_Wigner_HWxSU2(WORK["center"], j=j, seed=WORK["seed"])
+        TWA.average(sysg, observable=jz, N=max(world * 1024, N_total // 64), ts=ts, distribution=Wg, **solver)
+        Wg.offset = 0
+        _, wall_ms = timed(lambda: TWA.average(sysg, observable=jz, N=N_total, ts=ts, distribution=Wg, **solver))
+        ig = dict(TWA.last_info)
+        km = max(gather(ig["kernel_ms"]))
+        extras["general_parameters"] = {"workload": "the headline workload at w0=1, w=0.8, g=0.66: no unit-parameter specialisation (96 FP64 instr/step)",
+                                        "steps_per_s": ig["steps_accepted"] / (km * 1e-3), "steps_per_s_wall": ig["steps_accepted"] / (wall_ms * 1e-3),
+                                        "kernel_ms": km, "specialised": ig["jit"]}
+
+    def leg_inproc():
+        """the in-process N-device context (dtwa_create(ndev = world) + ncclCommInitAll + grouped ncclAllReduce: what the Julia
+        shim uses), driven by rank 0 alone while the other ranks wait on the host"""
+        if world == 1:
+            return
+        res = None
+        if rank == 0:
+            distributed_mode(False)
+            try:
+                ctxN = pkg.Context(list(range(world)))
+                pkg.set_default_context(ctxN)
+                Wn = TWA.coherent_Wigner_HWxSU2(WORK["center"], j=j, seed=WORK["seed"])
+                TWA.average(system, observable=jz, N=max(world * 1024, N_total // 64), ts=ts, distribution=Wn, **solver)
+                Wn.offset = 0
+                t0 = time.perf_counter()
+                outN = TWA.average(system, observable=jz, N=N_total, ts=ts, distribution=Wn, **solver)
+                wall = time.perf_counter() - t0
+                iN = dict(TWA.last_info)
+                cN, _ = hist_chain(hist_check["Nc"], TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=WORK["seed"]))
+                res = {"nranks": world, "steps_per_s": iN["steps_accepted"] / (iN["kernel_ms"] * 1e-3), "steps_per_s_wall": iN["steps_accepted"] / wall,
+                       "kernel_ms": iN["kernel_ms"], "max_abs_diff_vs_torchrun_leg": float(np.max(np.abs(outN - last))),
+                       "hist_counts_bit_equal_to_torchrun": bool(all(np.array_equal(x, y) for x, y in zip(cN, hist_check["counts"]))),
+                       "note": "dtwa_create(ndev) context in ONE process (rank 0): contiguous index blocks, one grouped ncclAllReduce of the arenas"}
+                ctxN.close()
+            finally:
+                pkg.set_default_context(ctx)
+                distributed_mode(True)
+        host_barrier()
+        if res:
+            extras["inproc_ctx"] = res
+
+    if not args.no_extras:
+        leg("config2_histograms", leg_hist)
+        leg("adaptive", leg_adaptive)
+        leg("general_parameters", leg_general)
+        leg("inproc_ctx", leg_inproc)
+
+    # ---- one GPU only, for the record: configs[0] next to the CPU port, and small instances of SURVEY 8f ranks 2-4 ----
+    if rank == 0 and world == 1 and not args.no_cpu and not args.no_extras:
+        try:
             # BASELINE.json configs[0] (the CPU-runnable case): N = 1e4, adaptive 8th order at the reference's default
             # tol = 1e-12, GPU next to the oracle port on all host cores, same Philox samples
             from oracle import oracle as O
+            import warnings
             ts0 = TWA.jrange(0, WORK["t_step"], WORK["t_end"])
-            for _ in range(2):
-                W0 = TWA.coherent_Wigner_HWxSU2(WORK["center"], j=j, seed=WORK["seed"])
-                t0 = time.perf_counter()
-                g0 = TWA.average(system, observable=jz, N=10000, ts=ts0, distribution=W0)
-                wall0 = time.perf_counter() - t0
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                for _ in range(2):
+                    W0 = TWA.coherent_Wigner_HWxSU2(WORK["center"], j=j, seed=WORK["seed"])
+                    t0 = time.perf_counter()
+                    g0 = TWA.average(system, observable=jz, N=10000, ts=ts0, distribution=W0)
+                    wall0 = time.perf_counter() - t0
             i0 = dict(TWA.last_info)
             sp0 = O.make_sampler(O.SAMPLER_HWXSU2, WORK["center"], 1.0 / j, seed=WORK["seed"])
             cj = float(np.sqrt(j * (j + 1)))
             thr = host_threads()
             t0 = time.perf_counter()
             r0 = O.ensemble(O.SYS_DICKE, WORK["par"], sp0, 10000, np.asarray(ts0), values=[(2, 0, cj)], alg=O.ALG_DOP853, tol=1e-12,
-                            workers=thr, fast=True)
+                            workers=thr, fast=True, controller="tsitpap8")
             cpu0 = time.perf_counter() - t0
             extras["config0_default_adaptive"] = {
-                "workload": "configs[0]: N=1e4, ts=0:0.05:100, DOP853 tol=1e-12 (TsitPap8 is not available offline)",
+                "workload": "configs[0]: N=1e4, ts=0:0.05:100, the reference default integrator_alg=TsitPap8() at tol=1e-12 -> DOP853 tableau under "
+                            "OrdinaryDiffEq's controller for TsitPap8 (the tableau itself is not available offline)",
                 "gpu_wall_s": wall0, "gpu_kernel_ms": i0["kernel_ms"], "gpu_attempted_steps": i0["steps_accepted"] + i0["steps_rejected"],
                 "cpu_port_s": cpu0, "cpu_cores": thr, "cpu_attempted_steps": r0["steps_accepted"] + r0["steps_rejected"],
                 "max_abs_diff_mean_jz": float(np.max(np.abs(r0["sums"][:, 0] / j / 10000 - g0)))}
@@ -385,30 +542,38 @@ def main():
                                                   "nodes_per_s": ish["nodes"] / (ish["kernel_ms"] * 1e-3),
                                                   "volume_over_closed_form": float(np.nansum(mat[..., 0]) * 1e-4 / CD.energy_shell_volume(system, -0.5))}
         except Exception as e:   # never lose the headline line over the extras
-            extras = dict(extras or {}, error=repr(e))
+            extras["error_single_gpu_extras"] = repr(e)
 
     if rank == 0:
         if not (abs(float(last[0]) + 1.0) < 0.02 and steps_done == args.steps * N_total * 14000):
             raise SystemExit(f"bench self-check failed: <Jz>/j(t=0) = {float(last[0])}, steps counted {steps_done} "
                              f"(expected {args.steps * N_total * 14000}): the per-rank arenas were not merged")
+        nominal_tflops = 148 * 64 * 2 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
         line = {
             "metric": "FP64 trajectory-steps/s", "value": value, "unit": "trajectory-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.n_traj), "trajectories_total": N_total, "steps_per_trajectory": 14000,
                        "cache": "no input tensors (Philox sampling is fused into the kernel); a 256 MiB buffer is written before every step to flush the 126 MB L2",
-                       "block_threads": args.block or 256, "integrator": "RK4", "sampler": "coherent_Wigner_HWxSU2, Philox4x32-10"},
+                       "block_threads": args.block or 256, "integrator": "RK4", "sampler": "coherent_Wigner_HWxSU2, Philox4x32-10",
+                       "reference_arm_note": "the CPU arms (cpu_baseline, --impl reference) integrate a bounded SAMPLE of this ensemble per step "
+                                             "(same workload, fewer trajectories): the metric is a rate"},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / peak_tflops, "traffic": traffic, "traffic_source": traffic_src,
+                         "frac": achieved_tflops / peak_tflops, "frac_nominal": achieved_tflops / nominal_tflops, "peak_nominal": nominal_tflops,
+                         "k0_ms": k0_ms, "k0_flops": peak_tflops * 1e12 * k0_ms * 1e-3,
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "flops_per_step": FLOPS_PER_STEP["dicke_rk4"],
-                         "peak_source": "K0 DFMA-chain micro-benchmark run in this process (dtwa_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; nominal 37.2 TFLOP/s at 1965 MHz",
+                         "peak_source": "K0 DFMA-chain micro-benchmark run in this process (dtwa_fp64_peak: k0_flops in k0_ms, best of 5); MEASURED_PEAKS.json has "
+                                        "no FP64 entry; peak_nominal = 148 SM x 64 DFMA/clk x 2 x sm_max_mhz",
                          "kernel": "dtwa_jit_ensemble (NVRTC specialisation of ensemble_kernel<DICKE,RK4> for this reducer set)", "kernel_ms_per_step": kernel_ms / args.steps,
                          "kernel_steps_per_s_per_gpu": kern_rate,
-                         "fp64_pipe_frac_est": kern_rate * FP64_INSTR_PER_STEP["dicke_rk4"] / (peak_tflops * 1e12 / 2.0),
-                         "note": "frac is ALGORITHMIC flops (136/step) over the measured DFMA peak; fp64_pipe_frac_est counts the 88 FP64-pipe instructions/step of the SASS hot loop (w = g = 1 specialisation), each of which occupies one DFMA issue slot"},
+                         "fp64_pipe_frac_est": kern_rate * FP64_INSTR_PER_STEP["dicke_rk4"] / (nominal_tflops * 1e12 / 2.0),
+                         "note": "frac is ALGORITHMIC flops (136/step) over the measured DFMA peak, frac_nominal over the nominal one; fp64_pipe_frac_est counts the 88 "
+                                 "FP64-pipe instructions/step of the SASS hot loop (w = g = 1 specialisation; 96 in general: extras.general_parameters), each of "
+                                 "which occupies one DFMA issue slot, over the nominal issue rate"},
             "cpu_baseline": cpu,
             "extras": extras,
             "result_check": {"mean_jz_t0": float(last[0]), "mean_jz_t5": float(last[100]), "mean_jz_t100": float(last[-1])},

@@ -163,6 +163,42 @@ def test_resampling_of_failed_trajectories(ctx, mods, O):
     assert np.abs(info["n_valid"].astype(np.int64) - ref["n_valid"].astype(np.int64)).max() <= max(3, 0.03 * ref["n_failed"])
 
 
+def test_resampling_with_known_failing_indices(ctx, mods, O):
+    """Deterministic twin of the test above: LMG (polynomial field, no singular passages) sampled from a planar Gaussian so
+    broad (hbar = 0.5 around Q = 1.5) that many draws fall outside the disk Q^2 + P^2 < 4.  Those -- and only those -- fail
+    (the reference's integrate raises "out of bounds", src/ClassicalSystems.jl:100-102, and monte_carlo_integrate redraws,
+    src/TWA.jl:186-209), so the failing indices, the number of rounds and the final ensemble follow from the samples alone."""
+    TWA, _, CL, _ = mods
+    system = CL.ClassicalLMGSystem(Ω=1, ξ=-1)
+    N, hbar, seed = 6000, 0.5, 31
+    ts = np.array([0.0, 0.5, 1.0, 1.5])
+    W = TWA.coherent_Wigner_HW(q0=1.5, p0=0.0, ħ=hbar, seed=seed)
+    got = TWA.average(system, observable=["Q", "P"], N=N, ts=ts, distribution=W, integrator_alg="RK4", dt=2.0 ** -6)
+    info = dict(TWA.last_info)
+    # replay the rounds on the host from the library's own sampler hook (dtwa_sample with the attempt counter)
+    final = np.full((N, 2), np.nan)
+    pending, n_failed, rounds = np.arange(N), 0, 0
+    for attempt in range(50):
+        u = ctx.sample(TWA.coherent_Wigner_HW(q0=1.5, p0=0.0, ħ=hbar, seed=seed)._c_sampler(), N, attempt)
+        ok = 4 - u[pending, 1] ** 2 - u[pending, 0] ** 2 > 0
+        final[pending[ok]] = u[pending[ok]]
+        n_failed += int((~ok).sum())
+        pending = pending[~ok]
+        if len(pending) == 0:
+            break
+        rounds += 1
+    assert n_failed > 0.2 * N and rounds >= 3                      # the test does exercise several rounds
+    assert info["n_failed"] == n_failed and info["resample_rounds"] == rounds and info["n_unfinished"] == 0
+    assert (info["n_valid"] == N).all()                              # a redraw at k = 0 contributes at every time, exactly once
+    traj, st, _, _ = O.integrate(O.SYS_LMG, [1.0, -1.0], final, ts, alg=O.ALG_RK4, dt=2.0 ** -6)
+    assert (st == 0).all()
+    assert np.abs(got - traj.mean(axis=0)).max() < 1e-11
+    # and the oracle's own driver replays the same rounds
+    ref = O.ensemble(O.SYS_LMG, [1.0, -1.0], O.make_sampler(O.SAMPLER_HW, [1.5, 0.0], hbar, seed=seed), N, ts, values=[(0, 0, 0.0), (0, 1, 0.0)],
+                     alg=O.ALG_RK4, dt=2.0 ** -6)
+    assert ref["n_failed"] == n_failed and np.abs(ref["sums"] / N - got).max() < 1e-11
+
+
 def test_lmg_variance_example(ctx, mods, O):
     """docs/src/ClassicalLMGExamples.md:22-38"""
     TWA, _, CL, _ = mods

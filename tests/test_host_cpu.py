@@ -364,6 +364,74 @@ def test_sharded_ensemble_world_size_2_gloo(tmp_path, pkg):
         assert sum(map(sum, per_rank)) == N and chunk <= (mb if mb != math.inf else N)
 
 
+CHUNK_WORKER = r'''
+import json, os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["DTWA_ROOT"])
+import __graft_entry__ as graft
+pkg = graft.load_package()
+from dickemodel_jl_b200 import TWA, ClassicalDicke as CD
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+
+
+class StubContext:
+    """stands in for _lib.Context.ensemble: `sums[0][0]` = trajectories of this launch, then the caller's all-reduce"""
+    calls = []
+
+    def ensemble(self, csys, sol, smp, n, ts, reducers, tolerate_errors=True, allreduce=None):
+        StubContext.calls.append((int(smp.offset), int(n)))
+        a = np.zeros((len(ts), 1))
+        a[:, 0] = n
+        if allreduce is not None:
+            allreduce([a])
+        info = {"n_valid": np.zeros(len(ts), dtype=np.uint64), "n_failed": 0, "n_unfinished": 0, "steps_accepted": n, "steps_rejected": 0,
+                "lane_steps": n, "resample_rounds": 0, "launches": 1 if n else 0, "jit": 0, "kernel_ms": 0.0, "total_ms": 0.0}
+        return [a], info
+
+
+pkg.set_default_context(StubContext())
+pkg.set_distributed(rank, world, lambda arrays: pkg.distributed.reduce_host_arrays(arrays))
+system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+out = {}
+for N, mb in ((7, 2), (100, 5), (2, float("inf")), (9, float("inf")), (25, 3)):
+    StubContext.calls.clear()
+    W = TWA.coherent_Wigner_HWxSU2([0, 0, 0, 0], j=10, seed=5)
+    res = TWA.average(system, observable="Q", N=N, ts=[0.0, 1.0], distribution=W, integrator_alg="RK4", dt=0.1, maxNBatch=mb)
+    # every rank made the same number of launches (collectives); the all-reduced total covers N exactly once
+    out[f"{N},{mb}"] = [len(StubContext.calls), float(res[0] * N), sorted(StubContext.calls)]
+print(json.dumps({"rank": rank, "out": out}), flush=True)
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_uneven_shards_and_maxNBatch_issue_the_same_collectives_on_every_rank(tmp_path, pkg):
+    """ADVICE r1: N not divisible by the world size, more ranks than trajectories, and maxNBatch chunks must not leave a rank
+    with fewer all-reduces than the others (NCCL would hang).  3 gloo ranks drive TWA.monte_carlo_integrate over a stub context."""
+    script = tmp_path / "chunk_worker.py"
+    script.write_text(CHUNK_WORKER)
+    env = dict(os.environ, DTWA_ROOT=ROOT, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3", "--master-addr", "127.0.0.1",
+                        "--master-port", "29617", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    import json
+    rows = sorted((json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")), key=lambda x: x["rank"])
+    assert len(rows) == 3
+    for key in rows[0]["out"]:
+        N = int(key.split(",")[0])
+        launches = {row["out"][key][0] for row in rows}
+        assert len(launches) == 1, (key, launches)                        # same collective count on every rank
+        assert all(abs(row["out"][key][1] - N) < 1e-9 for row in rows)    # all-reduced total = N on every rank
+        covered = sorted((o, n) for row in rows for o, n in row["out"][key][2] if n > 0)
+        pos = 0
+        for o, n in covered:                                              # blocks tile [0, N) without gap or overlap
+            assert o == pos, (key, covered)
+            pos += n
+        assert pos == N
+
+
 def test_quantum_dicke_system_delegates_to_the_classical_one(pkg):
     """src/DickeBCE.jl:51-72: the carrier every classical function accepts"""
     from dickemodel_jl_b200 import ClassicalDicke as CD, DickeBCE

@@ -25,6 +25,10 @@ ap.add_argument("--mode", default="", choices=["", "hist2d", "animate", "varianc
 ap.add_argument("--state", default="A", choices=["A", "B"])
 ap.add_argument("--tol", type=float, default=1e-8)
 ap.add_argument("--jit", type=int, default=2)
+ap.add_argument("--controller", default=None, help="ode (default) | scipy")
+ap.add_argument("--gains", default="", help="beta1,beta2[,qmin,qmax[,gamma]] for the OrdinaryDiffEq controller")
+ap.add_argument("--w", type=float, default=1.0)
+ap.add_argument("--g", type=float, default=1.0)
 a = ap.parse_args()
 pkg = graft.load_package()
 TWA, CD = pkg.TWA, pkg.ClassicalDicke
@@ -32,13 +36,20 @@ ctx = pkg.default_context()
 ctx.set_jit(a.jit)
 if a.block or a.ctas_per_sm:
     ctx.set_launch(a.block, a.ctas_per_sm)
-system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+system = CD.ClassicalDickeSystem(w0=1, w=a.w, g=a.g)
 j = 100
 center = [0, 0, 0, 0] if a.state == "A" else [1.0, 0.31783724519578205, 1.0, 0.0]
 ts = TWA.jrange(0, a.tstep, a.tend)
 jz = TWA.Weyl.Jz(j) / j
 ap_dt = {"RK4": 2.0 ** -7, "RK8": 0.05}
 kw = dict(integrator_alg=a.alg, dt=ap_dt[a.alg]) if a.alg in ap_dt else dict(integrator_alg=a.alg, tol=a.tol)
+if a.alg not in ap_dt:
+    if a.controller:
+        kw["controller"] = a.controller
+    if a.gains:
+        kw.update(zip(("beta1", "beta2", "qmin", "qmax", "gamma"), (float(x) for x in a.gains.split(","))))
+import warnings
+warnings.simplefilter("ignore")
 for rep in range(a.reps):
     W = TWA.coherent_Wigner_HWxSU2(center, j=j, seed=20261019)
     qs, ps = TWA.jrange(-4.3, 0.02, 4.3), TWA.jrange(-2.4, 0.02, 2.4)
@@ -61,4 +72,5 @@ for rep in range(a.reps):
     i = TWA.last_info
     steps = i["steps_accepted"] + i["steps_rejected"]
     print(f"rep {rep}: {steps} steps in {i['kernel_ms']:.3f} ms kernel = {steps / i['kernel_ms'] / 1e6:.2f} Gsteps/s; "
-          f"lane efficiency {steps / max(1, i['lane_steps']):.3f}; failed {i['n_failed']}; launches {i['launches']}; jit {i['jit']}")
+          f"lane efficiency {steps / max(1, i['lane_steps']):.3f}; rejected {i['steps_rejected'] / max(1, steps):.4f}; failed {i['n_failed']}; "
+          f"launches {i['launches']}; jit {i['jit']}; alg {i.get('algorithm')} ctrl {i.get('controller')} {i.get('controller_gains')}", flush=True)
