@@ -88,14 +88,34 @@ def _as_linrange(r, what):
 
 # ------------------------------------------------------------------------------------------------
 class PhaseSpaceDistribution:
-    """src/TWA.jl:22-26: (probability_density, sample, ħ).  Also carries the POD sampler the
-    kernels use.  Samples come from Philox4x32-10 keyed by `seed`; every draw advances `offset`, so
-    consecutive ensembles use fresh trajectories, like consecutive rand() calls in the reference."""
+    """src/TWA.jl:22-26: (probability_density, sample, ħ).
 
-    def __init__(self, kind, center, ħ, seed, u0=None):
+    `PhaseSpaceDistribution(probability_density, sample, ħ)` -- the reference's own constructor -- builds a USER-DEFINED
+    distribution: `sample()` returns one phase-space point (it is called N times on the host and the points go to the
+    GPU as host-supplied initial conditions), `probability_density(u)` is needed only by survival_probability and must be
+    traceable into an expression (arithmetic and the functions of dickemodel_jl_b200.symbolic), because it is evaluated
+    on the GPU along every trajectory.  Trajectories of a user-defined sampler that fail are not re-drawn on the device
+    (the library cannot call back into Python): they are reported in TWA.last_info["n_unfinished"].
+
+    The coherent_Wigner_* constructors below build the library's own distributions: samples come from Philox4x32-10
+    keyed by `seed` inside the kernel; every draw advances `offset`, so consecutive ensembles use fresh trajectories,
+    like consecutive rand() calls in the reference."""
+
+    def __init__(self, kind, center, ħ, seed=0, u0=None):
+        self.user_sample = self.user_pdf = None
+        if callable(center):   # (probability_density, sample, ħ)
+            self.user_pdf, self.user_sample = kind, center
+            kind, center = _lib.SAMPLER_HOST_ARRAY, [0, 0, 0, 0]
         self.kind, self.center, self.ħ, self.seed = kind, [float(c) for c in center], float(ħ), int(seed)
         self.offset = 0
         self.u0 = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64)
+
+    def draw_host(self, n, nv):
+        """n points of a user-defined sampler as an [n][nvar] array"""
+        u = np.array([np.asarray(self.user_sample(), dtype=np.float64).ravel() for _ in range(int(n))], dtype=np.float64).reshape(int(n), -1)
+        if n and u.shape[1] != nv:
+            raise ValueError(f"the distribution samples {u.shape[1]} variables but the system has {nv}")
+        return np.ascontiguousarray(u.reshape(int(n), nv))
 
     hbar = property(lambda self: self.ħ)
 
@@ -113,11 +133,15 @@ class PhaseSpaceDistribution:
 
     @property
     def nvar(self):
+        if self.user_sample is not None:
+            return None   # known once a point has been drawn
         if self.u0 is not None:
             return self.u0.shape[1]
         return 4 if self.kind == _lib.SAMPLER_COHERENT_HWXSU2 else 2
 
     def sample(self):
+        if self.user_sample is not None:
+            return np.asarray(self.user_sample(), dtype=np.float64)
         if self.u0 is not None:
             u = self.u0[self.offset % len(self.u0)]
             self.offset += 1
@@ -132,6 +156,10 @@ class PhaseSpaceDistribution:
         return u
 
     def probability_density(self, u):
+        if self.user_sample is not None:
+            if self.user_pdf is None:
+                raise ValueError("this distribution was built without a probability density")
+            return float(self.user_pdf(np.asarray(u, dtype=float)))
         if self.u0 is not None:
             raise ValueError("a distribution given by samples has no probability density")
         return float(_lib.default_context().pdf(self._c_sampler(), np.asarray(u, dtype=float))[0])
@@ -313,6 +341,10 @@ def mcs_for_variance(system, *, observable, N, ts=(0.0,), return_average=False, 
 def mcs_for_survival_probability(system, *, N, ts, distribution):
     """src/TWA.jl:652-668"""
     spec = {"kind": _lib.RED_SURVIVAL}
+    if distribution.user_sample is not None:   # user-defined distribution: its density, traced into an expression, is the observable
+        if distribution.user_pdf is None:
+            raise ValueError("survival_probability needs a distribution with a probability density")
+        spec = {"kind": _lib.RED_AVERAGE, "exprs": [_expr_of(system, distribution.user_pdf)]}
     L = len(system.varnames()) / 2
 
     def f_final(res):
@@ -400,7 +432,7 @@ def monte_carlo_integrate(system, mc_system, *, tolerate_errors=True, show_progr
     if N < 1:
         raise ValueError("N must be >= 1")
     nv = len(system.varnames())
-    if dist.nvar != nv:
+    if dist.nvar is not None and dist.nvar != nv:
         raise ValueError(f"the distribution samples {dist.nvar} variables but the system has {nv}")
     sol = ClassicalSystems.solver_from_kargs(kargs)
     csys = system._c_system()
@@ -417,7 +449,10 @@ def monte_carlo_integrate(system, mc_system, *, tolerate_errors=True, show_progr
     for c in range(nchunks):
         pos = min(hi, lo + c * chunk)
         n = max(0, min(chunk, hi - pos))
-        u0 = dist.u0[base + pos: base + pos + n] if (dist.u0 is not None and n > 0) else None
+        if dist.user_sample is not None:      # user-defined sampler: n calls on the host, points handed over as an array
+            u0 = dist.draw_host(n, nv) if n > 0 else None
+        else:
+            u0 = dist.u0[base + pos: base + pos + n] if (dist.u0 is not None and n > 0) else None
         smp = dist._c_sampler(offset=base + pos, u0=u0)
         arrays, info = ctx.ensemble(csys, sol, smp, n, ts, mc_system.f_loop, tolerate_errors=tolerate_errors,
                                     allreduce=dcfg["allreduce"] if world > 1 else None)

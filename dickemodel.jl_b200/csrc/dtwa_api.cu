@@ -1414,6 +1414,25 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
         return set_err(DTWA_ERR_CAPACITY, "reducer set exceeds the VM limits (instructions/constants/ranges/histograms/slots)");
     if (prog.consts.empty()) prog.consts.push_back(0.0);
 
+    // ---- device-memory bound: the count arena (animate: nt x ny x nx u64) must fit next to the other buffers ----
+    for (int di = 0; di < ndev; ++di) {
+        DevCtx &d = ctx->devs[di];
+        CK(cudaSetDevice(d.device));
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const double need = 8.0 * (double)u64_len * 1.125 + 256.0;              // DevBuf::ensure over-allocates by 1/8
+        const double avail = (double)free_b + (double)d.arena_u64.cap - 512.0 * 1024 * 1024;   // keep 512 MiB for everything else
+        if ((size_t)u64_len * 8 > d.arena_u64.cap && need > avail) {
+            char msg[512];
+            std::snprintf(msg, sizeof(msg),
+                          "the histogram counts of this call need %.2f GB of device memory (%lld u64 cells; animate=true keeps one ny x nx "
+                          "matrix per output time) but device %d has %.2f GB free: use fewer output times or coarser bins, or split ts "
+                          "into several calls",
+                          8.0 * (double)u64_len / 1e9, (long long)u64_len, d.device, (double)free_b / 1e9);
+            return set_err(DTWA_ERR_CAPACITY, msg);
+        }
+    }
+
     // ---- which kernel: the interpreter, or a run-time specialisation of it for this reducer set ----
     const void *kern = interpreter_kernel(sys->kind, sol->alg);
     // auto mode: specialise when the estimated work repays ~1 s of NVRTC.  Fixed step: the reducers run N * nt times.

@@ -245,3 +245,26 @@ def test_full_size_properties_config4_share_and_config5(ctx, mods, system):
     assert np.array_equal(v[:, 3], np.ones(v.shape[0]))
     assert np.abs(v[:, 0] - v[0, 0]).max() < 1e-9           # <h> conserved (RK4 at dt = 2^-7 drifts by 1.5e-10 over t = 50)
     assert np.abs(v[:, 1]).max() < 5e-4 and (v[:, 2] > 0).all()          # the cloud stays centred; variance of Q positive
+
+
+@pytest.mark.gpu
+def test_animate_request_that_does_not_fit_is_refused(ctx):
+    """src/TWA.jl:441,480-541 keeps per-time sparse dictionaries and flushes them; the library keeps one dense ny x nx u64
+    matrix per output time on the device, so a request beyond the free device memory is refused up front (no partial
+    allocation, no launch) with DTWA_ERR_CAPACITY and a message that says what to change"""
+    from dickemodel_jl_b200 import TWA, ClassicalDicke as CD
+    import dickemodel_jl_b200 as pkg
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    W = TWA.coherent_Wigner_HWxSU2([0, 0, 0, 0], j=100, seed=1)
+    ts = TWA.jrange(0, 0.05, 40)                                    # 801 times
+    big = dict(x="q", xs=TWA.jrange(-4.3, 0.001, 4.3), y="p", ys=TWA.jrange(-4.3, 0.001, 4.3))   # 8601 x 8601 bins
+    with pytest.raises(pkg.DtwaError, match="device memory") as e:
+        TWA.calculate_distribution(system, N=1000, ts=ts, distribution=W, animate=True, integrator_alg="RK4", dt=2.0 ** -7, **big)
+    assert e.value.code == pkg._lib.ERR_CAPACITY
+    # the same bins without animate are one matrix (592 MB): accepted
+    m = TWA.calculate_distribution(system, N=1000, ts=TWA.jrange(0, 0.5, 1), distribution=W, integrator_alg="RK4", dt=2.0 ** -7, **big)
+    assert m.shape == (8601, 8601) and abs(m.sum() - 3.0) < 1e-9
+    # and the context is still usable after the refusal
+    small = TWA.calculate_distribution(system, N=1000, ts=TWA.jrange(0, 0.5, 1), distribution=W, animate=True, integrator_alg="RK4", dt=2.0 ** -7,
+                                       x="q", xs=TWA.jrange(-4.3, 0.1, 4.3), y="p", ys=TWA.jrange(-4.3, 0.1, 4.3))
+    assert len(small) == 3 and all(abs(mk.sum() - 1.0) < 1e-9 for mk in small)

@@ -299,3 +299,30 @@ def test_multi_device_context_matches_single_device(pkg, mods, O, solver):
     assert np.array_equal(one[1], two[1])
     assert np.abs(one[0] - two[0]).max() < 1e-12
     assert i1["steps_accepted"] == i2["steps_accepted"] and np.array_equal(i1["n_valid"], i2["n_valid"])
+
+
+def test_user_defined_phase_space_distribution(ctx, mods, O):
+    """src/TWA.jl:22-26: a distribution given by user closures.  sample() feeds host-drawn points to the kernel; the traced
+    probability_density is the survival-probability observable (src/TWA.jl:656-665)"""
+    TWA, CD, _, _ = mods
+    from dickemodel_jl_b200 import symbolic as S
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    j, N = 40, 3000
+    hb = 1 / j
+    x0 = np.array(CD.Point(system, Q=1.0, P=0, p=0, ϵ=-0.6))
+    pts = x0 + np.random.default_rng(5).normal(0, np.sqrt(hb / 2), (N, 4))
+    it = iter(pts)
+    pdf = lambda u: S.exp(-((u[0] - x0[0]) ** 2 + (u[1] - x0[1]) ** 2 + (u[2] - x0[2]) ** 2 + (u[3] - x0[3]) ** 2) / hb) / (np.pi * hb) ** 2   # noqa: E731
+    D = TWA.PhaseSpaceDistribution(pdf, lambda: next(it), hb)
+    ts = np.array([0.0, 0.5, 1.0, 2.0])
+    got = TWA.average(system, observable=["Q", "q"], N=N, ts=ts, distribution=D, integrator_alg="RK4", dt=2.0 ** -6)
+    same = TWA.average(system, observable=["Q", "q"], N=N, ts=ts, distribution=TWA.samples_from_array(pts, j=j), integrator_alg="RK4", dt=2.0 ** -6)
+    assert np.array_equal(got, same)                     # the same points, the same kernel
+    it = iter(pts)
+    sp = TWA.survival_probability(system, distribution=D, N=N, ts=ts, integrator_alg="RK4", dt=2.0 ** -6)
+    traj, st, _, _ = O.integrate(O.SYS_DICKE, DPAR, pts, ts, alg=O.ALG_RK4, dt=2.0 ** -6, backwards=True)
+    assert (st == 0).all()
+    w = np.exp(-((traj - x0) ** 2).sum(axis=2) / hb) / (np.pi * hb) ** 2
+    want = w.sum(axis=0) * (2 * np.pi * hb) ** 2 / N
+    assert relerr(sp, want, floor=1e-6).max() < 1e-9
+    assert abs(sp[0] - 1.0) < 0.1                        # (2 pi hbar)^2 E_W[W] = 1 for this Gaussian

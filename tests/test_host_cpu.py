@@ -534,3 +534,21 @@ def test_step_and_eye_protocol_functions(pkg, O):
         g = np.array([(H(np.array(u) + e * d) - H(np.array(u) - e * d)) / (2 * e) for d in np.eye(len(u))])
         ham = np.concatenate([g[n:], -g[:n]]) if kind == O.SYS_DICKE else np.array([g[1], -g[0]])
         assert np.allclose(du, ham, atol=1e-8)
+
+
+def test_user_defined_phase_space_distribution_host_side(pkg):
+    """src/TWA.jl:22-26: PhaseSpaceDistribution(probability_density, sample, ħ) with user closures"""
+    from dickemodel_jl_b200 import TWA, ClassicalDicke as CD, symbolic as S
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    rng = np.random.default_rng(0)
+    D = TWA.PhaseSpaceDistribution(lambda u: S.exp(-(u[0] ** 2 + u[1] ** 2 + u[2] ** 2 + u[3] ** 2) / 0.02) / (math.pi * 0.02) ** 2,
+                                   lambda: rng.normal(0, 0.1, 4), 0.02)
+    assert D.ħ == 0.02 and D.nvar is None and D.sample().shape == (4,)
+    assert math.isclose(D.probability_density([0, 0, 0, 0]), 1 / (math.pi * 0.02) ** 2)
+    assert D.draw_host(5, 4).shape == (5, 4)
+    with pytest.raises(ValueError, match="samples 4 variables"):
+        D.draw_host(2, 2)
+    mc = TWA.mcs_for_survival_probability(system, N=10, ts=[0.0, 1.0], distribution=D)
+    assert mc.f_loop[0]["kind"] == pkg._lib.RED_AVERAGE and mc.f_loop[0]["exprs"][0].startswith("(exp(")   # the traced density is the observable
+    with pytest.raises(ValueError, match="probability density"):
+        TWA.mcs_for_survival_probability(system, N=10, ts=[0.0], distribution=TWA.PhaseSpaceDistribution(None, lambda: np.zeros(4), 0.02))
