@@ -134,6 +134,7 @@ def solver_from_kargs(kargs: dict) -> _lib.Solver:
     dtmin = k.pop("dtmin", None)
     maxiters = k.pop("maxiters", None)
     controller = k.pop("controller", None)
+    chart = k.pop("chart", None)
     gains = {g: k.pop(g, None) for g in ("beta1", "beta2", "qmin", "qmax", "gamma", "qoldinit")}   # solve()'s own keywords
     for ignored in ("save_everystep", "show_progress", "progress", "verbose", "dense"):
         k.pop(ignored, None)
@@ -167,6 +168,12 @@ def solver_from_kargs(kargs: dict) -> _lib.Solver:
     s.tol = tol
     s.dtmin = float(dtmin) if dtmin else 0.0
     s.maxiters = int(maxiters) if maxiters else 0
+    if chart in (None, "qp", "QP", "canonical"):
+        s.chart = _lib.CHART_QP
+    elif chart in ("bloch", "Bloch", "cartesian"):
+        s.chart = _lib.CHART_BLOCH     # opt-in: same equations in (jx,jy,jz,q,p); leaves the reference's step sequence
+    else:
+        raise ValueError(f"chart={chart!r}: use 'qp' (the reference's coordinates, default) or 'bloch'")
     if controller in (None, "ode", "OrdinaryDiffEq", "pi", "PI"):
         s.controller = _lib.CTRL_ODE
         b1, b2, qmin, qmax = alg.gains if alg.gains is not None else (0.0, 0.0, 0.0, 0.0)
@@ -190,7 +197,7 @@ def solver_from_kargs(kargs: dict) -> _lib.Solver:
         raise ValueError(f"controller={controller!r}: use 'ode' (OrdinaryDiffEq's, the default) or 'scipy'")
     last_solver.clear()
     last_solver.update(requested=alg.name, algorithm={_lib.ALG_RK4: "RK4", _lib.ALG_RK8: "RK8", _lib.ALG_DP5: "DP5", _lib.ALG_DOP853: "DOP853"}[code],
-                       substituted=bool(alg.note), controller=None if fixed else ctrl_name,
+                       substituted=bool(alg.note), controller=None if fixed else ctrl_name, chart="bloch" if s.chart == _lib.CHART_BLOCH else "qp",
                        gains=None if (fixed or s.controller != _lib.CTRL_ODE) else effective_gains(s))
     return s
 

@@ -316,7 +316,7 @@ static SysPar make_par(const dtwa_system *sys, int backwards)
         p.a = sg * sys->params[0];
         p.b = sg * sys->params[1];
         p.c = sg * sys->params[2];
-        p.d = 0.0;
+        p.d = 2.0 * p.c;   // (the Bloch chart's 2 g)
     } else {
         const double Om = sg * sys->params[0], xi = sg * sys->params[1];
         p.a = Om;
@@ -345,6 +345,7 @@ static int check_solver(const dtwa_solver *sol, bool fixed_needs_dt = true)
     const bool fixed = sol->alg == DTWA_ALG_RK4 || sol->alg == DTWA_ALG_RK8;
     if (fixed && fixed_needs_dt && !(sol->dt > 0)) return set_err(DTWA_ERR_INVALID, "fixed-step algorithms need dt > 0");
     if (!fixed && !(sol->tol > 0)) return set_err(DTWA_ERR_INVALID, "adaptive algorithms need tol > 0");
+    if (sol->chart != DTWA_CHART_QP && sol->chart != DTWA_CHART_BLOCH) return set_err(DTWA_ERR_INVALID, "unknown chart");
     return 0;
 }
 
@@ -422,26 +423,38 @@ static CtrlPar make_ctrl(const dtwa_solver *sol, bool force_scipy)
 {
     CtrlPar c;
     std::memset(&c, 0, sizeof(c));
+    const bool dp5 = sol->alg == DTWA_ALG_DP5;
     if (force_scipy || sol->controller == DTWA_CTRL_SCIPY) {
         c.kind = DTWA_CTRL_SCIPY;
+        c.b1 = dp5 ? 0.2f : 0.125f;      // 1 / (error estimator order + 1)
+        c.nb2 = 0.0f;
+        c.g = 0.9f;
+        c.fac_max = 10.0f;
+        c.fac_min_acc = 0.0f;
+        c.fac_min_rej = 0.2f;
+        c.post_reject_cap = 1.0f;
+        c.lqoldinit = 0.0f;
+        c.acc_thr = 1.0;
         c.dom_shrink = 0.2;
-        c.qoldinit = 1e-4f;
         return c;
     }
-    const bool dp5 = sol->alg == DTWA_ALG_DP5;
     // gains: beta1 > 0 means the caller sets beta1 AND beta2 (beta2 = 0 is a legitimate choice); otherwise the defaults
     const double beta2 = sol->beta1 > 0 ? std::max(0.0, sol->beta2) : (dp5 ? 0.04 : 0.0);
     const double beta1 = sol->beta1 > 0 ? sol->beta1 : (dp5 ? 0.2 - 3.0 * beta2 / 4.0 : 0.125 - beta2 / 5.0);
     const double qmin = sol->qmin > 0 ? sol->qmin : (dp5 ? 0.2 : 1.0 / 3.0);
     const double qmax = sol->qmax > 0 ? sol->qmax : (dp5 ? 10.0 : 6.0);
     const double gamma = sol->gamma > 0 ? sol->gamma : 0.9;
+    const double qoldinit = sol->qoldinit > 0 ? sol->qoldinit : 1e-4;
     c.kind = DTWA_CTRL_ODE;
-    c.beta1 = (float)beta1;
-    c.nbeta2 = (float)(-beta2);
-    c.inv_gamma = (float)(1.0 / gamma);
-    c.q_lo = (float)(1.0 / qmax);
-    c.q_hi = (float)(1.0 / qmin);
-    c.qoldinit = (float)(sol->qoldinit > 0 ? sol->qoldinit : 1e-4);
+    c.b1 = (float)beta1;
+    c.nb2 = (float)(-beta2);
+    c.g = (float)gamma;
+    c.fac_max = (float)qmax;
+    c.fac_min_acc = (float)qmin;
+    c.fac_min_rej = (float)qmin;
+    c.post_reject_cap = (float)qmax;
+    c.lqoldinit = (float)std::log2(qoldinit);
+    c.acc_thr = std::nextafter(1.0, 2.0);   // EEst <= 1
     c.dom_shrink = qmin;
     return c;
 }
@@ -497,7 +510,19 @@ template <typename F>
 static int by_system(int kind, F &&f)
 {
     if (kind == DTWA_SYS_DICKE) return f(std::integral_constant<int, DTWA_SYS_DICKE>());
+    if (kind == DTWA_SYS_DICKE_BLOCH) return f(std::integral_constant<int, DTWA_SYS_DICKE_BLOCH>());
     return f(std::integral_constant<int, DTWA_SYS_LMG>());
+}
+template <typename F>
+static int by_base_system(int kind, F &&f)   // entry points that only exist in the reference's chart
+{
+    if (kind == DTWA_SYS_DICKE) return f(std::integral_constant<int, DTWA_SYS_DICKE>());
+    return f(std::integral_constant<int, DTWA_SYS_LMG>());
+}
+// the template system the integrating kernels are instantiated for: the caller's system in the chart dtwa_solver.chart names
+static int chart_sys(const dtwa_system *sys, const dtwa_solver *sol)
+{
+    return (sys->kind == DTWA_SYS_DICKE && sol->chart == DTWA_CHART_BLOCH) ? DTWA_SYS_DICKE_BLOCH : sys->kind;
 }
 template <typename F>
 static int by_alg(int alg, F &&f)
@@ -637,6 +662,8 @@ static int make_range(const dtwa_range &r, RangeD &out)
     out.stop = r.stop;
     out.len = r.len;
     out.lenm1 = (double)(r.len - 1);
+    out.c = out.lenm1 / (r.stop - r.start);   // (Inf/NaN for a degenerate range: the fast path then never accepts)
+    out.pad = 0.0;
     return 0;
 }
 
@@ -690,7 +717,9 @@ extern "C" int dtwa_integrate(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_
     CK(cudaMemcpyAsync(d.u0.p, u0, sizeof(double) * n * nv, cudaMemcpyHostToDevice, d.stream));
     const SolverArgs S = make_solver_args(sys, sol, (const StepTab *)meta, (const double *)(meta + tab_b), ts, nt, tab);
     const unsigned grid = blocks_for(n, 128);
-    by_system(sys->kind, [&](auto sk) {
+    if (sol->chart == DTWA_CHART_BLOCH && sys->kind != DTWA_SYS_DICKE)
+        return set_err(DTWA_ERR_INVALID, "chart = DTWA_CHART_BLOCH is defined for the Dicke model (the LMG field is polynomial in (Q,P) already)");
+    by_system(chart_sys(sys, sol), [&](auto sk) {
         return by_alg(sol->alg, [&](auto ak) {
             integrate_kernel<decltype(sk)::value, decltype(ak)::value><<<grid, 128, 0, d.stream>>>(
                 S, (const double *)d.u0.p, n, (double *)d.scratch_a.p, (int32_t *)d.scratch_b.p, (long long *)d.scratch_c.p);
@@ -925,7 +954,7 @@ static int events_solve(dtwa_ctx *ctx, const dtwa_system *sys, const dtwa_solver
     int32_t *d_dir = (int32_t *)d.scratch_b.p, *d_cnt = d_dir + n * cap, *d_st = d_cnt + n;
     double *d_end = (double *)((unsigned char *)d.u0.p + b_u0);
     CK(cudaEventRecord(d.ev[0], d.stream));
-    by_system(sys->kind, [&](auto sk) {
+    by_base_system(sys->kind, [&](auto sk) {
         return by_alg(sol->alg, [&](auto ak) {
             events_kernel<decltype(sk)::value, decltype(ak)::value><<<blocks_for(n, EVENTS_BLOCK), EVENTS_BLOCK, 0, d.stream>>>(
                 S, E, (const double *)d.u0.p, n, d_t, d_u, d_dir, d_cnt, d_end, d_st, (long long *)d.scratch_c.p);
@@ -1212,7 +1241,7 @@ struct LaunchShape {
 static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const EnsArgs &A, long long n, LaunchShape &ls)
 {
     const bool fixed = alg == DTWA_ALG_RK4 || alg == DTWA_ALG_RK8;
-    const int max_threads = alg == DTWA_ALG_RK4 ? ens_launch<DTWA_ALG_RK4>::max_threads : ens_launch<DTWA_ALG_DOP853>::max_threads;
+    const int max_threads = alg == DTWA_ALG_RK4 ? ens_launch<DTWA_ALG_RK4>::max_threads : alg == DTWA_ALG_RK8 ? ens_launch<DTWA_ALG_RK8>::max_threads : 32;
     int block = ctx->block_threads ? ctx->block_threads : 256;
     if (block > max_threads) block = max_threads;
     if (!fixed) block = 32;   // adaptive kernels: one warp per CTA (warp-level sliding flush, see ensemble_body)
@@ -1226,7 +1255,7 @@ static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const 
     size_t wcap = fixed ? 32 : 256, wbudget = 24 * 1024;
     if (const char *e = std::getenv("DTWA_WINDOW")) wcap = (size_t)std::max(1, std::atoi(e));  // tuning experiments
     int window = (int)std::max<size_t>(1, std::min<size_t>({wcap, (size_t)A.S.nt, wbudget / per_out}));
-    size_t smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, rows, window);
+    size_t smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, rows, window, A.stage2d_bins);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
@@ -1246,7 +1275,7 @@ static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const 
             d.packed_total = 0;   // (packed events of an earlier dtwa_integrate_events_packed lived here)
             ls.ring = (double *)d.ring.p;
         }
-        smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, rows, window);
+        smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, rows, window, A.stage2d_bins);
     }
     ls.window = window;
     ls.block = block;
@@ -1327,8 +1356,9 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
     std::vector<RedLayout> reds(nred);
     int nslots = 0;
     int64_t u64_len = CNT_N + nt;
-    int stage_bins = 0;
+    int stage_bins = 0, stage2d_bins = 0;
     const int STAGE_BUDGET_BINS = 8192;  // x2 buffers x4 B = 64 KB of shared memory at most
+    const int STAGE2D_BUDGET_BINS = 8192;  // 32 KB per CTA: keeps four CTAs of the fixed-step kernels on an SM
     auto vars = varnames_of(sys->kind);
     try {
         ExprCompiler comp(vars);
@@ -1394,6 +1424,12 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
                     H.n0 = (int32_t)rx.len;
                     H.n1 = (int32_t)ry.len;
                     H.tstride = R.animate ? rx.len * ry.len : 0;
+                    // a matrix shared by all times that fits the budget is accumulated in a per-CTA shared-memory tile
+                    // (fixed-step kernels; the adaptive ones run one warp per CTA, 12-16 CTAs per SM: no room)
+                    if (fixed && !R.animate && stage2d_bins + rx.len * ry.len <= STAGE2D_BUDGET_BINS && std::getenv("DTWA_NO_STAGE2D") == nullptr) {
+                        H.staged_off = stage2d_bins;
+                        stage2d_bins += (int)(rx.len * ry.len);
+                    }
                     L.counts_len = (R.animate ? (int64_t)nt : 1) * rx.len * ry.len;
                 }
                 L.u64_off = u64_len;
@@ -1434,7 +1470,9 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
     }
 
     // ---- which kernel: the interpreter, or a run-time specialisation of it for this reducer set ----
-    const void *kern = interpreter_kernel(sys->kind, sol->alg);
+    if (sol->chart == DTWA_CHART_BLOCH && sys->kind != DTWA_SYS_DICKE)
+        return set_err(DTWA_ERR_INVALID, "chart = DTWA_CHART_BLOCH is defined for the Dicke model (the LMG field is polynomial in (Q,P) already)");
+    const void *kern = interpreter_kernel(chart_sys(sys, sol), sol->alg);
     // auto mode: specialise when the estimated work repays ~1 s of NVRTC.  Fixed step: the reducers run N * nt times.
     // Adaptive: lanes reach their output times out of step, so the reducer code runs (partially masked) in most
     // iterations of the step loop -- count attempted steps instead, ~8 per unit time as a floor.
@@ -1448,7 +1486,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
         cudaKernel_t jk;
         CK(cudaSetDevice(ctx->devs[0].device));
         const int wflag = unit_flags(sys, sol->backwards);
-        if (jit_cache().get_async(sys->kind, sol->alg, wflag, prog, &jk) == 0) {
+        if (jit_cache().get_async(chart_sys(sys, sol), sol->alg, wflag, prog, &jk) == 0) {
             kern = (const void *)jk;
             used_jit = true;
         }
@@ -1458,7 +1496,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
         std::string jerr;
         CK(cudaSetDevice(ctx->devs[0].device));
         const int wflag = unit_flags(sys, sol->backwards);
-        if (jit_cache().get(sys->kind, sol->alg, wflag, prog, &jk, jerr)) {
+        if (jit_cache().get(chart_sys(sys, sol), sol->alg, wflag, prog, &jk, jerr)) {
             // forced specialisation fails loudly; in auto mode the (slower) interpreter kernel runs instead -- still on
             // the GPU -- and the result reports jit = 0 (e.g. libnvrtc is not installed next to the driver)
             if (ctx->jit_mode == 1) return set_err(DTWA_ERR_JIT, jerr);
@@ -1545,6 +1583,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
             A.nrange = (int)ranges.size();
             A.nhist = (int)hists.size();
             A.stage_bins = stage_bins;
+            A.stage2d_bins = stage2d_bins;
             A.redo = nullptr;
             const bool can_redo = tolerate_errors && smp->kind != DTWA_SAMPLER_HOST_ARRAY && smp->kind != DTWA_SAMPLER_DEVICE_ARRAY;
             fail_caps[di] = (unsigned)std::min<long long>(dp.n, 1ll << 22);
@@ -1852,7 +1891,7 @@ extern "C" int dtwa_jit_compile(const dtwa_system *sys, const dtwa_solver *sol, 
         return set_err(DTWA_ERR_EXPR, e.what());
     }
     prog.emit(OP_END);
-    const std::string src = jit_source(sys->kind, sol->alg, unit_flags(sys, sol->backwards), prog);
+    const std::string src = jit_source(chart_sys(sys, sol), sol->alg, unit_flags(sys, sol->backwards), prog);
     if (src_out && src_cap > 0) {
         std::snprintf(src_out, (size_t)src_cap, "%s", src.c_str());
     }

@@ -66,6 +66,7 @@ struct Sys;
 template <>
 struct Sys<DTWA_SYS_DICKE> {
     static constexpr int NV = 4;
+    static constexpr int NVO = 4;                         // phase-space coordinates the samplers / observables see
     static constexpr int QI = 0, PI = 2;
     static constexpr int NVB = 4, GROUP = 1, NORM_N = 4;  // see the variational systems below
     // 18 FP64-pipe instructions + 1 MUFU.  FOLDQ: du[1] is returned as p (the factor w lives in the
@@ -131,6 +132,7 @@ struct Sys<DTWA_SYS_DICKE> {
 template <>
 struct Sys<DTWA_SYS_LMG> {
     static constexpr int NV = 2;
+    static constexpr int NVO = 2;
     static constexpr int QI = 0, PI = 1;
     static constexpr int NVB = 2, GROUP = 1, NORM_N = 2;
     // 7 FP64-pipe instructions
@@ -154,6 +156,80 @@ struct Sys<DTWA_SYS_LMG> {
         return __dsub_rn(__dadd_rn(a, __dmul_rn(xi, b)), Om);
     }
 };
+
+// ------------------------------------------------------------------------------------------------
+// Opt-in chart for the Dicke model (dtwa_solver.chart = DTWA_CHART_BLOCH): the spin as a Cartesian unit vector
+//   jx = Q s/2,  jy = -P s/2,  jz = (Q^2 + P^2)/2 - 1,   s = sqrt(4 - Q^2 - P^2)        (src/TWA.jl:816-826, src/PhaseSpaces.jl:49,63)
+// in which Hamilton's equations of src/ClassicalDicke.jl:11-17 become bilinear (chain rule, h = w0 jz + w (q^2+p^2)/2 + 2 g q jx):
+//   djx = -w0 jy,   djy = w0 jx - 2 g q jz,   djz = 2 g q jy,   dq = w p,   dp = -w q - 2 g jx.
+// No square root, no division, no chart singularity at Q^2 + P^2 -> 4 (where the (Q,P) field grows like 1/s and an adaptive
+// integrator legitimately needs 10^4-10^5 steps of ~dtmin): 8 FP64 instructions per right-hand side instead of 19 + MUFU.
+// The SAME differential equation in other coordinates: exact solutions coincide, numerical ones differ by the truncation
+// error of the method, so this chart leaves the reference's step sequence -- it is never the default.
+// State y = [jx, jy, jz, q, p]; samplers and observables keep seeing (Q, q, P, p) through to_chart / from_chart.
+constexpr int DTWA_SYS_DICKE_BLOCH = 6;
+template <>
+struct Sys<DTWA_SYS_DICKE_BLOCH> {
+    static constexpr int NV = 5;
+    static constexpr int NVO = 4;
+    static constexpr int QI = 0, PI = 1;   // (unused: no chart boundary)
+    static constexpr int NVB = 5, GROUP = 1, NORM_N = 5;
+    // p.a = w0, p.b = w, p.c = g, p.d = 2 g (sign of integate_backwards folded into all of them)
+    __device__ __forceinline__ static void rhs(const SysPar &p, const double (&y)[5], double (&dy)[5])
+    {
+        const double jx = y[0], jy = y[1], jz = y[2], q = y[3], pp = y[4];
+        const double gq2 = __dmul_rn(p.d, q);              // 2 g q
+        dy[0] = __dmul_rn(-p.a, jy);
+        dy[1] = fma(p.a, jx, -__dmul_rn(gq2, jz));
+        dy[2] = __dmul_rn(gq2, jy);
+#if defined(DTWA_W_IS_ONE)
+        dy[3] = pp;
+        dy[4] = fma(-p.d, jx, -q);
+#elif defined(DTWA_W_IS_MINUS_ONE)
+        dy[3] = -pp;
+        dy[4] = fma(-p.d, jx, q);
+#else
+        dy[3] = __dmul_rn(p.b, pp);
+        dy[4] = fma(-p.d, jx, -__dmul_rn(p.b, q));
+#endif
+    }
+};
+
+// phase-space point (the samplers', observables' and callers' coordinates) <-> integration state
+template <int SYS>
+__device__ __forceinline__ void to_chart(const double (&x)[Sys<SYS>::NVO], double (&y)[Sys<SYS>::NV])
+{
+    if constexpr (SYS == DTWA_SYS_DICKE_BLOCH) {
+        const double Q = x[0], P = x[2];
+        const double R = fma(P, P, __dmul_rn(Q, Q));
+        const double hs = __dmul_rn(0.5, sqrt(4.0 - R));   // NaN outside the disk: caught by the finiteness test
+        y[0] = __dmul_rn(Q, hs);
+        y[1] = -__dmul_rn(P, hs);
+        y[2] = fma(0.5, R, -1.0);
+        y[3] = x[1];
+        y[4] = x[3];
+    } else {
+#pragma unroll
+        for (int i = 0; i < Sys<SYS>::NV; ++i) y[i] = x[i];
+    }
+}
+template <int SYS>
+__device__ __forceinline__ void from_chart(const double (&y)[Sys<SYS>::NV], double (&x)[Sys<SYS>::NVO])
+{
+    if constexpr (SYS == DTWA_SYS_DICKE_BLOCH) {
+        // (Q, P) = (jx, -jy) sqrt(2 / (1 - jz)), which gives Q^2 + P^2 = 2 (1 + jz) on the unit sphere
+        const double c = 1.0 - y[2];
+        double is, sq;
+        rsqrt_sqrt_pair(__dmul_rn(0.5, c), is, sq);        // 1 / sqrt((1 - jz)/2)
+        x[0] = __dmul_rn(y[0], is);
+        x[2] = -__dmul_rn(y[1], is);
+        x[1] = y[3];
+        x[3] = y[4];
+    } else {
+#pragma unroll
+        for (int i = 0; i < Sys<SYS>::NV; ++i) x[i] = y[i];
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Variational systems (src/ClassicalSystems.jl:110-128, `get_fundamental_matrix=true`):
@@ -319,6 +395,13 @@ __device__ __forceinline__ bool state_bad(const double (&u)[Sys<SYS>::NV])
         for (int i = 0; i < Sys<SYS>::NV; ++i) nonfinite |= ((__double2hiint(u[i]) & 0x7ff00000) == 0x7ff00000);
         const bool bad = nonfinite || !(r2 > 0.0);
         return (__ballot_sync(mask, bad) & mask) != 0u;
+    } else if constexpr (SYS == DTWA_SYS_DICKE_BLOCH) {
+        // no chart boundary; a state is bad when it is non-finite or sits on the pole jz >= 1 of the (Q,P) chart, where the
+        // observables' coordinates do not exist (4 - Q^2 - P^2 = 2 (1 - jz) <= 0, the reference's out_of_bounds)
+        bool nonfinite = false;
+#pragma unroll
+        for (int i = 0; i < Sys<SYS>::NV; ++i) nonfinite |= ((__double2hiint(u[i]) & 0x7ff00000) == 0x7ff00000);
+        return nonfinite || !(u[2] < 1.0);
     } else {
         const double Q = u[Sys<SYS>::QI], P = u[Sys<SYS>::PI];
         const double r2 = __dsub_rn(__dsub_rn(4.0, __dmul_rn(P, P)), __dmul_rn(Q, Q));
@@ -433,23 +516,34 @@ __device__ __forceinline__ void rk8_step(const SysPar &p, double (&y)[Sys<SYS>::
 // Both under the reference's solver contract: dtmin with force_dtmin, isoutofdomain, maxiters.
 // The powers only size the next step (never the accept/reject decision, taken on err in full double precision), so
 // single precision through the MUFU units is ample.
+// One branch-free rule covers both (lg2/ex2 through the MUFU units, no division, no libm slow paths: the controller is a
+// serial, latency-bound tail of every attempt during which the warp feeds nothing to the FP64 pipe):
+//   le = lg2(err);  accepted step: h *= min(fac_max, max(fac_min_acc, g 2^-(b1 le + nb2 lqold)))   [capped by post_reject_cap
+//   right after a rejection];  rejected step: h *= max(fac_min_rej, g 2^-(b1 le));  accept when err < acc_thr.
+//   ODE:   b1 = beta1, nb2 = -beta2, g = gamma, [fac_min_acc, fac_max] = [qmin, qmax], fac_min_rej = qmin, acc_thr = 1 + ulp,
+//          lqold = lg2(max(EEst, qoldinit)) of the last accepted un-clipped step, post_reject_cap = qmax
+//   SciPy: b1 = 1/(q+1), nb2 = 0, g = 0.9, fac_max = 10, fac_min_acc = 0, fac_min_rej = 0.2, acc_thr = 1, post_reject_cap = 1
 struct CtrlPar {
     int32_t kind;
-    float beta1, nbeta2;           // q = EEst^beta1 * qold^nbeta2   (nbeta2 = -beta2)
-    float inv_gamma, q_lo, q_hi;   // q / gamma clamped to [q_lo, q_hi] = [1/qmax, 1/qmin]
-    float qoldinit;
+    float b1, nb2, g;
+    float fac_max, fac_min_acc, fac_min_rej, post_reject_cap;
+    float lqoldinit;
     float pad;
+    double acc_thr;
     double dom_shrink;             // step factor after an isoutofdomain rejection: qmin (SciPy mode: 0.2)
 };
 
-template <int ERR_ORDER>
-__device__ __forceinline__ double step_factor_pow(double err)
+__device__ __forceinline__ float lg2_approx(float x)
 {
-    const float e = fminf(fmaxf((float)err, 1e-30f), 1e30f);
-    if constexpr (ERR_ORDER == 7)
-        return (double)rsqrtf(sqrtf(sqrtf(e)));   // e^(-1/8)
-    else
-        return (double)exp2f((-1.0f / (ERR_ORDER + 1)) * __log2f(e));
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 template <int SYS, int ALG>
@@ -458,15 +552,14 @@ struct Adaptive {
     static constexpr int ERR_ORDER = (ALG == DTWA_ALG_DP5) ? 4 : 7;
     double t, habs;
     double k0[NV];
-    float qold, q11;   // PI controller memory
+    float lqold;       // PI controller memory: lg2 of the error estimate of the last accepted (un-clipped) step
     bool rejected;
 
     __device__ __forceinline__ void init(const SysPar &p, const double (&y)[NV], double tend, double tol, const CtrlPar &c)
     {
         t = 0.0;
         rejected = false;
-        qold = c.qoldinit;
-        q11 = 1.0f;
+        lqold = c.lqoldinit;
         RHS(y, k0);
         // Hairer's starting step (scipy common.select_initial_step, direction +1, max_step inf)
         double sc[NV], a[NV];
@@ -566,55 +659,31 @@ struct Adaptive {
             rejected = true;
             return 0;
         }
-        if (c.kind == DTWA_CTRL_SCIPY) {
-            if (err < 1.0 || forced) {
-                double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * step_factor_pow<ERR_ORDER>(err));
-                if (rejected) factor = fmin(1.0, factor);
-                double hn = h * factor;
-                if (clipped && hn < habs) hn = habs;
-                habs = hn;
-                t = last ? tstop : t + h;
+        const float le = lg2_approx(fminf(fmaxf((float)err, 1e-30f), 1e30f));
+        const float e_rej = ex2_approx(-c.b1 * le);
+        const float e_acc = ex2_approx(-fmaf(c.b1, le, c.nb2 * lqold));
+        float fac_acc = fminf(c.fac_max, fmaxf(c.fac_min_acc, c.g * e_acc));   // err == 0: e_acc = +inf, clamped to fac_max
+        if (rejected) fac_acc = fminf(fac_acc, c.post_reject_cap);
+        const float fac_rej = fmaxf(c.fac_min_rej, c.g * e_rej);
+        const bool acc = forced || err < c.acc_thr;
+        double hn = h * (double)(acc ? fac_acc : fac_rej);
+        if (acc) {
+            if (clipped) {
+                // a step cut short to land on ts[k] (the reference interpolates there, src/TWA.jl:180) does not feed the
+                // controller: the un-clipped proposal stands unless the new one is larger
+                if (hn < habs) hn = habs;
+            } else
+                lqold = fmaxf(le, c.lqoldinit);
+            t = last ? tstop : t + h;
 #pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    y[i] = yn[i];
-                    k0[i] = kn[i];
-                }
-                rejected = false;
-                accepted = true;
-            } else {
-                habs = h * fmax(0.2, 0.9 * step_factor_pow<ERR_ORDER>(err));
-                rejected = true;
-            }
-        } else {
-            float q = c.q_lo;
-            if (err != 0.0) {
-                const float le = __log2f(fminf(fmaxf((float)err, 1e-30f), 1e30f));
-                q11 = exp2f(c.beta1 * le);
-                q = q11 * exp2f(c.nbeta2 * __log2f(qold));
-                q = fmaxf(c.q_lo, fminf(c.q_hi, q * c.inv_gamma));
-            }
-            if (err <= 1.0 || forced) {
-                double hn = h * (double)__frcp_rn(q);
-                if (clipped) {
-                    // a step cut short to land on ts[k] (the reference interpolates there, src/TWA.jl:180) does not feed the
-                    // controller: the un-clipped proposal stands unless the new one is larger
-                    if (hn < habs) hn = habs;
-                } else
-                    qold = fmaxf((float)err, c.qoldinit);
-                habs = hn;
-                t = last ? tstop : t + h;
-#pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    y[i] = yn[i];
-                    k0[i] = kn[i];
-                }
-                rejected = false;
-                accepted = true;
-            } else {
-                habs = h * (double)__frcp_rn(fminf(c.q_hi, q11 * c.inv_gamma));
-                rejected = true;
+            for (int i = 0; i < NV; ++i) {
+                y[i] = yn[i];
+                k0[i] = kn[i];
             }
         }
+        habs = hn;
+        rejected = !acc;
+        accepted = acc;
         return 0;
     }
 };
@@ -781,14 +850,25 @@ __device__ __forceinline__ double pdf_eval(const SamplerPar &sp, const double (&
 struct RangeD {
     double start, stop, lenm1;
     int64_t len;
+    double c;     // lenm1 / (stop - start), for the fast path
+    double pad;
 };
-__device__ __forceinline__ long long scale_to_index(double v, const RangeD &r)
+// The reference's formula is Int(round((v - start)/(stop - start) * (len - 1) + 1)): a correctly rounded division, a
+// multiplication and an addition, then round-half-even.  A division costs ~12 FP64-pipe instructions and runs for every
+// sample of every histogram, so the index is first computed as rint(fma(v - start, c, 1)) with c = (len-1)/(stop-start):
+// both values lie within a few ulp of the exact real number, hence they round to the same integer unless that number sits
+// within 16 ulp of a rounding boundary k + 1/2 -- only then (probability ~1e-13 len per sample) the reference's own
+// operation sequence decides.  Bit-exact with the un-fused formula by construction (tests: edges, ties, NaN, +-Inf).
+__device__ __forceinline__ int scale_to_index(double v, const RangeD &r)
 {
-    if (v < r.start || r.stop < v) return 0;
-    if (!(v == v)) return 0;
+    if (!(v >= r.start && v <= r.stop)) return 0;   // outside, or NaN
     if (r.len == 1) return 1;
-    const double x = __ddiv_rn(__dsub_rn(v, r.start), __dsub_rn(r.stop, r.start));
-    return (long long)rint(__dadd_rn(__dmul_rn(x, r.lenm1), 1.0));
+    const double d = __dsub_rn(v, r.start);
+    const double y = fma(d, r.c, 1.0);
+    const double k = rint(y);
+    if (0.5 - fabs(y - k) > y * 0x1p-48) return (int)k;
+    const double x = __ddiv_rn(d, __dsub_rn(r.stop, r.start));
+    return (int)rint(__dadd_rn(__dmul_rn(x, r.lenm1), 1.0));
 }
 
 // ------------------------------------------------------------------------------------------------

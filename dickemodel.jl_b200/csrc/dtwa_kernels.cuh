@@ -129,7 +129,8 @@ struct FailRec {
 
 struct HistDesc {
     int32_t two_d;       // 0: one expression axis (index register 0) against time; 1: two expression axes
-    int32_t staged_off;  // offset (u32 elements) of the per-CTA shared-memory staging bins, -1 = straight to global
+    int32_t staged_off;  // offset (u32 elements) of the per-CTA shared-memory staging bins (1-D: per window slot; 2-D, all
+                         // times in one matrix: one tile for the CTA's whole life), -1 = straight to global
     int64_t base;        // element offset in the u64 arena
     int64_t tstride;     // elements per output time (0: all times share one matrix)
     int32_t n0, n1;      // bins along index register 0 (x) / 1 (y)
@@ -145,7 +146,7 @@ struct EnsArgs {
     uint32_t attempt;  // resampling round (0 = first draw)
     int32_t nslots, nins, ncst, nrange, nhist, stage_bins;
     int32_t window;    // output times staged in shared memory between two CTA-wide flushes
-    int32_t pad0;
+    int32_t stage2d_bins;  // u32 cells of the per-CTA tiles of small 2-D histograms (fixed-step kernels)
     const FailRec *redo;  // NULL in the main pass; else trajectory j re-draws redo[j].idx and contributes from redo[j].k
     FailRec *fail_out;
     unsigned *fail_count;
@@ -175,11 +176,12 @@ struct VmShared {
     double *wsum;
     unsigned *stage;
     unsigned *nvalid;
+    unsigned *stage2d;
     int nslots, stage_bins, nwarps, window;
 };
 
 __host__ __device__ inline size_t ens_smem_bytes(int ncst, int nrange, int nhist, int nslots, int stage_bins, int nins,
-                                                 int rows, int window)
+                                                 int rows, int window, int stage2d_bins = 0)
 {
     size_t b = 0;
     b += sizeof(double) * (size_t)ncst;
@@ -188,6 +190,7 @@ __host__ __device__ inline size_t ens_smem_bytes(int ncst, int nrange, int nhist
     b += sizeof(double) * (size_t)rows * (size_t)window * (size_t)(nslots > 0 ? nslots : 1);
     b += sizeof(unsigned) * (size_t)window * (size_t)stage_bins;
     b += sizeof(unsigned) * (size_t)window;
+    b += sizeof(unsigned) * (size_t)stage2d_bins;
     b += sizeof(VmIns) * (size_t)nins;
     return (b + 15) & ~size_t(15);
 }
@@ -225,7 +228,7 @@ __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp,
     double acc = 0.0, s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     double ov[VM_STACK - VM_REG_STACK];
     int depth = 0;
-    long long ireg0 = 0, ireg1 = 0;
+    int ireg0 = 0, ireg1 = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #define VM_PUSH()                               \
     do {                                        \
@@ -308,7 +311,7 @@ __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp,
             break;
         }
         case OP_BIN: {
-            const long long idx = scale_to_index(acc, V.ranges[in.b]);
+            const int idx = scale_to_index(acc, V.ranges[in.b]);
             if (in.a == 0)
                 ireg0 = idx;
             else
@@ -325,8 +328,13 @@ __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp,
                         atomicAdd(&u64[h.base + (long long)k * h.tstride + (ireg0 - 1)], 1ull);
                 }
             } else {
-                if (valid && ireg0 > 0 && ireg1 > 0)
-                    atomicAdd(&u64[h.base + (long long)k * h.tstride + (ireg1 - 1) * (long long)h.n0 + (ireg0 - 1)], 1ull);
+                if (valid && ireg0 > 0 && ireg1 > 0) {
+                    const unsigned cell = (unsigned)(ireg1 - 1) * (unsigned)h.n0 + (unsigned)(ireg0 - 1);   // n0 * n1 < 2^31 (checked)
+                    if (h.staged_off >= 0)
+                        atomicAdd(&V.stage2d[h.staged_off + cell], 1u);
+                    else
+                        atomicAdd(&u64[h.base + (long long)k * h.tstride + cell], 1ull);
+                }
             }
             break;
         }
@@ -342,16 +350,20 @@ __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp,
 #undef VM_VAR
 }
 
-#ifndef DTWA_ADAPT_MAX_THREADS
-#define DTWA_ADAPT_MAX_THREADS 128
+#ifndef DTWA_RK8_MAX_THREADS
+#define DTWA_RK8_MAX_THREADS 128
 #endif
 #ifndef DTWA_ADAPT_MIN_BLOCKS
-#define DTWA_ADAPT_MIN_BLOCKS 1
+#define DTWA_ADAPT_MIN_BLOCKS 12
 #endif
+// Register budgets.  RK4 fits 64 registers/thread: 4 CTAs of 256 threads per SM.  The embedded pairs run ONE warp per CTA
+// (adaptive_stream); the register file is split over the four SM sub-partitions (16384 registers each), so the only
+// occupancies there are 3 warps per sub-partition at <= 168 registers (12 CTAs/SM) or 4 at <= 128 (16 CTAs/SM, with spills
+// for the 12-stage pair).  Without a bound ptxas takes 170-213 registers and lands on 2 warps per sub-partition.
 template <int ALG>
-struct ens_launch {  // register budget: RK4 fits 64 regs/thread (4 CTAs of 256), the embedded pairs want more
-    static constexpr int max_threads = (ALG == DTWA_ALG_RK4) ? 256 : DTWA_ADAPT_MAX_THREADS;
-    static constexpr int min_blocks = (ALG == DTWA_ALG_RK4) ? 4 : DTWA_ADAPT_MIN_BLOCKS;
+struct ens_launch {
+    static constexpr int max_threads = (ALG == DTWA_ALG_RK4) ? 256 : (ALG == DTWA_ALG_RK8) ? DTWA_RK8_MAX_THREADS : 32;
+    static constexpr int min_blocks = (ALG == DTWA_ALG_RK4) ? 4 : (ALG == DTWA_ALG_RK8) ? 1 : DTWA_ADAPT_MIN_BLOCKS;
 };
 
 // Reducers compiled at run time for one reducer set (dtwa_jit.hpp generates the definition: the same
@@ -374,7 +386,7 @@ template <int SYS, int ALG, bool JIT>
 __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared &V, double *my_partial,
                                                 unsigned long long *nvalid_g)
 {
-    constexpr int NV = Sys<SYS>::NV;
+    constexpr int NV = Sys<SYS>::NV, NVO = Sys<SYS>::NVO;
     const int lane = threadIdx.x & 31;
     const int nt = A.S.nt, W = A.window;
     const int H = (W >= 2) ? W / 2 : 1, R = (W >= 2) ? 2 * H : 1;   // half and ring size
@@ -388,6 +400,7 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
     bool have = false;                                                // a trajectory is in flight
     double tstop = 0.0;
     uint32_t iters = 0;
+    int budget = 0;                                                   // attempts left before maxiters (current trajectory)
     unsigned long long acc_steps = 0, rej_steps = 0;
     Traj<SYS, ALG> T;
     T.status = ST_INACTIVE;
@@ -432,11 +445,16 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
             acc_steps += T.nacc;
             rej_steps += T.nrej;
             T.status = ST_OK;
-            draw_initial<NV>(A.smp, idx, A.attempt, T.u);
+            {
+                double x[NVO];
+                draw_initial<NVO>(A.smp, idx, A.attempt, x);
+                to_chart<SYS>(x, T.u);
+            }
             T.begin(A.S);
             have = true;
             k = 0;
             tstop = A.S.ts[0];
+            budget = (int)(A.S.maxiters > 0x7fffffffll ? 0x7fffffffll : A.S.maxiters);
         }
         // failures end a trajectory: report, skip the rest of its outputs
         if (have && T.status != ST_OK) {
@@ -485,19 +503,23 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
         }
         if (__any_sync(0xffffffffu, !have && j < A.N)) continue;   // somebody still has to draw
         // ================= hot loop: one attempted step per lane and iteration =================
-        const long long glimit = flushed + R;
+        // (lane-local 32-bit bookkeeping: `ahead` = outputs this lane is ahead of the flushed part of the ring, `budget` = attempts
+        //  left before maxiters; one REDUX decides whether to leave)
+        int ahead = have ? (int)(g - flushed) : 0;
 #pragma unroll 1
         while (true) {
             // leave when a lane needs service or a half of the ring can be flushed
             const bool service = have && (T.status != ST_OK || k >= nt);
-            const int ahead = (!have) ? 0x7fffffff : (int)(g - flushed);
-            if (__any_sync(0xffffffffu, service) || __reduce_min_sync(0xffffffffu, ahead) >= H) break;
+            const bool behind = have && ahead < H;          // this lane still keeps the older half of the ring busy
+            const unsigned vote = __reduce_or_sync(0xffffffffu, (service ? 1u : 0u) | (behind ? 2u : 0u));
+            if ((vote & 1u) || !(vote & 2u)) break;
             ++iters;
-            const bool stepping = have && g < glimit;
+            const bool stepping = have && ahead < R;
             if (stepping && T.ad.t < tstop) {
-                if ((long long)(T.nacc + T.nrej) >= A.S.maxiters) {
+                if (budget <= 0) {
                     T.status = ST_MAXITERS;
                 } else {
+                    --budget;
                     bool accepted;
                     if (T.ad.attempt(A.S.par, T.u, tstop, A.S.tol, A.S.dtmin, accepted, A.S.ctrl)) T.status = ST_DOMAIN;
                     if (accepted)
@@ -509,25 +531,32 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
             const bool reached = stepping && T.status == ST_OK && !(T.ad.t < tstop);   // this lane emits output k now
             const bool valid = reached && (k >= start_k);
             if constexpr (JIT) {
-                if (reached)
-                    jit_reduce<NV, true>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0, valid, k,
-                                         wslot);
+                if (reached) {
+                    double xo[NVO];
+                    from_chart<SYS>(T.u, xo);   // the observables' coordinates (the identity except in the Bloch chart)
+                    jit_reduce<NVO, true>(V, &A.smp, A.u64, xo[0], xo[1], NVO == 4 ? xo[NVO - 2] : 0.0, NVO == 4 ? xo[NVO - 1] : 0.0, valid, k,
+                                          wslot);
+                }
             } else {
                 // the interpreter's per-instruction loop is run by the WHOLE warp whenever some lane emits (lanes that do
                 // not emit are masked): run by the emitting lanes alone it left the warp split in two groups that then
                 // executed the step body one after the other (1.66 body executions per iteration at 18 active lanes)
-                if (__any_sync(0xffffffffu, reached))
-                    vm_run<NV, true>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0, valid, k, wslot,
-                                     nullptr, reached);
+                if (__any_sync(0xffffffffu, reached)) {
+                    double xo[NVO];
+                    from_chart<SYS>(T.u, xo);
+                    vm_run<NVO, true>(V, &A.smp, A.u64, xo[0], xo[1], NVO == 4 ? xo[NVO - 2] : 0.0, NVO == 4 ? xo[NVO - 1] : 0.0, valid, k, wslot,
+                                      nullptr, reached);
+                }
             }
             if (reached) {
                 if (valid) atomicAdd(&V.nvalid[wslot], 1u);
                 ++k;
-                ++g;
+                ++ahead;
                 wslot = (wslot + 1 == R) ? 0 : wslot + 1;
                 if (k < nt) tstop = A.S.ts[k];
             }
         }
+        if (have) g = flushed + ahead;
     }
     // ---- step counters: one atomic per warp ----
     acc_steps += T.nacc;
@@ -548,7 +577,7 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
 template <int SYS, int ALG, bool JIT>
 __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
 {
-    constexpr int NV = Sys<SYS>::NV;
+    constexpr int NV = Sys<SYS>::NV, NVO = Sys<SYS>::NVO;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool FIXED = is_fixed<ALG>::value;
     constexpr bool PERLANE = !FIXED;  // adaptive: one staging row per thread, no warp-level reduction
@@ -573,6 +602,8 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
         p += sizeof(unsigned) * (size_t)W * A.stage_bins;
         V.nvalid = reinterpret_cast<unsigned *>(p);
         p += sizeof(unsigned) * W;
+        V.stage2d = reinterpret_cast<unsigned *>(p);
+        p += sizeof(unsigned) * A.stage2d_bins;
         VmIns *prog = reinterpret_cast<VmIns *>(p);
         for (int i = threadIdx.x; i < A.ncst; i += blockDim.x) consts[i] = A.consts[i];
         for (int i = threadIdx.x; i < A.nrange; i += blockDim.x) ranges[i] = A.ranges[i];
@@ -580,6 +611,7 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
         for (int i = threadIdx.x; i < A.nins; i += blockDim.x) prog[i] = A.prog[i];
         for (int i = threadIdx.x; i < W * A.stage_bins; i += blockDim.x) V.stage[i] = 0u;
         for (int i = threadIdx.x; i < W; i += blockDim.x) V.nvalid[i] = 0u;
+        for (int i = threadIdx.x; i < A.stage2d_bins; i += blockDim.x) V.stage2d[i] = 0u;
         if constexpr (PERLANE) {   // one row per lane, in global memory (stays in L2)
             V.wsum = A.ring + (size_t)blockIdx.x * 32 * W * A.nslots;
             if (A.nslots > 0)
@@ -609,11 +641,34 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
     double *my_partial = A.partial + (size_t)blockIdx.x * nt * A.nslots;
     unsigned long long *nvalid_g = A.u64 + CNT_N;
 
+    // small 2-D histograms (all times in one matrix) live in a per-CTA shared-memory tile: one shared-memory atomic per sample,
+    // one global RED per non-empty cell when the tile is flushed (at the end of the CTA's life, and often enough on the way
+    // that no 32-bit cell can overflow)
+    auto flush_tiles = [&]() {
+        __syncthreads();
+        for (int hI = 0; hI < A.nhist; ++hI) {
+            const HistDesc h = V.hists[hI];
+            if (!h.two_d || h.staged_off < 0) continue;
+            const int cells = h.n0 * h.n1;
+            for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+                const unsigned c = V.stage2d[h.staged_off + i];
+                if (c) {
+                    atomicAdd(&A.u64[h.base + i], (unsigned long long)c);
+                    V.stage2d[h.staged_off + i] = 0u;
+                }
+            }
+        }
+        __syncthreads();
+    };
+    const long long tile_flush_every = A.stage2d_bins > 0 ? max(1ll, (1ll << 31) / ((long long)blockDim.x * max(1, A.S.nt))) : 0;
+    long long batches_done = 0;
+
     if constexpr (!FIXED) {
         adaptive_stream<SYS, ALG, JIT>(A, V, my_partial, nvalid_g);
     } else {
     // ---- fixed step: persistent loop over batches of blockDim.x trajectories ----
     for (long long batch = blockIdx.x; batch * (long long)blockDim.x < A.N; batch += gridDim.x) {
+        if (A.stage2d_bins > 0 && ++batches_done % tile_flush_every == 0) flush_tiles();
         const long long j = batch * (long long)blockDim.x + threadIdx.x;
         const bool active = j < A.N;
         Traj<SYS, ALG> T;
@@ -628,7 +683,9 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
                 idx = r.idx;
                 start_k = r.k;
             }
-            draw_initial<NV>(A.smp, idx, A.attempt, T.u);
+            double x[NVO];
+            draw_initial<NVO>(A.smp, idx, A.attempt, x);
+            to_chart<SYS>(x, T.u);
         }
         T.begin(A.S);
         bool failed_reported = false;
@@ -655,12 +712,14 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
             if (!queued) atomicAdd(&A.u64[CNT_UNFINISHED], 1ull);
         };
         auto reduce_at = [&](bool valid, int k, int w) {   // observables + reducers into the window staging
+            double xo[NVO];
+            from_chart<SYS>(T.u, xo);   // the observables' coordinates (the identity except in the Bloch chart)
             if constexpr (JIT)
-                jit_reduce<NV, PERLANE>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0,
-                                        valid, k, w);
+                jit_reduce<NVO, PERLANE>(V, &A.smp, A.u64, xo[0], xo[1], NVO == 4 ? xo[NVO - 2] : 0.0, NVO == 4 ? xo[NVO - 1] : 0.0,
+                                         valid, k, w);
             else
-                vm_run<NV, PERLANE>(V, &A.smp, A.u64, T.u[0], T.u[1], NV == 4 ? T.u[NV - 2] : 0.0, NV == 4 ? T.u[NV - 1] : 0.0,
-                                    valid, k, w, nullptr);
+                vm_run<NVO, PERLANE>(V, &A.smp, A.u64, xo[0], xo[1], NVO == 4 ? xo[NVO - 2] : 0.0, NVO == 4 ? xo[NVO - 1] : 0.0,
+                                     valid, k, w, nullptr);
         };
 
         if constexpr (FIXED) {
@@ -722,6 +781,7 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
             atomicAdd(&A.u64[CNT_LANE], 32ull * warp_iters);
         }
     }
+    if (A.stage2d_bins > 0) flush_tiles();
     }  // fixed step
 }
 
@@ -749,22 +809,28 @@ __global__ void __launch_bounds__(128) integrate_kernel(const SolverArgs S, cons
                                                         double *__restrict__ out, int32_t *__restrict__ status,
                                                         long long *__restrict__ nsteps)
 {
-    constexpr int NV = Sys<SYS>::NV;
+    constexpr int NV = Sys<SYS>::NV, NVO = Sys<SYS>::NVO;
     const long long j0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const bool live = j0 < n;
     const long long j = live ? j0 : n - 1;  // tail lanes shadow the last trajectory: warp-wide ops need every lane
     Traj<SYS, ALG> T;
     T.status = ST_OK;
+    {
+        double x[NVO];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) T.u[i] = u0[j * NV + i];
+        for (int i = 0; i < NVO; ++i) x[i] = u0[j * NVO + i];
+        to_chart<SYS>(x, T.u);
+    }
     T.begin(S);
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
     auto emit = [&](int k) {
         if (T.status == ST_OK && state_bad<SYS>(T.u)) T.status = ST_DOMAIN;
         if (live) {
-            double *o = out + ((size_t)j * S.nt + k) * NV;
+            double xo[NVO];
+            from_chart<SYS>(T.u, xo);
+            double *o = out + ((size_t)j * S.nt + k) * NVO;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) o[i] = (T.status == ST_OK) ? T.u[i] : qnan;
+            for (int i = 0; i < NVO; ++i) o[i] = (T.status == ST_OK) ? xo[i] : qnan;
         }
     };
     if constexpr (is_fixed<ALG>::value) {

@@ -33,7 +33,7 @@ struct CSolver
     dtmin::Float64
     maxiters::Int64
     controller::Int32
-    reserved::Int32
+    chart::Int32
     beta1::Float64
     beta2::Float64
     qmin::Float64
@@ -94,6 +94,7 @@ end
 const SYS_DICKE, SYS_LMG = Int32(0), Int32(1)
 const ALG_RK4, ALG_RK8, ALG_DP5, ALG_DOP853 = Int32(0), Int32(1), Int32(2), Int32(3)
 const CTRL_ODE, CTRL_SCIPY = Int32(0), Int32(1)
+const CHART_QP, CHART_BLOCH = Int32(0), Int32(1)
 const SAMPLER_HOST_ARRAY, SAMPLER_HW, SAMPLER_SU2, SAMPLER_HWXSU2 = Int32(0), Int32(1), Int32(2), Int32(3)
 const RED_AVERAGE, RED_HIST, RED_SURVIVAL = Int32(0), Int32(1), Int32(2)
 const AXIS_EXPR, AXIS_TIME = Int32(0), Int32(1)
@@ -157,7 +158,7 @@ end
 const warned_substitution = Set{Symbol}()
 function csolver(; tol::Real=1e-12, integrator_alg=:TsitPap8, integate_backwards::Bool=false, dt=nothing,
                  adaptive=nothing, dtmin=nothing, maxiters=nothing, controller=:ode, beta1=nothing, beta2=nothing,
-                 qmin=nothing, qmax=nothing, gamma=nothing, qoldinit=nothing, ignored...)
+                 qmin=nothing, qmax=nothing, gamma=nothing, qoldinit=nothing, chart=:qp, ignored...)
     name = Symbol(replace(string(integrator_alg isa Symbol ? integrator_alg : nameof(typeof(integrator_alg))), "()" => ""))
     alg = name in (:DP8, :TsitPap8, :Vern8, :DOP853) ? ALG_DOP853 :
           name in (:DP5, :Tsit5) ? ALG_DP5 :
@@ -180,7 +181,7 @@ function csolver(; tol::Real=1e-12, integrator_alg=:TsitPap8, integate_backwards
     scipy = controller in (:scipy, :SciPy, "scipy")
     CSolver(alg, integate_backwards ? 1 : 0, dt === nothing ? 0.0 : Float64(dt), Float64(tol),
             dtmin === nothing ? 0.0 : Float64(dtmin), maxiters === nothing ? 0 : Int64(maxiters),
-            scipy ? CTRL_SCIPY : CTRL_ODE, 0, scipy ? 0.0 : b1, scipy ? 0.0 : b2,
+            scipy ? CTRL_SCIPY : CTRL_ODE, chart in (:bloch, "bloch") ? CHART_BLOCH : CHART_QP, scipy ? 0.0 : b1, scipy ? 0.0 : b2,
             qmin === nothing ? generic[3] : Float64(qmin), qmax === nothing ? generic[4] : Float64(qmax),
             gamma === nothing ? 0.0 : Float64(gamma), qoldinit === nothing ? 0.0 : Float64(qoldinit))
 end

@@ -87,6 +87,14 @@ typedef struct {
  * (dtwa_integrate_fm, dtwa_lyapunov, dtwa_integrate_events*) always run DTWA_CTRL_SCIPY. */
 #define DTWA_CTRL_ODE 0
 #define DTWA_CTRL_SCIPY 1
+/* Coordinates the Dicke trajectories are integrated in.  DTWA_CHART_QP (0, default): the reference's (Q,q,P,p)
+ * (src/ClassicalDicke.jl:11-17) -- the parity contract.  DTWA_CHART_BLOCH (1, opt-in): the spin as the Cartesian unit vector
+ * (jx,jy,jz) = (Q s/2, -P s/2, (Q^2+P^2)/2 - 1), in which the same equations of motion are bilinear: no square root, no
+ * division, no singular passage at Q^2+P^2 -> 4.  Exact solutions coincide; numerical ones differ by the truncation error
+ * of the method, so results are NOT step-for-step comparable with the reference's.  Inputs, outputs and observables stay
+ * in (Q,q,P,p) either way. */
+#define DTWA_CHART_QP 0
+#define DTWA_CHART_BLOCH 1
 typedef struct {
     int32_t alg;
     int32_t backwards; /* the reference's `integate_backwards` [sic] */
@@ -95,7 +103,7 @@ typedef struct {
     double dtmin;
     int64_t maxiters;
     int32_t controller; /* DTWA_CTRL_* */
-    int32_t reserved;
+    int32_t chart;      /* DTWA_CHART_* (dtwa_integrate and dtwa_ensemble(_launch) only) */
     double beta1, beta2, qmin, qmax, gamma, qoldinit;
 } dtwa_solver;
 

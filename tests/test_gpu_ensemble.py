@@ -326,3 +326,84 @@ def test_user_defined_phase_space_distribution(ctx, mods, O):
     want = w.sum(axis=0) * (2 * np.pi * hb) ** 2 / N
     assert relerr(sp, want, floor=1e-6).max() < 1e-9
     assert abs(sp[0] - 1.0) < 0.1                        # (2 pi hbar)^2 E_W[W] = 1 for this Gaussian
+
+
+def test_small_2d_histogram_tile_in_shared_memory_is_bit_exact(ctx, mods, O):
+    """2-D histograms whose matrix fits the per-CTA shared-memory tile (<= 8192 cells, all times in one matrix) are staged
+    there and flushed with one global RED per non-empty cell; the counts must equal those of the straight-to-global path
+    (DTWA_NO_STAGE2D=1) and the oracle's binning of the same trajectories"""
+    import os
+    TWA, CD, _, CS = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    j, N = 60, 6000
+    u0 = O.sample(O.SAMPLER_HWXSU2, DOCS_PT, 1 / j, N, seed=21)
+    ts = TWA.jrange(0, 0.25, 6)
+    qs, ps = TWA.jrange(-4.0, 0.1, 4.0), TWA.jrange(-4.0, 0.1, 4.0)     # 81 x 81 = 6561 cells
+    run = lambda: TWA.calculate_distribution(system, N=N, ts=ts, distribution=TWA.samples_from_array(u0, j=j), x="q", xs=qs, y="p", ys=ps,   # noqa: E731
+                                             integrator_alg="RK4", dt=2.0 ** -6)
+    staged = run()
+    os.environ["DTWA_NO_STAGE2D"] = "1"
+    try:
+        direct = run()
+    finally:
+        del os.environ["DTWA_NO_STAGE2D"]
+    assert np.array_equal(staged, direct)
+    traj, st, _ = CS.integrate_batch(system, u0, np.asarray(ts), integrator_alg="RK4", dt=2.0 ** -6)
+    valid = (st == 0)[:, None] & np.isfinite(traj).all(axis=2)
+    want = O.hist_2d(traj[:, :, 1], traj[:, :, 3], valid, qs.linrange(), ps.linrange(), animate=False)
+    assert np.array_equal(staged, want / N) and want.sum() > 0.99 * N * len(ts)
+    # many batches per CTA and a chain of two tiles + a 1-D histogram: Philox sampling, larger N
+    W = TWA.coherent_Wigner_HWxSU2([0, 0, 0, 0], j=100, seed=3)
+    mk = lambda **kw: TWA.mcs_for_distributions(system, N=400000, distribution=W, ts=TWA.jrange(0, 0.5, 2), **kw)   # noqa: E731
+    chain = lambda: TWA.monte_carlo_integrate(system, TWA.mcs_chain(mk(x="q", xs=TWA.jrange(-1, 0.05, 1), y="p", ys=TWA.jrange(-1, 0.05, 1)),   # noqa: E731
+                                                                    mk(x="Q", xs=TWA.jrange(-1, 0.05, 1), y="P", ys=TWA.jrange(-1, 0.05, 1)),
+                                                                    mk(y="t", x="q", xs=TWA.jrange(-1, 0.01, 1))), integrator_alg="RK4", dt=2.0 ** -5)
+    a = chain()
+    W.offset = 0
+    os.environ["DTWA_NO_STAGE2D"] = "1"
+    try:
+        b = chain()
+    finally:
+        del os.environ["DTWA_NO_STAGE2D"]
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and abs(a[0].sum() - 5.0) < 1e-9
+
+
+def test_bloch_chart_is_the_same_dynamics(ctx, mods, O, gold):
+    """chart="bloch" (opt-in): Hamilton's equations in (jx, jy, jz, q, p), bilinear, no square root.  Coordinate-free checks:
+    against the 40-digit mpmath truth at tight tolerance, against the reference's chart at the truncation-error level with
+    the method's convergence order, and through the ensemble kernels (same Philox samples, same observables)"""
+    TWA, CD, _, CS = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    for c in gold["truth_mpmath"]["cases"]:
+        if c["system"] != "dicke":
+            continue
+        keep = [i for i, t in enumerate(c["times"]) if float(t) <= 10.0]
+        ts = np.array([float(c["times"][i]) for i in keep])
+        sysc = CD.ClassicalDickeSystem(w0=c["par"][0], w=c["par"][1], g=c["par"][2])
+        out, st, _ = CS.integrate_batch(sysc, [c["u0"]], ts, integrator_alg="DP8", tol=1e-13, chart="bloch")
+        assert st[0] == 0
+        want = np.array([[float(x) for x in c["u"][i]] for i in keep])
+        assert relerr(out[0], want).max() < 2e-10, relerr(out[0], want).max()
+    u0 = O.sample(O.SAMPLER_HWXSU2, DOCS_PT, 1 / 50, 64, seed=4)
+    ts = np.array([0.0, 1.0, 2.0])
+    ref, st, _ = CS.integrate_batch(system, u0, ts, integrator_alg="DP8", tol=1e-13)
+    errs = []
+    for dt in (2.0 ** -5, 2.0 ** -6):
+        b, stb, _ = CS.integrate_batch(system, u0, ts, integrator_alg="RK4", dt=dt, chart="bloch")
+        assert (stb == 0).all()
+        errs.append(np.abs(b - ref).max())
+    assert errs[0] < 1e-5 and 10 < errs[0] / errs[1] < 24          # 4th order in the other chart as well
+    # ensembles: same Philox samples, Bloch chart vs (Q,P) chart, adaptive at a tight tolerance -> same averages
+    kw = dict(observable=[TWA.Weyl.Jz(50) / 50, "q", "Q*p"], N=4096, ts=TWA.jrange(0, 0.5, 3), integrator_alg="DP8", tol=1e-12)
+    a = TWA.average(system, distribution=TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=50, seed=9), **kw)
+    b = TWA.average(system, distribution=TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=50, seed=9), chart="bloch", **kw)
+    assert TWA.last_info["n_failed"] == 0 and np.abs(a - b).max() < 1e-9
+    with pytest.raises(pkg_error(), match="Dicke"):
+        from dickemodel_jl_b200 import ClassicalLMG as CL
+        TWA.average(CL.ClassicalLMGSystem(Ω=1, ξ=-1), observable="Q", N=10, ts=[0.0, 1.0], distribution=TWA.coherent_Wigner_SU2([0, 0], j=10),
+                    integrator_alg="RK4", dt=0.1, chart="bloch")
+
+
+def pkg_error():
+    import dickemodel_jl_b200 as pkg
+    return pkg.DtwaError

@@ -171,6 +171,25 @@ def test_scale_to_index_bit_exact(ctx, O):
         assert np.array_equal(ctx.scale_to_index(v, a, b, n), O.scale_to_index(v, a, b, n))
 
 
+def test_scale_to_index_fast_path_never_disagrees_with_the_formula(ctx, O):
+    """the kernels take rint(fma(v - start, c, 1)) unless that sits within 16 ulp of a rounding boundary, where the
+    reference's division decides (csrc/dtwa_device.cuh scale_to_index): values AT the boundaries k + 1/2 and a few ulp
+    either side of them, for short and very long axes, must give the reference's index (src/TWA.jl:53-64)"""
+    rng = np.random.default_rng(11)
+    for (a, b, n) in ((-1.1, 1.1, 221), (-4.3, 4.3, 431), (-4.3, 4.3, 8601), (0.0, 1.0, 2), (-7.25, 13.5, 100001), (1e-3, 2e-3, 1001),
+                      (-2.0, 2.0, 2 ** 31 - 1), (0.5, 0.5, 7)):
+        mids = a + (rng.integers(0, max(1, n - 1), 20000) + 0.5) * (b - a) / max(1, n - 1)
+        vs = [rng.uniform(a - 0.1 * (b - a + 1), b + 0.1 * (b - a + 1), 50000), mids, np.array([a, b, np.nextafter(a, -np.inf), np.nextafter(b, np.inf)])]
+        for s in range(1, 5):
+            up, dn = mids.copy(), mids.copy()
+            for _ in range(s):
+                up, dn = np.nextafter(up, np.inf), np.nextafter(dn, -np.inf)
+            vs += [up, dn]
+        v = np.concatenate(vs)
+        with np.errstate(all="ignore"):
+            assert np.array_equal(ctx.scale_to_index(v, a, b, n), O.scale_to_index(v, a, b, n)), (a, b, n)
+
+
 def _random_expression(rng, depth):
     """a random arithmetic expression over Q,q,P,p with + - * / integer powers and sqrt(abs-free positive arguments)"""
     if depth == 0 or rng.random() < 0.2:

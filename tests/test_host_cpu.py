@@ -401,7 +401,8 @@ for N, mb in ((7, 2), (100, 5), (2, float("inf")), (9, float("inf")), (25, 3)):
     res = TWA.average(system, observable="Q", N=N, ts=[0.0, 1.0], distribution=W, integrator_alg="RK4", dt=0.1, maxNBatch=mb)
     # every rank made the same number of launches (collectives); the all-reduced total covers N exactly once
     out[f"{N},{mb}"] = [len(StubContext.calls), float(res[0] * N), sorted(StubContext.calls)]
-print(json.dumps({"rank": rank, "out": out}), flush=True)
+with open(os.path.join(os.environ["DTWA_OUT"], f"rank{rank}.json"), "w") as f:   # (stdout of several ranks interleaves)
+    json.dump({"rank": rank, "out": out}, f)
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -412,13 +413,12 @@ def test_uneven_shards_and_maxNBatch_issue_the_same_collectives_on_every_rank(tm
     with fewer all-reduces than the others (NCCL would hang).  3 gloo ranks drive TWA.monte_carlo_integrate over a stub context."""
     script = tmp_path / "chunk_worker.py"
     script.write_text(CHUNK_WORKER)
-    env = dict(os.environ, DTWA_ROOT=ROOT, OMP_NUM_THREADS="1")
+    env = dict(os.environ, DTWA_ROOT=ROOT, OMP_NUM_THREADS="1", DTWA_OUT=str(tmp_path))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3", "--master-addr", "127.0.0.1",
                         "--master-port", "29617", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
     import json
-    rows = sorted((json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")), key=lambda x: x["rank"])
-    assert len(rows) == 3
+    rows = [json.load(open(tmp_path / f"rank{k}.json")) for k in range(3)]
     for key in rows[0]["out"]:
         N = int(key.split(",")[0])
         launches = {row["out"][key][0] for row in rows}

@@ -25,6 +25,8 @@ ap.add_argument("--mode", default="", choices=["", "hist2d", "animate", "varianc
 ap.add_argument("--state", default="A", choices=["A", "B"])
 ap.add_argument("--tol", type=float, default=1e-8)
 ap.add_argument("--jit", type=int, default=2)
+ap.add_argument("--chart", default=None, help="qp (default) | bloch")
+ap.add_argument("--small-bins", action="store_true", help="hist2d on an 81 x 81 grid (fits the per-CTA shared-memory tile)")
 ap.add_argument("--controller", default=None, help="ode (default) | scipy")
 ap.add_argument("--gains", default="", help="beta1,beta2[,qmin,qmax[,gamma]] for the OrdinaryDiffEq controller")
 ap.add_argument("--w", type=float, default=1.0)
@@ -43,6 +45,8 @@ ts = TWA.jrange(0, a.tstep, a.tend)
 jz = TWA.Weyl.Jz(j) / j
 ap_dt = {"RK4": 2.0 ** -7, "RK8": 0.05}
 kw = dict(integrator_alg=a.alg, dt=ap_dt[a.alg]) if a.alg in ap_dt else dict(integrator_alg=a.alg, tol=a.tol)
+if a.chart:
+    kw["chart"] = a.chart
 if a.alg not in ap_dt:
     if a.controller:
         kw["controller"] = a.controller
@@ -53,6 +57,8 @@ warnings.simplefilter("ignore")
 for rep in range(a.reps):
     W = TWA.coherent_Wigner_HWxSU2(center, j=j, seed=20261019)
     qs, ps = TWA.jrange(-4.3, 0.02, 4.3), TWA.jrange(-2.4, 0.02, 2.4)
+    if a.small_bins:
+        qs, ps = TWA.jrange(-4.0, 0.1, 4.0), TWA.jrange(-4.0, 0.1, 4.0)
     if a.mode == "hist2d":
         out = TWA.calculate_distribution(system, x="q", xs=qs, y="p", ys=ps, ts=ts, N=a.n, distribution=W, **kw)
     elif a.mode == "animate":
