@@ -551,6 +551,7 @@ struct Adaptive {
     static constexpr int NV = Sys<SYS>::NV;
     static constexpr int ERR_ORDER = (ALG == DTWA_ALG_DP5) ? 4 : 7;
     double t, habs;
+    double hlast;      // length of the last accepted step (interpolated outputs)
     double k0[NV];
     float lqold;       // PI controller memory: lg2 of the error estimate of the last accepted (un-clipped) step
     bool rejected;
@@ -595,9 +596,12 @@ struct Adaptive {
     }
 
     // one attempted step towards tstop.  Returns 0 = keep going, 1 = trajectory failed (DOMAIN).
-    // `accepted` reports whether y/t advanced.
+    // `accepted` reports whether y/t advanced.  KEEP: an accepted step also hands back the state and the derivative at its
+    // START (yprev, fprev) and its length (hlast) -- what the Hermite interpolant of interpolated outputs needs; they take
+    // the registers of the trial values, which are dead by then.
+    template <bool KEEP = false>
     __device__ __forceinline__ int attempt(const SysPar &p, double (&y)[NV], double tstop, double tol, double dtmin,
-                                           bool &accepted, const CtrlPar &c)
+                                           bool &accepted, const CtrlPar &c, double *yprev = nullptr, double *fprev = nullptr)
     {
         accepted = false;
         bool forced = false;
@@ -675,6 +679,14 @@ struct Adaptive {
             } else
                 lqold = fmaxf(le, c.lqoldinit);
             t = last ? tstop : t + h;
+            if constexpr (KEEP) {
+                hlast = h;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    yprev[i] = y[i];
+                    fprev[i] = k0[i];
+                }
+            }
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 y[i] = yn[i];
@@ -688,6 +700,23 @@ struct Adaptive {
     }
 };
 #undef RHS
+
+// 3rd-order Hermite interpolant over an accepted step: OrdinaryDiffEq's hermite_interpolant, what the reference's
+// FunctionCallingCallback(funcat = ts) evaluates at the output times (src/TWA.jl:180) for algorithms without a dense output
+// of their own (TsitPap8, the reference default):
+//   u(Theta) = (1 - Theta) y0 + Theta y1 + Theta (Theta - 1) ((1 - 2 Theta)(y1 - y0) + (Theta - 1) h f0 + Theta h f1)
+template <int NV>
+__device__ __forceinline__ void hermite_interpolant(const double *y0, const double *f0, const double (&y1)[NV], const double (&f1)[NV], double h,
+                                                    double theta, double (&u)[NV])
+{
+    const double tm1 = theta - 1.0, a = theta * tm1, b = 1.0 - 2.0 * theta;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const double dy = y1[i] - y0[i];
+        const double inner = fma(b, dy, h * fma(tm1, f0[i], theta * f1[i]));
+        u[i] = fma(a, inner, fma(theta, dy, y0[i]));
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  key = seed, counter = (idx, attempt, block).

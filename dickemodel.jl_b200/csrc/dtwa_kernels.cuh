@@ -758,7 +758,7 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
             }
             for (int hI = 0; hI < A.nhist; ++hI) {
                 const HistDesc h = V.hists[hI];
-                if (h.staged_off < 0) continue;
+                if (h.staged_off < 0 || h.two_d) continue;   // (2-D tiles are flushed by flush_tiles)
                 for (int i = threadIdx.x; i < nw * h.n0; i += blockDim.x) {
                     const int w = i / h.n0, b = i - w * h.n0;
                     unsigned *cell = V.stage + (size_t)w * A.stage_bins + h.staged_off + b;

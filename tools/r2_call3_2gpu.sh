@@ -1,0 +1,8 @@
+#!/bin/bash
+# round 2, GPU call 3 (2 GPUs): the multi-GPU tests (in-process N-device context + torchrun path) and bench.py at N=2
+cd "$GRAFT_REPO_ROOT" || exit 1
+O=gpurun_out
+nvidia-smi -L > $O/r2c3_gpus.txt
+timeout 1200 python -m pytest tests/test_gpu_distributed.py tests/test_gpu_ensemble.py -m gpu -q -rs > $O/r2c3_pytest_2gpu.log 2>&1; echo "pytest rc $?" | tee -a $O/r2c3_status.txt
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > $O/r2c3_bench_n2.json 2> $O/r2c3_bench_n2.err; echo "bench n2 rc $?" | tee -a $O/r2c3_status.txt
+tail -5 $O/r2c3_bench_n2.err
