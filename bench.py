@@ -368,11 +368,22 @@ def main():
             fn()
         except Exception as e:   # noqa: BLE001
             extras[name] = {"error": repr(e)}
+        finally:
+            ctx.set_jit(2)
+
+    def warm(fn):
+        """warm-up call with the run-time specialisation forced, so that the NVRTC compile (about a second per new kernel)
+        happens here and not inside the timed call that follows"""
+        ctx.set_jit(1)
+        try:
+            return fn()
+        finally:
+            ctx.set_jit(2)
 
     def leg_hist():
         n_per = max(1024, int(1.25e8 * scale))
         Nh = n_per * world
-        hist_chain(max(1024, Nh // 64), TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=WORK["seed"]))   # warm-up (and run-time specialisation)
+        warm(lambda: hist_chain(max(1024, Nh // 64), TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=WORK["seed"])))   # warm-up (and run-time specialisation)
         (counts, ih), wall_ms = timed(lambda: hist_chain(Nh, TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=WORK["seed"])))
         kms = gather(ih["kernel_ms"])
         # integer bit-exactness across the GPU count: the same index range [0, Nc), sharded over all ranks + all-reduce,
@@ -413,8 +424,8 @@ def main():
             import warnings
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
-                TWA.average(system, observable=jz, N=max(world * 32, Na // 64), ts=tsa, distribution=TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=1),
-                            integrator_alg=alg, tol=1e-8)     # warm-up (and run-time specialisation)
+                warm(lambda: TWA.average(system, observable=jz, N=max(world * 32, Na // 64), ts=tsa, distribution=TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=1),
+                                         integrator_alg=alg, tol=1e-8))     # warm-up (and run-time specialisation)
                 _, wall_ms = timed(lambda: TWA.average(system, observable=jz, N=Na, ts=tsa, distribution=TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=1),
                                                        integrator_alg=alg, tol=1e-8))
             ia = dict(TWA.last_info)
@@ -438,7 +449,7 @@ def main():
         """the headline workload away from the unit-parameter specialisation (w = g = 1 saves 8 of 96 FP64 instructions/step)"""
         sysg = CD.ClassicalDickeSystem(w0=1.0, w=0.8, g=0.66)
         Wg = TWA.coherent_Wigner_HWxSU2(WORK["center"], j=j, seed=WORK["seed"])
-        TWA.average(sysg, observable=jz, N=max(world * 1024, N_total // 64), ts=ts, distribution=Wg, **solver)
+        warm(lambda: TWA.average(sysg, observable=jz, N=max(world * 1024, N_total // 64), ts=ts, distribution=Wg, **solver))
         Wg.offset = 0
         _, wall_ms = timed(lambda: TWA.average(sysg, observable=jz, N=N_total, ts=ts, distribution=Wg, **solver))
         ig = dict(TWA.last_info)
@@ -446,6 +457,36 @@ def main():
         extras["general_parameters"] = {"workload": "the headline workload at w0=1, w=0.8, g=0.66: no unit-parameter specialisation (96 FP64 instr/step)",
                                         "steps_per_s": ig["steps_accepted"] / (km * 1e-3), "steps_per_s_wall": ig["steps_accepted"] / (wall_ms * 1e-3),
                                         "kernel_ms": km, "specialised": ig["jit"]}
+
+    def leg_bloch():
+        """opt-in chart="bloch" (the same equations of motion in (jx,jy,jz,q,p): bilinear, no square root) on the headline
+        workload and on configs[3] -- NOT the parity path: it leaves the reference's step sequence"""
+        Wb = TWA.coherent_Wigner_HWxSU2(WORK["center"], j=j, seed=WORK["seed"])
+        warm(lambda: TWA.average(system, observable=jz, N=max(world * 1024, N_total // 64), ts=ts, distribution=Wb, chart="bloch", **solver))
+        Wb.offset = 0
+        outb, wall_ms = timed(lambda: TWA.average(system, observable=jz, N=N_total, ts=ts, distribution=Wb, chart="bloch", **solver))
+        ib = dict(TWA.last_info)
+        km = max(gather(ib["kernel_ms"]))
+        res = {"workload": "the headline workload with chart='bloch' (59 FP64 instr/step instead of 88)",
+               "rk4_steps_per_s": ib["steps_accepted"] / (km * 1e-3), "rk4_steps_per_s_wall": ib["steps_accepted"] / (wall_ms * 1e-3), "rk4_kernel_ms": km,
+               "max_abs_diff_mean_jz_vs_qp_chart": float(np.max(np.abs(outb - last))),
+               "note": "same Philox samples as the headline leg; the two charts differ by the RK4 truncation error (~1e-8 here), far inside the MC error"}
+        tsa = TWA.jrange(0, 1, 1000)
+        Na = max(world * 32, int(8e6 * scale))
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            warm(lambda: TWA.average(system, observable=jz, N=max(world * 32, Na // 64), ts=tsa, distribution=TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=1),
+                                     tol=1e-8, chart="bloch"))
+            _, wall_a = timed(lambda: TWA.average(system, observable=jz, N=Na, ts=tsa, distribution=TWA.coherent_Wigner_HWxSU2(Bpt, j=j, seed=1), tol=1e-8, chart="bloch"))
+        ia = dict(TWA.last_info)
+        kms = gather(ia["kernel_ms"])
+        att = ia["steps_accepted"] + ia["steps_rejected"]
+        res["configs3_default_pi"] = {"attempted_steps": att, "attempted_steps_per_s": att / (max(kms) * 1e-3), "kernel_ms_max": max(kms), "wall_ms": wall_a,
+                                      "rejected_fraction": ia["steps_rejected"] / max(1, att), "lane_efficiency": att / max(1, ia["lane_steps"]),
+                                      "n_failed": ia["n_failed"],
+                                      "time_vs_qp_chart": (max(kms) / extras["adaptive_default_pi"]["kernel_ms_max"]) if "kernel_ms_max" in extras.get("adaptive_default_pi", {}) else None}
+        extras["bloch_chart"] = res
 
     def leg_inproc():
         """the in-process N-device context (dtwa_create(ndev = world) + ncclCommInitAll + grouped ncclAllReduce: what the Julia
@@ -482,6 +523,7 @@ def main():
         leg("config2_histograms", leg_hist)
         leg("adaptive", leg_adaptive)
         leg("general_parameters", leg_general)
+        leg("bloch_chart", leg_bloch)
         leg("inproc_ctx", leg_inproc)
 
     # ---- one GPU only, for the record: configs[0] next to the CPU port, and small instances of SURVEY 8f ranks 2-4 ----
@@ -500,6 +542,14 @@ def main():
                     g0 = TWA.average(system, observable=jz, N=10000, ts=ts0, distribution=W0)
                     wall0 = time.perf_counter() - t0
             i0 = dict(TWA.last_info)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                for _ in range(2):
+                    W0 = TWA.coherent_Wigner_HWxSU2(WORK["center"], j=j, seed=WORK["seed"])
+                    t0 = time.perf_counter()
+                    g0h = TWA.average(system, observable=jz, N=10000, ts=ts0, distribution=W0, output="hermite")
+                    wall0h = time.perf_counter() - t0
+            i0h = dict(TWA.last_info)
             sp0 = O.make_sampler(O.SAMPLER_HWXSU2, WORK["center"], 1.0 / j, seed=WORK["seed"])
             cj = float(np.sqrt(j * (j + 1)))
             thr = host_threads()
@@ -512,7 +562,10 @@ def main():
                             "OrdinaryDiffEq's controller for TsitPap8 (the tableau itself is not available offline)",
                 "gpu_wall_s": wall0, "gpu_kernel_ms": i0["kernel_ms"], "gpu_attempted_steps": i0["steps_accepted"] + i0["steps_rejected"],
                 "cpu_port_s": cpu0, "cpu_cores": thr, "cpu_attempted_steps": r0["steps_accepted"] + r0["steps_rejected"],
-                "max_abs_diff_mean_jz": float(np.max(np.abs(r0["sums"][:, 0] / j / 10000 - g0)))}
+                "max_abs_diff_mean_jz": float(np.max(np.abs(r0["sums"][:, 0] / j / 10000 - g0))),
+                "hermite_output": {"note": "output='hermite': the reference's interpolated outputs (src/TWA.jl:180) instead of landing on every ts[k]",
+                                   "gpu_wall_s": wall0h, "gpu_kernel_ms": i0h["kernel_ms"], "gpu_attempted_steps": i0h["steps_accepted"] + i0h["steps_rejected"],
+                                   "max_abs_diff_mean_jz_vs_stepping": float(np.max(np.abs(g0h - g0)))}}
             # SURVEY 8f ranks 2-4 (the callers on the other side of `integrate`), small instances, for the record
             CSm, ESP = pkg.ClassicalSystems, pkg.EnergyShellProjections
             sysw = CD.ClassicalDickeSystem(w=0.8, g=0.8, w0=1)

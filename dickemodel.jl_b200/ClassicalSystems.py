@@ -135,6 +135,7 @@ def solver_from_kargs(kargs: dict) -> _lib.Solver:
     maxiters = k.pop("maxiters", None)
     controller = k.pop("controller", None)
     chart = k.pop("chart", None)
+    output = k.pop("output", None)
     gains = {g: k.pop(g, None) for g in ("beta1", "beta2", "qmin", "qmax", "gamma", "qoldinit")}   # solve()'s own keywords
     for ignored in ("save_everystep", "show_progress", "progress", "verbose", "dense"):
         k.pop(ignored, None)
@@ -174,6 +175,12 @@ def solver_from_kargs(kargs: dict) -> _lib.Solver:
         s.chart = _lib.CHART_BLOCH     # opt-in: same equations in (jx,jy,jz,q,p); leaves the reference's step sequence
     else:
         raise ValueError(f"chart={chart!r}: use 'qp' (the reference's coordinates, default) or 'bloch'")
+    if output in (None, "step", "tstops"):
+        s.output = _lib.OUTPUT_STEP
+    elif output in ("hermite", "interpolate"):
+        s.output = _lib.OUTPUT_HERMITE   # the reference's semantics: outputs interpolated inside un-clipped steps (src/TWA.jl:180)
+    else:
+        raise ValueError(f"output={output!r}: use 'step' (land on every output time, default) or 'hermite'")
     if controller in (None, "ode", "OrdinaryDiffEq", "pi", "PI"):
         s.controller = _lib.CTRL_ODE
         b1, b2, qmin, qmax = alg.gains if alg.gains is not None else (0.0, 0.0, 0.0, 0.0)
@@ -197,7 +204,7 @@ def solver_from_kargs(kargs: dict) -> _lib.Solver:
         raise ValueError(f"controller={controller!r}: use 'ode' (OrdinaryDiffEq's, the default) or 'scipy'")
     last_solver.clear()
     last_solver.update(requested=alg.name, algorithm={_lib.ALG_RK4: "RK4", _lib.ALG_RK8: "RK8", _lib.ALG_DP5: "DP5", _lib.ALG_DOP853: "DOP853"}[code],
-                       substituted=bool(alg.note), controller=None if fixed else ctrl_name, chart="bloch" if s.chart == _lib.CHART_BLOCH else "qp",
+                       substituted=bool(alg.note), controller=None if fixed else ctrl_name, chart="bloch" if s.chart == _lib.CHART_BLOCH else "qp", output="hermite" if (s.output == _lib.OUTPUT_HERMITE and not fixed) else "step",
                        gains=None if (fixed or s.controller != _lib.CTRL_ODE) else effective_gains(s))
     return s
 

@@ -23,6 +23,7 @@ SYS_DICKE, SYS_LMG = 0, 1
 ALG_RK4, ALG_RK8, ALG_DP5, ALG_DOP853 = 0, 1, 2, 3
 CTRL_ODE, CTRL_SCIPY = 0, 1
 CHART_QP, CHART_BLOCH = 0, 1
+OUTPUT_STEP, OUTPUT_HERMITE = 0, 1
 SAMPLER_HOST_ARRAY, SAMPLER_COHERENT_HW, SAMPLER_COHERENT_SU2, SAMPLER_COHERENT_HWXSU2, SAMPLER_DEVICE_ARRAY = 0, 1, 2, 3, 4
 RED_AVERAGE, RED_HIST, RED_SURVIVAL = 0, 1, 2
 AXIS_EXPR, AXIS_TIME = 0, 1
@@ -55,7 +56,7 @@ class Solver(C.Structure):
     _fields_ = [("alg", C.c_int32), ("backwards", C.c_int32), ("dt", C.c_double), ("tol", C.c_double),
                 ("dtmin", C.c_double), ("maxiters", C.c_int64), ("controller", C.c_int32), ("chart", C.c_int32),
                 ("beta1", C.c_double), ("beta2", C.c_double), ("qmin", C.c_double), ("qmax", C.c_double),
-                ("gamma", C.c_double), ("qoldinit", C.c_double)]
+                ("gamma", C.c_double), ("qoldinit", C.c_double), ("output", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Sampler(C.Structure):

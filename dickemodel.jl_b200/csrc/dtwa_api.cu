@@ -346,6 +346,7 @@ static int check_solver(const dtwa_solver *sol, bool fixed_needs_dt = true)
     if (fixed && fixed_needs_dt && !(sol->dt > 0)) return set_err(DTWA_ERR_INVALID, "fixed-step algorithms need dt > 0");
     if (!fixed && !(sol->tol > 0)) return set_err(DTWA_ERR_INVALID, "adaptive algorithms need tol > 0");
     if (sol->chart != DTWA_CHART_QP && sol->chart != DTWA_CHART_BLOCH) return set_err(DTWA_ERR_INVALID, "unknown chart");
+    if (sol->output != DTWA_OUTPUT_STEP && sol->output != DTWA_OUTPUT_HERMITE) return set_err(DTWA_ERR_INVALID, "unknown output mode");
     return 0;
 }
 
@@ -473,7 +474,7 @@ static SolverArgs make_solver_args(const dtwa_system *sys, const dtwa_solver *so
     S.tend = ts[nt - 1];
     S.maxiters = sol->maxiters > 0 ? sol->maxiters : 100000;
     S.nt = nt;
-    S.pad = 0;
+    S.interp = (!force_scipy && sol->output == DTWA_OUTPUT_HERMITE && sol->alg != DTWA_ALG_RK4 && sol->alg != DTWA_ALG_RK8) ? 1 : 0;
     return S;
 }
 

@@ -34,9 +34,10 @@ struct SolverArgs {
     double tol, dtmin, tend;
     long long maxiters;
     int32_t nt;
-    int32_t pad;
+    int32_t interp;      // adaptive pairs: 1 = outputs from the Hermite interpolant over un-clipped steps (DTWA_OUTPUT_HERMITE)
     CtrlPar ctrl;        // step-size controller of the adaptive pairs
 };
+constexpr int INTERP_MAX_OUT = 32;   // an interpolating step is clipped so that it spans at most this many output times
 
 template <int ALG>
 struct is_fixed {
@@ -514,6 +515,7 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
             const unsigned vote = __reduce_or_sync(0xffffffffu, (service ? 1u : 0u) | (behind ? 2u : 0u));
             if ((vote & 1u) || !(vote & 2u)) break;
             ++iters;
+            if (!A.S.interp) {
             const bool stepping = have && ahead < R;
             if (stepping && T.ad.t < tstop) {
                 if (budget <= 0) {
@@ -554,6 +556,65 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
                 ++ahead;
                 wslot = (wslot + 1 == R) ? 0 : wslot + 1;
                 if (k < nt) tstop = A.S.ts[k];
+            }
+            } else {
+            // ---- DTWA_OUTPUT_HERMITE: steps ignore the output times (clipped only at tlim = the INTERP_MAX_OUT-th output time
+            // ahead, so that one step never fills more than INTERP_MAX_OUT ring slots, and at the last one); every output time
+            // inside an accepted step is served from the Hermite interpolant over that step, right away ----
+            const int maxout = min(INTERP_MAX_OUT, H);   // (H >= 32 whenever the ring holds >= 64 output times)
+            const bool stepping = have && ahead <= R - maxout;
+            bool accepted = false;
+            double yprev[NV], fprev[NV];
+            if (stepping && T.status == ST_OK && T.ad.t < tstop) {
+                if (budget <= 0) {
+                    T.status = ST_MAXITERS;
+                } else {
+                    --budget;
+                    const int klim = min(k + maxout - 1, nt - 1);
+                    const double tlim = A.S.ts[klim];
+                    if (T.ad.template attempt<true>(A.S.par, T.u, tlim, A.S.tol, A.S.dtmin, accepted, A.S.ctrl, yprev, fprev)) T.status = ST_DOMAIN;
+                    if (accepted)
+                        ++T.nacc;
+                    else if (T.status == ST_OK)
+                        ++T.nrej;
+                }
+            }
+            // outputs due: after an accepted step all ts[k] <= t (interpolated); before the first step the ones at t = 0
+            bool due = stepping && T.status == ST_OK && k < nt && !(T.ad.t < tstop);
+            while (JIT ? due : __any_sync(0xffffffffu, due)) {
+                double uo[NV];
+                if (due) {
+                    if (accepted && tstop < T.ad.t) {
+                        const double theta = (tstop - (T.ad.t - T.ad.hlast)) / T.ad.hlast;
+                        hermite_interpolant<NV>(yprev, fprev, T.u, T.ad.k0, T.ad.hlast, theta, uo);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) uo[i] = T.u[i];
+                    }
+                    if (state_bad<SYS>(uo)) {   // the interpolated state left the chart: the trajectory fails at this output
+                        T.status = ST_DOMAIN;
+                        due = false;
+                    }
+                }
+                const bool valid = due && (k >= start_k);
+                double xo[NVO];
+                if (due || !JIT) from_chart<SYS>(uo, xo);
+                if constexpr (JIT) {
+                    if (due)
+                        jit_reduce<NVO, true>(V, &A.smp, A.u64, xo[0], xo[1], NVO == 4 ? xo[NVO - 2] : 0.0, NVO == 4 ? xo[NVO - 1] : 0.0, valid, k, wslot);
+                } else {
+                    vm_run<NVO, true>(V, &A.smp, A.u64, xo[0], xo[1], NVO == 4 ? xo[NVO - 2] : 0.0, NVO == 4 ? xo[NVO - 1] : 0.0, valid, k, wslot,
+                                      nullptr, due);
+                }
+                if (due) {
+                    if (valid) atomicAdd(&V.nvalid[wslot], 1u);
+                    ++k;
+                    ++ahead;
+                    wslot = (wslot + 1 == R) ? 0 : wslot + 1;
+                    if (k < nt) tstop = A.S.ts[k];
+                    due = k < nt && !(T.ad.t < tstop);
+                }
+            }
             }
         }
         if (have) g = flushed + ahead;
@@ -843,6 +904,7 @@ __global__ void __launch_bounds__(128) integrate_kernel(const SolverArgs S, cons
         // moves on to the next one without waiting for the others (nested "for each output time: while (t < t_k) step"
         // loops make every lane wait for the slowest one at every output time)
         int k = 0;
+        if (!S.interp) {
 #pragma unroll 1
         while (__any_sync(0xffffffffu, k < S.nt)) {
             if (k < S.nt) {
@@ -865,6 +927,50 @@ __global__ void __launch_bounds__(128) integrate_kernel(const SolverArgs S, cons
                     ++k;
                 }
             }
+        }
+        } else {
+        // DTWA_OUTPUT_HERMITE: same step sequence as the ensemble kernel's (clip at the maxout-th output time ahead, see
+        // adaptive_stream: maxout = min(32, half of a ring of min(256, nt) outputs)), outputs from the Hermite interpolant
+        const int wfull = S.nt < 256 ? S.nt : 256;
+        const int maxout = min(INTERP_MAX_OUT, wfull >= 2 ? wfull / 2 : 1);
+#pragma unroll 1
+        while (__any_sync(0xffffffffu, k < S.nt)) {
+            if (k < S.nt) {
+                bool accepted = false;
+                double yprev[NV], fprev[NV];
+                if (T.status == ST_OK && T.ad.t < S.ts[k]) {
+                    if ((long long)(T.nacc + T.nrej) >= S.maxiters) {
+                        T.status = ST_MAXITERS;
+                    } else {
+                        const double tlim = S.ts[min(k + maxout - 1, S.nt - 1)];
+                        if (T.ad.template attempt<true>(S.par, T.u, tlim, S.tol, S.dtmin, accepted, S.ctrl, yprev, fprev))
+                            T.status = ST_DOMAIN;
+                        else if (accepted)
+                            ++T.nacc;
+                        else
+                            ++T.nrej;
+                    }
+                }
+                while (k < S.nt && (T.status != ST_OK || !(T.ad.t < S.ts[k]))) {
+                    const double tk = S.ts[k];
+                    if (T.status == ST_OK && accepted && tk < T.ad.t) {
+                        double uo[NV], keep[NV];
+                        const double theta = (tk - (T.ad.t - T.ad.hlast)) / T.ad.hlast;
+                        hermite_interpolant<NV>(yprev, fprev, T.u, T.ad.k0, T.ad.hlast, theta, uo);
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) {
+                            keep[i] = T.u[i];
+                            T.u[i] = uo[i];
+                        }
+                        emit(k);   // (reports the interpolated state; a bad one ends the trajectory here)
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) T.u[i] = keep[i];
+                    } else
+                        emit(k);
+                    ++k;
+                }
+            }
+        }
         }
     }
     if (live) {

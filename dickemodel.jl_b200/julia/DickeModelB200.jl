@@ -40,6 +40,8 @@ struct CSolver
     qmax::Float64
     gamma::Float64
     qoldinit::Float64
+    output::Int32
+    reserved::Int32
 end
 struct CSampler
     kind::Int32
@@ -95,6 +97,7 @@ const SYS_DICKE, SYS_LMG = Int32(0), Int32(1)
 const ALG_RK4, ALG_RK8, ALG_DP5, ALG_DOP853 = Int32(0), Int32(1), Int32(2), Int32(3)
 const CTRL_ODE, CTRL_SCIPY = Int32(0), Int32(1)
 const CHART_QP, CHART_BLOCH = Int32(0), Int32(1)
+const OUTPUT_STEP, OUTPUT_HERMITE = Int32(0), Int32(1)
 const SAMPLER_HOST_ARRAY, SAMPLER_HW, SAMPLER_SU2, SAMPLER_HWXSU2 = Int32(0), Int32(1), Int32(2), Int32(3)
 const RED_AVERAGE, RED_HIST, RED_SURVIVAL = Int32(0), Int32(1), Int32(2)
 const AXIS_EXPR, AXIS_TIME = Int32(0), Int32(1)
@@ -158,7 +161,7 @@ end
 const warned_substitution = Set{Symbol}()
 function csolver(; tol::Real=1e-12, integrator_alg=:TsitPap8, integate_backwards::Bool=false, dt=nothing,
                  adaptive=nothing, dtmin=nothing, maxiters=nothing, controller=:ode, beta1=nothing, beta2=nothing,
-                 qmin=nothing, qmax=nothing, gamma=nothing, qoldinit=nothing, chart=:qp, ignored...)
+                 qmin=nothing, qmax=nothing, gamma=nothing, qoldinit=nothing, chart=:qp, output=:step, ignored...)
     name = Symbol(replace(string(integrator_alg isa Symbol ? integrator_alg : nameof(typeof(integrator_alg))), "()" => ""))
     alg = name in (:DP8, :TsitPap8, :Vern8, :DOP853) ? ALG_DOP853 :
           name in (:DP5, :Tsit5) ? ALG_DP5 :
@@ -183,7 +186,8 @@ function csolver(; tol::Real=1e-12, integrator_alg=:TsitPap8, integate_backwards
             dtmin === nothing ? 0.0 : Float64(dtmin), maxiters === nothing ? 0 : Int64(maxiters),
             scipy ? CTRL_SCIPY : CTRL_ODE, chart in (:bloch, "bloch") ? CHART_BLOCH : CHART_QP, scipy ? 0.0 : b1, scipy ? 0.0 : b2,
             qmin === nothing ? generic[3] : Float64(qmin), qmax === nothing ? generic[4] : Float64(qmax),
-            gamma === nothing ? 0.0 : Float64(gamma), qoldinit === nothing ? 0.0 : Float64(qoldinit))
+            gamma === nothing ? 0.0 : Float64(gamma), qoldinit === nothing ? 0.0 : Float64(qoldinit),
+            output in (:hermite, :interpolate, "hermite") ? OUTPUT_HERMITE : OUTPUT_STEP, 0)
 end
 
 # ---- integrate (src/ClassicalSystems.jl:78-140) -------------------------------------------------

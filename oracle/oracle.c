@@ -233,6 +233,36 @@ static double initial_step(int kind, const double *par, double sg, const double 
     return fmin(h, interval);
 }
 
+/* error norm of an embedded pair (scipy rk.py RungeKutta._estimate_error_norm / DOP853; OrdinaryDiffEq's calculate_residuals agrees) */
+static double orc_error_norm(int alg, int nv, int S, double tol, double h, const double *u, const double *yn, double K[][4])
+{
+    double sc[4];
+    for (int i = 0; i < nv; ++i) sc[i] = tol + fmax(fabs(u[i]), fabs(yn[i])) * tol;
+    if (alg == ALG_DP5) {
+        double e[4];
+        for (int i = 0; i < nv; ++i) {
+            double s = 0;
+            for (int j = 0; j <= S; ++j) s += DP5_E[j] * K[j][i];
+            e[i] = s * h / sc[i];
+        }
+        return rms(e, nv);
+    }
+    double n5 = 0, n3 = 0;
+    for (int i = 0; i < nv; ++i) {
+        double s5 = 0, s3 = 0;
+        for (int j = 0; j <= S; ++j) {
+            s5 += DOP853_E5[j] * K[j][i];
+            s3 += DOP853_E3[j] * K[j][i];
+        }
+        s5 /= sc[i];
+        s3 /= sc[i];
+        n5 += s5 * s5;
+        n3 += s3 * s3;
+    }
+    if (n5 == 0 && n3 == 0) return 0;
+    return fabs(h) * n5 / sqrt((n5 + 0.01 * n3) * nv);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* a7 + the per-time callback of a20.  One trajectory, stepping exactly onto every ts[k]; calls
  * cb(user, k, u) at each output.  src/ClassicalSystems.jl:78-140 contract: abstol=reltol=tol,
@@ -255,6 +285,12 @@ typedef struct {
      * 1 = SciPy's (rk.py _step_impl): what tests/golden/scipy_pairs.json pins. */
     int controller;
     double beta1, beta2, qmin, qmax, gamma, qoldinit;
+    /* 0: adaptive steps are clipped so that they land on every ts[k] (the library's default).  1: the reference's semantics
+     * (FunctionCallingCallback(funcat=ts), src/TWA.jl:180): steps ignore the output times and the state at ts[k] is
+     * OrdinaryDiffEq's 3rd-order Hermite interpolant over the accepted step that contains it; a step is clipped only at the
+     * maxout-th output time ahead (maxout = min(32, half of a ring of min(256, nt) outputs): the library's ring rule) and at
+     * the last one. */
+    int interp;
 } orc_problem;
 
 #define CTRL_ODE 0
@@ -303,6 +339,128 @@ int orc_solve_one(const orc_problem *pb, const double *u0, const double *ts, int
         double h_abs = 0;
         int rejected = 0;
         double qold = pb->qoldinit, q11 = 1.0;
+        if (pb->interp) {
+            int wfull = nt < 256 ? nt : 256;
+            int maxout = wfull >= 2 ? wfull / 2 : 1;
+            if (maxout > 32) maxout = 32;
+            double yprev[4], fprev[4], hlast = 0;
+            k = 0;
+            while (k < nt && status == ST_OK) {
+                /* outputs due at the current time (before the first step: those at t = 0) */
+                while (k < nt && !(t < ts[k])) {
+                    if (nonfinite(u, nv) || orc_out_of_bounds(kind, u)) {
+                        status = ST_DOMAIN;
+                        break;
+                    }
+                    cb(user, k, u);
+                    ++k;
+                }
+                if (k >= nt || status != ST_OK) break;
+                if (!have_f) {
+                    if (orc_rhs(kind, par, sg, u, K[0])) {
+                        status = ST_DOMAIN;
+                        break;
+                    }
+                    h_abs = initial_step(kind, par, sg, u, K[0], tend - t, err_order, tol);
+                    have_f = 1;
+                }
+                if (attempts >= pb->maxiters) {
+                    status = ST_MAXITERS;
+                    break;
+                }
+                attempts++;
+                int klim = k + maxout - 1 < nt - 1 ? k + maxout - 1 : nt - 1;
+                double tlim = ts[klim];
+                int forced = 0;
+                if (h_abs < dtmin) {
+                    h_abs = dtmin;
+                    forced = 1;
+                }
+                double h = h_abs;
+                int clipped = 0, last = 0;
+                if (t + h >= tlim) {
+                    clipped = (tlim - t) < h_abs;
+                    h = tlim - t;
+                    last = 1;
+                }
+                int bad;
+                if (pb->alg == ALG_DP5)
+                    bad = rk_trial(kind, par, sg, 6, &DP5_A[0][0], 6, DP5_B, h, u, K, yn);
+                else
+                    bad = rk_trial(kind, par, sg, 12, &DOP853_A[0][0], 12, DOP853_B, h, u, K, yn);
+                double err = orc_error_norm(pb->alg, nv, S, tol, h, u, yn, K);
+                bad = bad || nonfinite(yn, nv) || !isfinite(err) || orc_out_of_bounds(kind, yn);
+                if (bad) {
+                    if (forced) {
+                        status = ST_DOMAIN;
+                        break;
+                    }
+                    h_abs = h * (pb->controller == CTRL_SCIPY ? 0.2 : pb->qmin);
+                    rejected = 1;
+                    rej++;
+                    continue;
+                }
+                int accept;
+                double hn;
+                if (pb->controller == CTRL_SCIPY) {
+                    accept = err < 1 || forced;
+                    if (accept) {
+                        double factor = (err == 0) ? 10.0 : fmin(10.0, 0.9 * pow(err, expo));
+                        if (rejected) factor = fmin(1.0, factor);
+                        hn = h * factor;
+                    } else
+                        hn = h * fmax(0.2, 0.9 * pow(err, expo));
+                } else {
+                    double q;
+                    if (err == 0)
+                        q = 1.0 / pb->qmax;
+                    else {
+                        q11 = pow(err, pb->beta1);
+                        q = q11 / pow(qold, pb->beta2);
+                        q = fmax(1.0 / pb->qmax, fmin(1.0 / pb->qmin, q / pb->gamma));
+                    }
+                    accept = err <= 1 || forced;
+                    hn = accept ? h / q : h / fmin(1.0 / pb->qmin, q11 / pb->gamma);
+                }
+                if (!accept) {
+                    h_abs = hn;
+                    rejected = 1;
+                    rej++;
+                    continue;
+                }
+                if (clipped) {
+                    if (hn < h_abs) hn = h_abs;
+                } else if (pb->controller != CTRL_SCIPY)
+                    qold = fmax(err, pb->qoldinit);
+                h_abs = hn;
+                double t1 = last ? tlim : t + h;
+                for (int i = 0; i < nv; ++i) {
+                    yprev[i] = u[i];
+                    fprev[i] = K[0][i];
+                    u[i] = yn[i];
+                    K[0][i] = K[S][i];
+                }
+                hlast = h;
+                rejected = 0;
+                acc++;
+                /* outputs inside (t, t1): Hermite interpolant, OrdinaryDiffEq's hermite_interpolant */
+                while (k < nt && ts[k] < t1) {
+                    double th = (ts[k] - (t1 - hlast)) / hlast, uo[4];
+                    for (int i = 0; i < nv; ++i) {
+                        double dy = u[i] - yprev[i];
+                        uo[i] = (1 - th) * yprev[i] + th * u[i] +
+                                th * (th - 1) * ((1 - 2 * th) * dy + (th - 1) * hlast * fprev[i] + th * hlast * K[0][i]);
+                    }
+                    if (nonfinite(uo, nv) || orc_out_of_bounds(kind, uo)) {
+                        status = ST_DOMAIN;
+                        break;
+                    }
+                    cb(user, k, uo);
+                    ++k;
+                }
+                t = t1;
+            }
+        } else
         for (k = 0; k < nt && status == ST_OK; ++k) {
             double tstop = ts[k];
             while (t < tstop) {

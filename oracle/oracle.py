@@ -42,7 +42,7 @@ class Problem(C.Structure):
     _fields_ = [("kind", C.c_int), ("par", C.c_double * 4), ("backwards", C.c_int), ("alg", C.c_int),
                 ("dt", C.c_double), ("tol", C.c_double), ("dtmin", C.c_double), ("maxiters", C.c_long),
                 ("controller", C.c_int), ("beta1", C.c_double), ("beta2", C.c_double), ("qmin", C.c_double),
-                ("qmax", C.c_double), ("gamma", C.c_double), ("qoldinit", C.c_double)]
+                ("qmax", C.c_double), ("gamma", C.c_double), ("qoldinit", C.c_double), ("interp", C.c_int)]
 
 
 class Sampler(C.Structure):
@@ -145,9 +145,10 @@ def _controller_fields(p, alg, controller):
         p.gamma = float(controller[4])
 
 
-def make_problem(kind, par, alg=ALG_DOP853, dt=0.0, tol=1e-12, dtmin=None, maxiters=100000, backwards=False, controller=None):
+def make_problem(kind, par, alg=ALG_DOP853, dt=0.0, tol=1e-12, dtmin=None, maxiters=100000, backwards=False, controller=None, output=None):
     p = Problem()
     _controller_fields(p, alg, controller)
+    p.interp = 1 if output in ("hermite", "interpolate") else 0
     p.kind = kind
     for i, v in enumerate(par):
         p.par[i] = float(v)
@@ -198,7 +199,7 @@ def step_table(ts, dt):
 
 
 def integrate(kind, par, u0, ts, alg=ALG_DOP853, dt=0.0, tol=1e-12, dtmin=None, maxiters=100000,
-              backwards=False, fast=False, controller=None):
+              backwards=False, fast=False, controller=None, output=None):
     """Dense restatement of ClassicalSystems.integrate + the per-time callback: returns
     (out[n][nt][nvar], status[n], accepted[n], rejected[n])."""
     nv = nvar(kind)
@@ -209,7 +210,7 @@ def integrate(kind, par, u0, ts, alg=ALG_DOP853, dt=0.0, tol=1e-12, dtmin=None, 
     status = np.empty(n, dtype=np.int32)
     nacc = np.empty(n, dtype=np.int64)
     nrej = np.empty(n, dtype=np.int64)
-    pb = make_problem(kind, par, alg, dt, tol, dtmin, maxiters, backwards, controller)
+    pb = make_problem(kind, par, alg, dt, tol, dtmin, maxiters, backwards, controller, output)
     rc = lib(fast).orc_integrate(C.byref(pb), _dp(u0), n, _dp(ts), nt, _dp(out),
                                  status.ctypes.data_as(C.POINTER(C.c_int)),
                                  nacc.ctypes.data_as(C.POINTER(C.c_long)),
@@ -512,12 +513,12 @@ def hist_2d(xv, yv, valid, xr, yr, animate):
 
 
 def ensemble(kind, par, sampler, N, ts, values, hists=(), alg=ALG_RK4, dt=2.0 ** -7, tol=1e-12, dtmin=None,
-             maxiters=100000, backwards=False, host_u0=None, workers=1, tolerate_errors=True, fast=False, controller=None):
+             maxiters=100000, backwards=False, host_u0=None, workers=1, tolerate_errors=True, fast=False, controller=None, output=None):
     """The C driver (src/TWA.jl:100-224 restated).  values: list of (kind, a, c); hists: list of
     (value_index, start, stop, len).  Returns a dict of raw sums / counts / counters."""
     ts = np.ascontiguousarray(ts, dtype=np.float64)
     nt = len(ts)
-    pb = make_problem(kind, par, alg, dt, tol, dtmin, maxiters, backwards, controller)
+    pb = make_problem(kind, par, alg, dt, tol, dtmin, maxiters, backwards, controller, output)
     vals = (Value * len(values))(*[Value(k, a, c) for (k, a, c) in values])
     hs = (Hist * max(1, len(hists)))(*[Hist(v, a, b, n) for (v, a, b, n) in hists])
     sums = np.zeros((nt, len(values)))

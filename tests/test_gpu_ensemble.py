@@ -365,7 +365,7 @@ def test_small_2d_histogram_tile_in_shared_memory_is_bit_exact(ctx, mods, O):
         b = chain()
     finally:
         del os.environ["DTWA_NO_STAGE2D"]
-    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and abs(a[0].sum() - 5.0) < 1e-9
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and 4.9 < a[0].sum() <= 5.0 + 1e-9    # (a few samples leave q in [-1, 1] by t = 2)
 
 
 def test_bloch_chart_is_the_same_dynamics(ctx, mods, O, gold):
@@ -407,3 +407,35 @@ def test_bloch_chart_is_the_same_dynamics(ctx, mods, O, gold):
 def pkg_error():
     import dickemodel_jl_b200 as pkg
     return pkg.DtwaError
+
+
+def test_hermite_output_in_the_ensemble_kernels(ctx, mods, O):
+    """output="hermite" through TWA.average / calculate_distribution: same trajectories as dtwa_integrate in that mode
+    (histogram counts bit-exact against the binned dense output), averages equal to the oracle's, fewer attempts than
+    stepping onto every output time"""
+    TWA, CD, _, CS = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)
+    j, N = 100, 3000
+    u0 = O.sample(O.SAMPLER_HWXSU2, DOCS_PT, 1 / j, N, seed=17)
+    ts = TWA.jrange(0, 0.05, 6)
+    kw = dict(integrator_alg="DP8", tol=1e-9, output="hermite")
+    qs = TWA.jrange(-4.3, 0.02, 4.3)
+    mk = lambda **k: TWA.mcs_for_distributions(system, N=N, distribution=TWA.samples_from_array(u0, j=j), ts=ts, **k)   # noqa: E731
+    D = TWA.samples_from_array(u0, j=j)
+    m_q, avg = TWA.monte_carlo_integrate(system, TWA.mcs_chain(TWA.mcs_for_distributions(system, N=N, distribution=D, ts=ts, y="t", x="q", xs=qs),
+                                                               TWA.mcs_for_averaging(system, N=N, distribution=D, ts=ts, observable=["Q", "q*p"])), **kw)
+    n_h = TWA.last_info["steps_accepted"] + TWA.last_info["steps_rejected"]
+    traj, st, _ = CS.integrate_batch(system, u0, np.asarray(ts), **kw)
+    assert (st == 0).all()
+    assert np.array_equal(m_q, O.hist_time(traj[:, :, 1], np.ones(traj.shape[:2], bool), *qs.linrange()) / N)
+    ref, rst, _, _ = O.integrate(O.SYS_DICKE, DPAR, u0, np.asarray(ts), alg=O.ALG_DOP853, tol=1e-9, output="hermite")
+    assert np.abs(avg[:, 0] - ref[:, :, 0].mean(axis=0)).max() < 1e-8
+    TWA.average(system, observable="Q", N=N, ts=ts, distribution=TWA.samples_from_array(u0, j=j), integrator_alg="DP8", tol=1e-9)
+    assert n_h < 0.7 * (TWA.last_info["steps_accepted"] + TWA.last_info["steps_rejected"])
+    # the interpreter kernel (no run-time specialisation) takes the same path
+    ctx.set_jit(0)
+    try:
+        avg0 = TWA.average(system, observable=["Q", "q*p"], N=N, ts=ts, distribution=TWA.samples_from_array(u0, j=j), **kw)
+    finally:
+        ctx.set_jit(2)
+    assert np.array_equal(avg0, avg)

@@ -83,6 +83,24 @@ def test_adaptive_trajectories_match_oracle_and_truth(ctx, pkg, O, gold, kind, p
         assert relerr(out[:, short], truth[:, short]).max() < 1e-10   # north_star bound
 
 
+def test_hermite_output_mode_matches_the_oracle(ctx, pkg, O, gold):
+    """DTWA_OUTPUT_HERMITE (the reference's interpolated outputs, src/TWA.jl:180): same un-clipped step sequence and the same
+    interpolant as the oracle's restatement -> same values to the tolerance level, same step counts to within 2 %"""
+    g = gold["truth_ld"]["dicke"]
+    u0 = np.array(g["u0"])[:96]
+    ts = np.arange(0, 161) * 0.05
+    for alg, oalg in ((pkg._lib.ALG_DOP853, O.ALG_DOP853), (pkg._lib.ALG_DP5, O.ALG_DP5)):
+        sol = csol(pkg, alg, tol=1e-10)
+        sol.output = pkg._lib.OUTPUT_HERMITE
+        out, st, ns = ctx.integrate(csys(pkg, 0, g["par"]), sol, u0, ts)
+        ref, rst, acc, rej = O.integrate(O.SYS_DICKE, g["par"], u0, ts, alg=oalg, tol=1e-10, output="hermite")
+        assert (st == 0).all() and (rst == 0).all()
+        assert relerr(out, ref).max() < 1e-7
+        assert abs(ns.sum() - (acc + rej).sum()) <= 0.02 * (acc + rej).sum()
+        stepped, _, ns2 = ctx.integrate(csys(pkg, 0, g["par"]), csol(pkg, alg, tol=1e-10), u0, ts)
+        assert ns.sum() < 0.85 * ns2.sum() and 1e-9 < np.abs(out - stepped).max() < 1e-4
+
+
 def test_docs_point_against_mpmath(ctx, pkg, gold):
     c = gold["truth_mpmath"]["cases"][0]
     ts = np.array([float(t) for t in c["times"]])

@@ -94,7 +94,7 @@ def test_struct_layouts_match_the_header(pkg):
     """field names, offsets and sizes of the ctypes mirror, parsed against include/dicketwa.h"""
     lib = pkg._lib
     H = _parse_header_structs()
-    assert H["dtwa_solver"]["size"] == 96 and H["dtwa_system"]["size"] == 40 and H["dtwa_result"]["size"] == 88
+    assert H["dtwa_solver"]["size"] == 104 and H["dtwa_system"]["size"] == 40 and H["dtwa_result"]["size"] == 88
     for cname, pyname, _ in _PAIRS:
         S = getattr(lib, pyname)
         got = [(n, getattr(S, n).offset, getattr(S, n).size) for n, _ in S._fields_]
