@@ -25,6 +25,7 @@ ap.add_argument("--mode", default="", choices=["", "hist2d", "animate", "varianc
 ap.add_argument("--state", default="A", choices=["A", "B"])
 ap.add_argument("--tol", type=float, default=1e-8)
 ap.add_argument("--jit", type=int, default=2)
+ap.add_argument("--output", default=None, help="step (default) | hermite")
 ap.add_argument("--chart", default=None, help="qp (default) | bloch")
 ap.add_argument("--small-bins", action="store_true", help="hist2d on an 81 x 81 grid (fits the per-CTA shared-memory tile)")
 ap.add_argument("--controller", default=None, help="ode (default) | scipy")
@@ -47,6 +48,8 @@ ap_dt = {"RK4": 2.0 ** -7, "RK8": 0.05}
 kw = dict(integrator_alg=a.alg, dt=ap_dt[a.alg]) if a.alg in ap_dt else dict(integrator_alg=a.alg, tol=a.tol)
 if a.chart:
     kw["chart"] = a.chart
+if a.output:
+    kw["output"] = a.output
 if a.alg not in ap_dt:
     if a.controller:
         kw["controller"] = a.controller
