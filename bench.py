@@ -470,7 +470,10 @@ def main():
         res = {"workload": "the headline workload with chart='bloch' (59 FP64 instr/step instead of 88)",
                "rk4_steps_per_s": ib["steps_accepted"] / (km * 1e-3), "rk4_steps_per_s_wall": ib["steps_accepted"] / (wall_ms * 1e-3), "rk4_kernel_ms": km,
                "max_abs_diff_mean_jz_vs_qp_chart": float(np.max(np.abs(outb - last))),
-               "note": "same Philox samples as the headline leg; the two charts differ by the RK4 truncation error (~1e-8 here), far inside the MC error"}
+               "max_abs_diff_mean_jz_vs_qp_chart_t_le_2": float(np.max(np.abs(outb - last)[:41])),
+               "mc_standard_error": float(0.3 / np.sqrt(N_total)),
+               "note": "same Philox samples as the headline leg; the two charts differ by the RK4 truncation error (t <= 2: see above), which the chaotic "
+                       "dynamics amplifies until, at late times, the two ensembles are independent at the level of the Monte-Carlo standard error"}
         tsa = TWA.jrange(0, 1, 1000)
         Na = max(world * 32, int(8e6 * scale))
         import warnings

@@ -595,29 +595,11 @@ struct Adaptive {
         habs = fmin(h, tend);
     }
 
-    // one attempted step towards tstop.  Returns 0 = keep going, 1 = trajectory failed (DOMAIN).
-    // `accepted` reports whether y/t advanced.  KEEP: an accepted step also hands back the state and the derivative at its
-    // START (yprev, fprev) and its length (hlast) -- what the Hermite interpolant of interpolated outputs needs; they take
-    // the registers of the trial values, which are dead by then.
-    template <bool KEEP = false>
-    __device__ __forceinline__ int attempt(const SysPar &p, double (&y)[NV], double tstop, double tol, double dtmin,
-                                           bool &accepted, const CtrlPar &c, double *yprev = nullptr, double *fprev = nullptr)
+    // The stages and the error estimate of ONE trial step of length h from (y, k0): no decision, no state change.  Shared by
+    // attempt() below and by the software-pipelined hot loop of the ensemble kernels, so that both take bit-identical steps.
+    __device__ __forceinline__ void trial(const SysPar &p, const double (&y)[NV], const double h, const double tol, double (&yn)[NV],
+                                          double (&kn)[NV], double &err) const
     {
-        accepted = false;
-        bool forced = false;
-        if (habs < dtmin) {
-            habs = dtmin;
-            forced = true;
-        }
-        double h = habs;
-        bool clipped = false;
-        const bool last = (t + h >= tstop);
-        if (last) {
-            clipped = (tstop - t) < habs;
-            h = tstop - t;
-        }
-        double err;
-        double yn[NV], kn[NV];
         if constexpr (ALG == DTWA_ALG_DP5) {
 #include "dp5_body.inc"
             (void)dy;
@@ -647,15 +629,40 @@ struct Adaptive {
             }
             n5 = group_sum<SYS>(n5);
             n3 = group_sum<SYS>(n3);
-            if (n5 == 0.0 && n3 == 0.0)
-                err = 0.0;
-            else {
+            {
                 double is, sq;
                 rsqrt_sqrt_pair(fma(0.01, n3, n5) * (double)Sys<SYS>::NORM_N, is, sq);
-                err = fabs(h) * n5 * is;
+                const double e = fabs(h) * n5 * is;
+                err = (n5 == 0.0 && n3 == 0.0) ? 0.0 : e;   // (0 * Inf otherwise)
             }
 #undef DOP853_KNEW
         }
+    }
+
+    // one attempted step towards tstop.  Returns 0 = keep going, 1 = trajectory failed (DOMAIN).
+    // `accepted` reports whether y/t advanced.  KEEP: an accepted step also hands back the state and the derivative at its
+    // START (yprev, fprev) and its length (hlast) -- what the Hermite interpolant of interpolated outputs needs; they take
+    // the registers of the trial values, which are dead by then.
+    template <bool KEEP = false>
+    __device__ __forceinline__ int attempt(const SysPar &p, double (&y)[NV], double tstop, double tol, double dtmin,
+                                           bool &accepted, const CtrlPar &c, double *yprev = nullptr, double *fprev = nullptr)
+    {
+        accepted = false;
+        bool forced = false;
+        if (habs < dtmin) {
+            habs = dtmin;
+            forced = true;
+        }
+        double h = habs;
+        bool clipped = false;
+        const bool last = (t + h >= tstop);
+        if (last) {
+            clipped = (tstop - t) < habs;
+            h = tstop - t;
+        }
+        double err;
+        double yn[NV], kn[NV];
+        trial(p, y, h, tol, yn, kn, err);
         const bool bad = state_bad<SYS>(yn) || !(err == err) || isinf(err);
         if (bad) {
             if (forced) return 1;

@@ -372,7 +372,7 @@ struct ens_launch {
 template <int NV, bool PERLANE>
 __device__ __forceinline__ void jit_reduce(const VmShared &V, const SamplerPar *smp, unsigned long long *u64, const double x0,
                                            const double x1, const double x2, const double x3, const bool valid, const int k,
-                                           const int w);
+                                           const int w, const bool emit = true);   // emit = false: compute, store nothing (valid implies emit)
 
 // Adaptive pairs: ONE warp per CTA (the host launches 32 threads).  Each lane integrates its own STREAM of
 // trajectories -- lane l of CTA c takes trajectories (c*32 + l) + m*gridDim*32, m = 0, 1, ... -- and numbers the output
@@ -402,6 +402,8 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
     double tstop = 0.0;
     uint32_t iters = 0;
     int budget = 0;                                                   // attempts left before maxiters (current trajectory)
+    int tlim_k = -1;                                                  // Hermite outputs: the output index `tlim` was loaded for
+    double tlim = 0.0;                                                // ... and the time a step is clipped at
     unsigned long long acc_steps = 0, rej_steps = 0;
     Traj<SYS, ALG> T;
     T.status = ST_INACTIVE;
@@ -456,6 +458,7 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
             k = 0;
             tstop = A.S.ts[0];
             budget = (int)(A.S.maxiters > 0x7fffffffll ? 0x7fffffffll : A.S.maxiters);
+            tlim_k = -1;
         }
         // failures end a trajectory: report, skip the rest of its outputs
         if (have && T.status != ST_OK) {
@@ -507,6 +510,89 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
         // (lane-local 32-bit bookkeeping: `ahead` = outputs this lane is ahead of the flushed part of the ring, `budget` = attempts
         //  left before maxiters; one REDUX decides whether to leave)
         int ahead = have ? (int)(g - flushed) : 0;
+#ifndef DTWA_NO_PIPELINED_LOOP
+        if (JIT && !A.S.interp) {
+            // ---- software-pipelined form (specialised kernels, outputs by stepping onto ts[k]) ----
+            // An attempt ends in a serial, latency-bound tail -- error norm -> controller -> commit -> emit -> vote -- during
+            // which the warp feeds nothing to the FP64 pipe (30-40 % of its time with three warps per scheduler, ncu source
+            // page of r2_ncu_dop853_cfg4_v6).  Only the accept decision and the next step size are needed by the next
+            // attempt.  So the loop body is rotated: the output a lane landed on in iteration n-1 is emitted at the START of
+            // iteration n, the exit vote taken there is acted on one iteration later, every lane runs the trial step
+            // (inactive ones with h = 0) and the decisions are selects -- one straight-line block in which the scheduler
+            // overlaps the emit, the vote and the bookkeeping with the stage arithmetic of the next attempt.  Same trial(),
+            // same controller expressions as Adaptive::attempt: bit-identical trajectories.
+            const CtrlPar &c = A.S.ctrl;
+            bool pend = have && T.status == ST_OK && k < nt && ahead < R && !(T.ad.t < tstop);
+            double tnext = (have && k + 1 < nt) ? A.S.ts[k + 1] : tstop;
+            unsigned vote = 2u;
+#pragma unroll 1
+            while (true) {
+                if ((vote & 1u) || !(vote & 2u)) break;
+                ++iters;
+                {   // [E] the output reached in the previous iteration (state T.u is still the one that landed on ts[k])
+                    double xo[NVO];
+                    from_chart<SYS>(T.u, xo);
+                    const bool valid = pend && (k >= start_k);
+                    jit_reduce<NVO, true>(V, &A.smp, A.u64, xo[0], xo[1], NVO == 4 ? xo[NVO - 2] : 0.0, NVO == 4 ? xo[NVO - 1] : 0.0, valid, k, wslot,
+                                          pend);
+                    if (valid) atomicAdd(&V.nvalid[wslot], 1u);
+                    if (pend) {
+                        ++k;
+                        ++ahead;
+                        wslot = (wslot + 1 == R) ? 0 : wslot + 1;
+                        tstop = tnext;
+                        if (k + 1 < nt) tnext = A.S.ts[k + 1];   // prefetched: needed one output time from now
+                    }
+                }
+                {   // [V] exit vote, acted on at the top of the next iteration
+                    const bool service = have && (T.status != ST_OK || k >= nt);
+                    const bool behind = have && ahead < H;
+                    vote = __reduce_or_sync(0xffffffffu, (service ? 1u : 0u) | (behind ? 2u : 0u));
+                }
+                // [S] trial step (every lane; inactive ones take h = 0)
+                const bool want = have && T.status == ST_OK && k < nt && ahead < R && T.ad.t < tstop;
+                const bool active = want && budget > 0;
+                if (want && budget <= 0) T.status = ST_MAXITERS;
+                budget -= active ? 1 : 0;
+                const bool forced = T.ad.habs < A.S.dtmin;
+                const double habs_eff = forced ? A.S.dtmin : T.ad.habs;
+                const bool last = (T.ad.t + habs_eff >= tstop);
+                const bool clipped = last && ((tstop - T.ad.t) < habs_eff);
+                double h = last ? tstop - T.ad.t : habs_eff;
+                if (!active) h = 0.0;
+                double yn[NV], kn[NV], err;
+                T.ad.trial(A.S.par, T.u, h, A.S.tol, yn, kn, err);
+                // [C] decisions as selects
+                const bool bad = state_bad<SYS>(yn) || !(err == err) || isinf(err);
+                const float le = lg2_approx(fminf(fmaxf((float)err, 1e-30f), 1e30f));
+                const float e_rej = ex2_approx(-c.b1 * le);
+                const float e_acc = ex2_approx(-fmaf(c.b1, le, c.nb2 * T.ad.lqold));
+                float fac_acc = fminf(c.fac_max, fmaxf(c.fac_min_acc, c.g * e_acc));
+                if (T.ad.rejected) fac_acc = fminf(fac_acc, c.post_reject_cap);
+                const float fac_rej = fmaxf(c.fac_min_rej, c.g * e_rej);
+                const bool acc = active && !bad && (forced || err < c.acc_thr);
+                const bool fail = active && bad && forced;
+                double hn = h * (double)(acc ? fac_acc : fac_rej);
+                if (bad) hn = h * c.dom_shrink;
+                if (acc && clipped && hn < habs_eff) hn = habs_eff;
+                if (acc && !clipped) T.ad.lqold = fmaxf(le, c.lqoldinit);
+                if (active && !fail) T.ad.habs = hn;
+                if (active) T.ad.rejected = !acc;
+                if (acc) {
+                    T.ad.t = last ? tstop : T.ad.t + h;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        T.u[i] = yn[i];
+                        T.ad.k0[i] = kn[i];
+                    }
+                }
+                if (fail) T.status = ST_DOMAIN;
+                T.nacc += acc ? 1u : 0u;
+                T.nrej += (active && !acc && !fail) ? 1u : 0u;
+                pend = have && T.status == ST_OK && k < nt && ahead < R && !(T.ad.t < tstop);
+            }
+        } else
+#endif
 #pragma unroll 1
         while (true) {
             // leave when a lane needs service or a half of the ring can be flushed
@@ -570,8 +656,10 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
                     T.status = ST_MAXITERS;
                 } else {
                     --budget;
-                    const int klim = min(k + maxout - 1, nt - 1);
-                    const double tlim = A.S.ts[klim];
+                    if (k != tlim_k) {   // (a global load: only when the next output index has moved)
+                        tlim_k = k;
+                        tlim = A.S.ts[min(k + maxout - 1, nt - 1)];
+                    }
                     if (T.ad.template attempt<true>(A.S.par, T.u, tlim, A.S.tol, A.S.dtmin, accepted, A.S.ctrl, yprev, fprev)) T.status = ST_DOMAIN;
                     if (accepted)
                         ++T.nacc;

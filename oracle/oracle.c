@@ -790,7 +790,9 @@ long orc_scale_to_index(double v, double start, double stop, long len)
     if (v < start || stop < v) return 0;
     if (!(v == v)) return 0; /* NaN: the reference would throw InexactError; we drop */
     if (len == 1) return 1;
-    return (long)rint(((v - start) / (stop - start)) * (double)(len - 1) + 1);
+    double z = ((v - start) / (stop - start)) * (double)(len - 1) + 1;
+    if (!(z == z)) return 0; /* degenerate range (start == stop, len > 1): 0/0; the reference would throw InexactError; dropped */
+    return (long)rint(z);
 }
 void orc_scale_to_index_batch(const double *v, long n, double start, double stop, long len, long *idx)
 {

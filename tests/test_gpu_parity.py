@@ -95,7 +95,8 @@ def test_hermite_output_mode_matches_the_oracle(ctx, pkg, O, gold):
         out, st, ns = ctx.integrate(csys(pkg, 0, g["par"]), sol, u0, ts)
         ref, rst, acc, rej = O.integrate(O.SYS_DICKE, g["par"], u0, ts, alg=oalg, tol=1e-10, output="hermite")
         assert (st == 0).all() and (rst == 0).all()
-        assert relerr(out, ref).max() < 1e-7
+        assert relerr(out, ref).max() < 2e-5       # (Hermite error ~1e-6 at the outputs; it moves with the last-digit differences of the step sizes)
+        assert relerr(out[:, -1], ref[:, -1]).max() < 1e-8
         assert abs(ns.sum() - (acc + rej).sum()) <= 0.02 * (acc + rej).sum()
         stepped, _, ns2 = ctx.integrate(csys(pkg, 0, g["par"]), csol(pkg, alg, tol=1e-10), u0, ts)
         assert ns.sum() < 0.85 * ns2.sum() and 1e-9 < np.abs(out - stepped).max() < 1e-4
