@@ -1236,10 +1236,10 @@ struct dtwa_plan {
 struct LaunchShape {
     int block, grid, window;
     size_t smem;
-    double *ring;   // adaptive kernels: per-lane ring of observable values in global memory (L2-resident)
+    double *ring;   // adaptive kernels: ring of raw states in global memory, [grid][window][32 lanes][nvar]
 };
 
-static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const EnsArgs &A, long long n, LaunchShape &ls)
+static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const EnsArgs &A, long long n, int nvar, LaunchShape &ls)
 {
     const bool fixed = alg == DTWA_ALG_RK4 || alg == DTWA_ALG_RK8;
     const int max_threads = alg == DTWA_ALG_RK4 ? ens_launch<DTWA_ALG_RK4>::max_threads : alg == DTWA_ALG_RK8 ? ens_launch<DTWA_ALG_RK8>::max_threads : 32;
@@ -1247,16 +1247,16 @@ static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const 
     if (block > max_threads) block = max_threads;
     if (!fixed) block = 32;   // adaptive kernels: one warp per CTA (warp-level sliding flush, see ensemble_body)
     // window: output times staged between two flushes.  Fixed step: one row per warp in shared memory (<= 24 KB),
-    // one CTA-wide flush per window (16 -> 32 outputs per barrier is worth 0.6 %, measured).  Adaptive: one row per
-    // lane; the ring lives in global memory (it stays in L2: a lane writes 8 B per observable and output time) so
-    // that it can be long -- lanes only wait for each other when they drift more than half a ring apart.
+    // one CTA-wide flush per window (16 -> 32 outputs per barrier is worth 0.6 %, measured).  Adaptive: a ring of raw
+    // states in global memory (32 lanes x nvar doubles per output time and CTA), long enough (<= 256 output times, <= 1 GiB)
+    // that lanes only wait for each other when they drift more than half a ring apart; shared memory holds one row of sums.
     const size_t slots = A.nslots > 0 ? A.nslots : 1;
-    const int rows = fixed ? block / 32 : 0;   // rows of the shared-memory staging
+    const int rows = fixed ? block / 32 : 1;   // rows of the shared-memory staging
     const size_t per_out = sizeof(double) * rows * slots + sizeof(unsigned) * A.stage_bins + sizeof(unsigned);
     size_t wcap = fixed ? 32 : 256, wbudget = 24 * 1024;
     if (const char *e = std::getenv("DTWA_WINDOW")) wcap = (size_t)std::max(1, std::atoi(e));  // tuning experiments
-    int window = (int)std::max<size_t>(1, std::min<size_t>({wcap, (size_t)A.S.nt, wbudget / per_out}));
-    size_t smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, rows, window, A.stage2d_bins);
+    int window = (int)std::max<size_t>(1, std::min<size_t>({wcap, (size_t)A.S.nt, fixed ? wbudget / per_out : wcap}));
+    size_t smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, rows, fixed ? window : 1, A.stage2d_bins);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
@@ -1268,15 +1268,12 @@ static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const 
     ls.ring = nullptr;
     if (!fixed) {
         // ring length: even, <= wcap, and the whole ring buffer <= 1 GiB
-        const size_t per_ring_out = sizeof(double) * 32 * slots * (size_t)grid;
+        const size_t per_ring_out = sizeof(double) * 32 * (size_t)nvar * (size_t)grid;
         window = (int)std::max<size_t>(1, std::min<size_t>((size_t)window, ((size_t)1 << 30) / per_ring_out));
         if (window > 1) window &= ~1;
-        if (A.nslots > 0) {
-            TRY(d.ring.ensure(per_ring_out * (size_t)window));
-            d.packed_total = 0;   // (packed events of an earlier dtwa_integrate_events_packed lived here)
-            ls.ring = (double *)d.ring.p;
-        }
-        smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, rows, window, A.stage2d_bins);
+        TRY(d.ring.ensure(per_ring_out * (size_t)window));
+        d.packed_total = 0;   // (packed events of an earlier dtwa_integrate_events_packed lived here)
+        ls.ring = (double *)d.ring.p;
     }
     ls.window = window;
     ls.block = block;
@@ -1600,7 +1597,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
             A.ranges = (const RangeD *)(m + o_r);
             A.hists = (const HistDesc *)(m + o_h);
             A.u64 = dp.d_u64;
-            TRY(shape_for(ctx, d, kern, sol->alg, A, dp.n, shapes[di]));
+            TRY(shape_for(ctx, d, kern, sol->alg, A, dp.n, nv, shapes[di]));
             dp.grid = shapes[di].grid;
             dp.block = shapes[di].block;
             const size_t pbytes = sizeof(double) * (size_t)dp.grid * nt * std::max(nslots, 1);

@@ -904,7 +904,9 @@ __device__ __forceinline__ int scale_to_index(double v, const RangeD &r)
     const double k = rint(y);
     if (0.5 - fabs(y - k) > y * 0x1p-48) return (int)k;
     const double x = __ddiv_rn(d, __dsub_rn(r.stop, r.start));
-    return (int)rint(__dadd_rn(__dmul_rn(x, r.lenm1), 1.0));
+    const double z = __dadd_rn(__dmul_rn(x, r.lenm1), 1.0);
+    if (!(z == z)) return 0;   // degenerate range (start == stop, len > 1): 0/0 -- the reference would throw; dropped
+    return (int)rint(z);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -156,7 +156,7 @@ struct EnsArgs {
     const double *consts;
     const RangeD *ranges;
     const HistDesc *hists;
-    double *ring;             // adaptive kernels: [grid][32 lanes][window][nslots] staging ring (global memory), or NULL
+    double *ring;             // adaptive kernels: [grid][window][32 lanes][NVO] ring of raw states (global memory)
     double *partial;          // [grid][nt][nslots]
     unsigned long long *u64;  // [CNT_N | n_valid[nt] | histograms...]
 };
@@ -377,15 +377,20 @@ __device__ __forceinline__ void jit_reduce(const VmShared &V, const SamplerPar *
 // Adaptive pairs: ONE warp per CTA (the host launches 32 threads).  Each lane integrates its own STREAM of
 // trajectories -- lane l of CTA c takes trajectories (c*32 + l) + m*gridDim*32, m = 0, 1, ... -- and numbers the output
 // times of the stream g = m*nt + k.  In every iteration of the flat loop each lane that owes a step attempts ONE
-// step; a lane that has reached its next output time emits it into its own row of a ring of R <= 256 outputs in
-// global memory (A.ring; 8 B per observable and output, it stays in L2) and, at the end of a trajectory, draws the
-// next one without waiting for the other lanes.  The ring is flushed in halves, in the order of g, as soon as the
-// slowest lane has passed a half: sums over the lanes in lane order, then one RED per (time, slot) into the CTA's
-// partial row -- the same values in the same order in every run.  A lane only waits when it is more than R/2 .. R
-// outputs ahead of the slowest lane of its warp.
+// step; a lane that has reached its next output time stores its STATE (the observables' coordinates, 8 NVO bytes) into
+// its cell of a ring of R <= 256 outputs in global memory (A.ring, layout [w][lane][NVO]; 0.5 GB at most -- larger than
+// L2, it streams through DRAM at ~60 GB/s, 1 % of the HBM bandwidth) and, at the end of a trajectory, draws the next one
+// without waiting for the other lanes.  Observables and reducers do NOT run when a lane emits -- lanes emit at different
+// iterations, so that code would run in almost every iteration with 2-3 active lanes (ncu: 93 % of the iterations, 8-12 %
+// of a warp's time) -- but when the ring is flushed: in halves, in the order of g, as soon as the slowest lane has
+// passed a half, the whole warp reads one output time per step (a coalesced 1 KB row), every lane evaluates the reducer
+// program for its cell, sums go through the shuffle tree of the fixed-step kernels and one RED per (time, slot) into the
+// CTA's partial row -- the same values in the same order in every run.  An empty cell (lane failed, skipped, ran out of
+// trajectories, or re-draws a trajectory that contributes only from a later time on) holds a NaN marker.  A lane only
+// waits when it is more than R/2 .. R outputs ahead of the slowest lane of its warp.
 template <int SYS, int ALG, bool JIT>
 __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared &V, double *my_partial,
-                                                unsigned long long *nvalid_g)
+                                                unsigned long long *nvalid_g, double *ring)
 {
     constexpr int NV = Sys<SYS>::NV, NVO = Sys<SYS>::NVO;
     const int lane = threadIdx.x & 31;
@@ -411,26 +416,47 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
 #pragma unroll
     for (int i = 0; i < NV; ++i) T.u[i] = 0.0;
 
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    double *mycell = ring + (size_t)lane * NVO;     // this lane's cell of ring slot 0; slot w is 32 * NVO doubles further per w
     auto flush_half = [&](long long f0, long long f1) {   // stream outputs [f0, f1), executed by the whole warp, fixed order
         __syncwarp();
-        const int cnt = (int)(f1 - f0), w0 = (int)(f0 % R), k0 = (int)(f0 % nt);
-        for (int i = lane; i < cnt * A.nslots; i += 32) {
-            const int o = i / A.nslots, sl = i % A.nslots, w = (w0 + o) % R, kq = (k0 + o) % nt;
-            double s = 0.0;
-            for (int rw = 0; rw < 32; ++rw) {
-                double *cell = &V.wsum[((size_t)rw * W + w) * A.nslots + sl];
-                s = __dadd_rn(s, *cell);
-                *cell = 0.0;  // lanes that failed, skipped or ran out of trajectories leave zeros behind
+        const int cnt = (int)(f1 - f0);
+        int w = (int)(f0 % R), kq = (int)(f0 % nt);
+        for (int o = 0; o < cnt; ++o) {
+            double *cell = mycell + (size_t)w * (32 * NVO);
+            double x[4] = {0.0, 0.0, 0.0, 0.0};
+            if constexpr (NVO == 4) {
+                const double2 a = *reinterpret_cast<const double2 *>(cell), b = *reinterpret_cast<const double2 *>(cell + 2);
+                x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+            } else {
+                const double2 a = *reinterpret_cast<const double2 *>(cell);
+                x[0] = a.x; x[1] = a.y;
             }
-            atomicAdd(&my_partial[(size_t)kq * A.nslots + sl], s);
+            const bool valid = (x[0] == x[0]);
+            cell[0] = qnan;   // the cell is free again
+            if constexpr (JIT)
+                jit_reduce<NVO, false>(V, &A.smp, A.u64, x[0], x[1], x[2], x[3], valid, kq, 0);
+            else
+                vm_run<NVO, false>(V, &A.smp, A.u64, x[0], x[1], x[2], x[3], valid, kq, 0, nullptr);
+            __syncwarp();
+            for (int sl = lane; sl < A.nslots; sl += 32) atomicAdd(&my_partial[(size_t)kq * A.nslots + sl], V.wsum[sl]);
+            const unsigned vb = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0 && vb) atomicAdd(&nvalid_g[kq], (unsigned long long)__popc(vb));
+            __syncwarp();
+            w = (w + 1 == R) ? 0 : w + 1;
+            kq = (kq + 1 == nt) ? 0 : kq + 1;
         }
-        for (int i = lane; i < cnt; i += 32) {
-            const int w = (w0 + i) % R;
-            const unsigned c = V.nvalid[w];
-            if (c) atomicAdd(&nvalid_g[(k0 + i) % nt], (unsigned long long)c);
-            V.nvalid[w] = 0u;
-        }
-        __syncwarp();
+    };
+    auto emit_state = [&](const double (&uo)[NV], bool valid, int wslot_) {   // the lane's state at an output time -> its ring cell
+        if (!valid) return;
+        double xo[NVO];
+        from_chart<SYS>(uo, xo);
+        double *cell = mycell + (size_t)wslot_ * (32 * NVO);
+        if constexpr (NVO == 4) {
+            *reinterpret_cast<double2 *>(cell) = make_double2(xo[0], xo[1]);
+            *reinterpret_cast<double2 *>(cell + 2) = make_double2(xo[2], xo[3]);
+        } else
+            *reinterpret_cast<double2 *>(cell) = make_double2(xo[0], xo[1]);
     };
 
 #pragma unroll 1
@@ -510,7 +536,7 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
         // (lane-local 32-bit bookkeeping: `ahead` = outputs this lane is ahead of the flushed part of the ring, `budget` = attempts
         //  left before maxiters; one REDUX decides whether to leave)
         int ahead = have ? (int)(g - flushed) : 0;
-#ifndef DTWA_NO_PIPELINED_LOOP
+#ifdef DTWA_PIPELINED_LOOP   // (opt-in experiment, measured 0-3 % SLOWER except DP5 +3.6 %: ptxas keeps the emit block behind a branch)
         if (JIT && !A.S.interp) {
             // ---- software-pipelined form (specialised kernels, outputs by stepping onto ts[k]) ----
             // An attempt ends in a serial, latency-bound tail -- error norm -> controller -> commit -> emit -> vote -- during
@@ -530,12 +556,7 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
                 if ((vote & 1u) || !(vote & 2u)) break;
                 ++iters;
                 {   // [E] the output reached in the previous iteration (state T.u is still the one that landed on ts[k])
-                    double xo[NVO];
-                    from_chart<SYS>(T.u, xo);
-                    const bool valid = pend && (k >= start_k);
-                    jit_reduce<NVO, true>(V, &A.smp, A.u64, xo[0], xo[1], NVO == 4 ? xo[NVO - 2] : 0.0, NVO == 4 ? xo[NVO - 1] : 0.0, valid, k, wslot,
-                                          pend);
-                    if (valid) atomicAdd(&V.nvalid[wslot], 1u);
+                    emit_state(T.u, pend && (k >= start_k), wslot);
                     if (pend) {
                         ++k;
                         ++ahead;
@@ -617,27 +638,8 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
                 }
             }
             const bool reached = stepping && T.status == ST_OK && !(T.ad.t < tstop);   // this lane emits output k now
-            const bool valid = reached && (k >= start_k);
-            if constexpr (JIT) {
-                if (reached) {
-                    double xo[NVO];
-                    from_chart<SYS>(T.u, xo);   // the observables' coordinates (the identity except in the Bloch chart)
-                    jit_reduce<NVO, true>(V, &A.smp, A.u64, xo[0], xo[1], NVO == 4 ? xo[NVO - 2] : 0.0, NVO == 4 ? xo[NVO - 1] : 0.0, valid, k,
-                                          wslot);
-                }
-            } else {
-                // the interpreter's per-instruction loop is run by the WHOLE warp whenever some lane emits (lanes that do
-                // not emit are masked): run by the emitting lanes alone it left the warp split in two groups that then
-                // executed the step body one after the other (1.66 body executions per iteration at 18 active lanes)
-                if (__any_sync(0xffffffffu, reached)) {
-                    double xo[NVO];
-                    from_chart<SYS>(T.u, xo);
-                    vm_run<NVO, true>(V, &A.smp, A.u64, xo[0], xo[1], NVO == 4 ? xo[NVO - 2] : 0.0, NVO == 4 ? xo[NVO - 1] : 0.0, valid, k, wslot,
-                                      nullptr, reached);
-                }
-            }
             if (reached) {
-                if (valid) atomicAdd(&V.nvalid[wslot], 1u);
+                emit_state(T.u, k >= start_k, wslot);
                 ++k;
                 ++ahead;
                 wslot = (wslot + 1 == R) ? 0 : wslot + 1;
@@ -669,39 +671,25 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
             }
             // outputs due: after an accepted step all ts[k] <= t (interpolated); before the first step the ones at t = 0
             bool due = stepping && T.status == ST_OK && k < nt && !(T.ad.t < tstop);
-            while (JIT ? due : __any_sync(0xffffffffu, due)) {
+            while (due) {
                 double uo[NV];
-                if (due) {
-                    if (accepted && tstop < T.ad.t) {
-                        const double theta = (tstop - (T.ad.t - T.ad.hlast)) / T.ad.hlast;
-                        hermite_interpolant<NV>(yprev, fprev, T.u, T.ad.k0, T.ad.hlast, theta, uo);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < NV; ++i) uo[i] = T.u[i];
-                    }
-                    if (state_bad<SYS>(uo)) {   // the interpolated state left the chart: the trajectory fails at this output
-                        T.status = ST_DOMAIN;
-                        due = false;
-                    }
-                }
-                const bool valid = due && (k >= start_k);
-                double xo[NVO];
-                if (due || !JIT) from_chart<SYS>(uo, xo);
-                if constexpr (JIT) {
-                    if (due)
-                        jit_reduce<NVO, true>(V, &A.smp, A.u64, xo[0], xo[1], NVO == 4 ? xo[NVO - 2] : 0.0, NVO == 4 ? xo[NVO - 1] : 0.0, valid, k, wslot);
+                if (accepted && tstop < T.ad.t) {
+                    const double theta = (tstop - (T.ad.t - T.ad.hlast)) / T.ad.hlast;
+                    hermite_interpolant<NV>(yprev, fprev, T.u, T.ad.k0, T.ad.hlast, theta, uo);
                 } else {
-                    vm_run<NVO, true>(V, &A.smp, A.u64, xo[0], xo[1], NVO == 4 ? xo[NVO - 2] : 0.0, NVO == 4 ? xo[NVO - 1] : 0.0, valid, k, wslot,
-                                      nullptr, due);
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) uo[i] = T.u[i];
                 }
-                if (due) {
-                    if (valid) atomicAdd(&V.nvalid[wslot], 1u);
-                    ++k;
-                    ++ahead;
-                    wslot = (wslot + 1 == R) ? 0 : wslot + 1;
-                    if (k < nt) tstop = A.S.ts[k];
-                    due = k < nt && !(T.ad.t < tstop);
+                if (state_bad<SYS>(uo)) {   // the interpolated state left the chart: the trajectory fails at this output
+                    T.status = ST_DOMAIN;
+                    break;
                 }
+                emit_state(uo, k >= start_k, wslot);
+                ++k;
+                ++ahead;
+                wslot = (wslot + 1 == R) ? 0 : wslot + 1;
+                if (k < nt) tstop = A.S.ts[k];
+                due = k < nt && !(T.ad.t < tstop);
             }
             }
         }
@@ -731,9 +719,10 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
     constexpr bool FIXED = is_fixed<ALG>::value;
     constexpr bool PERLANE = !FIXED;  // adaptive: one staging row per thread, no warp-level reduction
     const int nwarps = blockDim.x >> 5;
-    const int rows = PERLANE ? 0 : nwarps;   // rows of the shared-memory staging (adaptive kernels stage in A.ring)
+    const int rows = nwarps;   // rows of the shared-memory staging (adaptive kernels: one warp, one row of one output time)
     const int lane = threadIdx.x & 31;
     const int W = A.window;
+    const int Ws = PERLANE ? 1 : W;   // output times staged in SHARED memory (the adaptive kernels' ring lives in global memory)
 
     // ---- carve shared memory and stage the reducer program ----
     VmShared V;
@@ -746,11 +735,11 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
         HistDesc *hists = reinterpret_cast<HistDesc *>(p);
         p += sizeof(HistDesc) * A.nhist;
         V.wsum = reinterpret_cast<double *>(p);
-        p += sizeof(double) * (size_t)rows * W * (A.nslots > 0 ? A.nslots : 1);
+        p += sizeof(double) * (size_t)rows * Ws * (A.nslots > 0 ? A.nslots : 1);
         V.stage = reinterpret_cast<unsigned *>(p);
-        p += sizeof(unsigned) * (size_t)W * A.stage_bins;
+        p += sizeof(unsigned) * (size_t)Ws * A.stage_bins;
         V.nvalid = reinterpret_cast<unsigned *>(p);
-        p += sizeof(unsigned) * W;
+        p += sizeof(unsigned) * Ws;
         V.stage2d = reinterpret_cast<unsigned *>(p);
         p += sizeof(unsigned) * A.stage2d_bins;
         VmIns *prog = reinterpret_cast<VmIns *>(p);
@@ -758,13 +747,12 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
         for (int i = threadIdx.x; i < A.nrange; i += blockDim.x) ranges[i] = A.ranges[i];
         for (int i = threadIdx.x; i < A.nhist; i += blockDim.x) hists[i] = A.hists[i];
         for (int i = threadIdx.x; i < A.nins; i += blockDim.x) prog[i] = A.prog[i];
-        for (int i = threadIdx.x; i < W * A.stage_bins; i += blockDim.x) V.stage[i] = 0u;
-        for (int i = threadIdx.x; i < W; i += blockDim.x) V.nvalid[i] = 0u;
+        for (int i = threadIdx.x; i < Ws * A.stage_bins; i += blockDim.x) V.stage[i] = 0u;
+        for (int i = threadIdx.x; i < Ws; i += blockDim.x) V.nvalid[i] = 0u;
         for (int i = threadIdx.x; i < A.stage2d_bins; i += blockDim.x) V.stage2d[i] = 0u;
-        if constexpr (PERLANE) {   // one row per lane, in global memory (stays in L2)
-            V.wsum = A.ring + (size_t)blockIdx.x * 32 * W * A.nslots;
-            if (A.nslots > 0)
-                for (int i = threadIdx.x; i < 32 * W * A.nslots; i += blockDim.x) V.wsum[i] = 0.0;
+        if constexpr (PERLANE) {   // the CTA's ring of raw states in global memory: every cell starts empty (NaN marker)
+            double *ring = A.ring + (size_t)blockIdx.x * 32 * W * Sys<SYS>::NVO;
+            for (int i = threadIdx.x; i < 32 * W; i += blockDim.x) ring[(size_t)i * Sys<SYS>::NVO] = __longlong_as_double(0x7ff8000000000000ll);
         }
         V.consts = consts;
         V.ranges = ranges;
@@ -773,7 +761,7 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
         V.nslots = A.nslots;
         V.stage_bins = A.stage_bins;
         V.nwarps = nwarps;
-        V.window = W;
+        V.window = Ws;
     }
     __syncthreads();
 
@@ -813,7 +801,7 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
     long long batches_done = 0;
 
     if constexpr (!FIXED) {
-        adaptive_stream<SYS, ALG, JIT>(A, V, my_partial, nvalid_g);
+        adaptive_stream<SYS, ALG, JIT>(A, V, my_partial, nvalid_g, A.ring + (size_t)blockIdx.x * 32 * W * Sys<SYS>::NVO);
     } else {
     // ---- fixed step: persistent loop over batches of blockDim.x trajectories ----
     for (long long batch = blockIdx.x; batch * (long long)blockDim.x < A.N; batch += gridDim.x) {
