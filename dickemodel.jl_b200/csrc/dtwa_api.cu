@@ -1251,7 +1251,7 @@ static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const 
     // states in global memory (32 lanes x nvar doubles per output time and CTA), long enough (<= 256 output times, <= 1 GiB)
     // that lanes only wait for each other when they drift more than half a ring apart; shared memory holds one row of sums.
     const size_t slots = A.nslots > 0 ? A.nslots : 1;
-    const int rows = fixed ? block / 32 : 1;   // rows of the shared-memory staging
+    const int rows = fixed ? block / 32 : 32;   // rows of the shared-memory staging (adaptive: one row of sums per lane for the ring flush)
     const size_t per_out = sizeof(double) * rows * slots + sizeof(unsigned) * A.stage_bins + sizeof(unsigned);
     size_t wcap = fixed ? 32 : 256, wbudget = 24 * 1024;
     if (const char *e = std::getenv("DTWA_WINDOW")) wcap = (size_t)std::max(1, std::atoi(e));  // tuning experiments

@@ -302,8 +302,8 @@ __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp,
         case OP_ABS: acc = fabs(acc); break;
         case OP_SUM: {
             double v = valid ? acc : 0.0;
-            if constexpr (PERLANE) {
-                if (emit) V.wsum[((size_t)threadIdx.x * V.window + w) * V.nslots + in.b] = v;
+            if constexpr (PERLANE) {   // adaptive kernels' flush: every lane accumulates one output time in its own row
+                if (emit) V.wsum[(size_t)threadIdx.x * V.nslots + in.b] += v;
             } else {
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
@@ -419,33 +419,44 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
     double *mycell = ring + (size_t)lane * NVO;     // this lane's cell of ring slot 0; slot w is 32 * NVO doubles further per w
     auto flush_half = [&](long long f0, long long f1) {   // stream outputs [f0, f1), executed by the whole warp, fixed order
+        // lane l takes output time f0 + c + l of every chunk c of 32 and walks over the 32 lanes' cells of that time in lane
+        // order: no shuffles, no barrier per output, a fixed summation order, one RED per (time, slot)
         __syncwarp();
         const int cnt = (int)(f1 - f0);
-        int w = (int)(f0 % R), kq = (int)(f0 % nt);
-        for (int o = 0; o < cnt; ++o) {
-            double *cell = mycell + (size_t)w * (32 * NVO);
-            double x[4] = {0.0, 0.0, 0.0, 0.0};
-            if constexpr (NVO == 4) {
-                const double2 a = *reinterpret_cast<const double2 *>(cell), b = *reinterpret_cast<const double2 *>(cell + 2);
-                x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
-            } else {
-                const double2 a = *reinterpret_cast<const double2 *>(cell);
-                x[0] = a.x; x[1] = a.y;
+        const int w0 = (int)(f0 % R), k0 = (int)(f0 % nt);
+        double *row = V.wsum + (size_t)lane * A.nslots;
+        for (int c = 0; c < cnt; c += 32) {
+            const int o = c + lane;
+            const bool mine = o < cnt;
+            const int w = (w0 + o) % R, kq = (k0 + o) % nt;
+            for (int sl = 0; sl < A.nslots; ++sl) row[sl] = 0.0;
+            unsigned nv = 0;
+            for (int r = 0; r < 32; ++r) {
+                double *cell = ring + ((size_t)w * 32 + r) * NVO;
+                double x[4] = {qnan, 0.0, 0.0, 0.0};
+                if (mine) {
+                    if constexpr (NVO == 4) {
+                        const double2 a = *reinterpret_cast<const double2 *>(cell), b = *reinterpret_cast<const double2 *>(cell + 2);
+                        x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+                    } else {
+                        const double2 a = *reinterpret_cast<const double2 *>(cell);
+                        x[0] = a.x; x[1] = a.y;
+                    }
+                    cell[0] = qnan;   // the cell is free again
+                }
+                const bool valid = (x[0] == x[0]);
+                nv += valid ? 1u : 0u;
+                if constexpr (JIT)
+                    jit_reduce<NVO, true>(V, &A.smp, A.u64, x[0], x[1], x[2], x[3], valid, kq, 0, valid);
+                else
+                    vm_run<NVO, true>(V, &A.smp, A.u64, x[0], x[1], x[2], x[3], valid, kq, 0, nullptr, valid);
             }
-            const bool valid = (x[0] == x[0]);
-            cell[0] = qnan;   // the cell is free again
-            if constexpr (JIT)
-                jit_reduce<NVO, false>(V, &A.smp, A.u64, x[0], x[1], x[2], x[3], valid, kq, 0);
-            else
-                vm_run<NVO, false>(V, &A.smp, A.u64, x[0], x[1], x[2], x[3], valid, kq, 0, nullptr);
-            __syncwarp();
-            for (int sl = lane; sl < A.nslots; sl += 32) atomicAdd(&my_partial[(size_t)kq * A.nslots + sl], V.wsum[sl]);
-            const unsigned vb = __ballot_sync(0xffffffffu, valid);
-            if (lane == 0 && vb) atomicAdd(&nvalid_g[kq], (unsigned long long)__popc(vb));
-            __syncwarp();
-            w = (w + 1 == R) ? 0 : w + 1;
-            kq = (kq + 1 == nt) ? 0 : kq + 1;
+            if (mine) {
+                for (int sl = 0; sl < A.nslots; ++sl) atomicAdd(&my_partial[(size_t)kq * A.nslots + sl], row[sl]);
+                if (nv) atomicAdd(&nvalid_g[kq], (unsigned long long)nv);
+            }
         }
+        __syncwarp();
     };
     auto emit_state = [&](const double (&uo)[NV], bool valid, int wslot_) {   // the lane's state at an output time -> its ring cell
         if (!valid) return;
@@ -719,7 +730,7 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
     constexpr bool FIXED = is_fixed<ALG>::value;
     constexpr bool PERLANE = !FIXED;  // adaptive: one staging row per thread, no warp-level reduction
     const int nwarps = blockDim.x >> 5;
-    const int rows = nwarps;   // rows of the shared-memory staging (adaptive kernels: one warp, one row of one output time)
+    const int rows = PERLANE ? 32 : nwarps;   // rows of the shared-memory staging (adaptive kernels: one row of sums per LANE, used by the ring flush)
     const int lane = threadIdx.x & 31;
     const int W = A.window;
     const int Ws = PERLANE ? 1 : W;   // output times staged in SHARED memory (the adaptive kernels' ring lives in global memory)
