@@ -1867,6 +1867,40 @@ extern "C" int dtwa_fp64_peak_regs(dtwa_ctx *ctx, double *tflops, double *ms_out
     return DTWA_OK;
 }
 
+// K0c: DFMA rate with `chains` independent chains per thread and `warps_per_sm` one-warp CTAs per SM (chains in {1,2,4,8,16})
+extern "C" int dtwa_fp64_chains(dtwa_ctx *ctx, int chains, int warps_per_sm, double *tflops, double *ms_out)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    if (warps_per_sm < 1 || warps_per_sm > 32) return set_err(DTWA_ERR_INVALID, "warps_per_sm must be in [1, 32]");
+    DevCtx &d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    const int block = 32, grid = d.sm_count * warps_per_sm, iters = 16384;
+    TRY(d.scratch_a.ensure(sizeof(double) * (size_t)grid * block));
+    double best = 1e30;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(d.ev[0], d.stream));
+        double *o = (double *)d.scratch_a.p;
+        switch (chains) {
+        case 1: fp64_chains_kernel<1><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7); break;
+        case 2: fp64_chains_kernel<2><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7); break;
+        case 4: fp64_chains_kernel<4><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7); break;
+        case 8: fp64_chains_kernel<8><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7); break;
+        case 16: fp64_chains_kernel<16><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7); break;
+        default: return set_err(DTWA_ERR_INVALID, "chains must be 1, 2, 4, 8 or 16");
+        }
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(d.ev[3], d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+        float m = 0.f;
+        CK(cudaEventElapsedTime(&m, d.ev[0], d.ev[3]));
+        if (rep > 0 && m < best) best = m;
+    }
+    const double flops = (double)grid * block * (double)iters * 64.0 * 2.0;
+    if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return DTWA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Compile-only check of the run-time specialisation (needs libnvrtc but no GPU): generates the
 // specialised source for `nexpr` averaged observables, compiles it for sm_100a and reports the

@@ -431,25 +431,41 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
             const int w = (w0 + o) % R, kq = (k0 + o) % nt;
             for (int sl = 0; sl < A.nslots; ++sl) row[sl] = 0.0;
             unsigned nv = 0;
-            for (int r = 0; r < 32; ++r) {
-                double *cell = ring + ((size_t)w * 32 + r) * NVO;
-                double x[4] = {qnan, 0.0, 0.0, 0.0};
-                if (mine) {
-                    if constexpr (NVO == 4) {
-                        const double2 a = *reinterpret_cast<const double2 *>(cell), b = *reinterpret_cast<const double2 *>(cell + 2);
-                        x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+            constexpr int RB = JIT ? 8 : 2;   // cells in flight per lane: the scattered 32-byte loads of a batch overlap (one DRAM round trip per
+                                              // batch); the interpreter's reducer call is large, so its loop is unrolled only twice
+#pragma unroll 1
+            for (int r0 = 0; r0 < 32; r0 += RB) {
+                double xa[RB][NVO];
+#pragma unroll
+                for (int q = 0; q < RB; ++q) {
+                    const double *cell = ring + ((size_t)w * 32 + (r0 + q)) * NVO;
+                    if (mine) {
+                        if constexpr (NVO == 4) {
+                            const double2 a = __ldcg(reinterpret_cast<const double2 *>(cell)), b = __ldcg(reinterpret_cast<const double2 *>(cell + 2));
+                            xa[q][0] = a.x; xa[q][1] = a.y; xa[q][2] = b.x; xa[q][3] = b.y;
+                        } else {
+                            const double2 a = __ldcg(reinterpret_cast<const double2 *>(cell));
+                            xa[q][0] = a.x; xa[q][1] = a.y;
+                        }
                     } else {
-                        const double2 a = *reinterpret_cast<const double2 *>(cell);
-                        x[0] = a.x; x[1] = a.y;
+#pragma unroll
+                        for (int i = 0; i < NVO; ++i) xa[q][i] = qnan;
                     }
-                    cell[0] = qnan;   // the cell is free again
                 }
-                const bool valid = (x[0] == x[0]);
-                nv += valid ? 1u : 0u;
-                if constexpr (JIT)
-                    jit_reduce<NVO, true>(V, &A.smp, A.u64, x[0], x[1], x[2], x[3], valid, kq, 0, valid);
-                else
-                    vm_run<NVO, true>(V, &A.smp, A.u64, x[0], x[1], x[2], x[3], valid, kq, 0, nullptr, valid);
+#pragma unroll
+                for (int q = 0; q < RB; ++q)
+                    if (mine) ring[((size_t)w * 32 + (r0 + q)) * NVO] = qnan;   // the cells are free again
+#pragma unroll
+                for (int q = 0; q < RB; ++q) {
+                    const bool valid = (xa[q][0] == xa[q][0]);
+                    nv += valid ? 1u : 0u;
+                    if constexpr (JIT)
+                        jit_reduce<NVO, true>(V, &A.smp, A.u64, xa[q][0], xa[q][1], NVO == 4 ? xa[q][NVO - 2] : 0.0, NVO == 4 ? xa[q][NVO - 1] : 0.0, valid, kq,
+                                              0, valid);
+                    else
+                        vm_run<NVO, true>(V, &A.smp, A.u64, xa[q][0], xa[q][1], NVO == 4 ? xa[q][NVO - 2] : 0.0, NVO == 4 ? xa[q][NVO - 1] : 0.0, valid, kq, 0,
+                                          nullptr, valid);
+                }
             }
             if (mine) {
                 for (int sl = 0; sl < A.nslots; ++sl) atomicAdd(&my_partial[(size_t)kq * A.nslots + sl], row[sl]);
@@ -1836,6 +1852,29 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
         }
     }
     const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// K0c: CHAINS independent DFMA chains per thread, one warp per CTA, any number of CTAs per SM -- how much of the FP64 pipe
+// a given (instruction-level parallelism x warps per scheduler) can keep busy.  The adaptive kernels run 3 warps per
+// scheduler with 4 independent chains in their stage sums; this kernel reproduces exactly that shape without anything else.
+template <int CHAINS>
+__global__ void __launch_bounds__(32) fp64_chains_kernel(double *out, int iters, double a, double b)
+{
+    double x[CHAINS];
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) x[c] = threadIdx.x * 1e-3 + c;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 64 / CHAINS; ++r) {
+#pragma unroll
+            for (int c = 0; c < CHAINS; ++c) x[c] = fma(x[c], a, b);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) s += x[c];
     if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 

@@ -333,6 +333,9 @@ int dtwa_plan_free(dtwa_plan *plan);
 int dtwa_fp64_peak(dtwa_ctx *ctx, double *tflops, double *ms);
 /* K0b: the same with three distinct register operands per DFMA (the practical ceiling of an ODE kernel) */
 int dtwa_fp64_peak_regs(dtwa_ctx *ctx, double *tflops, double *ms);
+/* K0c: the DFMA rate that `chains` independent chains per thread reach with `warps_per_sm` one-warp CTAs per SM --
+ * the shape of the adaptive kernels (3 warps per scheduler, 4 chains) without anything else; a profiling aid. */
+int dtwa_fp64_chains(dtwa_ctx *ctx, int chains, int warps_per_sm, double *tflops, double *ms_out);
 
 #ifdef __cplusplus
 }
