@@ -125,7 +125,7 @@ def load():
         L.dtwa_plan_free.argtypes = [vp]
         L.dtwa_fp64_peak.argtypes = [vp, dp, dp]
         L.dtwa_fp64_peak_regs.argtypes = [vp, dp, dp]
-        L.dtwa_fp64_chains.argtypes = [vp, C.c_int, C.c_int, dp, dp]
+        L.dtwa_fp64_chains.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp]
         L.dtwa_jit_quiesce.argtypes = []
         import atexit
         atexit.register(L.dtwa_jit_quiesce)   # no thread may be inside libnvrtc when the process tears it down
@@ -206,9 +206,9 @@ class Context:
         _check(load().dtwa_fp64_peak(self._h, C.byref(tf), C.byref(ms)))
         return tf.value, ms.value
 
-    def fp64_chains(self, chains, warps_per_sm):
+    def fp64_chains(self, chains, warps_per_sm, nreg=1):
         tf, ms = C.c_double(), C.c_double()
-        _check(load().dtwa_fp64_chains(self._h, int(chains), int(warps_per_sm), C.byref(tf), C.byref(ms)))
+        _check(load().dtwa_fp64_chains(self._h, int(chains), int(warps_per_sm), int(nreg), C.byref(tf), C.byref(ms)))
         return tf.value, ms.value
 
     def fp64_peak_regs(self):

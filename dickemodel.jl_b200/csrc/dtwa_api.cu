@@ -1868,26 +1868,39 @@ extern "C" int dtwa_fp64_peak_regs(dtwa_ctx *ctx, double *tflops, double *ms_out
 }
 
 // K0c: DFMA rate with `chains` independent chains per thread and `warps_per_sm` one-warp CTAs per SM (chains in {1,2,4,8,16})
-extern "C" int dtwa_fp64_chains(dtwa_ctx *ctx, int chains, int warps_per_sm, double *tflops, double *ms_out)
+extern "C" int dtwa_fp64_chains(dtwa_ctx *ctx, int chains, int warps_per_sm, int nreg, double *tflops, double *ms_out)
 {
     if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
     if (warps_per_sm < 1 || warps_per_sm > 32) return set_err(DTWA_ERR_INVALID, "warps_per_sm must be in [1, 32]");
+    if (nreg < 1 || nreg > 3) return set_err(DTWA_ERR_INVALID, "nreg must be 1, 2 or 3");
     DevCtx &d = ctx->devs[0];
     CK(cudaSetDevice(d.device));
     const int block = 32, grid = d.sm_count * warps_per_sm, iters = 16384;
     TRY(d.scratch_a.ensure(sizeof(double) * (size_t)grid * block));
+    TRY(d.scratch_b.ensure(sizeof(double) * 64));
+    double host[64];
+    for (int i = 0; i < 64; ++i) host[i] = 1.0 + 1e-3 * i;
+    CK(cudaMemcpyAsync(d.scratch_b.p, host, sizeof(host), cudaMemcpyHostToDevice, d.stream));
     double best = 1e30;
     for (int rep = 0; rep < 4; ++rep) {
         CK(cudaEventRecord(d.ev[0], d.stream));
         double *o = (double *)d.scratch_a.p;
+        const double *in = (const double *)d.scratch_b.p;
+#define DTWA_CHAINS_CASE(C)                                                                                              \
+    case C:                                                                                                              \
+        if (nreg == 1) fp64_chains_kernel<C, 1><<<grid, block, 0, d.stream>>>(o, in, iters, 0.999999, 1e-7);              \
+        else if (nreg == 2) fp64_chains_kernel<C, 2><<<grid, block, 0, d.stream>>>(o, in, iters, 0.999999, 1e-7);         \
+        else fp64_chains_kernel<C, 3><<<grid, block, 0, d.stream>>>(o, in, iters, 0.999999, 1e-7);                        \
+        break;
         switch (chains) {
-        case 1: fp64_chains_kernel<1><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7); break;
-        case 2: fp64_chains_kernel<2><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7); break;
-        case 4: fp64_chains_kernel<4><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7); break;
-        case 8: fp64_chains_kernel<8><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7); break;
-        case 16: fp64_chains_kernel<16><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7); break;
+            DTWA_CHAINS_CASE(1)
+            DTWA_CHAINS_CASE(2)
+            DTWA_CHAINS_CASE(4)
+            DTWA_CHAINS_CASE(8)
+            DTWA_CHAINS_CASE(16)
         default: return set_err(DTWA_ERR_INVALID, "chains must be 1, 2, 4, 8 or 16");
         }
+#undef DTWA_CHAINS_CASE
         CK(cudaGetLastError());
         CK(cudaEventRecord(d.ev[3], d.stream));
         CK(cudaStreamSynchronize(d.stream));

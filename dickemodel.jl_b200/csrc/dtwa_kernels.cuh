@@ -1858,18 +1858,31 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 // K0c: CHAINS independent DFMA chains per thread, one warp per CTA, any number of CTAs per SM -- how much of the FP64 pipe
 // a given (instruction-level parallelism x warps per scheduler) can keep busy.  The adaptive kernels run 3 warps per
 // scheduler with 4 independent chains in their stage sums; this kernel reproduces exactly that shape without anything else.
-template <int CHAINS>
-__global__ void __launch_bounds__(32) fp64_chains_kernel(double *out, int iters, double a, double b)
+template <int CHAINS, int NREG>
+__global__ void __launch_bounds__(32) fp64_chains_kernel(double *out, const double *in, int iters, double a, double b)
 {
-    double x[CHAINS];
+    // NREG distinct vector-register operands per DFMA: 1 = x*a + b (a, b warp-uniform: K0's form), 2 = x*a + y (the form of a
+    // stage sum: coefficient uniform, stage value and accumulator in registers), 3 = x*z + y
+    double x[CHAINS], y[CHAINS], z[CHAINS];
 #pragma unroll
-    for (int c = 0; c < CHAINS; ++c) x[c] = threadIdx.x * 1e-3 + c;
+    for (int c = 0; c < CHAINS; ++c) {
+        x[c] = threadIdx.x * 1e-3 + c;
+        y[c] = in[(threadIdx.x + c) & 63] * 1e-7;
+        z[c] = 1.0 - in[(threadIdx.x + 2 * c + 1) & 63] * 1e-6;
+    }
 #pragma unroll 1
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int r = 0; r < 64 / CHAINS; ++r) {
 #pragma unroll
-            for (int c = 0; c < CHAINS; ++c) x[c] = fma(x[c], a, b);
+            for (int c = 0; c < CHAINS; ++c) {
+                if constexpr (NREG == 1)
+                    x[c] = fma(x[c], a, b);
+                else if constexpr (NREG == 2)
+                    x[c] = fma(x[c], a, y[c]);
+                else
+                    x[c] = fma(x[c], z[c], y[c]);
+            }
         }
     }
     double s = 0.0;

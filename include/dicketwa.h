@@ -334,8 +334,9 @@ int dtwa_fp64_peak(dtwa_ctx *ctx, double *tflops, double *ms);
 /* K0b: the same with three distinct register operands per DFMA (the practical ceiling of an ODE kernel) */
 int dtwa_fp64_peak_regs(dtwa_ctx *ctx, double *tflops, double *ms);
 /* K0c: the DFMA rate that `chains` independent chains per thread reach with `warps_per_sm` one-warp CTAs per SM --
- * the shape of the adaptive kernels (3 warps per scheduler, 4 chains) without anything else; a profiling aid. */
-int dtwa_fp64_chains(dtwa_ctx *ctx, int chains, int warps_per_sm, double *tflops, double *ms_out);
+ * the shape of the adaptive kernels (3 warps per scheduler, 4 chains) without anything else; nreg = distinct vector-register
+ * operands per DFMA (1: x*a+b with uniform a, b; 2: x*a+y, the form of a stage sum; 3: x*z+y).  A profiling aid. */
+int dtwa_fp64_chains(dtwa_ctx *ctx, int chains, int warps_per_sm, int nreg, double *tflops, double *ms_out);
 
 #ifdef __cplusplus
 }

@@ -13,9 +13,10 @@ pkg = graft.load_package()
 ctx = pkg.default_context()
 peak, _ = ctx.fp64_peak()
 rows = []
-for warps in (4, 8, 12, 16, 20, 24, 32):
-    for chains in (1, 2, 4, 8, 16):
-        tf, ms = ctx.fp64_chains(chains, warps)
-        rows.append({"warps_per_sm": warps, "chains": chains, "tflops": round(tf, 2), "frac_of_k0": round(tf / peak, 3)})
-        print(rows[-1], flush=True)
+for nreg in (1, 2, 3):
+    for warps in (4, 8, 12, 16, 32):
+        for chains in (1, 2, 4, 8, 16):
+            tf, ms = ctx.fp64_chains(chains, warps, nreg)
+            rows.append({"nreg": nreg, "warps_per_sm": warps, "chains": chains, "tflops": round(tf, 2), "frac_of_k0": round(tf / peak, 3)})
+            print(rows[-1], flush=True)
 print(json.dumps({"k0_tflops": peak, "rows": rows}))
