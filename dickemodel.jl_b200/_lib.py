@@ -31,7 +31,7 @@ AXIS_EXPR, AXIS_TIME = 0, 1
 EXPORTS = ["dtwa_last_error", "dtwa_version", "dtwa_create", "dtwa_destroy", "dtwa_device_info", "dtwa_set_launch",
            "dtwa_hamiltonian", "dtwa_integrate", "dtwa_sample", "dtwa_pdf", "dtwa_eval_expr", "dtwa_scale_to_index",
            "dtwa_ensemble", "dtwa_ensemble_launch", "dtwa_plan_arenas", "dtwa_plan_fetch", "dtwa_plan_free",
-           "dtwa_fp64_peak", "dtwa_fp64_peak_regs", "dtwa_fp64_chains", "dtwa_set_jit", "dtwa_jit_compile", "dtwa_integrate_fm", "dtwa_lyapunov", "dtwa_integrate_events",
+           "dtwa_fp64_peak", "dtwa_fp64_peak_regs", "dtwa_fp64_chains", "dtwa_fp64_mix", "dtwa_set_jit", "dtwa_jit_compile", "dtwa_integrate_fm", "dtwa_lyapunov", "dtwa_integrate_events",
            "dtwa_integrate_events_packed", "dtwa_integrate_events_packed_fetch", "dtwa_shell_quadrature", "dtwa_jit_quiesce"]
 
 
@@ -126,6 +126,7 @@ def load():
         L.dtwa_fp64_peak.argtypes = [vp, dp, dp]
         L.dtwa_fp64_peak_regs.argtypes = [vp, dp, dp]
         L.dtwa_fp64_chains.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp]
+        L.dtwa_fp64_mix.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp]
         L.dtwa_jit_quiesce.argtypes = []
         import atexit
         atexit.register(L.dtwa_jit_quiesce)   # no thread may be inside libnvrtc when the process tears it down
@@ -209,6 +210,11 @@ class Context:
     def fp64_chains(self, chains, warps_per_sm, nreg=1):
         tf, ms = C.c_double(), C.c_double()
         _check(load().dtwa_fp64_chains(self._h, int(chains), int(warps_per_sm), int(nreg), C.byref(tf), C.byref(ms)))
+        return tf.value, ms.value
+
+    def fp64_mix(self, alu_per_8, kind, warps_per_sm):
+        tf, ms = C.c_double(), C.c_double()
+        _check(load().dtwa_fp64_mix(self._h, int(alu_per_8), int(kind), int(warps_per_sm), C.byref(tf), C.byref(ms)))
         return tf.value, ms.value
 
     def fp64_peak_regs(self):

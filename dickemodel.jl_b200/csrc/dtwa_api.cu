@@ -338,6 +338,23 @@ static int unit_flags(const dtwa_system *sys, int backwards)
     return wf + 3 * gf;
 }
 
+#ifndef DTWA_ADAPT_PAIR_DEFAULT
+#define DTWA_ADAPT_PAIR_DEFAULT false
+#endif
+// Adaptive pairs with outputs by stepping onto ts[k]: the specialised kernel carries two warp streams per physical warp
+// (adaptive_stream_pair).  DTWA_ADAPT_PAIR=0 in the environment selects the one-stream form (same results, bit for bit).
+static bool pair_streams(const dtwa_solver *sol)
+{
+    static const bool enabled = [] {
+        const char *e = std::getenv("DTWA_ADAPT_PAIR");
+        return e ? std::atoi(e) != 0 : DTWA_ADAPT_PAIR_DEFAULT;
+    }();
+    const bool fixed = sol->alg == DTWA_ALG_RK4 || sol->alg == DTWA_ALG_RK8;
+    return enabled && !fixed && sol->output == DTWA_OUTPUT_STEP;
+}
+// what jit_source specialises on: the unit flags and (+9) the two-stream form
+static int jit_flags(const dtwa_system *sys, const dtwa_solver *sol) { return unit_flags(sys, sol->backwards) + (pair_streams(sol) ? 9 : 0); }
+
 static int check_solver(const dtwa_solver *sol, bool fixed_needs_dt = true)
 {
     if (!sol) return set_err(DTWA_ERR_INVALID, "solver is NULL");
@@ -1234,12 +1251,13 @@ struct dtwa_plan {
 };
 
 struct LaunchShape {
-    int block, grid, window;
+    int block, grid, window;   // grid: CTAs -- for the adaptive kernels the number of warp STREAMS (per_warp of them per CTA)
+    int per_warp = 1;
     size_t smem;
     double *ring;   // adaptive kernels: ring of raw states in global memory, [grid][window][32 lanes][nvar]
 };
 
-static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const EnsArgs &A, long long n, int nvar, LaunchShape &ls)
+static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const EnsArgs &A, long long n, int nvar, LaunchShape &ls, int per_warp = 1)
 {
     const bool fixed = alg == DTWA_ALG_RK4 || alg == DTWA_ALG_RK8;
     const int max_threads = alg == DTWA_ALG_RK4 ? ens_launch<DTWA_ALG_RK4>::max_threads : alg == DTWA_ALG_RK8 ? ens_launch<DTWA_ALG_RK8>::max_threads : 32;
@@ -1263,8 +1281,9 @@ static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const 
     if (per_sm < 1) return set_err(DTWA_ERR_CAPACITY, "ensemble kernel does not fit on an SM with this reducer set");
     if (ctx->ctas_per_sm > 0 && ctx->ctas_per_sm < per_sm) per_sm = ctx->ctas_per_sm;
     long long want = (n + block - 1) / block;
-    long long cap = (long long)d.sm_count * per_sm;
+    long long cap = (long long)d.sm_count * per_sm * per_warp;
     const int grid = (int)std::max(1ll, std::min(want, cap));
+    ls.per_warp = per_warp;
     ls.ring = nullptr;
     if (!fixed) {
         // ring length: even, <= wcap, and the whole ring buffer <= 1 GiB
@@ -1287,8 +1306,9 @@ static int launch_ens(DevCtx &d, const void *kern, const EnsArgs &A0, const Laun
     EnsArgs A = A0;
     A.window = ls.window;
     A.ring = ls.ring;
+    A.vgrid = ls.grid;
     void *args[] = {(void *)&A};
-    CK(cudaLaunchKernel(kern, dim3(ls.grid), dim3(ls.block), args, ls.smem, d.stream));
+    CK(cudaLaunchKernel(kern, dim3((ls.grid + ls.per_warp - 1) / ls.per_warp), dim3(ls.block), args, ls.smem, d.stream));
     return 0;
 }
 
@@ -1483,7 +1503,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
         // (parameter scans) pick the specialised kernel up once it is ready -- same bits as the interpreter
         cudaKernel_t jk;
         CK(cudaSetDevice(ctx->devs[0].device));
-        const int wflag = unit_flags(sys, sol->backwards);
+        const int wflag = jit_flags(sys, sol);
         if (jit_cache().get_async(chart_sys(sys, sol), sol->alg, wflag, prog, &jk) == 0) {
             kern = (const void *)jk;
             used_jit = true;
@@ -1493,7 +1513,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
         cudaKernel_t jk;
         std::string jerr;
         CK(cudaSetDevice(ctx->devs[0].device));
-        const int wflag = unit_flags(sys, sol->backwards);
+        const int wflag = jit_flags(sys, sol);
         if (jit_cache().get(chart_sys(sys, sol), sol->alg, wflag, prog, &jk, jerr)) {
             // forced specialisation fails loudly; in auto mode the (slower) interpreter kernel runs instead -- still on
             // the GPU -- and the result reports jit = 0 (e.g. libnvrtc is not installed next to the driver)
@@ -1597,7 +1617,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
             A.ranges = (const RangeD *)(m + o_r);
             A.hists = (const HistDesc *)(m + o_h);
             A.u64 = dp.d_u64;
-            TRY(shape_for(ctx, d, kern, sol->alg, A, dp.n, nv, shapes[di]));
+            TRY(shape_for(ctx, d, kern, sol->alg, A, dp.n, nv, shapes[di], used_jit && pair_streams(sol) ? 2 : 1));
             dp.grid = shapes[di].grid;
             dp.block = shapes[di].block;
             const size_t pbytes = sizeof(double) * (size_t)dp.grid * nt * std::max(nslots, 1);
@@ -1914,6 +1934,49 @@ extern "C" int dtwa_fp64_chains(dtwa_ctx *ctx, int chains, int warps_per_sm, int
     return DTWA_OK;
 }
 
+// K0d: K0's DFMA chains with `alu_per_8` instructions of another pipe woven in per 8 DFMAs (0, 2, 4, 8, 16), kind 0 = integer
+// add, 1 = FP32 FMA, 2 = MUFU; `warps_per_sm` one-warp CTAs per SM.  Reports the DFMA rate alone.
+extern "C" int dtwa_fp64_mix(dtwa_ctx *ctx, int alu_per_8, int kind, int warps_per_sm, double *tflops, double *ms_out)
+{
+    if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
+    if (warps_per_sm < 1 || warps_per_sm > 32) return set_err(DTWA_ERR_INVALID, "warps_per_sm must be in [1, 32]");
+    if (kind < 0 || kind > 2) return set_err(DTWA_ERR_INVALID, "kind must be 0, 1 or 2");
+    DevCtx &d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    const int block = 32, grid = d.sm_count * warps_per_sm, iters = 16384;
+    TRY(d.scratch_a.ensure(sizeof(double) * (size_t)grid * block));
+    double best = 1e30;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(d.ev[0], d.stream));
+        double *o = (double *)d.scratch_a.p;
+#define DTWA_MIX_CASE(A)                                                                                       \
+    case A:                                                                                                    \
+        if (kind == 0) fp64_mix_kernel<A, 0><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7);          \
+        else if (kind == 1) fp64_mix_kernel<A, 1><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7);     \
+        else fp64_mix_kernel<A, 2><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7);                    \
+        break;
+        switch (alu_per_8) {
+            DTWA_MIX_CASE(0)
+            DTWA_MIX_CASE(2)
+            DTWA_MIX_CASE(4)
+            DTWA_MIX_CASE(8)
+            DTWA_MIX_CASE(16)
+        default: return set_err(DTWA_ERR_INVALID, "alu_per_8 must be 0, 2, 4, 8 or 16");
+        }
+#undef DTWA_MIX_CASE
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(d.ev[3], d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+        float m = 0.f;
+        CK(cudaEventElapsedTime(&m, d.ev[0], d.ev[3]));
+        if (rep > 0 && m < best) best = m;
+    }
+    const double flops = (double)grid * block * (double)iters * 64.0 * 2.0;
+    if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return DTWA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Compile-only check of the run-time specialisation (needs libnvrtc but no GPU): generates the
 // specialised source for `nexpr` averaged observables, compiles it for sm_100a and reports the
@@ -1936,7 +1999,7 @@ extern "C" int dtwa_jit_compile(const dtwa_system *sys, const dtwa_solver *sol, 
         return set_err(DTWA_ERR_EXPR, e.what());
     }
     prog.emit(OP_END);
-    const std::string src = jit_source(chart_sys(sys, sol), sol->alg, unit_flags(sys, sol->backwards), prog);
+    const std::string src = jit_source(chart_sys(sys, sol), sol->alg, jit_flags(sys, sol), prog);
     if (src_out && src_cap > 0) {
         std::snprintf(src_out, (size_t)src_cap, "%s", src.c_str());
     }

@@ -27,6 +27,30 @@ struct SysPar {
     double a, b, c, d;  // Dicke: w0, w, g, -      LMG: Omega, xi, xi/2, 2*xi+Omega
 };
 
+// Two independent values side by side: the arithmetic type of Adaptive::trial2, which integrates two trajectories of one lane
+// with every operation issued for the first and then for the second -- the source order that makes ptxas interleave the two
+// dependency chains (given the stage code of one and then of the other it leaves them one after the other).
+struct D2 {
+    double a, b;
+};
+template <class T>
+__device__ __forceinline__ T bc(double c);   // a constant as T
+template <>
+__device__ __forceinline__ double bc<double>(double c) { return c; }
+template <>
+__device__ __forceinline__ D2 bc<D2>(double c) { return D2{c, c}; }
+__device__ __forceinline__ double dm(double x, double y) { return __dmul_rn(x, y); }
+__device__ __forceinline__ D2 dm(D2 x, D2 y) { return D2{__dmul_rn(x.a, y.a), __dmul_rn(x.b, y.b)}; }
+__device__ __forceinline__ D2 dm(double x, D2 y) { return D2{__dmul_rn(x, y.a), __dmul_rn(x, y.b)}; }
+__device__ __forceinline__ D2 dm(D2 x, double y) { return D2{__dmul_rn(x.a, y), __dmul_rn(x.b, y)}; }
+__device__ __forceinline__ double ng(double x) { return -x; }
+__device__ __forceinline__ D2 ng(D2 x) { return D2{-x.a, -x.b}; }
+__host__ __device__ __forceinline__ double fma(double x, double y, double z) { return ::fma(x, y, z); }   // (the overloads below hide ::fma)
+__device__ __forceinline__ D2 fma(D2 x, D2 y, D2 z) { return D2{fma(x.a, y.a, z.a), fma(x.b, y.b, z.b)}; }
+__device__ __forceinline__ D2 fma(double x, D2 y, D2 z) { return D2{fma(x, y.a, z.a), fma(x, y.b, z.b)}; }
+__device__ __forceinline__ D2 fma(D2 x, D2 y, double z) { return D2{fma(x.a, y.a, z), fma(x.b, y.b, z)}; }
+__device__ __forceinline__ D2 fma(double x, D2 y, double z) { return D2{fma(x, y.a, z), fma(x, y.b, z)}; }
+
 // 1/sqrt(x) and sqrt(x) for x > 0 together: MUFU.RSQ64H seed (rel. err ~2^-22) + one third-order
 // polish, six FP64 instructions.  No special cases: x <= 0 or non-finite yields NaN/Inf, which the
 // domain checks catch.  No instruction reads three distinct registers (a DFMA with three distinct
@@ -40,6 +64,20 @@ __device__ __forceinline__ void rsqrt_sqrt_pair(double x, double &is, double &s)
     const double e = fma(-t, y0, 1.0);           // 1 - x*y0^2
     const double p = fma(0.375, e, 0.5);
     const double ep = __dmul_rn(e, p);           // e/2 + 3/8 e^2
+    is = fma(y0, ep, y0);
+    s = fma(t, ep, t);
+}
+
+__device__ __forceinline__ void rsqrt_sqrt_pair(D2 x, D2 &is, D2 &s)   // (the same operations, a then b)
+{
+    double ya, yb;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(ya) : "d"(x.a));
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(yb) : "d"(x.b));
+    const D2 y0{ya, yb};
+    const D2 t = dm(x, y0);
+    const D2 e = fma(ng(t), y0, 1.0);
+    const D2 p = fma(0.375, e, 0.5);
+    const D2 ep = dm(e, p);
     is = fma(y0, ep, y0);
     s = fma(t, ep, t);
 }
@@ -73,46 +111,46 @@ struct Sys<DTWA_SYS_DICKE> {
     // caller's step constants), 17 instructions.  DTWA_W_IS_ONE / DTWA_W_IS_MINUS_ONE (defined by the
     // run-time specialisation when |w| == 1; x*1.0 == x exactly, so results do not change): 16.  DTWA_G_IS_ONE /
     // DTWA_G_IS_MINUS_ONE (|g| == 1, the same argument for g*q): 15.
-    template <bool FOLDQ = false>
-    __device__ __forceinline__ static void rhs(const SysPar &p, const double (&u)[4], double (&du)[4])
+    template <bool FOLDQ = false, class T = double>
+    __device__ __forceinline__ static void rhs(const SysPar &p, const T (&u)[4], T (&du)[4])
     {
-        const double Q = u[0], q = u[1], P = u[2], pp = u[3];
-        double r2 = fma(-P, P, 4.0);
-        r2 = fma(-Q, Q, r2);               // 4 - P^2 - Q^2
-        double is, s;
+        const T Q = u[0], q = u[1], P = u[2], pp = u[3];
+        T r2 = fma(ng(P), P, 4.0);
+        r2 = fma(ng(Q), Q, r2);            // 4 - P^2 - Q^2
+        T is, s;
         rsqrt_sqrt_pair(r2, is, s);        // 1/s and s
 #if defined(DTWA_G_IS_ONE)
-        const double gq = q;
+        const T gq = q;
 #elif defined(DTWA_G_IS_MINUS_ONE)
-        const double gq = -q;
+        const T gq = ng(q);
 #else
-        const double gq = __dmul_rn(p.c, q);
+        const T gq = dm(p.c, q);
 #endif
-        const double gqQ = __dmul_rn(gq, Q);
-        const double e = fma(gqQ, is, -p.a);      // g q Q / s - w0
-        du[0] = __dmul_rn(-P, e);                 // P w0 - g P q Q / s
+        const T gqQ = dm(gq, Q);
+        const T e = fma(gqQ, is, -p.a);           // g q Q / s - w0
+        du[0] = dm(ng(P), e);                     // P w0 - g P q Q / s
         if constexpr (FOLDQ)
             du[1] = pp;
         else {
 #if defined(DTWA_W_IS_ONE)
             du[1] = pp;
 #elif defined(DTWA_W_IS_MINUS_ONE)
-            du[1] = -pp;
+            du[1] = ng(pp);
 #else
-            du[1] = __dmul_rn(pp, p.b);           // p w
+            du[1] = dm(pp, p.b);                  // p w
 #endif
         }
-        const double gqs = __dmul_rn(gq, s);
-        du[2] = fma(Q, e, -gqs);                  // g q Q^2/s - g q s - Q w0
-        const double Qs = __dmul_rn(Q, s);
+        const T gqs = dm(gq, s);
+        du[2] = fma(Q, e, ng(gqs));               // g q Q^2/s - g q s - Q w0
+        const T Qs = dm(Q, s);
 #if defined(DTWA_W_IS_ONE)
-        const double qw = q;
+        const T qw = q;
 #elif defined(DTWA_W_IS_MINUS_ONE)
-        const double qw = -q;
+        const T qw = ng(q);
 #else
-        const double qw = __dmul_rn(q, p.b);
+        const T qw = dm(q, p.b);
 #endif
-        du[3] = fma(-p.c, Qs, -qw);               // -g Q s - q w
+        du[3] = fma(-p.c, Qs, ng(qw));            // -g Q s - q w
     }
     __device__ __forceinline__ static double hamiltonian(const double *par, const double *u)
     {
@@ -136,14 +174,15 @@ struct Sys<DTWA_SYS_LMG> {
     static constexpr int QI = 0, PI = 1;
     static constexpr int NVB = 2, GROUP = 1, NORM_N = 2;
     // 7 FP64-pipe instructions
-    __device__ __forceinline__ static void rhs(const SysPar &p, const double (&u)[2], double (&du)[2])
+    template <bool FOLDQ = false, class T = double>
+    __device__ __forceinline__ static void rhs(const SysPar &p, const T (&u)[2], T (&du)[2])
     {
-        const double Q = u[0], P = u[1];
-        const double Q2 = __dmul_rn(Q, Q);
-        const double P2 = __dmul_rn(P, P);
-        du[0] = __dmul_rn(P, fma(-p.c, Q2, p.a));        // P (Om - xi Q^2/2)
-        const double in = fma(p.c, P2, -p.d);            // xi P^2/2 - (2 xi + Om)
-        du[1] = __dmul_rn(Q, fma(p.b, Q2, in));          // Q(...) + xi Q^3
+        const T Q = u[0], P = u[1];
+        const T Q2 = dm(Q, Q);
+        const T P2 = dm(P, P);
+        du[0] = dm(P, fma(-p.c, Q2, p.a));               // P (Om - xi Q^2/2)
+        const T in = fma(p.c, P2, -p.d);                 // xi P^2/2 - (2 xi + Om)
+        du[1] = dm(Q, fma(p.b, Q2, in));                 // Q(...) + xi Q^3
     }
     __device__ __forceinline__ static double hamiltonian(const double *par, const double *u)
     {
@@ -175,22 +214,23 @@ struct Sys<DTWA_SYS_DICKE_BLOCH> {
     static constexpr int QI = 0, PI = 1;   // (unused: no chart boundary)
     static constexpr int NVB = 5, GROUP = 1, NORM_N = 5;
     // p.a = w0, p.b = w, p.c = g, p.d = 2 g (sign of integate_backwards folded into all of them)
-    __device__ __forceinline__ static void rhs(const SysPar &p, const double (&y)[5], double (&dy)[5])
+    template <bool FOLDQ = false, class T = double>
+    __device__ __forceinline__ static void rhs(const SysPar &p, const T (&y)[5], T (&dy)[5])
     {
-        const double jx = y[0], jy = y[1], jz = y[2], q = y[3], pp = y[4];
-        const double gq2 = __dmul_rn(p.d, q);              // 2 g q
-        dy[0] = __dmul_rn(-p.a, jy);
-        dy[1] = fma(p.a, jx, -__dmul_rn(gq2, jz));
-        dy[2] = __dmul_rn(gq2, jy);
+        const T jx = y[0], jy = y[1], jz = y[2], q = y[3], pp = y[4];
+        const T gq2 = dm(p.d, q);                          // 2 g q
+        dy[0] = dm(-p.a, jy);
+        dy[1] = fma(p.a, jx, ng(dm(gq2, jz)));
+        dy[2] = dm(gq2, jy);
 #if defined(DTWA_W_IS_ONE)
         dy[3] = pp;
-        dy[4] = fma(-p.d, jx, -q);
+        dy[4] = fma(-p.d, jx, ng(q));
 #elif defined(DTWA_W_IS_MINUS_ONE)
-        dy[3] = -pp;
+        dy[3] = ng(pp);
         dy[4] = fma(-p.d, jx, q);
 #else
-        dy[3] = __dmul_rn(p.b, pp);
-        dy[4] = fma(-p.d, jx, -__dmul_rn(p.b, q));
+        dy[3] = dm(p.b, pp);
+        dy[4] = fma(-p.d, jx, ng(dm(p.b, q)));
 #endif
     }
 };
@@ -482,6 +522,9 @@ __device__ __forceinline__ void rk4_step(const SysPar &p, double (&u)[Sys<SYS>::
 #undef DTWA_TABLEAU_CONSTANTS
 
 #define RHS(in, out) Sys<SYS>::rhs(p, in, out)
+#define DTWA_STEP_H(i) h            // what the generated stage code is instantiated with: the step length,
+#define DTWA_REAL double             // the arithmetic type (trial2 below: D2, two trajectories side by side)
+#define DTWA_CMUL(c, x) ((c) * (x))  // and coefficient * value
 
 // one DOP853 step with the 8th-order weights only (fixed step)
 template <int SYS>
@@ -639,6 +682,83 @@ struct Adaptive {
         }
     }
 
+    // The same for TWO independent trajectories of one lane (a, b): the generated stage code and the right-hand side are
+    // instantiated for the arithmetic type D2, so that every operation is issued for a and then for b and the two dependency
+    // chains (stage sum -> rsqrt -> right-hand side, ~11 dependent FP64 instructions per stage) interleave instruction by
+    // instruction in ONE basic block.  Every arithmetic operation is the one trial() executes for the same trajectory:
+    // bit-identical steps.
+    __device__ __forceinline__ static void trial2(const SysPar &p, const Adaptive &A0, const Adaptive &A1, const double (&ya)[NV], const double (&yb)[NV],
+                                                  const double ha, const double hb, const double tol, double (&yna)[NV], double (&ynb)[NV],
+                                                  double (&kna)[NV], double (&knb)[NV], double &erra, double &errb)
+    {
+        D2 y[NV], k0[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            y[i] = D2{ya[i], yb[i]};
+            k0[i] = D2{A0.k0[i], A1.k0[i]};
+        }
+        const D2 h2{ha, hb};
+#undef DTWA_STEP_H
+#undef DTWA_REAL
+#undef DTWA_CMUL
+#define DTWA_STEP_H(i) h2
+#define DTWA_REAL D2
+#define DTWA_CMUL(c, x) dm(c, x)
+        if constexpr (ALG == DTWA_ALG_DP5) {
+#include "dp5_body.inc"
+            (void)dy;
+            double ena[NV], enb[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const double sca = fma(fmax(fabs(y[i].a), fabs(ynew[i].a)), tol, tol), scb = fma(fmax(fabs(y[i].b), fabs(ynew[i].b)), tol, tol);
+                ena[i] = e5[i].a * ha * rcp_fast(sca);
+                enb[i] = e5[i].b * hb * rcp_fast(scb);
+                yna[i] = ynew[i].a;
+                ynb[i] = ynew[i].b;
+                kna[i] = DP5_KNEW[i].a;
+                knb[i] = DP5_KNEW[i].b;
+            }
+            erra = group_rms<SYS>(ena);
+            errb = group_rms<SYS>(enb);
+#undef DP5_KNEW
+        } else {
+#include "dop853_body.inc"
+            double n5a = 0.0, n3a = 0.0, n5b = 0.0, n3b = 0.0;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const double isca = rcp_fast(fma(fmax(fabs(y[i].a), fabs(ynew[i].a)), tol, tol));
+                const double iscb = rcp_fast(fma(fmax(fabs(y[i].b), fabs(ynew[i].b)), tol, tol));
+                const double a5a = e5[i].a * isca, a3a = e3[i].a * isca, a5b = e5[i].b * iscb, a3b = e3[i].b * iscb;
+                if (norm_counted<SYS>(i)) {
+                    n5a = fma(a5a, a5a, n5a);
+                    n5b = fma(a5b, a5b, n5b);
+                    n3a = fma(a3a, a3a, n3a);
+                    n3b = fma(a3b, a3b, n3b);
+                }
+                yna[i] = ynew[i].a;
+                ynb[i] = ynew[i].b;
+                kna[i] = DOP853_KNEW[i].a;
+                knb[i] = DOP853_KNEW[i].b;
+            }
+            n5a = group_sum<SYS>(n5a);
+            n5b = group_sum<SYS>(n5b);
+            n3a = group_sum<SYS>(n3a);
+            n3b = group_sum<SYS>(n3b);
+            D2 is, sq;
+            rsqrt_sqrt_pair(D2{fma(0.01, n3a, n5a) * (double)Sys<SYS>::NORM_N, fma(0.01, n3b, n5b) * (double)Sys<SYS>::NORM_N}, is, sq);
+            const double ea = fabs(ha) * n5a * is.a, eb = fabs(hb) * n5b * is.b;
+            erra = (n5a == 0.0 && n3a == 0.0) ? 0.0 : ea;
+            errb = (n5b == 0.0 && n3b == 0.0) ? 0.0 : eb;
+#undef DOP853_KNEW
+        }
+#undef DTWA_STEP_H
+#undef DTWA_REAL
+#undef DTWA_CMUL
+#define DTWA_STEP_H(i) h
+#define DTWA_REAL double
+#define DTWA_CMUL(c, x) ((c) * (x))
+    }
+
     // one attempted step towards tstop.  Returns 0 = keep going, 1 = trajectory failed (DOMAIN).
     // `accepted` reports whether y/t advanced.  KEEP: an accepted step also hands back the state and the derivative at its
     // START (yprev, fprev) and its length (hlast) -- what the Hermite interpolant of interpolated outputs needs; they take
@@ -707,6 +827,9 @@ struct Adaptive {
     }
 };
 #undef RHS
+#undef DTWA_STEP_H
+#undef DTWA_REAL
+#undef DTWA_CMUL
 
 // 3rd-order Hermite interpolant over an accepted step: OrdinaryDiffEq's hermite_interpolant, what the reference's
 // FunctionCallingCallback(funcat = ts) evaluates at the output times (src/TWA.jl:180) for algorithms without a dense output

@@ -148,6 +148,7 @@ struct EnsArgs {
     int32_t nslots, nins, ncst, nrange, nhist, stage_bins;
     int32_t window;    // output times staged in shared memory between two CTA-wide flushes
     int32_t stage2d_bins;  // u32 cells of the per-CTA tiles of small 2-D histograms (fixed-step kernels)
+    int32_t vgrid;         // adaptive kernels: number of warp STREAMS of the launch (= CTAs, or 2 x CTAs minus at most one for the pair kernels)
     const FailRec *redo;  // NULL in the main pass; else trajectory j re-draws redo[j].idx and contributes from redo[j].k
     FailRec *fail_out;
     unsigned *fail_count;
@@ -354,8 +355,15 @@ __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp,
 #ifndef DTWA_RK8_MAX_THREADS
 #define DTWA_RK8_MAX_THREADS 128
 #endif
+#if defined(DTWA_ADAPT_PAIR) && defined(DTWA_JIT_UNIT)
+#define DTWA_PAIR_UNIT 1   // this translation unit is a run-time specialisation with two warp streams per warp
+#endif
 #ifndef DTWA_ADAPT_MIN_BLOCKS
+#ifdef DTWA_PAIR_UNIT
+#define DTWA_ADAPT_MIN_BLOCKS 8    // two warps per scheduler, <= 255 registers: two trajectories per lane
+#else
 #define DTWA_ADAPT_MIN_BLOCKS 12
+#endif
 #endif
 // Register budgets.  RK4 fits 64 registers/thread: 4 CTAs of 256 threads per SM.  The embedded pairs run ONE warp per CTA
 // (adaptive_stream); the register file is split over the four SM sub-partitions (16384 registers each), so the only
@@ -738,6 +746,295 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
     }
 }
 
+#ifdef DTWA_PAIR_UNIT
+// adaptive_stream for TWO warp streams per physical warp (run-time specialised kernels, outputs by stepping onto ts[k]).
+// The embedded pairs are latency-bound: their register budget allows three warps per scheduler, and one attempt is a chain of
+// ~13 x 11 dependent FP64 instructions plus a serial tail (error norm -> controller -> commit -> emit -> vote); with three
+// warps the FP64 pipe is 70 % busy (profiles/r2_ncu_dop853_cfg4.md).  Here every lane carries the trajectories of TWO streams
+// -- warp stream 2 b + s of a launch with `vgrid` streams, s = 0, 1: the same trajectories, the same ring, the same partial
+// row and the same summation order as CTA 2 b + s of the one-stream kernel launched on vgrid CTAs, hence bit-identical
+// results -- and attempts one step of each per iteration through Adaptive::trial2, whose generated stage code interleaves the
+// two dependency chains in one basic block.  Two resident warps per scheduler (<= 255 registers) then carry four streams
+// with instruction-level parallelism 2 each.  Decisions are selects (the expressions of Adaptive::attempt).
+template <int SYS, int ALG>
+__device__ __forceinline__ void adaptive_stream_pair(const EnsArgs &A, const VmShared &V, unsigned long long *nvalid_g)
+{
+    constexpr int NV = Sys<SYS>::NV, NVO = Sys<SYS>::NVO;
+    const int lane = threadIdx.x & 31;
+    const int nt = A.S.nt, W = A.window;
+    const int H = (W >= 2) ? W / 2 : 1, R = (W >= 2) ? 2 * H : 1;   // half and ring size
+    const long long stride = (long long)A.vgrid * 32;
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    const CtrlPar &c = A.S.ctrl;
+
+    struct Stream {
+        long long j, g, flushed;
+        uint64_t idx;
+        double tstop;
+        double *ring, *partial;
+        int k, wslot, start_k, budget;
+        bool have, done;
+        unsigned long long acc_steps, rej_steps;
+    };
+    Stream X[2];
+    Traj<SYS, ALG> T[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const long long vc = 2ll * blockIdx.x + s;
+        X[s].done = false;
+        X[s].j = vc < A.vgrid ? vc * 32 + lane : A.N;   // (an odd number of streams: the last warp carries one)
+        X[s].g = X[s].flushed = 0;
+        X[s].idx = 0;
+        X[s].tstop = 0.0;
+        X[s].ring = A.ring + (size_t)vc * 32 * W * NVO;
+        X[s].partial = A.partial + (size_t)vc * nt * A.nslots;
+        X[s].k = nt;
+        X[s].wslot = X[s].start_k = X[s].budget = 0;
+        X[s].have = false;
+        X[s].acc_steps = X[s].rej_steps = 0;
+        T[s].status = ST_INACTIVE;
+        T[s].nacc = T[s].nrej = 0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) T[s].u[i] = 0.0;
+        T[s].ad.t = 0.0;
+        T[s].ad.habs = 0.0;
+        T[s].ad.lqold = c.lqoldinit;
+        T[s].ad.rejected = false;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) T[s].ad.k0[i] = 0.0;
+        if (vc < A.vgrid)
+            for (int i = lane; i < 32 * W; i += 32) X[s].ring[(size_t)i * NVO] = qnan;   // every cell starts empty
+    }
+    __syncwarp();
+    uint32_t iters = 0;
+
+    auto flush_half = [&](double *ring, double *partial, long long f0, long long f1) {   // (adaptive_stream's, per stream)
+        __syncwarp();
+        const int cnt = (int)(f1 - f0);
+        const int w0 = (int)(f0 % R), k0 = (int)(f0 % nt);
+        double *row = V.wsum + (size_t)lane * A.nslots;
+        for (int cc = 0; cc < cnt; cc += 32) {
+            const int o = cc + lane;
+            const bool mine = o < cnt;
+            const int w = (w0 + o) % R, kq = (k0 + o) % nt;
+            for (int sl = 0; sl < A.nslots; ++sl) row[sl] = 0.0;
+            unsigned nv = 0;
+            constexpr int RB = 8;
+#pragma unroll 1
+            for (int r0 = 0; r0 < 32; r0 += RB) {
+                double xa[RB][NVO];
+#pragma unroll
+                for (int q = 0; q < RB; ++q) {
+                    const double *cell = ring + ((size_t)w * 32 + (r0 + q)) * NVO;
+                    if (mine) {
+                        if constexpr (NVO == 4) {
+                            const double2 a = __ldcg(reinterpret_cast<const double2 *>(cell)), b = __ldcg(reinterpret_cast<const double2 *>(cell + 2));
+                            xa[q][0] = a.x; xa[q][1] = a.y; xa[q][2] = b.x; xa[q][3] = b.y;
+                        } else {
+                            const double2 a = __ldcg(reinterpret_cast<const double2 *>(cell));
+                            xa[q][0] = a.x; xa[q][1] = a.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NVO; ++i) xa[q][i] = qnan;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < RB; ++q)
+                    if (mine) ring[((size_t)w * 32 + (r0 + q)) * NVO] = qnan;   // the cells are free again
+#pragma unroll
+                for (int q = 0; q < RB; ++q) {
+                    const bool valid = (xa[q][0] == xa[q][0]);
+                    nv += valid ? 1u : 0u;
+                    jit_reduce<NVO, true>(V, &A.smp, A.u64, xa[q][0], xa[q][1], NVO == 4 ? xa[q][NVO - 2] : 0.0, NVO == 4 ? xa[q][NVO - 1] : 0.0, valid, kq, 0, valid);
+                }
+            }
+            if (mine) {
+                for (int sl = 0; sl < A.nslots; ++sl) atomicAdd(&partial[(size_t)kq * A.nslots + sl], row[sl]);
+                if (nv) atomicAdd(&nvalid_g[kq], (unsigned long long)nv);
+            }
+        }
+        __syncwarp();
+    };
+    auto emit_state = [&](const double (&uo)[NV], bool valid, double *cell) {
+        if (!valid) return;
+        double xo[NVO];
+        from_chart<SYS>(uo, xo);
+        if constexpr (NVO == 4) {
+            *reinterpret_cast<double2 *>(cell) = make_double2(xo[0], xo[1]);
+            *reinterpret_cast<double2 *>(cell + 2) = make_double2(xo[2], xo[3]);
+        } else
+            *reinterpret_cast<double2 *>(cell) = make_double2(xo[0], xo[1]);
+    };
+
+#pragma unroll 1
+    while (true) {
+        // ================= service part (cold), stream by stream =================
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            Stream &x = X[s];
+            if (x.done) continue;   // (warp-uniform)
+            if (!x.have && x.j < A.N) {   // draw the next trajectory of the stream
+                x.idx = (uint64_t)x.j;
+                x.start_k = 0;
+                if (A.redo) {
+                    const FailRec r = A.redo[x.j];
+                    x.idx = r.idx;
+                    x.start_k = r.k;
+                }
+                x.acc_steps += T[s].nacc;
+                x.rej_steps += T[s].nrej;
+                T[s].status = ST_OK;
+                {
+                    double xi[NVO];
+                    draw_initial<NVO>(A.smp, x.idx, A.attempt, xi);
+                    to_chart<SYS>(xi, T[s].u);
+                }
+                T[s].begin(A.S);
+                x.have = true;
+                x.k = 0;
+                x.tstop = A.S.ts[0];
+                x.budget = (int)(A.S.maxiters > 0x7fffffffll ? 0x7fffffffll : A.S.maxiters);
+            }
+            if (x.have && T[s].status != ST_OK) {   // failures end a trajectory: report, skip the rest of its outputs
+                bool queued = false;
+                if (T[s].status != ST_MAXITERS) {
+                    atomicAdd(&A.u64[CNT_FAILED], 1ull);
+                    if (A.fail_out && A.smp.kind != DTWA_SAMPLER_HOST_ARRAY && A.smp.kind != DTWA_SAMPLER_DEVICE_ARRAY) {
+                        const unsigned pos = atomicAdd(A.fail_count, 1u);
+                        if (pos < A.fail_cap) {
+                            FailRec r;
+                            r.idx = x.idx;
+                            r.k = x.k;
+                            r.pad = 0;
+                            A.fail_out[pos] = r;
+                            queued = true;
+                        }
+                    }
+                }
+                if (!queued) atomicAdd(&A.u64[CNT_UNFINISHED], 1ull);
+                x.g += (long long)(nt - x.k);
+                x.wslot = (int)(((long long)x.wslot + (nt - x.k)) % R);
+                x.k = nt;
+            }
+            if (x.have && x.k >= nt) {
+                x.have = false;
+                x.j += stride;
+            }
+            {   // flush what every lane of the stream has passed
+                const bool retired = !x.have && x.j >= A.N;
+                const long long ahead = retired ? (long long)0x7fffffff : x.g - x.flushed;
+                const int amin = __reduce_min_sync(0xffffffffu, (int)(ahead > 0x7fffffff ? 0x7fffffff : ahead));
+                if (amin == 0x7fffffff) {   // the stream has ended: flush its tail
+                    const long long gend = __reduce_max_sync(0xffffffffu, (int)(x.g - x.flushed)) + x.flushed;
+                    while (x.flushed < gend) {
+                        const long long f1 = (x.flushed + H < gend) ? x.flushed + H : gend;
+                        flush_half(x.ring, x.partial, x.flushed, f1);
+                        x.flushed = f1;
+                    }
+                    x.done = true;
+                } else if (amin >= H) {
+                    flush_half(x.ring, x.partial, x.flushed, x.flushed + H);
+                    x.flushed += H;
+                }
+            }
+        }
+        if (X[0].done && X[1].done) break;
+        if (__any_sync(0xffffffffu, (!X[0].done && !X[0].have && X[0].j < A.N) || (!X[1].done && !X[1].have && X[1].j < A.N))) continue;
+
+        // ================= hot loop: one attempted step of each stream per lane and iteration =================
+        int ahead0 = X[0].have ? (int)(X[0].g - X[0].flushed) : 0, ahead1 = X[1].have ? (int)(X[1].g - X[1].flushed) : 0;
+        const bool live0 = !X[0].done, live1 = !X[1].done;
+#pragma unroll 1
+        while (true) {
+            // leave when a lane needs service or a half of a ring can be flushed
+            const bool service = (X[0].have && (T[0].status != ST_OK || X[0].k >= nt)) || (X[1].have && (T[1].status != ST_OK || X[1].k >= nt));
+            const bool behind0 = X[0].have && ahead0 < H, behind1 = X[1].have && ahead1 < H;
+            const unsigned vote = __reduce_or_sync(0xffffffffu, (service ? 1u : 0u) | (behind0 ? 2u : 0u) | (behind1 ? 4u : 0u));
+            if ((vote & 1u) || (live0 && !(vote & 2u)) || (live1 && !(vote & 4u))) break;
+            ++iters;
+            const bool step0 = X[0].have && ahead0 < R, step1 = X[1].have && ahead1 < R;
+            const bool want0 = step0 && T[0].ad.t < X[0].tstop, want1 = step1 && T[1].ad.t < X[1].tstop;
+            if (want0 || want1) {
+                bool act[2] = {want0 && X[0].budget > 0, want1 && X[1].budget > 0};
+                bool forced[2], last[2], clipped[2];
+                double h[2], habs_eff[2];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    if ((s ? want1 : want0) && !act[s]) T[s].status = ST_MAXITERS;
+                    X[s].budget -= act[s] ? 1 : 0;
+                    forced[s] = T[s].ad.habs < A.S.dtmin;
+                    habs_eff[s] = forced[s] ? A.S.dtmin : T[s].ad.habs;
+                    last[s] = (T[s].ad.t + habs_eff[s] >= X[s].tstop);
+                    clipped[s] = last[s] && ((X[s].tstop - T[s].ad.t) < habs_eff[s]);
+                    h[s] = last[s] ? X[s].tstop - T[s].ad.t : habs_eff[s];
+                    if (!act[s]) h[s] = 0.0;
+                }
+                double yn[2][NV], kn[2][NV], err[2];
+                Adaptive<SYS, ALG>::trial2(A.S.par, T[0].ad, T[1].ad, T[0].u, T[1].u, h[0], h[1], A.S.tol, yn[0], yn[1], kn[0], kn[1], err[0], err[1]);
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    // the decisions of Adaptive::attempt, as selects
+                    const bool bad = state_bad<SYS>(yn[s]) || !(err[s] == err[s]) || isinf(err[s]);
+                    const float le = lg2_approx(fminf(fmaxf((float)err[s], 1e-30f), 1e30f));
+                    const float e_rej = ex2_approx(-c.b1 * le);
+                    const float e_acc = ex2_approx(-fmaf(c.b1, le, c.nb2 * T[s].ad.lqold));
+                    float fac_acc = fminf(c.fac_max, fmaxf(c.fac_min_acc, c.g * e_acc));
+                    if (T[s].ad.rejected) fac_acc = fminf(fac_acc, c.post_reject_cap);
+                    const float fac_rej = fmaxf(c.fac_min_rej, c.g * e_rej);
+                    const bool acc = act[s] && !bad && (forced[s] || err[s] < c.acc_thr);
+                    const bool fail = act[s] && bad && forced[s];
+                    double hn = h[s] * (double)(acc ? fac_acc : fac_rej);
+                    if (bad) hn = h[s] * c.dom_shrink;
+                    if (acc && clipped[s] && hn < habs_eff[s]) hn = habs_eff[s];
+                    if (acc && !clipped[s]) T[s].ad.lqold = fmaxf(le, c.lqoldinit);
+                    if (act[s] && !fail) T[s].ad.habs = hn;
+                    if (act[s] && fail) T[s].ad.habs = habs_eff[s];
+                    if (act[s]) T[s].ad.rejected = !acc;
+                    if (acc) {
+                        T[s].ad.t = last[s] ? X[s].tstop : T[s].ad.t + h[s];
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) {
+                            T[s].u[i] = yn[s][i];
+                            T[s].ad.k0[i] = kn[s][i];
+                        }
+                    }
+                    if (fail) T[s].status = ST_DOMAIN;
+                    T[s].nacc += acc ? 1u : 0u;
+                    T[s].nrej += (act[s] && !acc && !fail) ? 1u : 0u;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const bool stepping = s ? step1 : step0;
+                const bool reached = stepping && T[s].status == ST_OK && !(T[s].ad.t < X[s].tstop);   // this stream emits output k now
+                if (reached) {
+                    emit_state(T[s].u, X[s].k >= X[s].start_k, X[s].ring + ((size_t)X[s].wslot * 32 + lane) * NVO);
+                    ++X[s].k;
+                    if (s) ++ahead1; else ++ahead0;
+                    X[s].wslot = (X[s].wslot + 1 == R) ? 0 : X[s].wslot + 1;
+                    if (X[s].k < nt) X[s].tstop = A.S.ts[X[s].k];
+                }
+            }
+        }
+        if (X[0].have) X[0].g = X[0].flushed + ahead0;
+        if (X[1].have) X[1].g = X[1].flushed + ahead1;
+    }
+    // ---- step counters: one atomic per warp ----
+    unsigned long long a = X[0].acc_steps + X[1].acc_steps + T[0].nacc + T[1].nacc, r = X[0].rej_steps + X[1].rej_steps + T[0].nrej + T[1].nrej;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        r += __shfl_xor_sync(0xffffffffu, r, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&A.u64[CNT_ACC], a);
+        if (r) atomicAdd(&A.u64[CNT_REJ], r);
+        atomicAdd(&A.u64[CNT_LANE], 64ull * iters);
+    }
+}
+#endif
+
 template <int SYS, int ALG, bool JIT>
 __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
 {
@@ -777,10 +1074,12 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
         for (int i = threadIdx.x; i < Ws * A.stage_bins; i += blockDim.x) V.stage[i] = 0u;
         for (int i = threadIdx.x; i < Ws; i += blockDim.x) V.nvalid[i] = 0u;
         for (int i = threadIdx.x; i < A.stage2d_bins; i += blockDim.x) V.stage2d[i] = 0u;
+#ifndef DTWA_PAIR_UNIT   // (the two-stream kernels initialise the rings of their streams themselves)
         if constexpr (PERLANE) {   // the CTA's ring of raw states in global memory: every cell starts empty (NaN marker)
             double *ring = A.ring + (size_t)blockIdx.x * 32 * W * Sys<SYS>::NVO;
             for (int i = threadIdx.x; i < 32 * W; i += blockDim.x) ring[(size_t)i * Sys<SYS>::NVO] = __longlong_as_double(0x7ff8000000000000ll);
         }
+#endif
         V.consts = consts;
         V.ranges = ranges;
         V.hists = hists;
@@ -828,7 +1127,11 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
     long long batches_done = 0;
 
     if constexpr (!FIXED) {
+#ifdef DTWA_PAIR_UNIT
+        adaptive_stream_pair<SYS, ALG>(A, V, nvalid_g);
+#else
         adaptive_stream<SYS, ALG, JIT>(A, V, my_partial, nvalid_g, A.ring + (size_t)blockIdx.x * 32 * W * Sys<SYS>::NVO);
+#endif
     } else {
     // ---- fixed step: persistent loop over batches of blockDim.x trajectories ----
     for (long long batch = blockIdx.x; batch * (long long)blockDim.x < A.N; batch += gridDim.x) {
@@ -1888,6 +2191,50 @@ __global__ void __launch_bounds__(32) fp64_chains_kernel(double *out, const doub
     double s = 0.0;
 #pragma unroll
     for (int c = 0; c < CHAINS; ++c) s += x[c];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// K0d: 8 DFMA chains per thread (K0's form) with ALU other instructions woven in per group of 8 DFMAs -- does an
+// instruction of another pipe issue "for free" in the cycle the FP64 pipe cannot accept a second DFMA, or does it take an
+// issue slot away from the DFMAs?  KIND 0: integer adds (ALU pipe), 1: FP32 FMAs (FMA pipe), 2: MUFU.RSQ64H (XU pipe).
+template <int ALU, int KIND>
+__global__ void __launch_bounds__(32) fp64_mix_kernel(double *out, int iters, double a, double b)
+{
+    double x[8];
+    unsigned u[4];
+    float f[4];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) x[c] = threadIdx.x * 1e-3 + c;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        u[c] = threadIdx.x + c;
+        f[c] = 1.0f + threadIdx.x * 1e-3f + c;
+    }
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                x[c] = fma(x[c], a, b);
+                // ALU other instructions per 8 DFMAs, spread evenly
+#pragma unroll
+                for (int m = 0; m < ((c + 1) * ALU) / 8 - (c * ALU) / 8; ++m) {
+                    const int k = (c + m) & 3;
+                    if constexpr (KIND == 0)
+                        asm volatile("add.u32 %0, %0, %1;" : "+r"(u[k]) : "r"(i));
+                    else if constexpr (KIND == 1)
+                        asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f[k]) : "f"(1.0000001f));
+                    else
+                        asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(f[k]));
+                }
+            }
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s += x[c];
+    s += (double)(u[0] ^ u[1] ^ u[2] ^ u[3]) + (double)(f[0] + f[1] + f[2] + f[3]);
     if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 

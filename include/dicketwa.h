@@ -337,6 +337,10 @@ int dtwa_fp64_peak_regs(dtwa_ctx *ctx, double *tflops, double *ms);
  * the shape of the adaptive kernels (3 warps per scheduler, 4 chains) without anything else; nreg = distinct vector-register
  * operands per DFMA (1: x*a+b with uniform a, b; 2: x*a+y, the form of a stage sum; 3: x*z+y).  A profiling aid. */
 int dtwa_fp64_chains(dtwa_ctx *ctx, int chains, int warps_per_sm, int nreg, double *tflops, double *ms_out);
+/* K0d: K0's DFMA chains with `alu_per_8` (0, 2, 4, 8, 16) instructions of another pipe woven in per 8 DFMAs (kind 0: integer
+ * add, 1: FP32 FMA, 2: MUFU) -- whether the instructions around the FP64 arithmetic of a kernel cost DFMA issue slots.
+ * Reports the DFMA rate alone.  A profiling aid. */
+int dtwa_fp64_mix(dtwa_ctx *ctx, int alu_per_8, int kind, int warps_per_sm, double *tflops, double *ms_out);
 
 #ifdef __cplusplus
 }
