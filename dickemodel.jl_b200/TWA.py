@@ -42,6 +42,7 @@ class JRange:
             raise ValueError("range step cannot be zero")
         n = int((b - a) / s) + 1 if (b - a) / s >= 0 else 0
         self._a, self._s, self.len = a, s, max(n, 0)
+        self._arr = None
         self.start = float(a)
         self.step = float(s)
         self.stop = float(a + (self.len - 1) * s) if self.len else float(a)
@@ -50,7 +51,17 @@ class JRange:
         return self.len
 
     def __array__(self, dtype=None, copy=None):
-        return np.array([float(self._a + k * self._s) for k in range(self.len)], dtype=np.float64)
+        # elements a + k s = (pa qs + k ps qa) / (qa qs): Python's int / int is correctly rounded, so this is float(Fraction)
+        # without the rational arithmetic (10 ms for 2001 output times -- more than the kernel of a 10^4-trajectory call);
+        # computed once per range (a JRange is immutable) and handed out read-only
+        if self._arr is None:
+            pa, qa, ps, qs = self._a.numerator, self._a.denominator, self._s.numerator, self._s.denominator
+            den, n0, dn = qa * qs, pa * qs, ps * qa
+            arr = np.array([(n0 + k * dn) / den for k in range(self.len)], dtype=np.float64)
+            arr.flags.writeable = False
+            self._arr = arr
+        a = self._arr if dtype is None else self._arr.astype(dtype, copy=False)
+        return a.copy() if copy else a
 
     def __iter__(self):
         return iter(np.asarray(self))

@@ -365,6 +365,13 @@ __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp,
 #define DTWA_ADAPT_MIN_BLOCKS 12
 #endif
 #endif
+#ifndef DTWA_DP5_MIN_BLOCKS
+#ifdef DTWA_JIT_UNIT
+#define DTWA_DP5_MIN_BLOCKS (DTWA_ADAPT_MIN_BLOCKS == 12 ? 16 : DTWA_ADAPT_MIN_BLOCKS)   // the 7-stage pair fits 128 registers without spills: 4 warps per scheduler (+3.6 %)
+#else
+#define DTWA_DP5_MIN_BLOCKS DTWA_ADAPT_MIN_BLOCKS   // (the interpreter build needs the registers for the reducer VM)
+#endif
+#endif
 // Register budgets.  RK4 fits 64 registers/thread: 4 CTAs of 256 threads per SM.  The embedded pairs run ONE warp per CTA
 // (adaptive_stream); the register file is split over the four SM sub-partitions (16384 registers each), so the only
 // occupancies there are 3 warps per sub-partition at <= 168 registers (12 CTAs/SM) or 4 at <= 128 (16 CTAs/SM, with spills
@@ -372,7 +379,7 @@ __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp,
 template <int ALG>
 struct ens_launch {
     static constexpr int max_threads = (ALG == DTWA_ALG_RK4) ? 256 : (ALG == DTWA_ALG_RK8) ? DTWA_RK8_MAX_THREADS : 32;
-    static constexpr int min_blocks = (ALG == DTWA_ALG_RK4) ? 4 : (ALG == DTWA_ALG_RK8) ? 1 : DTWA_ADAPT_MIN_BLOCKS;
+    static constexpr int min_blocks = (ALG == DTWA_ALG_RK4) ? 4 : (ALG == DTWA_ALG_RK8) ? 1 : (ALG == DTWA_ALG_DP5) ? DTWA_DP5_MIN_BLOCKS : DTWA_ADAPT_MIN_BLOCKS;
 };
 
 // Reducers compiled at run time for one reducer set (dtwa_jit.hpp generates the definition: the same
