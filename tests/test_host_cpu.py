@@ -126,6 +126,101 @@ def test_julia_shim_struct_layouts_match_the_header():
     assert nargs == len(J["CSolver"]["fields"]), nargs
 
 
+def _parse_header_prototypes():
+    """{name: (return type, [parameter type classes])} for every `int|const char * dtwa_*(...)` prototype of the header.
+    Type classes: 'ptr', 'i32', 'i64', 'f64'."""
+    header = open(os.path.join(ROOT, "include", "dicketwa.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = {}
+    for ret, name, params in re.findall(r"^\s*((?:const\s+)?\w+\s*\*?)\s*(dtwa_\w+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S | re.M):
+        cls = []
+        params = " ".join(params.split())
+        if params and params != "void":
+            for prm in params.split(","):
+                prm = prm.strip()
+                if "*" in prm:
+                    cls.append("ptr")
+                else:
+                    base = re.sub(r"\bconst\b", "", prm).split()[0]
+                    cls.append({"int32_t": "i32", "uint32_t": "i32", "int": "i32", "int64_t": "i64", "uint64_t": "i64", "double": "f64"}[base])
+        protos[name] = ("ptr" if "*" in ret else "i32", cls)
+    return protos
+
+
+def _split_top_level(text):
+    out, depth, cur = [], 0, ""
+    for ch in text:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_shim_ccall_signatures_match_the_header():
+    """Julia cannot run here: every `ccall((:dtwa_x, libdicketwa), Ret, (ArgTypes...), args...)` of the shim must name an exported
+    function and pass the return type, the number of arguments and the pointer / 32-bit / 64-bit / double class of each one that
+    the prototype in include/dicketwa.h declares."""
+    P = _parse_header_prototypes()
+    assert len(P) >= 25 and "dtwa_ensemble" in P and P["dtwa_last_error"][0] == "ptr"
+    src = open(os.path.join(ROOT, "dickemodel.jl_b200", "julia", "DickeModelB200.jl")).read()
+    jl_cls = {"Cint": "i32", "Int32": "i32", "UInt32": "i32", "Int64": "i64", "UInt64": "i64", "Float64": "f64", "Cdouble": "f64", "Cstring": "ptr"}
+    seen = set()
+    for m in re.finditer(r"ccall\(\(:(dtwa_\w+), libdicketwa\),", src):
+        name = m.group(1)
+        seen.add(name)
+        assert name in P, f"{name} is not declared in include/dicketwa.h"
+        # the text of the call up to its matching parenthesis
+        i, depth = m.start() + len("ccall"), 0
+        for j in range(i, len(src)):
+            depth += src[j] in "([{"
+            depth -= src[j] in ")]}"
+            if depth == 0:
+                break
+        parts = _split_top_level(src[i + 1:j])
+        ret, argtypes, args = parts[1], parts[2], parts[3:]
+        assert argtypes.startswith("(") and argtypes.endswith(")"), (name, argtypes)
+        types = _split_top_level(argtypes[1:-1])
+        got = ["ptr" if t.startswith(("Ptr{", "Ref{")) else jl_cls[t] for t in types]
+        assert jl_cls.get(ret, "ptr" if ret.startswith("Ptr") else None) == P[name][0], (name, ret)
+        assert got == P[name][1], (name, got, P[name][1])
+        assert len(args) == len(types), (name, len(args), len(types))
+    # the entry points a DickeModel.jl user reaches through the shim
+    assert {"dtwa_create", "dtwa_destroy", "dtwa_integrate", "dtwa_ensemble", "dtwa_integrate_fm", "dtwa_lyapunov", "dtwa_integrate_events",
+            "dtwa_shell_quadrature", "dtwa_last_error"} <= seen
+
+
+def test_ctypes_prototypes_match_the_header(pkg):
+    """the mirror's `argtypes` (count and class of every parameter) against the prototypes of include/dicketwa.h"""
+    P = _parse_header_prototypes()
+    L = pkg._lib.load()
+
+    def cls_of(t):
+        if t in (ctypes.c_int, ctypes.c_int32, ctypes.c_uint32):
+            return "i32"
+        if t in (ctypes.c_int64, ctypes.c_uint64, ctypes.c_longlong, ctypes.c_ulonglong):
+            return "i64"
+        if t is ctypes.c_double:
+            return "f64"
+        return "ptr"
+    checked = 0
+    for name, (ret, params) in P.items():
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            continue
+        got = [cls_of(t) for t in fn.argtypes]
+        assert got == params, (name, got, params)
+        checked += 1
+    assert checked >= 20, checked
+
+
 def test_no_cpu_fallback(pkg):
     """without a CUDA device the product fails loudly instead of computing on the host"""
     try:
