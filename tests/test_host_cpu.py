@@ -385,6 +385,32 @@ def test_runtime_specialisation_compiles_without_a_gpu(pkg):
         lib.jit_compile(s, sol, ["q"])
 
 
+def test_specialised_kernels_keep_their_register_budgets(pkg, tmp_path, monkeypatch):
+    """the occupancy the kernels are designed for is a property of the compiled code: RK4 <= 64 registers
+    (4 CTAs of 256 threads per SM), DP5 <= 128 (16 one-warp CTAs), DOP853 <= 168 (12), no spill code beyond the samplers' stack
+    frame -- checked on the cubin NVRTC produces here, without a GPU"""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump is not on PATH")
+    from dickemodel_jl_b200 import TWA
+    lib = pkg._lib
+    out = str(tmp_path / "k.cubin")
+    monkeypatch.setenv("DTWA_JIT_DUMP", out)
+    s = lib.System()
+    s.kind = lib.SYS_DICKE
+    s.params[0], s.params[1], s.params[2] = 1.0, 1.0, 1.0
+    for alg, max_regs in ((lib.ALG_RK4, 64), (lib.ALG_DP5, 128), (lib.ALG_DOP853, 168)):
+        sol = lib.Solver()
+        sol.alg, sol.dt, sol.tol = alg, 2.0 ** -7, 1e-8
+        lib.jit_compile(s, sol, [str(TWA.Weyl.Jz(100) / 100)])
+        res = subprocess.run(["cuobjdump", "-res-usage", out], capture_output=True, text=True).stdout
+        m = re.search(r"Function dtwa_jit_ensemble:\s*REG:(\d+) STACK:(\d+)", res)
+        assert m, res
+        assert int(m.group(1)) <= max_regs, (alg, res)
+        assert int(m.group(2)) <= 128, (alg, res)   # (the out-of-line samplers pass the drawn point through the stack)
+
+
 def test_runtime_specialisation_marks_unit_parameters(pkg):
     """the generated source drops the multiplications by w and g only when the (sign-folded) parameter is exactly +-1
     (x * 1.0 == x, so the specialised kernel keeps the bits of the generic one)"""
