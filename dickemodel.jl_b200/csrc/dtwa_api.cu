@@ -352,8 +352,12 @@ static bool pair_streams(const dtwa_solver *sol)
     const bool fixed = sol->alg == DTWA_ALG_RK4 || sol->alg == DTWA_ALG_RK8;
     return enabled && !fixed && sol->output == DTWA_OUTPUT_STEP;
 }
-// what jit_source specialises on: the unit flags and (+9) the two-stream form
-static int jit_flags(const dtwa_system *sys, const dtwa_solver *sol) { return unit_flags(sys, sol->backwards) + (pair_streams(sol) ? 9 : 0); }
+// what jit_source specialises on: the unit flags, (+9) the two-stream form and (+18) the output mode of the adaptive kernels
+static int jit_flags(const dtwa_system *sys, const dtwa_solver *sol)
+{
+    const bool fixed = sol->alg == DTWA_ALG_RK4 || sol->alg == DTWA_ALG_RK8;
+    return unit_flags(sys, sol->backwards) + (pair_streams(sol) ? 9 : 0) + (!fixed && sol->output == DTWA_OUTPUT_HERMITE ? 18 : 0);
+}
 
 static int check_solver(const dtwa_solver *sol, bool fixed_needs_dt = true)
 {

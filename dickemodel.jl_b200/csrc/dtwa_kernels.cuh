@@ -419,7 +419,18 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
     int start_k = 0;
     uint64_t idx = 0;
     bool have = false;                                                // a trajectory is in flight
-    double tstop = 0.0;
+    double tstop = 0.0, tnext = 0.0;                                  // the next output time and the one after it (prefetched: a lane that
+                                                                      // lands on ts[k] must not wait for the load of ts[k+1])
+    // The loop control of the 7-stage pair is written lean: the output mode is a compile-time constant of a specialised unit (the
+    // other loop body is not generated), the maxiters test is a select, ts[k+1] is prefetched.  For the 12-stage pair the same
+    // source makes ptxas hoist 16 coefficients into vector registers (168 registers + spills, 32 R2UR per attempt: 838
+    // instructions and 2 080 statically scheduled cycles per attempt instead of 818 / 1 925), so it keeps the plain form.
+    constexpr bool LEAN = (ALG == DTWA_ALG_DP5);
+#ifdef DTWA_JIT_INTERP
+    const bool interp_mode = LEAN ? (DTWA_JIT_INTERP != 0) : (A.S.interp != 0);
+#else
+    const bool interp_mode = A.S.interp != 0;
+#endif
     uint32_t iters = 0;
     int budget = 0;                                                   // attempts left before maxiters (current trajectory)
     int tlim_k = -1;                                                  // Hermite outputs: the output index `tlim` was loaded for
@@ -525,6 +536,7 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
             have = true;
             k = 0;
             tstop = A.S.ts[0];
+            if constexpr (LEAN) tnext = A.S.ts[nt > 1 ? 1 : 0];
             budget = (int)(A.S.maxiters > 0x7fffffffll ? 0x7fffffffll : A.S.maxiters);
             tlim_k = -1;
         }
@@ -579,7 +591,7 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
         //  left before maxiters; one REDUX decides whether to leave)
         int ahead = have ? (int)(g - flushed) : 0;
 #ifdef DTWA_PIPELINED_LOOP   // (opt-in experiment, measured 0-3 % SLOWER except DP5 +3.6 %: ptxas keeps the emit block behind a branch)
-        if (JIT && !A.S.interp) {
+        if (JIT && !interp_mode) {
             // ---- software-pipelined form (specialised kernels, outputs by stepping onto ts[k]) ----
             // An attempt ends in a serial, latency-bound tail -- error norm -> controller -> commit -> emit -> vote -- during
             // which the warp feeds nothing to the FP64 pipe (30-40 % of its time with three warps per scheduler, ncu source
@@ -591,7 +603,7 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
             // same controller expressions as Adaptive::attempt: bit-identical trajectories.
             const CtrlPar &c = A.S.ctrl;
             bool pend = have && T.status == ST_OK && k < nt && ahead < R && !(T.ad.t < tstop);
-            double tnext = (have && k + 1 < nt) ? A.S.ts[k + 1] : tstop;
+            tnext = (have && k + 1 < nt) ? A.S.ts[k + 1] : tstop;
             unsigned vote = 2u;
 #pragma unroll 1
             while (true) {
@@ -664,19 +676,27 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
             const unsigned vote = __reduce_or_sync(0xffffffffu, (service ? 1u : 0u) | (behind ? 2u : 0u));
             if ((vote & 1u) || !(vote & 2u)) break;
             ++iters;
-            if (!A.S.interp) {
+            if (!interp_mode) {
             const bool stepping = have && ahead < R;
-            if (stepping && T.ad.t < tstop) {
-                if (budget <= 0) {
-                    T.status = ST_MAXITERS;
-                } else {
-                    --budget;
-                    bool accepted;
-                    if (T.ad.attempt(A.S.par, T.u, tstop, A.S.tol, A.S.dtmin, accepted, A.S.ctrl)) T.status = ST_DOMAIN;
-                    if (accepted)
-                        ++T.nacc;
-                    else if (T.status == ST_OK)
-                        ++T.nrej;
+            auto one_attempt = [&]() {
+                --budget;
+                bool accepted;
+                if (T.ad.attempt(A.S.par, T.u, tstop, A.S.tol, A.S.dtmin, accepted, A.S.ctrl)) T.status = ST_DOMAIN;
+                if (accepted)
+                    ++T.nacc;
+                else if (T.status == ST_OK)
+                    ++T.nrej;
+            };
+            if constexpr (LEAN) {
+                const bool want = stepping && T.ad.t < tstop;
+                if (want && budget <= 0) T.status = ST_MAXITERS;
+                if (want && budget > 0) one_attempt();
+            } else {
+                if (stepping && T.ad.t < tstop) {
+                    if (budget <= 0)
+                        T.status = ST_MAXITERS;
+                    else
+                        one_attempt();
                 }
             }
             const bool reached = stepping && T.status == ST_OK && !(T.ad.t < tstop);   // this lane emits output k now
@@ -685,7 +705,11 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
                 ++k;
                 ++ahead;
                 wslot = (wslot + 1 == R) ? 0 : wslot + 1;
-                if (k < nt) tstop = A.S.ts[k];
+                if constexpr (LEAN) {
+                    tstop = tnext;                                  // (== ts[k] whenever k < nt)
+                    if (k + 1 < nt) tnext = A.S.ts[k + 1];
+                } else if (k < nt)
+                    tstop = A.S.ts[k];
             }
             } else {
             // ---- DTWA_OUTPUT_HERMITE: steps ignore the output times (clipped only at tlim = the INTERP_MAX_OUT-th output time
