@@ -425,7 +425,10 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
     // other loop body is not generated), the maxiters test is a select, ts[k+1] is prefetched.  For the 12-stage pair the same
     // source makes ptxas hoist 16 coefficients into vector registers (168 registers + spills, 32 R2UR per attempt: 838
     // instructions and 2 080 statically scheduled cycles per attempt instead of 818 / 1 925), so it keeps the plain form.
-    constexpr bool LEAN = (ALG == DTWA_ALG_DP5);
+#ifndef DTWA_LEAN_DOP853
+#define DTWA_LEAN_DOP853 0   // (tuning experiments)
+#endif
+    constexpr bool LEAN = (ALG == DTWA_ALG_DP5) || (DTWA_LEAN_DOP853 != 0);
 #ifdef DTWA_JIT_INTERP
     const bool interp_mode = LEAN ? (DTWA_JIT_INTERP != 0) : (A.S.interp != 0);
 #else
