@@ -1261,19 +1261,32 @@ struct LaunchShape {
     double *ring;   // adaptive kernels: ring of raw states in global memory, [grid][window][32 lanes][nvar]
 };
 
-static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const EnsArgs &A, long long n, int nvar, LaunchShape &ls, int per_warp = 1)
+// DTWA_ADAPT_WARPS=n (environment; tuning experiment): the run-time specialised adaptive kernels are compiled for and launched
+// with n warp streams per CTA (dtwa_kernels.cuh); the interpreter kernels keep one.
+static int adapt_warps_env()
+{
+    static const int v = [] {
+        const char *e = std::getenv("DTWA_ADAPT_WARPS");
+        const int n = e ? std::atoi(e) : 1;
+        return (n == 2 || n == 4 || n == 8) ? n : 1;
+    }();
+    return v;
+}
+
+static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const EnsArgs &A, long long n, int nvar, LaunchShape &ls, int per_warp = 1,
+                     int warps = 1)
 {
     const bool fixed = alg == DTWA_ALG_RK4 || alg == DTWA_ALG_RK8;
     const int max_threads = alg == DTWA_ALG_RK4 ? ens_launch<DTWA_ALG_RK4>::max_threads : alg == DTWA_ALG_RK8 ? ens_launch<DTWA_ALG_RK8>::max_threads : 32;
     int block = ctx->block_threads ? ctx->block_threads : 256;
     if (block > max_threads) block = max_threads;
-    if (!fixed) block = 32;   // adaptive kernels: one warp per CTA (warp-level sliding flush, see ensemble_body)
+    if (!fixed) block = 32 * warps;   // adaptive kernels: independent warp streams (warp-level sliding flush, see ensemble_body), one per CTA by default
     // window: output times staged between two flushes.  Fixed step: one row per warp in shared memory (<= 24 KB),
     // one CTA-wide flush per window (16 -> 32 outputs per barrier is worth 0.6 %, measured).  Adaptive: a ring of raw
     // states in global memory (32 lanes x nvar doubles per output time and CTA), long enough (<= 256 output times, <= 1 GiB)
     // that lanes only wait for each other when they drift more than half a ring apart; shared memory holds one row of sums.
     const size_t slots = A.nslots > 0 ? A.nslots : 1;
-    const int rows = fixed ? block / 32 : 32;   // rows of the shared-memory staging (adaptive: one row of sums per lane for the ring flush)
+    const int rows = fixed ? block / 32 : block;   // rows of the shared-memory staging (adaptive: one row of sums per lane for the ring flush)
     const size_t per_out = sizeof(double) * rows * slots + sizeof(unsigned) * A.stage_bins + sizeof(unsigned);
     size_t wcap = fixed ? 32 : 256, wbudget = 24 * 1024;
     if (const char *e = std::getenv("DTWA_WINDOW")) wcap = (size_t)std::max(1, std::atoi(e));  // tuning experiments
@@ -1284,10 +1297,10 @@ static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const 
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
     if (per_sm < 1) return set_err(DTWA_ERR_CAPACITY, "ensemble kernel does not fit on an SM with this reducer set");
     if (ctx->ctas_per_sm > 0 && ctx->ctas_per_sm < per_sm) per_sm = ctx->ctas_per_sm;
-    long long want = (n + block - 1) / block;
-    long long cap = (long long)d.sm_count * per_sm * per_warp;
+    long long want = fixed ? (n + block - 1) / block : (n + 31) / 32;
+    long long cap = (long long)d.sm_count * per_sm * per_warp * (fixed ? 1 : warps);
     const int grid = (int)std::max(1ll, std::min(want, cap));
-    ls.per_warp = per_warp;
+    ls.per_warp = per_warp * (fixed ? 1 : warps);   // warp streams per CTA
     ls.ring = nullptr;
     if (!fixed) {
         // ring length: even, <= wcap, and the whole ring buffer <= 1 GiB
@@ -1621,7 +1634,8 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
             A.ranges = (const RangeD *)(m + o_r);
             A.hists = (const HistDesc *)(m + o_h);
             A.u64 = dp.d_u64;
-            TRY(shape_for(ctx, d, kern, sol->alg, A, dp.n, nv, shapes[di], used_jit && pair_streams(sol) ? 2 : 1));
+            TRY(shape_for(ctx, d, kern, sol->alg, A, dp.n, nv, shapes[di], used_jit && pair_streams(sol) ? 2 : 1,
+                          used_jit && !fixed && !pair_streams(sol) ? adapt_warps_env() : 1));
             dp.grid = shapes[di].grid;
             dp.block = shapes[di].block;
             const size_t pbytes = sizeof(double) * (size_t)dp.grid * nt * std::max(nslots, 1);
@@ -1696,7 +1710,8 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
                     A.N = cnt[di];
                     A.attempt = (uint32_t)round;
                     LaunchShape ls = shapes[di];
-                    ls.grid = (int)std::max(1ll, std::min<long long>((cnt[di] + ls.block - 1) / ls.block, shapes[di].grid));
+                    const int per_unit = fixed ? ls.block : 32;   // trajectories of the first pass of a CTA (fixed step) / warp stream (adaptive)
+                    ls.grid = (int)std::max(1ll, std::min<long long>((cnt[di] + per_unit - 1) / per_unit, shapes[di].grid));
                     TRY(launch_ens(d, kern, A, ls));
                     plan->launches++;
                     plan->rounds = std::max(plan->rounds, round);

@@ -376,10 +376,18 @@ __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp,
 // (adaptive_stream); the register file is split over the four SM sub-partitions (16384 registers each), so the only
 // occupancies there are 3 warps per sub-partition at <= 168 registers (12 CTAs/SM) or 4 at <= 128 (16 CTAs/SM, with spills
 // for the 12-stage pair).  Without a bound ptxas takes 170-213 registers and lands on 2 warps per sub-partition.
+// DTWA_ADAPT_WARPS: warp streams per CTA of the adaptive kernels.  Every warp is still its own "virtual CTA" (stream number
+// vcta = blockIdx.x * DTWA_ADAPT_WARPS + warp: its own ring, its own partial row, its own trajectories -- the same ones as
+// CTA vcta of the one-warp launch, so results are bit-identical); what changes is how the hardware places them: the warps of
+// one CTA go to the four schedulers of an SM in turn, one-warp CTAs go wherever a warp slot is free.
+#ifndef DTWA_ADAPT_WARPS
+#define DTWA_ADAPT_WARPS 1
+#endif
 template <int ALG>
 struct ens_launch {
-    static constexpr int max_threads = (ALG == DTWA_ALG_RK4) ? 256 : (ALG == DTWA_ALG_RK8) ? DTWA_RK8_MAX_THREADS : 32;
-    static constexpr int min_blocks = (ALG == DTWA_ALG_RK4) ? 4 : (ALG == DTWA_ALG_RK8) ? 1 : (ALG == DTWA_ALG_DP5) ? DTWA_DP5_MIN_BLOCKS : DTWA_ADAPT_MIN_BLOCKS;
+    static constexpr int adapt_blocks = (ALG == DTWA_ALG_DP5) ? DTWA_DP5_MIN_BLOCKS : DTWA_ADAPT_MIN_BLOCKS;
+    static constexpr int max_threads = (ALG == DTWA_ALG_RK4) ? 256 : (ALG == DTWA_ALG_RK8) ? DTWA_RK8_MAX_THREADS : 32 * DTWA_ADAPT_WARPS;
+    static constexpr int min_blocks = (ALG == DTWA_ALG_RK4) ? 4 : (ALG == DTWA_ALG_RK8) ? 1 : (adapt_blocks + DTWA_ADAPT_WARPS - 1) / DTWA_ADAPT_WARPS;
 };
 
 // Reducers compiled at run time for one reducer set (dtwa_jit.hpp generates the definition: the same
@@ -405,14 +413,14 @@ __device__ __forceinline__ void jit_reduce(const VmShared &V, const SamplerPar *
 // waits when it is more than R/2 .. R outputs ahead of the slowest lane of its warp.
 template <int SYS, int ALG, bool JIT>
 __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared &V, double *my_partial,
-                                                unsigned long long *nvalid_g, double *ring)
+                                                unsigned long long *nvalid_g, double *ring, const int vcta)
 {
     constexpr int NV = Sys<SYS>::NV, NVO = Sys<SYS>::NVO;
     const int lane = threadIdx.x & 31;
     const int nt = A.S.nt, W = A.window;
     const int H = (W >= 2) ? W / 2 : 1, R = (W >= 2) ? 2 * H : 1;   // half and ring size
-    const long long stride = (long long)gridDim.x * 32;
-    long long j = (long long)blockIdx.x * 32 + lane;                  // current trajectory of this lane
+    const long long stride = (long long)A.vgrid * 32;                 // (vgrid warp streams: one per warp of every CTA)
+    long long j = (long long)vcta * 32 + lane;                        // current trajectory of this lane
     long long g = 0, flushed = 0;                                     // stream positions: next output of this lane / flushed
     int k = nt;                                                       // next output index of the current trajectory (nt: none)
     int wslot = 0;                                                    // g % R, kept incrementally (no 64-bit division in the loop)
@@ -453,7 +461,7 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
         __syncwarp();
         const int cnt = (int)(f1 - f0);
         const int w0 = (int)(f0 % R), k0 = (int)(f0 % nt);
-        double *row = V.wsum + (size_t)lane * A.nslots;
+        double *row = V.wsum + (size_t)threadIdx.x * A.nslots;
         for (int c = 0; c < cnt; c += 32) {
             const int o = c + lane;
             const bool mine = o < cnt;
@@ -1077,7 +1085,12 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
     constexpr bool FIXED = is_fixed<ALG>::value;
     constexpr bool PERLANE = !FIXED;  // adaptive: one staging row per thread, no warp-level reduction
     const int nwarps = blockDim.x >> 5;
-    const int rows = PERLANE ? 32 : nwarps;   // rows of the shared-memory staging (adaptive kernels: one row of sums per LANE, used by the ring flush)
+    const int rows = PERLANE ? (int)blockDim.x : nwarps;   // rows of the shared-memory staging (adaptive kernels: one row of sums per LANE, used by the ring flush)
+#ifdef DTWA_PAIR_UNIT
+    const int vcta = blockIdx.x;
+#else
+    const int vcta = PERLANE ? (int)(blockIdx.x * nwarps + (threadIdx.x >> 5)) : (int)blockIdx.x;   // adaptive kernels: the warp's stream number
+#endif
     const int lane = threadIdx.x & 31;
     const int W = A.window;
     const int Ws = PERLANE ? 1 : W;   // output times staged in SHARED memory (the adaptive kernels' ring lives in global memory)
@@ -1109,9 +1122,11 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
         for (int i = threadIdx.x; i < Ws; i += blockDim.x) V.nvalid[i] = 0u;
         for (int i = threadIdx.x; i < A.stage2d_bins; i += blockDim.x) V.stage2d[i] = 0u;
 #ifndef DTWA_PAIR_UNIT   // (the two-stream kernels initialise the rings of their streams themselves)
-        if constexpr (PERLANE) {   // the CTA's ring of raw states in global memory: every cell starts empty (NaN marker)
-            double *ring = A.ring + (size_t)blockIdx.x * 32 * W * Sys<SYS>::NVO;
-            for (int i = threadIdx.x; i < 32 * W; i += blockDim.x) ring[(size_t)i * Sys<SYS>::NVO] = __longlong_as_double(0x7ff8000000000000ll);
+        if constexpr (PERLANE) {   // the warp's ring of raw states in global memory: every cell starts empty (NaN marker)
+            if (vcta < A.vgrid) {
+                double *ring = A.ring + (size_t)vcta * 32 * W * Sys<SYS>::NVO;
+                for (int i = lane; i < 32 * W; i += 32) ring[(size_t)i * Sys<SYS>::NVO] = __longlong_as_double(0x7ff8000000000000ll);
+            }
         }
 #endif
         V.consts = consts;
@@ -1134,8 +1149,16 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
         printf("CTA %d sm %u t %llu\n", (int)blockIdx.x, smid, t0);
     }
 #endif
+#if defined(DTWA_DIAG_WARPID)
+    if (lane == 0) {   // diagnostic: which SM and which warp slot (slot % 4 = scheduler) hosts this warp
+        unsigned smid, wid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        printf("WARP %d sm %u slot %u\n", vcta, smid, wid);
+    }
+#endif
     const int nt = A.S.nt;
-    double *my_partial = A.partial + (size_t)blockIdx.x * nt * A.nslots;
+    double *my_partial = A.partial + (size_t)vcta * nt * A.nslots;
     unsigned long long *nvalid_g = A.u64 + CNT_N;
 
     // small 2-D histograms (all times in one matrix) live in a per-CTA shared-memory tile: one shared-memory atomic per sample,
@@ -1164,7 +1187,8 @@ __device__ __forceinline__ void ensemble_body(const EnsArgs &A)
 #ifdef DTWA_PAIR_UNIT
         adaptive_stream_pair<SYS, ALG>(A, V, nvalid_g);
 #else
-        adaptive_stream<SYS, ALG, JIT>(A, V, my_partial, nvalid_g, A.ring + (size_t)blockIdx.x * 32 * W * Sys<SYS>::NVO);
+        if (vcta >= A.vgrid) return;   // (a CTA's last warps when the number of streams is not a multiple of DTWA_ADAPT_WARPS; no CTA barrier follows)
+        adaptive_stream<SYS, ALG, JIT>(A, V, my_partial, nvalid_g, A.ring + (size_t)vcta * 32 * W * Sys<SYS>::NVO, vcta);
 #endif
     } else {
     // ---- fixed step: persistent loop over batches of blockDim.x trajectories ----

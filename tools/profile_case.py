@@ -55,7 +55,23 @@ if a.alg not in ap_dt:
         kw["controller"] = a.controller
     if a.gains:
         kw.update(zip(("beta1", "beta2", "qmin", "qmax", "gamma"), (float(x) for x in a.gains.split(","))))
+import hashlib
 import warnings
+
+import numpy as np
+
+
+def _digest(out):   # bit-identity of the result across launch shapes
+    try:
+        arrs = out if isinstance(out, (list, tuple)) else [out]
+        h = hashlib.sha1()
+        for x in arrs:
+            h.update(np.ascontiguousarray(np.asarray(x, dtype=np.float64)).tobytes())
+        return h.hexdigest()[:12]
+    except Exception:
+        return "n/a"
+
+
 warnings.simplefilter("ignore")
 for rep in range(a.reps):
     W = TWA.coherent_Wigner_HWxSU2(center, j=j, seed=20261019)
@@ -82,4 +98,5 @@ for rep in range(a.reps):
     steps = i["steps_accepted"] + i["steps_rejected"]
     print(f"rep {rep}: {steps} steps in {i['kernel_ms']:.3f} ms kernel = {steps / i['kernel_ms'] / 1e6:.2f} Gsteps/s; "
           f"lane efficiency {steps / max(1, i['lane_steps']):.3f}; rejected {i['steps_rejected'] / max(1, steps):.4f}; failed {i['n_failed']}; "
-          f"launches {i['launches']}; jit {i['jit']}; alg {i.get('algorithm')} ctrl {i.get('controller')} {i.get('controller_gains')}", flush=True)
+          f"launches {i['launches']}; jit {i['jit']}; alg {i.get('algorithm')} ctrl {i.get('controller')} {i.get('controller_gains')}; "
+          f"sha1 {_digest(out)}", flush=True)
