@@ -1273,8 +1273,25 @@ static int adapt_warps_env()
     return v;
 }
 
+// Ring length of the adaptive kernels (output times per warp stream).  A long ring lets the lanes of a warp drift apart (lane
+// efficiency 0.97 at 256 against 0.94 at 64); a short one costs less per output -- measured on a B200 (profiles/r2_ring_length.md):
+// with about one output per attempted step (configs[0]: ts = 0:0.05:100 at tol 1e-12) 64 output times are 16 % faster for an
+// average, 5 % for histograms and the same for a variance, with one output per 3 or more attempts 256 are 1-2 % faster.  The
+// attempts per output interval are estimated from the tolerance: the embedded pairs take steps of about tol^(1/p) time units of
+// the fastest frequency (p = 8: 0.032 at 1e-12, 0.1 at 1e-8, measured 0.033 / 0.09; p = 5: measured 1.2-1.4 x that).
+static int adaptive_ring_cap(const dtwa_system *sys, const dtwa_solver *sol, const double *ts, int nt)
+{
+    if (nt < 2 || !(sol->tol > 0)) return 256;
+    double wmax = 1.0;
+    const int npar = sys->kind == DTWA_SYS_DICKE ? 3 : 2;
+    for (int i = 0; i < npar; ++i) wmax = std::max(wmax, std::fabs(sys->params[i]));
+    const double h = std::pow(sol->tol, sol->alg == DTWA_ALG_DP5 ? 0.2 : 0.125) / wmax;
+    const double spacing = std::fabs(ts[nt - 1] - ts[0]) / (nt - 1);
+    return (h >= 0.5 * spacing) ? 64 : 256;
+}
+
 static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const EnsArgs &A, long long n, int nvar, LaunchShape &ls, int per_warp = 1,
-                     int warps = 1)
+                     int warps = 1, int ring_cap = 256)
 {
     const bool fixed = alg == DTWA_ALG_RK4 || alg == DTWA_ALG_RK8;
     const int max_threads = alg == DTWA_ALG_RK4 ? ens_launch<DTWA_ALG_RK4>::max_threads : alg == DTWA_ALG_RK8 ? ens_launch<DTWA_ALG_RK8>::max_threads : 32;
@@ -1288,7 +1305,7 @@ static int shape_for(dtwa_ctx *ctx, DevCtx &d, const void *kern, int alg, const 
     const size_t slots = A.nslots > 0 ? A.nslots : 1;
     const int rows = fixed ? block / 32 : block;   // rows of the shared-memory staging (adaptive: one row of sums per lane for the ring flush)
     const size_t per_out = sizeof(double) * rows * slots + sizeof(unsigned) * A.stage_bins + sizeof(unsigned);
-    size_t wcap = fixed ? 32 : 256, wbudget = 24 * 1024;
+    size_t wcap = fixed ? 32 : (size_t)ring_cap, wbudget = 24 * 1024;
     if (const char *e = std::getenv("DTWA_WINDOW")) wcap = (size_t)std::max(1, std::atoi(e));  // tuning experiments
     int window = (int)std::max<size_t>(1, std::min<size_t>({wcap, (size_t)A.S.nt, fixed ? wbudget / per_out : wcap}));
     size_t smem = ens_smem_bytes(A.ncst, A.nrange, A.nhist, A.nslots, A.stage_bins, A.nins, rows, fixed ? window : 1, A.stage2d_bins);
@@ -1635,7 +1652,7 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
             A.hists = (const HistDesc *)(m + o_h);
             A.u64 = dp.d_u64;
             TRY(shape_for(ctx, d, kern, sol->alg, A, dp.n, nv, shapes[di], used_jit && pair_streams(sol) ? 2 : 1,
-                          used_jit && !fixed && !pair_streams(sol) ? adapt_warps_env() : 1));
+                          used_jit && !fixed && !pair_streams(sol) ? adapt_warps_env() : 1, fixed ? 256 : adaptive_ring_cap(sys, sol, ts, nt)));
             dp.grid = shapes[di].grid;
             dp.block = shapes[di].block;
             const size_t pbytes = sizeof(double) * (size_t)dp.grid * nt * std::max(nslots, 1);
