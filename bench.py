@@ -573,6 +573,20 @@ def main():
                 "hermite_output": {"note": "output='hermite': the reference's interpolated outputs (src/TWA.jl:180) instead of landing on every ts[k]",
                                    "gpu_wall_s": wall0h, "gpu_kernel_ms": i0h["kernel_ms"], "gpu_attempted_steps": i0h["steps_accepted"] + i0h["steps_rejected"],
                                    "max_abs_diff_mean_jz_vs_stepping": float(np.max(np.abs(g0h - g0)))}}
+            # the same dense grid in the throughput regime (the docs' larger ensembles): 1e6 trajectories
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                for _ in range(2):
+                    W0 = TWA.coherent_Wigner_HWxSU2(WORK["center"], j=j, seed=WORK["seed"])
+                    t0 = time.perf_counter()
+                    TWA.average(system, observable=jz, N=1000000, ts=ts0, distribution=W0)
+                    wall1 = time.perf_counter() - t0
+            i1 = dict(TWA.last_info)
+            extras["config0_grid_1e6_trajectories"] = {
+                "workload": "configs[0]'s grid and integrator (ts=0:0.05:100, tol=1e-12: about one output per 1.5 attempted steps) with N=1e6",
+                "gpu_wall_s": wall1, "gpu_kernel_ms": i1["kernel_ms"], "attempted_steps": i1["steps_accepted"] + i1["steps_rejected"],
+                "attempted_steps_per_s": (i1["steps_accepted"] + i1["steps_rejected"]) / (i1["kernel_ms"] * 1e-3),
+                "lane_efficiency": (i1["steps_accepted"] + i1["steps_rejected"]) / max(1, i1["lane_steps"])}
             # SURVEY 8f ranks 2-4 (the callers on the other side of `integrate`), small instances, for the record
             CSm, ESP = pkg.ClassicalSystems, pkg.EnergyShellProjections
             sysw = CD.ClassicalDickeSystem(w=0.8, g=0.8, w0=1)

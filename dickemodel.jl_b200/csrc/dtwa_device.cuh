@@ -407,14 +407,19 @@ __device__ __forceinline__ double group_sum(double s)
     return s;
 }
 template <int SYS>
-__device__ __forceinline__ double group_rms(const double (&x)[Sys<SYS>::NV])
+__device__ __forceinline__ double group_meansq(const double (&x)[Sys<SYS>::NV])
 {
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < Sys<SYS>::NV; ++i)
         if (norm_counted<SYS>(i)) s = fma(x[i], x[i], s);
     s = group_sum<SYS>(s);
-    return sqrt_fast(s * (1.0 / (double)Sys<SYS>::NORM_N));
+    return s * (1.0 / (double)Sys<SYS>::NORM_N);
+}
+template <int SYS>
+__device__ __forceinline__ double group_rms(const double (&x)[Sys<SYS>::NV])
+{
+    return sqrt_fast(group_meansq<SYS>(x));
 }
 
 template <int SYS>
@@ -588,6 +593,19 @@ __device__ __forceinline__ float ex2_approx(float x)
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// lg2 of a non-negative double from its bits: exponent + lg2 of the leading 24 bits of the significand (integer pipe + one
+// MUFU.LG2; no conversion that could overflow or flush).  0 and denormals give about -1023, +Inf and NaN about 1024.
+__device__ __forceinline__ float lg2_of_double(double x)
+{
+    const int hi = __double2hiint(x);
+    const unsigned lo = (unsigned)__double2loint(x);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    const float m = __int_as_float(0x3f800000 | ((hi & 0xfffff) << 3) | (int)(lo >> 29));
+    return (float)e + lg2_approx(m);
+}
+// lg2 of the error estimate for the step-size controller, clamped like err in [1e-30, 1e30]
+#define DTWA_LE_CLAMP 99.65784f
+__device__ __forceinline__ float clamp_le(float le) { return fminf(fmaxf(le, -DTWA_LE_CLAMP), DTWA_LE_CLAMP); }
 
 template <int SYS, int ALG>
 struct Adaptive {
@@ -640,8 +658,14 @@ struct Adaptive {
 
     // The stages and the error estimate of ONE trial step of length h from (y, k0): no decision, no state change.  Shared by
     // attempt() below and by the software-pipelined hot loop of the ensemble kernels, so that both take bit-identical steps.
+    // `le` = lg2(err) for the step-size controller, taken from the FACTORS of err in parallel with the square root that err itself
+    // needs (lg2 err = lg2|h| + lg2 n5 - lg2(den)/2 for the 5/3 combination, lg2(mean square)/2 for the 7-stage pair), so that the
+    // controller's chain does not wait for rsqrt -> product -> conversion.  MEASURED (call 23, -DDTWA_LE_FROM_FACTORS): +2.8 % for
+    // DOP853 under TsitPap8's gains, -4.7 % under DP8's gains and for DP5, a 10^4-trajectory call 4.93 instead of 4.84 ms -- the
+    // extra integer/MUFU instructions cost what the shorter chain returns.  attempt() therefore overrides it with lg2 of the
+    // finished estimate (the compiler drops the unused factor form); the two-stream and pipelined experiments do the same.
     __device__ __forceinline__ void trial(const SysPar &p, const double (&y)[NV], const double h, const double tol, double (&yn)[NV],
-                                          double (&kn)[NV], double &err) const
+                                          double (&kn)[NV], double &err, float &le) const
     {
         if constexpr (ALG == DTWA_ALG_DP5) {
 #include "dp5_body.inc"
@@ -654,7 +678,9 @@ struct Adaptive {
                 yn[i] = ynew[i];
                 kn[i] = DP5_KNEW[i];
             }
-            err = group_rms<SYS>(en);
+            const double msq = group_meansq<SYS>(en);
+            err = sqrt_fast(msq);
+            le = clamp_le(0.5f * lg2_of_double(msq));
 #undef DP5_KNEW
         } else {
 #include "dop853_body.inc"
@@ -674,9 +700,11 @@ struct Adaptive {
             n3 = group_sum<SYS>(n3);
             {
                 double is, sq;
-                rsqrt_sqrt_pair(fma(0.01, n3, n5) * (double)Sys<SYS>::NORM_N, is, sq);
+                const double den = fma(0.01, n3, n5) * (double)Sys<SYS>::NORM_N;
+                rsqrt_sqrt_pair(den, is, sq);
                 const double e = fabs(h) * n5 * is;
                 err = (n5 == 0.0 && n3 == 0.0) ? 0.0 : e;   // (0 * Inf otherwise)
+                le = clamp_le(lg2_of_double(fabs(h)) + fmaf(-0.5f, lg2_of_double(den), lg2_of_double(n5)));
             }
 #undef DOP853_KNEW
         }
@@ -689,7 +717,7 @@ struct Adaptive {
     // bit-identical steps.
     __device__ __forceinline__ static void trial2(const SysPar &p, const Adaptive &A0, const Adaptive &A1, const double (&ya)[NV], const double (&yb)[NV],
                                                   const double ha, const double hb, const double tol, double (&yna)[NV], double (&ynb)[NV],
-                                                  double (&kna)[NV], double (&knb)[NV], double &erra, double &errb)
+                                                  double (&kna)[NV], double (&knb)[NV], double &erra, double &errb, float &lea, float &leb)
     {
         D2 y[NV], k0[NV];
 #pragma unroll
@@ -718,8 +746,11 @@ struct Adaptive {
                 kna[i] = DP5_KNEW[i].a;
                 knb[i] = DP5_KNEW[i].b;
             }
-            erra = group_rms<SYS>(ena);
-            errb = group_rms<SYS>(enb);
+            const double msqa = group_meansq<SYS>(ena), msqb = group_meansq<SYS>(enb);
+            erra = sqrt_fast(msqa);
+            errb = sqrt_fast(msqb);
+            lea = clamp_le(0.5f * lg2_of_double(msqa));
+            leb = clamp_le(0.5f * lg2_of_double(msqb));
 #undef DP5_KNEW
         } else {
 #include "dop853_body.inc"
@@ -745,10 +776,13 @@ struct Adaptive {
             n3a = group_sum<SYS>(n3a);
             n3b = group_sum<SYS>(n3b);
             D2 is, sq;
-            rsqrt_sqrt_pair(D2{fma(0.01, n3a, n5a) * (double)Sys<SYS>::NORM_N, fma(0.01, n3b, n5b) * (double)Sys<SYS>::NORM_N}, is, sq);
+            const D2 den{fma(0.01, n3a, n5a) * (double)Sys<SYS>::NORM_N, fma(0.01, n3b, n5b) * (double)Sys<SYS>::NORM_N};
+            rsqrt_sqrt_pair(den, is, sq);
             const double ea = fabs(ha) * n5a * is.a, eb = fabs(hb) * n5b * is.b;
             erra = (n5a == 0.0 && n3a == 0.0) ? 0.0 : ea;
             errb = (n5b == 0.0 && n3b == 0.0) ? 0.0 : eb;
+            lea = clamp_le(lg2_of_double(fabs(ha)) + fmaf(-0.5f, lg2_of_double(den.a), lg2_of_double(n5a)));
+            leb = clamp_le(lg2_of_double(fabs(hb)) + fmaf(-0.5f, lg2_of_double(den.b), lg2_of_double(n5b)));
 #undef DOP853_KNEW
         }
 #undef DTWA_STEP_H
@@ -781,8 +815,12 @@ struct Adaptive {
             h = tstop - t;
         }
         double err;
+        float le;
         double yn[NV], kn[NV];
-        trial(p, y, h, tol, yn, kn, err);
+        trial(p, y, h, tol, yn, kn, err, le);
+#ifndef DTWA_LE_FROM_FACTORS   // default: lg2 of the finished error estimate (trial()'s factor form is an opt-in experiment)
+        le = lg2_approx(fminf(fmaxf((float)err, 1e-30f), 1e30f));
+#endif
         const bool bad = state_bad<SYS>(yn) || !(err == err) || isinf(err);
         if (bad) {
             if (forced) return 1;
@@ -790,7 +828,6 @@ struct Adaptive {
             rejected = true;
             return 0;
         }
-        const float le = lg2_approx(fminf(fmaxf((float)err, 1e-30f), 1e30f));
         const float e_rej = ex2_approx(-c.b1 * le);
         const float e_acc = ex2_approx(-fmaf(c.b1, le, c.nb2 * lqold));
         float fac_acc = fminf(c.fac_max, fmaxf(c.fac_min_acc, c.g * e_acc));   // err == 0: e_acc = +inf, clamped to fac_max

@@ -647,10 +647,13 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
                 double h = last ? tstop - T.ad.t : habs_eff;
                 if (!active) h = 0.0;
                 double yn[NV], kn[NV], err;
-                T.ad.trial(A.S.par, T.u, h, A.S.tol, yn, kn, err);
+                float le;
+                T.ad.trial(A.S.par, T.u, h, A.S.tol, yn, kn, err, le);
                 // [C] decisions as selects
                 const bool bad = state_bad<SYS>(yn) || !(err == err) || isinf(err);
-                const float le = lg2_approx(fminf(fmaxf((float)err, 1e-30f), 1e30f));
+#ifndef DTWA_LE_FROM_FACTORS
+                le = lg2_approx(fminf(fmaxf((float)err, 1e-30f), 1e30f));
+#endif
                 const float e_rej = ex2_approx(-c.b1 * le);
                 const float e_acc = ex2_approx(-fmaf(c.b1, le, c.nb2 * T.ad.lqold));
                 float fac_acc = fminf(c.fac_max, fmaxf(c.fac_min_acc, c.g * e_acc));
@@ -684,8 +687,12 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
             // leave when a lane needs service or a half of the ring can be flushed
             const bool service = have && (T.status != ST_OK || k >= nt);
             const bool behind = have && ahead < H;          // this lane still keeps the older half of the ring busy
+#ifndef DTWA_VOTE_ANY
             const unsigned vote = __reduce_or_sync(0xffffffffu, (service ? 1u : 0u) | (behind ? 2u : 0u));
             if ((vote & 1u) || !(vote & 2u)) break;
+#else   // (experiment, call 23: two VOTE.ANY straight into predicates -- 1 % slower than the one REDUX.OR)
+            if (__any_sync(0xffffffffu, service) || !__any_sync(0xffffffffu, behind)) break;
+#endif
             ++iters;
             if (!interp_mode) {
             const bool stepping = have && ahead < R;
@@ -1013,12 +1020,18 @@ __device__ __forceinline__ void adaptive_stream_pair(const EnsArgs &A, const VmS
                     if (!act[s]) h[s] = 0.0;
                 }
                 double yn[2][NV], kn[2][NV], err[2];
-                Adaptive<SYS, ALG>::trial2(A.S.par, T[0].ad, T[1].ad, T[0].u, T[1].u, h[0], h[1], A.S.tol, yn[0], yn[1], kn[0], kn[1], err[0], err[1]);
+                float le2[2];
+                Adaptive<SYS, ALG>::trial2(A.S.par, T[0].ad, T[1].ad, T[0].u, T[1].u, h[0], h[1], A.S.tol, yn[0], yn[1], kn[0], kn[1], err[0], err[1], le2[0],
+                                           le2[1]);
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     // the decisions of Adaptive::attempt, as selects
                     const bool bad = state_bad<SYS>(yn[s]) || !(err[s] == err[s]) || isinf(err[s]);
+#ifdef DTWA_LE_FROM_FACTORS
+                    const float le = le2[s];
+#else
                     const float le = lg2_approx(fminf(fmaxf((float)err[s], 1e-30f), 1e30f));
+#endif
                     const float e_rej = ex2_approx(-c.b1 * le);
                     const float e_acc = ex2_approx(-fmaf(c.b1, le, c.nb2 * T[s].ad.lqold));
                     float fac_acc = fminf(c.fac_max, fmaxf(c.fac_min_acc, c.g * e_acc));
