@@ -48,7 +48,52 @@ def workload_name(n_per_gpu):
             f"ts=0:0.05:100 (nt=2001), RK4 with 7 sub-steps of 0.05/7 per output interval (dt <= 2^-7; 14000 steps/trajectory), <Jz>/j")
 
 
-def clocks_sampler_start(path):
+class _NvmlSampler:
+    """SM clock, power and clock-event reasons of one GPU every 200 ms from a thread of this process (NVML through pynvml:
+    ~50 us per sample).  Writes the rows `nvidia-smi --query-gpu=... -lms 200` would write, for clocks_summary().  A separate
+    nvidia-smi process polling during the timed region cost the device leg 1-17 ms per 0.8 s step depending on the box
+    (profiles/r2_bench_n1_*.json: ms_per_step - kernel_ms_per_step), which the leg without a sampler never showed."""
+
+    def __init__(self, path, device_index, pci_bus_id):
+        import threading
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        self.h = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode()) if pci_bus_id else pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        self.idx, self.f, self.stop = device_index, open(path, "w"), threading.Event()
+        self.smax = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        names = (nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown, nv.nvmlClocksEventReasonSwThermalSlowdown,
+                 nv.nvmlClocksEventReasonSwPowerCap)
+        while not self.stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                flags = ",".join("Active" if (r & m) else "Not Active" for m in names)
+                self.f.write(f"{self.idx},{sm},{self.smax},{pw:.2f},0x{r:016x},{flags}\n")
+                self.f.flush()
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def terminate(self):
+        self.stop.set()
+
+    def wait(self):
+        self.t.join(timeout=2.0)
+        self.f.close()
+
+
+def clocks_sampler_start(path, device_index=0, pci_bus_id=None):
+    try:
+        return _NvmlSampler(path, device_index, pci_bus_id)
+    except Exception:
+        pass
     q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     try:
@@ -260,7 +305,12 @@ def main():
     barrier()
     clk_path = os.path.join(ROOT, "gpurun_out", f"clocks_rank{rank}.csv")
     os.makedirs(os.path.dirname(clk_path), exist_ok=True)
-    sampler = clocks_sampler_start(clk_path) if rank == 0 else None
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        pci = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+    except Exception:
+        pci = None
+    sampler = clocks_sampler_start(clk_path, local, pci) if rank == 0 else None
     e0.record(stream)
     steps_done, kernel_ms, launches, last = 0, 0.0, 0, None
     for _ in range(args.steps):

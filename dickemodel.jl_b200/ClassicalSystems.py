@@ -90,7 +90,8 @@ class _Alg:
 
     @property
     def runs_as(self):
-        return {_lib.ALG_RK4: "RK4", _lib.ALG_RK8: "RK8 (DOP853 weights, fixed step)", _lib.ALG_DP5: "DP5", _lib.ALG_DOP853: "DOP853"}[self.code]
+        return {_lib.ALG_RK4: "RK4", _lib.ALG_RK8: "RK8 (DOP853 weights, fixed step)", _lib.ALG_DP5: "DP5", _lib.ALG_DOP853: "DOP853",
+                _lib.ALG_TSIT5: "Tsit5"}[self.code]
 
 
 DP8 = _Alg("DP8", _lib.ALG_DOP853, False)
@@ -105,7 +106,9 @@ _GENERIC8 = (7.0 / 80.0, 2.0 / 40.0, 0.2, 10.0)
 _GENERIC5 = (7.0 / 50.0, 2.0 / 25.0, 0.2, 10.0)
 TsitPap8 = _Alg("TsitPap8", _lib.ALG_DOP853, False, "the Tsitouras-Papakostas tableau is not available offline", _GENERIC8)
 Vern8 = _Alg("Vern8", _lib.ALG_DOP853, False, "Verner's tableau is not available offline", _GENERIC8)
-Tsit5 = _Alg("Tsit5", _lib.ALG_DP5, False, "Tsitouras' tableau is not available offline", _GENERIC5)
+# Tsitouras' 5(4) pair itself (tools/gen_tableaux.py: the published coefficients, checked against the order conditions), under the
+# generic order-5 gains OrdinaryDiffEq gives it
+Tsit5 = _Alg("Tsit5", _lib.ALG_TSIT5, False, "", _GENERIC5)
 _BY_NAME = {a.name.lower(): a for a in (DP8, DP5, RK4, RK8, TsitPap8, Vern8, Tsit5)}
 _BY_NAME["dop853"] = DP8
 _warned_substitution = set()
@@ -203,7 +206,7 @@ def solver_from_kargs(kargs: dict) -> _lib.Solver:
     else:
         raise ValueError(f"controller={controller!r}: use 'ode' (OrdinaryDiffEq's, the default) or 'scipy'")
     last_solver.clear()
-    last_solver.update(requested=alg.name, algorithm={_lib.ALG_RK4: "RK4", _lib.ALG_RK8: "RK8", _lib.ALG_DP5: "DP5", _lib.ALG_DOP853: "DOP853"}[code],
+    last_solver.update(requested=alg.name, algorithm={_lib.ALG_RK4: "RK4", _lib.ALG_RK8: "RK8", _lib.ALG_DP5: "DP5", _lib.ALG_DOP853: "DOP853", _lib.ALG_TSIT5: "Tsit5"}[code],
                        substituted=bool(alg.note), controller=None if fixed else ctrl_name, chart="bloch" if s.chart == _lib.CHART_BLOCH else "qp", output="hermite" if (s.output == _lib.OUTPUT_HERMITE and not fixed) else "step",
                        gains=None if (fixed or s.controller != _lib.CTRL_ODE) else effective_gains(s))
     return s
@@ -224,9 +227,10 @@ def _beta1_from_beta2(alg, code, beta2):
 
 def effective_gains(s: _lib.Solver):
     """the gains the library will use for this solver (mirror of make_ctrl in csrc/dtwa_api.cu)"""
-    dp5 = s.alg == _lib.ALG_DP5
-    beta2 = max(0.0, s.beta2) if s.beta1 > 0 else (0.04 if dp5 else 0.0)
-    beta1 = s.beta1 if s.beta1 > 0 else (0.2 - 3.0 * beta2 / 4.0 if dp5 else 0.125 - beta2 / 5.0)
+    tsit5 = s.alg == _lib.ALG_TSIT5
+    dp5 = s.alg == _lib.ALG_DP5 or tsit5
+    beta2 = max(0.0, s.beta2) if s.beta1 > 0 else (0.08 if tsit5 else 0.04 if dp5 else 0.0)
+    beta1 = s.beta1 if s.beta1 > 0 else (0.14 if tsit5 else 0.2 - 3.0 * beta2 / 4.0 if dp5 else 0.125 - beta2 / 5.0)
     return {"beta1": beta1, "beta2": beta2, "qmin": s.qmin if s.qmin > 0 else (0.2 if dp5 else 1.0 / 3.0),
             "qmax": s.qmax if s.qmax > 0 else (10.0 if dp5 else 6.0), "gamma": s.gamma if s.gamma > 0 else 0.9,
             "qoldinit": s.qoldinit if s.qoldinit > 0 else 1e-4}

@@ -20,7 +20,7 @@ ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_EXPR, ERR_NCCL, ERR_TOO_MANY_FAILURES,
 TRAJ_OK, TRAJ_DOMAIN, TRAJ_MAXITERS, TRAJ_BAD_IC = 0, 1, 2, 3
 LYAP_MAXITERS = 5
 SYS_DICKE, SYS_LMG = 0, 1
-ALG_RK4, ALG_RK8, ALG_DP5, ALG_DOP853 = 0, 1, 2, 3
+ALG_RK4, ALG_RK8, ALG_DP5, ALG_DOP853, ALG_TSIT5 = 0, 1, 2, 3, 4
 CTRL_ODE, CTRL_SCIPY = 0, 1
 CHART_QP, CHART_BLOCH = 0, 1
 OUTPUT_STEP, OUTPUT_HERMITE = 0, 1

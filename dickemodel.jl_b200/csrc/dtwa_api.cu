@@ -362,7 +362,7 @@ static int jit_flags(const dtwa_system *sys, const dtwa_solver *sol)
 static int check_solver(const dtwa_solver *sol, bool fixed_needs_dt = true)
 {
     if (!sol) return set_err(DTWA_ERR_INVALID, "solver is NULL");
-    if (sol->alg < DTWA_ALG_RK4 || sol->alg > DTWA_ALG_DOP853) return set_err(DTWA_ERR_INVALID, "unknown solver alg");
+    if (sol->alg < DTWA_ALG_RK4 || sol->alg > DTWA_ALG_TSIT5) return set_err(DTWA_ERR_INVALID, "unknown solver alg");
     const bool fixed = sol->alg == DTWA_ALG_RK4 || sol->alg == DTWA_ALG_RK8;
     if (fixed && fixed_needs_dt && !(sol->dt > 0)) return set_err(DTWA_ERR_INVALID, "fixed-step algorithms need dt > 0");
     if (!fixed && !(sol->tol > 0)) return set_err(DTWA_ERR_INVALID, "adaptive algorithms need tol > 0");
@@ -445,7 +445,8 @@ static CtrlPar make_ctrl(const dtwa_solver *sol, bool force_scipy)
 {
     CtrlPar c;
     std::memset(&c, 0, sizeof(c));
-    const bool dp5 = sol->alg == DTWA_ALG_DP5;
+    const bool tsit5 = sol->alg == DTWA_ALG_TSIT5;       // generic gains of an order-5 method: beta2 = 2/(5 p), beta1 = 7/(10 p)
+    const bool dp5 = sol->alg == DTWA_ALG_DP5 || tsit5;  // (what the two 5(4) pairs share: exponent 1/5, qmin 1/5, qmax 10)
     if (force_scipy || sol->controller == DTWA_CTRL_SCIPY) {
         c.kind = DTWA_CTRL_SCIPY;
         c.b1 = dp5 ? 0.2f : 0.125f;      // 1 / (error estimator order + 1)
@@ -461,8 +462,8 @@ static CtrlPar make_ctrl(const dtwa_solver *sol, bool force_scipy)
         return c;
     }
     // gains: beta1 > 0 means the caller sets beta1 AND beta2 (beta2 = 0 is a legitimate choice); otherwise the defaults
-    const double beta2 = sol->beta1 > 0 ? std::max(0.0, sol->beta2) : (dp5 ? 0.04 : 0.0);
-    const double beta1 = sol->beta1 > 0 ? sol->beta1 : (dp5 ? 0.2 - 3.0 * beta2 / 4.0 : 0.125 - beta2 / 5.0);
+    const double beta2 = sol->beta1 > 0 ? std::max(0.0, sol->beta2) : (tsit5 ? 0.08 : dp5 ? 0.04 : 0.0);
+    const double beta1 = sol->beta1 > 0 ? sol->beta1 : (tsit5 ? 0.14 : dp5 ? 0.2 - 3.0 * beta2 / 4.0 : 0.125 - beta2 / 5.0);
     const double qmin = sol->qmin > 0 ? sol->qmin : (dp5 ? 0.2 : 1.0 / 3.0);
     const double qmax = sol->qmax > 0 ? sol->qmax : (dp5 ? 10.0 : 6.0);
     const double gamma = sol->gamma > 0 ? sol->gamma : 0.9;
@@ -553,6 +554,7 @@ static int by_alg(int alg, F &&f)
     case DTWA_ALG_RK4: return f(std::integral_constant<int, DTWA_ALG_RK4>());
     case DTWA_ALG_RK8: return f(std::integral_constant<int, DTWA_ALG_RK8>());
     case DTWA_ALG_DP5: return f(std::integral_constant<int, DTWA_ALG_DP5>());
+    case DTWA_ALG_TSIT5: return f(std::integral_constant<int, DTWA_ALG_TSIT5>());
     default: return f(std::integral_constant<int, DTWA_ALG_DOP853>());
     }
 }
@@ -1285,7 +1287,7 @@ static int adaptive_ring_cap(const dtwa_system *sys, const dtwa_solver *sol, con
     double wmax = 1.0;
     const int npar = sys->kind == DTWA_SYS_DICKE ? 3 : 2;
     for (int i = 0; i < npar; ++i) wmax = std::max(wmax, std::fabs(sys->params[i]));
-    const double h = std::pow(sol->tol, sol->alg == DTWA_ALG_DP5 ? 0.2 : 0.125) / wmax;
+    const double h = std::pow(sol->tol, (sol->alg == DTWA_ALG_DP5 || sol->alg == DTWA_ALG_TSIT5) ? 0.2 : 0.125) / wmax;
     const double spacing = std::fabs(ts[nt - 1] - ts[0]) / (nt - 1);
     return (h >= 0.5 * spacing) ? 64 : 256;
 }
@@ -2021,7 +2023,7 @@ extern "C" int dtwa_jit_compile(const dtwa_system *sys, const dtwa_solver *sol, 
                                 char *src_out, int64_t src_cap, int64_t *cubin_bytes)
 {
     TRY(check_system(sys));
-    if (!sol || sol->alg < DTWA_ALG_RK4 || sol->alg > DTWA_ALG_DOP853) return set_err(DTWA_ERR_INVALID, "unknown solver alg");
+    if (!sol || sol->alg < DTWA_ALG_RK4 || sol->alg > DTWA_ALG_TSIT5) return set_err(DTWA_ERR_INVALID, "unknown solver alg");
     if (!exprs || nexpr < 1) return set_err(DTWA_ERR_INVALID, "at least one expression is required");
     Program prog;
     try {

@@ -523,6 +523,7 @@ __device__ __forceinline__ void rk4_step(const SysPar &p, double (&u)[Sys<SYS>::
 // coefficient tables of the embedded pairs, in constant memory (see tools/gen_tableaux.py)
 #define DTWA_TABLEAU_CONSTANTS
 #include "dp5_body.inc"
+#include "tsit5_body.inc"
 #include "dop853_body.inc"
 #undef DTWA_TABLEAU_CONSTANTS
 
@@ -610,7 +611,8 @@ __device__ __forceinline__ float clamp_le(float le) { return fminf(fmaxf(le, -DT
 template <int SYS, int ALG>
 struct Adaptive {
     static constexpr int NV = Sys<SYS>::NV;
-    static constexpr int ERR_ORDER = (ALG == DTWA_ALG_DP5) ? 4 : 7;
+    static constexpr bool FIVE = (ALG == DTWA_ALG_DP5 || ALG == DTWA_ALG_TSIT5);   // the two 7-stage FSAL pairs of order 5(4)
+    static constexpr int ERR_ORDER = FIVE ? 4 : 7;
     double t, habs;
     double hlast;      // length of the last accepted step (interpolated outputs)
     double k0[NV];
@@ -682,6 +684,21 @@ struct Adaptive {
             err = sqrt_fast(msq);
             le = clamp_le(0.5f * lg2_of_double(msq));
 #undef DP5_KNEW
+        } else if constexpr (ALG == DTWA_ALG_TSIT5) {
+#include "tsit5_body.inc"
+            (void)dy;
+            double en[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const double sc = fma(fmax(fabs(y[i]), fabs(ynew[i])), tol, tol);
+                en[i] = e5[i] * h * rcp_fast(sc);
+                yn[i] = ynew[i];
+                kn[i] = TSIT5_KNEW[i];
+            }
+            const double msq = group_meansq<SYS>(en);
+            err = sqrt_fast(msq);
+            le = clamp_le(0.5f * lg2_of_double(msq));
+#undef TSIT5_KNEW
         } else {
 #include "dop853_body.inc"
             double n5 = 0.0, n3 = 0.0;
@@ -752,6 +769,26 @@ struct Adaptive {
             lea = clamp_le(0.5f * lg2_of_double(msqa));
             leb = clamp_le(0.5f * lg2_of_double(msqb));
 #undef DP5_KNEW
+        } else if constexpr (ALG == DTWA_ALG_TSIT5) {
+#include "tsit5_body.inc"
+            (void)dy;
+            double ena[NV], enb[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const double sca = fma(fmax(fabs(y[i].a), fabs(ynew[i].a)), tol, tol), scb = fma(fmax(fabs(y[i].b), fabs(ynew[i].b)), tol, tol);
+                ena[i] = e5[i].a * ha * rcp_fast(sca);
+                enb[i] = e5[i].b * hb * rcp_fast(scb);
+                yna[i] = ynew[i].a;
+                ynb[i] = ynew[i].b;
+                kna[i] = TSIT5_KNEW[i].a;
+                knb[i] = TSIT5_KNEW[i].b;
+            }
+            const double msqa = group_meansq<SYS>(ena), msqb = group_meansq<SYS>(enb);
+            erra = sqrt_fast(msqa);
+            errb = sqrt_fast(msqb);
+            lea = clamp_le(0.5f * lg2_of_double(msqa));
+            leb = clamp_le(0.5f * lg2_of_double(msqb));
+#undef TSIT5_KNEW
         } else {
 #include "dop853_body.inc"
             double n5a = 0.0, n3a = 0.0, n5b = 0.0, n3b = 0.0;

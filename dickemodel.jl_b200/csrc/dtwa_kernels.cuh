@@ -385,7 +385,7 @@ __device__ __forceinline__ void vm_run(const VmShared &V, const SamplerPar *smp,
 #endif
 template <int ALG>
 struct ens_launch {
-    static constexpr int adapt_blocks = (ALG == DTWA_ALG_DP5) ? DTWA_DP5_MIN_BLOCKS : DTWA_ADAPT_MIN_BLOCKS;
+    static constexpr int adapt_blocks = (ALG == DTWA_ALG_DP5 || ALG == DTWA_ALG_TSIT5) ? DTWA_DP5_MIN_BLOCKS : DTWA_ADAPT_MIN_BLOCKS;
     static constexpr int max_threads = (ALG == DTWA_ALG_RK4) ? 256 : (ALG == DTWA_ALG_RK8) ? DTWA_RK8_MAX_THREADS : 32 * DTWA_ADAPT_WARPS;
     static constexpr int min_blocks = (ALG == DTWA_ALG_RK4) ? 4 : (ALG == DTWA_ALG_RK8) ? 1 : (adapt_blocks + DTWA_ADAPT_WARPS - 1) / DTWA_ADAPT_WARPS;
 };
@@ -436,7 +436,7 @@ __device__ __forceinline__ void adaptive_stream(const EnsArgs &A, const VmShared
 #ifndef DTWA_LEAN_DOP853
 #define DTWA_LEAN_DOP853 0   // (tuning experiments)
 #endif
-    constexpr bool LEAN = (ALG == DTWA_ALG_DP5) || (DTWA_LEAN_DOP853 != 0);
+    constexpr bool LEAN = (ALG == DTWA_ALG_DP5 || ALG == DTWA_ALG_TSIT5) || (DTWA_LEAN_DOP853 != 0);
 #ifdef DTWA_JIT_INTERP
     const bool interp_mode = LEAN ? (DTWA_JIT_INTERP != 0) : (A.S.interp != 0);
 #else

@@ -94,7 +94,7 @@ mutable struct CResult
 end
 
 const SYS_DICKE, SYS_LMG = Int32(0), Int32(1)
-const ALG_RK4, ALG_RK8, ALG_DP5, ALG_DOP853 = Int32(0), Int32(1), Int32(2), Int32(3)
+const ALG_RK4, ALG_RK8, ALG_DP5, ALG_DOP853, ALG_TSIT5 = Int32(0), Int32(1), Int32(2), Int32(3), Int32(4)
 const CTRL_ODE, CTRL_SCIPY = Int32(0), Int32(1)
 const CHART_QP, CHART_BLOCH = Int32(0), Int32(1)
 const OUTPUT_STEP, OUTPUT_HERMITE = Int32(0), Int32(1)
@@ -164,12 +164,12 @@ function csolver(; tol::Real=1e-12, integrator_alg=:TsitPap8, integate_backwards
                  qmin=nothing, qmax=nothing, gamma=nothing, qoldinit=nothing, chart=:qp, output=:step, ignored...)
     name = Symbol(replace(string(integrator_alg isa Symbol ? integrator_alg : nameof(typeof(integrator_alg))), "()" => ""))
     alg = name in (:DP8, :TsitPap8, :Vern8, :DOP853) ? ALG_DOP853 :
-          name in (:DP5, :Tsit5) ? ALG_DP5 :
+          name == :DP5 ? ALG_DP5 : name == :Tsit5 ? ALG_TSIT5 :
           name == :RK4 ? ALG_RK4 : name == :RK8 ? ALG_RK8 :
           error("integrator_alg=$name is not available in libdicketwa")
-    if name in (:TsitPap8, :Vern8, :Tsit5) && !(name in warned_substitution)
+    if name in (:TsitPap8, :Vern8) && !(name in warned_substitution)
         push!(warned_substitution, name)
-        @warn "integrator_alg=$name(): its tableau is not part of libdicketwa; the same-order pair $(alg == ALG_DOP853 ? "DOP853" : "DP5") runs instead, under OrdinaryDiffEq's step controller for $name"
+        @warn "integrator_alg=$name(): its tableau is not part of libdicketwa; the same-order pair DOP853 runs instead, under OrdinaryDiffEq's step controller for $name"
     end
     if adaptive === false && alg == ALG_DOP853
         alg = ALG_RK8

@@ -73,13 +73,15 @@ typedef struct {
 #define DTWA_ALG_RK8 1     /* DOP853 8th-order weights, fixed step dt */
 #define DTWA_ALG_DP5 2     /* Dormand-Prince 5(4), adaptive  (reference: integrator_alg=DP5()) */
 #define DTWA_ALG_DOP853 3  /* Hairer DOP853 8(5,3), adaptive (reference: integrator_alg=DP8()) */
+#define DTWA_ALG_TSIT5 4   /* Tsitouras 5(4), adaptive       (reference: integrator_alg=Tsit5()) */
 /* Step-size controller of the adaptive pairs.
  *  DTWA_CTRL_ODE (0, default): OrdinaryDiffEq's, i.e. what the reference's solve() runs (src/ClassicalSystems.jl:138):
  *    q = EEst^beta1 / qold^beta2 / gamma clamped to [1/qmax, 1/qmin]; accept when EEst <= 1, then dt/q and
  *    qold = max(EEst, qoldinit); rejected: dt / min(1/qmin, EEst^beta1/gamma); isoutofdomain: dt*qmin.
  *    beta1/beta2/qmin/qmax/gamma/qoldinit are solve()'s keywords of the same names.  beta1 > 0 sets beta1 and beta2
  *    together (beta2 = 0 is then taken literally); any other field <= 0 -- and a zero-initialised struct -- selects
- *    OrdinaryDiffEq's default for the algorithm: DP5 0.17/0.04/0.2/10, DP8 0.125/0/(1/3)/6, gamma 0.9, qoldinit 1e-4.
+ *    OrdinaryDiffEq's default for the algorithm: DP5 0.17/0.04/0.2/10, DP8 0.125/0/(1/3)/6, Tsit5 0.14/0.08/0.2/10, gamma 0.9,
+ *    qoldinit 1e-4.
  *    The shim passes the generic order-8 gains 7/80, 1/20, 1/5, 10 for integrator_alg = TsitPap8() / Vern8().
  *  DTWA_CTRL_SCIPY (1): SciPy's rk.py controller (factor 0.9 err^(-1/(q+1)) in [0.2,10], no growth after a rejection);
  *    the golden SciPy step counts (tests/golden/scipy_pairs.json) pin the tableaux through it.

@@ -34,6 +34,11 @@
 #define ALG_RK8 1 /* fixed step with the DOP853 8th-order weights */
 #define ALG_DP5 2
 #define ALG_DOP853 3
+#define ALG_TSIT5 4 /* Tsitouras 5(4): the same structure as DP5 (6 stages + FSAL, one 4th-order error estimator), its own tableau */
+#define IS_FIVE(alg) ((alg) == ALG_DP5 || (alg) == ALG_TSIT5)
+#define FIVE_A(alg) ((alg) == ALG_TSIT5 ? &TSIT5_A[0][0] : &DP5_A[0][0])
+#define FIVE_B(alg) ((alg) == ALG_TSIT5 ? TSIT5_B : DP5_B)
+#define FIVE_E(alg) ((alg) == ALG_TSIT5 ? TSIT5_E : DP5_E)
 
 #define ST_OK 0
 #define ST_DOMAIN 1   /* DomainError / NaN: the reference throws (src/ClassicalDicke.jl:12-15 sqrt of a negative) */
@@ -238,11 +243,11 @@ static double orc_error_norm(int alg, int nv, int S, double tol, double h, const
 {
     double sc[4];
     for (int i = 0; i < nv; ++i) sc[i] = tol + fmax(fabs(u[i]), fabs(yn[i])) * tol;
-    if (alg == ALG_DP5) {
+    if (IS_FIVE(alg)) {
         double e[4];
         for (int i = 0; i < nv; ++i) {
             double s = 0;
-            for (int j = 0; j <= S; ++j) s += DP5_E[j] * K[j][i];
+            for (int j = 0; j <= S; ++j) s += FIVE_E(alg)[j] * K[j][i];
             e[i] = s * h / sc[i];
         }
         return rms(e, nv);
@@ -328,8 +333,8 @@ int orc_solve_one(const orc_problem *pb, const double *u0, const double *ts, int
             cb(user, k, u);
         }
     } else {
-        int S = (pb->alg == ALG_DP5) ? 6 : 12;
-        int err_order = (pb->alg == ALG_DP5) ? 4 : 7;
+        int S = (IS_FIVE(pb->alg)) ? 6 : 12;
+        int err_order = (IS_FIVE(pb->alg)) ? 4 : 7;
         double expo = -1.0 / (err_order + 1);
         double tol = pb->tol, dtmin = pb->dtmin;
         double K[13][4], yn[4];
@@ -384,8 +389,8 @@ int orc_solve_one(const orc_problem *pb, const double *u0, const double *ts, int
                     last = 1;
                 }
                 int bad;
-                if (pb->alg == ALG_DP5)
-                    bad = rk_trial(kind, par, sg, 6, &DP5_A[0][0], 6, DP5_B, h, u, K, yn);
+                if (IS_FIVE(pb->alg))
+                    bad = rk_trial(kind, par, sg, 6, FIVE_A(pb->alg), 6, FIVE_B(pb->alg), h, u, K, yn);
                 else
                     bad = rk_trial(kind, par, sg, 12, &DOP853_A[0][0], 12, DOP853_B, h, u, K, yn);
                 double err = orc_error_norm(pb->alg, nv, S, tol, h, u, yn, K);
@@ -489,19 +494,19 @@ int orc_solve_one(const orc_problem *pb, const double *u0, const double *ts, int
                     h = tstop - t;
                 }
                 int bad;
-                if (pb->alg == ALG_DP5)
-                    bad = rk_trial(kind, par, sg, 6, &DP5_A[0][0], 6, DP5_B, h, u, K, yn);
+                if (IS_FIVE(pb->alg))
+                    bad = rk_trial(kind, par, sg, 6, FIVE_A(pb->alg), 6, FIVE_B(pb->alg), h, u, K, yn);
                 else
                     bad = rk_trial(kind, par, sg, 12, &DOP853_A[0][0], 12, DOP853_B, h, u, K, yn);
                 double err;
                 {
                     double sc[4];
                     for (int i = 0; i < nv; ++i) sc[i] = tol + fmax(fabs(u[i]), fabs(yn[i])) * tol;
-                    if (pb->alg == ALG_DP5) {
+                    if (IS_FIVE(pb->alg)) {
                         double e[4];
                         for (int i = 0; i < nv; ++i) {
                             double s = 0;
-                            for (int j = 0; j <= S; ++j) s += DP5_E[j] * K[j][i];
+                            for (int j = 0; j <= S; ++j) s += FIVE_E(pb->alg)[j] * K[j][i];
                             e[i] = s * h / sc[i];
                         }
                         err = rms(e, nv);
@@ -1183,8 +1188,8 @@ static int var_solve_one(const orc_problem *pb, double *y, const double *ts, int
             if (out) memcpy(out + (size_t)k * N, y, sizeof(double) * N);
         }
     } else {
-        int S = (pb->alg == ALG_DP5) ? 6 : 12;
-        int err_order = (pb->alg == ALG_DP5) ? 4 : 7;
+        int S = (IS_FIVE(pb->alg)) ? 6 : 12;
+        int err_order = (IS_FIVE(pb->alg)) ? 4 : 7;
         double expo = -1.0 / (err_order + 1);
         double tol = pb->tol, dtmin = pb->dtmin;
         double K[13][VAR_MAXN], yn[VAR_MAXN];
@@ -1218,17 +1223,17 @@ static int var_solve_one(const orc_problem *pb, double *y, const double *ts, int
                     h = tstop - t;
                 }
                 int bad;
-                if (pb->alg == ALG_DP5)
-                    bad = var_rk_trial(kind, par, sg, N, 6, &DP5_A[0][0], 6, DP5_B, h, y, K, yn);
+                if (IS_FIVE(pb->alg))
+                    bad = var_rk_trial(kind, par, sg, N, 6, FIVE_A(pb->alg), 6, FIVE_B(pb->alg), h, y, K, yn);
                 else
                     bad = var_rk_trial(kind, par, sg, N, 12, &DOP853_A[0][0], 12, DOP853_B, h, y, K, yn);
                 double err, sc[VAR_MAXN];
                 for (int i = 0; i < N; ++i) sc[i] = tol + fmax(fabs(y[i]), fabs(yn[i])) * tol;
-                if (pb->alg == ALG_DP5) {
+                if (IS_FIVE(pb->alg)) {
                     double e[VAR_MAXN];
                     for (int i = 0; i < N; ++i) {
                         double s = 0;
-                        for (int j = 0; j <= S; ++j) s += DP5_E[j] * K[j][i];
+                        for (int j = 0; j <= S; ++j) s += FIVE_E(pb->alg)[j] * K[j][i];
                         e[i] = s * h / sc[i];
                     }
                     err = rms(e, N);
@@ -1566,7 +1571,7 @@ int orc_integrate_events(const orc_problem *pb, const double *u0, long n, double
                 }
             } else {
                 /* the adaptive loop of orc_solve_one with a per-accepted-step hook */
-                int S = (pb->alg == ALG_DP5) ? 6 : 12, err_order = (pb->alg == ALG_DP5) ? 4 : 7;
+                int S = (IS_FIVE(pb->alg)) ? 6 : 12, err_order = (IS_FIVE(pb->alg)) ? 4 : 7;
                 double expo = -1.0 / (err_order + 1), tol = pb->tol, dtmin = pb->dtmin;
                 double K[13][4], yn[4], t = 0, h_abs;
                 int rejected = 0;
@@ -1591,15 +1596,15 @@ int orc_integrate_events(const orc_problem *pb, const double *u0, long n, double
                             clipped = (t_end - t) < h_abs;
                             h = t_end - t;
                         }
-                        int bad = (pb->alg == ALG_DP5) ? rk_trial(kind, par, sg, 6, &DP5_A[0][0], 6, DP5_B, h, u, K, yn)
+                        int bad = (IS_FIVE(pb->alg)) ? rk_trial(kind, par, sg, 6, FIVE_A(pb->alg), 6, FIVE_B(pb->alg), h, u, K, yn)
                                                        : rk_trial(kind, par, sg, 12, &DOP853_A[0][0], 12, DOP853_B, h, u, K, yn);
                         double err, sc[4];
                         for (int i = 0; i < nv; ++i) sc[i] = tol + fmax(fabs(u[i]), fabs(yn[i])) * tol;
-                        if (pb->alg == ALG_DP5) {
+                        if (IS_FIVE(pb->alg)) {
                             double e[4];
                             for (int i = 0; i < nv; ++i) {
                                 double s = 0;
-                                for (int j = 0; j <= S; ++j) s += DP5_E[j] * K[j][i];
+                                for (int j = 0; j <= S; ++j) s += FIVE_E(pb->alg)[j] * K[j][i];
                                 e[i] = s * h / sc[i];
                             }
                             err = rms(e, nv);

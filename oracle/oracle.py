@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 BUILD = os.path.join(HERE, "_build")
 
 SYS_DICKE, SYS_LMG = 0, 1
-ALG_RK4, ALG_RK8, ALG_DP5, ALG_DOP853 = 0, 1, 2, 3
+ALG_RK4, ALG_RK8, ALG_DP5, ALG_DOP853, ALG_TSIT5 = 0, 1, 2, 3, 4
 ST_OK, ST_DOMAIN, ST_MAXITERS, ST_BAD_IC = 0, 1, 2, 3
 SAMPLER_HOST, SAMPLER_HW, SAMPLER_SU2, SAMPLER_HWXSU2 = 0, 1, 2, 3
 
@@ -137,7 +137,7 @@ def _controller_fields(p, alg, controller):
         return
     p.controller = CTRL_ODE
     if controller is None or controller == "ode":
-        controller = "dp5" if alg == ALG_DP5 else "dp8"
+        controller = "dp5" if alg == ALG_DP5 else "tsit5" if alg == ALG_TSIT5 else "dp8"
     if isinstance(controller, str):
         controller = ODE_GAINS[controller.lower()]
     p.beta1, p.beta2, p.qmin, p.qmax = (float(x) for x in controller[:4])

@@ -66,7 +66,7 @@ def test_fixed_step_trajectories_match_oracle(ctx, pkg, O, gold, kind, par, name
 
 
 @pytest.mark.parametrize("kind,par,name", [(0, DPAR, "dicke"), (1, LPAR, "lmg")])
-@pytest.mark.parametrize("alg,tol", [("DOP853", 1e-12), ("DP5", 1e-10), ("DOP853", 1e-8)])
+@pytest.mark.parametrize("alg,tol", [("DOP853", 1e-12), ("DP5", 1e-10), ("DOP853", 1e-8), ("TSIT5", 1e-10), ("TSIT5", 1e-12)])
 def test_adaptive_trajectories_match_oracle_and_truth(ctx, pkg, O, gold, kind, par, name, alg, tol):
     g = gold["truth_ld"][name]
     ts = np.array(g["ts"])
@@ -89,7 +89,7 @@ def test_hermite_output_mode_matches_the_oracle(ctx, pkg, O, gold):
     g = gold["truth_ld"]["dicke"]
     u0 = np.array(g["u0"])[:96]
     ts = np.arange(0, 161) * 0.05
-    for alg, oalg in ((pkg._lib.ALG_DOP853, O.ALG_DOP853), (pkg._lib.ALG_DP5, O.ALG_DP5)):
+    for alg, oalg in ((pkg._lib.ALG_DOP853, O.ALG_DOP853), (pkg._lib.ALG_DP5, O.ALG_DP5), (pkg._lib.ALG_TSIT5, O.ALG_TSIT5)):
         sol = csol(pkg, alg, tol=1e-10)
         sol.output = pkg._lib.OUTPUT_HERMITE
         out, st, ns = ctx.integrate(csys(pkg, 0, g["par"]), sol, u0, ts)

@@ -324,6 +324,12 @@ def test_solver_keyword_mapping(pkg):
     s = CS.solver_from_kargs({"integrator_alg": CS.DP5(), "tol": 1e-8, "integate_backwards": True, "maxiters": 500})
     assert (s.alg, s.tol, s.backwards, s.maxiters) == (lib.ALG_DP5, 1e-8, 1, 500)
     assert CS.solver_from_kargs({"integrator_alg": "RK4", "dt": 0.01}).alg == lib.ALG_RK4
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")     # Tsit5 is the real tableau: no substitution warning
+        s = CS.solver_from_kargs({"integrator_alg": CS.Tsit5(), "tol": 1e-9})
+    assert s.alg == lib.ALG_TSIT5 and CS.last_solver["algorithm"] == "Tsit5" and not CS.last_solver["substituted"]
+    assert CS.last_solver["gains"]["beta1"] == pytest.approx(0.14) and CS.last_solver["gains"]["beta2"] == pytest.approx(0.08)   # generic order-5 gains
     assert CS.solver_from_kargs({"integrator_alg": CS.DP8(), "adaptive": False, "dt": 0.1}).alg == lib.ALG_RK8
     with pytest.raises(ValueError, match="dt > 0"):
         CS.solver_from_kargs({"integrator_alg": "RK4"})
@@ -400,7 +406,7 @@ def test_specialised_kernels_keep_their_register_budgets(pkg, tmp_path, monkeypa
     s = lib.System()
     s.kind = lib.SYS_DICKE
     s.params[0], s.params[1], s.params[2] = 1.0, 1.0, 1.0
-    for alg, max_regs in ((lib.ALG_RK4, 64), (lib.ALG_DP5, 128), (lib.ALG_DOP853, 168)):
+    for alg, max_regs in ((lib.ALG_RK4, 64), (lib.ALG_DP5, 128), (lib.ALG_TSIT5, 128), (lib.ALG_DOP853, 168)):
         sol = lib.Solver()
         sol.alg, sol.dt, sol.tol = alg, 2.0 ** -7, 1e-8
         lib.jit_compile(s, sol, [str(TWA.Weyl.Jz(100) / 100)])

@@ -7,9 +7,15 @@ Source of the numbers: SciPy (BSD) `scipy/integrate/_ivp/rk.py` (RK45 = Dormand-
 (/root/reference/src/ClassicalSystems.jl:84) has no coefficient source in this image, so it is not
 generated (SURVEY.md §7 hard part 8).
 
+Tsitouras' 5(4) pair (OrdinaryDiffEq's `Tsit5()`; Ch. Tsitouras, Comput. Math. Appl. 62 (2011) 770) is not in SciPy: its
+coefficients are written out below as published (16 significant digits) and CHECKED before anything is generated -- the row sums
+against the nodes, all 17 order conditions up to order 5 for the weights and the 8 conditions up to order 4 for the embedded
+weights must hold to 1e-14, otherwise the script stops.
+
 Outputs
   oracle/tableaux_gen.h                      dense C arrays for the CPU restatement
   dickemodel.jl_b200/csrc/dp5_body.inc       straight-line fma code for the sm_100a kernels
+  dickemodel.jl_b200/csrc/tsit5_body.inc
   dickemodel.jl_b200/csrc/dop853_body.inc
 
 The .inc bodies expect in scope:  `double y[NV]`, `double k0[NV]` (= f(y)), `double h`, a callable
@@ -52,6 +58,35 @@ class ConstTable:
         return "\n".join(lines)
 
 
+def tsit5_tableau():
+    """A (6 x 6, strictly lower), B (6) = the seventh row (FSAL), C (6), E (7) = btilde: dt * (E . k) is the error estimate."""
+    c = np.array([0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0])
+    A = np.zeros((7, 7))
+    A[1, 0] = 0.161
+    A[2, :2] = [-0.008480655492356989, 0.335480655492357]
+    A[3, :3] = [2.8971530571054935, -6.359448489975075, 4.3622954328695815]
+    A[4, :4] = [5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525]
+    A[5, :5] = [5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383]
+    A[6, :6] = [0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774]
+    bt = np.array([-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629, 0.5823571654525552,
+                   -0.45808210592918697, 0.015151515151515152])
+    b = A[6].copy()
+
+    def conditions(w, order):
+        Ac = A @ c
+        r = [w.sum() - 1, w @ c - 1 / 2, w @ c ** 2 - 1 / 3, w @ Ac - 1 / 6, w @ c ** 3 - 1 / 4, w @ (c * Ac) - 1 / 8, w @ (A @ c ** 2) - 1 / 12,
+             w @ (A @ Ac) - 1 / 24]
+        if order >= 5:
+            r += [w @ c ** 4 - 1 / 5, w @ (c ** 2 * Ac) - 1 / 10, w @ (c * (A @ c ** 2)) - 1 / 15, w @ (c * (A @ Ac)) - 1 / 30, w @ (Ac * Ac) - 1 / 20,
+                  w @ (A @ c ** 3) - 1 / 20, w @ (A @ (c * Ac)) - 1 / 40, w @ (A @ (A @ c ** 2)) - 1 / 60, w @ (A @ (A @ Ac)) - 1 / 120]
+        return np.abs(np.array(r)).max()
+
+    assert np.abs(A.sum(1) - c).max() < 1e-14, "Tsit5: row sums"
+    assert conditions(b, 5) < 1e-14, "Tsit5: order-5 conditions of the weights"
+    assert conditions(b - bt, 4) < 1e-14, "Tsit5: order-4 conditions of the embedded weights"
+    return A[:6, :6].copy(), b[:6].copy(), c[:6].copy(), bt
+
+
 def c_array(name, arr):
     arr = np.asarray(arr, dtype=float)
     if arr.ndim == 1:
@@ -70,6 +105,11 @@ def oracle_header():
     out.append(c_array("DP5_B", rk.RK45.B))
     out.append(c_array("DP5_C", rk.RK45.C))
     out.append(c_array("DP5_E", rk.RK45.E))
+    At, Bt, Ct, Et = tsit5_tableau()
+    out.append(c_array("TSIT5_A", At))
+    out.append(c_array("TSIT5_B", Bt))
+    out.append(c_array("TSIT5_C", Ct))
+    out.append(c_array("TSIT5_E", Et))
     out.append(c_array("DOP853_A", d8.A[:12, :12]))
     out.append(c_array("DOP853_B", d8.B))
     out.append(c_array("DOP853_C", d8.C[:12]))
@@ -150,9 +190,12 @@ def main():
     A5 = np.zeros((6, 6)); A5[:, :5] = rk.RK45.A
     with open(os.path.join(csrc, "dp5_body.inc"), "w") as f:
         f.write(body("DP5", A5, rk.RK45.B, [("e5", rk.RK45.E)], 6))
+    At, Bt, _, Et = tsit5_tableau()
+    with open(os.path.join(csrc, "tsit5_body.inc"), "w") as f:
+        f.write(body("TSIT5", At, Bt, [("e5", Et)], 6))
     with open(os.path.join(csrc, "dop853_body.inc"), "w") as f:
         f.write(body("DOP853", d8.A[:12, :12], d8.B, [("e5", d8.E5), ("e3", d8.E3)], 12))
-    print("wrote oracle/tableaux_gen.h, csrc/dp5_body.inc, csrc/dop853_body.inc")
+    print("wrote oracle/tableaux_gen.h, csrc/dp5_body.inc, csrc/tsit5_body.inc, csrc/dop853_body.inc")
 
 
 if __name__ == "__main__":
