@@ -313,8 +313,12 @@ def main():
     sampler = clocks_sampler_start(clk_path, local, pci) if rank == 0 else None
     e0.record(stream)
     steps_done, kernel_ms, launches, last = 0, 0.0, 0, None
+    step_wall_ms, step_lib_ms = [], []
     for _ in range(args.steps):
+        t_step = time.perf_counter()
         last, info = step_device()
+        step_wall_ms.append(round(1e3 * (time.perf_counter() - t_step), 2))   # (host clock, this rank: diagnostic only)
+        step_lib_ms.append(round(info.get("total_ms", 0.0), 2))
         steps_done += info["steps_accepted"]       # all-reduced: whole job
         kernel_ms += info["kernel_ms"]
         launches += info["launches"]
@@ -685,6 +689,9 @@ def main():
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches,
+            "step_timing": {"host_wall_ms": step_wall_ms, "library_total_ms": step_lib_ms,
+                            "note": "rank 0, per timed step of the device-resident leg: host clock around the public call (L2 flush + TWA.average) and the "
+                                    "library's own first-memset-to-last-copy time; ms_per_step is the CUDA-event time of the whole loop / steps"},
             "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved_tflops / peak_tflops, "frac_nominal": achieved_tflops / nominal_tflops, "peak_nominal": nominal_tflops,
                          "k0_ms": k0_ms, "k0_flops": peak_tflops * 1e12 * k0_ms * 1e-3,
