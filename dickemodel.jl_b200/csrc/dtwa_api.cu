@@ -75,6 +75,8 @@ struct DevCtx {
     int sm_count = 0, clock_khz = 0, cc = 0;
     char name[256] = {0};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;                 // uploads overlapped with the ensemble kernel (host-supplied initial conditions)
+    cudaEvent_t ev_copy_go = nullptr, ev_copy_done = nullptr;
     DevBuf partial, meta, u0, fail[2], scratch_a, scratch_b, scratch_c, ring;
     DevBuf arena_f64, arena_u64;   // result arenas of the ensemble in flight (grow-only: no cudaMalloc/cudaFree per call)
     // packed events left on the device by dtwa_integrate_events_packed (inside `ring`)
@@ -217,6 +219,10 @@ extern "C" int dtwa_create(dtwa_ctx **out, const int *device_ids, int ndev, void
             return set_err(DTWA_ERR_CUDA, "cudaStreamCreate failed");
         }
         for (auto &ev : d.ev) cudaEventCreate(&ev);
+        // (non-blocking: the caller's stream may be the legacy default stream, which a blocking stream would serialise with)
+        if (cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking) != cudaSuccess) d.copy_stream = nullptr;
+        cudaEventCreateWithFlags(&d.ev_copy_go, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&d.ev_copy_done, cudaEventDisableTiming);
     }
     if (ndev > 1) {
         int rc = load_nccl(ctx);
@@ -246,6 +252,12 @@ extern "C" int dtwa_destroy(dtwa_ctx *ctx)
     for (auto &d : ctx->devs) {
         cudaSetDevice(d.device);
         cudaStreamSynchronize(d.stream);
+        if (d.copy_stream) {
+            cudaStreamSynchronize(d.copy_stream);
+            cudaStreamDestroy(d.copy_stream);
+        }
+        if (d.ev_copy_go) cudaEventDestroy(d.ev_copy_go);
+        if (d.ev_copy_done) cudaEventDestroy(d.ev_copy_done);
         for (DevBuf *b : {&d.partial, &d.meta, &d.u0, &d.fail[0], &d.fail[1], &d.scratch_a, &d.scratch_b, &d.scratch_c, &d.ring, &d.arena_f64, &d.arena_u64})
             b->release();
         for (auto &ev : d.ev)
@@ -1368,6 +1380,7 @@ extern "C" int dtwa_plan_free(dtwa_plan *plan)
         if (!dp.dc) continue;
         cudaSetDevice(dp.dc->device);
         cudaStreamSynchronize(dp.dc->stream);
+        if (dp.dc->copy_stream) cudaStreamSynchronize(dp.dc->copy_stream);
     }
     if (plan->ctx) plan->ctx->plan_live = false;   // (the arenas stay in the context's grow-only buffers)
     delete plan;
@@ -1622,9 +1635,11 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
             A.S = make_solver_args(sys, sol, (const StepTab *)(m + o_t), (const double *)(m + o_s), ts, nt, tab);
             A.smp = sp0;
             A.smp.offset = smp->offset + (uint64_t)dp.lo;
+            const bool overlap_upload = smp->kind == DTWA_SAMPLER_HOST_ARRAY && fixed && d.copy_stream != nullptr && std::getenv("DTWA_NO_COPY_OVERLAP") == nullptr;
             if (smp->kind == DTWA_SAMPLER_HOST_ARRAY) {
                 TRY(d.u0.ensure(sizeof(double) * dp.n * nv));
-                CK(cudaMemcpyAsync(d.u0.p, smp->u0 + dp.lo * nv, sizeof(double) * dp.n * nv, cudaMemcpyHostToDevice, d.stream));
+                if (!overlap_upload)
+                    CK(cudaMemcpyAsync(d.u0.p, smp->u0 + dp.lo * nv, sizeof(double) * dp.n * nv, cudaMemcpyHostToDevice, d.stream));
                 A.smp.u0 = (const double *)d.u0.p;
             } else if (smp->kind == DTWA_SAMPLER_DEVICE_ARRAY) {
                 A.smp.u0 = smp->u0;
@@ -1661,6 +1676,37 @@ extern "C" int dtwa_ensemble_launch(dtwa_ctx *ctx, const dtwa_system *sys, const
             TRY(d.partial.ensure(pbytes));
             CK(cudaMemsetAsync(d.partial.p, 0, pbytes, d.stream));
             A.partial = (double *)d.partial.p;
+            // Host-supplied initial conditions, fixed-step kernels: the upload is overlapped with the integration.  The kernel deals
+            // trajectory j to CTA (j / block) % grid, so the first grid * block trajectories are exactly the first batch of every
+            // CTA: they are uploaded and launched on their own (LAUNCH A) while a second stream uploads the rest; LAUNCH B takes the
+            // remaining batches once that copy has landed.  Every trajectory meets the same thread, in the same order, accumulating
+            // into the same per-CTA rows as in one launch: bit-identical results; the cost is one more launch and one CTA-level
+            // synchronisation after batches of equal length.  (The adaptive kernels are not split: their lanes finish a pass at
+            // different times.)
+            const long long first_pass = (long long)shapes[di].grid * shapes[di].block;
+            if (overlap_upload && dp.n >= 8 * first_pass) {
+                const double *h0 = smp->u0 + dp.lo * nv;
+                CK(cudaMemcpyAsync(d.u0.p, h0, sizeof(double) * first_pass * nv, cudaMemcpyHostToDevice, d.stream));
+                CK(cudaEventRecord(d.ev_copy_go, d.stream));   // (orders the second stream behind every earlier user of d.u0)
+                CK(cudaEventRecord(d.ev[1], d.stream));
+                EnsArgs A1 = A;
+                A1.N = first_pass;
+                TRY(launch_ens(d, kern, A1, shapes[di]));
+                plan->launches++;
+                CK(cudaStreamWaitEvent(d.copy_stream, d.ev_copy_go, 0));
+                CK(cudaMemcpyAsync((double *)d.u0.p + first_pass * nv, h0 + first_pass * nv, sizeof(double) * (dp.n - first_pass) * nv, cudaMemcpyHostToDevice,
+                                   d.copy_stream));
+                CK(cudaEventRecord(d.ev_copy_done, d.copy_stream));
+                CK(cudaStreamWaitEvent(d.stream, d.ev_copy_done, 0));
+                EnsArgs A2 = A;
+                A2.N = dp.n - first_pass;
+                A2.smp.u0 = A.smp.u0 + first_pass * nv;
+                A2.smp.offset = A.smp.offset + (uint64_t)first_pass;
+                TRY(launch_ens(d, kern, A2, shapes[di]));
+                plan->launches++;
+                return 0;
+            }
+            if (overlap_upload) CK(cudaMemcpyAsync(d.u0.p, smp->u0 + dp.lo * nv, sizeof(double) * dp.n * nv, cudaMemcpyHostToDevice, d.stream));
             CK(cudaEventRecord(d.ev[1], d.stream));
             TRY(launch_ens(d, kern, A, shapes[di]));
             plan->launches++;

@@ -37,6 +37,35 @@ def test_average_matches_oracle_on_host_supplied_ics(ctx, mods, O):
     assert one.shape == (len(ts),) and np.array_equal(one, got[:, 0])
 
 
+def test_overlapped_upload_of_host_initial_conditions_is_bit_identical(ctx, mods, monkeypatch):
+    """Large host-supplied ensembles under a fixed-step integrator are uploaded while the first batch of every CTA is already
+    being integrated (two launches, dtwa_ensemble_launch); every trajectory still meets the same thread in the same order, so
+    sums, counts and counters equal those of the single-launch path bit for bit -- also when N is not a multiple of anything"""
+    TWA, CD, _, _ = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=0.9, g=1.1)
+    j, N = 80, 8 * 148 * 4 * 256 + 12345      # >= 8 first passes (148 SMs x 4 CTAs x 256 threads)
+    W = TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=j, seed=77)
+    u0 = W.sample_many(N)
+    ts = TWA.jrange(0, 0.05, 0.5)
+
+    def run():
+        avg = TWA.average(system, observable=[TWA.Weyl.Jz(j) / j, "q*p"], N=N, ts=ts, distribution=TWA.samples_from_array(u0, j=j), integrator_alg="RK4", dt=0.01)
+        ia = dict(TWA.last_info)
+        D = TWA.samples_from_array(u0, j=j)
+        h = TWA.monte_carlo_integrate(system, TWA.mcs_chain(TWA.mcs_for_distributions(system, N=N, distribution=D, ts=ts, x="t", y="q", ys=TWA.jrange(-3, 0.1, 3)),
+                                                            TWA.mcs_for_distributions(system, N=N, distribution=D, ts=ts, x="Q", xs=TWA.jrange(-2, 0.1, 2), y="P", ys=TWA.jrange(-2, 0.1, 2))),
+                                      integrator_alg="RK4", dt=0.01)
+        return avg, ia, h
+
+    a1, i1, h1 = run()
+    monkeypatch.setenv("DTWA_NO_COPY_OVERLAP", "1")
+    a0, i0, h0 = run()
+    assert i1["launches"] == i0["launches"] + 1            # the split launch really ran
+    assert np.array_equal(a1, a0)
+    assert all(np.array_equal(x, y) for x, y in zip(h1, h0))
+    assert i1["steps_accepted"] == i0["steps_accepted"] and i1["n_failed"] == i0["n_failed"] and np.array_equal(i1["n_valid"], i0["n_valid"])
+
+
 def test_runs_are_bitwise_reproducible(ctx, mods):
     TWA, CD, _, _ = mods
     system = CD.ClassicalDickeSystem(w0=1, w=1, g=1)

@@ -70,16 +70,24 @@ def run(label, dist, do_flush, sampler, steps=6, freeze=False):
 for _ in range(3):
     TWA.average(system, observable=jz, N=N, ts=ts, distribution=W, integrator_alg="RK4", dt=W0["dt"])
 run("philox, flush, no sampler", W, True, False)
-run("philox, flush, NVML sampler thread", W, True, True)
-run("philox, no flush, no sampler", W, False, False)
 run("philox, flush, no sampler (again)", W, True, False)
-run("philox, flush, no sampler, gc frozen", W, True, False, freeze=True)
-run("philox, flush, sampler, gc frozen", W, True, True, freeze=True)
 host = torch.empty((N, 4), dtype=torch.float64).pin_memory()
 hn = host.numpy()
 Wh = TWA.coherent_Wigner_HWxSU2(W0["center"], j=j, seed=W0["seed"])
 for s0 in range(0, N, 1 << 21):
     hn[s0:min(N, s0 + (1 << 21))] = Wh.sample_many(min(N, s0 + (1 << 21)) - s0)
 D = TWA.samples_from_array(hn, j=j)
+dev = torch.empty((N, 4), dtype=torch.float64, device="cuda")
+for _ in range(3):
+    torch.cuda.synchronize()
+    e0.record(stream)
+    dev.copy_(host, non_blocking=True)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    print(f"pinned H2D of {host.numel() * 8 / 1e6:.0f} MB alone: {e0.elapsed_time(e1):.2f} ms = {host.numel() * 8 / 1e6 / e0.elapsed_time(e1):.1f} GB/s", flush=True)
+del dev
 run("host array (pinned), flush, no sampler", D, True, False)
-run("host array (pinned), flush, NVML sampler", D, True, True)
+os.environ["DTWA_NO_COPY_OVERLAP"] = "1"
+run("host array (pinned), flush, NO upload overlap", D, True, False)
+del os.environ["DTWA_NO_COPY_OVERLAP"]
+run("host array (pinned), flush, overlap again", D, True, False)
