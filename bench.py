@@ -24,6 +24,7 @@ Weyl.Jz(j)/j averaged at every output time.  One bench "step" = one whole ensemb
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -311,6 +312,11 @@ def main():
     except Exception:
         pci = None
     sampler = clocks_sampler_start(clk_path, local, pci) if rank == 0 else None
+    # Python's cyclic collector is switched off inside the timed loops, as `timeit` does (a collection between two calls of a
+    # synchronous API leaves the GPU idle).  It does not remove the sporadic late calls of a busy host (profiles/r2_step_gap_call32.log:
+    # single steps 10-60 ms longer with an unchanged library time, with and without the collector): those stay in the number.
+    gc.collect()
+    gc.disable()
     e0.record(stream)
     steps_done, kernel_ms, launches, last = 0, 0.0, 0, None
     step_wall_ms, step_lib_ms = [], []
@@ -323,6 +329,7 @@ def main():
         kernel_ms += info["kernel_ms"]
         launches += info["launches"]
     e1.record(stream)
+    gc.enable()
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
     if sampler:
@@ -359,6 +366,8 @@ def main():
         for _ in range(max(1, min(args.warmup, 3))):
             step_e2e()
         barrier()
+        gc.collect()
+        gc.disable()
         e0.record(stream)
         st, e2e_out = 0, None
         n_e2e = max(1, args.steps)
@@ -366,6 +375,7 @@ def main():
             e2e_out, info = step_e2e()
             st += info["steps_accepted"]
         e1.record(stream)
+        gc.enable()
         barrier()
         e2e_ms = allmax([e0.elapsed_time(e1)])[0]
         e2e = {"value": st / (e2e_ms * 1e-3), "unit": "trajectory-steps/s",
@@ -683,6 +693,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.n_traj), "trajectories_total": N_total, "steps_per_trajectory": 14000,
                        "cache": "no input tensors (Philox sampling is fused into the kernel); a 256 MiB buffer is written before every step to flush the 126 MB L2",
+                       "python_gc": "disabled inside the two timed loops (as timeit does), collected right before them",
                        "block_threads": args.block or 256, "integrator": "RK4", "sampler": "coherent_Wigner_HWxSU2, Philox4x32-10",
                        "reference_arm_note": "the CPU arms (cpu_baseline, --impl reference) integrate a bounded SAMPLE of this ensemble per step "
                                              "(same workload, fewer trajectories): the metric is a rate"},

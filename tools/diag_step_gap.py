@@ -32,11 +32,14 @@ e0, e1, ef = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timin
 import gc
 
 
-def run(label, dist, do_flush, sampler, steps=6, freeze=False):
+def run(label, dist, do_flush, sampler, steps=6, freeze=False, nogc=False):
     s = None
     if freeze:
         gc.collect()
         gc.freeze()
+    if nogc:
+        gc.collect()
+        gc.disable()
     if sampler:
         pr = torch.cuda.get_device_properties(0)
         s = bench.clocks_sampler_start("/tmp/diag_clocks.csv", 0, f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
@@ -63,6 +66,8 @@ def run(label, dist, do_flush, sampler, steps=6, freeze=False):
     r = np.array(rows)
     if freeze:
         gc.unfreeze()
+    if nogc:
+        gc.enable()
     print(f"{label:46s} wall/step {wall:8.2f} | per step (host wall, events, library total, kernel, flush on the GPU, flush call on the host) ms: "
           + "; ".join(f"{a:.1f} {b:.1f} {c:.1f} {d:.1f} {e:.2f} {f:.2f}" for a, b, c, d, e, f in r), flush=True)
 
@@ -70,7 +75,10 @@ def run(label, dist, do_flush, sampler, steps=6, freeze=False):
 for _ in range(3):
     TWA.average(system, observable=jz, N=N, ts=ts, distribution=W, integrator_alg="RK4", dt=W0["dt"])
 run("philox, flush, no sampler", W, True, False)
-run("philox, flush, no sampler (again)", W, True, False)
+run("philox, flush, no sampler (again), 16 steps", W, True, False, steps=16)
+run("philox, flush, no sampler, gc disabled, 16 steps", W, True, False, steps=16, nogc=True)
+if len(sys.argv) > 2:
+    sys.exit(0)
 host = torch.empty((N, 4), dtype=torch.float64).pin_memory()
 hn = host.numpy()
 Wh = TWA.coherent_Wigner_HWxSU2(W0["center"], j=j, seed=W0["seed"])
