@@ -330,6 +330,38 @@ def test_multi_device_context_matches_single_device(pkg, mods, O, solver):
     assert i1["steps_accepted"] == i2["steps_accepted"] and np.array_equal(i1["n_valid"], i2["n_valid"])
 
 
+def test_multi_device_context_with_large_host_supplied_arrays(pkg, mods):
+    """dtwa_create(ndev=2) + host-supplied initial conditions large enough that every device overlaps its upload with its first
+    batch (two launches per device, each on its own copy stream): counts bit-identical to one device, sums to rounding"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    TWA, CD, _, _ = mods
+    system = CD.ClassicalDickeSystem(w0=1, w=0.9, g=1.1)
+    j, N = 80, 2 * (8 * 148 * 4 * 256) + 4321
+    u0 = TWA.coherent_Wigner_HWxSU2(DOCS_PT, j=j, seed=78).sample_many(N)
+    ts = TWA.jrange(0, 0.05, 0.5)
+
+    def run():
+        D = TWA.samples_from_array(u0, j=j)
+        chain = TWA.mcs_chain(TWA.mcs_for_averaging(system, observable=["q*p", TWA.Weyl.Jz(j) / j], N=N, ts=ts, distribution=D),
+                              TWA.mcs_for_distributions(system, x="t", y="q", ys=TWA.jrange(-3, 0.1, 3), N=N, ts=ts, distribution=D))
+        out = TWA.monte_carlo_integrate(system, chain, integrator_alg="RK4", dt=0.01)
+        return out, dict(TWA.last_info)
+
+    one, i1 = run()
+    old = pkg.default_context()
+    try:
+        pkg.set_default_context(pkg.Context([0, 1]))
+        two, i2 = run()
+    finally:
+        pkg.set_default_context(old)
+    assert i1["launches"] >= 3 and i2["launches"] >= 2 * 3 - 1     # split launches (+ the merge kernels) on one and on both devices
+    assert np.array_equal(one[1], two[1])
+    assert np.abs(one[0] - two[0]).max() < 1e-12
+    assert i1["steps_accepted"] == i2["steps_accepted"] and np.array_equal(i1["n_valid"], i2["n_valid"])
+
+
 def test_user_defined_phase_space_distribution(ctx, mods, O):
     """src/TWA.jl:22-26: a distribution given by user closures.  sample() feeds host-drawn points to the kernel; the traced
     probability_density is the survival-probability observable (src/TWA.jl:656-665)"""
