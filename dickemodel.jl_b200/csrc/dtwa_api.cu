@@ -2024,7 +2024,7 @@ extern "C" int dtwa_fp64_mix(dtwa_ctx *ctx, int alu_per_8, int kind, int warps_p
 {
     if (!ctx) return set_err(DTWA_ERR_INVALID, "NULL context");
     if (warps_per_sm < 1 || warps_per_sm > 32) return set_err(DTWA_ERR_INVALID, "warps_per_sm must be in [1, 32]");
-    if (kind < 0 || kind > 2) return set_err(DTWA_ERR_INVALID, "kind must be 0, 1 or 2");
+    if (kind < 0 || kind > 4) return set_err(DTWA_ERR_INVALID, "kind must be 0 .. 4");
     DevCtx &d = ctx->devs[0];
     CK(cudaSetDevice(d.device));
     const int block = 32, grid = d.sm_count * warps_per_sm, iters = 16384;
@@ -2037,7 +2037,9 @@ extern "C" int dtwa_fp64_mix(dtwa_ctx *ctx, int alu_per_8, int kind, int warps_p
     case A:                                                                                                    \
         if (kind == 0) fp64_mix_kernel<A, 0><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7);          \
         else if (kind == 1) fp64_mix_kernel<A, 1><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7);     \
-        else fp64_mix_kernel<A, 2><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7);                    \
+        else if (kind == 2) fp64_mix_kernel<A, 2><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7);     \
+        else if (kind == 3) fp64_mix_kernel<A, 3><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7);     \
+        else fp64_mix_kernel<A, 4><<<grid, block, 0, d.stream>>>(o, iters, 0.999999, 1e-7);                    \
         break;
         switch (alu_per_8) {
             DTWA_MIX_CASE(0)

@@ -2267,7 +2267,8 @@ __global__ void __launch_bounds__(32) fp64_chains_kernel(double *out, const doub
 
 // K0d: 8 DFMA chains per thread (K0's form) with ALU other instructions woven in per group of 8 DFMAs -- does an
 // instruction of another pipe issue "for free" in the cycle the FP64 pipe cannot accept a second DFMA, or does it take an
-// issue slot away from the DFMAs?  KIND 0: integer adds (ALU pipe), 1: FP32 FMAs (FMA pipe), 2: MUFU.RSQ64H (XU pipe).
+// issue slot away from the DFMAs?  KIND 0: integer adds (ALU pipe), 1: FP32 FMAs (FMA pipe), 2: MUFU (XU pipe), 3: IMAD (integer
+// multiply-add: FMA pipe -- the pipe ptxas also sends half of its register moves to, as IMAD.MOV), 4: LOP3 (ALU pipe).
 template <int ALU, int KIND>
 __global__ void __launch_bounds__(32) fp64_mix_kernel(double *out, int iters, double a, double b)
 {
@@ -2296,8 +2297,12 @@ __global__ void __launch_bounds__(32) fp64_mix_kernel(double *out, int iters, do
                         asm volatile("add.u32 %0, %0, %1;" : "+r"(u[k]) : "r"(i));
                     else if constexpr (KIND == 1)
                         asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f[k]) : "f"(1.0000001f));
-                    else
+                    else if constexpr (KIND == 2)
                         asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(f[k]));
+                    else if constexpr (KIND == 3)   // IMAD: integer multiply-add, issued to the FMA pipe like FFMA
+                        asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(u[k]) : "r"(i | 3));
+                    else                            // LOP3 (ALU pipe)
+                        asm volatile("xor.b32 %0, %0, %1;" : "+r"(u[k]) : "r"(i));
                 }
             }
         }

@@ -13,7 +13,10 @@ pkg = graft.load_package()
 ctx = pkg.default_context()
 peak, _ = ctx.fp64_peak()
 rows = []
-for kind, name in ((0, "iadd"), (1, "ffma"), (2, "mufu")):
+kinds = ((0, "iadd"), (1, "ffma"), (2, "mufu"), (3, "imad"), (4, "lop3"))
+if len(sys.argv) > 1:
+    kinds = tuple(k for k in kinds if k[1] in sys.argv[1:])
+for kind, name in kinds:
     for warps in (4, 12, 32):
         for alu in (0, 2, 4, 8, 16):
             tf, ms = ctx.fp64_mix(alu, kind, warps)
